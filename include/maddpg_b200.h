@@ -1,0 +1,212 @@
+/*
+ * maddpg_b200.h -- C ABI of the B200-native MADDPG hot path (libmaddpg_b200.so).
+ *
+ * The reference (adolfogonzalez3/maddpg) is 100% Python and has no FFI; the hot path sits
+ * behind two duck-typed Python interfaces:
+ *   - maddpg.AgentTrainer / MADDPGAgentTrainer      maddpg/__init__.py:1-15, maddpg/trainer/maddpg.py:112-196
+ *   - multiagent.environment.MultiAgentEnv + Scenario   call sites experiments/train.py:49-60,104,114,128
+ * Each entry point below names the reference function(s) it replaces.  The Python host code in
+ * maddpg_b200/{env,replay,trainer}.py binds these with ctypes and mirrors the reference surface.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  All data pointers are DEVICE pointers unless the
+ *     parameter name starts with h_.  The caller owns every buffer (the library never frees caller
+ *     memory and keeps no pointer past the call, except the buffers bound with mdp_core_bind()).
+ *   - Every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising.  Return value: 0 = MDP_OK, negative = error class; the message is available
+ *     from mdp_last_error() (thread local).  Asynchronous launch failures surface at the next call.
+ *   - Handles are not thread-safe.  One host thread per GPU.
+ *
+ * Joint layouts (row-major float32 unless noted; E = number of env instances in the call)
+ *   obs   (E, obs_stride)   agent i's observation in columns [obs_off[i], obs_off[i]+obs_dim[i])
+ *   act   (E, act_stride)   agent i's soft one-hot action in columns [act_off[i], act_off[i]+act_dim[i])
+ *   rew   (E, n_agents)     done (E, n_agents) uint8
+ *   state SoA [state_comps][E] of float32 (state_f64 = 0) or float64 (state_f64 = 1):
+ *         comp 4*i+{0,1,2,3} = agent i pos.x, pos.y, vel.x, vel.y ; then comm_dim comm values of the
+ *         non-silent agent(s) ; then 2*l+{0,1} = landmark l pos.x, pos.y
+ *   replay ring (capacity, row_stride): one JOINT row per lockstep transition
+ *         [ obs_0..obs_{n-1} | act_0..act_{n-1} | pad ]   columns [0, x_dim)           = critic input
+ *         [ next_obs_0..next_obs_{n-1} | pad ]            columns [nx_off, nx_off+sum D)
+ *         [ rew_0..rew_{n-1} | done_0..done_{n-1} | pad ] columns [rw_off, ..), [dn_off, ..)
+ *         every sub-block starts on a 16-byte boundary; row_stride is a multiple of 4 floats.
+ */
+#ifndef MADDPG_B200_H_
+#define MADDPG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDP_MAX_AGENTS 32
+#define MDP_MAX_HEADS 2
+
+enum { MDP_OK = 0, MDP_EINVAL = -1, MDP_ECUDA = -2, MDP_ENOTSUP = -3 };
+
+/* scenario ids: multiagent/scenarios/<name>.py, loaded at experiments/train.py:53 */
+enum { MDP_SIMPLE = 0, MDP_SIMPLE_SPREAD = 1, MDP_SIMPLE_TAG = 2, MDP_SIMPLE_WORLD_COMM = 3 };
+
+typedef struct mdp_env_cfg {
+  int32_t scenario;   /* MDP_SIMPLE ... */
+  int32_t num_agents; /* simple_spread only: N agents = N landmarks (0 -> 3, max 32) */
+  int32_t state_f64;  /* 0: float32 state (throughput); 1: float64 state like MPE's numpy (parity) */
+} mdp_env_cfg;
+
+typedef struct mdp_env_dims {
+  int32_t n_agents, n_landmarks, comm_dim, collaborative;
+  int32_t obs_dim[MDP_MAX_AGENTS], act_dim[MDP_MAX_AGENTS];
+  int32_t obs_off[MDP_MAX_AGENTS], act_off[MDP_MAX_AGENTS];
+  int32_t n_heads[MDP_MAX_AGENTS], head_dim[MDP_MAX_AGENTS][MDP_MAX_HEADS];
+  int32_t obs_sum, act_sum, obs_stride, act_stride;
+  int32_t state_comps;     /* 4*n_agents + comm_dim + 2*n_landmarks */
+  int32_t state_elem_size; /* 4 or 8 */
+  int32_t env_bytes_per_step; /* algorithmic bytes of one env step, SURVEY 8(d) formula (fp32 state) */
+} mdp_env_dims;
+
+typedef struct mdp_env mdp_env;
+
+/* scenario.make_world() + MultiAgentEnv.__init__ (train.py:48-61): builds the entity table and the
+ * observation column table.  No device work (usable without a GPU). */
+int mdp_env_create(const mdp_env_cfg* cfg, mdp_env** out);
+int mdp_env_get_dims(const mdp_env* env, mdp_env_dims* out);
+void mdp_env_destroy(mdp_env* env);
+
+/* scenario.reset_world() + env.reset() (train.py:104,128).  If init_state is non-null it is a device
+ * SoA array of the env's state precision that is copied into `state` (injected reset, parity tests);
+ * otherwise positions are drawn on device with Philox4x32-10 keyed by (seed, episode, env, comp).
+ * Writes the reset observations to obs_out (joint layout). */
+int mdp_env_reset(mdp_env* env, int32_t E, void* state, const void* init_state, uint64_t seed,
+                  uint64_t episode, float* obs_out, void* stream);
+
+/* MultiAgentEnv.step(action_n) -> World.step() -> per-agent observation()/reward() (train.py:114;
+ * SURVEY Appendix A.2): one fused kernel.  state is updated in place.  ring_row0 (optional, may be
+ * null): when non-null the kernel also writes the joint replay rows of this transition
+ * (obs_t, act_t, next_obs, rew, done) to ring rows (ring_cursor + e) % ring_capacity, fusing
+ * MADDPGAgentTrainer.experience / ReplayBuffer.add (maddpg.py:154-156, replay_buffer.py:25-32)
+ * into the step; obs_prev (joint obs_t) must then be non-null. */
+int mdp_env_step(mdp_env* env, int32_t E, void* state, const float* act, float* obs_out, float* rew_out,
+                 uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
+                 int32_t ring_row_stride, int64_t ring_cursor, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* replay ring (maddpg/trainer/replay_buffer.py)                                                */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct mdp_ring_layout {
+  int32_t n_agents;
+  int32_t obs_dim[MDP_MAX_AGENTS], act_dim[MDP_MAX_AGENTS];
+  int32_t obs_off[MDP_MAX_AGENTS], act_off[MDP_MAX_AGENTS]; /* within the obs / act blocks */
+  int32_t obs_sum, act_sum;
+  int32_t x_dim;      /* obs_sum + act_sum = centralized critic input width C */
+  int32_t nx_off, rw_off, dn_off, row_stride; /* in floats */
+} mdp_ring_layout;
+
+/* Derives the joint-row layout from per-agent dims (host only). */
+int mdp_ring_make_layout(int32_t n_agents, const int32_t* obs_dim, const int32_t* act_dim, mdp_ring_layout* out);
+
+/* ReplayBuffer.add for E lockstep transitions (replay_buffer.py:25-32): row (cursor + e) % capacity
+ * <- (obs[e], act[e], rew[e], next_obs[e], done[e]).  agent = -1 writes every agent's columns;
+ * agent = i writes only agent i's columns (per-agent experience() calls, maddpg.py:154-156). */
+int mdp_replay_insert(const mdp_ring_layout* lay, float* ring, int64_t capacity, int64_t cursor, int32_t E,
+                      int32_t agent, const float* obs, int32_t obs_stride, const float* act, int32_t act_stride,
+                      const float* rew, int32_t rew_stride, const float* next_obs, int32_t next_obs_stride,
+                      const uint8_t* done, int32_t done_stride, void* stream);
+
+/* ReplayBuffer.sample_index / _encode_sample (replay_buffer.py:34-44,55-56): out[b, :] = ring[idx[b], :]
+ * for b < B (whole joint rows; per-agent fields are column views of `out`).  mode 0 = vectorised
+ * warp-per-row copy, mode 1 = cp.async.bulk (TMA bulk copy engine) row copies through shared memory. */
+int mdp_replay_gather(const float* ring, int64_t capacity, int32_t row_stride, const int64_t* idx, int32_t B,
+                      float* out, int32_t mode, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* trainer core (maddpg/trainer/maddpg.py)                                                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct mdp_core_cfg {
+  int32_t n_agents;
+  int32_t num_units; /* args.num_units: 64 or 128 (train.py:24) */
+  int32_t obs_dim[MDP_MAX_AGENTS], act_dim[MDP_MAX_AGENTS];
+  int32_t n_heads[MDP_MAX_AGENTS], head_dim[MDP_MAX_AGENTS][MDP_MAX_HEADS];
+  int32_t local_q[MDP_MAX_AGENTS]; /* local_q_func (ddpg mode), maddpg.py:51-52,86-87 */
+  double lr, gamma, polyak, grad_clip, actor_reg, beta1, beta2, adam_eps; /* polyak = 0.99 (maddpg.py:21) */
+} mdp_core_cfg;
+
+/* network ids inside one agent's parameter block */
+enum { MDP_NET_P = 0, MDP_NET_TARGET_P = 1, MDP_NET_Q = 2, MDP_NET_TARGET_Q = 3 };
+
+typedef struct mdp_core_layout {
+  int64_t total_params;               /* floats in the flat parameter buffer (all agents, 4 nets each) */
+  int64_t total_train;                /* floats in the flat grad / adam_m / adam_v buffers (P and Q nets) */
+  int64_t net_off[MDP_MAX_AGENTS][4]; /* offset of [W1|b1|W2|b2|W3|b3] of each net in `params` */
+  int64_t train_off[MDP_MAX_AGENTS][2]; /* offset of the P (0) and Q (1) net in grads/adam buffers */
+  int32_t net_in[MDP_MAX_AGENTS][4], net_out[MDP_MAX_AGENTS][4];
+  int64_t net_size[MDP_MAX_AGENTS][4];
+  int64_t update_flops_critic[MDP_MAX_AGENTS], update_flops_actor[MDP_MAX_AGENTS]; /* per batch row, SURVEY 8(d) */
+} mdp_core_layout;
+
+typedef struct mdp_core mdp_core;
+
+/* MADDPGAgentTrainer.__init__ x n (maddpg.py:113-149): derives the flat parameter layout. Host only. */
+int mdp_core_create(const mdp_core_cfg* cfg, mdp_core** out);
+int mdp_core_get_layout(const mdp_core* core, mdp_core_layout* out);
+void mdp_core_destroy(mdp_core* core);
+
+/* Registers the caller-owned device buffers (lifetime: until mdp_core_destroy or the next bind).
+ * params[total_params]; grads, adam_m, adam_v [total_train]; adam_t[2*n_agents] int32 step counters
+ * (P, Q per agent); stats[8*n_agents] float64 accumulators. */
+int mdp_core_bind(mdp_core* core, float* params, float* grads, float* adam_m, float* adam_v, int32_t* adam_t,
+                  double* stats);
+
+/* MADDPGAgentTrainer.action (maddpg.py:151-152) / p_debug['target_act'] (:70-71) for agents
+ * [agent_begin, agent_begin+agent_count): act_i = gumbel_softmax(mlp(obs_i)) in one grouped launch.
+ * obs/act are joint arrays.  u (optional, joint act layout): injected U[0,1) draws; when null the
+ * kernel draws Philox4x32-10 uniforms keyed by (seed, counter, env, column).  use_target selects the
+ * target actor.  logits_out (optional, joint act layout) receives the pre-noise logits (p_values). */
+int mdp_actor_act(mdp_core* core, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
+                  const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u,
+                  uint64_t seed, uint64_t counter, float* logits_out, void* stream);
+
+/* q_debug['q_values'] / ['target_q_values'] (maddpg.py:101,108): q[b] = Q_j(x[b, :]) where x is a
+ * (B, x_stride) array whose first x_dim columns are the joint critic input. */
+int mdp_critic_q(mdp_core* core, int32_t agent, int32_t use_target, int32_t B, const float* x, int32_t x_stride,
+                 float* q_out, void* stream);
+
+/* TD target of agent j (maddpg.py:181-187) on a gathered batch (B, row_stride) of joint ring rows:
+ * a'_i = gumbel_softmax(target_p_i(next_obs_i)) for all i, q' = target_q_j(next_obs, a'),
+ * y = float32(rew_j + gamma * (1 - done_j) * q') -- one fused kernel.  u_target (optional, (B, act_stride)
+ * joint layout) injects the uniforms.  Accumulates sum(y), sum(y^2), sum(rew), sum(q') into stats. */
+int mdp_td_target(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                  const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter, float* y_out,
+                  float* target_act_out, void* stream);
+
+/* q_train forward/backward (maddpg.py:75-100): grads of mean((Q_j(x) - y)^2) wrt the critic's six
+ * tensors are ACCUMULATED into the bound grad buffer (fused fwd + bwd kernel); sum((q-y)^2) -> stats. */
+int mdp_critic_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                     const float* y, float* q_out, void* stream);
+
+/* p_train forward/backward (maddpg.py:28-61): grads of -mean(Q_j(o, a_-j, gumbel_softmax(p_j(o_j))))
+ * + actor_reg * mean(logits^2) wrt the actor's tensors, through the RUNNING critic (fused kernel). */
+int mdp_actor_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                    const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter, void* stream);
+
+/* U.minimize_and_clip + tf.train.AdamOptimizer + make_update_exp (tf_util.py:166-182, maddpg.py:20-26):
+ * per-variable clip_by_norm, TF-Adam step (t = adam_t, incremented by the *_grads call), polyak update
+ * of the matching target net, and re-zeroing of the grad segment -- one kernel.  which: 0 = actor (P),
+ * 1 = critic (Q).  grad_scale multiplies the gradient first (1/world_size after an allreduce). */
+int mdp_clip_adam_polyak(mdp_core* core, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak,
+                         void* stream);
+
+/* MADDPGAgentTrainer.update body for agent j on one stream (maddpg.py:181-194), single GPU:
+ * td_target -> critic_grads -> clip_adam(Q) -> actor_grads -> clip_adam(P) + polyak(P) + polyak(Q). */
+int mdp_update_agent(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                     const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
+                     uint64_t counter, float* y_scratch, void* stream);
+
+const char* mdp_last_error(void);
+const char* mdp_version(void);
+/* number of kernels launched by this library in this process (bench.py's gpu_launches) */
+int64_t mdp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MADDPG_B200_H_ */

@@ -1,0 +1,86 @@
+// Shared host/device helpers for libmaddpg_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/maddpg_b200.h"
+
+namespace mdp {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: int status across the ABI, message in a thread-local buffer (header contract)
+// ---------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MDP_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  return MDP_OK;
+}
+
+#define MDP_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) return mdp::fail(MDP_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define MDP_REQUIRE(cond, ...)                                    \
+  do {                                                            \
+    if (!(cond)) return mdp::fail(MDP_EINVAL, __VA_ARGS__);       \
+  } while (0)
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al. 2011).  key = (seed lo, seed hi); counter =
+// (c0, c1, c2, c3).  Used for on-device reset draws and Gumbel noise (the reference's
+// TF / numpy / python RNG streams cannot be reproduced; parity tests inject the draws instead).
+// ---------------------------------------------------------------------------------------------
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * (uint64_t)b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ static inline uint4 gen(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(M0, c0, hi0, lo0);
+      mulhilo(M1, c2, hi1, lo1);
+      uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      k0 += W0; k1 += W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+  // U[0,1) with 24 random bits, like tf.random_uniform(float32) / numpy float32 draws
+  __host__ __device__ static inline float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+  // U[0,1) with 53 random bits
+  __host__ __device__ static inline double u01d(uint32_t hi, uint32_t lo) {
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+  }
+};
+
+// Gumbel-softmax noise term -log(-log(u)) in float32 (distributions.py:264-266)
+__device__ __forceinline__ float gumbel_from_u(float u) { return -logf(-logf(u)); }
+
+}  // namespace mdp

@@ -1,0 +1,45 @@
+// Trainer-core structures shared by mdp_train.cu (forward/backward kernels) and mdp_optim.cu.
+#pragma once
+#include "mdp_common.cuh"
+
+#include <vector>
+
+namespace mdp {
+
+struct MlpW {
+  const float *W1, *b1, *W2, *b2, *W3, *b3;
+  int in, out;
+};
+struct MlpG {
+  float *W1, *b1, *W2, *b2, *W3, *b3;
+};
+
+struct AgentDev {
+  MlpW net[4];  // MDP_NET_P, TARGET_P, Q, TARGET_Q
+  MlpG grad[2]; // P, Q
+  int obs_dim, act_dim, obs_off, act_off, n_heads, head_dim[2], local_q, q_in;
+};
+
+struct CoreDev {
+  const AgentDev* agents;
+  int n_agents, units;
+  int obs_sum, act_sum, act_stride;
+  double gamma, actor_reg;
+  int* adam_t;
+  double* stats;
+};
+
+}  // namespace mdp
+
+struct mdp_core {
+  mdp_core_cfg cfg;
+  mdp_core_layout lay;
+  int obs_off[MDP_MAX_AGENTS], act_off[MDP_MAX_AGENTS];
+  int obs_sum = 0, act_sum = 0, act_stride = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  int32_t* adam_t = nullptr;
+  double* stats = nullptr;
+  mdp::AgentDev* d_agents = nullptr;
+  std::vector<mdp::AgentDev> h_agents;
+};
+

@@ -1,0 +1,99 @@
+// Fused per-variable clip_by_norm + TF-Adam + polyak target sync + gradient re-zeroing (sm_100a).
+//
+// Replaces, per SURVEY.md 8(a) rows a11/a12:
+//   U.minimize_and_clip              maddpg/common/tf_util.py:166-182  (clip_by_norm PER VARIABLE, 0.5)
+//   tf.train.AdamOptimizer(lr)       maddpg/trainer/maddpg.py:129,141  (TF-1.8 formulation, SURVEY B.4:
+//                                    eps is added to the uncorrected sqrt(v); lr_t carries the bias terms)
+//   make_update_exp (polyak 0.99)    maddpg/trainer/maddpg.py:20-26, invoked :193-194
+// One CTA per variable (six per network): pass 1 reduces the squared norm of the (optionally
+// 1/world_size-scaled, i.e. all-reduced) gradient, pass 2 streams grad/m/v/param/target once.
+// HBM bound: 7 floats read + 5 written per parameter.
+#include "mdp_core.cuh"
+
+namespace mdp {
+
+struct OptSeg {
+  long long off[6];  // offsets of W1,b1,W2,b2,W3,b3 inside the net block
+  long long len[6];
+};
+
+__global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ param, float* __restrict__ target,
+                                                           float* __restrict__ grad, float* __restrict__ m,
+                                                           float* __restrict__ v, OptSeg seg, const int* __restrict__ t_ptr,
+                                                           float grad_scale, float clip, double lr, double beta1,
+                                                           double beta2, float eps, float polyak, int do_polyak) {
+  __shared__ float red[32];
+  __shared__ float s_factor;
+  const long long off = seg.off[blockIdx.x], len = seg.len[blockIdx.x];
+  float* g = grad + off;
+  // pass 1: ||scale * g||_2
+  float ss = 0.f;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const float x = g[i] * grad_scale;
+    ss = fmaf(x, x, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      const float norm = sqrtf(s);
+      s_factor = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;  // tf.clip_by_norm: g * clip / max(||g||, clip)
+    }
+  }
+  __syncthreads();
+  const float factor = s_factor * grad_scale;
+  const int t = *t_ptr;
+  const float lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+  const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2);
+  const float opol = 1.0f - polyak;
+  float* p = param + off;
+  float* tg = target + off;
+  float* mm = m + off;
+  float* vv = v + off;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const float gi = g[i] * factor;
+    const float mi = b1 * mm[i] + ob1 * gi;
+    const float vi = b2 * vv[i] + ob2 * gi * gi;
+    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    mm[i] = mi;
+    vv[i] = vi;
+    p[i] = pi;
+    if (do_polyak) tg[i] = polyak * tg[i] + opol * pi;
+    g[i] = 0.f;  // the *_grads kernels accumulate with atomics: leave the bucket clean for the next round
+  }
+}
+
+}  // namespace mdp
+
+using namespace mdp;
+
+extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak,
+                                    void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_clip_adam_polyak: core not bound");
+  MDP_REQUIRE(agent >= 0 && agent < c->cfg.n_agents && (which == 0 || which == 1), "mdp_clip_adam_polyak: bad argument");
+  const int U = c->cfg.num_units;
+  const int net = which == 0 ? MDP_NET_P : MDP_NET_Q;
+  const int tnet = which == 0 ? MDP_NET_TARGET_P : MDP_NET_TARGET_Q;
+  const long long in = c->lay.net_in[agent][net], out = c->lay.net_out[agent][net];
+  OptSeg seg;
+  const long long lens[6] = {in * U, U, (long long)U * U, U, (long long)U * out, out};
+  long long o = 0;
+  for (int k = 0; k < 6; ++k) {
+    seg.off[k] = o;
+    seg.len[k] = lens[k];
+    o += lens[k];
+  }
+  float* param = c->params + c->lay.net_off[agent][net];
+  float* target = c->params + c->lay.net_off[agent][tnet];
+  float* grad = c->grads + c->lay.train_off[agent][which];
+  float* m = c->adam_m + c->lay.train_off[agent][which];
+  float* v = c->adam_v + c->lay.train_off[agent][which];
+  k_clip_adam_polyak<<<6, 1024, 0, (cudaStream_t)stream>>>(param, target, grad, m, v, seg, c->adam_t + 2 * agent + which,
+                                                           grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
+                                                           c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak,
+                                                           do_polyak);
+  return check_launch("k_clip_adam_polyak");
+}

@@ -1,0 +1,965 @@
+// MADDPG trainer kernels: grouped actor inference + Gumbel-softmax, fused TD target, fused critic
+// forward/backward, fused actor forward/backward through the running critic (sm_100a, fp32).
+//
+// Replaces, per SURVEY.md 8(a):
+//   a2/a3  MADDPGAgentTrainer.action -> mlp_model -> SoftCategoricalPd.sample
+//          (maddpg/trainer/maddpg.py:151-152,:62; experiments/train.py:39-46;
+//           maddpg/common/distributions.py:264-266, 332-336)
+//   a8     target computation                      maddpg/trainer/maddpg.py:181-187 (:70-71, :104,108)
+//   a9     q_train                                 maddpg/trainer/maddpg.py:75-110
+//   a10    p_train                                 maddpg/trainer/maddpg.py:28-73
+//   a16    local_q_func (ddpg mode)                maddpg/trainer/maddpg.py:51-52, 86-87
+//
+// Design: every kernel owns a tile of TM batch rows per CTA and carries it through the WHOLE
+// 3-layer MLP (and, for the update kernels, back again) without leaving shared memory: layer-1
+// streams the (B, C) input and W1 through smem in K-chunks (C goes up to 3576), hidden activations
+// live in smem, per-CTA weight-gradient partials are reduced into the flat gradient bucket with
+// fp32 RED atomics.  The fp32 SIMT path is the parity path (1e-4 on Q/loss needs ~fp32 products);
+// see DESIGN.md for the tensor-core plan.
+#include "mdp_core.cuh"
+
+#include <new>
+
+namespace mdp {
+
+constexpr int TM = 32;    // batch rows per CTA
+constexpr int NT = 256;   // threads per CTA: 16 (row pairs) x 16 (column quads)
+constexpr int KC = 32;    // K-chunk streamed through shared memory
+constexpr int XP = KC + 4;
+constexpr int KPAD = 12;  // pitch of per-row action/logit scratch (max act_dim 9)
+constexpr int MAXK = 9;
+
+// Layer-1 input: up to two global column segments plus an optional shared-memory override range
+// (the freshly sampled action that replaces the replayed one).
+struct XSrc {
+  const float* g0; int ld0, n0;
+  const float* g1; int ld1, n1;
+  const float* s_over; int over_ld, over_c0, over_n;
+  __device__ __forceinline__ float get(int r_local, long long r_global, int c) const {
+    if (c >= over_c0 && c < over_c0 + over_n) return s_over[r_local * over_ld + (c - over_c0)];
+    if (c < n0) return g0[r_global * ld0 + c];
+    c -= n0;
+    if (c < n1) return g1[r_global * ld1 + c];
+    return 0.f;
+  }
+};
+
+__device__ __forceinline__ XSrc make_xsrc(const float* g0, int ld0, int n0) {
+  XSrc x; x.g0 = g0; x.ld0 = ld0; x.n0 = n0; x.g1 = nullptr; x.ld1 = 0; x.n1 = 0;
+  x.s_over = nullptr; x.over_ld = 0; x.over_c0 = 0; x.over_n = 0; return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile primitives.  Thread (ty, tx) = (tid >> 4, tid & 15) owns rows {2ty, 2ty+1} and columns
+// {64g + 4tx .. +3 : g < U/64} of a TM x U tile.
+// ---------------------------------------------------------------------------------------------
+template <int U>
+__device__ __forceinline__ void zero_acc(float (&acc)[2][U / 16]) {
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < U / 16; ++c) acc[r][c] = 0.f;
+}
+
+template <int U>
+__device__ __forceinline__ void mma_tile(float (&acc)[2][U / 16], const float* __restrict__ sA, int lda,
+                                         const float* __restrict__ sW, int kc) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const float* a0p = sA + (2 * ty) * lda;
+  const float* a1p = a0p + lda;
+#pragma unroll 2
+  for (int k = 0; k < kc; k += 4) {
+    const float4 a0 = *reinterpret_cast<const float4*>(a0p + k);
+    const float4 a1 = *reinterpret_cast<const float4*>(a1p + k);
+    const float a0v[4] = {a0.x, a0.y, a0.z, a0.w};
+    const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int g = 0; g < U / 64; ++g) {
+        const float4 w = *reinterpret_cast<const float4*>(sW + (k + kk) * U + g * 64 + 4 * tx);
+        acc[0][4 * g + 0] = fmaf(a0v[kk], w.x, acc[0][4 * g + 0]);
+        acc[0][4 * g + 1] = fmaf(a0v[kk], w.y, acc[0][4 * g + 1]);
+        acc[0][4 * g + 2] = fmaf(a0v[kk], w.z, acc[0][4 * g + 2]);
+        acc[0][4 * g + 3] = fmaf(a0v[kk], w.w, acc[0][4 * g + 3]);
+        acc[1][4 * g + 0] = fmaf(a1v[kk], w.x, acc[1][4 * g + 0]);
+        acc[1][4 * g + 1] = fmaf(a1v[kk], w.y, acc[1][4 * g + 1]);
+        acc[1][4 * g + 2] = fmaf(a1v[kk], w.z, acc[1][4 * g + 2]);
+        acc[1][4 * g + 3] = fmaf(a1v[kk], w.w, acc[1][4 * g + 3]);
+      }
+    }
+  }
+}
+
+// rows [k0, k0+KC) of a row-major (K, U) weight -> sW[KC][U], zero past K
+template <int U>
+__device__ __forceinline__ void load_w_rows(float* __restrict__ sW, const float* __restrict__ W, int k0, int K) {
+  for (int idx = threadIdx.x * 4; idx < KC * U; idx += NT * 4) {
+    const int k = idx / U;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k0 + k < K) v = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * U + (idx - k * U));
+    *reinterpret_cast<float4*>(sW + idx) = v;
+  }
+}
+
+// transposed chunk of a (U, U) weight: sW[ul][k] = W[k][u0 + ul]  (for dX = dY * W^T)
+template <int U>
+__device__ __forceinline__ void load_wT_rows(float* __restrict__ sW, const float* __restrict__ W, int u0) {
+  for (int idx = threadIdx.x; idx < KC * U; idx += NT) {
+    const int ul = idx / U, k = idx - ul * U;
+    sW[idx] = W[(size_t)k * U + u0 + ul];
+  }
+}
+
+__device__ __forceinline__ void load_x_chunk(float* __restrict__ sX, const XSrc& xs, long long row0, int nrows, int k0) {
+  for (int idx = threadIdx.x; idx < TM * KC; idx += NT) {
+    const int r = idx >> 5, c = idx & 31;
+    sX[r * XP + c] = (r < nrows) ? xs.get(r, row0 + r, k0 + c) : 0.f;
+  }
+}
+
+// acc = X[rows] * W1 streamed in K-chunks (ends synchronised)
+template <int U>
+__device__ __forceinline__ void layer1(float (&acc)[2][U / 16], const XSrc& xs, int K, const float* __restrict__ W1,
+                                       long long row0, int nrows, float* sX, float* sW) {
+  zero_acc<U>(acc);
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    load_x_chunk(sX, xs, row0, nrows, k0);
+    load_w_rows<U>(sW, W1, k0, K);
+    __syncthreads();
+    mma_tile<U>(acc, sX, XP, sW, KC);
+    __syncthreads();
+  }
+}
+
+// acc = sA[TM][U] * W (U,U)   (TRANSPOSED: * W^T), W streamed in KC-row chunks (ends synchronised)
+template <int U, bool TRANSPOSED>
+__device__ __forceinline__ void layer_h(float (&acc)[2][U / 16], const float* __restrict__ sA, const float* __restrict__ W,
+                                        float* sW) {
+  constexpr int HP = U + 4;
+  zero_acc<U>(acc);
+  for (int k0 = 0; k0 < U; k0 += KC) {
+    if (TRANSPOSED) load_wT_rows<U>(sW, W, k0); else load_w_rows<U>(sW, W, k0, U);
+    __syncthreads();
+    mma_tile<U>(acc, sA + k0, HP, sW, KC);
+    __syncthreads();
+  }
+}
+
+// sH[r][c] = relu(acc + bias[c])   (caller synchronises)
+template <int U>
+__device__ __forceinline__ void store_bias_relu(const float (&acc)[2][U / 16], const float* __restrict__ bias, float* sH) {
+  constexpr int HP = U + 4;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int g = 0; g < U / 64; ++g) {
+    const int c = g * 64 + 4 * tx;
+    const float4 b = *reinterpret_cast<const float4*>(bias + c);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float4 v;
+      v.x = fmaxf(acc[rr][4 * g + 0] + b.x, 0.f);
+      v.y = fmaxf(acc[rr][4 * g + 1] + b.y, 0.f);
+      v.z = fmaxf(acc[rr][4 * g + 2] + b.z, 0.f);
+      v.w = fmaxf(acc[rr][4 * g + 3] + b.w, 0.f);
+      *reinterpret_cast<float4*>(sH + (2 * ty + rr) * HP + c) = v;
+    }
+  }
+}
+
+// sH[r][c] = (sH[r][c] > 0) ? acc : 0     in place: dz = dh * relu'(h)   (caller synchronises)
+template <int U>
+__device__ __forceinline__ void store_masked(const float (&acc)[2][U / 16], float* sH) {
+  constexpr int HP = U + 4;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int g = 0; g < U / 64; ++g) {
+    const int c = g * 64 + 4 * tx;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      float4 h = *reinterpret_cast<const float4*>(sH + (2 * ty + rr) * HP + c);
+      h.x = h.x > 0.f ? acc[rr][4 * g + 0] : 0.f;
+      h.y = h.y > 0.f ? acc[rr][4 * g + 1] : 0.f;
+      h.z = h.z > 0.f ? acc[rr][4 * g + 2] : 0.f;
+      h.w = h.w > 0.f ? acc[rr][4 * g + 3] : 0.f;
+      *reinterpret_cast<float4*>(sH + (2 * ty + rr) * HP + c) = h;
+    }
+  }
+}
+
+// h1 -> sH1, h2 -> sH2 for the tile (ends synchronised)
+template <int U>
+__device__ __forceinline__ void forward_hidden(const XSrc& xs, const MlpW& w, long long row0, int nrows, float* sX,
+                                               float* sW, float* sH1, float* sH2) {
+  float acc[2][U / 16];
+  layer1<U>(acc, xs, w.in, w.W1, row0, nrows, sX, sW);
+  store_bias_relu<U>(acc, w.b1, sH1);
+  __syncthreads();
+  layer_h<U, false>(acc, sH1, w.W2, sW);
+  store_bias_relu<U>(acc, w.b2, sH2);
+  __syncthreads();
+}
+
+// out_dim == 1 head: sQ[r] = h2[r,:] . W3 + b3   (8 threads per row; ends synchronised)
+template <int U>
+__device__ __forceinline__ void critic_head(const float* __restrict__ sH2, const MlpW& w, float* sQ) {
+  constexpr int HP = U + 4;
+  const int row = threadIdx.x >> 3, part = threadIdx.x & 7;
+  float s = 0.f;
+  for (int u = part; u < U; u += 8) s = fmaf(sH2[row * HP + u], w.W3[u], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (part == 0) sQ[row] = s + w.b3[0];
+  __syncthreads();
+}
+
+// general head: sL[r][a] = h2[r,:] . W3[:,a] + b3[a], a < out   (ends synchronised)
+template <int U>
+__device__ __forceinline__ void actor_head(const float* __restrict__ sH2, const MlpW& w, float* sL) {
+  constexpr int HP = U + 4;
+  const int K = w.out;
+  for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
+    const int r = idx / K, a = idx - r * K;
+    float s = 0.f;
+    for (int u = 0; u < U; ++u) s = fmaf(sH2[r * HP + u], w.W3[u * K + a], s);
+    sL[r * KPAD + a] = s + w.b3[a];
+  }
+  __syncthreads();
+}
+
+// Gumbel-softmax per (row, head): softmax(logits - log(-log u))   (ends synchronised)
+__device__ __forceinline__ void gumbel_softmax_tile(const float* __restrict__ sL, float* __restrict__ sOut, int out_ld,
+                                                    int nrows, int n_heads, const int* head_dim,
+                                                    const float* __restrict__ u_glob, int u_ld, int u_col0,
+                                                    long long row0, uint64_t seed, uint64_t counter, uint32_t tag) {
+  for (int idx = threadIdx.x; idx < TM * n_heads; idx += NT) {
+    const int r = idx / n_heads, h = idx - r * n_heads;
+    if (r >= nrows) continue;
+    const int o = h ? head_dim[0] : 0, n = head_dim[h];
+    float z[MAXK];
+    float m = -INFINITY;
+    uint4 rnd = make_uint4(0, 0, 0, 0);
+    for (int a = 0; a < n; ++a) {
+      float u;
+      if (u_glob) {
+        u = u_glob[(row0 + r) * u_ld + u_col0 + o + a];
+      } else {
+        if ((a & 3) == 0)
+          rnd = Philox::gen(seed, (uint32_t)(row0 + r), (uint32_t)((row0 + r) >> 32) ^ (tag << 8) ^ (uint32_t)(o + a),
+                            (uint32_t)counter, (uint32_t)(counter >> 32));
+        const uint32_t x = (a & 3) == 0 ? rnd.x : (a & 3) == 1 ? rnd.y : (a & 3) == 2 ? rnd.z : rnd.w;
+        u = Philox::u01(x);
+      }
+      z[a] = sL[r * KPAD + o + a] + gumbel_from_u(u);
+      m = fmaxf(m, z[a]);
+    }
+    float s = 0.f;
+    for (int a = 0; a < n; ++a) {
+      z[a] = expf(z[a] - m);
+      s += z[a];
+    }
+    for (int a = 0; a < n; ++a) sOut[r * out_ld + o + a] = z[a] / s;
+  }
+  __syncthreads();
+}
+
+// gW (U,U) += sA^T (h, TM x U) * sD (dz, TM x U); thread owns rows ty*RN.. and the usual columns
+template <int U>
+__device__ __forceinline__ void grad_w_hidden(const float* __restrict__ sA, const float* __restrict__ sD, float* __restrict__ gW) {
+  constexpr int HP = U + 4, RN = U / 16;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[RN][RN];
+#pragma unroll
+  for (int a = 0; a < RN; ++a)
+#pragma unroll
+    for (int b = 0; b < RN; ++b) acc[a][b] = 0.f;
+  for (int r = 0; r < TM; ++r) {
+    float av[RN], dv[RN];
+#pragma unroll
+    for (int q = 0; q < RN / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(sA + r * HP + ty * RN + 4 * q);
+      av[4 * q + 0] = t.x; av[4 * q + 1] = t.y; av[4 * q + 2] = t.z; av[4 * q + 3] = t.w;
+      const float4 d = *reinterpret_cast<const float4*>(sD + r * HP + q * 64 + 4 * tx);
+      dv[4 * q + 0] = d.x; dv[4 * q + 1] = d.y; dv[4 * q + 2] = d.z; dv[4 * q + 3] = d.w;
+    }
+#pragma unroll
+    for (int a = 0; a < RN; ++a)
+#pragma unroll
+      for (int b = 0; b < RN; ++b) acc[a][b] = fmaf(av[a], dv[b], acc[a][b]);
+  }
+#pragma unroll
+  for (int a = 0; a < RN; ++a)
+#pragma unroll
+    for (int b = 0; b < RN; ++b)
+      atomicAdd(gW + (size_t)(ty * RN + a) * U + (b / 4) * 64 + 4 * tx + (b & 3), acc[a][b]);
+}
+
+// gW1 rows [k0, k0+KC) += sX^T (TM x KC chunk) * sD (TM x U)
+template <int U>
+__device__ __forceinline__ void grad_w_chunk(const float* __restrict__ sX, const float* __restrict__ sD,
+                                             float* __restrict__ gW1, int k0, int K) {
+  constexpr int HP = U + 4, RN = U / 16;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  float acc[2][RN];
+  zero_acc<U>(acc);
+  for (int r = 0; r < TM; ++r) {
+    const float2 a = *reinterpret_cast<const float2*>(sX + r * XP + 2 * ty);
+#pragma unroll
+    for (int q = 0; q < RN / 4; ++q) {
+      const float4 d = *reinterpret_cast<const float4*>(sD + r * HP + q * 64 + 4 * tx);
+      acc[0][4 * q + 0] = fmaf(a.x, d.x, acc[0][4 * q + 0]);
+      acc[0][4 * q + 1] = fmaf(a.x, d.y, acc[0][4 * q + 1]);
+      acc[0][4 * q + 2] = fmaf(a.x, d.z, acc[0][4 * q + 2]);
+      acc[0][4 * q + 3] = fmaf(a.x, d.w, acc[0][4 * q + 3]);
+      acc[1][4 * q + 0] = fmaf(a.y, d.x, acc[1][4 * q + 0]);
+      acc[1][4 * q + 1] = fmaf(a.y, d.y, acc[1][4 * q + 1]);
+      acc[1][4 * q + 2] = fmaf(a.y, d.z, acc[1][4 * q + 2]);
+      acc[1][4 * q + 3] = fmaf(a.y, d.w, acc[1][4 * q + 3]);
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int k = k0 + 2 * ty + rr;
+    if (k < K) {
+#pragma unroll
+      for (int b = 0; b < RN; ++b) atomicAdd(gW1 + (size_t)k * U + (b / 4) * 64 + 4 * tx + (b & 3), acc[rr][b]);
+    }
+  }
+}
+
+template <int U>
+__device__ __forceinline__ void grad_bias(const float* __restrict__ sD, float* __restrict__ gb) {
+  constexpr int HP = U + 4;
+  if (threadIdx.x < U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s += sD[r * HP + threadIdx.x];
+    atomicAdd(gb + threadIdx.x, s);
+  }
+}
+
+// full backward below the second hidden layer: given dz2 in sH2 (already masked) and h1 in sH1,
+// accumulates gW2, gb2, then dz1 -> sH1 (in place), then optionally gW1/gb1 (re-streaming X).
+template <int U>
+__device__ __forceinline__ void backward_hidden(const XSrc& xs, const MlpW& w, const MlpG* g, long long row0, int nrows,
+                                                float* sX, float* sW, float* sH1, float* sH2) {
+  if (g) {
+    grad_w_hidden<U>(sH1, sH2, g->W2);
+    grad_bias<U>(sH2, g->b2);
+  }
+  float acc[2][U / 16];
+  __syncthreads();
+  layer_h<U, true>(acc, sH2, w.W2, sW);  // dh1 = dz2 * W2^T
+  store_masked<U>(acc, sH1);              // dz1 = dh1 * relu'(h1)
+  __syncthreads();
+  if (g) {
+    grad_bias<U>(sH1, g->b1);
+    for (int k0 = 0; k0 < w.in; k0 += KC) {
+      load_x_chunk(sX, xs, row0, nrows, k0);
+      __syncthreads();
+      grad_w_chunk<U>(sX, sH1, g->W1, k0, w.in);
+      __syncthreads();
+    }
+  }
+}
+
+struct SmemCarve {
+  float* p;
+  __device__ explicit SmemCarve(void* base) : p(reinterpret_cast<float*>(base)) {}
+  __device__ float* take(int nfloats) {
+    float* r = p;
+    p += (nfloats + 3) & ~3;
+    return r;
+  }
+};
+
+template <int U>
+constexpr int smem_floats_base() { return KC * U + TM * XP + 2 * TM * (U + 4); }
+
+// ---------------------------------------------------------------------------------------------
+// K1: grouped actor inference + Gumbel-softmax.  grid = (ceil(E/TM), agent_count)
+// ---------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, int use_target, int E,
+                                                  const float* __restrict__ obs, int obs_stride, float* __restrict__ act,
+                                                  int act_stride, const float* __restrict__ u, uint64_t seed,
+                                                  uint64_t counter, float* __restrict__ logits_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarve sm(smem_raw);
+  float* sW = sm.take(KC * U);
+  float* sX = sm.take(TM * XP);
+  float* sH1 = sm.take(TM * (U + 4));
+  float* sH2 = sm.take(TM * (U + 4));
+  float* sL = sm.take(TM * KPAD);
+  float* sA = sm.take(TM * KPAD);
+  const int i = agent_begin + blockIdx.y;
+  const AgentDev& ag = C.agents[i];
+  const MlpW& w = ag.net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, E - row0);
+  XSrc xs = make_xsrc(obs + ag.obs_off, obs_stride, ag.obs_dim);
+  forward_hidden<U>(xs, w, row0, nrows, sX, sW, sH1, sH2);
+  actor_head<U>(sH2, w, sL);
+  gumbel_softmax_tile(sL, sA, KPAD, nrows, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off, row0, seed, counter,
+                      (uint32_t)i);
+  for (int idx = threadIdx.x; idx < nrows * ag.act_dim; idx += NT) {
+    const int r = idx / ag.act_dim, a = idx - r * ag.act_dim;
+    act[(row0 + r) * act_stride + ag.act_off + a] = sA[r * KPAD + a];
+    if (logits_out) logits_out[(row0 + r) * act_stride + ag.act_off + a] = sL[r * KPAD + a];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// q-values of one critic (debug surface q_debug[...]).  grid = ceil(B/TM)
+// ---------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(NT) k_critic_q(CoreDev C, int agent, int use_target, int B, const float* __restrict__ x,
+                                                 int x_stride, float* __restrict__ q_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarve sm(smem_raw);
+  float* sW = sm.take(KC * U);
+  float* sX = sm.take(TM * XP);
+  float* sH1 = sm.take(TM * (U + 4));
+  float* sH2 = sm.take(TM * (U + 4));
+  float* sQ = sm.take(TM);
+  const AgentDev& ag = C.agents[agent];
+  const MlpW& w = ag.net[use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  XSrc xs;
+  if (ag.local_q) {
+    xs = make_xsrc(x + ag.obs_off, x_stride, ag.obs_dim);
+    xs.g1 = x + C.obs_sum + ag.act_off; xs.ld1 = x_stride; xs.n1 = ag.act_dim;
+  } else {
+    xs = make_xsrc(x, x_stride, C.obs_sum + C.act_sum);
+  }
+  forward_hidden<U>(xs, w, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(sH2, w, sQ);
+  if (threadIdx.x < nrows) q_out[row0 + threadIdx.x] = sQ[threadIdx.x];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: fused TD target of agent j.  grid = ceil(B/TM)
+// ---------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                  const float* __restrict__ u_target, int u_stride, uint64_t seed,
+                                                  uint64_t counter, float* __restrict__ y_out,
+                                                  float* __restrict__ target_act_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemCarve sm(smem_raw);
+  float* sW = sm.take(KC * U);
+  float* sX = sm.take(TM * XP);
+  float* sH1 = sm.take(TM * (U + 4));
+  float* sH2 = sm.take(TM * (U + 4));
+  float* sL = sm.take(TM * KPAD);
+  float* sQ = sm.take(TM);
+  const int ASP = C.act_stride | 1;
+  float* sAct = sm.take(TM * ASP);
+  const AgentDev& me = C.agents[j];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  const int R = L.row_stride;
+
+  // a'_i = gumbel_softmax(target_p_i(next_obs_i)) for every agent the critic sees
+  const int i_begin = me.local_q ? j : 0, i_end = me.local_q ? j + 1 : C.n_agents;
+  for (int i = i_begin; i < i_end; ++i) {
+    const AgentDev& ag = C.agents[i];
+    XSrc xs = make_xsrc(batch + L.nx_off + ag.obs_off, R, ag.obs_dim);
+    forward_hidden<U>(xs, ag.net[MDP_NET_TARGET_P], row0, nrows, sX, sW, sH1, sH2);
+    actor_head<U>(sH2, ag.net[MDP_NET_TARGET_P], sL);
+    gumbel_softmax_tile(sL, sAct + ag.act_off, ASP, nrows, ag.n_heads, ag.head_dim, u_target, u_stride, ag.act_off, row0,
+                        seed, counter, (uint32_t)(0x100 + i));
+  }
+  if (target_act_out) {
+    for (int idx = threadIdx.x; idx < nrows * C.act_sum; idx += NT) {
+      const int r = idx / C.act_sum, c = idx - r * C.act_sum;
+      const bool mine = !me.local_q || (c >= me.act_off && c < me.act_off + me.act_dim);
+      if (mine) target_act_out[(row0 + r) * u_stride + c] = sAct[r * ASP + c];
+    }
+  }
+  // q' = target_q_j([next_obs | a'])
+  XSrc xs;
+  if (me.local_q) {
+    xs = make_xsrc(batch + L.nx_off + me.obs_off, R, me.obs_dim);
+    xs.s_over = sAct + me.act_off; xs.over_ld = ASP; xs.over_c0 = me.obs_dim; xs.over_n = me.act_dim;
+  } else {
+    xs = make_xsrc(batch + L.nx_off, R, C.obs_sum);
+    xs.s_over = sAct; xs.over_ld = ASP; xs.over_c0 = C.obs_sum; xs.over_n = C.act_sum;
+  }
+  const MlpW& tq = me.net[MDP_NET_TARGET_Q];
+  forward_hidden<U>(xs, tq, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(sH2, tq, sQ);
+  // y = float32(rew + gamma * (1 - done) * q')  -- float64 combine like numpy (maddpg.py:186)
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    double sy = 0, syy = 0, sr = 0, sq = 0;
+    if (r < nrows) {
+      const float* row = batch + (row0 + r) * R;
+      const double rew = (double)row[L.rw_off + j], done = (double)row[L.dn_off + j];
+      const float qn = sQ[r];
+      const double y = rew + C.gamma * (1.0 - done) * (double)qn;
+      y_out[row0 + r] = (float)y;
+      sy = y; syy = y * y; sr = rew; sq = (double)qn;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      syy += __shfl_xor_sync(0xffffffffu, syy, o);
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (r == 0) {
+      double* st = C.stats + 8 * j;
+      atomicAdd(st + 3, sy); atomicAdd(st + 4, syy); atomicAdd(st + 5, sr); atomicAdd(st + 6, sq);
+      atomicAdd(st + 7, (double)nrows);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: fused critic forward + MSE + backward.  grid = ceil(B/TM)
+// ---------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                     const float* __restrict__ y, float* __restrict__ q_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int HP = U + 4;
+  SmemCarve sm(smem_raw);
+  float* sW = sm.take(KC * U);
+  float* sX = sm.take(TM * XP);
+  float* sH1 = sm.take(TM * HP);
+  float* sH2 = sm.take(TM * HP);
+  float* sQ = sm.take(TM);
+  float* sDq = sm.take(TM);
+  const AgentDev& me = C.agents[j];
+  const MlpW& w = me.net[MDP_NET_Q];
+  const MlpG& g = me.grad[1];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  const int R = L.row_stride;
+  if (blockIdx.x == 0 && threadIdx.x == 0) C.adam_t[2 * j + 1] += 1;  // one more Adam step for this net
+  XSrc xs;
+  if (me.local_q) {
+    xs = make_xsrc(batch + me.obs_off, R, me.obs_dim);
+    xs.g1 = batch + L.obs_sum + me.act_off; xs.ld1 = R; xs.n1 = me.act_dim;
+  } else {
+    xs = make_xsrc(batch, R, L.x_dim);
+  }
+  forward_hidden<U>(xs, w, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(sH2, w, sQ);
+  // dL/dq = 2 (q - y) / B ; loss partial
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    float d = 0.f;
+    double se = 0.0;
+    if (r < nrows) {
+      const float q = sQ[r];
+      const float diff = q - y[row0 + r];
+      d = 2.0f * diff / (float)B;
+      se = (double)diff * (double)diff;
+      if (q_out) q_out[row0 + r] = q;
+    }
+    sDq[r] = d;
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (r == 0) atomicAdd(C.stats + 8 * j + 0, se);
+  }
+  __syncthreads();
+  // gW3[u] = sum_r h2[r][u] dq[r] ; gb3 = sum_r dq[r]
+  if (threadIdx.x < U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s = fmaf(sH2[r * HP + threadIdx.x], sDq[r], s);
+    atomicAdd(g.W3 + threadIdx.x, s);
+  } else if (threadIdx.x == U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s += sDq[r];
+    atomicAdd(g.b3, s);
+  }
+  __syncthreads();
+  // dz2 = dq * W3^T * relu'(h2), in place over h2
+  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sH2[r * HP + u];
+    sH2[r * HP + u] = h > 0.f ? sDq[r] * w.W3[u] : 0.f;
+  }
+  __syncthreads();
+  backward_hidden<U>(xs, w, &g, row0, nrows, sX, sW, sH1, sH2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: fused actor forward -> Gumbel-softmax -> running critic forward -> backward to the action
+// columns -> softmax Jacobian + logit regulariser -> actor backward.  grid = ceil(B/TM)
+// ---------------------------------------------------------------------------------------------
+template <int U>
+__global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                    const float* __restrict__ u_actor, int u_stride, uint64_t seed,
+                                                    uint64_t counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int HP = U + 4;
+  SmemCarve sm(smem_raw);
+  float* sW = sm.take(KC * U);
+  float* sX = sm.take(TM * XP);
+  float* sH1 = sm.take(TM * HP);
+  float* sH2 = sm.take(TM * HP);
+  float* sP1 = sm.take(TM * HP);   // actor h1
+  float* sP2 = sm.take(TM * HP);   // actor h2
+  float* sL = sm.take(TM * KPAD);  // logits
+  float* sA = sm.take(TM * KPAD);  // sampled action
+  float* sDa = sm.take(TM * KPAD); // dQ/da then dL/dlogits
+  float* sQ = sm.take(TM);
+  const AgentDev& me = C.agents[j];
+  const MlpW& pw = me.net[MDP_NET_P];
+  const MlpW& qw = me.net[MDP_NET_Q];
+  const MlpG& pg = me.grad[0];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  const int R = L.row_stride, K = me.act_dim;
+  if (blockIdx.x == 0 && threadIdx.x == 0) C.adam_t[2 * j + 0] += 1;
+
+  // actor forward on o_j, fresh Gumbel-softmax sample (maddpg.py:49)
+  XSrc xp = make_xsrc(batch + me.obs_off, R, me.obs_dim);
+  forward_hidden<U>(xp, pw, row0, nrows, sX, sW, sP1, sP2);
+  actor_head<U>(sP2, pw, sL);
+  gumbel_softmax_tile(sL, sA, KPAD, nrows, me.n_heads, me.head_dim, u_actor, u_stride, me.act_off, row0, seed, counter,
+                      (uint32_t)(0x200 + j));
+  // running critic on [o, a_-j, a_hat_j]
+  XSrc xq;
+  int a_col0;
+  if (me.local_q) {
+    xq = make_xsrc(batch + me.obs_off, R, me.obs_dim);
+    a_col0 = me.obs_dim;
+  } else {
+    xq = make_xsrc(batch, R, L.x_dim);
+    a_col0 = L.obs_sum + me.act_off;
+  }
+  xq.s_over = sA; xq.over_ld = KPAD; xq.over_c0 = a_col0; xq.over_n = K;
+  forward_hidden<U>(xq, qw, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(sH2, qw, sQ);
+  // loss partials: sum(-q), sum(logits^2)
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    double sq = 0.0, sl = 0.0;
+    if (r < nrows) {
+      sq = -(double)sQ[r];
+      for (int a = 0; a < K; ++a) sl += (double)sL[r * KPAD + a] * (double)sL[r * KPAD + a];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    }
+    if (r == 0) {
+      atomicAdd(C.stats + 8 * j + 1, sq);
+      atomicAdd(C.stats + 8 * j + 2, sl);
+    }
+  }
+  // dz2 = (-1/B) * W3^T * relu'(h2) for valid rows
+  const float dq = -1.0f / (float)B;
+  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sH2[r * HP + u];
+    sH2[r * HP + u] = (h > 0.f && r < nrows) ? dq * qw.W3[u] : 0.f;
+  }
+  __syncthreads();
+  backward_hidden<U>(xq, qw, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 (critic) now in sH1
+  // dQ/da[r][a] = dz1[r,:] . W1[a_col0 + a, :]
+  for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
+    const int r = idx / K, a = idx - r * K;
+    const float* w1row = qw.W1 + (size_t)(a_col0 + a) * U;
+    float s = 0.f;
+    for (int u = 0; u < U; ++u) s = fmaf(sH1[r * HP + u], w1row[u], s);
+    sDa[r * KPAD + a] = s;
+  }
+  __syncthreads();
+  // dL/dlogits = softmax Jacobian per head + 2 * reg * logits / (B * K)
+  const float regc = (float)(2.0 * C.actor_reg / ((double)B * (double)K));
+  for (int idx = threadIdx.x; idx < TM * me.n_heads; idx += NT) {
+    const int r = idx / me.n_heads, h = idx - r * me.n_heads;
+    const int o = h ? me.head_dim[0] : 0, n = me.head_dim[h];
+    float dot = 0.f;
+    for (int a = 0; a < n; ++a) dot = fmaf(sA[r * KPAD + o + a], sDa[r * KPAD + o + a], dot);
+    for (int a = 0; a < n; ++a) {
+      const float p = sA[r * KPAD + o + a];
+      float dl = p * (sDa[r * KPAD + o + a] - dot) + regc * sL[r * KPAD + o + a];
+      sDa[r * KPAD + o + a] = (r < nrows) ? dl : 0.f;
+    }
+  }
+  __syncthreads();
+  // actor head backward: gW3[u][a], gb3[a], dz2a = dl * W3^T * relu'(h2a)
+  for (int idx = threadIdx.x; idx < U * K; idx += NT) {
+    const int u = idx / K, a = idx - u * K;
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s = fmaf(sP2[r * HP + u], sDa[r * KPAD + a], s);
+    atomicAdd(pg.W3 + idx, s);
+  }
+  if (threadIdx.x < K) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s += sDa[r * KPAD + threadIdx.x];
+    atomicAdd(pg.b3 + threadIdx.x, s);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sP2[r * HP + u];
+    float s = 0.f;
+    if (h > 0.f)
+      for (int a = 0; a < K; ++a) s = fmaf(sDa[r * KPAD + a], pw.W3[u * K + a], s);
+    sP2[r * HP + u] = s;
+  }
+  __syncthreads();
+  backward_hidden<U>(xp, pw, &pg, row0, nrows, sX, sW, sP1, sP2);
+}
+
+}  // namespace mdp
+
+// =============================================================================================
+// host side
+// =============================================================================================
+namespace mdp {
+
+static inline int64_t net_floats(int in, int U, int out) { return (int64_t)in * U + U + (int64_t)U * U + U + (int64_t)U * out + out; }
+
+static MlpW make_w(float* base, int in, int U, int out) {
+  MlpW w;
+  float* p = base;
+  w.W1 = p; p += (size_t)in * U;
+  w.b1 = p; p += U;
+  w.W2 = p; p += (size_t)U * U;
+  w.b2 = p; p += U;
+  w.W3 = p; p += (size_t)U * out;
+  w.b3 = p;
+  w.in = in; w.out = out;
+  return w;
+}
+static MlpG make_g(float* base, int in, int U, int out) {
+  MlpW w = make_w(base, in, U, out);
+  MlpG g;
+  g.W1 = const_cast<float*>(w.W1); g.b1 = const_cast<float*>(w.b1); g.W2 = const_cast<float*>(w.W2);
+  g.b2 = const_cast<float*>(w.b2); g.W3 = const_cast<float*>(w.W3); g.b3 = const_cast<float*>(w.b3);
+  return g;
+}
+
+static CoreDev core_dev(const mdp_core* c) {
+  CoreDev d;
+  d.agents = c->d_agents;
+  d.n_agents = c->cfg.n_agents;
+  d.units = c->cfg.num_units;
+  d.obs_sum = c->obs_sum; d.act_sum = c->act_sum; d.act_stride = c->act_stride;
+  d.gamma = c->cfg.gamma; d.actor_reg = c->cfg.actor_reg;
+  d.adam_t = c->adam_t; d.stats = c->stats;
+  return d;
+}
+
+template <int U>
+static size_t smem_bytes(int extra_floats) { return (size_t)(smem_floats_base<U>() + extra_floats + 64) * sizeof(float); }
+
+template <typename Kern>
+static int set_smem(Kern kern, size_t smem) {
+  if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return MDP_OK;
+}
+
+static int check_lay(const mdp_core* c, const mdp_ring_layout* lay) {
+  MDP_REQUIRE(lay, "null ring layout");
+  MDP_REQUIRE(lay->n_agents == c->cfg.n_agents && lay->obs_sum == c->obs_sum && lay->act_sum == c->act_sum,
+              "ring layout does not match the core (agents %d/%d, obs %d/%d, act %d/%d)", lay->n_agents, c->cfg.n_agents,
+              lay->obs_sum, c->obs_sum, lay->act_sum, c->act_sum);
+  return MDP_OK;
+}
+
+}  // namespace mdp
+
+using namespace mdp;
+
+extern "C" int mdp_core_create(const mdp_core_cfg* cfg, mdp_core** out) {
+  MDP_REQUIRE(cfg && out, "mdp_core_create: null argument");
+  MDP_REQUIRE(cfg->n_agents > 0 && cfg->n_agents <= MDP_MAX_AGENTS, "mdp_core_create: n_agents %d out of range", cfg->n_agents);
+  MDP_REQUIRE(cfg->num_units == 64 || cfg->num_units == 128, "mdp_core_create: num_units must be 64 or 128 (got %d)", cfg->num_units);
+  mdp_core* c = new (std::nothrow) mdp_core();
+  MDP_REQUIRE(c, "mdp_core_create: out of memory");
+  c->cfg = *cfg;
+  memset(&c->lay, 0, sizeof(c->lay));
+  const int n = cfg->n_agents, U = cfg->num_units;
+  int od = 0, ad = 0;
+  for (int i = 0; i < n; ++i) {
+    int hsum = 0;
+    if (!(cfg->n_heads[i] >= 1 && cfg->n_heads[i] <= MDP_MAX_HEADS)) { delete c; return fail(MDP_EINVAL, "agent %d: n_heads %d", i, cfg->n_heads[i]); }
+    for (int h = 0; h < cfg->n_heads[i]; ++h) hsum += cfg->head_dim[i][h];
+    if (hsum != cfg->act_dim[i] || cfg->act_dim[i] > MAXK || cfg->act_dim[i] < 1 || cfg->obs_dim[i] < 1) {
+      delete c;
+      return fail(MDP_EINVAL, "agent %d: act_dim %d (heads sum %d, max %d), obs_dim %d", i, cfg->act_dim[i], hsum, MAXK, cfg->obs_dim[i]);
+    }
+    c->obs_off[i] = od; c->act_off[i] = ad;
+    od += cfg->obs_dim[i]; ad += cfg->act_dim[i];
+  }
+  c->obs_sum = od; c->act_sum = ad; c->act_stride = round_up(ad, 4);
+  int64_t po = 0, to = 0;
+  for (int i = 0; i < n; ++i) {
+    const int q_in = cfg->local_q[i] ? cfg->obs_dim[i] + cfg->act_dim[i] : od + ad;
+    const int ins[4] = {cfg->obs_dim[i], cfg->obs_dim[i], q_in, q_in};
+    const int outs[4] = {cfg->act_dim[i], cfg->act_dim[i], 1, 1};
+    for (int k = 0; k < 4; ++k) {
+      c->lay.net_off[i][k] = po;
+      c->lay.net_in[i][k] = ins[k];
+      c->lay.net_out[i][k] = outs[k];
+      c->lay.net_size[i][k] = net_floats(ins[k], U, outs[k]);
+      po += round_up64(c->lay.net_size[i][k], 4);
+    }
+    c->lay.train_off[i][0] = to; to += round_up64(c->lay.net_size[i][MDP_NET_P], 4);
+    c->lay.train_off[i][1] = to; to += round_up64(c->lay.net_size[i][MDP_NET_Q], 4);
+  }
+  c->lay.total_params = po;
+  c->lay.total_train = to;
+  // SURVEY 8(d) FLOP model per batch row: Fq = C*U + U^2 + U, Fpi_i = D_i*U + U^2 + U*K_i
+  for (int i = 0; i < n; ++i) {
+    const int64_t Cq = c->lay.net_in[i][MDP_NET_Q];
+    const int64_t Fq = Cq * U + (int64_t)U * U + U;
+    int64_t Fpi_all = 0;
+    for (int k = 0; k < n; ++k)
+      if (!cfg->local_q[i] || k == i) Fpi_all += (int64_t)cfg->obs_dim[k] * U + (int64_t)U * U + (int64_t)U * cfg->act_dim[k];
+    const int64_t Fpj = (int64_t)cfg->obs_dim[i] * U + (int64_t)U * U + (int64_t)U * cfg->act_dim[i];
+    c->lay.update_flops_critic[i] = 2 * (3 * Fq + ((int64_t)U * U + U) + Fpi_all);
+    c->lay.update_flops_actor[i] = 2 * (3 * Fpj - (int64_t)cfg->obs_dim[i] * U + Fq + (U + (int64_t)U * U + (int64_t)cfg->act_dim[i] * U));
+  }
+  *out = c;
+  return MDP_OK;
+}
+
+extern "C" int mdp_core_get_layout(const mdp_core* core, mdp_core_layout* out) {
+  MDP_REQUIRE(core && out, "mdp_core_get_layout: null argument");
+  *out = core->lay;
+  return MDP_OK;
+}
+
+extern "C" void mdp_core_destroy(mdp_core* core) {
+  if (!core) return;
+  if (core->d_agents) cudaFree(core->d_agents);
+  delete core;
+}
+
+extern "C" int mdp_core_bind(mdp_core* c, float* params, float* grads, float* adam_m, float* adam_v, int32_t* adam_t,
+                             double* stats) {
+  MDP_REQUIRE(c && params && grads && adam_m && adam_v && adam_t && stats, "mdp_core_bind: null argument");
+  MDP_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)adam_m | (uintptr_t)adam_v) & 15) == 0,
+              "mdp_core_bind: buffers must be 16-byte aligned");
+  c->params = params; c->grads = grads; c->adam_m = adam_m; c->adam_v = adam_v; c->adam_t = adam_t; c->stats = stats;
+  const int n = c->cfg.n_agents, U = c->cfg.num_units;
+  c->h_agents.assign(n, AgentDev());
+  for (int i = 0; i < n; ++i) {
+    AgentDev& a = c->h_agents[i];
+    for (int k = 0; k < 4; ++k) a.net[k] = make_w(params + c->lay.net_off[i][k], c->lay.net_in[i][k], U, c->lay.net_out[i][k]);
+    a.grad[0] = make_g(grads + c->lay.train_off[i][0], c->lay.net_in[i][MDP_NET_P], U, c->lay.net_out[i][MDP_NET_P]);
+    a.grad[1] = make_g(grads + c->lay.train_off[i][1], c->lay.net_in[i][MDP_NET_Q], U, c->lay.net_out[i][MDP_NET_Q]);
+    a.obs_dim = c->cfg.obs_dim[i]; a.act_dim = c->cfg.act_dim[i];
+    a.obs_off = c->obs_off[i]; a.act_off = c->act_off[i];
+    a.n_heads = c->cfg.n_heads[i]; a.head_dim[0] = c->cfg.head_dim[i][0]; a.head_dim[1] = c->cfg.head_dim[i][1];
+    a.local_q = c->cfg.local_q[i]; a.q_in = c->lay.net_in[i][MDP_NET_Q];
+  }
+  if (c->d_agents) cudaFree(c->d_agents);
+  c->d_agents = nullptr;
+  MDP_CUDA(cudaMalloc(&c->d_agents, n * sizeof(AgentDev)));
+  MDP_CUDA(cudaMemcpy(c->d_agents, c->h_agents.data(), n * sizeof(AgentDev), cudaMemcpyHostToDevice));
+  return MDP_OK;
+}
+
+#define MDP_DISPATCH_U(core, expr64, expr128) ((core)->cfg.num_units == 64 ? (expr64) : (expr128))
+
+extern "C" int mdp_actor_act(mdp_core* c, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
+                             const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u,
+                             uint64_t seed, uint64_t counter, float* logits_out, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_actor_act: core not bound");
+  MDP_REQUIRE(obs && act && E > 0 && agent_count > 0 && agent_begin >= 0 && agent_begin + agent_count <= c->cfg.n_agents,
+              "mdp_actor_act: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CoreDev d = core_dev(c);
+  dim3 grid(cdiv(E, TM), agent_count);
+  auto go = [&](auto kern, size_t smem) -> int {
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<grid, NT, smem, st>>>(d, agent_begin, use_target, E, obs, obs_stride, act, act_stride, u, seed, counter, logits_out);
+    return check_launch("k_actor_act");
+  };
+  return MDP_DISPATCH_U(c, go(k_actor_act<64>, smem_bytes<64>(2 * TM * KPAD)), go(k_actor_act<128>, smem_bytes<128>(2 * TM * KPAD)));
+}
+
+extern "C" int mdp_critic_q(mdp_core* c, int32_t agent, int32_t use_target, int32_t B, const float* x, int32_t x_stride,
+                            float* q_out, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_critic_q: core not bound");
+  MDP_REQUIRE(x && q_out && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_critic_q: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CoreDev d = core_dev(c);
+  auto go = [&](auto kern, size_t smem) -> int {
+    int rc = set_smem(kern, smem);
+    if (rc) return rc;
+    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, use_target, B, x, x_stride, q_out);
+    return check_launch("k_critic_q");
+  };
+  return MDP_DISPATCH_U(c, go(k_critic_q<64>, smem_bytes<64>(TM)), go(k_critic_q<128>, smem_bytes<128>(TM)));
+}
+
+extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                             const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter, float* y_out,
+                             float* target_act_out, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_td_target: core not bound");
+  int rc = check_lay(c, lay);
+  if (rc) return rc;
+  MDP_REQUIRE(batch && y_out && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_td_target: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double), st));
+  CoreDev d = core_dev(c);
+  const int extra = TM * KPAD + TM + TM * (c->act_stride | 1);
+  auto go = [&](auto kern, size_t smem) -> int {
+    int rc2 = set_smem(kern, smem);
+    if (rc2) return rc2;
+    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, *lay, B, batch, u_target, u_stride, seed, counter, y_out, target_act_out);
+    return check_launch("k_td_target");
+  };
+  return MDP_DISPATCH_U(c, go(k_td_target<64>, smem_bytes<64>(extra)), go(k_td_target<128>, smem_bytes<128>(extra)));
+}
+
+extern "C" int mdp_critic_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                                const float* y, float* q_out, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_critic_grads: core not bound");
+  int rc = check_lay(c, lay);
+  if (rc) return rc;
+  MDP_REQUIRE(batch && y && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_critic_grads: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CoreDev d = core_dev(c);
+  auto go = [&](auto kern, size_t smem) -> int {
+    int rc2 = set_smem(kern, smem);
+    if (rc2) return rc2;
+    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, *lay, B, batch, y, q_out);
+    return check_launch("k_critic_grads");
+  };
+  return MDP_DISPATCH_U(c, go(k_critic_grads<64>, smem_bytes<64>(2 * TM)), go(k_critic_grads<128>, smem_bytes<128>(2 * TM)));
+}
+
+extern "C" int mdp_actor_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                               const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_actor_grads: core not bound");
+  int rc = check_lay(c, lay);
+  if (rc) return rc;
+  MDP_REQUIRE(batch && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_actor_grads: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  CoreDev d = core_dev(c);
+  auto go = [&](auto kern, size_t smem) -> int {
+    int rc2 = set_smem(kern, smem);
+    if (rc2) return rc2;
+    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, *lay, B, batch, u_actor, u_stride, seed, counter);
+    return check_launch("k_actor_grads");
+  };
+  const int extra64 = 2 * TM * (64 + 4) + 3 * TM * KPAD + TM, extra128 = 2 * TM * (128 + 4) + 3 * TM * KPAD + TM;
+  return MDP_DISPATCH_U(c, go(k_actor_grads<64>, smem_bytes<64>(extra64)), go(k_actor_grads<128>, smem_bytes<128>(extra128)));
+}
+
+extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                                const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
+                                uint64_t counter, float* y_scratch, void* stream) {
+  int rc = mdp_td_target(c, agent, lay, B, batch, u_target, u_stride, seed, counter, y_scratch, nullptr, stream);
+  if (rc) return rc;
+  rc = mdp_critic_grads(c, agent, lay, B, batch, y_scratch, nullptr, stream);
+  if (rc) return rc;
+  rc = mdp_clip_adam_polyak(c, agent, 1, 1.0f, 1, stream);
+  if (rc) return rc;
+  rc = mdp_actor_grads(c, agent, lay, B, batch, u_actor, u_stride, seed, counter, stream);
+  if (rc) return rc;
+  return mdp_clip_adam_polyak(c, agent, 0, 1.0f, 1, stream);
+}

@@ -1,0 +1,207 @@
+"""Batched MPE environment: the reference-facing mirror of ``multiagent.environment.MultiAgentEnv``.
+
+The reference builds its env at experiments/train.py:48-61 (``scenarios.load(name + ".py").Scenario()``,
+``MultiAgentEnv(world, reset_world, reward, observation)``) and drives it with ``env.reset()``
+(:104,:128) and ``env.step(action_n)`` (:114).  ``BatchedMultiAgentEnv`` keeps that surface --
+``n``, ``observation_space[i].shape``, ``action_space[i]``, ``reset()``, ``step(action_n)`` -- over
+``num_envs`` lockstep instances whose physics runs in one fused CUDA kernel (csrc/mdp_env.cu).
+
+* ``num_envs == 1`` (the reference's shape): numpy in, numpy out, shapes ``(D_i,)`` / scalars, so
+  experiments/train.py's loop runs unmodified apart from its imports.
+* ``num_envs > 1``: every per-agent array gains a leading env axis and is a CUDA ``torch.Tensor``
+  (views into the joint device arrays described in include/maddpg_b200.h).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spaces import Box, Discrete, MultiDiscrete
+
+SCENARIOS = ("simple", "simple_spread", "simple_tag", "simple_world_comm")
+
+
+def _dims_for(scenario, num_agents=None, state_f64=False):
+    cfg = _lib.EnvCfg(_lib.SCENARIO_IDS[scenario], int(num_agents or 0), int(bool(state_f64)))
+    h = C.c_void_p()
+    _lib.check(_lib.lib.mdp_env_create(C.byref(cfg), C.byref(h)), "mdp_env_create")
+    d = _lib.EnvDims()
+    _lib.check(_lib.lib.mdp_env_get_dims(h, C.byref(d)), "mdp_env_get_dims")
+    return h, d
+
+
+class BatchedMultiAgentEnv(object):
+    def __init__(self, scenario, num_envs=1, num_agents=None, device="cuda", state_dtype=torch.float32, seed=0,
+                 squeeze=None):
+        if scenario.endswith(".py"):
+            scenario = scenario[:-3]
+        if scenario not in _lib.SCENARIO_IDS:
+            raise NotImplementedError("scenario %r is not implemented (have %s)" % (scenario, SCENARIOS))
+        assert state_dtype in (torch.float32, torch.float64)
+        self.scenario_name = scenario
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        self.state_dtype = state_dtype
+        self.seed = int(seed)
+        self.squeeze = (self.num_envs == 1) if squeeze is None else bool(squeeze)
+        self._h, d = _dims_for(scenario, num_agents, state_dtype == torch.float64)
+        self.dims = d
+        self.n = int(d.n_agents)
+        self.obs_dims = [int(d.obs_dim[i]) for i in range(self.n)]
+        self.act_dims = [int(d.act_dim[i]) for i in range(self.n)]
+        self.obs_off = [int(d.obs_off[i]) for i in range(self.n)]
+        self.act_off = [int(d.act_off[i]) for i in range(self.n)]
+        self.obs_stride, self.act_stride = int(d.obs_stride), int(d.act_stride)
+        self.state_comps = int(d.state_comps)
+        self.comm_dim = int(d.comm_dim)
+        self.n_landmarks = int(d.n_landmarks)
+        self.env_bytes_per_step = int(d.env_bytes_per_step)
+        self.observation_space = [Box(-np.inf, np.inf, (D,)) for D in self.obs_dims]
+        self.action_space = []
+        for i in range(self.n):
+            if d.n_heads[i] == 1:
+                self.action_space.append(Discrete(d.head_dim[i][0]))
+            else:
+                self.action_space.append(MultiDiscrete([[0, int(d.head_dim[i][h]) - 1] for h in range(d.n_heads[i])]))
+        E = self.num_envs
+        dev = self.device
+        self.state = torch.zeros((self.state_comps, E), dtype=state_dtype, device=dev)
+        self._obs = [torch.zeros((E, self.obs_stride), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._cur = 0
+        self.act = torch.zeros((E, self.act_stride), dtype=torch.float32, device=dev)
+        self.rew = torch.zeros((E, self.n), dtype=torch.float32, device=dev)
+        self.done = torch.zeros((E, self.n), dtype=torch.uint8, device=dev)
+        self.episode = 0
+        # pinned staging for the numpy (reference-shaped) path: one H2D and one D2H copy per step
+        self._h_act = torch.zeros((E, self.act_stride), dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
+        self._h_out = torch.zeros((E, self.obs_stride + self.n), dtype=torch.float32).pin_memory() if dev.type == "cuda" else None
+        self._d_out = torch.zeros((E, self.obs_stride + self.n), dtype=torch.float32, device=dev)
+
+    def __del__(self):
+        try:
+            _lib.lib.mdp_env_destroy(self._h)
+        except Exception:
+            pass
+
+    # -- joint device views ------------------------------------------------------------------
+    @property
+    def obs(self):
+        """Current joint observation array (E, obs_stride)."""
+        return self._obs[self._cur]
+
+    def _split_obs(self, joint):
+        return [joint[:, o:o + D] for o, D in zip(self.obs_off, self.obs_dims)]
+
+    def _obs_out(self):
+        if not self.squeeze:
+            return self._split_obs(self.obs)
+        host = self.obs.cpu().numpy()
+        return [host[0, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]
+
+    # -- state injection (parity tests) ------------------------------------------------------
+    def state_from_arrays(self, agent_pos, agent_vel, landmark_pos, agent_c=None):
+        """(E,A,2), (E,A,2), (E,L,2)[, (E,A,dim_c)] -> SoA state tensor [comp][E] (see header)."""
+        A, L, E = self.n, self.n_landmarks, self.num_envs
+        s = np.zeros((self.state_comps, E), dtype=np.float64)
+        ap, av, lp = (np.asarray(x, np.float64) for x in (agent_pos, agent_vel, landmark_pos))
+        for i in range(A):
+            s[4 * i + 0], s[4 * i + 1] = ap[:, i, 0], ap[:, i, 1]
+            s[4 * i + 2], s[4 * i + 3] = av[:, i, 0], av[:, i, 1]
+        if self.comm_dim and agent_c is not None:
+            for k in range(self.comm_dim):
+                s[4 * A + k] = np.asarray(agent_c, np.float64)[:, 0, k]  # the only speaker is agent 0
+        for l in range(L):
+            s[4 * A + self.comm_dim + 2 * l + 0] = lp[:, l, 0]
+            s[4 * A + self.comm_dim + 2 * l + 1] = lp[:, l, 1]
+        return torch.from_numpy(s).to(self.state_dtype).to(self.device)
+
+    def state_to_arrays(self):
+        A, L = self.n, self.n_landmarks
+        s = self.state.detach().cpu().double().numpy()
+        ap = np.stack([np.stack([s[4 * i], s[4 * i + 1]], -1) for i in range(A)], 1)
+        av = np.stack([np.stack([s[4 * i + 2], s[4 * i + 3]], -1) for i in range(A)], 1)
+        b = 4 * A + self.comm_dim
+        lp = np.stack([np.stack([s[b + 2 * l], s[b + 2 * l + 1]], -1) for l in range(L)], 1)
+        return dict(agent_pos=ap, agent_vel=av, landmark_pos=lp, comm=s[4 * A:b].T.copy())
+
+    # -- reference surface -------------------------------------------------------------------
+    def reset(self, init_state=None):
+        """``env.reset()`` (train.py:104,128): new positions (Philox on device) or an injected SoA
+        state tensor; returns the list of per-agent observations."""
+        if init_state is not None:
+            assert init_state.shape == self.state.shape and init_state.dtype == self.state_dtype
+            init_state = init_state.contiguous()
+        self._cur ^= 1
+        _lib.check(_lib.lib.mdp_env_reset(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(init_state),
+                                          self.seed, self.episode, _lib.ptr(self.obs), _lib.current_stream()),
+                   "mdp_env_reset")
+        self.episode += 1
+        return self._obs_out()
+
+    def step_device(self, act_joint=None, ring=None):
+        """One lockstep step on device arrays only.  ``act_joint`` defaults to ``self.act``.  When a
+        ``JointReplayRing`` is given, the transition rows are inserted by the same call."""
+        act = self.act if act_joint is None else act_joint
+        prev = self.obs
+        self._cur ^= 1
+        if ring is None:
+            rc = _lib.lib.mdp_env_step(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(act), _lib.ptr(self.obs),
+                                       _lib.ptr(self.rew), _lib.ptr(self.done), None, None, 0, 0, 0, _lib.current_stream())
+        else:
+            cursor = ring.reserve_joint(self.num_envs)
+            rc = _lib.lib.mdp_env_step(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(act), _lib.ptr(self.obs),
+                                       _lib.ptr(self.rew), _lib.ptr(self.done), _lib.ptr(prev), _lib.ptr(ring.ring),
+                                       ring.capacity, ring.row_stride, cursor, _lib.current_stream())
+        _lib.check(rc, "mdp_env_step")
+
+    def step(self, action_n):
+        """``env.step(action_n)`` (train.py:114) -> (obs_n, rew_n, done_n, info_n)."""
+        assert len(action_n) == self.n
+        if self.squeeze:
+            h = self._h_act
+            for i, a in enumerate(action_n):
+                h[0, self.act_off[i]:self.act_off[i] + self.act_dims[i]] = torch.from_numpy(
+                    np.asarray(a, dtype=np.float32).reshape(-1))
+            self.act.copy_(h, non_blocking=True)
+        elif isinstance(action_n[0], torch.Tensor) and action_n[0].is_cuda:
+            for i, a in enumerate(action_n):
+                dst = self.act[:, self.act_off[i]:self.act_off[i] + self.act_dims[i]]
+                if a.data_ptr() != dst.data_ptr():
+                    dst.copy_(a)
+        else:  # host arrays with a leading env axis: one pinned staging buffer, one H2D copy
+            h = self._h_act
+            for i, a in enumerate(action_n):
+                h[:, self.act_off[i]:self.act_off[i] + self.act_dims[i]] = torch.as_tensor(np.asarray(a, dtype=np.float32))
+            self.act.copy_(h, non_blocking=True)
+        self.step_device()
+        host_io = self.squeeze or not (isinstance(action_n[0], torch.Tensor) and action_n[0].is_cuda)
+        if not host_io:
+            obs_n = self._split_obs(self.obs)
+            return obs_n, [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)], {"n": [{}] * self.n}
+        # one packed D2H copy: [obs | rew]; done is identically False in MPE (no done callback)
+        self._d_out[:, :self.obs_stride].copy_(self.obs)
+        self._d_out[:, self.obs_stride:].copy_(self.rew)
+        self._h_out.copy_(self._d_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host = self._h_out.numpy()
+        if self.squeeze:
+            obs_n = [host[0, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]
+            rew_n = [float(host[0, self.obs_stride + i]) for i in range(self.n)]
+            done_n = [False] * self.n
+        else:
+            obs_n = [host[:, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]
+            rew_n = [host[:, self.obs_stride + i].copy() for i in range(self.n)]
+            done_n = [np.zeros(self.num_envs, dtype=bool) for _ in range(self.n)]
+        return obs_n, rew_n, done_n, {"n": [{} for _ in range(self.n)]}
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is out of scope for the batched device environment")
+
+
+def make_env(scenario_name, arglist=None, benchmark=False, **kw):
+    """experiments/train.py:48-61 equivalent."""
+    if arglist is not None:
+        kw.setdefault("num_envs", getattr(arglist, "num_envs", 1))
+        kw.setdefault("seed", getattr(arglist, "seed", 0))
+    return BatchedMultiAgentEnv(scenario_name, **kw)

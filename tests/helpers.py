@@ -1,0 +1,160 @@
+"""Shared builders for the parity tests: seeded env cases and trainer cases driven through the
+oracle (oracle/) -- the CUDA path is checked against these on the same inputs."""
+import argparse
+
+import numpy as np
+
+from oracle import maddpg as omaddpg
+from oracle import mpe as ompe
+
+ENV_CASES = {
+    # name: (scenario, num_agents, E, T)
+    "simple": ("simple", None, 16, 25),
+    "simple_spread": ("simple_spread", 3, 16, 25),
+    "simple_tag": ("simple_tag", None, 16, 25),
+    "simple_world_comm": ("simple_world_comm", None, 8, 25),
+    "simple_spread_24": ("simple_spread", 24, 2, 4),
+}
+
+
+def soft_actions(rng, E, K, heads=None, sharp=2.0):
+    """(E, K) float32 rows that look like Gumbel-softmax samples (each head sums to 1)."""
+    z = rng.randn(E, K) * sharp
+    out = np.empty((E, K), np.float32)
+    o = 0
+    for h in (heads or [K]):
+        zz = z[:, o:o + h]
+        e = np.exp(zz - zz.max(1, keepdims=True))
+        out[:, o:o + h] = (e / e.sum(1, keepdims=True)).astype(np.float32)
+        o += h
+    return out
+
+
+def env_case(name, seed=0, crowd=0.45):
+    """Seeded initial state (crowded so that contacts and collisions happen) + action tape."""
+    scenario, na, E, T = ENV_CASES[name]
+    rng = np.random.RandomState(seed)
+    env = ompe.BatchedOracleEnv(scenario, E, na, seed=seed)
+    A, L = env.n, len(env.envs[0].world.landmarks)
+    agent_pos = rng.uniform(-crowd, crowd, size=(E, A, 2))
+    agent_vel = rng.uniform(-0.3, 0.3, size=(E, A, 2))
+    landmark_pos = rng.uniform(-crowd, crowd, size=(E, L, 2))
+    dim_c = env.envs[0].world.dim_c
+    agent_c = np.zeros((E, A, dim_c))
+    heads = [omaddpg.act_heads(s) for s in env.action_space]
+    tape = [[soft_actions(rng, E, env.act_dims[i], heads[i]) for i in range(A)] for _ in range(T)]
+    return dict(scenario=scenario, num_agents=na, E=E, T=T, env=env, agent_pos=agent_pos, agent_vel=agent_vel,
+                landmark_pos=landmark_pos, agent_c=agent_c, tape=tape, heads=heads)
+
+
+def run_oracle_rollout(case):
+    env = case["env"]
+    env.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    obs0 = env.observe()
+    obs_t, rew_t = [], []
+    for acts in case["tape"]:
+        o, r, d = env.step(acts)
+        assert not d.any()
+        obs_t.append(np.concatenate(o, axis=1))
+        rew_t.append(r)
+    return dict(obs0=np.concatenate(obs0, axis=1), obs=np.stack(obs_t), rew=np.stack(rew_t), final=env.get_state())
+
+
+# ------------------------------------------------------------------------------------------------
+TRAINER_CASES = {
+    # name: (scenario, num_agents, units, B, local_q per agent or None)
+    "simple": ("simple", None, 64, 96, None),
+    "simple_spread": ("simple_spread", 3, 64, 160, None),
+    "simple_tag": ("simple_tag", None, 64, 100, None),
+    "simple_world_comm": ("simple_world_comm", None, 128, 64, None),
+    "simple_tag_ddpg_adv": ("simple_tag", None, 64, 64, [True, True, True, False]),
+    "simple_spread_6": ("simple_spread", 6, 64, 48, None),
+}
+
+
+def make_args(units, batch_size, lr=1e-2, gamma=0.95, max_episode_len=25):
+    return argparse.Namespace(lr=lr, gamma=gamma, batch_size=batch_size, num_units=units,
+                              max_episode_len=max_episode_len)
+
+
+def trainer_case(name, seed=0, rows=None):
+    """Oracle trainers with seeded weights + a seeded pool of transitions + noise tapes."""
+    scenario, na, units, B, local_q = TRAINER_CASES[name]
+    rng = np.random.RandomState(1000 + seed)
+    env = ompe.make_env(scenario, np.random.RandomState(seed), na)
+    n = env.n
+    obs_shape_n = [s.shape for s in env.observation_space]
+    args = make_args(units, B)
+    local_q = local_q or [False] * n
+    trainers = [omaddpg.OracleAgentTrainer("agent_%d" % i, None, obs_shape_n, env.action_space, i, args,
+                                           local_q_func=local_q[i], rng=np.random.RandomState(seed * 100 + i))
+                for i in range(n)]
+    for tr in trainers:  # non-zero biases so that bias paths are exercised
+        for net in (tr.q, tr.target_q, tr.p, tr.target_p):
+            for k in (1, 3, 5):
+                net.p[k][...] = rng.uniform(-0.1, 0.1, size=net.p[k].shape).astype(np.float32)
+    rows = rows or (B * 2 + 7)
+    obs_dims = [s[0] for s in obs_shape_n]
+    act_dims = trainers[0].act_dims
+    heads = trainers[0].heads_n
+    pool = dict(
+        obs=[rng.randn(rows, D).astype(np.float32) for D in obs_dims],
+        act=[soft_actions(rng, rows, K, h) for K, h in zip(act_dims, heads)],
+        rew=[rng.randn(rows).astype(np.float32) for _ in range(n)],
+        nobs=[rng.randn(rows, D).astype(np.float32) for D in obs_dims],
+        done=[(rng.rand(rows) < 0.15).astype(np.float32) for _ in range(n)],
+    )
+    idx = [rng.randint(0, rows, size=B).tolist() for _ in range(n)]
+    u_target = [rng.uniform(1e-6, 1.0, size=(B, sum(act_dims))).astype(np.float32) for _ in range(n)]
+    u_actor = [rng.uniform(1e-6, 1.0, size=(B, act_dims[j])).astype(np.float32) for j in range(n)]
+    return dict(name=name, n=n, units=units, B=B, local_q=local_q, env=env, args=args, trainers=trainers,
+                obs_dims=obs_dims, act_dims=act_dims, heads=heads, pool=pool, idx=idx, u_target=u_target,
+                u_actor=u_actor, rows=rows, obs_shape_n=obs_shape_n)
+
+
+def fill_oracle_replay(case):
+    p = case["pool"]
+    for i, tr in enumerate(case["trainers"]):
+        for r in range(case["rows"]):
+            tr.replay_buffer.add(p["obs"][i][r].astype(np.float64), p["act"][i][r], float(p["rew"][i][r]),
+                                 p["nobs"][i][r].astype(np.float64), float(p["done"][i][r]))
+
+
+class NoiseTape(object):
+    """Feeds the oracle's ``noise(shape)`` calls from pre-drawn arrays, in call order."""
+
+    def __init__(self):
+        self.queue = []
+
+    def push(self, arr):
+        self.queue.append(np.asarray(arr, np.float32))
+
+    def __call__(self, shape):
+        a = self.queue.pop(0)
+        assert tuple(a.shape) == tuple(shape), (a.shape, shape)
+        return a
+
+
+def oracle_update_round(case):
+    """Sequential update of every agent (train.py:160-161) with injected indices / noise.
+    Returns per-agent dicts of everything the CUDA path is compared against."""
+    trainers, n = case["trainers"], case["n"]
+    fill_oracle_replay(case)
+    tape = NoiseTape()
+    for tr in trainers:
+        tr.noise = tape
+        tr.max_replay_buffer_len = 0
+    out = []
+    off = np.concatenate([[0], np.cumsum(case["act_dims"])]).astype(int)
+    for j, tr in enumerate(trainers):
+        ut = case["u_target"][j]
+        for i in range(n):  # target_act of every agent, in agent order (maddpg.py:184)
+            tape.push(ut[:, off[i]:off[i + 1]])
+        tape.push(case["u_actor"][j])  # p_train's sample (maddpg.py:49)
+        stats = tr.update(trainers, 100, index=case["idx"][j])
+        assert not tape.queue
+        out.append(dict(stats=stats, y=tr.last_target_q.astype(np.float32),
+                        q_grads=tr.last_grads["q"], p_grads=tr.last_grads["p"],
+                        q=[x.copy() for x in tr.q.p], p=[x.copy() for x in tr.p.p],
+                        target_q=[x.copy() for x in tr.target_q.p], target_p=[x.copy() for x in tr.target_p.p]))
+    return out

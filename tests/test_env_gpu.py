@@ -1,0 +1,167 @@
+"""CUDA env kernel (through the C ABI) against the MPE oracle on the same injected states/actions.
+Tolerance from BASELINE.json north_star: observations and rewards within 1e-5 relative after a
+fixed-seed rollout (absolute floor 1e-5 for entries that pass through zero)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import ENV_CASES, env_case, run_oracle_rollout, soft_actions
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-5, 1e-5
+
+
+def _make(case, dtype):
+    from maddpg_b200 import BatchedMultiAgentEnv
+    env = BatchedMultiAgentEnv(case["scenario"], num_envs=case["E"], num_agents=case["num_agents"],
+                               state_dtype=dtype, squeeze=False)
+    assert env.obs_dims == case["env"].obs_dims and env.act_dims == case["env"].act_dims
+    return env
+
+
+def _joint_act(env, acts):
+    a = torch.zeros((env.num_envs, env.act_stride), dtype=torch.float32)
+    for i, x in enumerate(acts):
+        a[:, env.act_off[i]:env.act_off[i] + env.act_dims[i]] = torch.from_numpy(x)
+    return a.cuda()
+
+
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_rollout_f64_state_matches_oracle(name):
+    case = env_case(name, seed=11)
+    ref = run_oracle_rollout(case)
+    env = _make(case, torch.float64)
+    init = env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    obs0 = torch.cat(env.reset(init_state=init), dim=1).cpu().numpy()
+    np.testing.assert_allclose(obs0, ref["obs0"], rtol=RTOL, atol=ATOL)
+    for t, acts in enumerate(case["tape"]):
+        env.step_device(_joint_act(env, acts))
+        obs = env.obs[:, :sum(env.obs_dims)].cpu().numpy()
+        np.testing.assert_allclose(obs, ref["obs"][t], rtol=RTOL, atol=ATOL, err_msg="obs step %d" % t)
+        np.testing.assert_allclose(env.rew.cpu().numpy(), ref["rew"][t], rtol=RTOL, atol=ATOL, err_msg="rew step %d" % t)
+        assert int(env.done.sum()) == 0
+    st = env.state_to_arrays()
+    np.testing.assert_allclose(st["agent_pos"], ref["final"]["agent_pos"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(st["agent_vel"], ref["final"]["agent_vel"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_single_steps_f32_state_match_oracle(name):
+    """float32 state (throughput mode): every step restarts from the oracle's float64 state, so the
+    comparison isolates one step of float32 arithmetic."""
+    case = env_case(name, seed=5)
+    oenv = case["env"]
+    oenv.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    env = _make(case, torch.float32)
+    for t, acts in enumerate(case["tape"][:10]):
+        st = oenv.get_state()
+        init = env.state_from_arrays(st["agent_pos"], st["agent_vel"], st["landmark_pos"], st["agent_c"])
+        env.reset(init_state=init)
+        o, r, d = oenv.step(acts)
+        env.step_device(_joint_act(env, acts))
+        obs = env.obs[:, :sum(env.obs_dims)].cpu().numpy()
+        np.testing.assert_allclose(obs, np.concatenate(o, 1), rtol=1e-4, atol=2e-5, err_msg="obs step %d" % t)
+        # rewards jump by +-1/5/10 at contact thresholds; float32 may legitimately flip an exact tie
+        bad = ~np.isclose(env.rew.cpu().numpy(), r, rtol=1e-4, atol=1e-4)
+        assert bad.mean() < 0.02, "rew step %d: %d mismatches" % (t, bad.sum())
+
+
+@pytest.mark.parametrize("name", ["simple_spread", "simple_tag", "simple_world_comm"])
+def test_device_reset_ranges_and_obs(name):
+    from maddpg_b200 import BatchedMultiAgentEnv
+    from oracle import mpe
+    scenario, na, _, _ = ENV_CASES[name]
+    E = 64
+    env = BatchedMultiAgentEnv(scenario, num_envs=E, num_agents=na, state_dtype=torch.float64, squeeze=False, seed=3)
+    obs = torch.cat(env.reset(), 1).cpu().numpy()
+    st = env.state_to_arrays()
+    lo, hi = (-1.0, 1.0) if name == "simple_spread" else (-0.9, 0.9)
+    assert st["agent_pos"].min() >= -1 and st["agent_pos"].max() < 1
+    assert st["landmark_pos"].min() >= lo and st["landmark_pos"].max() < hi
+    assert np.all(st["agent_vel"] == 0)
+    assert st["agent_pos"].std() > 0.4  # actually random
+    oenv = mpe.BatchedOracleEnv(scenario, E, na)
+    oenv.set_state(st["agent_pos"], st["agent_vel"], st["landmark_pos"])
+    np.testing.assert_allclose(obs, np.concatenate(oenv.observe(), 1), rtol=RTOL, atol=ATOL)
+    obs2 = torch.cat(env.reset(), 1).cpu().numpy()  # next episode draws new positions
+    assert not np.allclose(obs, obs2)
+
+
+def test_full_size_properties_spread_4096():
+    """BASELINE config 2 size: translation equivariance of observations, shared reward equality,
+    run-to-run determinism."""
+    from maddpg_b200 import BatchedMultiAgentEnv
+    E = 4096
+    rng = np.random.RandomState(0)
+    env = BatchedMultiAgentEnv("simple_spread", num_envs=E, state_dtype=torch.float32, squeeze=False)
+    ap, av, lp = rng.uniform(-1, 1, (E, 3, 2)), rng.uniform(-.2, .2, (E, 3, 2)), rng.uniform(-1, 1, (E, 3, 2))
+    acts = [soft_actions(rng, E, 5) for _ in range(3)]
+    a = _joint_act(env, acts)
+
+    def run(shift):
+        env.reset(init_state=env.state_from_arrays(ap + shift, av, lp + shift))
+        env.step_device(a)
+        return env.obs.cpu().numpy().copy(), env.rew.cpu().numpy().copy()
+
+    o0, r0 = run(0.0)
+    o1, r1 = run(0.0)
+    assert np.array_equal(o0, o1) and np.array_equal(r0, r1)
+    o2, r2 = run(0.25)
+    mask = np.ones(56, bool)
+    for i in range(3):
+        mask[18 * i + 2:18 * i + 4] = False  # absolute p_pos columns shift, everything else is relative
+    np.testing.assert_allclose(o2[:, mask], o0[:, mask], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(r2, r0, rtol=1e-5, atol=1e-5)
+    assert np.all(r0[:, 0] == r0[:, 1]) and np.all(r0[:, 1] == r0[:, 2])
+    assert np.all(o0[:, 54:] == 0)
+
+
+def test_numpy_single_env_surface_matches_oracle():
+    """num_envs=1: numpy in / numpy out with the reference's shapes (train.py:104-120)."""
+    from maddpg_b200 import make_env
+    case = env_case("simple_tag", seed=2)
+    env = make_env("simple_tag", state_dtype=torch.float64)
+    assert env.n == 4 and [s.shape for s in env.observation_space] == [(16,), (16,), (16,), (14,)]
+    assert all(s.n == 5 for s in env.action_space)
+    init = env.state_from_arrays(case["agent_pos"][:1], case["agent_vel"][:1], case["landmark_pos"][:1])
+    obs_n = env.reset(init_state=init)
+    assert isinstance(obs_n[0], np.ndarray) and obs_n[0].shape == (16,) and obs_n[3].shape == (14,)
+    from oracle import mpe
+    o = mpe.BatchedOracleEnv("simple_tag", 1)
+    o.set_state(case["agent_pos"][:1], case["agent_vel"][:1], case["landmark_pos"][:1])
+    for t in range(5):
+        acts = [case["tape"][t][i][0] for i in range(4)]
+        obs_n, rew_n, done_n, info_n = env.step(acts)
+        oo, rr, dd = o.step([a[None] for a in acts])
+        assert isinstance(rew_n[0], float) and done_n == [False] * 4 and "n" in info_n
+        for i in range(4):
+            np.testing.assert_allclose(obs_n[i], oo[i][0], rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(rew_n[i], rr[0][i], rtol=RTOL, atol=ATOL)
+
+
+def test_step_with_fused_ring_insert():
+    from maddpg_b200 import BatchedMultiAgentEnv, JointReplayRing
+    E = 96
+    rng = np.random.RandomState(1)
+    env = BatchedMultiAgentEnv("simple_tag", num_envs=E, squeeze=False)
+    ring = JointReplayRing(env.obs_dims, env.act_dims, capacity=250)
+    env.reset()
+    rows = []
+    for t in range(4):  # 4 * 96 = 384 rows into 250: wraps
+        prev = env.obs.clone()
+        a = _joint_act(env, [soft_actions(rng, E, 5) for _ in range(4)])
+        env.step_device(a, ring=ring)
+        row = torch.zeros((E, ring.row_stride))
+        L = ring.layout
+        row[:, :L.obs_sum] = prev[:, :L.obs_sum].cpu()
+        row[:, L.obs_sum:L.x_dim] = a[:, :L.act_sum].cpu()
+        row[:, L.nx_off:L.nx_off + L.obs_sum] = env.obs[:, :L.obs_sum].cpu()
+        row[:, L.rw_off:L.rw_off + 4] = env.rew.cpu()
+        rows.append(row)
+    assert ring.length == [250] * 4 and ring.next_idx == [384 % 250] * 4
+    allrows = torch.cat(rows)
+    got = ring.ring.cpu()
+    L = ring.layout
+    used = list(range(0, L.x_dim)) + list(range(L.nx_off, L.nx_off + L.obs_sum)) + list(range(L.rw_off, L.dn_off + 4))
+    for k in range(384 - 250, 384):
+        assert torch.equal(got[k % 250, used], allrows[k, used]), k

@@ -1,0 +1,132 @@
+"""oracle/maddpg.py cross-checked against torch autograd (float64) and the reference's own polyak
+invariant (reference tests/test_policy.py:71-86, tests/test_critic.py:67-81)."""
+import numpy as np
+import torch
+
+from oracle import maddpg as om
+from tests.helpers import NoiseTape, fill_oracle_replay, trainer_case
+
+
+def _t(params):
+    return [torch.tensor(p, dtype=torch.float64, requires_grad=True) for p in params]
+
+
+def _mlp(p, x):
+    h = torch.relu(x @ p[0] + p[1])
+    h = torch.relu(h @ p[2] + p[3])
+    return h @ p[4] + p[5]
+
+
+def _gs(logits, u, heads):
+    z = logits - torch.log(-torch.log(u))
+    outs, o = [], 0
+    for h in heads:
+        outs.append(torch.softmax(z[:, o:o + h], dim=1))
+        o += h
+    return torch.cat(outs, dim=1)
+
+
+def _check_case(name):
+    case = trainer_case(name, seed=3)
+    n, B = case["n"], case["B"]
+    fill_oracle_replay(case)
+    trainers = case["trainers"]
+    j = n - 1
+    tr = trainers[j]
+    idx = case["idx"][j]
+    obs_n, act_n, nobs_n = [], [], []
+    for i in range(n):
+        o, a, r, n2, d = trainers[i].replay_buffer.sample_index(idx)
+        obs_n.append(o), act_n.append(a), nobs_n.append(n2)
+    _, _, rew, _, done = tr.replay_buffer.sample_index(idx)
+    off = np.concatenate([[0], np.cumsum(case["act_dims"])]).astype(int)
+    ut, ua = case["u_target"][j], case["u_actor"][j]
+    # ---- torch float64 reference of the same graph, from the pre-update weights
+    q, tq, p = _t(tr.q.p), _t(tr.target_q.p), _t(tr.p.p)
+    tps = [_t(t.target_p.p) for t in trainers]
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    ta = [_gs(_mlp(tps[i], T(nobs_n[i])), T(ut[:, off[i]:off[i + 1]]), case["heads"][i]) for i in range(n)]
+    if case["local_q"][j]:
+        xq_next = torch.cat([T(nobs_n[j]), ta[j]], 1)
+        xq = torch.cat([T(obs_n[j]), T(act_n[j])], 1)
+    else:
+        xq_next = torch.cat([T(x) for x in nobs_n] + ta, 1)
+        xq = torch.cat([T(x) for x in obs_n] + [T(a) for a in act_n], 1)
+    qn = _mlp(tq, xq_next)[:, 0]
+    y = (T(rew) + 0.95 * (1 - T(done)) * qn).detach()
+    q_loss = torch.mean((_mlp(q, xq)[:, 0] - y) ** 2)
+    gq = torch.autograd.grad(q_loss, q)
+    # ---- oracle step
+    tape = NoiseTape()
+    for t_ in trainers:
+        t_.noise = tape
+        t_.max_replay_buffer_len = 0
+    for i in range(n):
+        tape.push(ut[:, off[i]:off[i + 1]])
+    tape.push(ua)
+    stats = tr.update(trainers, 100, index=idx)
+    assert np.allclose(tr.last_target_q, y.numpy(), rtol=2e-5, atol=2e-6)
+    assert np.isclose(stats[0], q_loss.item(), rtol=1e-4)
+    for g_o, g_t in zip(tr.last_grads["q"], gq):
+        assert np.allclose(g_o, g_t.numpy(), rtol=2e-3, atol=2e-6)
+    # actor loss goes through the critic AFTER its Adam step (maddpg.py:188 then :191)
+    q2 = _t(tr.q.p)
+    logits = _mlp(p, T(obs_n[j]))
+    a_hat = _gs(logits, T(ua), case["heads"][j])
+    acts = [T(a) for a in act_n]
+    acts[j] = a_hat
+    xq2 = torch.cat([T(obs_n[j]), a_hat], 1) if case["local_q"][j] else torch.cat([T(x) for x in obs_n] + acts, 1)
+    p_loss = -torch.mean(_mlp(q2, xq2)[:, 0]) + 1e-3 * torch.mean(logits ** 2)
+    gp = torch.autograd.grad(p_loss, p)
+    assert np.isclose(stats[1], p_loss.item(), rtol=1e-4, atol=1e-6)
+    for g_o, g_t in zip(tr.last_grads["p"], gp):
+        assert np.allclose(g_o, g_t.numpy(), rtol=2e-3, atol=2e-6)
+
+
+def test_oracle_grads_vs_torch_spread():
+    _check_case("simple_spread")
+
+
+def test_oracle_grads_vs_torch_world_comm_multihead():
+    _check_case("simple_world_comm")
+
+
+def test_oracle_grads_vs_torch_ddpg_local_q():
+    _check_case("simple_tag_ddpg_adv")
+
+
+def test_adam_is_tf_formulation():
+    p = [np.array([1.0, -2.0], np.float32)]
+    g = [np.array([0.5, -0.25], np.float32)]
+    opt = om.Adam(p, lr=1e-2)
+    opt.step(p, g)
+    # t=1: m=(1-b1)g, v=(1-b2)g^2, lr_t = lr*sqrt(1-b2)/(1-b1); eps added to sqrt(v) (uncorrected)
+    lr_t = 1e-2 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    exp = np.array([1.0, -2.0]) - lr_t * (0.1 * g[0]) / (np.sqrt(0.001 * g[0] ** 2) + 1e-8)
+    assert np.allclose(p[0], exp, rtol=1e-6)
+
+
+def test_clip_by_norm_per_variable():
+    g = np.array([3.0, 4.0], np.float32)
+    assert np.allclose(om.clip_by_norm(g, 0.5), g * 0.1)
+    small = np.array([0.1, 0.2], np.float32)
+    assert np.allclose(om.clip_by_norm(small, 0.5), small)
+
+
+def test_polyak_invariants():
+    rng = np.random.RandomState(0)
+    a, b = om.MLP(5, 8, 3, rng), om.MLP(5, 8, 3, rng)
+    tgt = [x.copy() for x in b.p]
+    om.polyak_update(b, a, polyak=0.0)   # reference tests/test_policy.py:71-86: target == running
+    assert all(np.array_equal(x, y) for x, y in zip(b.p, a.p))
+    b.p = [x.copy() for x in tgt]
+    om.polyak_update(b, a, polyak=1.0)   # unchanged
+    assert all(np.array_equal(x, y) for x, y in zip(b.p, tgt))
+    om.polyak_update(b, a)               # 0.99 / 0.01 mix
+    assert all(np.allclose(x, 0.99 * t + 0.01 * r, rtol=1e-6) for x, t, r in zip(b.p, tgt, a.p))
+
+
+def test_gumbel_softmax_heads_sum_to_one():
+    rng = np.random.RandomState(1)
+    a = om.gumbel_softmax(rng.randn(7, 9), rng.uniform(0.01, 1, (7, 9)), [5, 4])
+    assert np.allclose(a[:, :5].sum(1), 1, atol=1e-6) and np.allclose(a[:, 5:].sum(1), 1, atol=1e-6)

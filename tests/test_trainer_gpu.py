@@ -1,0 +1,197 @@
+"""CUDA trainer kernels (through the C ABI and the reference-shaped MADDPGAgentTrainer surface)
+against the numpy oracle on the same weights, replay rows, index sets and uniform draws.
+Tolerance from BASELINE.json north_star: Q-values and losses within 1e-4 relative after a
+fixed-seed update."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import TRAINER_CASES, oracle_update_round, trainer_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _build(case):
+    """MADDPGAgentTrainer objects built exactly like get_trainers (train.py:63-75), then loaded with
+    the oracle's weights and replay rows."""
+    from maddpg_b200 import MADDPGAgentTrainer, _lib
+    env = case["env"]
+    act_space_n = list(env.action_space)
+    trainers = [MADDPGAgentTrainer("agent_%d" % i, None, case["obs_shape_n"], act_space_n, i, case["args"],
+                                   local_q_func=case["local_q"][i]) for i in range(case["n"])]
+    core = trainers[0].core
+    for i, o in enumerate(case["trainers"]):
+        core.set_weights(i, _lib.NET_P, o.p.p)
+        core.set_weights(i, _lib.NET_TARGET_P, o.target_p.p)
+        core.set_weights(i, _lib.NET_Q, o.q.p)
+        core.set_weights(i, _lib.NET_TARGET_Q, o.target_q.p)
+    p = case["pool"]
+    for r in range(case["rows"]):  # every agent inserts every step, like train.py:119-120
+        for i, tr in enumerate(trainers):
+            tr.experience(p["obs"][i][r], p["act"][i][r], float(p["rew"][i][r]), p["nobs"][i][r], bool(p["done"][i][r]), False)
+    for tr in trainers:
+        tr.max_replay_buffer_len = 0
+    return trainers, core
+
+
+def _close(a, b, rtol=RTOL, atol=1e-6, msg=""):
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol, err_msg=msg)
+
+
+@pytest.mark.parametrize("name", list(TRAINER_CASES))
+def test_forward_surfaces_match_oracle(name):
+    case = trainer_case(name, seed=1)
+    trainers, core = _build(case)
+    n, B = case["n"], case["B"]
+    p = case["pool"]
+    rows = np.arange(B)
+    obs_n = [p["obs"][i][rows] for i in range(n)]
+    act_n = [p["act"][i][rows] for i in range(n)]
+    off = np.concatenate([[0], np.cumsum(case["act_dims"])]).astype(int)
+    for j, (tr, o) in enumerate(zip(trainers, case["trainers"])):
+        u = case["u_actor"][j]
+        o.noise = lambda shape, u=u: u
+        _close(tr.p_debug["p_values"](obs_n[j]), o.p_values(obs_n[j]), msg="p_values %d" % j)
+        _close(tr.act(obs_n[j], u=u), o.act(obs_n[j]), msg="act %d" % j)
+        _close(tr.p_debug["target_act"](obs_n[j], u=u), o.target_act(obs_n[j]), msg="target_act %d" % j)
+        _close(tr.q_debug["q_values"](*(obs_n + act_n)), o.q_values(*(obs_n + act_n)), atol=2e-6, msg="q %d" % j)
+        _close(tr.q_debug["target_q_values"](*(obs_n + act_n)), o.target_q_values(*(obs_n + act_n)), atol=2e-6, msg="tq %d" % j)
+        a1 = tr.action(obs_n[j][0])  # reference shape: (D,) in -> (K,) float32 out, rows sum to one per head
+        assert a1.shape == (case["act_dims"][j],) and a1.dtype == np.float32
+        assert abs(float(a1[:case["heads"][j][0]].sum()) - 1.0) < 1e-5
+    # ring rows agree bit-exactly with what was inserted (per-agent sample_index surface)
+    idx = case["idx"][0]
+    for i, tr in enumerate(trainers):
+        o_, a_, r_, n_, d_ = tr.replay_buffer.sample_index(idx)
+        assert np.array_equal(o_, p["obs"][i][idx]) and np.array_equal(a_, p["act"][i][idx])
+        assert np.array_equal(r_, p["rew"][i][idx]) and np.array_equal(n_, p["nobs"][i][idx])
+        assert np.array_equal(d_, p["done"][i][idx])
+
+
+@pytest.mark.parametrize("name", list(TRAINER_CASES))
+def test_gradients_match_oracle(name):
+    """td_target / critic_grads / actor_grads entry points, agent 0 from the pre-update weights."""
+    case = trainer_case(name, seed=2)
+    ref = oracle_update_round(trainer_case(name, seed=2))
+    trainers, core = _build(case)
+    j = 0
+    idx = core.ring.index_tensor(case["idx"][j])
+    batch = core.ring.gather(idx)
+    B = case["B"]
+    ut = torch.zeros((B, core.act_stride), device="cuda")
+    ut[:, :core.act_sum] = torch.from_numpy(case["u_target"][j]).cuda()
+    y = core.td_target(j, batch, ut)
+    _close(y.cpu().numpy(), ref[j]["y"], atol=2e-6, msg="td target")
+    q = core.critic_grads(j, batch, y, want_q=True)
+    got = [g.cpu().numpy() for g in core.train_view(core.grads, j, 1)]
+    for k, (g, r) in enumerate(zip(got, ref[j]["q_grads"])):
+        _close(g, r, rtol=1e-3, atol=1e-6 + 1e-4 * np.abs(r).max(), msg="critic grad %d" % k)
+    core.clip_adam_polyak(j, 1)
+    assert float(core.grads.abs().max()) == 0.0  # bucket re-zeroed
+    for k, (w, r) in enumerate(zip(core.get_weights(j, 2), ref[j]["q"])):
+        _close(w, r, rtol=1e-3, atol=2e-4, msg="critic param %d after Adam" % k)
+    ua = torch.zeros((B, core.act_stride), device="cuda")
+    o = core.act_off[j]
+    ua[:, o:o + core.act_dims[j]] = torch.from_numpy(case["u_actor"][j]).cuda()
+    core.actor_grads(j, batch, ua)
+    got = [g.cpu().numpy() for g in core.train_view(core.grads, j, 0)]
+    for k, (g, r) in enumerate(zip(got, ref[j]["p_grads"])):
+        _close(g, r, rtol=2e-3, atol=1e-7 + 2e-4 * np.abs(r).max(), msg="actor grad %d" % k)
+    assert core.adam_t.cpu().tolist()[:2] == [1, 1]
+
+
+@pytest.mark.parametrize("name", list(TRAINER_CASES))
+def test_sequential_update_round_matches_oracle(name):
+    """agent.update(trainers, t) for every agent in order (train.py:160-161), injected index sets and
+    uniforms: returned statistics, post-update Q-values and parameters."""
+    case = trainer_case(name, seed=4)
+    ref = oracle_update_round(trainer_case(name, seed=4))
+    oracle_after = trainer_case(name, seed=4)
+    trainers, core = _build(case)
+    n = case["n"]
+    assert trainers[0].update(trainers, 99, index=case["idx"][0]) is None  # off-period gate (maddpg.py:164)
+    for j, tr in enumerate(trainers):
+        tr.preupdate()
+        tr.inject_noise(u_target=case["u_target"][j], u_actor=case["u_actor"][j])
+        stats = tr.update(trainers, 100, index=case["idx"][j])
+        rs = ref[j]["stats"]
+        assert len(stats) == 6
+        for k, nm in enumerate(["q_loss", "p_loss", "mean_target_q", "mean_rew", "mean_target_q_next", "std_target_q"]):
+            _close(stats[k], rs[k], rtol=RTOL, atol=2e-6, msg="%s agent %d" % (nm, j))
+    # post-update networks: parameters and Q-values on a fresh batch
+    p = case["pool"]
+    rows = np.arange(case["B"], 2 * case["B"])
+    obs_n = [p["obs"][i][rows] for i in range(n)]
+    act_n = [p["act"][i][rows] for i in range(n)]
+    from oracle import maddpg as om
+    for j, tr in enumerate(trainers):
+        for net, key in ((2, "q"), (3, "target_q"), (0, "p"), (1, "target_p")):
+            for k, (w, r) in enumerate(zip(core.get_weights(j, net), ref[j][key])):
+                _close(w, r, rtol=1e-3, atol=2e-4, msg="agent %d %s[%d]" % (j, key, k))
+        o = oracle_after["trainers"][j]
+        o.q.p, o.p.p = ref[j]["q"], ref[j]["p"]
+        q_ref = o.q_values(*(obs_n + act_n))
+        q_got = tr.q_debug["q_values"](*(obs_n + act_n))
+        scale = np.abs(q_ref).mean()
+        _close(q_got, q_ref, rtol=RTOL, atol=RTOL * scale, msg="post-update Q agent %d" % j)
+
+
+def test_warmup_gate_and_index_stream():
+    """update() returns None until batch_size*max_episode_len rows exist (maddpg.py:162-163) and draws
+    its indices from python ``random`` like replay_buffer.py:46-47."""
+    import random
+    case = trainer_case("simple", seed=0)
+    trainers, core = _build(case)
+    tr = trainers[0]
+    tr.max_replay_buffer_len = case["rows"] + 1
+    assert tr.update(trainers, 100) is None
+    tr.max_replay_buffer_len = case["rows"]
+    random.seed(77)
+    expect = [random.randint(0, case["rows"] - 1) for _ in range(case["B"])]
+    random.seed(77)
+    out = tr.update(trainers, 100)
+    assert out is not None and tr.replay_sample_index == expect
+    assert all(np.isfinite(out))
+
+
+def test_polyak_tau_invariants():
+    """Reference invariant (tests/test_policy.py:71-86): polyak 0 => target == running; 1 => unchanged."""
+    from maddpg_b200 import MADDPGCore
+    from maddpg_b200.spaces import Discrete
+    for pol in (0.0, 1.0):
+        core = MADDPGCore([6, 6], [Discrete(5), Discrete(5)], [False, False], polyak=pol, replay_capacity=64, seed=1)
+        before_t = core.get_weights(0, 3)
+        core.grads.normal_()
+        core.adam_t += 1
+        core.clip_adam_polyak(0, 1)
+        run, tgt = core.get_weights(0, 2), core.get_weights(0, 3)
+        for r, t, b in zip(run, tgt, before_t):
+            assert np.array_equal(t, r) if pol == 0.0 else np.array_equal(t, b)
+
+
+def test_philox_actions_are_valid_and_reproducible():
+    from maddpg_b200 import MADDPGCore
+    from maddpg_b200.spaces import Discrete, MultiDiscrete
+    spaces = [MultiDiscrete([[0, 4], [0, 3]]), Discrete(5)]
+    outs = []
+    for rep in range(2):
+        core = MADDPGCore([34, 28], spaces, [False, False], num_units=128, replay_capacity=64, seed=9)
+        obs = torch.randn(4096, core.obs_stride, generator=torch.Generator().manual_seed(0)).cuda()
+        act = torch.zeros(4096, core.act_stride, device="cuda")
+        core.act(obs, act)
+        a = act.cpu().numpy()
+        outs.append(a)
+        assert np.allclose(a[:, 0:5].sum(1), 1, atol=1e-5) and np.allclose(a[:, 5:9].sum(1), 1, atol=1e-5)
+        assert np.allclose(a[:, 9:14].sum(1), 1, atol=1e-5) and np.all(a >= 0)
+        act2 = torch.zeros_like(act)
+        core.act(obs, act2)  # the Philox counter advanced: a fresh sample
+        assert not torch.equal(act, act2)
+    assert np.array_equal(outs[0], outs[1])  # same seed, same counter -> same draws
+    # argmax frequencies follow the Gumbel-max law: compare with softmax(logits) means
+    logits = torch.zeros_like(act)
+    core2 = MADDPGCore([34, 28], spaces, [False, False], num_units=128, replay_capacity=64, seed=9)
+    core2.act(obs, act, logits_out=logits)
+    pl = torch.softmax(logits[:, 9:14], 1).mean(0).cpu().numpy()
+    freq = np.bincount(act[:, 9:14].argmax(1).cpu().numpy(), minlength=5) / 4096.0
+    assert np.abs(freq - pl).max() < 0.04
