@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the MADDPG hot path on B200 (contract in the task statement; metric from BASELINE.json:
+"agent-env-steps/sec + critic updates/sec at 1/2/4/8 B200 vs CPU ref").
+
+Workload (BASELINE.json configs[1]): simple_spread N=3, 4096 lockstep env instances PER GPU (weak
+scaling: env instances and replay shards are rank-local), batch 1024, num_units 64, maddpg/maddpg.
+
+  step            one lockstep rollout step of all env instances of a rank: grouped actor inference +
+                  Gumbel-softmax sampling, fused MPE step, replay insert; device reset every 25 steps
+                  (experiments/train.py:110-133 batched).  value = E*A*K*n_gpus / max-over-ranks device time.
+  critic_updates  sequential per-agent updates (maddpg/trainer/maddpg.py:167-194: gather, TD target, critic
+                  step, actor step, polyak), each on a batch of 1024 rows per rank; under N>1 the gradient
+                  bucket of the network being stepped is all-reduced over NCCL (2 collectives per agent update).
+  e2e             the same loop through the reference-shaped public API (MADDPGAgentTrainer.action /
+                  BatchedMultiAgentEnv.step / .experience / .update) with HOST numpy buffers: every H2D/D2H
+                  copy is inside the timed region.
+
+Timing protocol: CUDA events on the launching stream; the timed region is cut into episodes (25 steps) /
+update rounds and the L2 is flushed (256 MB write, untimed) before each, so every episode starts cold; within
+an episode the 1.7 MB env state is re-read from L2 exactly as in a real rollout.  Multi-GPU numbers take the
+max over ranks of the summed device time, bracketed by barrier + synchronize.
+
+`--impl reference` times the restated reference loop (oracle/train_loop.py: numpy MPE + numpy trainer, one
+env, batch-1 actor calls) as `os.cpu_count()` independent single-threaded replicas on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCENARIO, N_AGENTS, ENVS_PER_GPU, BATCH, UNITS, EP_LEN = "simple_spread", 3, 4096, 1024, 64, 25
+WORKLOAD = "simple_spread N=3, 4096 envs per GPU, batch 1024, num_units 64, maddpg/maddpg (BASELINE.json configs[1])"
+METRIC, UNIT = "agent-env-steps/sec", "agent-env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--update-rounds", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the restated reference loop on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = "1"
+    from oracle import train_loop as tl
+    cores = os.cpu_count() or 1
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    if warm:
+        tl.time_parallel("rollout", SCENARIO, N_AGENTS, warm, cores, BATCH, UNITS)
+    value, wall = tl.time_parallel("rollout", SCENARIO, N_AGENTS, steps, cores, BATCH, UNITS)
+    rounds = max(2, min(20, steps // 100))
+    upd, upd_wall = tl.time_parallel("updates", SCENARIO, N_AGENTS, rounds, cores, BATCH, UNITS)
+    sample = ("%d single-threaded replicas of the restated train.py loop (numpy MPE + numpy trainer, 1 env each), "
+              "%d env steps each after %d warm-up; updates: %d forced rounds x %d agents each" %
+              (cores, steps, warm, rounds, N_AGENTS))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * N_AGENTS * cores / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 env / f32 nets", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_path": "oracle/train_loop.py (TF-free restatement; real train.py "
+                   "needs tensorflow 1.8 + gym + MPE, not installable here)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "critic_updates": {"value": upd, "unit": "critic updates/s", "cores": cores},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                if v == "Active":
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGAgentTrainer, _lib
+    from maddpg_b200.distributed import DataParallelUpdater, rank_seed
+    from maddpg_b200.rollout import BatchedRollout
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    E, A = args.envs, N_AGENTS
+    K, W = max(EP_LEN, args.steps // EP_LEN * EP_LEN), max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def flush_l2():
+        flush_buf.fill_(1.0)
+
+    # ---- build the experiment exactly like train.py:80-85 (env, trainers) on this rank's shard -------------
+    arglist = argparse.Namespace(lr=1e-2, gamma=0.95, batch_size=BATCH, num_units=UNITS, max_episode_len=EP_LEN,
+                                 seed=0, device=str(dev))
+    env = BatchedMultiAgentEnv(SCENARIO, num_envs=E, num_agents=N_AGENTS, device=dev, seed=rank_seed(0, rank), squeeze=False)
+    obs_shape_n = [env.observation_space[i].shape for i in range(env.n)]
+    trainers = [MADDPGAgentTrainer("agent_%d" % i, None, obs_shape_n, env.action_space, i, arglist) for i in range(env.n)]
+    core = trainers[0].core
+    dp = DataParallelUpdater(core)
+    dp.broadcast_params(core.params)
+    roll = BatchedRollout(env, core, EP_LEN, use_graph=not args.no_graph)
+    env.reset()
+
+    # ---- (1) device-resident rollout -----------------------------------------------------------------------
+    roll.run(max(W, EP_LEN) // EP_LEN * EP_LEN)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n_eps = K // EP_LEN
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eps)]
+    l0 = _lib.launch_count()
+    barrier()
+    for e0, e1 in evs:
+        flush_l2()
+        e0.record()
+        roll.run(EP_LEN)
+        e1.record()
+    barrier()
+    launches_roll = _lib.launch_count() - l0
+    roll_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    value = E * A * K * world / (roll_ms * 1e-3)
+
+    # ---- (2) env-step kernel alone (roofline) ----------------------------------------------------------------
+    reps = 20
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in kev:
+        flush_l2()
+        a.record()
+        for _ in range(EP_LEN):
+            env.step_device()
+        b.record()
+    torch.cuda.synchronize()
+    env_us = sum(a.elapsed_time(b) for a, b in kev) * 1e3 / (reps * EP_LEN)
+    peak, peak_src = measured_peak_hbm()
+    env_bytes = env.env_bytes_per_step * E
+    achieved = env_bytes / (env_us * 1e-6) / 1e9
+
+    # ---- (3) critic updates: sequential agent updates on gathered batches ------------------------------------
+    while core.ring.length[0] < BATCH * EP_LEN:  # the reference's warm-up gate (maddpg.py:148,162)
+        roll.run(EP_LEN)
+    R = max(1, args.update_rounds)
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+
+    def draw_idx():
+        return torch.randint(0, core.ring.length[0], (BATCH,), generator=g).to(dev, non_blocking=False)
+
+    idx_pool = [[draw_idx() for _ in range(A)] for _ in range(8)]
+    _, batch = core._scratch(BATCH)
+
+    def update_round(r):
+        for j in range(A):
+            core.ring.gather(idx_pool[r % 8][j], out=batch)
+            dp.update_agent(j, batch)
+
+    for r in range(3):
+        update_round(r)
+    barrier()
+    uev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+    l0 = _lib.launch_count()
+    for r, (a, b) in enumerate(uev):
+        flush_l2()
+        a.record()
+        update_round(r)
+        b.record()
+    barrier()
+    launches_upd = _lib.launch_count() - l0
+    upd_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in uev))
+    upd_value = R * A * world / (upd_ms * 1e-3)
+    clocks = sampler.stop()
+
+    # ---- (4) end to end through the reference-shaped API with host buffers ------------------------------------
+    Ke = max(EP_LEN, args.e2e_steps // EP_LEN * EP_LEN)
+    obs_n = [o.cpu().numpy() for o in env.reset()]
+    h2d = d2h = 0
+
+    def e2e_step(obs_n, episode_step):
+        action_n = [agent.action(obs) for agent, obs in zip(trainers, obs_n)]               # train.py:112
+        new_obs_n, rew_n, done_n, info_n = env.step(action_n)                                 # train.py:114
+        for i, agent in enumerate(trainers):                                                  # train.py:119-120
+            agent.experience(obs_n[i], action_n[i], rew_n[i], new_obs_n[i], done_n[i], False)
+        episode_step += 1
+        if episode_step >= EP_LEN:                                                            # train.py:127-129
+            new_obs_n = [o.cpu().numpy() for o in env.reset()]
+            episode_step = 0
+        return new_obs_n, episode_step
+
+    ep = 0
+    for _ in range(5):
+        obs_n, ep = e2e_step(obs_n, ep)
+    obs_n = [o.cpu().numpy() for o in env.reset()]
+    ep = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        obs_n, ep = e2e_step(obs_n, ep)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = E * A * Ke * world / e2e_s
+    row_f = sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
+    h2d = 4 * E * (sum(env.obs_dims) + env.act_stride + row_f)   # action() obs, step() actions, experience() rows
+    d2h = 4 * E * (sum(env.act_dims) + env.obs_stride + env.n)   # actions, [obs | rew]
+    # e2e updates: trainer.update() per agent incl. python index draw, H2D of indices, D2H of the statistics
+    for tr in trainers:
+        tr.max_replay_buffer_len = BATCH * EP_LEN
+    import random
+    random.seed(rank)
+    Re = max(3, min(30, R))
+    for j, tr in enumerate(trainers):
+        tr.update(trainers, 100)
+    barrier()
+    t0 = time.perf_counter()
+    for r in range(Re):
+        for tr in trainers:
+            tr.preupdate()
+        for tr in trainers:
+            out = tr.update(trainers, 100)
+            assert out is not None
+    barrier()
+    e2e_upd_s = max_over_ranks(time.perf_counter() - t0)
+
+    # ---- (5) CPU baseline: the restated reference loop on this box's host cores (rank 0, N=1 only) -------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+            os.environ[k] = "1"
+        from oracle import train_loop as tl
+        cpu_steps, cpu_rounds = 10000, 30
+        a_sps, e_sps, dt = tl.time_rollout(SCENARIO, N_AGENTS, cpu_steps)
+        u_ps, udt = tl.time_updates(SCENARIO, N_AGENTS, cpu_rounds)
+        cpu = {"value": a_sps, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d env steps of the restated train.py loop (1 env, %.1f s) ; %d forced update rounds x %d agents "
+                         "(%.1f s)" % (cpu_steps, dt, cpu_rounds, A, udt),
+               "critic_updates_per_sec": u_ps, "host_cores_available": os.cpu_count()}
+
+    if rank == 0:
+        flops_round = sum(int(core.layout.update_flops_critic[j]) + int(core.layout.update_flops_actor[j]) for j in range(A)) * BATCH
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": roll_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents": A, "batch": BATCH, "episode_len": EP_LEN,
+                       "replay_capacity_rows": core.ring.capacity, "cuda_graph": bool(roll.use_graph and roll.graph_ok),
+                       "l2": "flushed (256 MB write) before every 25-step episode / update round; inside an episode the "
+                             "1.7 MB env state is L2-resident as in a real rollout"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
+                    "api": "MADDPGAgentTrainer.action / BatchedMultiAgentEnv.step / .experience with host numpy arrays"},
+            "gpu_launches": int(launches_roll),
+            "roofline": {"kernel": "k_env_step<float,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": env_bytes, "avg_launch_us": env_us},
+            "critic_updates": {"value": upd_value, "unit": "critic updates/s", "rounds": R, "ms_per_round": upd_ms / R,
+                               "gpu_launches": int(launches_upd), "flops_per_round": flops_round,
+                               "achieved_tflops": flops_round * R / (upd_ms * 1e-3) / 1e12,
+                               "allreduce_bytes_per_round": dp.allreduce_bytes // max(1, R + 3),
+                               "e2e": {"value": Re * A * world / e2e_upd_s, "unit": "critic updates/s",
+                                       "api": "MADDPGAgentTrainer.update (python index draw + H2D idx + D2H stats)"}},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,8 +92,8 @@ class JointReplayRing(object):
         cur = self._advance(agent, E)
         _lib.check(_lib.lib.mdp_replay_insert(C.byref(self.layout), _lib.ptr(self.ring), self.capacity, cur, E, agent,
                                               _lib.ptr(obs), obs.stride(0), _lib.ptr(act), act.stride(0),
-                                              _lib.ptr(rew), 1, _lib.ptr(next_obs), next_obs.stride(0),
-                                              _lib.ptr(done), 1, _lib.current_stream()),
+                                              _lib.ptr(rew), rew.stride(0), _lib.ptr(next_obs), next_obs.stride(0),
+                                              _lib.ptr(done), done.stride(0), _lib.current_stream()),
                    "mdp_replay_insert")
 
     def gather(self, idx, out=None, mode=None):
@@ -127,6 +127,7 @@ class DeviceReplayBuffer(object):
             self._h = self._h.pin_memory()
         self._d = torch.zeros(self._pack, dtype=torch.float32, device=ring.device)
         self._d_done = torch.zeros(1, dtype=torch.uint8, device=ring.device)
+        self._staged = None  # event marking the end of the last async copy out of the pinned buffer
 
     def __len__(self):
         return self.ring.length[self.agent]
@@ -151,17 +152,40 @@ class DeviceReplayBuffer(object):
             rew_t = reward if isinstance(reward, torch.Tensor) else torch.full((E,), float(reward), dtype=torch.float32, device=r.device)
             r.insert_agent(i, obs_t, action, rew_t.contiguous(), obs_tp1, done_t.contiguous())
             return
-        h = self._h
-        h[:D] = torch.from_numpy(np.asarray(obs_t, dtype=np.float32).reshape(-1))
-        h[D:D + K] = torch.from_numpy(np.asarray(action, dtype=np.float32).reshape(-1))
-        h[D + K] = float(reward)
-        h[D + K + 1:2 * D + K + 1] = torch.from_numpy(np.asarray(obs_tp1, dtype=np.float32).reshape(-1))
-        h[2 * D + K + 1] = float(done)
-        self._d.copy_(h, non_blocking=True)
-        d = self._d
-        self._d_done.copy_((d[2 * D + K + 1:] != 0).to(torch.uint8))
-        r.insert_agent(i, d[:D].unsqueeze(0), d[D:D + K].unsqueeze(0), d[D + K:D + K + 1],
-                       d[D + K + 1:2 * D + K + 1].unsqueeze(0), self._d_done)
+        # host path: E transitions (E = 1 for the reference's per-step call) packed into ONE pinned
+        # staging buffer -> one H2D copy -> one insert kernel
+        obs_h = np.asarray(obs_t, dtype=np.float32)
+        E = 1 if obs_h.ndim == 1 else obs_h.shape[0]
+        pack = self._pack
+        if self._h.shape[0] < E * pack:
+            self._h = torch.zeros(E * pack, dtype=torch.float32)
+            if r.device.type == "cuda":
+                self._h = self._h.pin_memory()
+            self._d = torch.zeros(E * pack, dtype=torch.float32, device=r.device)
+            self._d_done = torch.zeros(E, dtype=torch.uint8, device=r.device)
+            self._staged = None
+        if self._staged is not None:
+            self._staged.synchronize()  # the previous H2D copy must have left the pinned buffer
+        h = self._h[:E * pack].view(E, pack).numpy()
+        h[:, :D] = obs_h.reshape(E, D)
+        h[:, D:D + K] = np.asarray(action, dtype=np.float32).reshape(E, K)
+        h[:, D + K] = np.asarray(reward, dtype=np.float32).reshape(E)
+        h[:, D + K + 1:2 * D + K + 1] = np.asarray(obs_tp1, dtype=np.float32).reshape(E, D)
+        h[:, 2 * D + K + 1] = np.asarray(done, dtype=np.float32).reshape(-1)
+        d = self._d[:E * pack].view(E, pack)
+        d.copy_(self._h[:E * pack].view(E, pack), non_blocking=True)
+        if r.device.type == "cuda":
+            self._staged = torch.cuda.Event()
+            self._staged.record()
+        dn = self._d_done[:E]
+        torch.ne(d[:, 2 * D + K + 1], 0, out=self._ne_buf(E))
+        dn.copy_(self._ne_buf(E))
+        r.insert_agent(i, d[:, :D], d[:, D:D + K], d[:, D + K], d[:, D + K + 1:2 * D + K + 1], dn)
+
+    def _ne_buf(self, E):
+        if getattr(self, "_ne", None) is None or self._ne.shape[0] < E:
+            self._ne = torch.zeros(E, dtype=torch.bool, device=self.ring.device)
+        return self._ne[:E]
 
     def make_index(self, batch_size):
         # replay_buffer.py:46-47 -- the same python MT19937 stream as the reference

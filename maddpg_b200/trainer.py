@@ -357,14 +357,14 @@ class MADDPGAgentTrainer(AgentTrainer):
         """maddpg.py:151-152: ``self.act(obs[None])[0]``; a CUDA (E, D_i) tensor is treated as a batch."""
         if isinstance(obs, torch.Tensor) and obs.dim() == 2:
             return self.core.act_agent(self.agent_index, obs)
-        return self.act(np.asarray(obs, dtype=np.float32)[None])[0]
+        obs = np.asarray(obs, dtype=np.float32)
+        if obs.ndim == 2:  # host batch (E, D_i) -> (E, K_i)
+            return self.act(obs)
+        return self.act(obs[None])[0]
 
     def experience(self, obs, act, rew, new_obs, done, terminal):
         """maddpg.py:154-156 (``terminal`` is ignored by the reference too)."""
-        if isinstance(done, torch.Tensor):
-            self.replay_buffer.add(obs, act, rew, new_obs, done)
-        else:
-            self.replay_buffer.add(obs, act, rew, new_obs, float(np.all(done)) if np.ndim(done) else float(done))
+        self.replay_buffer.add(obs, act, rew, new_obs, done if isinstance(done, torch.Tensor) or np.ndim(done) else float(done))
 
     def process_experience(self, obs, act, rew, new_obs, done, terminal):
         return self.experience(obs, act, rew, new_obs, done, terminal)

@@ -93,7 +93,9 @@ def test_full_size_properties_spread_4096():
     from maddpg_b200 import BatchedMultiAgentEnv
     E = 4096
     rng = np.random.RandomState(0)
-    env = BatchedMultiAgentEnv("simple_spread", num_envs=E, state_dtype=torch.float32, squeeze=False)
+    # float64 state: a float32 shift re-rounds positions and the stiff contact model (k = 1e-3)
+    # amplifies that by ~100x per step in contact, which is not what this property is about
+    env = BatchedMultiAgentEnv("simple_spread", num_envs=E, state_dtype=torch.float64, squeeze=False)
     ap, av, lp = rng.uniform(-1, 1, (E, 3, 2)), rng.uniform(-.2, .2, (E, 3, 2)), rng.uniform(-1, 1, (E, 3, 2))
     acts = [soft_actions(rng, E, 5) for _ in range(3)]
     a = _joint_act(env, acts)
@@ -110,7 +112,7 @@ def test_full_size_properties_spread_4096():
     mask = np.ones(56, bool)
     for i in range(3):
         mask[18 * i + 2:18 * i + 4] = False  # absolute p_pos columns shift, everything else is relative
-    np.testing.assert_allclose(o2[:, mask], o0[:, mask], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(o2[:, mask], o0[:, mask], rtol=0, atol=1e-6)
     np.testing.assert_allclose(r2, r0, rtol=1e-5, atol=1e-5)
     assert np.all(r0[:, 0] == r0[:, 1]) and np.all(r0[:, 1] == r0[:, 2])
     assert np.all(o0[:, 54:] == 0)
