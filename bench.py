@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--rollout-mode", default="mega", choices=["mega", "graph", "eager"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     return ap.parse_args()
 
@@ -108,6 +109,13 @@ class ClockSampler(object):
         except Exception:
             self.p = None
 
+    def wait_first(self, timeout):
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < timeout:
+            if os.path.getsize(self.f.name) > 0:
+                return
+            time.sleep(0.05)
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
@@ -161,7 +169,7 @@ def main():
     import torch.distributed as dist
     from maddpg_b200 import BatchedMultiAgentEnv, MADDPGAgentTrainer, _lib
     from maddpg_b200.distributed import DataParallelUpdater, rank_seed
-    from maddpg_b200.rollout import BatchedRollout
+    from maddpg_b200.rollout import BatchedRollout, GraphedUpdateRound
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,17 +206,18 @@ def main():
     core = trainers[0].core
     dp = DataParallelUpdater(core)
     dp.broadcast_params(core.params)
-    roll = BatchedRollout(env, core, EP_LEN, use_graph=not args.no_graph)
+    roll = BatchedRollout(env, core, EP_LEN, mode=args.rollout_mode)
     env.reset()
 
     # ---- (1) device-resident rollout -----------------------------------------------------------------------
-    roll.run(max(W, EP_LEN) // EP_LEN * EP_LEN)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    roll.run(max(W, EP_LEN) // EP_LEN * EP_LEN)
+    barrier()
+    sampler.wait_first(3.0)
     n_eps = K // EP_LEN
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eps)]
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + roll.graph_launches
     barrier()
     for e0, e1 in evs:
         flush_l2()
@@ -216,21 +225,31 @@ def main():
         roll.run(EP_LEN)
         e1.record()
     barrier()
-    launches_roll = _lib.launch_count() - l0
+    launches_roll = _lib.launch_count() + roll.graph_launches - l0
     roll_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
     value = E * A * K * world / (roll_ms * 1e-3)
 
     # ---- (2) env-step kernel alone (roofline) ----------------------------------------------------------------
-    reps = 20
+    reps, per = 20, EP_LEN - 1  # an even number of launches keeps the observation double buffer in phase
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    env_graph = None
+    if not args.no_graph:
+        env_graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(env_graph):
+            for _ in range(per):
+                env.step_device()
     for a, b in kev:
         flush_l2()
         a.record()
-        for _ in range(EP_LEN):
-            env.step_device()
+        if env_graph is not None:
+            env_graph.replay()
+        else:
+            for _ in range(per):
+                env.step_device()
         b.record()
     torch.cuda.synchronize()
-    env_us = sum(a.elapsed_time(b) for a, b in kev) * 1e3 / (reps * EP_LEN)
+    env_us = sum(a.elapsed_time(b) for a, b in kev) * 1e3 / (reps * per)
     peak, peak_src = measured_peak_hbm()
     env_bytes = env.env_bytes_per_step * E
     achieved = env_bytes / (env_us * 1e-6) / 1e9
@@ -247,7 +266,11 @@ def main():
     idx_pool = [[draw_idx() for _ in range(A)] for _ in range(8)]
     _, batch = core._scratch(BATCH)
 
+    gupd = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph) if world == 1 else None
+
     def update_round(r):
+        if gupd is not None:  # single GPU: device-side index draw + gather + 5 update kernels per agent, graph-replayed
+            return gupd.run(1)
         for j in range(A):
             core.ring.gather(idx_pool[r % 8][j], out=batch)
             dp.update_agent(j, batch)
@@ -256,14 +279,14 @@ def main():
         update_round(r)
     barrier()
     uev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + (gupd.graph_launches if gupd else 0)
     for r, (a, b) in enumerate(uev):
         flush_l2()
         a.record()
         update_round(r)
         b.record()
     barrier()
-    launches_upd = _lib.launch_count() - l0
+    launches_upd = _lib.launch_count() + (gupd.graph_launches if gupd else 0) - l0
     upd_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in uev))
     upd_value = R * A * world / (upd_ms * 1e-3)
     clocks = sampler.stop()
@@ -339,7 +362,7 @@ def main():
             "ms_per_step": roll_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents": A, "batch": BATCH, "episode_len": EP_LEN,
-                       "replay_capacity_rows": core.ring.capacity, "cuda_graph": bool(roll.use_graph and roll.graph_ok),
+                       "replay_capacity_rows": core.ring.capacity, "rollout_mode": roll.mode, "cuda_graph_updates": bool(gupd is not None and gupd.use_graph),
                        "l2": "flushed (256 MB write) before every 25-step episode / update round; inside an episode the "
                              "1.7 MB env state is L2-resident as in a real rollout"},
             "clocks": clocks,

@@ -201,6 +201,39 @@ int mdp_update_agent(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, 
                      const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
                      uint64_t counter, float* y_scratch, void* stream);
 
+/* Persistent episode kernel: `steps` lockstep iterations of experiments/train.py:112-133 (action ->
+ * env.step -> experience, optional env.reset at the end) in ONE launch.  Each CTA keeps 32 env instances'
+ * state, observation tile, sampled actions and (when they fit) all agents' actor weights in shared
+ * memory for the whole episode; only the joint replay rows stream to `ring` at rows
+ * (ring_cursor + s*E + e) % ring_capacity.  Step s draws its Gumbel noise from Philox counter
+ * `counter + s + 1`, so the result equals `steps` x (mdp_actor_act(counter+s+1), mdp_env_step with ring)
+ * [+ mdp_env_reset(env_seed, episode)].  obs: joint current observations (E, obs_stride), read at entry and
+ * replaced by the final (post-reset) observations.  ep_return (optional, (E, n_agents)): += sum of rewards.
+ * float32 state only; MDP_ENOTSUP when the observation tile does not fit in shared memory (callers then use
+ * the per-step kernels). */
+int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
+                        int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
+                        uint64_t seed, uint64_t counter, int32_t reset_after, uint64_t env_seed, uint64_t episode,
+                        float* ep_return, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* device control block: lets a captured CUDA graph advance its own counters                    */
+/* ------------------------------------------------------------------------------------------ */
+/* ctl is a caller-owned DEVICE array of 4 uint64: {philox_counter, ring_cursor, episode, ring_length}.
+ * Once attached, kernels ADD ctl[0] to the `counter` argument, ctl[2] to `episode`, and take the ring
+ * cursor as (ring_cursor argument + ctl[1]) % capacity -- so the host can bake step-relative offsets
+ * into a CUDA graph of a whole episode / update round and replay it.  Pass NULL to detach. */
+int mdp_env_set_ctl(mdp_env* env, const uint64_t* ctl);
+int mdp_core_set_ctl(mdp_core* core, const uint64_t* ctl);
+/* ctl[0] += d_counter; ctl[1] = (ctl[1] + d_rows) % capacity; ctl[2] += d_episode;
+ * ctl[3] = min(capacity, ctl[3] + d_rows)   (one tiny kernel, graph-capturable) */
+int mdp_ctl_advance(uint64_t* ctl, uint64_t d_counter, int64_t d_rows, int64_t capacity, uint64_t d_episode,
+                    void* stream);
+/* ReplayBuffer.make_index on device (replay_buffer.py:46-47 draws B uniform indices in [0, len) with
+ * replacement): Philox4x32-10 keyed by (seed, counter [+ctl[0]], b).  length <= 0 reads ctl[3]. */
+int mdp_replay_make_index(int64_t* idx_out, int32_t B, int64_t length, uint64_t seed, uint64_t counter,
+                          const uint64_t* ctl, void* stream);
+
 const char* mdp_last_error(void);
 const char* mdp_version(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */

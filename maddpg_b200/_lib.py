@@ -84,6 +84,12 @@ SYMBOLS = {
     "mdp_clip_adam_polyak": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
     "mdp_update_agent": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, C.c_int32,
                                    C.c_uint64, C.c_uint64, _P, _P]),
+    "mdp_rollout_episode": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
+                                      C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
+    "mdp_env_set_ctl": (C.c_int, [_P, _P]),
+    "mdp_core_set_ctl": (C.c_int, [_P, _P]),
+    "mdp_ctl_advance": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, _P]),
+    "mdp_replay_make_index": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
     "mdp_last_error": (C.c_char_p, []),
     "mdp_version": (C.c_char_p, []),
     "mdp_launch_count": (C.c_int64, []),

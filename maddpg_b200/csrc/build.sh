@@ -8,7 +8,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
        -Xptxas -v --expt-relaxed-constexpr -cudart static)
 objs=()
-for f in mdp_api mdp_env mdp_replay mdp_train mdp_optim; do
+for f in mdp_api mdp_env mdp_replay mdp_train mdp_optim mdp_rollout; do
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$out/$f.o" 2> "$out/$f.ptxas.log" || { cat "$out/$f.ptxas.log"; exit 1; }
   objs+=("$out/$f.o")
 done

@@ -80,6 +80,12 @@ struct Philox {
   }
 };
 
+// mdp_replay_insert with an optional device control block (see mdp_env_set_ctl)
+int replay_insert_ctl(const mdp_ring_layout* lay, float* ring, int64_t capacity, int64_t cursor, int32_t E, int32_t agent,
+                      const float* obs, int32_t obs_stride, const float* act, int32_t act_stride, const float* rew,
+                      int32_t rew_stride, const float* next_obs, int32_t next_obs_stride, const uint8_t* done,
+                      int32_t done_stride, const unsigned long long* ctl, void* stream);
+
 // Gumbel-softmax noise term -log(-log(u)) in float32 (distributions.py:264-266)
 __device__ __forceinline__ float gumbel_from_u(float u) { return -logf(-logf(u)); }
 

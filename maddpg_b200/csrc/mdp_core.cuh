@@ -27,6 +27,7 @@ struct CoreDev {
   double gamma, actor_reg;
   int* adam_t;
   double* stats;
+  const unsigned long long* ctl;
 };
 
 }  // namespace mdp
@@ -40,6 +41,7 @@ struct mdp_core {
   int32_t* adam_t = nullptr;
   double* stats = nullptr;
   mdp::AgentDev* d_agents = nullptr;
+  const unsigned long long* ctl = nullptr;
   std::vector<mdp::AgentDev> h_agents;
 };
 

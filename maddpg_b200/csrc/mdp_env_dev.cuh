@@ -1,0 +1,378 @@
+// Device-side MPE physics shared by the per-step kernel (mdp_env.cu) and the persistent episode
+// kernel (mdp_rollout.cu).  A CTA owns a tile of EB consecutive env instances whose SoA state lives
+// in shared memory as [component][env]; all functions here are CTA-collective (every thread of the
+// block must call them; they synchronise internally where noted).
+//
+// Semantics follow SURVEY.md Appendix A (upstream openai/multiagent-particle-envs):
+//   env_physics        MultiAgentEnv._set_action + World.step (apply_action_force,
+//                      apply_environment_force/get_collision_force, integrate_state, update_agent_state)
+//   env_flags_rewards  Scenario.reward (+ shared-reward sum of MultiAgentEnv.step) and the forest
+//                      visibility flags of simple_world_comm's observation()
+//   env_obs_value      one column of Scenario.observation(), driven by the per-scenario column table
+#pragma once
+#include "mdp_common.cuh"
+
+#include <vector>
+
+namespace mdp {
+
+enum ObsKind : uint8_t {
+  OK_PAD = 0,
+  OK_DIRECT = 1,    // S[a]
+  OK_REL = 2,       // S[a] - S[b]
+  OK_ZERO = 3,      // literal zero (silent agents' comm in simple_spread)
+  OK_REL_MASK = 4,  // visible(i,o) ? S[a] - S[b] : 0        (simple_world_comm)
+  OK_DIR_MASK = 5,  // visible(i,o) ? S[a] : 0
+  OK_FOREST = 6,    // in_forest(i, k) ? +1 : -1
+};
+
+struct ObsCol {
+  uint8_t kind, i, o, k;
+  uint8_t a, b, pad0, pad1;
+};
+
+constexpr int MAX_ENT = 2 * MDP_MAX_AGENTS;
+
+struct EnvParams {
+  int scenario, A, L, NE, cdim, scomp, obs_stride, act_stride, obs_sum, act_sum;
+  int n_adv;       // adversaries are agents [0, n_adv)
+  int food0, n_food, forest0, n_forest;  // landmark indices (simple_world_comm)
+  int collaborative;
+  int act_off[MDP_MAX_AGENTS];
+  double size[MAX_ENT];
+  float sizef[MAX_ENT];
+  double sens[MDP_MAX_AGENTS];       // accel if set else 5.0
+  double max_speed[MDP_MAX_AGENTS];  // <= 0: no clamp
+  uint64_t collide_mask;             // bit per entity
+  uint32_t silent_mask;              // bit per agent
+  double dt, damping, contact_force, contact_margin;
+};
+
+template <typename real> __device__ __forceinline__ real r_sqrt(real x);
+template <> __device__ __forceinline__ float r_sqrt<float>(float x) { return sqrtf(x); }
+template <> __device__ __forceinline__ double r_sqrt<double>(double x) { return sqrt(x); }
+template <typename real> __device__ __forceinline__ real r_exp(real x);
+template <> __device__ __forceinline__ float r_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ double r_exp<double>(double x) { return exp(x); }
+template <typename real> __device__ __forceinline__ real r_log1p(real x);
+template <> __device__ __forceinline__ float r_log1p<float>(float x) { return log1pf(x); }
+template <> __device__ __forceinline__ double r_log1p<double>(double x) { return log1p(x); }
+template <typename real> __device__ __forceinline__ real ent_size(const EnvParams& P, int j);
+template <> __device__ __forceinline__ float ent_size<float>(const EnvParams& P, int j) { return P.sizef[j]; }
+template <> __device__ __forceinline__ double ent_size<double>(const EnvParams& P, int j) { return P.size[j]; }
+
+// numpy.logaddexp(0, z): the soft-contact penetration of World.get_collision_force
+template <typename real>
+__device__ __forceinline__ real logaddexp0(real z) {
+  if (z == (real)0) return (real)0.693147180559945309417232121458;
+  if (z < (real)0) return r_log1p<real>(r_exp<real>(z));
+  return z + r_log1p<real>(r_exp<real>(-z));
+}
+
+// Scenario.bound(x) of simple_tag / simple_world_comm
+template <typename real>
+__device__ __forceinline__ real bound_pen(real x) {
+  if (x < (real)0.9) return (real)0;
+  if (x < (real)1.0) return (x - (real)0.9) * (real)10;
+  real e = r_exp<real>((real)2 * x - (real)2);
+  return e < (real)10 ? e : (real)10;
+}
+
+__device__ __forceinline__ int ent_comp(const EnvParams& P, int ent) {
+  return ent < P.A ? 4 * ent : 4 * P.A + P.cdim + 2 * (ent - P.A);
+}
+
+// Shared-memory tile of EB env instances.
+template <typename real, int EB>
+struct EnvTile {
+  static constexpr int EBP = EB + 1;
+  real* sS;   // [scomp][EBP] state
+  real* sR;   // [A][EBP] per-agent reward
+  real* sT;   // [A][EBP] scratch (simple_spread landmark minima)
+  int* sF;    // [A][EBP] forest flags (simple_world_comm)
+  float* sA;  // [EB][ASP] joint actions of the tile
+  int ASP;
+
+  __host__ __device__ static size_t bytes(int scomp, int A, int act_stride, bool with_actions) {
+    size_t b = ((size_t)scomp + 2 * A) * EBP * sizeof(real) + (size_t)A * EBP * sizeof(int);
+    if (with_actions) b += (size_t)EB * (act_stride | 1) * sizeof(float);
+    return (b + 15) & ~(size_t)15;
+  }
+  __device__ void carve(void* base, const EnvParams& P, float* actions_or_null) {
+    sS = reinterpret_cast<real*>(base);
+    sR = sS + (size_t)P.scomp * EBP;
+    sT = sR + (size_t)P.A * EBP;
+    sF = reinterpret_cast<int*>(sT + (size_t)P.A * EBP);
+    ASP = P.act_stride | 1;
+    sA = actions_or_null ? actions_or_null : reinterpret_cast<float*>(sF + (size_t)P.A * EBP);
+  }
+};
+
+template <typename real, int EB>
+__device__ __forceinline__ void env_load_state(const EnvParams& P, EnvTile<real, EB>& T, const real* __restrict__ state,
+                                               int E, int e0, int nE) {
+  constexpr int EBP = EB + 1;
+  for (int idx = threadIdx.x; idx < P.scomp * EB; idx += blockDim.x) {
+    const int comp = idx / EB, e = idx % EB;  // EB is a power of two: shifts
+    T.sS[comp * EBP + e] = (e < nE) ? state[(size_t)comp * E + e0 + e] : (real)0;
+  }
+}
+
+// movable state only (agents' pos/vel + comm); landmarks never move
+template <typename real, int EB>
+__device__ __forceinline__ void env_store_state(const EnvParams& P, const EnvTile<real, EB>& T, real* __restrict__ state,
+                                                int E, int e0, int nE, bool all_comps) {
+  constexpr int EBP = EB + 1;
+  const int wcomp = all_comps ? P.scomp : 4 * P.A + P.cdim;
+  for (int idx = threadIdx.x; idx < wcomp * EB; idx += blockDim.x) {
+    const int comp = idx / EB, e = idx % EB;
+    if (e < nE) state[(size_t)comp * E + e0 + e] = T.sS[comp * EBP + e];
+  }
+}
+
+template <typename real, int EB>
+__device__ __forceinline__ void env_load_actions(const EnvParams& P, EnvTile<real, EB>& T, const float* __restrict__ act,
+                                                 int e0, int nE) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int e = warp; e < nE; e += nwarps) {
+    const float* arow = act + (size_t)(e0 + e) * P.act_stride;
+    for (int c = lane; c < P.act_stride; c += 32) T.sA[e * T.ASP + c] = arow[c];
+  }
+}
+
+// World.step for the tile: thread tid < EB*A owns (env e = tid % EB, agent i = tid / EB) so warps are
+// agent-uniform.  Contains two __syncthreads; the new state is visible to the whole CTA on return.
+template <typename real, int EB>
+__device__ __forceinline__ void env_physics(const EnvParams& P, EnvTile<real, EB>& T, int nE) {
+  constexpr int EBP = EB + 1;
+  const int tid = threadIdx.x;
+  const int e = tid % EB, i = tid / EB;
+  const bool live = (i < P.A) && (e < nE);
+  real px = 0, py = 0, vx = 0, vy = 0;
+  if (live) {
+    real* sS = T.sS;
+    px = sS[(4 * i + 0) * EBP + e];
+    py = sS[(4 * i + 1) * EBP + e];
+    vx = sS[(4 * i + 2) * EBP + e];
+    vy = sS[(4 * i + 3) * EBP + e];
+    const float* a = T.sA + e * T.ASP + P.act_off[i];
+    // _set_action: float32 differences, then scaling by accel / 5.0 in the state precision
+    real fx = (real)(a[1] - a[2]);
+    real fy = (real)(a[3] - a[4]);
+    const real sens = (real)P.sens[i];
+    fx *= sens;
+    fy *= sens;
+    // apply_environment_force: soft contact with every other collidable entity, in partner order
+    if ((P.collide_mask >> i) & 1ull) {
+      const real k = (real)P.contact_margin, cf = (real)P.contact_force;
+      const real si = ent_size<real>(P, i);
+      // exact shortcut: exp(z) underflows to +0 below this, so the penetration is exactly 0
+      const real zmin = sizeof(real) == 4 ? (real)-104.0 : (real)-746.0;
+      for (int j = 0; j < P.NE; ++j) {
+        if (j == i || !((P.collide_mask >> j) & 1ull)) continue;
+        const int cj = ent_comp(P, j);
+        const real dx = px - sS[cj * EBP + e];
+        const real dy = py - sS[(cj + 1) * EBP + e];
+        const real dist = r_sqrt<real>(dx * dx + dy * dy);
+        const real dmin = si + ent_size<real>(P, j);
+        const real z = -(dist - dmin) / k;
+        if (z < zmin) continue;
+        const real pen = logaddexp0<real>(z) * k;
+        fx = cf * dx / dist * pen + fx;
+        fy = cf * dy / dist * pen + fy;
+      }
+    }
+    // integrate_state (mass = 1)
+    const real damp = (real)1 - (real)P.damping, dt = (real)P.dt;
+    vx = vx * damp;
+    vy = vy * damp;
+    vx += fx * dt;
+    vy += fy * dt;
+    const real ms = (real)P.max_speed[i];
+    if (ms > (real)0) {
+      const real speed = r_sqrt<real>(vx * vx + vy * vy);
+      if (speed > ms) {
+        vx = vx / speed * ms;
+        vy = vy / speed * ms;
+      }
+    }
+    px += vx * dt;
+    py += vy * dt;
+  }
+  __syncthreads();  // everyone has read the old positions
+  if (live) {
+    real* sS = T.sS;
+    sS[(4 * i + 0) * EBP + e] = px;
+    sS[(4 * i + 1) * EBP + e] = py;
+    sS[(4 * i + 2) * EBP + e] = vx;
+    sS[(4 * i + 3) * EBP + e] = vy;
+    // update_agent_state: non-silent agents publish their comm head (simple_world_comm leader)
+    if (P.cdim > 0 && !((P.silent_mask >> i) & 1u)) {
+      const float* a = T.sA + e * T.ASP + P.act_off[i] + 5;
+      for (int c = 0; c < P.cdim; ++c) sS[(4 * P.A + c) * EBP + e] = (real)a[c];
+    }
+  }
+  __syncthreads();
+}
+
+// Scenario rewards (DO_REWARD) and simple_world_comm forest flags from the current tile state.
+// On return sR[i][e] holds agent i's own reward (before the shared-reward sum).  Ends synchronised.
+template <typename real, int EB, bool DO_REWARD>
+__device__ __forceinline__ void env_flags_rewards(const EnvParams& P, EnvTile<real, EB>& T, int nE) {
+  constexpr int EBP = EB + 1;
+  const int tid = threadIdx.x;
+  const int e = tid % EB, i = tid / EB;
+  const bool live = (i < P.A) && (e < nE);
+  real* sS = T.sS;
+  auto PX = [&](int ent) -> real { return sS[ent_comp(P, ent) * EBP + e]; };
+  auto PY = [&](int ent) -> real { return sS[(ent_comp(P, ent) + 1) * EBP + e]; };
+  auto dist_ee = [&](int a, int b) -> real {
+    const real dx = PX(a) - PX(b), dy = PY(a) - PY(b);
+    return r_sqrt<real>(dx * dx + dy * dy);
+  };
+  auto collide_ee = [&](int a, int b) -> bool { return dist_ee(a, b) < ent_size<real>(P, a) + ent_size<real>(P, b); };
+
+  if (P.scenario == MDP_SIMPLE_WORLD_COMM && live) {
+    int f = 0;
+    for (int q = 0; q < P.n_forest; ++q)
+      if (collide_ee(i, P.A + P.forest0 + q)) f |= (1 << q);
+    T.sF[i * EBP + e] = f;
+  }
+  if (DO_REWARD) {
+    if (live) {
+      real r = 0;
+      if (P.scenario == MDP_SIMPLE) {
+        const real dx = PX(0) - PX(P.A), dy = PY(0) - PY(P.A);
+        r = -(dx * dx + dy * dy);
+      } else if (P.scenario == MDP_SIMPLE_SPREAD) {
+        // thread i owns landmark i: min over agents of the distance (the "occupied landmark" term)
+        real m = dist_ee(0, P.A + i);
+        for (int a = 1; a < P.A; ++a) {
+          const real d = dist_ee(a, P.A + i);
+          m = d < m ? d : m;
+        }
+        T.sT[i * EBP + e] = m;
+        int cnt = 0;  // includes a == i (distance 0 < 2*size): the reference's constant -1
+        for (int a = 0; a < P.A; ++a) cnt += collide_ee(a, i) ? 1 : 0;
+        r = (real)cnt;  // finished after the sync below
+      } else if (P.scenario == MDP_SIMPLE_TAG) {
+        if (i < P.n_adv) {
+          for (int g = P.n_adv; g < P.A; ++g)
+            for (int a = 0; a < P.n_adv; ++a)
+              if (collide_ee(g, a)) r += (real)10;
+        } else {
+          for (int a = 0; a < P.n_adv; ++a)
+            if (collide_ee(a, i)) r -= (real)10;
+          const real ax = PX(i), ay = PY(i);
+          r -= bound_pen<real>(ax < 0 ? -ax : ax);
+          r -= bound_pen<real>(ay < 0 ? -ay : ay);
+        }
+      } else {  // MDP_SIMPLE_WORLD_COMM
+        if (i < P.n_adv) {
+          real m = dist_ee(P.n_adv, i);
+          for (int g = P.n_adv + 1; g < P.A; ++g) {
+            const real d = dist_ee(g, i);
+            m = d < m ? d : m;
+          }
+          r -= (real)0.1 * m;
+          for (int g = P.n_adv; g < P.A; ++g)
+            for (int a = 0; a < P.n_adv; ++a)
+              if (collide_ee(g, a)) r += (real)5;
+        } else {
+          for (int a = 0; a < P.n_adv; ++a)
+            if (collide_ee(a, i)) r -= (real)5;
+          const real ax = PX(i), ay = PY(i);
+          r -= (real)2 * bound_pen<real>(ax < 0 ? -ax : ax);
+          r -= (real)2 * bound_pen<real>(ay < 0 ? -ay : ay);
+          real m = 0;
+          for (int q = 0; q < P.n_food; ++q) {
+            const int fe = P.A + P.food0 + q;
+            if (collide_ee(i, fe)) r += (real)2;
+            const real d = dist_ee(fe, i);
+            m = (q == 0 || d < m) ? d : m;
+          }
+          r += (real)0.05 * m;
+        }
+      }
+      T.sR[i * EBP + e] = r;
+    }
+    if (P.scenario == MDP_SIMPLE_SPREAD) {
+      __syncthreads();
+      real r = 0;
+      if (live) {
+        for (int l = 0; l < P.L; ++l) r -= T.sT[l * EBP + e];
+        r -= T.sR[i * EBP + e];  // collision count
+      }
+      __syncthreads();
+      if (live) T.sR[i * EBP + e] = r;
+    }
+  }
+  __syncthreads();
+}
+
+// reward agent ii of env ee receives (shared reward: the sum over agents, environment.py step())
+template <typename real, int EB>
+__device__ __forceinline__ float env_reward_out(const EnvParams& P, const EnvTile<real, EB>& T, int ee, int ii) {
+  constexpr int EBP = EB + 1;
+  if (P.collaborative) {
+    real r = 0;
+    for (int a = 0; a < P.A; ++a) r += T.sR[a * EBP + ee];
+    return (float)r;
+  }
+  return (float)T.sR[ii * EBP + ee];
+}
+
+// one observation column of env ee (joint layout), from the tile state
+template <typename real, int EB>
+__device__ __forceinline__ float env_obs_value(const EnvTile<real, EB>& T, const ObsCol d, int ee) {
+  constexpr int EBP = EB + 1;
+  const real* sS = T.sS;
+  real v = 0;
+  switch (d.kind) {
+    case OK_DIRECT: v = sS[d.a * EBP + ee]; break;
+    case OK_REL: v = sS[d.a * EBP + ee] - sS[d.b * EBP + ee]; break;
+    case OK_REL_MASK:
+    case OK_DIR_MASK: {
+      const int fi = T.sF[d.i * EBP + ee], fo = T.sF[d.o * EBP + ee];
+      const bool inf1 = fi & 1, inf2 = fi & 2, of1 = fo & 1, of2 = fo & 2;
+      const bool vis = (inf1 && of1) || (inf2 && of2) || (!inf1 && !of1 && !inf2 && !of2) || (d.i == 0);
+      if (vis) v = (d.kind == OK_REL_MASK) ? sS[d.a * EBP + ee] - sS[d.b * EBP + ee] : sS[d.a * EBP + ee];
+      break;
+    }
+    case OK_FOREST: v = ((T.sF[d.i * EBP + ee] >> d.k) & 1) ? (real)1 : (real)-1; break;
+    default: break;
+  }
+  return (float)v;
+}
+
+// reset_world draw for state component `comp` of env `e_global` (agents U(-1,1), landmarks U(lo,hi))
+template <typename real>
+__device__ __forceinline__ real env_reset_value(const EnvParams& P, int comp, long long e_global, uint64_t seed,
+                                                uint64_t episode, float lm_lo, float lm_hi) {
+  const bool agent_pos = comp < 4 * P.A && (comp & 3) < 2;
+  const bool lm_pos = comp >= 4 * P.A + P.cdim;
+  if (!(agent_pos || lm_pos)) return (real)0;
+  uint4 r = Philox::gen(seed, (uint32_t)e_global, (uint32_t)comp, (uint32_t)episode, (uint32_t)(episode >> 32) ^ 0x5EEDu);
+  const real u = sizeof(real) == 4 ? (real)Philox::u01(r.x) : (real)Philox::u01d(r.x, r.y);
+  const real lo = agent_pos ? (real)-1 : (real)lm_lo, hi = agent_pos ? (real)1 : (real)lm_hi;
+  return lo + (hi - lo) * u;
+}
+
+}  // namespace mdp
+
+struct mdp_env {
+  mdp_env_cfg cfg;
+  mdp_env_dims dims;
+  mdp::EnvParams P;
+  std::vector<mdp::ObsCol> cols;
+  mdp::ObsCol* d_cols = nullptr;
+  int d_cols_device = -1;
+  float reset_lo_lm, reset_hi_lm;
+  const unsigned long long* ctl = nullptr;
+};
+
+
+namespace mdp {
+// uploads the observation column table to the current device (lazy; not graph-capturable)
+int env_ensure_cols(mdp_env* env);
+}  // namespace mdp

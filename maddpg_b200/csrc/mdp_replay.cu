@@ -19,7 +19,9 @@ __global__ void k_replay_insert(mdp_ring_layout L, float* __restrict__ ring, lon
                                 int E, int agent, const float* __restrict__ obs, int obs_stride,
                                 const float* __restrict__ act, int act_stride, const float* __restrict__ rew,
                                 int rew_stride, const float* __restrict__ next_obs, int next_obs_stride,
-                                const uint8_t* __restrict__ done, int done_stride) {
+                                const uint8_t* __restrict__ done, int done_stride,
+                                const unsigned long long* __restrict__ ctl) {
+  if (ctl) cursor = (cursor + (long long)ctl[1]) % capacity;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (long long e = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); e < E;
@@ -123,9 +125,47 @@ __global__ void k_replay_gather_bulk(const float* __restrict__ ring, long long c
   }
 }
 
+// ctl = {philox_counter, ring_cursor, episode, ring_length}
+__global__ void k_ctl_advance(unsigned long long* ctl, unsigned long long d_counter, long long d_rows, long long capacity,
+                              unsigned long long d_episode) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ctl[0] += d_counter;
+    ctl[1] = (unsigned long long)(((long long)ctl[1] + d_rows) % capacity);
+    ctl[2] += d_episode;
+    long long len = (long long)ctl[3] + d_rows;
+    ctl[3] = (unsigned long long)(len > capacity ? capacity : len);
+  }
+}
+
+__global__ void k_replay_make_index(long long* __restrict__ idx_out, int B, long long length, uint64_t seed,
+                                    uint64_t counter, const unsigned long long* __restrict__ ctl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (ctl) counter += ctl[0];
+  if (length <= 0) length = (long long)ctl[3];
+  uint4 r = Philox::gen(seed, (uint32_t)b, 0x1D3Au, (uint32_t)counter, (uint32_t)(counter >> 32));
+  long long i = (long long)(Philox::u01d(r.x, r.y) * (double)length);
+  idx_out[b] = i < length ? i : length - 1;
+}
+
 }  // namespace mdp
 
 using namespace mdp;
+
+extern "C" int mdp_ctl_advance(uint64_t* ctl, uint64_t d_counter, int64_t d_rows, int64_t capacity, uint64_t d_episode,
+                               void* stream) {
+  MDP_REQUIRE(ctl && capacity > 0 && d_rows >= 0, "mdp_ctl_advance: bad argument");
+  k_ctl_advance<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)ctl, d_counter, d_rows, capacity, d_episode);
+  return check_launch("k_ctl_advance");
+}
+
+extern "C" int mdp_replay_make_index(int64_t* idx_out, int32_t B, int64_t length, uint64_t seed, uint64_t counter,
+                                     const uint64_t* ctl, void* stream) {
+  MDP_REQUIRE(idx_out && B > 0 && (length > 0 || ctl), "mdp_replay_make_index: bad argument");
+  k_replay_make_index<<<cdiv(B, 256), 256, 0, (cudaStream_t)stream>>>((long long*)idx_out, B, length, seed, counter,
+                                                                    (const unsigned long long*)ctl);
+  return check_launch("k_replay_make_index");
+}
 
 extern "C" int mdp_ring_make_layout(int32_t n_agents, const int32_t* obs_dim, const int32_t* act_dim,
                                     mdp_ring_layout* out) {
@@ -156,6 +196,14 @@ extern "C" int mdp_replay_insert(const mdp_ring_layout* lay, float* ring, int64_
                                  int32_t agent, const float* obs, int32_t obs_stride, const float* act,
                                  int32_t act_stride, const float* rew, int32_t rew_stride, const float* next_obs,
                                  int32_t next_obs_stride, const uint8_t* done, int32_t done_stride, void* stream) {
+  return mdp::replay_insert_ctl(lay, ring, capacity, cursor, E, agent, obs, obs_stride, act, act_stride, rew, rew_stride,
+                                next_obs, next_obs_stride, done, done_stride, nullptr, stream);
+}
+
+int mdp::replay_insert_ctl(const mdp_ring_layout* lay, float* ring, int64_t capacity, int64_t cursor, int32_t E,
+                           int32_t agent, const float* obs, int32_t obs_stride, const float* act, int32_t act_stride,
+                           const float* rew, int32_t rew_stride, const float* next_obs, int32_t next_obs_stride,
+                           const uint8_t* done, int32_t done_stride, const unsigned long long* ctl, void* stream) {
   MDP_REQUIRE(lay && ring && obs && act && rew && next_obs && done, "mdp_replay_insert: null argument");
   MDP_REQUIRE(capacity > 0 && E > 0 && E <= capacity && cursor >= 0 && cursor < capacity,
               "mdp_replay_insert: bad sizes (capacity %lld, cursor %lld, E %d)", (long long)capacity, (long long)cursor, E);
@@ -165,7 +213,7 @@ extern "C" int mdp_replay_insert(const mdp_ring_layout* lay, float* ring, int64_
   if (grid > 148 * 16) grid = 148 * 16;
   k_replay_insert<<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(*lay, ring, capacity, cursor, E, agent, obs, obs_stride,
                                                               act, act_stride, rew, rew_stride, next_obs,
-                                                              next_obs_stride, done, done_stride);
+                                                              next_obs_stride, done, done_stride, ctl);
   return check_launch("k_replay_insert");
 }
 

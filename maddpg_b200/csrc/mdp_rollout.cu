@@ -1,0 +1,287 @@
+// Persistent episode kernel: the whole lockstep rollout of experiments/train.py:110-133 --
+//   action_n = [agent.action(obs)]          maddpg/trainer/maddpg.py:151-152 (mlp_model + SoftCategoricalPd.sample)
+//   new_obs, rew, done = env.step(action_n) multiagent.environment.MultiAgentEnv.step
+//   agent.experience(...)                   maddpg/trainer/maddpg.py:154-156 -> ReplayBuffer.add
+//   env.reset() every max_episode_len steps train.py:127-129
+// -- for `steps` steps in ONE launch.  A CTA owns 32 env instances for the whole episode: their SoA
+// state, the joint observation tile, the sampled actions and (when they fit) ALL agents' actor
+// weights stay resident in shared memory; per step the only global traffic is the joint replay row
+// (obs_t, act_t, next_obs, rew, done) streaming out to the ring.  Results are identical to the
+// per-step path (mdp_actor_act + mdp_env_step with ring + mdp_env_reset) on the same Philox counters.
+#include "mdp_env_dev.cuh"
+#include "mdp_mlp.cuh"
+
+namespace mdp {
+
+constexpr int REB = 32;  // env instances per CTA == TM rows of the MLP tile
+static_assert(REB == TM, "the episode kernel maps one env instance to one MLP tile row");
+
+// acc += sA[rows 2ty, 2ty+1][0..kc) * sW[0..kc)[cols], A read with scalar loads (no alignment demands)
+template <int U>
+__device__ __forceinline__ void mma_tile_sa(const Grp& G, float (&acc)[2][U / 16], const float* __restrict__ sA, int lda,
+                                            const float* __restrict__ sW, int kc) {
+  const int ty = G.tid >> 4, tx = G.tid & 15;
+  const float* a0p = sA + (2 * ty) * lda;
+  const float* a1p = a0p + lda;
+#pragma unroll 2
+  for (int k = 0; k < kc; ++k) {
+    const float a0 = a0p[k], a1 = a1p[k];
+#pragma unroll
+    for (int g = 0; g < U / 64; ++g) {
+      const float4 w = *reinterpret_cast<const float4*>(sW + k * U + g * 64 + 4 * tx);
+      acc[0][4 * g + 0] = fmaf(a0, w.x, acc[0][4 * g + 0]);
+      acc[0][4 * g + 1] = fmaf(a0, w.y, acc[0][4 * g + 1]);
+      acc[0][4 * g + 2] = fmaf(a0, w.z, acc[0][4 * g + 2]);
+      acc[0][4 * g + 3] = fmaf(a0, w.w, acc[0][4 * g + 3]);
+      acc[1][4 * g + 0] = fmaf(a1, w.x, acc[1][4 * g + 0]);
+      acc[1][4 * g + 1] = fmaf(a1, w.y, acc[1][4 * g + 1]);
+      acc[1][4 * g + 2] = fmaf(a1, w.z, acc[1][4 * g + 2]);
+      acc[1][4 * g + 3] = fmaf(a1, w.w, acc[1][4 * g + 3]);
+    }
+  }
+}
+
+__host__ __device__ inline int actor_net_floats(int D, int U, int K) {
+  return ((D * U + U + U * U + U + U * K + K) + 3) & ~3;
+}
+
+struct RolloutArgs {
+  int E, steps, reset_after;
+  float* state;
+  float* obs;  // (E, obs_stride) joint current observations, in/out
+  float* ring;
+  long long capacity, cursor;
+  unsigned long long seed, counter, env_seed, episode;
+  float lm_lo, lm_hi;
+  const unsigned long long* ctl;
+  float* ep_return;  // optional (E, A): sum of rewards over the launch
+};
+
+// NG groups of NT = 256 threads; group g runs the actor MLPs of agents g, g+NG, ... concurrently with the
+// other groups (named barriers 1..NG); the env phases use all NG*256 threads.
+template <int U, bool RESIDENT>
+__global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
+                                                          mdp_ring_layout L, RolloutArgs R, int NG) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int HP = U + 4, EBP = REB + 1;
+  const int tid = threadIdx.x, NTB = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = NTB >> 5;
+  const int grp = tid / NT;
+  const Grp G{tid - grp * NT, grp + 1};
+  const int OS = P.obs_stride, A = P.A;
+  const int e0 = blockIdx.x * REB;
+  const int nE = min(REB, R.E - e0);
+
+  // ---- shared memory carve-up ------------------------------------------------------------------
+  SmemCarve sm(smem_raw);
+  float* sH1 = sm.take(NG * TM * HP) + grp * TM * HP;
+  float* sH2 = sm.take(NG * TM * HP) + grp * TM * HP;
+  float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
+  float* sObs = sm.take(TM * OS);
+  float* sAct = sm.take(TM * (P.act_stride | 1));
+  float* sRet = sm.take(A * EBP);
+  int* sOff = reinterpret_cast<int*>(sm.take(MDP_MAX_AGENTS + 1));
+  ObsCol* sCols = reinterpret_cast<ObsCol*>(sm.take(2 * OS));
+  float* sEnv = sm.take((int)(EnvTile<float, REB>::bytes(P.scomp, A, P.act_stride, false) / 4));
+  // RESIDENT: every agent's actor net ; else one [KC][U] staging chunk per group
+  float* sWts = RESIDENT ? sm.p : sm.p + grp * KC * U;
+  EnvTile<float, REB> T;
+  T.carve(sEnv, P, sAct);
+
+  unsigned long long counter = R.counter, episode = R.episode;
+  long long cursor = R.cursor;
+  if (R.ctl) {
+    counter += R.ctl[0];
+    cursor = (cursor + (long long)R.ctl[1]) % R.capacity;
+    episode += R.ctl[2];
+  }
+
+  // ---- prologue: state tile, observation tile, column table, actor weights -------------------------
+  env_load_state<float, REB>(P, T, R.state, R.E, e0, nE);
+  for (int ee = warp; ee < TM; ee += nwarps)
+    for (int c = lane; c < OS; c += 32) sObs[ee * OS + c] = (ee < nE) ? R.obs[(size_t)(e0 + ee) * OS + c] : 0.f;
+  for (int c = tid; c < OS; c += NTB) sCols[c] = cols[c];
+  for (int idx = tid; idx < A * EBP; idx += NTB) sRet[idx] = 0.f;
+  if (tid == 0) {
+    int o = 0;
+    for (int i = 0; i < A; ++i) {
+      sOff[i] = o;
+      o += actor_net_floats(C.agents[i].obs_dim, U, C.agents[i].act_dim);
+    }
+    sOff[A] = o;
+  }
+  __syncthreads();
+  if (RESIDENT) {
+    for (int i = 0; i < A; ++i) {
+      const float4* src = reinterpret_cast<const float4*>(C.agents[i].net[MDP_NET_P].W1);
+      float4* dst = reinterpret_cast<float4*>(sWts + sOff[i]);
+      const int n4 = (sOff[i + 1] - sOff[i]) >> 2;
+      for (int q = tid; q < n4; q += NTB) dst[q] = src[q];
+    }
+    __syncthreads();
+  }
+
+  // ---- the episode -----------------------------------------------------------------------------------
+  for (int s = 0; s < R.steps; ++s) {
+    // (1) actions: a_i = gumbel_softmax(mlp_i(obs_i)) for every agent
+    for (int i = grp; i < A; i += NG) {
+      const AgentDev& ag = C.agents[i];
+      const int D = ag.obs_dim, K = ag.act_dim;
+      MlpW w = ag.net[MDP_NET_P];
+      if (RESIDENT) {
+        const float* b = sWts + sOff[i];
+        w.W1 = b; b += D * U;
+        w.b1 = b; b += U;
+        w.W2 = b; b += U * U;
+        w.b2 = b; b += U;
+        w.W3 = b; b += U * K;
+        w.b3 = b;
+      }
+      float acc[2][U / 16];
+      zero_acc<U>(acc);
+      if (RESIDENT) {
+        mma_tile_sa<U>(G, acc, sObs + ag.obs_off, OS, w.W1, D);
+      } else {
+        for (int k0 = 0; k0 < D; k0 += KC) {
+          load_w_rows<U>(G, sWts, w.W1, k0, D);
+          G.sync();
+          mma_tile_sa<U>(G, acc, sObs + ag.obs_off + k0, OS, sWts, min(KC, D - k0));
+          G.sync();
+        }
+      }
+      store_bias_relu<U>(G, acc, w.b1, sH1);
+      G.sync();
+      if (RESIDENT) {
+        zero_acc<U>(acc);
+        mma_tile<U>(G, acc, sH1, HP, w.W2, U);
+      } else {
+        layer_h<U, false>(G, acc, sH1, w.W2, sWts);
+      }
+      store_bias_relu<U>(G, acc, w.b2, sH2);
+      G.sync();
+      actor_head<U>(G, sH2, w, sL);
+      gumbel_softmax_tile(G, sL, sAct + ag.act_off, T.ASP, nE, K, ag.n_heads, ag.head_dim, nullptr, 0, 0, (long long)e0, R.seed,
+                          counter + (unsigned long long)s + 1ull, (uint32_t)i);
+    }
+    __syncthreads();  // all groups' actions are in sAct
+    // (2) replay row, first half: obs_t and act_t
+    for (int ee = warp; ee < nE; ee += nwarps) {
+      float* row = R.ring + ((cursor + (long long)s * R.E + e0 + ee) % R.capacity) * (long long)L.row_stride;
+      for (int c = lane; c < L.obs_sum; c += 32) row[c] = sObs[ee * OS + c];
+      for (int c = lane; c < L.act_sum; c += 32) row[L.obs_sum + c] = sAct[ee * T.ASP + c];
+    }
+    // (3) World.step and rewards (both CTA-collective, synchronised on return)
+    env_physics<float, REB>(P, T, nE);
+    env_flags_rewards<float, REB, true>(P, T, nE);
+    // (4) next observations into the tile
+    for (int c = lane; c < OS; c += 32) {
+      const ObsCol d = sCols[c];
+      for (int ee = warp; ee < nE; ee += nwarps) sObs[ee * OS + c] = env_obs_value<float, REB>(T, d, ee);
+    }
+    __syncthreads();
+    // (5) replay row, second half: next_obs, rew, done
+    for (int ee = warp; ee < nE; ee += nwarps) {
+      float* row = R.ring + ((cursor + (long long)s * R.E + e0 + ee) % R.capacity) * (long long)L.row_stride;
+      for (int c = lane; c < L.obs_sum; c += 32) row[L.nx_off + c] = sObs[ee * OS + c];
+      if (lane < A) {
+        const float r = env_reward_out<float, REB>(P, T, ee, lane);
+        row[L.rw_off + lane] = r;
+        row[L.dn_off + lane] = 0.f;
+        sRet[lane * EBP + ee] += r;
+      }
+    }
+    // the next step's actor pass only reads sObs (complete) and rewrites sH1/sH2/sL/sAct, none of which
+    // phase (5) touches; sR is rewritten only after the barriers inside env_physics
+  }
+
+  // ---- epilogue: optional reset_world, then hand state and observations back ----------------------------
+  __syncthreads();
+  if (R.reset_after) {
+    for (int idx = tid; idx < P.scomp * REB; idx += NTB) {
+      const int comp = idx / REB, e = idx % REB;
+      T.sS[comp * EBP + e] = env_reset_value<float>(P, comp, e0 + e, R.env_seed, episode, R.lm_lo, R.lm_hi);
+    }
+    __syncthreads();
+    env_flags_rewards<float, REB, false>(P, T, nE);
+    for (int c = lane; c < OS; c += 32) {
+      const ObsCol d = sCols[c];
+      for (int ee = warp; ee < nE; ee += nwarps) sObs[ee * OS + c] = env_obs_value<float, REB>(T, d, ee);
+    }
+    __syncthreads();
+  }
+  env_store_state<float, REB>(P, T, R.state, R.E, e0, nE, R.reset_after != 0);
+  for (int ee = warp; ee < nE; ee += nwarps)
+    for (int c = lane; c < OS; c += 32) R.obs[(size_t)(e0 + ee) * OS + c] = sObs[ee * OS + c];
+  if (R.ep_return)
+    for (int idx = tid; idx < nE * A; idx += NTB) {
+      const int ee = idx / A, ii = idx - ee * A;
+      R.ep_return[(size_t)(e0 + ee) * A + ii] += sRet[ii * EBP + ee];
+    }
+}
+
+}  // namespace mdp
+
+using namespace mdp;
+
+namespace mdp {
+CoreDev core_dev_for_rollout(const mdp_core* c);
+}
+
+extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
+                                   int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
+                                   uint64_t seed, uint64_t counter, int32_t reset_after, uint64_t env_seed,
+                                   uint64_t episode, float* ep_return, void* stream) {
+  MDP_REQUIRE(env && core && core->d_agents, "mdp_rollout_episode: env/core not ready");
+  MDP_REQUIRE(state && obs && ring && E > 0 && steps > 0 && ring_capacity >= (int64_t)E * steps,
+              "mdp_rollout_episode: bad argument (E %d, steps %d, capacity %lld)", E, steps, (long long)ring_capacity);
+  if (env->cfg.state_f64) return fail(MDP_ENOTSUP, "mdp_rollout_episode: float64 state is served by the per-step kernels");
+  const EnvParams& P = env->P;
+  MDP_REQUIRE(P.A == core->cfg.n_agents, "mdp_rollout_episode: env has %d agents, core %d", P.A, core->cfg.n_agents);
+  for (int i = 0; i < P.A; ++i)
+    MDP_REQUIRE(env->dims.obs_dim[i] == core->cfg.obs_dim[i] && env->dims.act_dim[i] == core->cfg.act_dim[i],
+                "mdp_rollout_episode: agent %d dims differ between env and core", i);
+  mdp_ring_layout lay;
+  int rc = mdp_ring_make_layout(P.A, env->dims.obs_dim, env->dims.act_dim, &lay);
+  if (rc) return rc;
+  MDP_REQUIRE(lay.row_stride == ring_row_stride, "mdp_rollout_episode: ring_row_stride %d != layout %d", ring_row_stride, lay.row_stride);
+  rc = env_ensure_cols(env);
+  if (rc) return rc;
+  const int U = core->cfg.num_units, HP = U + 4;
+  size_t wts = 0;
+  for (int i = 0; i < P.A; ++i) wts += actor_net_floats(core->cfg.obs_dim[i], U, core->cfg.act_dim[i]);
+  auto r4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
+  const size_t limit = 200 * 1024;
+  // agent groups of 256 threads running concurrently: as many as fit (<= 1024 threads, <= ~200 KB smem)
+  int NG = 0;
+  bool resident = false;
+  size_t smem = 0;
+  for (int ng = P.A < 4 ? P.A : 4; ng >= 1 && NG == 0; --ng) {
+    if (ng * NT < REB * P.A) break;  // the physics phase needs one thread per (env, agent)
+    const size_t base = 2 * r4((size_t)ng * TM * HP) + r4((size_t)ng * TM * KPAD) + r4((size_t)TM * P.obs_stride) +
+                        r4((size_t)TM * (P.act_stride | 1)) + r4((size_t)P.A * (REB + 1)) + r4(MDP_MAX_AGENTS + 1) +
+                        r4(2 * (size_t)P.obs_stride) + r4(EnvTile<float, REB>::bytes(P.scomp, P.A, P.act_stride, false) / 4);
+    const size_t smem_res = (base + wts + 16) * 4, smem_str = (base + (size_t)ng * KC * U + 16) * 4;
+    if (smem_res <= limit) { NG = ng; resident = true; smem = smem_res; }
+    else if (smem_str <= limit) { NG = ng; resident = false; smem = smem_str; }
+  }
+  if (NG == 0)
+    return fail(MDP_ENOTSUP, "mdp_rollout_episode: %d agents x %d observation floats do not fit one CTA's shared memory",
+                P.A, P.obs_stride);
+  RolloutArgs R;
+  R.E = E; R.steps = steps; R.reset_after = reset_after;
+  R.state = (float*)state; R.obs = obs; R.ring = ring;
+  R.capacity = ring_capacity; R.cursor = ring_cursor;
+  R.seed = seed; R.counter = counter; R.env_seed = env_seed; R.episode = episode;
+  R.lm_lo = env->reset_lo_lm; R.lm_hi = env->reset_hi_lm;
+  R.ctl = env->ctl ? env->ctl : core->ctl;
+  R.ep_return = ep_return;
+  CoreDev d = core_dev_for_rollout(core);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto kern) -> int {
+    if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<cdiv(E, REB), NG * NT, smem, st>>>(d, P, env->d_cols, lay, R, NG);
+    return check_launch("k_rollout_episode");
+  };
+  if (U == 64) return resident ? go(k_rollout_episode<64, true>) : go(k_rollout_episode<64, false>);
+  return resident ? go(k_rollout_episode<128, true>) : go(k_rollout_episode<128, false>);
+}

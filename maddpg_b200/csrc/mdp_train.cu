@@ -16,365 +16,11 @@
 // live in smem, per-CTA weight-gradient partials are reduced into the flat gradient bucket with
 // fp32 RED atomics.  The fp32 SIMT path is the parity path (1e-4 on Q/loss needs ~fp32 products);
 // see DESIGN.md for the tensor-core plan.
-#include "mdp_core.cuh"
+#include "mdp_mlp.cuh"
 
 #include <new>
 
 namespace mdp {
-
-constexpr int TM = 32;    // batch rows per CTA
-constexpr int NT = 256;   // threads per CTA: 16 (row pairs) x 16 (column quads)
-constexpr int KC = 32;    // K-chunk streamed through shared memory
-constexpr int XP = KC + 4;
-constexpr int KPAD = 12;  // pitch of per-row action/logit scratch (max act_dim 9)
-constexpr int MAXK = 9;
-
-// Layer-1 input: up to two global column segments plus an optional shared-memory override range
-// (the freshly sampled action that replaces the replayed one).
-struct XSrc {
-  const float* g0; int ld0, n0;
-  const float* g1; int ld1, n1;
-  const float* s_over; int over_ld, over_c0, over_n;
-  __device__ __forceinline__ float get(int r_local, long long r_global, int c) const {
-    if (c >= over_c0 && c < over_c0 + over_n) return s_over[r_local * over_ld + (c - over_c0)];
-    if (c < n0) return g0[r_global * ld0 + c];
-    c -= n0;
-    if (c < n1) return g1[r_global * ld1 + c];
-    return 0.f;
-  }
-};
-
-__device__ __forceinline__ XSrc make_xsrc(const float* g0, int ld0, int n0) {
-  XSrc x; x.g0 = g0; x.ld0 = ld0; x.n0 = n0; x.g1 = nullptr; x.ld1 = 0; x.n1 = 0;
-  x.s_over = nullptr; x.over_ld = 0; x.over_c0 = 0; x.over_n = 0; return x;
-}
-
-// ---------------------------------------------------------------------------------------------
-// tile primitives.  Thread (ty, tx) = (tid >> 4, tid & 15) owns rows {2ty, 2ty+1} and columns
-// {64g + 4tx .. +3 : g < U/64} of a TM x U tile.
-// ---------------------------------------------------------------------------------------------
-template <int U>
-__device__ __forceinline__ void zero_acc(float (&acc)[2][U / 16]) {
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int c = 0; c < U / 16; ++c) acc[r][c] = 0.f;
-}
-
-template <int U>
-__device__ __forceinline__ void mma_tile(float (&acc)[2][U / 16], const float* __restrict__ sA, int lda,
-                                         const float* __restrict__ sW, int kc) {
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  const float* a0p = sA + (2 * ty) * lda;
-  const float* a1p = a0p + lda;
-#pragma unroll 2
-  for (int k = 0; k < kc; k += 4) {
-    const float4 a0 = *reinterpret_cast<const float4*>(a0p + k);
-    const float4 a1 = *reinterpret_cast<const float4*>(a1p + k);
-    const float a0v[4] = {a0.x, a0.y, a0.z, a0.w};
-    const float a1v[4] = {a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int g = 0; g < U / 64; ++g) {
-        const float4 w = *reinterpret_cast<const float4*>(sW + (k + kk) * U + g * 64 + 4 * tx);
-        acc[0][4 * g + 0] = fmaf(a0v[kk], w.x, acc[0][4 * g + 0]);
-        acc[0][4 * g + 1] = fmaf(a0v[kk], w.y, acc[0][4 * g + 1]);
-        acc[0][4 * g + 2] = fmaf(a0v[kk], w.z, acc[0][4 * g + 2]);
-        acc[0][4 * g + 3] = fmaf(a0v[kk], w.w, acc[0][4 * g + 3]);
-        acc[1][4 * g + 0] = fmaf(a1v[kk], w.x, acc[1][4 * g + 0]);
-        acc[1][4 * g + 1] = fmaf(a1v[kk], w.y, acc[1][4 * g + 1]);
-        acc[1][4 * g + 2] = fmaf(a1v[kk], w.z, acc[1][4 * g + 2]);
-        acc[1][4 * g + 3] = fmaf(a1v[kk], w.w, acc[1][4 * g + 3]);
-      }
-    }
-  }
-}
-
-// rows [k0, k0+KC) of a row-major (K, U) weight -> sW[KC][U], zero past K
-template <int U>
-__device__ __forceinline__ void load_w_rows(float* __restrict__ sW, const float* __restrict__ W, int k0, int K) {
-  for (int idx = threadIdx.x * 4; idx < KC * U; idx += NT * 4) {
-    const int k = idx / U;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k0 + k < K) v = *reinterpret_cast<const float4*>(W + (size_t)(k0 + k) * U + (idx - k * U));
-    *reinterpret_cast<float4*>(sW + idx) = v;
-  }
-}
-
-// transposed chunk of a (U, U) weight: sW[ul][k] = W[k][u0 + ul]  (for dX = dY * W^T)
-template <int U>
-__device__ __forceinline__ void load_wT_rows(float* __restrict__ sW, const float* __restrict__ W, int u0) {
-  for (int idx = threadIdx.x; idx < KC * U; idx += NT) {
-    const int ul = idx / U, k = idx - ul * U;
-    sW[idx] = W[(size_t)k * U + u0 + ul];
-  }
-}
-
-__device__ __forceinline__ void load_x_chunk(float* __restrict__ sX, const XSrc& xs, long long row0, int nrows, int k0) {
-  for (int idx = threadIdx.x; idx < TM * KC; idx += NT) {
-    const int r = idx >> 5, c = idx & 31;
-    sX[r * XP + c] = (r < nrows) ? xs.get(r, row0 + r, k0 + c) : 0.f;
-  }
-}
-
-// acc = X[rows] * W1 streamed in K-chunks (ends synchronised)
-template <int U>
-__device__ __forceinline__ void layer1(float (&acc)[2][U / 16], const XSrc& xs, int K, const float* __restrict__ W1,
-                                       long long row0, int nrows, float* sX, float* sW) {
-  zero_acc<U>(acc);
-  for (int k0 = 0; k0 < K; k0 += KC) {
-    load_x_chunk(sX, xs, row0, nrows, k0);
-    load_w_rows<U>(sW, W1, k0, K);
-    __syncthreads();
-    mma_tile<U>(acc, sX, XP, sW, KC);
-    __syncthreads();
-  }
-}
-
-// acc = sA[TM][U] * W (U,U)   (TRANSPOSED: * W^T), W streamed in KC-row chunks (ends synchronised)
-template <int U, bool TRANSPOSED>
-__device__ __forceinline__ void layer_h(float (&acc)[2][U / 16], const float* __restrict__ sA, const float* __restrict__ W,
-                                        float* sW) {
-  constexpr int HP = U + 4;
-  zero_acc<U>(acc);
-  for (int k0 = 0; k0 < U; k0 += KC) {
-    if (TRANSPOSED) load_wT_rows<U>(sW, W, k0); else load_w_rows<U>(sW, W, k0, U);
-    __syncthreads();
-    mma_tile<U>(acc, sA + k0, HP, sW, KC);
-    __syncthreads();
-  }
-}
-
-// sH[r][c] = relu(acc + bias[c])   (caller synchronises)
-template <int U>
-__device__ __forceinline__ void store_bias_relu(const float (&acc)[2][U / 16], const float* __restrict__ bias, float* sH) {
-  constexpr int HP = U + 4;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-#pragma unroll
-  for (int g = 0; g < U / 64; ++g) {
-    const int c = g * 64 + 4 * tx;
-    const float4 b = *reinterpret_cast<const float4*>(bias + c);
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      float4 v;
-      v.x = fmaxf(acc[rr][4 * g + 0] + b.x, 0.f);
-      v.y = fmaxf(acc[rr][4 * g + 1] + b.y, 0.f);
-      v.z = fmaxf(acc[rr][4 * g + 2] + b.z, 0.f);
-      v.w = fmaxf(acc[rr][4 * g + 3] + b.w, 0.f);
-      *reinterpret_cast<float4*>(sH + (2 * ty + rr) * HP + c) = v;
-    }
-  }
-}
-
-// sH[r][c] = (sH[r][c] > 0) ? acc : 0     in place: dz = dh * relu'(h)   (caller synchronises)
-template <int U>
-__device__ __forceinline__ void store_masked(const float (&acc)[2][U / 16], float* sH) {
-  constexpr int HP = U + 4;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-#pragma unroll
-  for (int g = 0; g < U / 64; ++g) {
-    const int c = g * 64 + 4 * tx;
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      float4 h = *reinterpret_cast<const float4*>(sH + (2 * ty + rr) * HP + c);
-      h.x = h.x > 0.f ? acc[rr][4 * g + 0] : 0.f;
-      h.y = h.y > 0.f ? acc[rr][4 * g + 1] : 0.f;
-      h.z = h.z > 0.f ? acc[rr][4 * g + 2] : 0.f;
-      h.w = h.w > 0.f ? acc[rr][4 * g + 3] : 0.f;
-      *reinterpret_cast<float4*>(sH + (2 * ty + rr) * HP + c) = h;
-    }
-  }
-}
-
-// h1 -> sH1, h2 -> sH2 for the tile (ends synchronised)
-template <int U>
-__device__ __forceinline__ void forward_hidden(const XSrc& xs, const MlpW& w, long long row0, int nrows, float* sX,
-                                               float* sW, float* sH1, float* sH2) {
-  float acc[2][U / 16];
-  layer1<U>(acc, xs, w.in, w.W1, row0, nrows, sX, sW);
-  store_bias_relu<U>(acc, w.b1, sH1);
-  __syncthreads();
-  layer_h<U, false>(acc, sH1, w.W2, sW);
-  store_bias_relu<U>(acc, w.b2, sH2);
-  __syncthreads();
-}
-
-// out_dim == 1 head: sQ[r] = h2[r,:] . W3 + b3   (8 threads per row; ends synchronised)
-template <int U>
-__device__ __forceinline__ void critic_head(const float* __restrict__ sH2, const MlpW& w, float* sQ) {
-  constexpr int HP = U + 4;
-  const int row = threadIdx.x >> 3, part = threadIdx.x & 7;
-  float s = 0.f;
-  for (int u = part; u < U; u += 8) s = fmaf(sH2[row * HP + u], w.W3[u], s);
-  s += __shfl_xor_sync(0xffffffffu, s, 4);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  if (part == 0) sQ[row] = s + w.b3[0];
-  __syncthreads();
-}
-
-// general head: sL[r][a] = h2[r,:] . W3[:,a] + b3[a], a < out   (ends synchronised)
-template <int U>
-__device__ __forceinline__ void actor_head(const float* __restrict__ sH2, const MlpW& w, float* sL) {
-  constexpr int HP = U + 4;
-  const int K = w.out;
-  for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
-    const int r = idx / K, a = idx - r * K;
-    float s = 0.f;
-    for (int u = 0; u < U; ++u) s = fmaf(sH2[r * HP + u], w.W3[u * K + a], s);
-    sL[r * KPAD + a] = s + w.b3[a];
-  }
-  __syncthreads();
-}
-
-// Gumbel-softmax per (row, head): softmax(logits - log(-log u))   (ends synchronised)
-__device__ __forceinline__ void gumbel_softmax_tile(const float* __restrict__ sL, float* __restrict__ sOut, int out_ld,
-                                                    int nrows, int n_heads, const int* head_dim,
-                                                    const float* __restrict__ u_glob, int u_ld, int u_col0,
-                                                    long long row0, uint64_t seed, uint64_t counter, uint32_t tag) {
-  for (int idx = threadIdx.x; idx < TM * n_heads; idx += NT) {
-    const int r = idx / n_heads, h = idx - r * n_heads;
-    if (r >= nrows) continue;
-    const int o = h ? head_dim[0] : 0, n = head_dim[h];
-    float z[MAXK];
-    float m = -INFINITY;
-    uint4 rnd = make_uint4(0, 0, 0, 0);
-    for (int a = 0; a < n; ++a) {
-      float u;
-      if (u_glob) {
-        u = u_glob[(row0 + r) * u_ld + u_col0 + o + a];
-      } else {
-        if ((a & 3) == 0)
-          rnd = Philox::gen(seed, (uint32_t)(row0 + r), (uint32_t)((row0 + r) >> 32) ^ (tag << 8) ^ (uint32_t)(o + a),
-                            (uint32_t)counter, (uint32_t)(counter >> 32));
-        const uint32_t x = (a & 3) == 0 ? rnd.x : (a & 3) == 1 ? rnd.y : (a & 3) == 2 ? rnd.z : rnd.w;
-        u = Philox::u01(x);
-      }
-      z[a] = sL[r * KPAD + o + a] + gumbel_from_u(u);
-      m = fmaxf(m, z[a]);
-    }
-    float s = 0.f;
-    for (int a = 0; a < n; ++a) {
-      z[a] = expf(z[a] - m);
-      s += z[a];
-    }
-    for (int a = 0; a < n; ++a) sOut[r * out_ld + o + a] = z[a] / s;
-  }
-  __syncthreads();
-}
-
-// gW (U,U) += sA^T (h, TM x U) * sD (dz, TM x U); thread owns rows ty*RN.. and the usual columns
-template <int U>
-__device__ __forceinline__ void grad_w_hidden(const float* __restrict__ sA, const float* __restrict__ sD, float* __restrict__ gW) {
-  constexpr int HP = U + 4, RN = U / 16;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc[RN][RN];
-#pragma unroll
-  for (int a = 0; a < RN; ++a)
-#pragma unroll
-    for (int b = 0; b < RN; ++b) acc[a][b] = 0.f;
-  for (int r = 0; r < TM; ++r) {
-    float av[RN], dv[RN];
-#pragma unroll
-    for (int q = 0; q < RN / 4; ++q) {
-      const float4 t = *reinterpret_cast<const float4*>(sA + r * HP + ty * RN + 4 * q);
-      av[4 * q + 0] = t.x; av[4 * q + 1] = t.y; av[4 * q + 2] = t.z; av[4 * q + 3] = t.w;
-      const float4 d = *reinterpret_cast<const float4*>(sD + r * HP + q * 64 + 4 * tx);
-      dv[4 * q + 0] = d.x; dv[4 * q + 1] = d.y; dv[4 * q + 2] = d.z; dv[4 * q + 3] = d.w;
-    }
-#pragma unroll
-    for (int a = 0; a < RN; ++a)
-#pragma unroll
-      for (int b = 0; b < RN; ++b) acc[a][b] = fmaf(av[a], dv[b], acc[a][b]);
-  }
-#pragma unroll
-  for (int a = 0; a < RN; ++a)
-#pragma unroll
-    for (int b = 0; b < RN; ++b)
-      atomicAdd(gW + (size_t)(ty * RN + a) * U + (b / 4) * 64 + 4 * tx + (b & 3), acc[a][b]);
-}
-
-// gW1 rows [k0, k0+KC) += sX^T (TM x KC chunk) * sD (TM x U)
-template <int U>
-__device__ __forceinline__ void grad_w_chunk(const float* __restrict__ sX, const float* __restrict__ sD,
-                                             float* __restrict__ gW1, int k0, int K) {
-  constexpr int HP = U + 4, RN = U / 16;
-  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  float acc[2][RN];
-  zero_acc<U>(acc);
-  for (int r = 0; r < TM; ++r) {
-    const float2 a = *reinterpret_cast<const float2*>(sX + r * XP + 2 * ty);
-#pragma unroll
-    for (int q = 0; q < RN / 4; ++q) {
-      const float4 d = *reinterpret_cast<const float4*>(sD + r * HP + q * 64 + 4 * tx);
-      acc[0][4 * q + 0] = fmaf(a.x, d.x, acc[0][4 * q + 0]);
-      acc[0][4 * q + 1] = fmaf(a.x, d.y, acc[0][4 * q + 1]);
-      acc[0][4 * q + 2] = fmaf(a.x, d.z, acc[0][4 * q + 2]);
-      acc[0][4 * q + 3] = fmaf(a.x, d.w, acc[0][4 * q + 3]);
-      acc[1][4 * q + 0] = fmaf(a.y, d.x, acc[1][4 * q + 0]);
-      acc[1][4 * q + 1] = fmaf(a.y, d.y, acc[1][4 * q + 1]);
-      acc[1][4 * q + 2] = fmaf(a.y, d.z, acc[1][4 * q + 2]);
-      acc[1][4 * q + 3] = fmaf(a.y, d.w, acc[1][4 * q + 3]);
-    }
-  }
-#pragma unroll
-  for (int rr = 0; rr < 2; ++rr) {
-    const int k = k0 + 2 * ty + rr;
-    if (k < K) {
-#pragma unroll
-      for (int b = 0; b < RN; ++b) atomicAdd(gW1 + (size_t)k * U + (b / 4) * 64 + 4 * tx + (b & 3), acc[rr][b]);
-    }
-  }
-}
-
-template <int U>
-__device__ __forceinline__ void grad_bias(const float* __restrict__ sD, float* __restrict__ gb) {
-  constexpr int HP = U + 4;
-  if (threadIdx.x < U) {
-    float s = 0.f;
-    for (int r = 0; r < TM; ++r) s += sD[r * HP + threadIdx.x];
-    atomicAdd(gb + threadIdx.x, s);
-  }
-}
-
-// full backward below the second hidden layer: given dz2 in sH2 (already masked) and h1 in sH1,
-// accumulates gW2, gb2, then dz1 -> sH1 (in place), then optionally gW1/gb1 (re-streaming X).
-template <int U>
-__device__ __forceinline__ void backward_hidden(const XSrc& xs, const MlpW& w, const MlpG* g, long long row0, int nrows,
-                                                float* sX, float* sW, float* sH1, float* sH2) {
-  if (g) {
-    grad_w_hidden<U>(sH1, sH2, g->W2);
-    grad_bias<U>(sH2, g->b2);
-  }
-  float acc[2][U / 16];
-  __syncthreads();
-  layer_h<U, true>(acc, sH2, w.W2, sW);  // dh1 = dz2 * W2^T
-  store_masked<U>(acc, sH1);              // dz1 = dh1 * relu'(h1)
-  __syncthreads();
-  if (g) {
-    grad_bias<U>(sH1, g->b1);
-    for (int k0 = 0; k0 < w.in; k0 += KC) {
-      load_x_chunk(sX, xs, row0, nrows, k0);
-      __syncthreads();
-      grad_w_chunk<U>(sX, sH1, g->W1, k0, w.in);
-      __syncthreads();
-    }
-  }
-}
-
-struct SmemCarve {
-  float* p;
-  __device__ explicit SmemCarve(void* base) : p(reinterpret_cast<float*>(base)) {}
-  __device__ float* take(int nfloats) {
-    float* r = p;
-    p += (nfloats + 3) & ~3;
-    return r;
-  }
-};
-
-template <int U>
-constexpr int smem_floats_base() { return KC * U + TM * XP + 2 * TM * (U + 4); }
 
 // ---------------------------------------------------------------------------------------------
 // K1: grouped actor inference + Gumbel-softmax.  grid = (ceil(E/TM), agent_count)
@@ -384,7 +30,9 @@ __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, in
                                                   const float* __restrict__ obs, int obs_stride, float* __restrict__ act,
                                                   int act_stride, const float* __restrict__ u, uint64_t seed,
                                                   uint64_t counter, float* __restrict__ logits_out) {
+  if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
   float* sW = sm.take(KC * U);
   float* sX = sm.take(TM * XP);
@@ -398,9 +46,9 @@ __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, in
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, E - row0);
   XSrc xs = make_xsrc(obs + ag.obs_off, obs_stride, ag.obs_dim);
-  forward_hidden<U>(xs, w, row0, nrows, sX, sW, sH1, sH2);
-  actor_head<U>(sH2, w, sL);
-  gumbel_softmax_tile(sL, sA, KPAD, nrows, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off, row0, seed, counter,
+  forward_hidden<U>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  actor_head<U>(G, sH2, w, sL);
+  gumbel_softmax_tile(G, sL, sA, KPAD, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off, row0, seed, counter,
                       (uint32_t)i);
   for (int idx = threadIdx.x; idx < nrows * ag.act_dim; idx += NT) {
     const int r = idx / ag.act_dim, a = idx - r * ag.act_dim;
@@ -416,6 +64,7 @@ template <int U>
 __global__ void __launch_bounds__(NT) k_critic_q(CoreDev C, int agent, int use_target, int B, const float* __restrict__ x,
                                                  int x_stride, float* __restrict__ q_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
   float* sW = sm.take(KC * U);
   float* sX = sm.take(TM * XP);
@@ -433,8 +82,8 @@ __global__ void __launch_bounds__(NT) k_critic_q(CoreDev C, int agent, int use_t
   } else {
     xs = make_xsrc(x, x_stride, C.obs_sum + C.act_sum);
   }
-  forward_hidden<U>(xs, w, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(sH2, w, sQ);
+  forward_hidden<U>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(G, sH2, w, sQ);
   if (threadIdx.x < nrows) q_out[row0 + threadIdx.x] = sQ[threadIdx.x];
 }
 
@@ -446,7 +95,9 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
                                                   const float* __restrict__ u_target, int u_stride, uint64_t seed,
                                                   uint64_t counter, float* __restrict__ y_out,
                                                   float* __restrict__ target_act_out) {
+  if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
   float* sW = sm.take(KC * U);
   float* sX = sm.take(TM * XP);
@@ -466,9 +117,9 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
   for (int i = i_begin; i < i_end; ++i) {
     const AgentDev& ag = C.agents[i];
     XSrc xs = make_xsrc(batch + L.nx_off + ag.obs_off, R, ag.obs_dim);
-    forward_hidden<U>(xs, ag.net[MDP_NET_TARGET_P], row0, nrows, sX, sW, sH1, sH2);
-    actor_head<U>(sH2, ag.net[MDP_NET_TARGET_P], sL);
-    gumbel_softmax_tile(sL, sAct + ag.act_off, ASP, nrows, ag.n_heads, ag.head_dim, u_target, u_stride, ag.act_off, row0,
+    forward_hidden<U>(G, xs, ag.net[MDP_NET_TARGET_P], row0, nrows, sX, sW, sH1, sH2);
+    actor_head<U>(G, sH2, ag.net[MDP_NET_TARGET_P], sL);
+    gumbel_softmax_tile(G, sL, sAct + ag.act_off, ASP, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u_target, u_stride, ag.act_off, row0,
                         seed, counter, (uint32_t)(0x100 + i));
   }
   if (target_act_out) {
@@ -488,8 +139,8 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
     xs.s_over = sAct; xs.over_ld = ASP; xs.over_c0 = C.obs_sum; xs.over_n = C.act_sum;
   }
   const MlpW& tq = me.net[MDP_NET_TARGET_Q];
-  forward_hidden<U>(xs, tq, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(sH2, tq, sQ);
+  forward_hidden<U>(G, xs, tq, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(G, sH2, tq, sQ);
   // y = float32(rew + gamma * (1 - done) * q')  -- float64 combine like numpy (maddpg.py:186)
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
@@ -523,6 +174,7 @@ template <int U>
 __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                      const float* __restrict__ y, float* __restrict__ q_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Grp G{(int)threadIdx.x, 0};
   constexpr int HP = U + 4;
   SmemCarve sm(smem_raw);
   float* sW = sm.take(KC * U);
@@ -545,8 +197,8 @@ __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_
   } else {
     xs = make_xsrc(batch, R, L.x_dim);
   }
-  forward_hidden<U>(xs, w, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(sH2, w, sQ);
+  forward_hidden<U>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(G, sH2, w, sQ);
   // dL/dq = 2 (q - y) / B ; loss partial
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
@@ -582,7 +234,7 @@ __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_
     sH2[r * HP + u] = h > 0.f ? sDq[r] * w.W3[u] : 0.f;
   }
   __syncthreads();
-  backward_hidden<U>(xs, w, &g, row0, nrows, sX, sW, sH1, sH2);
+  backward_hidden<U>(G, xs, w, &g, row0, nrows, sX, sW, sH1, sH2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -593,7 +245,9 @@ template <int U>
 __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                     const float* __restrict__ u_actor, int u_stride, uint64_t seed,
                                                     uint64_t counter) {
+  if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Grp G{(int)threadIdx.x, 0};
   constexpr int HP = U + 4;
   SmemCarve sm(smem_raw);
   float* sW = sm.take(KC * U);
@@ -617,9 +271,9 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
 
   // actor forward on o_j, fresh Gumbel-softmax sample (maddpg.py:49)
   XSrc xp = make_xsrc(batch + me.obs_off, R, me.obs_dim);
-  forward_hidden<U>(xp, pw, row0, nrows, sX, sW, sP1, sP2);
-  actor_head<U>(sP2, pw, sL);
-  gumbel_softmax_tile(sL, sA, KPAD, nrows, me.n_heads, me.head_dim, u_actor, u_stride, me.act_off, row0, seed, counter,
+  forward_hidden<U>(G, xp, pw, row0, nrows, sX, sW, sP1, sP2);
+  actor_head<U>(G, sP2, pw, sL);
+  gumbel_softmax_tile(G, sL, sA, KPAD, nrows, me.act_dim, me.n_heads, me.head_dim, u_actor, u_stride, me.act_off, row0, seed, counter,
                       (uint32_t)(0x200 + j));
   // running critic on [o, a_-j, a_hat_j]
   XSrc xq;
@@ -632,8 +286,8 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
     a_col0 = L.obs_sum + me.act_off;
   }
   xq.s_over = sA; xq.over_ld = KPAD; xq.over_c0 = a_col0; xq.over_n = K;
-  forward_hidden<U>(xq, qw, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(sH2, qw, sQ);
+  forward_hidden<U>(G, xq, qw, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U>(G, sH2, qw, sQ);
   // loss partials: sum(-q), sum(logits^2)
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
@@ -659,7 +313,7 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
     sH2[r * HP + u] = (h > 0.f && r < nrows) ? dq * qw.W3[u] : 0.f;
   }
   __syncthreads();
-  backward_hidden<U>(xq, qw, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 (critic) now in sH1
+  backward_hidden<U>(G, xq, qw, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 (critic) now in sH1
   // dQ/da[r][a] = dz1[r,:] . W1[a_col0 + a, :]
   for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
     const int r = idx / K, a = idx - r * K;
@@ -705,7 +359,7 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
     sP2[r * HP + u] = s;
   }
   __syncthreads();
-  backward_hidden<U>(xp, pw, &pg, row0, nrows, sX, sW, sP1, sP2);
+  backward_hidden<U>(G, xp, pw, &pg, row0, nrows, sX, sW, sP1, sP2);
 }
 
 }  // namespace mdp
@@ -744,9 +398,11 @@ static CoreDev core_dev(const mdp_core* c) {
   d.units = c->cfg.num_units;
   d.obs_sum = c->obs_sum; d.act_sum = c->act_sum; d.act_stride = c->act_stride;
   d.gamma = c->cfg.gamma; d.actor_reg = c->cfg.actor_reg;
-  d.adam_t = c->adam_t; d.stats = c->stats;
+  d.adam_t = c->adam_t; d.stats = c->stats; d.ctl = c->ctl;
   return d;
 }
+
+CoreDev core_dev_for_rollout(const mdp_core* c) { return core_dev(c); }
 
 template <int U>
 static size_t smem_bytes(int extra_floats) { return (size_t)(smem_floats_base<U>() + extra_floats + 64) * sizeof(float); }
@@ -833,6 +489,12 @@ extern "C" void mdp_core_destroy(mdp_core* core) {
   if (!core) return;
   if (core->d_agents) cudaFree(core->d_agents);
   delete core;
+}
+
+extern "C" int mdp_core_set_ctl(mdp_core* c, const uint64_t* ctl) {
+  MDP_REQUIRE(c, "mdp_core_set_ctl: null core");
+  c->ctl = reinterpret_cast<const unsigned long long*>(ctl);
+  return MDP_OK;
 }
 
 extern "C" int mdp_core_bind(mdp_core* c, float* params, float* grads, float* adam_m, float* adam_v, int32_t* adam_t,

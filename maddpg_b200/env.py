@@ -126,22 +126,33 @@ class BatchedMultiAgentEnv(object):
         return dict(agent_pos=ap, agent_vel=av, landmark_pos=lp, comm=s[4 * A:b].T.copy())
 
     # -- reference surface -------------------------------------------------------------------
-    def reset(self, init_state=None):
-        """``env.reset()`` (train.py:104,128): new positions (Philox on device) or an injected SoA
-        state tensor; returns the list of per-agent observations."""
+    def set_ctl(self, ctl):
+        """Attach / detach (None) a device control block (include/maddpg_b200.h: mdp_env_set_ctl)."""
+        _lib.check(_lib.lib.mdp_env_set_ctl(self._h, _lib.ptr(ctl)), "mdp_env_set_ctl")
+
+    def reset_device(self, init_state=None, episode=None):
+        """Device-only reset (no host copy of the observations); ``episode`` overrides the Philox
+        episode id (a graph-relative offset while a control block is attached)."""
         if init_state is not None:
             assert init_state.shape == self.state.shape and init_state.dtype == self.state_dtype
             init_state = init_state.contiguous()
         self._cur ^= 1
         _lib.check(_lib.lib.mdp_env_reset(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(init_state),
-                                          self.seed, self.episode, _lib.ptr(self.obs), _lib.current_stream()),
-                   "mdp_env_reset")
-        self.episode += 1
+                                          self.seed, self.episode if episode is None else episode, _lib.ptr(self.obs),
+                                          _lib.current_stream()), "mdp_env_reset")
+        if episode is None:
+            self.episode += 1
+
+    def reset(self, init_state=None):
+        """``env.reset()`` (train.py:104,128): new positions (Philox on device) or an injected SoA
+        state tensor; returns the list of per-agent observations."""
+        self.reset_device(init_state)
         return self._obs_out()
 
-    def step_device(self, act_joint=None, ring=None):
+    def step_device(self, act_joint=None, ring=None, cursor=None):
         """One lockstep step on device arrays only.  ``act_joint`` defaults to ``self.act``.  When a
-        ``JointReplayRing`` is given, the transition rows are inserted by the same call."""
+        ``JointReplayRing`` is given, the transition rows are inserted by the same call (``cursor``
+        overrides the ring's host cursor: a graph-relative offset while a control block is attached)."""
         act = self.act if act_joint is None else act_joint
         prev = self.obs
         self._cur ^= 1
@@ -149,7 +160,8 @@ class BatchedMultiAgentEnv(object):
             rc = _lib.lib.mdp_env_step(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(act), _lib.ptr(self.obs),
                                        _lib.ptr(self.rew), _lib.ptr(self.done), None, None, 0, 0, 0, _lib.current_stream())
         else:
-            cursor = ring.reserve_joint(self.num_envs)
+            if cursor is None:
+                cursor = ring.reserve_joint(self.num_envs)
             rc = _lib.lib.mdp_env_step(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(act), _lib.ptr(self.obs),
                                        _lib.ptr(self.rew), _lib.ptr(self.done), _lib.ptr(prev), _lib.ptr(ring.ring),
                                        ring.capacity, ring.row_stride, cursor, _lib.current_stream())

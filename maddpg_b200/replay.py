@@ -76,6 +76,12 @@ class JointReplayRing(object):
             cur = self._advance(i, E)
         return cur
 
+    def advance_all(self, rows):
+        """Host mirror of rows inserted on device by a replayed CUDA graph."""
+        for i in range(self.n):
+            self.length[i] = min(self.capacity, self.length[i] + rows)
+            self.next_idx[i] = (self.next_idx[i] + rows) % self.capacity
+
     def insert_joint(self, obs, act, rew, next_obs, done):
         """E lockstep transitions of all agents from joint device arrays (obs (E,obs_stride), ...)."""
         E = obs.shape[0]

@@ -1,41 +1,223 @@
-"""Device-resident lockstep rollout: the batched form of experiments/train.py:110-133
-(act -> env.step -> experience -> reset every max_episode_len steps) with no host round trip.
+"""Device-resident lockstep rollout and update rounds: the batched form of experiments/train.py:110-161
+(act -> env.step -> experience -> reset every max_episode_len steps; update rounds) with no host
+round trip.
 
 Per lockstep step: one grouped actor+Gumbel kernel (all agents), one fused env-step kernel, one
 replay-insert kernel; every ``max_episode_len`` steps a device reset (all env instances share the
-episode counter).  A whole episode can be captured into a CUDA graph."""
+episode counter).  With ``use_graph`` a whole episode (and a whole update round) is
+captured once into a CUDA graph; the Philox counter, ring cursor, episode id and ring length live
+in a 4-word device control block that the graph itself advances (include/maddpg_b200.h), so every
+replay draws fresh noise and appends to the ring.
+"""
 import torch
 
 from . import _lib
 
 
+class DeviceCtl(object):
+    """{philox_counter, ring_cursor, episode, ring_length} on the device + host mirrors."""
+
+    def __init__(self, env, core):
+        self.env, self.core = env, core
+        self.t = torch.zeros(4, dtype=torch.int64, device=core.device)
+        self._h = torch.zeros(4, dtype=torch.int64)
+        self.dirty = True
+
+    def upload(self):
+        core, env = self.core, self.env
+        self._h[0], self._h[1] = core.counter, core.ring.next_idx[0]
+        self._h[2], self._h[3] = (env.episode if env is not None else 0), core.ring.length[0]
+        self.t.copy_(self._h)
+        self.dirty = False
+
+    def advance(self, d_counter, d_rows, d_episode):
+        _lib.check(_lib.lib.mdp_ctl_advance(_lib.ptr(self.t), d_counter, d_rows, self.core.ring.capacity, d_episode,
+                                            _lib.current_stream()), "mdp_ctl_advance")
+
+
 class BatchedRollout(object):
-    def __init__(self, env, core, max_episode_len=25, use_graph=True):
+    """mode: "mega" = persistent episode kernel (one launch per episode; falls back to "graph" when the
+    scenario does not fit), "graph" = CUDA graph of per-step kernels, "eager" = per-step launches."""
+
+    def __init__(self, env, core, max_episode_len=25, use_graph=True, mode=None):
         assert env.obs_dims == core.obs_dims and env.act_dims == core.act_dims
         self.env, self.core = env, core
         self.max_episode_len = int(max_episode_len)
         self.episode_step = 0
         self.total_steps = 0
+        self.mode = mode or ("mega" if use_graph else "eager")
+        if self.mode == "mega" and env.state_dtype != torch.float32:
+            self.mode = "graph"
+        use_graph = self.mode != "eager"
+        self.mega_launches = 0
+        self.ep_return = None
         self.use_graph = use_graph
         self._graph = None
         self.graph_ok = False
-        self.ep_return = torch.zeros((env.num_envs, env.n), dtype=torch.float32, device=env.device)
+        self.launches_per_graph = 0  # kernels captured in one episode graph
+        self.graph_launches = 0      # kernels executed through graph replays (not seen by mdp_launch_count)
+        self.ctl = DeviceCtl(env, core)
 
+    # -- eager path ---------------------------------------------------------------------------------
     def step(self):
         """train.py:112-133 for all env instances."""
         env, core = self.env, self.core
         core.act(env.obs, env.act)
         env.step_device(ring=core.ring)
+        self.ctl.dirty = True
         self.episode_step += 1
         self.total_steps += 1
         if self.episode_step >= self.max_episode_len:
-            env.reset()
+            env.reset_device()
             self.episode_step = 0
 
-    def run(self, steps):
+    # -- graph path ---------------------------------------------------------------------------------
+    def _episode_body(self):
+        env, core, T, E = self.env, self.core, self.max_episode_len, self.env.num_envs
+        for s in range(T):
+            core.act(env.obs, env.act, counter=s + 1)
+            env.step_device(ring=core.ring, cursor=s * E)
+        env.reset_device(episode=0)
+        self.ctl.advance(T, T * E, 1)
+
+    def _capture(self):
+        env, core = self.env, self.core
+        assert self.episode_step == 0
+        self.ctl.upload()
+        env.set_ctl(self.ctl.t)
+        core.set_ctl(self.ctl.t)
+        cur0 = env._cur
+        g = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize()
+        try:
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(g):
+                self._episode_body()
+            self.launches_per_graph = _lib.launch_count() - l0
+            assert env._cur == cur0, "an episode must flip the observation double buffer an even number of times"
+            self._graph = g
+            self.graph_ok = True
+        finally:
+            env.set_ctl(None)
+            core.set_ctl(None)
+
+    def _mirror_episode(self):
+        T, E = self.max_episode_len, self.env.num_envs
+        self.core.counter += T
+        self.core.ring.advance_all(T * E)
+        self.env.episode += 1
+        self.total_steps += T
+
+    def run_mega(self, steps, reset_after=True):
+        """One launch of the persistent episode kernel (include/maddpg_b200.h: mdp_rollout_episode)."""
+        env, core = self.env, self.core
+        ring = core.ring
+        if not ring.aligned():
+            raise RuntimeError("the episode kernel needs index-aligned agents")
+        rc = _lib.lib.mdp_rollout_episode(env._h, core._h, env.num_envs, _lib.ptr(env.state), _lib.ptr(env.obs),
+                                          _lib.ptr(ring.ring), ring.capacity, ring.row_stride, ring.next_idx[0], steps,
+                                          core.seed, core.counter, int(reset_after), env.seed, env.episode,
+                                          _lib.ptr(self.ep_return), _lib.current_stream())
+        if rc == _lib.MDP_ENOTSUP:
+            return False
+        _lib.check(rc, "mdp_rollout_episode")
+        core.counter += steps
+        ring.advance_all(env.num_envs * steps)
+        if reset_after:
+            env.episode += 1
+        self.total_steps += steps
+        self.mega_launches += 1
+        self.ctl.dirty = True
+        return True
+
+    def run_episodes(self, n):
+        if self.mode == "mega" and self.episode_step == 0:
+            for k in range(n):
+                if not self.run_mega(self.max_episode_len, True):
+                    self.mode = "graph"  # scenario does not fit the episode kernel
+                    return self.run_episodes(n - k)
+            return
+        if not self.use_graph or self.episode_step != 0:
+            return self.run_eager(n * self.max_episode_len)
+        if self._graph is None:
+            self.run_eager(self.max_episode_len)  # warm-up: lazy allocations happen outside the capture
+            n -= 1
+            self._capture()
+        self.ctl.upload()  # host mirrors are the truth between graph launches (eager calls may have moved them)
+        for _ in range(n):
+            self._graph.replay()
+            self.graph_launches += self.launches_per_graph
+            self._mirror_episode()
+
+    def run_eager(self, steps):
         for _ in range(steps):
             self.step()
+
+    def run(self, steps):
+        T = self.max_episode_len
+        if self.use_graph and self.episode_step == 0 and steps % T == 0 and (self.mode == "mega" or (T + 1) % 2 == 0):
+            return self.run_episodes(steps // T)
+        return self.run_eager(steps)
 
     @property
     def agent_steps_per_step(self):
         return self.env.num_envs * self.env.n
+
+
+class GraphedUpdateRound(object):
+    """One update round (every agent once, sequentially: train.py:160-161 -> maddpg.py:167-194) with
+    device-side index draws, captured into a CUDA graph (single GPU; multi-GPU uses DataParallelUpdater)."""
+
+    def __init__(self, core, batch_size, ctl=None, use_graph=True):
+        self.core, self.B = core, int(batch_size)
+        self.ctl = ctl if ctl is not None else DeviceCtl(None, core)
+        self.use_graph = use_graph
+        self._graph = None
+        self.launches_per_graph = 0
+        self.graph_launches = 0
+        self.idx = [torch.zeros(self.B, dtype=torch.int64, device=core.device) for _ in range(core.n)]
+        _, self.batch = core._scratch(self.B)
+
+    def _body(self, relative):
+        core = self.core
+        c = 0
+        for j in range(core.n):
+            c += 1
+            if relative:
+                core.make_index(self.idx[j], length=0, counter=c, ctl=self.ctl.t)
+            else:
+                core.make_index(self.idx[j])
+            core.ring.gather(self.idx[j], out=self.batch)
+            c += 1
+            core.update_agent(j, self.batch, counter=c if relative else None)
+        if relative:
+            self.ctl.advance(c, 0, 0)
+        return c
+
+    def run(self, rounds=1):
+        core = self.core
+        if not self.use_graph:
+            for _ in range(rounds):
+                self._body(False)
+            self.ctl.dirty = True
+            return
+        if self._graph is None:
+            self._body(False)  # warm-up outside the capture
+            rounds -= 1
+            self.ctl.upload()
+            core.set_ctl(self.ctl.t)
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            try:
+                l0 = _lib.launch_count()
+                with torch.cuda.graph(g):
+                    self._per_round = self._body(True)
+                self.launches_per_graph = _lib.launch_count() - l0
+                self._graph = g
+            finally:
+                core.set_ctl(None)
+        self.ctl.upload()  # ring length / counter may have moved since the last replay
+        for _ in range(rounds):
+            self._graph.replay()
+            self.graph_launches += self.launches_per_graph
+            core.counter += self._per_round

@@ -156,13 +156,19 @@ class MADDPGCore(object):
         self.counter += 1
         return self.counter
 
-    def act(self, obs_joint, act_joint, agent_begin=0, agent_count=None, use_target=False, u=None, logits_out=None):
-        """Grouped actor inference + Gumbel-softmax on joint device arrays (see header)."""
+    def set_ctl(self, ctl):
+        """Attach / detach (None) a device control block (include/maddpg_b200.h: mdp_core_set_ctl)."""
+        _lib.check(_lib.lib.mdp_core_set_ctl(self._h, _lib.ptr(ctl)), "mdp_core_set_ctl")
+
+    def act(self, obs_joint, act_joint, agent_begin=0, agent_count=None, use_target=False, u=None, logits_out=None,
+            counter=None):
+        """Grouped actor inference + Gumbel-softmax on joint device arrays (see header).  ``counter``
+        overrides the host Philox counter (a graph-relative offset while a control block is attached)."""
         agent_count = self.n - agent_begin if agent_count is None else agent_count
         _lib.check(_lib.lib.mdp_actor_act(self._h, agent_begin, agent_count, int(use_target), obs_joint.shape[0],
                                           _lib.ptr(obs_joint), obs_joint.stride(0), _lib.ptr(act_joint), act_joint.stride(0),
-                                          _lib.ptr(u), self.seed, self.next_counter(), _lib.ptr(logits_out),
-                                          _lib.current_stream()), "mdp_actor_act")
+                                          _lib.ptr(u), self.seed, self.next_counter() if counter is None else counter,
+                                          _lib.ptr(logits_out), _lib.current_stream()), "mdp_actor_act")
 
     def act_agent(self, agent, obs, use_target=False, u=None, want_logits=False):
         """One agent on its own (E, D_i) device array -> (E, K_i).  The kernel addresses agent i's
@@ -224,13 +230,21 @@ class MADDPGCore(object):
         _lib.check(_lib.lib.mdp_clip_adam_polyak(self._h, agent, which, float(grad_scale), int(do_polyak),
                                                  _lib.current_stream()), "mdp_clip_adam_polyak")
 
-    def update_agent(self, agent, batch, u_target=None, u_actor=None):
+    def update_agent(self, agent, batch, u_target=None, u_actor=None, counter=None):
         """maddpg.py:181-194 for one agent, five kernels on the current stream."""
         B = batch.shape[0]
         y, _ = self._scratch(B)
         _lib.check(_lib.lib.mdp_update_agent(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch),
                                              _lib.ptr(u_target), _lib.ptr(u_actor), self.act_stride, self.seed,
-                                             self.next_counter(), _lib.ptr(y), _lib.current_stream()), "mdp_update_agent")
+                                             self.next_counter() if counter is None else counter, _lib.ptr(y),
+                                             _lib.current_stream()), "mdp_update_agent")
+
+    def make_index(self, idx_out, length=None, counter=None, ctl=None):
+        """Device-side ``ReplayBuffer.make_index`` (replay_buffer.py:46-47): B uniform draws in [0, len)."""
+        _lib.check(_lib.lib.mdp_replay_make_index(_lib.ptr(idx_out), idx_out.shape[0],
+                                                  int(self.ring.length[0] if length is None else length), self.seed,
+                                                  self.next_counter() if counter is None else counter, _lib.ptr(ctl),
+                                                  _lib.current_stream()), "mdp_replay_make_index")
 
     def read_stats(self, agent, B=None):
         """[q_loss, p_loss, mean(target_q), mean(rew), mean(target_q_next), std(target_q)] (maddpg.py:196)."""

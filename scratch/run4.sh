@@ -1,0 +1,4 @@
+set -x
+python -m pytest tests -m gpu -q -x 2>&1 | tail -15
+python bench.py --steps 2000 --warmup 100 --update-rounds 100 --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_r1_mega.json
+python bench.py --steps 2000 --warmup 100 --update-rounds 100 --no-cpu-baseline --rollout-mode graph 2>&1 | tail -3 | tee gpurun_out/bench_r1_graph2.json

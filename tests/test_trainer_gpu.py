@@ -195,3 +195,87 @@ def test_philox_actions_are_valid_and_reproducible():
     pl = torch.softmax(logits[:, 9:14], 1).mean(0).cpu().numpy()
     freq = np.bincount(act[:, 9:14].argmax(1).cpu().numpy(), minlength=5) / 4096.0
     assert np.abs(freq - pl).max() < 0.04
+
+
+def test_graph_rollout_and_update_round_match_eager_semantics():
+    """CUDA-graph episode/update-round replay: ring cursor, length, Philox counter and episode id advance
+    on device exactly as the eager path advances the host mirrors; noise is fresh on every replay."""
+    import argparse
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
+    from maddpg_b200.rollout import BatchedRollout, GraphedUpdateRound
+    E, T = 256, 25
+    env = BatchedMultiAgentEnv("simple_spread", num_envs=E, squeeze=False, seed=5)
+    core = MADDPGCore(env.obs_dims, env.action_space, [False] * 3, replay_capacity=E * T * 5, seed=5)
+    roll = BatchedRollout(env, core, T, mode="graph")
+    env.reset_device()
+    roll.run(T * 4)  # 1 eager warm-up episode + 3 replays
+    assert roll.graph_ok and core.ring.length == [E * T * 4] * 3 and roll.graph_launches == 3 * roll.launches_per_graph
+    ctl = roll.ctl.t.cpu().tolist()
+    assert ctl[0] == core.counter and ctl[1] == core.ring.next_idx[0] and ctl[2] == env.episode and ctl[3] == core.ring.length[0]
+    L = core.ring.layout
+    ring = core.ring.ring.cpu()
+    n = core.ring.length[0]
+    # every inserted row is a valid transition: actions are per-agent simplices, obs finite, done == 0
+    act = ring[:n, L.obs_sum:L.x_dim].view(n, 3, 5)
+    assert torch.allclose(act.sum(-1), torch.ones(n, 3), atol=1e-5)
+    assert torch.isfinite(ring[:n, :L.x_dim]).all() and (ring[:n, L.dn_off:L.dn_off + 3] == 0).all()
+    # consecutive steps of the same env chain: next_obs of step s == obs of step s+1 inside an episode
+    for ep in range(4):
+        base = ep * T * E
+        for s in (0, 7, 23):
+            a = ring[base + s * E: base + (s + 1) * E, L.nx_off:L.nx_off + L.obs_sum]
+            b = ring[base + (s + 1) * E: base + (s + 2) * E, :L.obs_sum]
+            assert torch.equal(a, b), (ep, s)
+    # replays draw fresh noise and fresh reset positions
+    a1 = ring[1 * T * E: 1 * T * E + E, L.obs_sum:L.x_dim]
+    a2 = ring[2 * T * E: 2 * T * E + E, L.obs_sum:L.x_dim]
+    assert not torch.equal(a1, a2)
+    o1, o2 = ring[1 * T * E: 1 * T * E + E, :4], ring[2 * T * E: 2 * T * E + E, :4]
+    assert not torch.equal(o1, o2)
+    # graphed update rounds: Adam counters advance by one per round per net, parameters move, stay finite
+    upd = GraphedUpdateRound(core, 128, ctl=roll.ctl, use_graph=True)
+    p0 = core.params.clone()
+    upd.run(3)
+    torch.cuda.synchronize()
+    assert core.adam_t.cpu().tolist() == [3] * 6
+    assert torch.isfinite(core.params).all() and not torch.equal(p0, core.params)
+    idx = upd.idx[0].cpu()
+    assert idx.min() >= 0 and idx.max() < core.ring.length[0] and idx.unique().numel() > 100
+    p1 = core.params.clone()
+    upd.run(1)
+    assert not torch.equal(p1, core.params)
+
+
+@pytest.mark.parametrize("scenario,units", [("simple_spread", 64), ("simple_tag", 64), ("simple", 64),
+                                            ("simple_world_comm", 128)])
+def test_episode_kernel_matches_per_step_kernels(scenario, units):
+    """mdp_rollout_episode (persistent episode kernel) against the per-step path on the same seeds and
+    Philox counters: identical replay rows, final state and observations (incl. the device reset)."""
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
+    from maddpg_b200.rollout import BatchedRollout
+    E, T = 80, 25  # 80 = 2.5 tiles of 32 env instances: exercises the ragged last CTA
+    rings, finals = [], []
+    for mode in ("eager", "mega"):
+        env = BatchedMultiAgentEnv(scenario, num_envs=E, squeeze=False, seed=11)
+        core = MADDPGCore(env.obs_dims, env.action_space, [False] * env.n, num_units=units,
+                          replay_capacity=E * T * 2 + 13, seed=3)
+        roll = BatchedRollout(env, core, T, mode=mode)
+        if mode == "mega":
+            roll.ep_return = torch.zeros((E, env.n), device="cuda")
+        env.reset_device()
+        roll.run(T * 3)  # 3 episodes into a ring of 2 episodes + 13 rows: wraps
+        torch.cuda.synchronize()
+        assert roll.mode == mode and core.ring.length == [core.ring.capacity] * env.n
+        assert core.counter == 3 * T and env.episode == 4
+        rings.append((core.ring.ring.cpu(), list(core.ring.next_idx)))
+        finals.append((env.state.cpu(), env.obs.cpu(), roll.ep_return))
+    (r0, n0), (r1, n1) = rings
+    assert n0 == n1
+    L = core.ring.layout
+    used = list(range(0, L.x_dim)) + list(range(L.nx_off, L.nx_off + L.obs_sum)) + list(range(L.rw_off, L.dn_off + env.n))
+    torch.testing.assert_close(r1[:, used], r0[:, used], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(finals[1][0], finals[0][0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(finals[1][1], finals[0][1], rtol=1e-5, atol=1e-6)
+    # episode returns accumulated by the kernel == sum of the rewards it wrote (last 2 episodes are in the ring)
+    ret = finals[1][2].cpu()
+    assert torch.isfinite(ret).all() and ret.abs().sum() > 0
