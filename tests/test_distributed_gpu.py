@@ -1,0 +1,69 @@
+"""Two-GPU data-parallel update (NCCL): ranks hold different replay shards, all-reduce the gradient bucket
+of the network being stepped, and must end with identical parameters that match a single-process update on
+the union batch.  Skipped unless two CUDA devices are visible."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _build_core(dev, B):
+    from maddpg_b200 import MADDPGCore
+    from maddpg_b200.spaces import Discrete
+    core = MADDPGCore([18, 18, 18], [Discrete(5)] * 3, [False] * 3, device=dev, replay_capacity=4 * B, seed=5)
+    return core
+
+
+def _rows(core, B, seed):
+    g = torch.Generator().manual_seed(seed)
+    L = core.ring.layout
+    batch = torch.randn(B, core.ring.row_stride, generator=g)
+    act = torch.softmax(torch.randn(B, 3, 5, generator=g), -1).reshape(B, 15)
+    batch[:, L.obs_sum:L.x_dim] = act
+    batch[:, L.dn_off:L.dn_off + 3] = (torch.rand(B, 3, generator=g) < 0.1).float()
+    return batch
+
+
+def _worker(rank, world, port, B, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from maddpg_b200.distributed import DataParallelUpdater
+    core = _build_core(dev, B)
+    dp = DataParallelUpdater(core)
+    dp.broadcast_params(core.params)
+    full = _rows(core, world * B, 1)
+    ut = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(2)).clamp_(1e-6, 1 - 1e-6)
+    ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6)
+    sl = slice(rank * B, (rank + 1) * B)
+    for j in range(3):
+        dp.update_agent(j, full[sl].contiguous().to(dev), ut[sl].contiguous().to(dev), ua[sl].contiguous().to(dev))
+    torch.cuda.synchronize()
+    out[rank] = core.params.cpu().numpy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_update_matches_union_batch():
+    B, world = 256, 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, 29400 + os.getpid() % 500, B, out), nprocs=world, join=True)
+    p0, p1 = out[0], out[1]
+    assert np.array_equal(p0, p1), "replicas diverged"
+    # single process on the union batch: mean over 2B rows == average of the two rank-local means
+    core = _build_core(torch.device("cuda", 0), B)
+    full = _rows(core, world * B, 1).cuda()
+    ut = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(2)).clamp_(1e-6, 1 - 1e-6).cuda()
+    ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6).cuda()
+    for j in range(3):
+        core.update_agent(j, full, ut, ua)
+    ref = core.params.cpu().numpy()
+    np.testing.assert_allclose(p0, ref, rtol=2e-3, atol=3e-4)

@@ -2,6 +2,8 @@
 against the numpy oracle on the same weights, replay rows, index sets and uniform draws.
 Tolerance from BASELINE.json north_star: Q-values and losses within 1e-4 relative after a
 fixed-seed update."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -279,3 +281,26 @@ def test_episode_kernel_matches_per_step_kernels(scenario, units):
     # episode returns accumulated by the kernel == sum of the rewards it wrote (last 2 episodes are in the ring)
     ret = finals[1][2].cpu()
     assert torch.isfinite(ret).all() and ret.abs().sum() > 0
+
+
+@pytest.mark.parametrize("num_envs", [1, 64])
+def test_train_loop_drop_in(tmp_path, num_envs):
+    """experiments/train.py's loop on the drop-ins: reference shapes (1 env, numpy) and the batched superset;
+    passes the warm-up gate, performs updates at t % 100 == 0, saves and restores parameters."""
+    from maddpg_b200 import train as T
+    argv = ["--scenario", "simple_tag", "--num-adversaries", "3", "--adv-policy", "ddpg", "--num-episodes", "12",
+            "--batch-size", "8", "--save-rate", "4", "--save-dir", str(tmp_path) + "/", "--plots-dir", str(tmp_path) + "/",
+            "--exp-name", "t", "--num-envs", str(num_envs), "--replay-capacity", "50000"]
+    arglist = T.parse_args(argv)
+    trainers, ep_rewards = T.train(arglist)
+    core = trainers[0].core
+    assert len(ep_rewards) == 13 and all(np.isfinite(ep_rewards))
+    assert core.local_q == [True, True, True, False]
+    assert len(trainers[0].replay_buffer) == 300 * num_envs
+    # warm-up gate needs 200 rows: reached at t = 200 with one env (updates at t = 200, 300), at t = 4 with 64
+    assert core.adam_t.cpu().tolist() == [2 if num_envs == 1 else 3] * 8
+    assert os.path.exists(os.path.join(str(tmp_path), "maddpg_b200.pt")) and os.path.exists(os.path.join(str(tmp_path), "t_rewards.pkl"))
+    saved = torch.load(os.path.join(str(tmp_path), "maddpg_b200.pt"))
+    core.params.zero_()
+    T.load_state(str(tmp_path), trainers)
+    assert torch.equal(core.params.cpu(), saved["params"])
