@@ -272,8 +272,7 @@ def main():
         if gupd is not None:  # single GPU: device-side index draw + gather + 5 update kernels per agent, graph-replayed
             return gupd.run(1)
         for j in range(A):
-            core.ring.gather(idx_pool[r % 8][j], out=batch)
-            dp.update_agent(j, batch)
+            dp.update_agent(j, core.ring.ring, idx=idx_pool[r % 8][j])  # gather fused into the kernels
 
     for r in range(3):
         update_round(r)

@@ -170,23 +170,29 @@ int mdp_actor_act(mdp_core* core, int32_t agent_begin, int32_t agent_count, int3
 int mdp_critic_q(mdp_core* core, int32_t agent, int32_t use_target, int32_t B, const float* x, int32_t x_stride,
                  float* q_out, void* stream);
 
-/* TD target of agent j (maddpg.py:181-187) on a gathered batch (B, row_stride) of joint ring rows:
+/* Row addressing of the three update kernels below: `batch` is a (rows, row_stride) array of joint ring rows.
+ * idx == NULL: logical row b is batch row b (an already gathered batch).  idx != NULL (device int64[B]): logical
+ * row b is batch row idx[b] -- pass the replay ring itself and the sampled indices and the gather
+ * (ReplayBuffer.sample_index, replay_buffer.py:34-44,55-56) is fused into the kernels' tile loads.
+ *
+ * TD target of agent j (maddpg.py:181-187) on a gathered batch (B, row_stride) of joint ring rows:
  * a'_i = gumbel_softmax(target_p_i(next_obs_i)) for all i, q' = target_q_j(next_obs, a'),
  * y = float32(rew_j + gamma * (1 - done_j) * q') -- one fused kernel.  u_target (optional, (B, act_stride)
  * joint layout) injects the uniforms.  Accumulates sum(y), sum(y^2), sum(rew), sum(q') into stats. */
 int mdp_td_target(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                  const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter, float* y_out,
-                  float* target_act_out, void* stream);
+                  const int64_t* idx, const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter,
+                  float* y_out, float* target_act_out, void* stream);
 
 /* q_train forward/backward (maddpg.py:75-100): grads of mean((Q_j(x) - y)^2) wrt the critic's six
  * tensors are ACCUMULATED into the bound grad buffer (fused fwd + bwd kernel); sum((q-y)^2) -> stats. */
 int mdp_critic_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                     const float* y, float* q_out, void* stream);
+                     const int64_t* idx, const float* y, float* q_out, void* stream);
 
 /* p_train forward/backward (maddpg.py:28-61): grads of -mean(Q_j(o, a_-j, gumbel_softmax(p_j(o_j))))
  * + actor_reg * mean(logits^2) wrt the actor's tensors, through the RUNNING critic (fused kernel). */
 int mdp_actor_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                    const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter, void* stream);
+                    const int64_t* idx, const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter,
+                    void* stream);
 
 /* U.minimize_and_clip + tf.train.AdamOptimizer + make_update_exp (tf_util.py:166-182, maddpg.py:20-26):
  * per-variable clip_by_norm, TF-Adam step (t = adam_t, incremented by the *_grads call), polyak update
@@ -198,7 +204,7 @@ int mdp_clip_adam_polyak(mdp_core* core, int32_t agent, int32_t which, float gra
 /* MADDPGAgentTrainer.update body for agent j on one stream (maddpg.py:181-194), single GPU:
  * td_target -> critic_grads -> clip_adam(Q) -> actor_grads -> clip_adam(P) + polyak(P) + polyak(Q). */
 int mdp_update_agent(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                     const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
+                     const int64_t* idx, const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
                      uint64_t counter, float* y_scratch, void* stream);
 
 /* Persistent episode kernel: `steps` lockstep iterations of experiments/train.py:112-133 (action ->

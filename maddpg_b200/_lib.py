@@ -76,13 +76,13 @@ SYMBOLS = {
     "mdp_actor_act": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P,
                                 C.c_uint64, C.c_uint64, _P, _P]),
     "mdp_critic_q": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
-    "mdp_td_target": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, C.c_int32, C.c_uint64,
+    "mdp_td_target": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, C.c_int32, C.c_uint64,
                                 C.c_uint64, _P, _P, _P]),
-    "mdp_critic_grads": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, _P]),
-    "mdp_actor_grads": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, C.c_int32, C.c_uint64,
+    "mdp_critic_grads": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, _P, _P]),
+    "mdp_actor_grads": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, C.c_int32, C.c_uint64,
                                   C.c_uint64, _P]),
     "mdp_clip_adam_polyak": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
-    "mdp_update_agent": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, C.c_int32,
+    "mdp_update_agent": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, _P, C.c_int32,
                                    C.c_uint64, C.c_uint64, _P, _P]),
     "mdp_rollout_episode": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                       C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),

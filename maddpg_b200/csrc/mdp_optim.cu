@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
                                                            float grad_scale, float clip, double lr, double beta1,
                                                            double beta2, float eps, float polyak, int do_polyak) {
   __shared__ float red[32];
-  __shared__ float s_factor;
+  __shared__ float s_factor, s_lr_t;
   const long long off = seg.off[blockIdx.x], len = seg.len[blockIdx.x];
   float* g = grad + off;
   // pass 1: ||scale * g||_2
@@ -41,12 +41,13 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
     if (threadIdx.x == 0) {
       const float norm = sqrtf(s);
       s_factor = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;  // tf.clip_by_norm: g * clip / max(||g||, clip)
+      const int t = *t_ptr;
+      s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
     }
   }
   __syncthreads();
   const float factor = s_factor * grad_scale;
-  const int t = *t_ptr;
-  const float lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+  const float lr_t = s_lr_t;
   const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2);
   const float opol = 1.0f - polyak;
   float* p = param + off;

@@ -79,7 +79,6 @@ __global__ void k_replay_gather_vec(const float4* __restrict__ ring, long long c
 // mode 1: TMA bulk-copy engine.  One elected thread per CTA moves ROWS_PER_CTA whole rows
 // global -> shared with cp.async.bulk (completion on an mbarrier), then shared -> global with
 // cp.async.bulk.global.shared::cta (bulk-group completion).  No register staging at all.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <int ROWS>
 __global__ void k_replay_gather_bulk(const float* __restrict__ ring, long long capacity, int row_stride,

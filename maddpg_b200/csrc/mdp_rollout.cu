@@ -13,33 +13,8 @@
 
 namespace mdp {
 
-constexpr int REB = 32;  // env instances per CTA == TM rows of the MLP tile
-static_assert(REB == TM, "the episode kernel maps one env instance to one MLP tile row");
-
-// acc += sA[rows 2ty, 2ty+1][0..kc) * sW[0..kc)[cols], A read with scalar loads (no alignment demands)
-template <int U>
-__device__ __forceinline__ void mma_tile_sa(const Grp& G, float (&acc)[2][U / 16], const float* __restrict__ sA, int lda,
-                                            const float* __restrict__ sW, int kc) {
-  const int ty = G.tid >> 4, tx = G.tid & 15;
-  const float* a0p = sA + (2 * ty) * lda;
-  const float* a1p = a0p + lda;
-#pragma unroll 2
-  for (int k = 0; k < kc; ++k) {
-    const float a0 = a0p[k], a1 = a1p[k];
-#pragma unroll
-    for (int g = 0; g < U / 64; ++g) {
-      const float4 w = *reinterpret_cast<const float4*>(sW + k * U + g * 64 + 4 * tx);
-      acc[0][4 * g + 0] = fmaf(a0, w.x, acc[0][4 * g + 0]);
-      acc[0][4 * g + 1] = fmaf(a0, w.y, acc[0][4 * g + 1]);
-      acc[0][4 * g + 2] = fmaf(a0, w.z, acc[0][4 * g + 2]);
-      acc[0][4 * g + 3] = fmaf(a0, w.w, acc[0][4 * g + 3]);
-      acc[1][4 * g + 0] = fmaf(a1, w.x, acc[1][4 * g + 0]);
-      acc[1][4 * g + 1] = fmaf(a1, w.y, acc[1][4 * g + 1]);
-      acc[1][4 * g + 2] = fmaf(a1, w.z, acc[1][4 * g + 2]);
-      acc[1][4 * g + 3] = fmaf(a1, w.w, acc[1][4 * g + 3]);
-    }
-  }
-}
+constexpr int REB = 32;  // env instances per CTA == rows of the MLP tile
+constexpr int TM = REB;
 
 __host__ __device__ inline int actor_net_floats(int D, int U, int K) {
   return ((D * U + U + U * U + U + U * K + K) + 3) & ~3;
@@ -137,30 +112,30 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
         w.W3 = b; b += U * K;
         w.b3 = b;
       }
-      float acc[2][U / 16];
-      zero_acc<U>(acc);
+      float acc[TM / 16][U / 16];
+      zero_acc<U, TM>(acc);
       if (RESIDENT) {
-        mma_tile_sa<U>(G, acc, sObs + ag.obs_off, OS, w.W1, D);
+        mma_tile_sa<U, TM>(G, acc, sObs + ag.obs_off, OS, w.W1, D);
       } else {
         for (int k0 = 0; k0 < D; k0 += KC) {
           load_w_rows<U>(G, sWts, w.W1, k0, D);
           G.sync();
-          mma_tile_sa<U>(G, acc, sObs + ag.obs_off + k0, OS, sWts, min(KC, D - k0));
+          mma_tile_sa<U, TM>(G, acc, sObs + ag.obs_off + k0, OS, sWts, min(KC, D - k0));
           G.sync();
         }
       }
-      store_bias_relu<U>(G, acc, w.b1, sH1);
+      store_bias_relu<U, TM>(G, acc, w.b1, sH1);
       G.sync();
       if (RESIDENT) {
-        zero_acc<U>(acc);
-        mma_tile<U>(G, acc, sH1, HP, w.W2, U);
+        zero_acc<U, TM>(acc);
+        mma_tile<U, TM>(G, acc, sH1, HP, w.W2, U);
       } else {
-        layer_h<U, false>(G, acc, sH1, w.W2, sWts);
+        layer_h<U, TM, false>(G, acc, sH1, w.W2, sWts);
       }
-      store_bias_relu<U>(G, acc, w.b2, sH2);
+      store_bias_relu<U, TM>(G, acc, w.b2, sH2);
       G.sync();
-      actor_head<U>(G, sH2, w, sL);
-      gumbel_softmax_tile(G, sL, sAct + ag.act_off, T.ASP, nE, K, ag.n_heads, ag.head_dim, nullptr, 0, 0, (long long)e0, R.seed,
+      actor_head<U, TM>(G, sH2, w, sL);
+      gumbel_softmax_tile<TM>(G, sL, sAct + ag.act_off, T.ASP, nE, K, ag.n_heads, ag.head_dim, nullptr, 0, 0, (long long)e0, R.seed,
                           counter + (unsigned long long)s + 1ull, (uint32_t)i);
     }
     __syncthreads();  // all groups' actions are in sAct

@@ -22,19 +22,22 @@
 
 namespace mdp {
 
+// net buffer sizes (floats) of the resident-weights variants
+__host__ __device__ inline int res_net_floats(int in, int U, int out) { return net_floats_padded(in, U, out); }
+
 // ---------------------------------------------------------------------------------------------
 // K1: grouped actor inference + Gumbel-softmax.  grid = (ceil(E/TM), agent_count)
 // ---------------------------------------------------------------------------------------------
-template <int U>
+template <int U, int TM, bool RES>
 __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, int use_target, int E,
                                                   const float* __restrict__ obs, int obs_stride, float* __restrict__ act,
                                                   int act_stride, const float* __restrict__ u, uint64_t seed,
-                                                  uint64_t counter, float* __restrict__ logits_out) {
+                                                  uint64_t counter, float* __restrict__ logits_out, int max_net) {
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * (U + 4));
   float* sH2 = sm.take(TM * (U + 4));
@@ -42,14 +45,15 @@ __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, in
   float* sA = sm.take(TM * KPAD);
   const int i = agent_begin + blockIdx.y;
   const AgentDev& ag = C.agents[i];
-  const MlpW& w = ag.net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
+  MlpW w = ag.net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
+  if (RES) w = load_net<U>(G, sW, w);  // visible after the first barrier inside layer1
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, E - row0);
   XSrc xs = make_xsrc(obs + ag.obs_off, obs_stride, ag.obs_dim);
-  forward_hidden<U>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
-  actor_head<U>(G, sH2, w, sL);
-  gumbel_softmax_tile(G, sL, sA, KPAD, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off, row0, seed, counter,
-                      (uint32_t)i);
+  forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  actor_head<U, TM>(G, sH2, w, sL);
+  gumbel_softmax_tile<TM>(G, sL, sA, KPAD, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off, row0, seed,
+                          counter, (uint32_t)i);
   for (int idx = threadIdx.x; idx < nrows * ag.act_dim; idx += NT) {
     const int r = idx / ag.act_dim, a = idx - r * ag.act_dim;
     act[(row0 + r) * act_stride + ag.act_off + a] = sA[r * KPAD + a];
@@ -60,19 +64,20 @@ __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, in
 // ---------------------------------------------------------------------------------------------
 // q-values of one critic (debug surface q_debug[...]).  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
-template <int U>
+template <int U, int TM, bool RES>
 __global__ void __launch_bounds__(NT) k_critic_q(CoreDev C, int agent, int use_target, int B, const float* __restrict__ x,
-                                                 int x_stride, float* __restrict__ q_out) {
+                                                 int x_stride, float* __restrict__ q_out, int max_net) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * (U + 4));
   float* sH2 = sm.take(TM * (U + 4));
   float* sQ = sm.take(TM);
   const AgentDev& ag = C.agents[agent];
-  const MlpW& w = ag.net[use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
+  MlpW w = ag.net[use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
+  if (RES) w = load_net<U>(G, sW, w);
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   XSrc xs;
@@ -82,24 +87,24 @@ __global__ void __launch_bounds__(NT) k_critic_q(CoreDev C, int agent, int use_t
   } else {
     xs = make_xsrc(x, x_stride, C.obs_sum + C.act_sum);
   }
-  forward_hidden<U>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(G, sH2, w, sQ);
+  forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U, TM>(G, sH2, w, sQ);
   if (threadIdx.x < nrows) q_out[row0 + threadIdx.x] = sQ[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
 // K5: fused TD target of agent j.  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
-template <int U>
+template <int U, int TM, bool RES>
 __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
-                                                  const float* __restrict__ u_target, int u_stride, uint64_t seed,
-                                                  uint64_t counter, float* __restrict__ y_out,
-                                                  float* __restrict__ target_act_out) {
+                                                  const long long* __restrict__ ridx, const float* __restrict__ u_target,
+                                                  int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
+                                                  float* __restrict__ target_act_out, int max_net) {
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * (U + 4));
   float* sH2 = sm.take(TM * (U + 4));
@@ -116,11 +121,14 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
   const int i_begin = me.local_q ? j : 0, i_end = me.local_q ? j + 1 : C.n_agents;
   for (int i = i_begin; i < i_end; ++i) {
     const AgentDev& ag = C.agents[i];
+    MlpW w = ag.net[MDP_NET_TARGET_P];
+    if (RES) w = load_net<U>(G, sW, w);  // the previous user of sW finished before the last barrier
     XSrc xs = make_xsrc(batch + L.nx_off + ag.obs_off, R, ag.obs_dim);
-    forward_hidden<U>(G, xs, ag.net[MDP_NET_TARGET_P], row0, nrows, sX, sW, sH1, sH2);
-    actor_head<U>(G, sH2, ag.net[MDP_NET_TARGET_P], sL);
-    gumbel_softmax_tile(G, sL, sAct + ag.act_off, ASP, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u_target, u_stride, ag.act_off, row0,
-                        seed, counter, (uint32_t)(0x100 + i));
+    xs.idx = ridx;
+    forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+    actor_head<U, TM>(G, sH2, w, sL);
+    gumbel_softmax_tile<TM>(G, sL, sAct + ag.act_off, ASP, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u_target, u_stride,
+                            ag.act_off, row0, seed, counter, (uint32_t)(0x100 + i));
   }
   if (target_act_out) {
     for (int idx = threadIdx.x; idx < nrows * C.act_sum; idx += NT) {
@@ -138,15 +146,17 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
     xs = make_xsrc(batch + L.nx_off, R, C.obs_sum);
     xs.s_over = sAct; xs.over_ld = ASP; xs.over_c0 = C.obs_sum; xs.over_n = C.act_sum;
   }
-  const MlpW& tq = me.net[MDP_NET_TARGET_Q];
-  forward_hidden<U>(G, xs, tq, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(G, sH2, tq, sQ);
+  xs.idx = ridx;
+  MlpW tq = me.net[MDP_NET_TARGET_Q];
+  if (RES) tq = load_net<U>(G, sW, tq);
+  forward_hidden<U, TM, RES>(G, xs, tq, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U, TM>(G, sH2, tq, sQ);
   // y = float32(rew + gamma * (1 - done) * q')  -- float64 combine like numpy (maddpg.py:186)
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
     double sy = 0, syy = 0, sr = 0, sq = 0;
     if (r < nrows) {
-      const float* row = batch + (row0 + r) * R;
+      const float* row = batch + (ridx ? ridx[row0 + r] : row0 + r) * R;
       const double rew = (double)row[L.rw_off + j], done = (double)row[L.dn_off + j];
       const float qn = sQ[r];
       const double y = rew + C.gamma * (1.0 - done) * (double)qn;
@@ -170,22 +180,28 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
 // ---------------------------------------------------------------------------------------------
 // K6: fused critic forward + MSE + backward.  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
-template <int U>
+template <int U, int TM, bool RES>
 __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
-                                                     const float* __restrict__ y, float* __restrict__ q_out) {
+                                                     const long long* __restrict__ ridx, const float* __restrict__ y,
+                                                     float* __restrict__ q_out, int max_net) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Grp G{(int)threadIdx.x, 0};
   constexpr int HP = U + 4;
+  const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);
+  float* sWT = sm.take(RES ? U * U : 4);
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * HP);
   float* sH2 = sm.take(TM * HP);
   float* sQ = sm.take(TM);
-  float* sDq = sm.take(TM);
+  float* sDq = sm.take(32);
   const AgentDev& me = C.agents[j];
-  const MlpW& w = me.net[MDP_NET_Q];
+  MlpW w = me.net[MDP_NET_Q];
   const MlpG& g = me.grad[1];
+  if (RES) {
+    load_wT_rows<U>(G, sWT, w.W2, 0, U);
+    w = load_net<U>(G, sW, w);
+  }
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   const int R = L.row_stride;
@@ -197,8 +213,9 @@ __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_
   } else {
     xs = make_xsrc(batch, R, L.x_dim);
   }
-  forward_hidden<U>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(G, sH2, w, sQ);
+  xs.idx = ridx;
+  forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U, TM>(G, sH2, w, sQ);
   // dL/dq = 2 (q - y) / B ; loss partial
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
@@ -234,23 +251,26 @@ __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_
     sH2[r * HP + u] = h > 0.f ? sDq[r] * w.W3[u] : 0.f;
   }
   __syncthreads();
-  backward_hidden<U>(G, xs, w, &g, row0, nrows, sX, sW, sH1, sH2);
+  backward_hidden<U, TM, RES>(G, xs, w, sWT, &g, row0, nrows, sX, sW, sH1, sH2);
 }
 
 // ---------------------------------------------------------------------------------------------
 // K7: fused actor forward -> Gumbel-softmax -> running critic forward -> backward to the action
 // columns -> softmax Jacobian + logit regulariser -> actor backward.  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
-template <int U>
+template <int U, int TM, bool RES>
 __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
-                                                    const float* __restrict__ u_actor, int u_stride, uint64_t seed,
-                                                    uint64_t counter) {
+                                                    const long long* __restrict__ ridx, const float* __restrict__ u_actor,
+                                                    int u_stride, uint64_t seed, uint64_t counter, int max_net) {
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Grp G{(int)threadIdx.x, 0};
   constexpr int HP = U + 4;
+  const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);   // RES: critic net ; else staging chunk
+  float* sWp = sm.take(RES ? max_net : 4);       // RES: actor net
+  float* sWT = sm.take(RES ? U * U : 4);         // RES: critic W2^T
+  float* sWTp = sm.take(RES ? U * U : 4);        // RES: actor W2^T
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * HP);
   float* sH2 = sm.take(TM * HP);
@@ -261,9 +281,15 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
   float* sDa = sm.take(TM * KPAD); // dQ/da then dL/dlogits
   float* sQ = sm.take(TM);
   const AgentDev& me = C.agents[j];
-  const MlpW& pw = me.net[MDP_NET_P];
-  const MlpW& qw = me.net[MDP_NET_Q];
+  MlpW pw = me.net[MDP_NET_P];
+  MlpW qw = me.net[MDP_NET_Q];
   const MlpG& pg = me.grad[0];
+  if (RES) {
+    load_wT_rows<U>(G, sWT, qw.W2, 0, U);
+    load_wT_rows<U>(G, sWTp, pw.W2, 0, U);
+    qw = load_net<U>(G, sW, qw);
+    pw = load_net<U>(G, sWp, pw);
+  }
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   const int R = L.row_stride, K = me.act_dim;
@@ -271,10 +297,11 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
 
   // actor forward on o_j, fresh Gumbel-softmax sample (maddpg.py:49)
   XSrc xp = make_xsrc(batch + me.obs_off, R, me.obs_dim);
-  forward_hidden<U>(G, xp, pw, row0, nrows, sX, sW, sP1, sP2);
-  actor_head<U>(G, sP2, pw, sL);
-  gumbel_softmax_tile(G, sL, sA, KPAD, nrows, me.act_dim, me.n_heads, me.head_dim, u_actor, u_stride, me.act_off, row0, seed, counter,
-                      (uint32_t)(0x200 + j));
+  xp.idx = ridx;
+  forward_hidden<U, TM, RES>(G, xp, pw, row0, nrows, sX, sW, sP1, sP2);
+  actor_head<U, TM>(G, sP2, pw, sL);
+  gumbel_softmax_tile<TM>(G, sL, sA, KPAD, nrows, K, me.n_heads, me.head_dim, u_actor, u_stride, me.act_off, row0, seed, counter,
+                          (uint32_t)(0x200 + j));
   // running critic on [o, a_-j, a_hat_j]
   XSrc xq;
   int a_col0;
@@ -286,8 +313,9 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
     a_col0 = L.obs_sum + me.act_off;
   }
   xq.s_over = sA; xq.over_ld = KPAD; xq.over_c0 = a_col0; xq.over_n = K;
-  forward_hidden<U>(G, xq, qw, row0, nrows, sX, sW, sH1, sH2);
-  critic_head<U>(G, sH2, qw, sQ);
+  xq.idx = ridx;
+  forward_hidden<U, TM, RES>(G, xq, qw, row0, nrows, sX, sW, sH1, sH2);
+  critic_head<U, TM>(G, sH2, qw, sQ);
   // loss partials: sum(-q), sum(logits^2)
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
@@ -313,7 +341,7 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
     sH2[r * HP + u] = (h > 0.f && r < nrows) ? dq * qw.W3[u] : 0.f;
   }
   __syncthreads();
-  backward_hidden<U>(G, xq, qw, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 (critic) now in sH1
+  backward_hidden<U, TM, RES>(G, xq, qw, sWT, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 (critic) now in sH1
   // dQ/da[r][a] = dz1[r,:] . W1[a_col0 + a, :]
   for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
     const int r = idx / K, a = idx - r * K;
@@ -359,7 +387,299 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
     sP2[r * HP + u] = s;
   }
   __syncthreads();
-  backward_hidden<U>(G, xp, pw, &pg, row0, nrows, sX, sW, sP1, sP2);
+  backward_hidden<U, TM, RES>(G, xp, pw, sWTp, &pg, row0, nrows, sX, sW, sP1, sP2);
+}
+
+
+// =============================================================================================
+// Tile-resident variants (small configs, maddpg-mode critics): one prologue loads the X row tile (gathered
+// through ridx straight from the replay ring) and every net the kernel touches into shared memory; the rest
+// of the kernel never waits on global memory again.
+// =============================================================================================
+template <int U, int TM>
+__global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                      const long long* __restrict__ ridx, const float* __restrict__ u_target,
+                                                      int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
+                                                      float* __restrict__ target_act_out, int XPf) {
+  if (C.ctl) counter += C.ctl[0];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int HP = U + 4;
+  const Grp G{(int)threadIdx.x, 0};
+  SmemCarve sm(smem_raw);
+  float* sXf = sm.take(TM * XPf);  // [next_obs_all | a'_all]
+  float* sH1 = sm.take(TM * HP);
+  float* sH2 = sm.take(TM * HP);
+  float* sL = sm.take(TM * KPAD);
+  float* sQ = sm.take(TM);
+  float* sRD = sm.take(2 * TM);    // rew_j, done_j
+  float* sNets = sm.p;
+  const AgentDev& me = C.agents[j];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  const int R = L.row_stride, n = C.n_agents;
+  // prologue: ONE burst of TMA bulk copies (all target actors, the target critic, the gathered next_obs rows)
+  __shared__ __align__(8) unsigned long long bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  const int nx4 = (L.obs_sum + 3) & ~3;
+  float* p = sNets;
+  if (threadIdx.x == 0) {
+    uint32_t total = (uint32_t)nrows * nx4 * 4u;
+    for (int i = 0; i < n; ++i) total += net_floats_padded(C.agents[i].obs_dim, U, C.agents[i].act_dim) * 4u;
+    total += net_floats_padded(me.net[MDP_NET_TARGET_Q].in, U, 1) * 4u;
+    mbar_arrive_expect_tx(&bar, total);
+    float* q = sNets;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t nf = net_floats_padded(C.agents[i].obs_dim, U, C.agents[i].act_dim);
+      bulk_g2s(q, C.agents[i].net[MDP_NET_TARGET_P].W1, nf * 4u, &bar);
+      q += nf;
+    }
+    bulk_g2s(q, me.net[MDP_NET_TARGET_Q].W1, net_floats_padded(me.net[MDP_NET_TARGET_Q].in, U, 1) * 4u, &bar);
+  }
+  bulk_rows<TM>(G, sXf, XPf, batch, R, ridx, row0, nrows, L.nx_off, nx4, &bar);
+  for (int i = threadIdx.x; i < 2 * TM; i += NT) {
+    const int r = i >> 1, which = i & 1;
+    float v = 0.f;
+    if (r < nrows) v = batch[(ridx ? ridx[row0 + r] : row0 + r) * R + (which ? L.dn_off : L.rw_off) + j];
+    sRD[i] = v;
+  }
+  for (int i = 0; i < n; ++i) p += net_floats_padded(C.agents[i].obs_dim, U, C.agents[i].act_dim);
+  const MlpW tq = net_at<U>(p, me.net[MDP_NET_TARGET_Q].in, 1);
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  // a'_i = gumbel_softmax(target_p_i(next_obs_i)) written straight into the critic-input columns of the tile
+  p = sNets;
+  for (int i = 0; i < n; ++i) {
+    const AgentDev& ag = C.agents[i];
+    const MlpW w = net_at<U>(p, ag.obs_dim, ag.act_dim);
+    p += net_floats_padded(ag.obs_dim, U, ag.act_dim);
+    forward_hidden_res<U, TM>(G, sXf + ag.obs_off, XPf, w, sH1, sH2);
+    actor_head<U, TM>(G, sH2, w, sL);
+    gumbel_softmax_tile<TM>(G, sL, sXf + L.obs_sum + ag.act_off, XPf, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u_target,
+                            u_stride, ag.act_off, row0, seed, counter, (uint32_t)(0x100 + i));
+  }
+  if (target_act_out) {
+    for (int idx = threadIdx.x; idx < nrows * C.act_sum; idx += NT) {
+      const int r = idx / C.act_sum, c = idx - r * C.act_sum;
+      target_act_out[(row0 + r) * u_stride + c] = sXf[r * XPf + L.obs_sum + c];
+    }
+  }
+  forward_hidden_res<U, TM>(G, sXf, XPf, tq, sH1, sH2);
+  critic_head<U, TM>(G, sH2, tq, sQ);
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    double sy = 0, syy = 0, sr = 0, sq = 0;
+    if (r < nrows && r < TM) {
+      const double rew = (double)sRD[2 * r], done = (double)sRD[2 * r + 1];
+      const float qn = sQ[r];
+      const double y = rew + C.gamma * (1.0 - done) * (double)qn;
+      y_out[row0 + r] = (float)y;
+      sy = y; syy = y * y; sr = rew; sq = (double)qn;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      syy += __shfl_xor_sync(0xffffffffu, syy, o);
+      sr += __shfl_xor_sync(0xffffffffu, sr, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (r == 0) {
+      double* st = C.stats + 8 * j;
+      atomicAdd(st + 3, sy); atomicAdd(st + 4, syy); atomicAdd(st + 5, sr); atomicAdd(st + 6, sq);
+      atomicAdd(st + 7, (double)nrows);
+    }
+  }
+}
+
+template <int U, int TM>
+__global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                         const long long* __restrict__ ridx, const float* __restrict__ y,
+                                                         float* __restrict__ q_out, int XPf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int HP = U + 4;
+  const Grp G{(int)threadIdx.x, 0};
+  SmemCarve sm(smem_raw);
+  float* sXf = sm.take(TM * XPf);
+  float* sH1 = sm.take(TM * HP);
+  float* sH2 = sm.take(TM * HP);
+  float* sQ = sm.take(TM);
+  float* sDq = sm.take(32);
+  float* sWT = sm.take(U * U);
+  float* sNet = sm.p;
+  const AgentDev& me = C.agents[j];
+  const MlpG& g = me.grad[1];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) C.adam_t[2 * j + 1] += 1;
+  __shared__ __align__(8) unsigned long long bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  const int x4 = (L.x_dim + 3) & ~3;
+  const MlpW gq = me.net[MDP_NET_Q];
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, (uint32_t)nrows * x4 * 4u + net_floats_padded(gq.in, U, 1) * 4u);
+    bulk_g2s(sNet, gq.W1, net_floats_padded(gq.in, U, 1) * 4u, &bar);
+  }
+  bulk_rows<TM>(G, sXf, XPf, batch, L.row_stride, ridx, row0, nrows, 0, x4, &bar);
+  const MlpW w = net_at<U>(sNet, gq.in, 1);
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  build_wT_swz<U>(G, sWT, w.W2);  // published by the barriers inside forward_hidden_res
+  forward_hidden_res<U, TM>(G, sXf, XPf, w, sH1, sH2);
+  critic_head<U, TM>(G, sH2, w, sQ);
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    float d = 0.f;
+    double se = 0.0;
+    if (r < nrows && r < TM) {
+      const float q = sQ[r];
+      const float diff = q - y[row0 + r];
+      d = 2.0f * diff / (float)B;
+      se = (double)diff * (double)diff;
+      if (q_out) q_out[row0 + r] = q;
+    }
+    sDq[r] = d;
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (r == 0) atomicAdd(C.stats + 8 * j + 0, se);
+  }
+  __syncthreads();
+  if (threadIdx.x < U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s = fmaf(sH2[r * HP + threadIdx.x], sDq[r], s);
+    atomicAdd(g.W3 + threadIdx.x, s);
+  } else if (threadIdx.x == U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s += sDq[r];
+    atomicAdd(g.b3, s);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sH2[r * HP + u];
+    sH2[r * HP + u] = h > 0.f ? sDq[r] * w.W3[u] : 0.f;
+  }
+  __syncthreads();
+  backward_hidden_res<U, TM>(G, sXf, XPf, w, sWT, &g, sH1, sH2);
+}
+
+template <int U, int TM>
+__global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                        const long long* __restrict__ ridx, const float* __restrict__ u_actor,
+                                                        int u_stride, uint64_t seed, uint64_t counter, int XPf) {
+  if (C.ctl) counter += C.ctl[0];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int HP = U + 4;
+  const Grp G{(int)threadIdx.x, 0};
+  SmemCarve sm(smem_raw);
+  float* sXf = sm.take(TM * XPf);
+  float* sH1 = sm.take(TM * HP);
+  float* sH2 = sm.take(TM * HP);
+  float* sP1 = sm.take(TM * HP);
+  float* sP2 = sm.take(TM * HP);
+  float* sL = sm.take(TM * KPAD);
+  float* sDa = sm.take(TM * KPAD);
+  float* sQ = sm.take(TM);
+  float* sWT = sm.take(U * U);
+  float* sWTp = sm.take(U * U);
+  float* sNets = sm.p;
+  const AgentDev& me = C.agents[j];
+  const MlpG& pg = me.grad[0];
+  const long long row0 = (long long)blockIdx.x * TM;
+  const int nrows = (int)min((long long)TM, B - row0);
+  const int K = me.act_dim;
+  const int a_col0 = L.obs_sum + me.act_off;
+  if (blockIdx.x == 0 && threadIdx.x == 0) C.adam_t[2 * j + 0] += 1;
+  __shared__ __align__(8) unsigned long long bar;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  const int x4 = (L.x_dim + 3) & ~3;
+  const MlpW gq = me.net[MDP_NET_Q], gp = me.net[MDP_NET_P];
+  const uint32_t nq = net_floats_padded(gq.in, U, 1), np_ = net_floats_padded(gp.in, U, gp.out);
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, (uint32_t)nrows * x4 * 4u + (nq + np_) * 4u);
+    bulk_g2s(sNets, gq.W1, nq * 4u, &bar);
+    bulk_g2s(sNets + nq, gp.W1, np_ * 4u, &bar);
+  }
+  bulk_rows<TM>(G, sXf, XPf, batch, L.row_stride, ridx, row0, nrows, 0, x4, &bar);
+  const MlpW qw = net_at<U>(sNets, gq.in, 1);
+  const MlpW pw = net_at<U>(sNets + nq, gp.in, gp.out);
+  mbar_wait(&bar, 0);
+  __syncthreads();
+  build_wT_swz<U>(G, sWT, qw.W2);
+  build_wT_swz<U>(G, sWTp, pw.W2);
+  // actor forward on o_j; the fresh sample replaces the replayed action inside the tile (maddpg.py:49-50)
+  forward_hidden_res<U, TM>(G, sXf + me.obs_off, XPf, pw, sP1, sP2);
+  actor_head<U, TM>(G, sP2, pw, sL);
+  gumbel_softmax_tile<TM>(G, sL, sXf + a_col0, XPf, nrows, K, me.n_heads, me.head_dim, u_actor, u_stride, me.act_off, row0, seed,
+                          counter, (uint32_t)(0x200 + j));
+  forward_hidden_res<U, TM>(G, sXf, XPf, qw, sH1, sH2);
+  critic_head<U, TM>(G, sH2, qw, sQ);
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    double sq = 0.0, sl = 0.0;
+    if (r < nrows && r < TM) {
+      sq = -(double)sQ[r];
+      for (int a = 0; a < K; ++a) sl += (double)sL[r * KPAD + a] * (double)sL[r * KPAD + a];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      sl += __shfl_xor_sync(0xffffffffu, sl, o);
+    }
+    if (r == 0) {
+      atomicAdd(C.stats + 8 * j + 1, sq);
+      atomicAdd(C.stats + 8 * j + 2, sl);
+    }
+  }
+  const float dq = -1.0f / (float)B;
+  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sH2[r * HP + u];
+    sH2[r * HP + u] = (h > 0.f && r < nrows) ? dq * qw.W3[u] : 0.f;
+  }
+  __syncthreads();
+  backward_hidden_res<U, TM>(G, sXf, XPf, qw, sWT, nullptr, sH1, sH2);  // dz1 (critic) now in sH1
+  for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
+    const int r = idx / K, a = idx - r * K;
+    const float* w1row = qw.W1 + (size_t)(a_col0 + a) * U;
+    float s = 0.f;
+    for (int u = 0; u < U; ++u) s = fmaf(sH1[r * HP + u], w1row[u], s);
+    sDa[r * KPAD + a] = s;
+  }
+  __syncthreads();
+  const float regc = (float)(2.0 * C.actor_reg / ((double)B * (double)K));
+  for (int idx = threadIdx.x; idx < TM * me.n_heads; idx += NT) {
+    const int r = idx / me.n_heads, h = idx - r * me.n_heads;
+    const int o = h ? me.head_dim[0] : 0, nh = me.head_dim[h];
+    const float* pa = sXf + r * XPf + a_col0;
+    float dot = 0.f;
+    for (int a = 0; a < nh; ++a) dot = fmaf(pa[o + a], sDa[r * KPAD + o + a], dot);
+    for (int a = 0; a < nh; ++a) {
+      const float dl = pa[o + a] * (sDa[r * KPAD + o + a] - dot) + regc * sL[r * KPAD + o + a];
+      sDa[r * KPAD + o + a] = (r < nrows) ? dl : 0.f;
+    }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < U * K; idx += NT) {
+    const int u = idx / K, a = idx - u * K;
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s = fmaf(sP2[r * HP + u], sDa[r * KPAD + a], s);
+    atomicAdd(pg.W3 + idx, s);
+  }
+  if (threadIdx.x < K) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s += sDa[r * KPAD + threadIdx.x];
+    atomicAdd(pg.b3 + threadIdx.x, s);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sP2[r * HP + u];
+    float s = 0.f;
+    if (h > 0.f)
+      for (int a = 0; a < K; ++a) s = fmaf(sDa[r * KPAD + a], pw.W3[u * K + a], s);
+    sP2[r * HP + u] = s;
+  }
+  __syncthreads();
+  backward_hidden_res<U, TM>(G, sXf + me.obs_off, XPf, pw, sWTp, &pg, sP1, sP2);
 }
 
 }  // namespace mdp
@@ -404,13 +724,56 @@ static CoreDev core_dev(const mdp_core* c) {
 
 CoreDev core_dev_for_rollout(const mdp_core* c) { return core_dev(c); }
 
-template <int U>
-static size_t smem_bytes(int extra_floats) { return (size_t)(smem_floats_base<U>() + extra_floats + 64) * sizeof(float); }
-
 template <typename Kern>
 static int set_smem(Kern kern, size_t smem) {
   if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return MDP_OK;
+}
+
+template <int V> struct IC { static constexpr int value = V; };
+template <bool V> struct BC { static constexpr bool value = V; };
+
+// Launch plan of the fused MLP kernels: tile rows (16 doubles the CTA count for the reference's batch of
+// 1024 on 148 SMs), and whether every net a kernel touches fits in shared memory (resident variant).
+struct Plan {
+  int TM;
+  bool res;
+  int max_net;  // floats of the largest net (padded), for the resident buffers
+};
+
+static Plan make_plan(const mdp_core* c, int rows) {
+  Plan p;
+  p.TM = rows <= 2048 ? 16 : 32;
+  int mx = 0;
+  for (int i = 0; i < c->cfg.n_agents; ++i)
+    for (int k = 0; k < 4; ++k) {
+      const int n = net_floats_padded(c->lay.net_in[i][k], c->cfg.num_units, c->lay.net_out[i][k]);
+      if (n > mx) mx = n;
+    }
+  p.max_net = mx;
+  // resident budget: two nets + two transposed W2 + activations must stay under ~160 KB (k_actor_grads)
+  p.res = c->cfg.num_units == 64 && (size_t)(2 * mx + 2 * 64 * 64) * 4 <= 120 * 1024;
+  return p;
+}
+
+template <typename F>
+static int dispatch(int U, const Plan& p, F&& f) {
+  if (U == 64) {
+    if (p.TM == 16) return p.res ? f(IC<64>{}, IC<16>{}, BC<true>{}) : f(IC<64>{}, IC<16>{}, BC<false>{});
+    return p.res ? f(IC<64>{}, IC<32>{}, BC<true>{}) : f(IC<64>{}, IC<32>{}, BC<false>{});
+  }
+  if (p.TM == 16) return f(IC<128>{}, IC<16>{}, BC<false>{});
+  return f(IC<128>{}, IC<32>{}, BC<false>{});
+}
+
+// floats of dynamic shared memory: weight buffers + x chunk + n_act activation tiles + extras
+static size_t smem_for(int U, const Plan& p, int n_wbuf, int n_wT, int n_act, int extra_floats) {
+  const int TMv = p.TM;
+  size_t f = 0;
+  f += (size_t)(p.res ? p.max_net : KC * U) + (size_t)(n_wbuf - 1) * (p.res ? p.max_net : 4);
+  f += (size_t)n_wT * (p.res ? U * U : 4);
+  f += (size_t)TMv * XP + (size_t)n_act * TMv * (U + 4) + extra_floats + 128;
+  return f * sizeof(float);
 }
 
 static int check_lay(const mdp_core* c, const mdp_ring_layout* lay) {
@@ -522,7 +885,6 @@ extern "C" int mdp_core_bind(mdp_core* c, float* params, float* grads, float* ad
   return MDP_OK;
 }
 
-#define MDP_DISPATCH_U(core, expr64, expr128) ((core)->cfg.num_units == 64 ? (expr64) : (expr128))
 
 extern "C" int mdp_actor_act(mdp_core* c, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
                              const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u,
@@ -532,14 +894,18 @@ extern "C" int mdp_actor_act(mdp_core* c, int32_t agent_begin, int32_t agent_cou
               "mdp_actor_act: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
-  dim3 grid(cdiv(E, TM), agent_count);
-  auto go = [&](auto kern, size_t smem) -> int {
+  const Plan p = make_plan(c, E >= 4096 ? 4096 : E);
+  return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
+    constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
+    constexpr bool RES = decltype(res_)::value;
+    auto kern = k_actor_act<U, TMv, RES>;
+    const size_t smem = smem_for(U, p, 1, 0, 2, 2 * TMv * KPAD);
     int rc = set_smem(kern, smem);
     if (rc) return rc;
-    kern<<<grid, NT, smem, st>>>(d, agent_begin, use_target, E, obs, obs_stride, act, act_stride, u, seed, counter, logits_out);
+    kern<<<dim3(cdiv(E, TMv), agent_count), NT, smem, st>>>(d, agent_begin, use_target, E, obs, obs_stride, act, act_stride, u,
+                                                          seed, counter, logits_out, p.max_net);
     return check_launch("k_actor_act");
-  };
-  return MDP_DISPATCH_U(c, go(k_actor_act<64>, smem_bytes<64>(2 * TM * KPAD)), go(k_actor_act<128>, smem_bytes<128>(2 * TM * KPAD)));
+  });
 }
 
 extern "C" int mdp_critic_q(mdp_core* c, int32_t agent, int32_t use_target, int32_t B, const float* x, int32_t x_stride,
@@ -548,18 +914,51 @@ extern "C" int mdp_critic_q(mdp_core* c, int32_t agent, int32_t use_target, int3
   MDP_REQUIRE(x && q_out && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_critic_q: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
-  auto go = [&](auto kern, size_t smem) -> int {
+  const Plan p = make_plan(c, B);
+  return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
+    constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
+    constexpr bool RES = decltype(res_)::value;
+    auto kern = k_critic_q<U, TMv, RES>;
+    const size_t smem = smem_for(U, p, 1, 0, 2, TMv);
     int rc = set_smem(kern, smem);
     if (rc) return rc;
-    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, use_target, B, x, x_stride, q_out);
+    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, use_target, B, x, x_stride, q_out, p.max_net);
     return check_launch("k_critic_q");
-  };
-  return MDP_DISPATCH_U(c, go(k_critic_q<64>, smem_bytes<64>(TM)), go(k_critic_q<128>, smem_bytes<128>(TM)));
+  });
+}
+
+// tile-resident plan: every net a kernel touches + the X row tile fit one CTA's shared memory, and no agent
+// uses a local critic (those keep the streaming kernels)
+struct ResPlan {
+  bool ok;
+  int XPf;                      // pitch of the X row tile
+  size_t td, critic, actor;     // dynamic shared memory (bytes) of the three kernels
+};
+
+static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
+  ResPlan r;
+  r.ok = false;
+  const int U = c->cfg.num_units, n = c->cfg.n_agents, TMv = p.TM, HP = U + 4;
+  for (int i = 0; i < n; ++i)
+    if (c->cfg.local_q[i]) return r;
+  r.XPf = round_up(c->obs_sum + c->act_sum, 4) + 4;
+  auto r4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
+  size_t actors = 0;
+  for (int i = 0; i < n; ++i) actors += net_floats_padded(c->cfg.obs_dim[i], U, c->cfg.act_dim[i]);
+  const size_t crit = net_floats_padded(c->lay.net_in[agent][MDP_NET_Q], U, 1);
+  const size_t act_j = net_floats_padded(c->cfg.obs_dim[agent], U, c->cfg.act_dim[agent]);
+  const size_t tile = r4((size_t)TMv * r.XPf);
+  r.td = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv * KPAD) + r4(TMv) + r4(2 * TMv) + actors + crit + 64) * 4;
+  r.critic = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv) + 32 + (size_t)U * U + crit + 64) * 4;
+  r.actor = (tile + 4 * r4((size_t)TMv * HP) + 2 * r4(TMv * KPAD) + r4(TMv) + 2 * (size_t)U * U + crit + act_j + 64) * 4;
+  const size_t limit = 200 * 1024;
+  r.ok = r.td <= limit && r.critic <= limit && r.actor <= limit;
+  return r;
 }
 
 extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                             const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter, float* y_out,
-                             float* target_act_out, void* stream) {
+                             const int64_t* idx, const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter,
+                             float* y_out, float* target_act_out, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_td_target: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
@@ -567,61 +966,101 @@ extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* 
   cudaStream_t st = (cudaStream_t)stream;
   MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double), st));
   CoreDev d = core_dev(c);
-  const int extra = TM * KPAD + TM + TM * (c->act_stride | 1);
-  auto go = [&](auto kern, size_t smem) -> int {
+  const Plan p = make_plan(c, B);
+  const ResPlan rp = make_res_plan(c, p, agent);
+  const long long* ridx = (const long long*)idx;
+  return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
+    constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
+    constexpr bool RES = decltype(res_)::value;
+    if (rp.ok) {
+      auto kern = k_td_target_res<U, TMv>;
+      int rc2 = set_smem(kern, rp.td);
+      if (rc2) return rc2;
+      kern<<<cdiv(B, TMv), NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
+                                            target_act_out, rp.XPf);
+      return check_launch("k_td_target_res");
+    }
+    auto kern = k_td_target<U, TMv, RES>;
+    const size_t smem = smem_for(U, p, 1, 0, 2, TMv * KPAD + TMv + TMv * (c->act_stride | 1));
     int rc2 = set_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, *lay, B, batch, u_target, u_stride, seed, counter, y_out, target_act_out);
+    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
+                                        target_act_out, p.max_net);
     return check_launch("k_td_target");
-  };
-  return MDP_DISPATCH_U(c, go(k_td_target<64>, smem_bytes<64>(extra)), go(k_td_target<128>, smem_bytes<128>(extra)));
+  });
 }
 
 extern "C" int mdp_critic_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                                const float* y, float* q_out, void* stream) {
+                                const int64_t* idx, const float* y, float* q_out, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_critic_grads: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
   MDP_REQUIRE(batch && y && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_critic_grads: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
-  auto go = [&](auto kern, size_t smem) -> int {
+  const Plan p = make_plan(c, B);
+  const ResPlan rp = make_res_plan(c, p, agent);
+  const long long* ridx = (const long long*)idx;
+  return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
+    constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
+    constexpr bool RES = decltype(res_)::value;
+    if (rp.ok) {
+      auto kern = k_critic_grads_res<U, TMv>;
+      int rc2 = set_smem(kern, rp.critic);
+      if (rc2) return rc2;
+      kern<<<cdiv(B, TMv), NT, rp.critic, st>>>(d, agent, *lay, B, batch, ridx, y, q_out, rp.XPf);
+      return check_launch("k_critic_grads_res");
+    }
+    auto kern = k_critic_grads<U, TMv, RES>;
+    const size_t smem = smem_for(U, p, 1, 1, 2, TMv + 32);
     int rc2 = set_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, *lay, B, batch, y, q_out);
+    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, y, q_out, p.max_net);
     return check_launch("k_critic_grads");
-  };
-  return MDP_DISPATCH_U(c, go(k_critic_grads<64>, smem_bytes<64>(2 * TM)), go(k_critic_grads<128>, smem_bytes<128>(2 * TM)));
+  });
 }
 
 extern "C" int mdp_actor_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                               const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter, void* stream) {
+                               const int64_t* idx, const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter,
+                               void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_actor_grads: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
   MDP_REQUIRE(batch && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_actor_grads: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
-  auto go = [&](auto kern, size_t smem) -> int {
+  const Plan p = make_plan(c, B);
+  const ResPlan rp = make_res_plan(c, p, agent);
+  const long long* ridx = (const long long*)idx;
+  return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
+    constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
+    constexpr bool RES = decltype(res_)::value;
+    if (rp.ok) {
+      auto kern = k_actor_grads_res<U, TMv>;
+      int rc2 = set_smem(kern, rp.actor);
+      if (rc2) return rc2;
+      kern<<<cdiv(B, TMv), NT, rp.actor, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, rp.XPf);
+      return check_launch("k_actor_grads_res");
+    }
+    auto kern = k_actor_grads<U, TMv, RES>;
+    const size_t smem = smem_for(U, p, 2, 2, 4, 3 * TMv * KPAD + TMv);
     int rc2 = set_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<cdiv(B, TM), NT, smem, st>>>(d, agent, *lay, B, batch, u_actor, u_stride, seed, counter);
+    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, p.max_net);
     return check_launch("k_actor_grads");
-  };
-  const int extra64 = 2 * TM * (64 + 4) + 3 * TM * KPAD + TM, extra128 = 2 * TM * (128 + 4) + 3 * TM * KPAD + TM;
-  return MDP_DISPATCH_U(c, go(k_actor_grads<64>, smem_bytes<64>(extra64)), go(k_actor_grads<128>, smem_bytes<128>(extra128)));
+  });
 }
 
 extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                                const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
-                                uint64_t counter, float* y_scratch, void* stream) {
-  int rc = mdp_td_target(c, agent, lay, B, batch, u_target, u_stride, seed, counter, y_scratch, nullptr, stream);
+                                const int64_t* idx, const float* u_target, const float* u_actor, int32_t u_stride,
+                                uint64_t seed, uint64_t counter, float* y_scratch, void* stream) {
+  int rc = mdp_td_target(c, agent, lay, B, batch, idx, u_target, u_stride, seed, counter, y_scratch, nullptr, stream);
   if (rc) return rc;
-  rc = mdp_critic_grads(c, agent, lay, B, batch, y_scratch, nullptr, stream);
+  rc = mdp_critic_grads(c, agent, lay, B, batch, idx, y_scratch, nullptr, stream);
   if (rc) return rc;
   rc = mdp_clip_adam_polyak(c, agent, 1, 1.0f, 1, stream);
   if (rc) return rc;
-  rc = mdp_actor_grads(c, agent, lay, B, batch, u_actor, u_stride, seed, counter, stream);
+  rc = mdp_actor_grads(c, agent, lay, B, batch, idx, u_actor, u_stride, seed, counter, stream);
   if (rc) return rc;
   return mdp_clip_adam_polyak(c, agent, 0, 1.0f, 1, stream);
 }

@@ -50,14 +50,14 @@ class DataParallelUpdater(object):
             self.allreduce_bytes += segment.numel() * segment.element_size()
         return segment
 
-    def update_agent(self, j, batch, u_target=None, u_actor=None):
+    def update_agent(self, j, batch, u_target=None, u_actor=None, idx=None):
         c = self.core
         scale = 1.0 / self.world
-        y = c.td_target(j, batch, u_target)
-        c.critic_grads(j, batch, y)
+        y = c.td_target(j, batch, u_target, idx=idx)
+        c.critic_grads(j, batch, y, idx=idx)
         self.allreduce_sum(c.train_segment(c.grads, j, 1))
         c.clip_adam_polyak(j, 1, grad_scale=scale)
-        c.actor_grads(j, batch, u_actor)
+        c.actor_grads(j, batch, u_actor, idx=idx)
         self.allreduce_sum(c.train_segment(c.grads, j, 0))
         c.clip_adam_polyak(j, 0, grad_scale=scale)
 

@@ -187,9 +187,8 @@ class GraphedUpdateRound(object):
                 core.make_index(self.idx[j], length=0, counter=c, ctl=self.ctl.t)
             else:
                 core.make_index(self.idx[j])
-            core.ring.gather(self.idx[j], out=self.batch)
             c += 1
-            core.update_agent(j, self.batch, counter=c if relative else None)
+            core.update_agent(j, core.ring.ring, counter=c if relative else None, idx=self.idx[j])  # fused gather
         if relative:
             self.ctl.advance(c, 0, 0)
         return c

@@ -204,25 +204,27 @@ class MADDPGCore(object):
             self._batch[B] = torch.empty((B, self.ring.row_stride), dtype=torch.float32, device=self.device)
         return self._y[B], self._batch[B]
 
-    def td_target(self, agent, batch, u_target=None, want_target_act=False):
-        B = batch.shape[0]
+    def td_target(self, agent, batch, u_target=None, want_target_act=False, idx=None):
+        """``idx`` (int64 CUDA tensor): rows are ``batch[idx[b]]`` (pass the ring: the gather is fused in)."""
+        B = batch.shape[0] if idx is None else idx.shape[0]
         y, _ = self._scratch(B)
         ta = torch.zeros((B, self.act_stride), dtype=torch.float32, device=self.device) if want_target_act else None
-        _lib.check(_lib.lib.mdp_td_target(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(u_target),
-                                          self.act_stride, self.seed, self.next_counter(), _lib.ptr(y), _lib.ptr(ta),
+        _lib.check(_lib.lib.mdp_td_target(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(idx),
+                                          _lib.ptr(u_target), self.act_stride, self.seed, self.next_counter(), _lib.ptr(y), _lib.ptr(ta),
                                           _lib.current_stream()), "mdp_td_target")
         return (y, ta) if want_target_act else y
 
-    def critic_grads(self, agent, batch, y, want_q=False):
-        B = batch.shape[0]
+    def critic_grads(self, agent, batch, y, want_q=False, idx=None):
+        B = batch.shape[0] if idx is None else idx.shape[0]
         q = torch.empty(B, dtype=torch.float32, device=self.device) if want_q else None
-        _lib.check(_lib.lib.mdp_critic_grads(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(y),
-                                             _lib.ptr(q), _lib.current_stream()), "mdp_critic_grads")
+        _lib.check(_lib.lib.mdp_critic_grads(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(idx),
+                                             _lib.ptr(y), _lib.ptr(q), _lib.current_stream()), "mdp_critic_grads")
         return q
 
-    def actor_grads(self, agent, batch, u_actor=None):
-        B = batch.shape[0]
-        _lib.check(_lib.lib.mdp_actor_grads(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(u_actor),
+    def actor_grads(self, agent, batch, u_actor=None, idx=None):
+        B = batch.shape[0] if idx is None else idx.shape[0]
+        _lib.check(_lib.lib.mdp_actor_grads(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(idx),
+                                            _lib.ptr(u_actor),
                                             self.act_stride, self.seed, self.next_counter(), _lib.current_stream()),
                    "mdp_actor_grads")
 
@@ -230,11 +232,12 @@ class MADDPGCore(object):
         _lib.check(_lib.lib.mdp_clip_adam_polyak(self._h, agent, which, float(grad_scale), int(do_polyak),
                                                  _lib.current_stream()), "mdp_clip_adam_polyak")
 
-    def update_agent(self, agent, batch, u_target=None, u_actor=None, counter=None):
-        """maddpg.py:181-194 for one agent, five kernels on the current stream."""
-        B = batch.shape[0]
+    def update_agent(self, agent, batch, u_target=None, u_actor=None, counter=None, idx=None):
+        """maddpg.py:181-194 for one agent, five kernels on the current stream.  With ``idx`` the rows are
+        ``batch[idx[b]]``: pass ``self.ring.ring`` and the sampled indices and no gather kernel is needed."""
+        B = batch.shape[0] if idx is None else idx.shape[0]
         y, _ = self._scratch(B)
-        _lib.check(_lib.lib.mdp_update_agent(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch),
+        _lib.check(_lib.lib.mdp_update_agent(self._h, agent, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(idx),
                                              _lib.ptr(u_target), _lib.ptr(u_actor), self.act_stride, self.seed,
                                              self.next_counter() if counter is None else counter, _lib.ptr(y),
                                              _lib.current_stream()), "mdp_update_agent")
@@ -399,8 +402,6 @@ class MADDPGAgentTrainer(AgentTrainer):
         B = self.args.batch_size
         self.replay_sample_index = self.replay_buffer.make_index(B) if index is None else index
         idx = core.ring.index_tensor(self.replay_sample_index)
-        _, batch = core._scratch(idx.shape[0])
-        core.ring.gather(idx, out=batch)
         ut, ua = self._noise.get("u_target"), self._noise.get("u_actor")
         self._noise = {}
         if ut is not None:
@@ -412,5 +413,5 @@ class MADDPGAgentTrainer(AgentTrainer):
             o = core.act_off[self.agent_index]
             ua_j[:, o:o + core.act_dims[self.agent_index]] = self._dev(ua)
             ua = ua_j
-        core.update_agent(self.agent_index, batch, ut, ua)
+        core.update_agent(self.agent_index, core.ring.ring, ut, ua, idx=idx)  # gather fused into the kernels
         return core.read_stats(self.agent_index, idx.shape[0])

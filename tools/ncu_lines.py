@@ -34,10 +34,8 @@ def main():
         secs = [i for i, l in enumerate(txt) if l.startswith(".text.")]
         for si, s in enumerate(secs):
             dem = subprocess.run(["c++filt", txt[s][6:].rstrip(":")], capture_output=True, text=True).stdout.strip()
-            if dem.replace(" ", "") != kname.replace("void ", "").replace(" ", "").replace("(int)", "").replace("(bool)", ""):
-                # tolerate formatting differences: compare on the template-less name + argument count
-                if kern not in dem or dem.count(",") != kname.count(",") or not _same_targs(dem, kname):
-                    continue
+            if _norm(dem) != _norm(kname):
+                continue
             end = secs[si + 1] if si + 1 < len(secs) else len(txt)
             cur = None
             for l in txt[s:end]:
@@ -52,7 +50,8 @@ def main():
             break
         if mang:
             break
-    assert insts and len(insts) == len(data), (len(insts), len(data), kname)
+    assert insts and len(data) >= len(insts), (len(insts), len(data), kname)
+    data = data[:len(insts)]  # the report may hold several launches of the kernel: use the first
     base = int(data[0][0], 16)
     a2l = dict(insts)
     by, samp = collections.Counter(), collections.Counter()
@@ -72,11 +71,11 @@ def main():
         print("%5.1f%% inst %5.1f%% stall-samples  %-18s:%4d  %s" % (100 * v / tot, 100 * samp[ln] / ts, f, n, text[:100]))
 
 
-def _same_targs(dem, kname):
-    nums = lambda s: re.findall(r"<([^>]*)>", s.replace("(int)", "").replace("(bool)", ""))
-    a, b = nums(dem), nums(kname)
-    norm = lambda t: t.replace(" ", "").replace("true", "1").replace("false", "0")
-    return bool(a and b) and norm(a[0]) == norm(b[0])
+def _norm(name):
+    """kernel name up to the argument list, with template arguments normalised"""
+    n = name.replace("void ", "").replace("(int)", "").replace("(bool)", "").replace(" ", "")
+    n = n.replace("true", "1").replace("false", "0")
+    return n.split("(")[0]
 
 
 if __name__ == "__main__":
