@@ -288,6 +288,22 @@ def main():
     launches_upd = _lib.launch_count() + (gupd.graph_launches if gupd else 0) - l0
     upd_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in uev))
     upd_value = R * A * world / (upd_ms * 1e-3)
+    # ---- (3b) grouped ("Jacobi") rounds: all agents per launch -- throughput mode, documented deviation ----------
+    grp_value = grp_ms = None
+    if world == 1:
+        ggrp = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph, grouped=True)
+        for r in range(3):
+            ggrp.run(1)
+        barrier()
+        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
+        for a, b in gev:
+            flush_l2()
+            a.record()
+            ggrp.run(1)
+            b.record()
+        barrier()
+        grp_ms = sum(a.elapsed_time(b) for a, b in gev)
+        grp_value = R * A / (grp_ms * 1e-3)
     clocks = sampler.stop()
 
     # ---- (4) end to end through the reference-shaped API with host buffers ------------------------------------
@@ -376,6 +392,10 @@ def main():
                                "gpu_launches": int(launches_upd), "flops_per_round": flops_round,
                                "achieved_tflops": flops_round * R / (upd_ms * 1e-3) / 1e12,
                                "allreduce_bytes_per_round": dp.allreduce_bytes // max(1, R + 3),
+                               "order": "sequential agents (reference order, parity mode)",
+                               "grouped": None if grp_value is None else {
+                                   "value": grp_value, "unit": "critic updates/s", "ms_per_round": grp_ms / R,
+                                   "order": "all agents per launch (Jacobi order; deviation documented in DESIGN.md)"},
                                "e2e": {"value": Re * A * world / e2e_upd_s, "unit": "critic updates/s",
                                        "api": "MADDPGAgentTrainer.update (python index draw + H2D idx + D2H stats)"}},
         }

@@ -207,6 +207,18 @@ int mdp_update_agent(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, 
                      const int64_t* idx, const float* u_target, const float* u_actor, int32_t u_stride, uint64_t seed,
                      uint64_t counter, float* y_scratch, void* stream);
 
+/* Grouped round ("Jacobi" order): the five kernels of mdp_update_agent launched ONCE for all agents
+ * (grid.y = agent): every TD target uses the pre-round target actors, then all critics step, then all actors.
+ * Differs from the reference's agent-by-agent order (train.py:160-161) only in that agent j does not see the
+ * polyak step of agents i < j taken earlier in the same round -- a documented throughput mode, not the parity
+ * mode.  idx: NULL, or int64 [n_agents][idx_agent_stride] index sets (idx_agent_stride = 0 shares one set);
+ * y_scratch: float [n_agents][B].  grad_scale as in mdp_clip_adam_polyak. */
+int mdp_update_all(mdp_core* core, const mdp_ring_layout* lay, int32_t B, const float* batch, const int64_t* idx,
+                   int64_t idx_agent_stride, uint64_t seed, uint64_t counter, float* y_scratch, float grad_scale,
+                   void* stream);
+/* mdp_clip_adam_polyak for every agent's actor (which = 0) or critic (which = 1) in one launch. */
+int mdp_clip_adam_polyak_all(mdp_core* core, int32_t which, float grad_scale, int32_t do_polyak, void* stream);
+
 /* Persistent episode kernel: `steps` lockstep iterations of experiments/train.py:112-133 (action ->
  * env.step -> experience, optional env.reset at the end) in ONE launch.  Each CTA keeps 32 env instances'
  * state, observation tile, sampled actions and (when they fit) all agents' actor weights in shared

@@ -67,9 +67,76 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
   }
 }
 
+// all agents in one launch: grid = (6 variables, n_agents); pointers come from the device agent table
+__global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* __restrict__ agents, int which, int units,
+                                                               float* __restrict__ grads_base, float* __restrict__ m_base,
+                                                               float* __restrict__ v_base, const int* __restrict__ adam_t,
+                                                               float grad_scale, float clip, double lr, double beta1,
+                                                               double beta2, float eps, float polyak, int do_polyak) {
+  __shared__ float red[32];
+  __shared__ float s_factor, s_lr_t;
+  const int j = blockIdx.y, var = blockIdx.x;
+  const AgentDev& ag = agents[j];
+  const MlpW& w = ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q];
+  const MlpW& wt = ag.net[which == 0 ? MDP_NET_TARGET_P : MDP_NET_TARGET_Q];
+  const long long U = units, in = w.in, out = w.out;
+  const long long lens[6] = {in * U, U, U * U, U, U * out, out};
+  long long off = 0;
+  for (int k = 0; k < var; ++k) off += lens[k];
+  const long long len = lens[var];
+  float* g = ag.grad[which].W1 + off;
+  const long long goff = g - grads_base;
+  float* p = const_cast<float*>(w.W1) + off;
+  float* tg = const_cast<float*>(wt.W1) + off;
+  float* mm = m_base + goff;
+  float* vv = v_base + goff;
+  float ss = 0.f;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const float x = g[i] * grad_scale;
+    ss = fmaf(x, x, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) {
+      const float norm = sqrtf(s);
+      s_factor = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;
+      const int t = adam_t[2 * j + which];
+      s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+    }
+  }
+  __syncthreads();
+  const float factor = s_factor * grad_scale, lr_t = s_lr_t;
+  const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2);
+  const float opol = 1.0f - polyak;
+  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+    const float gi = g[i] * factor;
+    const float mi = b1 * mm[i] + ob1 * gi;
+    const float vi = b2 * vv[i] + ob2 * gi * gi;
+    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    mm[i] = mi;
+    vv[i] = vi;
+    p[i] = pi;
+    if (do_polyak) tg[i] = polyak * tg[i] + opol * pi;
+    g[i] = 0.f;
+  }
+}
+
 }  // namespace mdp
 
 using namespace mdp;
+
+extern "C" int mdp_clip_adam_polyak_all(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_clip_adam_polyak_all: core not bound");
+  MDP_REQUIRE(which == 0 || which == 1, "mdp_clip_adam_polyak_all: bad argument");
+  k_clip_adam_polyak_all<<<dim3(6, c->cfg.n_agents), 1024, 0, (cudaStream_t)stream>>>(
+      c->d_agents, which, c->cfg.num_units, c->grads, c->adam_m, c->adam_v, c->adam_t, grad_scale, (float)c->cfg.grad_clip,
+      c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, do_polyak);
+  return check_launch("k_clip_adam_polyak_all");
+}
 
 extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak,
                                     void* stream) {

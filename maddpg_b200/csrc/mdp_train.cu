@@ -18,6 +18,7 @@
 // see DESIGN.md for the tensor-core plan.
 #include "mdp_mlp.cuh"
 
+#include <algorithm>
 #include <new>
 
 namespace mdp {
@@ -96,10 +97,13 @@ __global__ void __launch_bounds__(NT) k_critic_q(CoreDev C, int agent, int use_t
 // K5: fused TD target of agent j.  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
 template <int U, int TM, bool RES>
-__global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                   const long long* __restrict__ ridx, const float* __restrict__ u_target,
                                                   int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
-                                                  float* __restrict__ target_act_out, int max_net) {
+                                                  float* __restrict__ target_act_out, int max_net, long long idx_stride, long long y_stride) {
+  const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  y_out += blockIdx.y * y_stride;
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
@@ -181,9 +185,12 @@ __global__ void __launch_bounds__(NT) k_td_target(CoreDev C, int j, mdp_ring_lay
 // K6: fused critic forward + MSE + backward.  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
 template <int U, int TM, bool RES>
-__global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                      const long long* __restrict__ ridx, const float* __restrict__ y,
-                                                     float* __restrict__ q_out, int max_net) {
+                                                     float* __restrict__ q_out, int max_net, long long idx_stride, long long y_stride) {
+  const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  y += blockIdx.y * y_stride;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
   const Grp G{(int)threadIdx.x, 0};
@@ -259,9 +266,11 @@ __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j, mdp_ring_
 // columns -> softmax Jacobian + logit regulariser -> actor backward.  grid = ceil(B/TM)
 // ---------------------------------------------------------------------------------------------
 template <int U, int TM, bool RES>
-__global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                     const long long* __restrict__ ridx, const float* __restrict__ u_actor,
-                                                    int u_stride, uint64_t seed, uint64_t counter, int max_net) {
+                                                    int u_stride, uint64_t seed, uint64_t counter, int max_net, long long idx_stride, long long y_stride) {
+  const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
+  if (ridx) ridx += blockIdx.y * idx_stride;
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
@@ -397,10 +406,13 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j, mdp_ring_l
 // of the kernel never waits on global memory again.
 // =============================================================================================
 template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                       const long long* __restrict__ ridx, const float* __restrict__ u_target,
                                                       int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
-                                                      float* __restrict__ target_act_out, int XPf) {
+                                                      float* __restrict__ target_act_out, int XPf, long long idx_stride, long long y_stride) {
+  const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  y_out += blockIdx.y * y_stride;
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
@@ -491,9 +503,12 @@ __global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j, mdp_ring
 }
 
 template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                          const long long* __restrict__ ridx, const float* __restrict__ y,
-                                                         float* __restrict__ q_out, int XPf) {
+                                                         float* __restrict__ q_out, int XPf, long long idx_stride, long long y_stride) {
+  const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  y += blockIdx.y * y_stride;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
   const Grp G{(int)threadIdx.x, 0};
@@ -562,9 +577,11 @@ __global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j, mdp_r
 }
 
 template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                         const long long* __restrict__ ridx, const float* __restrict__ u_actor,
-                                                        int u_stride, uint64_t seed, uint64_t counter, int XPf) {
+                                                        int u_stride, uint64_t seed, uint64_t counter, int XPf, long long idx_stride, long long y_stride) {
+  const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
+  if (ridx) ridx += blockIdx.y * idx_stride;
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
@@ -945,8 +962,12 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   auto r4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
   size_t actors = 0;
   for (int i = 0; i < n; ++i) actors += net_floats_padded(c->cfg.obs_dim[i], U, c->cfg.act_dim[i]);
-  const size_t crit = net_floats_padded(c->lay.net_in[agent][MDP_NET_Q], U, 1);
-  const size_t act_j = net_floats_padded(c->cfg.obs_dim[agent], U, c->cfg.act_dim[agent]);
+  (void)agent;  // sized for the largest agent so that grouped launches (grid.y = agent) share one plan
+  size_t crit = 0, act_j = 0;
+  for (int i = 0; i < n; ++i) {
+    crit = std::max(crit, (size_t)net_floats_padded(c->lay.net_in[i][MDP_NET_Q], U, 1));
+    act_j = std::max(act_j, (size_t)net_floats_padded(c->cfg.obs_dim[i], U, c->cfg.act_dim[i]));
+  }
   const size_t tile = r4((size_t)TMv * r.XPf);
   r.td = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv * KPAD) + r4(TMv) + r4(2 * TMv) + actors + crit + 64) * 4;
   r.critic = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv) + 32 + (size_t)U * U + crit + 64) * 4;
@@ -956,15 +977,15 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   return r;
 }
 
-extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                             const int64_t* idx, const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter,
-                             float* y_out, float* target_act_out, void* stream) {
+static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                            const int64_t* idx, long long idx_stride, const float* u_target, int32_t u_stride, uint64_t seed,
+                            uint64_t counter, float* y_out, long long y_stride, float* target_act_out, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_td_target: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
-  MDP_REQUIRE(batch && y_out && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_td_target: bad argument");
+  MDP_REQUIRE(batch && y_out && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_td_target: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double), st));
+  MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
   CoreDev d = core_dev(c);
   const Plan p = make_plan(c, B);
   const ResPlan rp = make_res_plan(c, p, agent);
@@ -976,26 +997,33 @@ extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* 
       auto kern = k_td_target_res<U, TMv>;
       int rc2 = set_smem(kern, rp.td);
       if (rc2) return rc2;
-      kern<<<cdiv(B, TMv), NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
-                                            target_act_out, rp.XPf);
+      kern<<<dim3(cdiv(B, TMv), count), NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
+                                                         target_act_out, rp.XPf, idx_stride, y_stride);
       return check_launch("k_td_target_res");
     }
     auto kern = k_td_target<U, TMv, RES>;
     const size_t smem = smem_for(U, p, 1, 0, 2, TMv * KPAD + TMv + TMv * (c->act_stride | 1));
     int rc2 = set_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
-                                        target_act_out, p.max_net);
+    kern<<<dim3(cdiv(B, TMv), count), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
+                                                     target_act_out, p.max_net, idx_stride, y_stride);
     return check_launch("k_td_target");
   });
 }
 
-extern "C" int mdp_critic_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                                const int64_t* idx, const float* y, float* q_out, void* stream) {
+extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                             const int64_t* idx, const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter,
+                             float* y_out, float* target_act_out, void* stream) {
+  return launch_td_target(c, agent, 1, lay, B, batch, idx, 0, u_target, u_stride, seed, counter, y_out, 0, target_act_out, stream);
+}
+
+static int launch_critic_grads(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                               const int64_t* idx, long long idx_stride, const float* y, long long y_stride, float* q_out,
+                               void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_critic_grads: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
-  MDP_REQUIRE(batch && y && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_critic_grads: bad argument");
+  MDP_REQUIRE(batch && y && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_critic_grads: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
   const Plan p = make_plan(c, B);
@@ -1008,25 +1036,30 @@ extern "C" int mdp_critic_grads(mdp_core* c, int32_t agent, const mdp_ring_layou
       auto kern = k_critic_grads_res<U, TMv>;
       int rc2 = set_smem(kern, rp.critic);
       if (rc2) return rc2;
-      kern<<<cdiv(B, TMv), NT, rp.critic, st>>>(d, agent, *lay, B, batch, ridx, y, q_out, rp.XPf);
+      kern<<<dim3(cdiv(B, TMv), count), NT, rp.critic, st>>>(d, agent, *lay, B, batch, ridx, y, q_out, rp.XPf, idx_stride, y_stride);
       return check_launch("k_critic_grads_res");
     }
     auto kern = k_critic_grads<U, TMv, RES>;
     const size_t smem = smem_for(U, p, 1, 1, 2, TMv + 32);
     int rc2 = set_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, y, q_out, p.max_net);
+    kern<<<dim3(cdiv(B, TMv), count), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, y, q_out, p.max_net, idx_stride, y_stride);
     return check_launch("k_critic_grads");
   });
 }
 
-extern "C" int mdp_actor_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
-                               const int64_t* idx, const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter,
-                               void* stream) {
+extern "C" int mdp_critic_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                                const int64_t* idx, const float* y, float* q_out, void* stream) {
+  return launch_critic_grads(c, agent, 1, lay, B, batch, idx, 0, y, 0, q_out, stream);
+}
+
+static int launch_actor_grads(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                              const int64_t* idx, long long idx_stride, const float* u_actor, int32_t u_stride, uint64_t seed,
+                              uint64_t counter, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_actor_grads: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
-  MDP_REQUIRE(batch && B > 0 && agent >= 0 && agent < c->cfg.n_agents, "mdp_actor_grads: bad argument");
+  MDP_REQUIRE(batch && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_actor_grads: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
   const Plan p = make_plan(c, B);
@@ -1039,16 +1072,44 @@ extern "C" int mdp_actor_grads(mdp_core* c, int32_t agent, const mdp_ring_layout
       auto kern = k_actor_grads_res<U, TMv>;
       int rc2 = set_smem(kern, rp.actor);
       if (rc2) return rc2;
-      kern<<<cdiv(B, TMv), NT, rp.actor, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, rp.XPf);
+      kern<<<dim3(cdiv(B, TMv), count), NT, rp.actor, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, rp.XPf,
+                                                            idx_stride, 0);
       return check_launch("k_actor_grads_res");
     }
     auto kern = k_actor_grads<U, TMv, RES>;
     const size_t smem = smem_for(U, p, 2, 2, 4, 3 * TMv * KPAD + TMv);
     int rc2 = set_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<cdiv(B, TMv), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, p.max_net);
+    kern<<<dim3(cdiv(B, TMv), count), NT, smem, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, p.max_net,
+                                                     idx_stride, 0);
     return check_launch("k_actor_grads");
   });
+}
+
+extern "C" int mdp_actor_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                               const int64_t* idx, const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter,
+                               void* stream) {
+  return launch_actor_grads(c, agent, 1, lay, B, batch, idx, 0, u_actor, u_stride, seed, counter, stream);
+}
+
+// Grouped ("Jacobi") round: every agent's TD target is computed from the PRE-round target actors, then all
+// critics step, then all actors -- five launches for the whole round instead of five per agent.  Deviates from
+// the reference's sequential order (maddpg.py:181-194 run agent by agent, train.py:160-161) only in that agent j
+// does not see the polyak step (1% blend of one Adam step) of agents i < j made earlier in the same round.
+extern "C" int mdp_update_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B, const float* batch, const int64_t* idx,
+                              int64_t idx_agent_stride, uint64_t seed, uint64_t counter, float* y_scratch, float grad_scale,
+                              void* stream) {
+  MDP_REQUIRE(c && y_scratch, "mdp_update_all: null argument");
+  const int n = c->cfg.n_agents;
+  int rc = launch_td_target(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, y_scratch, B, nullptr, stream);
+  if (rc) return rc;
+  rc = launch_critic_grads(c, 0, n, lay, B, batch, idx, idx_agent_stride, y_scratch, B, nullptr, stream);
+  if (rc) return rc;
+  rc = mdp_clip_adam_polyak_all(c, 1, grad_scale, 1, stream);
+  if (rc) return rc;
+  rc = launch_actor_grads(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, stream);
+  if (rc) return rc;
+  return mdp_clip_adam_polyak_all(c, 0, grad_scale, 1, stream);
 }
 
 extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,

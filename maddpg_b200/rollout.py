@@ -168,8 +168,12 @@ class GraphedUpdateRound(object):
     """One update round (every agent once, sequentially: train.py:160-161 -> maddpg.py:167-194) with
     device-side index draws, captured into a CUDA graph (single GPU; multi-GPU uses DataParallelUpdater)."""
 
-    def __init__(self, core, batch_size, ctl=None, use_graph=True):
+    def __init__(self, core, batch_size, ctl=None, use_graph=True, grouped=False):
+        """grouped=False: agents one after the other (the reference's order, parity mode);
+        grouped=True: all agents per launch (mdp_update_all, "Jacobi" order -- throughput mode)."""
         self.core, self.B = core, int(batch_size)
+        self.grouped = bool(grouped)
+        self.idx_all = torch.zeros((core.n, self.B), dtype=torch.int64, device=core.device)
         self.ctl = ctl if ctl is not None else DeviceCtl(None, core)
         self.use_graph = use_graph
         self._graph = None
@@ -181,6 +185,16 @@ class GraphedUpdateRound(object):
     def _body(self, relative):
         core = self.core
         c = 0
+        if self.grouped:
+            flat = self.idx_all.view(-1)
+            if relative:
+                core.make_index(flat, length=0, counter=1, ctl=self.ctl.t)
+                core.update_all(core.ring.ring, idx=self.idx_all, counter=2)
+                self.ctl.advance(2, 0, 0)
+            else:
+                core.make_index(flat)
+                core.update_all(core.ring.ring, idx=self.idx_all)
+            return 2
         for j in range(core.n):
             c += 1
             if relative:

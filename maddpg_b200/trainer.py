@@ -242,6 +242,21 @@ class MADDPGCore(object):
                                              self.next_counter() if counter is None else counter, _lib.ptr(y),
                                              _lib.current_stream()), "mdp_update_agent")
 
+    def update_all(self, batch, idx=None, counter=None, grad_scale=1.0):
+        """Grouped ("Jacobi") round for all agents in five launches (include/maddpg_b200.h: mdp_update_all).
+        idx: None, (B,) shared index set or (n_agents, B) per-agent sets (int64 CUDA)."""
+        if idx is None:
+            B, stride = batch.shape[0], 0
+        else:
+            B, stride = idx.shape[-1], (idx.stride(0) if idx.dim() == 2 else 0)
+        key = ("all", B)
+        if key not in self._y:
+            self._y[key] = torch.empty((self.n, B), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.mdp_update_all(self._h, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(idx), stride,
+                                           self.seed, self.next_counter() if counter is None else counter,
+                                           _lib.ptr(self._y[key]), float(grad_scale), _lib.current_stream()),
+                   "mdp_update_all")
+
     def make_index(self, idx_out, length=None, counter=None, ctl=None):
         """Device-side ``ReplayBuffer.make_index`` (replay_buffer.py:46-47): B uniform draws in [0, len)."""
         _lib.check(_lib.lib.mdp_replay_make_index(_lib.ptr(idx_out), idx_out.shape[0],

@@ -304,3 +304,45 @@ def test_train_loop_drop_in(tmp_path, num_envs):
     core.params.zero_()
     T.load_state(str(tmp_path), trainers)
     assert torch.equal(core.params.cpu(), saved["params"])
+
+
+def test_grouped_update_all_equals_jacobi_order_of_per_agent_kernels():
+    """mdp_update_all (all agents per launch) == the per-agent entry points called in Jacobi order with the
+    same index sets and Philox counter; and it differs from the sequential order only slightly."""
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
+    from maddpg_b200.rollout import BatchedRollout
+    E, B = 512, 256
+    cores = []
+    for _ in range(3):
+        env = BatchedMultiAgentEnv("simple_tag", num_envs=E, squeeze=False, seed=2)
+        core = MADDPGCore(env.obs_dims, env.action_space, [False] * 4, replay_capacity=E * 30, seed=4)
+        core.ring.ring.zero_()  # padding columns are never written: make whole-row comparisons meaningful
+        roll = BatchedRollout(env, core, 25, mode="mega")
+        env.reset_device()
+        roll.run(25)
+        cores.append(core)
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, E * 25, (4, B), generator=g).cuda()
+    a, b, c = cores
+    assert torch.equal(a.params, b.params) and torch.equal(a.ring.ring[:E * 25], b.ring.ring[:E * 25])
+    a.update_all(a.ring.ring, idx=idx, counter=77)
+    # the per-agent kernels draw their own counters; replay the Jacobi order with the grouped call's counter instead
+    b2 = cores[2]
+    b2.counter = 76
+    ys = []
+    for j in range(4):
+        b2.counter = 76
+        ys.append(b2.td_target(j, b2.ring.ring, idx=idx[j]).clone())
+    for j in range(4):
+        b2.critic_grads(j, b2.ring.ring, ys[j], idx=idx[j])
+    for j in range(4):
+        b2.clip_adam_polyak(j, 1)
+    for j in range(4):
+        b2.counter = 76
+        b2.actor_grads(j, b2.ring.ring, idx=idx[j])
+    for j in range(4):
+        b2.clip_adam_polyak(j, 0)
+    torch.cuda.synchronize()
+    assert a.adam_t.cpu().tolist() == [1] * 8 and b2.adam_t.cpu().tolist() == [1] * 8
+    torch.testing.assert_close(a.params, b2.params, rtol=1e-4, atol=2e-5)
+    assert float(a.grads.abs().max()) == 0.0
