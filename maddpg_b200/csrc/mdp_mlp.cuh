@@ -50,16 +50,16 @@ __device__ __forceinline__ XSrc make_xsrc(const float* g0, int ld0, int n0) {
 }
 
 template <int U, int TM>
-__device__ __forceinline__ void zero_acc(float (&acc)[TM / 16][U / 16]) {
+__device__ __forceinline__ void zero_acc(float2 (&acc)[TM / 16][U / 32]) {
 #pragma unroll
   for (int r = 0; r < TM / 16; ++r)
 #pragma unroll
-    for (int c = 0; c < U / 16; ++c) acc[r][c] = 0.f;
+    for (int c = 0; c < U / 32; ++c) acc[r][c] = make_float2(0.f, 0.f);
 }
 
 // acc += sA[rows][0..kc) * sW[0..kc)[cols]; A read as float4 (lda % 4 == 0, kc % 4 == 0, 16-byte aligned)
 template <int U, int TM>
-__device__ __forceinline__ void mma_tile(const Grp& G, float (&acc)[TM / 16][U / 16], const float* __restrict__ sA, int lda,
+__device__ __forceinline__ void mma_tile(const Grp& G, float2 (&acc)[TM / 16][U / 32], const float* __restrict__ sA, int lda,
                                          const float* __restrict__ sW, int kc) {
   constexpr int RM = TM / 16;
   const int ty = G.tid >> 4, tx = G.tid & 15;
@@ -79,10 +79,9 @@ __device__ __forceinline__ void mma_tile(const Grp& G, float (&acc)[TM / 16][U /
         const float4 w = *reinterpret_cast<const float4*>(sW + (k + kk) * U + g * 64 + 4 * tx);
 #pragma unroll
         for (int rr = 0; rr < RM; ++rr) {
-          acc[rr][4 * g + 0] = fmaf(av[rr][kk], w.x, acc[rr][4 * g + 0]);
-          acc[rr][4 * g + 1] = fmaf(av[rr][kk], w.y, acc[rr][4 * g + 1]);
-          acc[rr][4 * g + 2] = fmaf(av[rr][kk], w.z, acc[rr][4 * g + 2]);
-          acc[rr][4 * g + 3] = fmaf(av[rr][kk], w.w, acc[rr][4 * g + 3]);
+          const float2 a2 = make_float2(av[rr][kk], av[rr][kk]);  // packed FFMA2: two fp32 FMAs per instruction
+          acc[rr][2 * g + 0] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[rr][2 * g + 0]);
+          acc[rr][2 * g + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[rr][2 * g + 1]);
         }
       }
     }
@@ -91,7 +90,7 @@ __device__ __forceinline__ void mma_tile(const Grp& G, float (&acc)[TM / 16][U /
 
 // same with scalar A loads (no alignment or multiple-of-4 demands)
 template <int U, int TM>
-__device__ __forceinline__ void mma_tile_sa(const Grp& G, float (&acc)[TM / 16][U / 16], const float* __restrict__ sA, int lda,
+__device__ __forceinline__ void mma_tile_sa(const Grp& G, float2 (&acc)[TM / 16][U / 32], const float* __restrict__ sA, int lda,
                                             const float* __restrict__ sW, int kc) {
   constexpr int RM = TM / 16;
   const int ty = G.tid >> 4, tx = G.tid & 15;
@@ -106,10 +105,9 @@ __device__ __forceinline__ void mma_tile_sa(const Grp& G, float (&acc)[TM / 16][
       const float4 w = *reinterpret_cast<const float4*>(sW + k * U + g * 64 + 4 * tx);
 #pragma unroll
       for (int rr = 0; rr < RM; ++rr) {
-        acc[rr][4 * g + 0] = fmaf(av[rr], w.x, acc[rr][4 * g + 0]);
-        acc[rr][4 * g + 1] = fmaf(av[rr], w.y, acc[rr][4 * g + 1]);
-        acc[rr][4 * g + 2] = fmaf(av[rr], w.z, acc[rr][4 * g + 2]);
-        acc[rr][4 * g + 3] = fmaf(av[rr], w.w, acc[rr][4 * g + 3]);
+        const float2 a2 = make_float2(av[rr], av[rr]);
+        acc[rr][2 * g + 0] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[rr][2 * g + 0]);
+        acc[rr][2 * g + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[rr][2 * g + 1]);
       }
     }
   }
@@ -171,7 +169,7 @@ __device__ __forceinline__ void load_x_chunk(const Grp& G, float* __restrict__ s
 
 // acc = X[rows] * W1, X streamed in K-chunks through sX; W1 from smem (RES) or staged through sW (ends synchronised)
 template <int U, int TM, bool RES>
-__device__ __forceinline__ void layer1(const Grp& G, float (&acc)[TM / 16][U / 16], const XSrc& xs, int K, const float* __restrict__ W1,
+__device__ __forceinline__ void layer1(const Grp& G, float2 (&acc)[TM / 16][U / 32], const XSrc& xs, int K, const float* __restrict__ W1,
                                        long long row0, int nrows, float* sX, float* sW) {
   zero_acc<U, TM>(acc);
   for (int k0 = 0; k0 < K; k0 += KC) {
@@ -186,7 +184,7 @@ __device__ __forceinline__ void layer1(const Grp& G, float (&acc)[TM / 16][U / 1
 
 // acc = sA[TM][U] * W (U,U); W from smem (RES, no barrier) or streamed in KC-row chunks (ends synchronised)
 template <int U, int TM, bool RES>
-__device__ __forceinline__ void layer_h(const Grp& G, float (&acc)[TM / 16][U / 16], const float* __restrict__ sA, const float* __restrict__ W,
+__device__ __forceinline__ void layer_h(const Grp& G, float2 (&acc)[TM / 16][U / 32], const float* __restrict__ sA, const float* __restrict__ W,
                                         float* sW) {
   constexpr int HP = U + 4;
   zero_acc<U, TM>(acc);
@@ -204,7 +202,7 @@ __device__ __forceinline__ void layer_h(const Grp& G, float (&acc)[TM / 16][U / 
 
 // acc = sA[TM][U] * W^T; WT = resident transposed copy (RES) else W streamed transposed (ends synchronised)
 template <int U, int TM, bool RES>
-__device__ __forceinline__ void layer_hT(const Grp& G, float (&acc)[TM / 16][U / 16], const float* __restrict__ sA, const float* __restrict__ W,
+__device__ __forceinline__ void layer_hT(const Grp& G, float2 (&acc)[TM / 16][U / 32], const float* __restrict__ sA, const float* __restrict__ W,
                                          const float* __restrict__ WT, float* sW) {
   constexpr int HP = U + 4;
   zero_acc<U, TM>(acc);
@@ -223,7 +221,7 @@ __device__ __forceinline__ void layer_hT(const Grp& G, float (&acc)[TM / 16][U /
 
 // sH[r][c] = relu(acc + bias[c])   (caller synchronises)
 template <int U, int TM>
-__device__ __forceinline__ void store_bias_relu(const Grp& G, const float (&acc)[TM / 16][U / 16], const float* __restrict__ bias, float* sH) {
+__device__ __forceinline__ void store_bias_relu(const Grp& G, const float2 (&acc)[TM / 16][U / 32], const float* __restrict__ bias, float* sH) {
   constexpr int HP = U + 4, RM = TM / 16;
   const int ty = G.tid >> 4, tx = G.tid & 15;
 #pragma unroll
@@ -233,10 +231,10 @@ __device__ __forceinline__ void store_bias_relu(const Grp& G, const float (&acc)
 #pragma unroll
     for (int rr = 0; rr < RM; ++rr) {
       float4 v;
-      v.x = fmaxf(acc[rr][4 * g + 0] + b.x, 0.f);
-      v.y = fmaxf(acc[rr][4 * g + 1] + b.y, 0.f);
-      v.z = fmaxf(acc[rr][4 * g + 2] + b.z, 0.f);
-      v.w = fmaxf(acc[rr][4 * g + 3] + b.w, 0.f);
+      v.x = fmaxf(acc[rr][2 * g + 0].x + b.x, 0.f);
+      v.y = fmaxf(acc[rr][2 * g + 0].y + b.y, 0.f);
+      v.z = fmaxf(acc[rr][2 * g + 1].x + b.z, 0.f);
+      v.w = fmaxf(acc[rr][2 * g + 1].y + b.w, 0.f);
       *reinterpret_cast<float4*>(sH + (RM * ty + rr) * HP + c) = v;
     }
   }
@@ -244,7 +242,7 @@ __device__ __forceinline__ void store_bias_relu(const Grp& G, const float (&acc)
 
 // sH[r][c] = (sH[r][c] > 0) ? acc : 0     in place: dz = dh * relu'(h)   (caller synchronises)
 template <int U, int TM>
-__device__ __forceinline__ void store_masked(const Grp& G, const float (&acc)[TM / 16][U / 16], float* sH) {
+__device__ __forceinline__ void store_masked(const Grp& G, const float2 (&acc)[TM / 16][U / 32], float* sH) {
   constexpr int HP = U + 4, RM = TM / 16;
   const int ty = G.tid >> 4, tx = G.tid & 15;
 #pragma unroll
@@ -253,10 +251,10 @@ __device__ __forceinline__ void store_masked(const Grp& G, const float (&acc)[TM
 #pragma unroll
     for (int rr = 0; rr < RM; ++rr) {
       float4 h = *reinterpret_cast<const float4*>(sH + (RM * ty + rr) * HP + c);
-      h.x = h.x > 0.f ? acc[rr][4 * g + 0] : 0.f;
-      h.y = h.y > 0.f ? acc[rr][4 * g + 1] : 0.f;
-      h.z = h.z > 0.f ? acc[rr][4 * g + 2] : 0.f;
-      h.w = h.w > 0.f ? acc[rr][4 * g + 3] : 0.f;
+      h.x = h.x > 0.f ? acc[rr][2 * g + 0].x : 0.f;
+      h.y = h.y > 0.f ? acc[rr][2 * g + 0].y : 0.f;
+      h.z = h.z > 0.f ? acc[rr][2 * g + 1].x : 0.f;
+      h.w = h.w > 0.f ? acc[rr][2 * g + 1].y : 0.f;
       *reinterpret_cast<float4*>(sH + (RM * ty + rr) * HP + c) = h;
     }
   }
@@ -266,7 +264,7 @@ __device__ __forceinline__ void store_masked(const Grp& G, const float (&acc)[TM
 template <int U, int TM, bool RES>
 __device__ __forceinline__ void forward_hidden(const Grp& G, const XSrc& xs, const MlpW& w, long long row0, int nrows, float* sX,
                                                float* sW, float* sH1, float* sH2) {
-  float acc[TM / 16][U / 16];
+  float2 acc[TM / 16][U / 32];
   layer1<U, TM, RES>(G, acc, xs, w.in, w.W1, row0, nrows, sX, sW);
   store_bias_relu<U, TM>(G, acc, w.b1, sH1);
   G.sync();
@@ -289,33 +287,44 @@ __device__ __forceinline__ void critic_head(const Grp& G, const float* __restric
 }
 
 // general head: sL[r][a] = h2[r,:] . W3[:,a] + b3[a], a < out.  8 threads per row, each sums U/8 hidden
-// units for all outputs, then a 3-step shuffle reduction (ends synchronised)
-template <int U, int TM>
-__device__ __forceinline__ void actor_head(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* sL) {
+// units for all outputs, then a 3-step shuffle reduction (ends synchronised).  KK = compile-time out width.
+template <int U, int TM, int KK>
+__device__ __forceinline__ void actor_head_k(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* sL) {
   constexpr int HP = U + 4;
-  const int K = w.out;
   for (int r = G.tid >> 3; r < TM; r += NT / 8) {  // one pass for TM <= 32
     const int part = G.tid & 7;
-    float s[MAXK];
+    float s[KK];
 #pragma unroll
-    for (int a = 0; a < MAXK; ++a) s[a] = 0.f;
+    for (int a = 0; a < KK; ++a) s[a] = 0.f;
     for (int u = part; u < U; u += 8) {
       const float h = sH2[r * HP + u];
-      const float* w3 = w.W3 + u * K;
+      const float* w3 = w.W3 + u * KK;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
-        if (a < K) s[a] = fmaf(h, w3[a], s[a]);
+      for (int a = 0; a < KK; ++a) s[a] = fmaf(h, w3[a], s[a]);
     }
 #pragma unroll
-    for (int a = 0; a < MAXK; ++a) {
-      if (a < K) {
-        float v = s[a];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if (part == 0) sL[r * KPAD + a] = v + w.b3[a];
-      }
+    for (int a = 0; a < KK; ++a) {
+      float v = s[a];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      if (part == 0) sL[r * KPAD + a] = v + w.b3[a];
     }
+  }
+  G.sync();
+}
+
+template <int U, int TM>
+__device__ __forceinline__ void actor_head(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* sL) {
+  if (w.out == 5) return actor_head_k<U, TM, 5>(G, sH2, w, sL);   // Discrete(5): every MPE movement head
+  if (w.out == 9) return actor_head_k<U, TM, 9>(G, sH2, w, sL);   // MultiDiscrete([5, 4]): simple_world_comm leader
+  constexpr int HP = U + 4;
+  const int K = w.out;
+  for (int idx = G.tid; idx < TM * K; idx += NT) {
+    const int r = idx / K, a = idx - r * K;
+    float s = 0.f;
+    for (int u = 0; u < U; ++u) s = fmaf(sH2[r * HP + u], w.W3[u * K + a], s);
+    sL[r * KPAD + a] = s + w.b3[a];
   }
   G.sync();
 }
@@ -453,7 +462,7 @@ __device__ __forceinline__ void backward_hidden(const Grp& G, const XSrc& xs, co
     grad_w_hidden<U, TM>(G, sH1, sH2, g->W2);
     grad_bias<U, TM>(G, sH2, g->b2);
   }
-  float acc[TM / 16][U / 16];
+  float2 acc[TM / 16][U / 32];
   G.sync();
   layer_hT<U, TM, RES>(G, acc, sH2, w.W2, w2T, sW);  // dh1 = dz2 * W2^T
   store_masked<U, TM>(G, acc, sH1);                   // dz1 = dh1 * relu'(h1)
@@ -529,7 +538,7 @@ __device__ __forceinline__ void build_wT_swz(const Grp& G, float* __restrict__ s
 
 // acc += sA[rows][0..U) * W^T where sWT is the swizzled transposed copy built by build_wT_swz
 template <int U, int TM>
-__device__ __forceinline__ void mma_tile_swz(const Grp& G, float (&acc)[TM / 16][U / 16], const float* __restrict__ sA, int lda,
+__device__ __forceinline__ void mma_tile_swz(const Grp& G, float2 (&acc)[TM / 16][U / 32], const float* __restrict__ sA, int lda,
                                              const float* __restrict__ sWT) {
   constexpr int RM = TM / 16, GM = U / 4 - 1;
   const int ty = G.tid >> 4, tx = G.tid & 15;
@@ -549,10 +558,9 @@ __device__ __forceinline__ void mma_tile_swz(const Grp& G, float (&acc)[TM / 16]
         const float4 w = *reinterpret_cast<const float4*>(sWT + (k + kk) * U + ((((g * 16 + tx) ^ ((k + kk) & GM))) << 2));
 #pragma unroll
         for (int rr = 0; rr < RM; ++rr) {
-          acc[rr][4 * g + 0] = fmaf(av[rr][kk], w.x, acc[rr][4 * g + 0]);
-          acc[rr][4 * g + 1] = fmaf(av[rr][kk], w.y, acc[rr][4 * g + 1]);
-          acc[rr][4 * g + 2] = fmaf(av[rr][kk], w.z, acc[rr][4 * g + 2]);
-          acc[rr][4 * g + 3] = fmaf(av[rr][kk], w.w, acc[rr][4 * g + 3]);
+          const float2 a2 = make_float2(av[rr][kk], av[rr][kk]);  // packed FFMA2: two fp32 FMAs per instruction
+          acc[rr][2 * g + 0] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[rr][2 * g + 0]);
+          acc[rr][2 * g + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[rr][2 * g + 1]);
         }
       }
     }
@@ -564,7 +572,7 @@ __device__ __forceinline__ void mma_tile_swz(const Grp& G, float (&acc)[TM / 16]
 template <int U, int TM>
 __device__ __forceinline__ void forward_hidden_res(const Grp& G, const float* __restrict__ sXf, int ldx, const MlpW& w,
                                                    float* sH1, float* sH2) {
-  float acc[TM / 16][U / 16];
+  float2 acc[TM / 16][U / 32];
   zero_acc<U, TM>(acc);
   mma_tile_sa<U, TM>(G, acc, sXf, ldx, w.W1, w.in);
   store_bias_relu<U, TM>(G, acc, w.b1, sH1);
@@ -583,7 +591,7 @@ __device__ __forceinline__ void backward_hidden_res(const Grp& G, const float* _
     grad_w_hidden<U, TM>(G, sH1, sH2, g->W2);
     grad_bias<U, TM>(G, sH2, g->b2);
   }
-  float acc[TM / 16][U / 16];
+  float2 acc[TM / 16][U / 32];
   zero_acc<U, TM>(acc);
   mma_tile_swz<U, TM>(G, acc, sH2, U + 4, sWT);  // dh1 = dz2 * W2^T
   G.sync();                                       // every reader of h1 (grad_w_hidden) is done

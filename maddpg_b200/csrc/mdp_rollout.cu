@@ -34,6 +34,12 @@ struct RolloutArgs {
 
 // NG groups of NT = 256 threads; group g runs the actor MLPs of agents g, g+NG, ... concurrently with the
 // other groups (named barriers 1..NG); the env phases use all NG*256 threads.
+//
+// Replay rows are ASSEMBLED IN PLACE: the CTA owns two [32][row_stride] row buffers (ping-pong).  In the buffer
+// of step s the actors read obs_t from columns [0, sum D), the Gumbel-softmax writes act_t into [sum D, C), the
+// env phase writes next_obs / rew / done into their columns (and next_obs also into the OTHER buffer's obs_t
+// columns); then ONE thread streams the 32 finished rows to the ring with a TMA bulk store
+// (cp.async.bulk.global.shared::cta) that overlaps with the next step's compute.
 template <int U, bool RESIDENT>
 __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
                                                           mdp_ring_layout L, RolloutArgs R, int NG) {
@@ -43,17 +49,16 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
   const int warp = tid >> 5, lane = tid & 31, nwarps = NTB >> 5;
   const int grp = tid / NT;
   const Grp G{tid - grp * NT, grp + 1};
-  const int OS = P.obs_stride, A = P.A;
+  const int OS = P.obs_stride, A = P.A, RS = L.row_stride;
   const int e0 = blockIdx.x * REB;
   const int nE = min(REB, R.E - e0);
 
   // ---- shared memory carve-up ------------------------------------------------------------------
   SmemCarve sm(smem_raw);
+  float* sRow = sm.take(2 * TM * RS);  // two row buffers, 16-byte aligned rows
   float* sH1 = sm.take(NG * TM * HP) + grp * TM * HP;
   float* sH2 = sm.take(NG * TM * HP) + grp * TM * HP;
   float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
-  float* sObs = sm.take(TM * OS);
-  float* sAct = sm.take(TM * (P.act_stride | 1));
   float* sRet = sm.take(A * EBP);
   int* sOff = reinterpret_cast<int*>(sm.take(MDP_MAX_AGENTS + 1));
   ObsCol* sCols = reinterpret_cast<ObsCol*>(sm.take(2 * OS));
@@ -61,7 +66,8 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
   // RESIDENT: every agent's actor net ; else one [KC][U] staging chunk per group
   float* sWts = RESIDENT ? sm.p : sm.p + grp * KC * U;
   EnvTile<float, REB> T;
-  T.carve(sEnv, P, sAct);
+  T.carve(sEnv, P, sRow + L.obs_sum);
+  T.ASP = RS;
 
   unsigned long long counter = R.counter, episode = R.episode;
   long long cursor = R.cursor;
@@ -73,8 +79,7 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
 
   // ---- prologue: state tile, observation tile, column table, actor weights -------------------------
   env_load_state<float, REB>(P, T, R.state, R.E, e0, nE);
-  for (int ee = warp; ee < TM; ee += nwarps)
-    for (int c = lane; c < OS; c += 32) sObs[ee * OS + c] = (ee < nE) ? R.obs[(size_t)(e0 + ee) * OS + c] : 0.f;
+  for (int i = tid; i < 2 * TM * RS; i += NTB) sRow[i] = 0.f;  // padding / done columns stay zero for good
   for (int c = tid; c < OS; c += NTB) sCols[c] = cols[c];
   for (int idx = tid; idx < A * EBP; idx += NTB) sRet[idx] = 0.f;
   if (tid == 0) {
@@ -86,6 +91,8 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
     sOff[A] = o;
   }
   __syncthreads();
+  for (int ee = warp; ee < nE; ee += nwarps)
+    for (int c = lane; c < L.obs_sum; c += 32) sRow[ee * RS + c] = R.obs[(size_t)(e0 + ee) * OS + c];
   if (RESIDENT) {
     for (int i = 0; i < A; ++i) {
       const float4* src = reinterpret_cast<const float4*>(C.agents[i].net[MDP_NET_P].W1);
@@ -93,34 +100,29 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
       const int n4 = (sOff[i + 1] - sOff[i]) >> 2;
       for (int q = tid; q < n4; q += NTB) dst[q] = src[q];
     }
-    __syncthreads();
   }
+  __syncthreads();
 
   // ---- the episode -----------------------------------------------------------------------------------
   for (int s = 0; s < R.steps; ++s) {
-    // (1) actions: a_i = gumbel_softmax(mlp_i(obs_i)) for every agent
+    float* buf = sRow + (s & 1) * TM * RS;        // rows of this step
+    float* nxt = sRow + ((s & 1) ^ 1) * TM * RS;  // rows of the next step (receive obs_{t+1} as their obs_t)
+    T.sA = buf + L.obs_sum;
+    // (1) actions: a_i = gumbel_softmax(mlp_i(obs_i)) for every agent, written into the row's act columns
     for (int i = grp; i < A; i += NG) {
       const AgentDev& ag = C.agents[i];
       const int D = ag.obs_dim, K = ag.act_dim;
       MlpW w = ag.net[MDP_NET_P];
-      if (RESIDENT) {
-        const float* b = sWts + sOff[i];
-        w.W1 = b; b += D * U;
-        w.b1 = b; b += U;
-        w.W2 = b; b += U * U;
-        w.b2 = b; b += U;
-        w.W3 = b; b += U * K;
-        w.b3 = b;
-      }
-      float acc[TM / 16][U / 16];
+      if (RESIDENT) w = net_at<U>(sWts + sOff[i], D, K);
+      float2 acc[TM / 16][U / 32];
       zero_acc<U, TM>(acc);
       if (RESIDENT) {
-        mma_tile_sa<U, TM>(G, acc, sObs + ag.obs_off, OS, w.W1, D);
+        mma_tile_sa<U, TM>(G, acc, buf + ag.obs_off, RS, w.W1, D);
       } else {
         for (int k0 = 0; k0 < D; k0 += KC) {
           load_w_rows<U>(G, sWts, w.W1, k0, D);
           G.sync();
-          mma_tile_sa<U, TM>(G, acc, sObs + ag.obs_off + k0, OS, sWts, min(KC, D - k0));
+          mma_tile_sa<U, TM>(G, acc, buf + ag.obs_off + k0, RS, sWts, min(KC, D - k0));
           G.sync();
         }
       }
@@ -135,41 +137,50 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
       store_bias_relu<U, TM>(G, acc, w.b2, sH2);
       G.sync();
       actor_head<U, TM>(G, sH2, w, sL);
-      gumbel_softmax_tile<TM>(G, sL, sAct + ag.act_off, T.ASP, nE, K, ag.n_heads, ag.head_dim, nullptr, 0, 0, (long long)e0, R.seed,
-                          counter + (unsigned long long)s + 1ull, (uint32_t)i);
+      gumbel_softmax_tile<TM>(G, sL, buf + L.obs_sum + ag.act_off, RS, nE, K, ag.n_heads, ag.head_dim, nullptr, 0, 0, (long long)e0,
+                              R.seed, counter + (unsigned long long)s + 1ull, (uint32_t)i);
     }
-    __syncthreads();  // all groups' actions are in sAct
-    // (2) replay row, first half: obs_t and act_t
-    for (int ee = warp; ee < nE; ee += nwarps) {
-      float* row = R.ring + ((cursor + (long long)s * R.E + e0 + ee) % R.capacity) * (long long)L.row_stride;
-      for (int c = lane; c < L.obs_sum; c += 32) row[c] = sObs[ee * OS + c];
-      for (int c = lane; c < L.act_sum; c += 32) row[L.obs_sum + c] = sAct[ee * T.ASP + c];
-    }
+    // the bulk store of step s-1 must have finished READING `nxt` before phase (4) overwrites its obs columns
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();  // all groups' actions are in the row buffer
     // (3) World.step and rewards (both CTA-collective, synchronised on return)
     env_physics<float, REB>(P, T, nE);
     env_flags_rewards<float, REB, true>(P, T, nE);
-    // (4) next observations into the tile
-    for (int c = lane; c < OS; c += 32) {
+    // (4) next observations: into this row's next_obs columns and into the next row buffer's obs columns
+    for (int c = lane; c < L.obs_sum; c += 32) {
       const ObsCol d = sCols[c];
-      for (int ee = warp; ee < nE; ee += nwarps) sObs[ee * OS + c] = env_obs_value<float, REB>(T, d, ee);
-    }
-    __syncthreads();
-    // (5) replay row, second half: next_obs, rew, done
-    for (int ee = warp; ee < nE; ee += nwarps) {
-      float* row = R.ring + ((cursor + (long long)s * R.E + e0 + ee) % R.capacity) * (long long)L.row_stride;
-      for (int c = lane; c < L.obs_sum; c += 32) row[L.nx_off + c] = sObs[ee * OS + c];
-      if (lane < A) {
-        const float r = env_reward_out<float, REB>(P, T, ee, lane);
-        row[L.rw_off + lane] = r;
-        row[L.dn_off + lane] = 0.f;
-        sRet[lane * EBP + ee] += r;
+      for (int ee = warp; ee < nE; ee += nwarps) {
+        const float v = env_obs_value<float, REB>(T, d, ee);
+        buf[ee * RS + L.nx_off + c] = v;
+        nxt[ee * RS + c] = v;
       }
     }
-    // the next step's actor pass only reads sObs (complete) and rewrites sH1/sH2/sL/sAct, none of which
-    // phase (5) touches; sR is rewritten only after the barriers inside env_physics
+    for (int idx = tid; idx < nE * A; idx += NTB) {
+      const int ee = idx / A, ii = idx - ee * A;
+      const float r = env_reward_out<float, REB>(P, T, ee, ii);
+      buf[ee * RS + L.rw_off + ii] = r;
+      sRet[ii * EBP + ee] += r;
+    }
+    // (5) hand the finished rows to the TMA engine: generic-proxy writes -> async proxy, then one bulk store
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      const long long r0 = (cursor + (long long)s * R.E + e0) % R.capacity;
+      const long long first = min((long long)nE, R.capacity - r0);  // rows before the ring wraps
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(R.ring + r0 * RS), "r"(smem_u32(buf)),
+                   "r"((uint32_t)(first * RS * 4))
+                   : "memory");
+      if (first < nE)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(R.ring), "r"(smem_u32(buf + first * RS)),
+                     "r"((uint32_t)((nE - first) * RS * 4))
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
   }
 
   // ---- epilogue: optional reset_world, then hand state and observations back ----------------------------
+  float* fin = sRow + (R.steps & 1) * TM * RS;  // obs_{T} lives in the obs columns of the next buffer
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncthreads();
   if (R.reset_after) {
     for (int idx = tid; idx < P.scomp * REB; idx += NTB) {
@@ -178,15 +189,15 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
     }
     __syncthreads();
     env_flags_rewards<float, REB, false>(P, T, nE);
-    for (int c = lane; c < OS; c += 32) {
+    for (int c = lane; c < L.obs_sum; c += 32) {
       const ObsCol d = sCols[c];
-      for (int ee = warp; ee < nE; ee += nwarps) sObs[ee * OS + c] = env_obs_value<float, REB>(T, d, ee);
+      for (int ee = warp; ee < nE; ee += nwarps) fin[ee * RS + c] = env_obs_value<float, REB>(T, d, ee);
     }
     __syncthreads();
   }
   env_store_state<float, REB>(P, T, R.state, R.E, e0, nE, R.reset_after != 0);
   for (int ee = warp; ee < nE; ee += nwarps)
-    for (int c = lane; c < OS; c += 32) R.obs[(size_t)(e0 + ee) * OS + c] = sObs[ee * OS + c];
+    for (int c = lane; c < OS; c += 32) R.obs[(size_t)(e0 + ee) * OS + c] = (c < L.obs_sum) ? fin[ee * RS + c] : 0.f;
   if (R.ep_return)
     for (int idx = tid; idx < nE * A; idx += NTB) {
       const int ee = idx / A, ii = idx - ee * A;
@@ -232,8 +243,8 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   size_t smem = 0;
   for (int ng = P.A < 4 ? P.A : 4; ng >= 1 && NG == 0; --ng) {
     if (ng * NT < REB * P.A) break;  // the physics phase needs one thread per (env, agent)
-    const size_t base = 2 * r4((size_t)ng * TM * HP) + r4((size_t)ng * TM * KPAD) + r4((size_t)TM * P.obs_stride) +
-                        r4((size_t)TM * (P.act_stride | 1)) + r4((size_t)P.A * (REB + 1)) + r4(MDP_MAX_AGENTS + 1) +
+    const size_t base = 2 * r4((size_t)ng * TM * HP) + r4((size_t)ng * TM * KPAD) + r4(2 * (size_t)TM * lay.row_stride) +
+                        r4((size_t)P.A * (REB + 1)) + r4(MDP_MAX_AGENTS + 1) +
                         r4(2 * (size_t)P.obs_stride) + r4(EnvTile<float, REB>::bytes(P.scomp, P.A, P.act_stride, false) / 4);
     const size_t smem_res = (base + wts + 16) * 4, smem_str = (base + (size_t)ng * KC * U + 16) * 4;
     if (smem_res <= limit) { NG = ng; resident = true; smem = smem_res; }
