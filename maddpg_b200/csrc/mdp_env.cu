@@ -47,12 +47,8 @@ __global__ void __launch_bounds__(1024) k_env_step(EnvParams P, int E, real* __r
       done_out[(size_t)(e0 + ee) * P.A + ii] = 0;  // MPE has no done callback: always False
     }
   }
-  // observations: one warp per env row, lanes sweep the joint columns (coalesced 128-byte stores)
-  const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
-  for (int c = lane; c < P.obs_stride; c += 32) {
-    const ObsCol d = cols[c];
-    for (int ee = warp; ee < nE; ee += nwarps) obs_out[(size_t)(e0 + ee) * P.obs_stride + c] = env_obs_value<real, EB>(T, d, ee);
-  }
+  // observations: flat (row, column-quad) sweep, one float4 store per thread iteration
+  env_write_obs<real, EB>(P, T, cols, obs_out + (size_t)e0 * P.obs_stride, P.obs_stride, nE);
 }
 
 // scenario.reset_world: agents U(-1,1), velocities / comm 0, landmarks U(lo,hi)
@@ -177,7 +173,15 @@ static int build_env(mdp_env* env) {
   D.obs_stride = round_up(D.obs_sum, 4);
   D.act_stride = round_up(D.act_sum, 4);
   while ((int)cols.size() < D.obs_stride) push_col(cols, OK_PAD, 0, 0, 0, 0, 0);
+  for (auto& c : cols) {  // plain columns are evaluated as S[a] - S[b]; row `scomp` of the smem tile is all zeros
+    if (c.kind == OK_DIRECT) c.b = (uint8_t)P.scomp;
+    if (c.kind == OK_ZERO || c.kind == OK_PAD) c.a = c.b = (uint8_t)P.scomp;
+    if (c.kind > OK_ZERO) P.has_mask = 1;
+  }
+  if (P.scomp + 1 > 255) return fail(MDP_ENOTSUP, "scenario has %d state components (max 254)", P.scomp);
   P.obs_stride = D.obs_stride; P.act_stride = D.act_stride; P.obs_sum = D.obs_sum; P.act_sum = D.act_sum;
+  P.os4_magic = (uint32_t)((0x100000000ull + (uint64_t)(D.obs_stride / 4) - 1) / (uint64_t)(D.obs_stride / 4));
+  P.as4_magic = (uint32_t)((0x100000000ull + (uint64_t)(D.act_stride / 4) - 1) / (uint64_t)(D.act_stride / 4));
   D.n_agents = A; D.n_landmarks = L; D.comm_dim = P.cdim; D.collaborative = P.collaborative;
   D.state_comps = P.scomp;
   D.state_elem_size = env->cfg.state_f64 ? 8 : 4;

@@ -45,6 +45,9 @@ struct EnvParams {
   double max_speed[MDP_MAX_AGENTS];  // <= 0: no clamp
   uint64_t collide_mask;             // bit per entity
   uint32_t silent_mask;              // bit per agent
+  int has_mask;                      // scenario has visibility-masked / flag columns (simple_world_comm)
+  uint32_t as4_magic;                // ceil(2^32 / (act_stride/4)): row = (i * magic) >> 32 for i < 2^15
+  uint32_t os4_magic;                // same for obs_stride/4
   double dt, damping, contact_force, contact_margin;
 };
 
@@ -94,13 +97,13 @@ struct EnvTile {
   int ASP;
 
   __host__ __device__ static size_t bytes(int scomp, int A, int act_stride, bool with_actions) {
-    size_t b = ((size_t)scomp + 2 * A) * EBP * sizeof(real) + (size_t)A * EBP * sizeof(int);
+    size_t b = ((size_t)scomp + 1 + 2 * A) * EBP * sizeof(real) + (size_t)A * EBP * sizeof(int);
     if (with_actions) b += (size_t)EB * (act_stride | 1) * sizeof(float);
     return (b + 15) & ~(size_t)15;
   }
   __device__ void carve(void* base, const EnvParams& P, float* actions_or_null) {
     sS = reinterpret_cast<real*>(base);
-    sR = sS + (size_t)P.scomp * EBP;
+    sR = sS + (size_t)(P.scomp + 1) * EBP;  // row P.scomp of sS is all zeros (the 'b' operand of plain columns)
     sT = sR + (size_t)P.A * EBP;
     sF = reinterpret_cast<int*>(sT + (size_t)P.A * EBP);
     ASP = P.act_stride | 1;
@@ -112,9 +115,9 @@ template <typename real, int EB>
 __device__ __forceinline__ void env_load_state(const EnvParams& P, EnvTile<real, EB>& T, const real* __restrict__ state,
                                                int E, int e0, int nE) {
   constexpr int EBP = EB + 1;
-  for (int idx = threadIdx.x; idx < P.scomp * EB; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < (P.scomp + 1) * EB; idx += blockDim.x) {
     const int comp = idx / EB, e = idx % EB;  // EB is a power of two: shifts
-    T.sS[comp * EBP + e] = (e < nE) ? state[(size_t)comp * E + e0 + e] : (real)0;
+    T.sS[comp * EBP + e] = (e < nE && comp < P.scomp) ? state[(size_t)comp * E + e0 + e] : (real)0;
   }
 }
 
@@ -133,10 +136,15 @@ __device__ __forceinline__ void env_store_state(const EnvParams& P, const EnvTil
 template <typename real, int EB>
 __device__ __forceinline__ void env_load_actions(const EnvParams& P, EnvTile<real, EB>& T, const float* __restrict__ act,
                                                  int e0, int nE) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int e = warp; e < nE; e += nwarps) {
-    const float* arow = act + (size_t)(e0 + e) * P.act_stride;
-    for (int c = lane; c < P.act_stride; c += 32) T.sA[e * T.ASP + c] = arow[c];
+  // the tile's action rows are contiguous in global memory: one flat float4 sweep, row = i / (act_stride/4)
+  const float4* src = reinterpret_cast<const float4*>(act + (size_t)e0 * P.act_stride);
+  const int as4 = P.act_stride >> 2;
+  for (int i = threadIdx.x; i < nE * as4; i += blockDim.x) {
+    const int e = P.as4_magic ? (int)__umulhi((unsigned)i, P.as4_magic) : i;
+    const int q = i - e * as4;
+    const float4 v = src[i];
+    float* d = T.sA + e * T.ASP + 4 * q;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
   }
 }
 
@@ -327,6 +335,7 @@ template <typename real, int EB>
 __device__ __forceinline__ float env_obs_value(const EnvTile<real, EB>& T, const ObsCol d, int ee) {
   constexpr int EBP = EB + 1;
   const real* sS = T.sS;
+  if (d.kind <= OK_ZERO) return (float)(sS[d.a * EBP + ee] - sS[d.b * EBP + ee]);  // plain columns: b may be the zero row
   real v = 0;
   switch (d.kind) {
     case OK_DIRECT: v = sS[d.a * EBP + ee]; break;
@@ -343,6 +352,31 @@ __device__ __forceinline__ float env_obs_value(const EnvTile<real, EB>& T, const
     default: break;
   }
   return (float)v;
+}
+
+// Joint observation rows of the tile -> dst (row pitch ld floats, 16-byte aligned rows): every thread
+// produces four consecutive columns of one row and stores them as one float4 (flat (row, quad) sweep).
+template <typename real, int EB>
+__device__ __forceinline__ void env_write_obs(const EnvParams& P, const EnvTile<real, EB>& T, const ObsCol* __restrict__ cols,
+                                              float* __restrict__ dst, long long ld, int nE) {
+  const int os4 = P.obs_stride >> 2;
+  for (int i = threadIdx.x; i < nE * os4; i += blockDim.x) {
+    const int ee = P.os4_magic ? (int)__umulhi((unsigned)i, P.os4_magic) : i;  // magic 0 <=> divisor 1
+    const int q = i - ee * os4;
+    const uint4 t0 = *reinterpret_cast<const uint4*>(cols + 4 * q);      // columns 4q, 4q+1
+    const uint4 t1 = *reinterpret_cast<const uint4*>(cols + 4 * q + 2);  // columns 4q+2, 4q+3
+    ObsCol d[4];
+    *reinterpret_cast<uint2*>(&d[0]) = make_uint2(t0.x, t0.y);
+    *reinterpret_cast<uint2*>(&d[1]) = make_uint2(t0.z, t0.w);
+    *reinterpret_cast<uint2*>(&d[2]) = make_uint2(t1.x, t1.y);
+    *reinterpret_cast<uint2*>(&d[3]) = make_uint2(t1.z, t1.w);
+    float4 v;
+    v.x = env_obs_value<real, EB>(T, d[0], ee);
+    v.y = env_obs_value<real, EB>(T, d[1], ee);
+    v.z = env_obs_value<real, EB>(T, d[2], ee);
+    v.w = env_obs_value<real, EB>(T, d[3], ee);
+    *reinterpret_cast<float4*>(dst + (long long)ee * ld + 4 * q) = v;
+  }
 }
 
 // reset_world draw for state component `comp` of env `e_global` (agents U(-1,1), landmarks U(lo,hi))
