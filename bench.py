@@ -253,6 +253,29 @@ def main():
     peak, peak_src = measured_peak_hbm()
     env_bytes = env.env_bytes_per_step * E
     achieved = env_bytes / (env_us * 1e-6) / 1e9
+    # the same per-step kernel where it is actually HBM-sized: 2^20 env instances (431 MB per step)
+    big = None
+    if rank == 0 and not args.no_graph:
+        EL = 1 << 20
+        envL = BatchedMultiAgentEnv(SCENARIO, num_envs=EL, num_agents=N_AGENTS, device=dev, squeeze=False)
+        envL.reset_device()
+        envL.act.copy_(torch.softmax(torch.randn_like(envL.act), -1))
+        for _ in range(4):
+            envL.step_device()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            envL.step_device()
+        b.record()
+        torch.cuda.synchronize()
+        usL = a.elapsed_time(b) * 1e3 / 10
+        bytesL = envL.env_bytes_per_step * EL
+        big = {"kernel": "k_env_step<float,32,true>", "envs": EL, "bound": "hbm", "achieved": bytesL / usL / 1e3, "peak": peak,
+               "unit": "GB/s", "frac": bytesL / usL / 1e3 / peak, "algorithmic_bytes_per_launch": bytesL, "avg_launch_us": usL,
+               "note": "issue-bound (about 170 warp instructions per env instance), see profiles/"}
+        del envL
+        torch.cuda.empty_cache()
 
     # ---- (3) critic updates: sequential agent updates on gathered batches ------------------------------------
     while core.ring.length[0] < BATCH * EP_LEN:  # the reference's warm-up gate (maddpg.py:148,162)
@@ -362,7 +385,7 @@ def main():
         for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
             os.environ[k] = "1"
         from oracle import train_loop as tl
-        cpu_steps, cpu_rounds = 10000, 30
+        cpu_steps, cpu_rounds = 40000, 150  # ~10-15 s of single-core work
         a_sps, e_sps, dt = tl.time_rollout(SCENARIO, N_AGENTS, cpu_steps)
         u_ps, udt = tl.time_updates(SCENARIO, N_AGENTS, cpu_rounds)
         cpu = {"value": a_sps, "unit": UNIT, "cores": 1, "kind": "port",
@@ -370,6 +393,18 @@ def main():
                          "(%.1f s)" % (cpu_steps, dt, cpu_rounds, A, udt),
                "critic_updates_per_sec": u_ps, "host_cores_available": os.cpu_count()}
 
+    # dominant kernel of the timed rollout region: the persistent episode kernel (one launch = 25 steps)
+    row_bytes = 4 * sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
+    ep_bytes = row_bytes * E * EP_LEN           # the replay rows are the only HBM traffic the algorithm needs
+    ep_us = roll_ms * 1e3 / max(1, n_eps)
+    actor_flops = 2 * sum(d * UNITS + UNITS * UNITS + UNITS * k for d, k in zip(env.obs_dims, env.act_dims)) * E * EP_LEN
+    ep_roof = {"kernel": "k_rollout_episode<64,true>" if roll.mode == "mega" else "per-step kernels", "bound": "hbm",
+               "achieved": ep_bytes / ep_us / 1e3, "peak": peak, "unit": "GB/s", "frac": ep_bytes / ep_us / 1e3 / peak,
+               "traffic": 5.3e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_raw.txt (dram read+write per launch; the "
+               "52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
+               "algorithmic_bytes_per_launch": ep_bytes, "avg_launch_us": ep_us,
+               "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the kernel is "
+                       "FP32-FMA-issue / latency bound", "fp32_fma_tflops": actor_flops / ep_us / 1e6}
     if rank == 0:
         flops_round = sum(int(core.layout.update_flops_critic[j]) + int(core.layout.update_flops_actor[j]) for j in range(A)) * BATCH
         line = {
@@ -385,9 +420,12 @@ def main():
                     "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
                     "api": "MADDPGAgentTrainer.action / BatchedMultiAgentEnv.step / .experience with host numpy arrays"},
             "gpu_launches": int(launches_roll),
-            "roofline": {"kernel": "k_env_step<float,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": env_bytes, "avg_launch_us": env_us},
+            "roofline": ep_roof,
+            "roofline_env_step_kernel": {"kernel": "k_env_step<float,32,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                                         "algorithmic_bytes_per_launch": env_bytes, "avg_launch_us": env_us,
+                                         "note": "per-step kernel of the reference-shaped API at the bench size (1.7 MB per "
+                                                 "launch: latency-bound, lives in L2)", "at_1M_envs": big},
             "critic_updates": {"value": upd_value, "unit": "critic updates/s", "rounds": R, "ms_per_round": upd_ms / R,
                                "gpu_launches": int(launches_upd), "flops_per_round": flops_round,
                                "achieved_tflops": flops_round * R / (upd_ms * 1e-3) / 1e12,
