@@ -355,11 +355,36 @@ def main():
     for _ in range(Ke):
         obs_n, ep = e2e_step(obs_n, ep)
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = E * A * Ke * world / e2e_s
+    percall_s = max_over_ranks(time.perf_counter() - t0)
+    percall_value = E * A * Ke * world / percall_s
     row_f = sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
-    h2d = 4 * E * (sum(env.obs_dims) + env.act_stride + row_f)   # action() obs, step() actions, experience() rows
-    d2h = 4 * E * (sum(env.act_dims) + env.obs_stride + env.n)   # actions, [obs | rew]
+    percall_h2d = 4 * E * (sum(env.obs_dims) + env.act_stride + row_f)   # action() obs, step() actions, experience() rows
+    percall_d2h = 4 * E * (sum(env.act_dims) + env.obs_stride + env.n)   # actions, [obs | rew]
+    # the same loop body as ONE C-ABI call per lockstep step with host buffers (mdp_host_step): H2D of the joint
+    # observations, actors + env step + replay insert, one packed D2H of (actions, next obs, rewards, done)
+    from maddpg_b200.rollout import HostRollout
+    host = HostRollout(env, core)
+    Kh = max(EP_LEN, (4 * args.e2e_steps) // EP_LEN * EP_LEN)
+
+    def host_loop(n_steps):
+        obs_n = host.reset()
+        ep = 0
+        for _ in range(n_steps):
+            action_n, obs_n, rew_n, done_n = host.step(obs_n)     # train.py:112-120
+            ep += 1
+            if ep >= EP_LEN:                                        # train.py:127-129
+                obs_n = host.reset()
+                ep = 0
+        return float(rew_n[0][0])                                   # the step's result is read on the host
+
+    host_loop(EP_LEN)
+    barrier()
+    t0 = time.perf_counter()
+    host_loop(Kh)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = E * A * Kh * world / e2e_s
+    h2d, d2h = host.h2d_bytes_per_step, host.d2h_bytes_per_step
     # e2e updates: trainer.update() per agent incl. python index draw, H2D of indices, D2H of the statistics
     for tr in trainers:
         tr.max_replay_buffer_len = BATCH * EP_LEN
@@ -417,8 +442,13 @@ def main():
                              "1.7 MB env state is L2-resident as in a real rollout"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": 1e3 * e2e_s / Ke,
-                    "api": "MADDPGAgentTrainer.action / BatchedMultiAgentEnv.step / .experience with host numpy arrays"},
+                    "steps": Kh, "ms_per_step": 1e3 * e2e_s / Kh,
+                    "api": "maddpg_b200.rollout.HostRollout.step -> C ABI mdp_host_step: train.py:112-120 (action, env.step, "
+                           "experience for all agents) per call with page-locked host numpy buffers; env.reset every 25 steps",
+                    "per_call_api": {"value": percall_value, "unit": UNIT, "steps": Ke, "ms_per_step": 1e3 * percall_s / Ke,
+                                     "h2d_bytes_per_step": percall_h2d, "d2h_bytes_per_step": percall_d2h,
+                                     "api": "MADDPGAgentTrainer.action / BatchedMultiAgentEnv.step / .experience, one call per "
+                                            "agent with pageable host numpy arrays (the reference's call granularity)"}},
             "gpu_launches": int(launches_roll),
             "roofline": ep_roof,
             "roofline_env_step_kernel": {"kernel": "k_env_step<float,32,true>", "bound": "hbm", "achieved": achieved, "peak": peak,

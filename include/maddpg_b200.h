@@ -156,6 +156,11 @@ void mdp_core_destroy(mdp_core* core);
 int mdp_core_bind(mdp_core* core, float* params, float* grads, float* adam_m, float* adam_v, int32_t* adam_t,
                   double* stats);
 
+/* Selects the MLP kernels: 0 = automatic, 1 = the tcgen05 tensor-core kernels wherever a shape is supported
+ * (3xTF32 split GEMMs with TMEM accumulators, csrc/mdp_train_tc.cu), -1 = the fp32 SIMT kernels only.  Both
+ * compute the same functions (mlp_model, train.py:39-46) to ~fp32 accuracy. */
+int mdp_core_set_tensor_cores(mdp_core* core, int32_t mode);
+
 /* MADDPGAgentTrainer.action (maddpg.py:151-152) / p_debug['target_act'] (:70-71) for agents
  * [agent_begin, agent_begin+agent_count): act_i = gumbel_softmax(mlp(obs_i)) in one grouped launch.
  * obs/act are joint arrays.  u (optional, joint act layout): injected U[0,1) draws; when null the
@@ -233,6 +238,26 @@ int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void* state, fl
                         int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
                         uint64_t seed, uint64_t counter, int32_t reset_after, uint64_t env_seed, uint64_t episode,
                         float* ep_return, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* host-buffer loop body                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+/* experiments/train.py:112-120 for E lockstep env instances with HOST input and output, one call:
+ *     action_n = [agent.action(obs) for agent, obs in zip(trainers, obs_n)]          (:112)
+ *     new_obs_n, rew_n, done_n, info_n = env.step(action_n)                           (:114)
+ *     agent.experience(obs_n[i], action_n[i], rew_n[i], new_obs_n[i], done_n[i], ..)  (:119-120, all agents)
+ * h_obs_in: HOST joint observations (E, obs_stride) -- copied to the caller's device staging d_obs_in;
+ * then grouped actor inference + Gumbel sampling (Philox stream (seed, counter)), the fused env step and the
+ * replay insert of the E joint rows at ring_cursor (ring may be NULL: no experience() calls); finally ONE
+ * device->host copy of the packed result block d_out -> h_out, laid out as mdp_host_step_layout reports:
+ *     offs4[0] next observations (E, obs_stride) f32 | offs4[1] rewards (E, n_agents) f32 |
+ *     offs4[2] sampled actions (E, act_stride) f32   | offs4[3] done (E, n_agents) u8      (256-byte aligned blocks)
+ * Both host buffers should be page-locked (the copies are then asynchronous DMA); the call only enqueues work
+ * on `stream` -- h_out is valid once the stream has been synchronised. */
+int mdp_host_step_layout(const mdp_env* env, int32_t E, int64_t* offs4, int64_t* total_bytes);
+int mdp_host_step(mdp_env* env, mdp_core* core, int32_t E, void* state, const float* h_obs_in, float* d_obs_in,
+                  void* d_out, void* h_out, float* ring, int64_t ring_capacity, int32_t ring_row_stride,
+                  int64_t ring_cursor, uint64_t seed, uint64_t counter, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* device control block: lets a captured CUDA graph advance its own counters                    */

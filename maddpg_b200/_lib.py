@@ -72,6 +72,7 @@ SYMBOLS = {
     "mdp_core_create": (C.c_int, [C.POINTER(CoreCfg), C.POINTER(_P)]),
     "mdp_core_get_layout": (C.c_int, [_P, C.POINTER(CoreLayout)]),
     "mdp_core_destroy": (None, [_P]),
+    "mdp_core_set_tensor_cores": (C.c_int, [_P, C.c_int32]),
     "mdp_core_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "mdp_actor_act": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P,
                                 C.c_uint64, C.c_uint64, _P, _P]),
@@ -89,6 +90,9 @@ SYMBOLS = {
     "mdp_clip_adam_polyak_all": (C.c_int, [_P, C.c_int32, C.c_float, C.c_int32, _P]),
     "mdp_rollout_episode": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                       C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
+    "mdp_host_step_layout": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mdp_host_step": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64,
+                                C.c_uint64, C.c_uint64, _P]),
     "mdp_env_set_ctl": (C.c_int, [_P, _P]),
     "mdp_core_set_ctl": (C.c_int, [_P, _P]),
     "mdp_ctl_advance": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, _P]),

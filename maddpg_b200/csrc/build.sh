@@ -8,9 +8,17 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall
        -Xptxas -v --expt-relaxed-constexpr -cudart static)
 objs=()
-for f in mdp_api mdp_env mdp_replay mdp_train mdp_optim mdp_rollout; do
-  "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$out/$f.o" 2> "$out/$f.ptxas.log" || { cat "$out/$f.ptxas.log"; exit 1; }
+pids=()
+srcs=(mdp_api mdp_host mdp_env mdp_replay mdp_train mdp_train_tc mdp_optim mdp_rollout)
+for f in "${srcs[@]}"; do  # one nvcc per translation unit, in parallel
+  "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$out/$f.o" 2> "$out/$f.ptxas.log" &
+  pids+=($!)
   objs+=("$out/$f.o")
 done
+fail=0
+for i in "${!pids[@]}"; do
+  if ! wait "${pids[$i]}"; then cat "$out/${srcs[$i]}.ptxas.log"; fail=1; fi
+done
+[ "$fail" = 0 ] || exit 1
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o "$out/libmaddpg_b200.so" "${objs[@]}"
 echo "built $out/libmaddpg_b200.so"

@@ -43,5 +43,10 @@ struct mdp_core {
   mdp::AgentDev* d_agents = nullptr;
   const unsigned long long* ctl = nullptr;
   std::vector<mdp::AgentDev> h_agents;
+  int tc_mode = 0;                 // tensor-core (tcgen05) kernels: 0 auto, 1 always where supported, -1 never
+  float* tc_scratch = nullptr;     // sampled-action tiles of the tensor-core TD-target kernel when they exceed shared memory
+  size_t tc_scratch_bytes = 0;
+  unsigned char* tc_arena = nullptr;  // pre-split UMMA weight images of every net (csrc/mdp_train_tc.cu)
+  const void* tc_imgs = nullptr;      // device table of tc::AgentImg inside the arena
 };
 

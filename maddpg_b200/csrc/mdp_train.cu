@@ -868,12 +868,20 @@ extern "C" int mdp_core_get_layout(const mdp_core* core, mdp_core_layout* out) {
 extern "C" void mdp_core_destroy(mdp_core* core) {
   if (!core) return;
   if (core->d_agents) cudaFree(core->d_agents);
+  if (core->tc_scratch) cudaFree(core->tc_scratch);
+  if (core->tc_arena) cudaFree(core->tc_arena);
   delete core;
 }
 
 extern "C" int mdp_core_set_ctl(mdp_core* c, const uint64_t* ctl) {
   MDP_REQUIRE(c, "mdp_core_set_ctl: null core");
   c->ctl = reinterpret_cast<const unsigned long long*>(ctl);
+  return MDP_OK;
+}
+
+extern "C" int mdp_core_set_tensor_cores(mdp_core* c, int32_t mode) {
+  MDP_REQUIRE(c && mode >= -1 && mode <= 1, "mdp_core_set_tensor_cores: mode must be -1, 0 or 1");
+  c->tc_mode = mode;
   return MDP_OK;
 }
 
@@ -977,6 +985,20 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   return r;
 }
 
+namespace mdp {
+int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,
+                        const float* batch, const long long* ridx, long long idx_stride, const float* u_target, int32_t u_stride,
+                        uint64_t seed, uint64_t counter, float* y_out, long long y_stride, float* target_act_out, cudaStream_t st);
+}
+
+// tensor-core path policy: forced on (1), forced off (-1), or automatic (0)
+static bool want_tc(const mdp_core* c, int B, int count) {
+  if (c->tc_mode < 0 || c->cfg.num_units != 64) return false;
+  if (c->tc_mode > 0) return true;
+  (void)B; (void)count;
+  return false;
+}
+
 static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
                             const int64_t* idx, long long idx_stride, const float* u_target, int32_t u_stride, uint64_t seed,
                             uint64_t counter, float* y_out, long long y_stride, float* target_act_out, void* stream) {
@@ -990,6 +1012,11 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
   const Plan p = make_plan(c, B);
   const ResPlan rp = make_res_plan(c, p, agent);
   const long long* ridx = (const long long*)idx;
+  if (want_tc(c, B, count)) {
+    rc = launch_td_target_tc(c, d, agent, count, lay, B, batch, ridx, idx_stride, u_target, u_stride, seed, counter, y_out, y_stride,
+                             target_act_out, st);
+    if (rc != MDP_ENOTSUP) return rc;
+  }
   return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
     constexpr bool RES = decltype(res_)::value;

@@ -9,6 +9,9 @@ captured once into a CUDA graph; the Philox counter, ring cursor, episode id and
 in a 4-word device control block that the graph itself advances (include/maddpg_b200.h), so every
 replay draws fresh noise and appends to the ring.
 """
+import ctypes as C
+
+import numpy as np
 import torch
 
 from . import _lib
@@ -162,6 +165,84 @@ class BatchedRollout(object):
     @property
     def agent_steps_per_step(self):
         return self.env.num_envs * self.env.n
+
+
+class HostRollout(object):
+    """experiments/train.py:110-133 for E lockstep env instances with HOST (numpy) buffers: one C-ABI call
+    per step (include/maddpg_b200.h: mdp_host_step) = one H2D copy of the joint observations, three kernels
+    (grouped actors + Gumbel sampling, fused env step, replay insert) and one packed D2H copy.
+
+        host = HostRollout(env, core)
+        obs_n = host.reset()                                   # env.reset()                       train.py:104
+        action_n, new_obs_n, rew_n, done_n = host.step(obs_n)  # action / env.step / experience    :112-120
+
+    The returned arrays are views into page-locked result buffers that alternate between two slots, so the
+    arrays of step t stay valid until step t+2 (train.py rebinds ``obs_n = new_obs_n`` every step)."""
+
+    def __init__(self, env, core, experience=True):
+        assert env.obs_dims == core.obs_dims and env.act_dims == core.act_dims
+        assert env.device.type == "cuda"
+        self.env, self.core, self.experience = env, core, bool(experience)
+        E = env.num_envs
+        offs = (C.c_int64 * 4)()
+        total = C.c_int64()
+        _lib.check(_lib.lib.mdp_host_step_layout(env._h, E, offs, C.byref(total)), "mdp_host_step_layout")
+        self.offs, self.total = [int(x) for x in offs], int(total.value)
+        self.h_out = [torch.zeros(self.total, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.h_in = torch.zeros((E, env.obs_stride), dtype=torch.float32).pin_memory()
+        self.d_in = torch.zeros((E, env.obs_stride), dtype=torch.float32, device=env.device)
+        self.d_out = torch.zeros(self.total, dtype=torch.uint8, device=env.device)
+        self._slot = 0
+        self._views = [self._make_views(h) for h in self.h_out]
+        self.h2d_bytes_per_step = 4 * E * env.obs_stride
+        self.d2h_bytes_per_step = self.total
+
+    def _make_views(self, h):
+        env, E, o = self.env, self.env.num_envs, self.offs
+        a = h.numpy()
+        obs = a[o[0]:o[0] + 4 * E * env.obs_stride].view(np.float32).reshape(E, env.obs_stride)
+        rew = a[o[1]:o[1] + 4 * E * env.n].view(np.float32).reshape(E, env.n)
+        act = a[o[2]:o[2] + 4 * E * env.act_stride].view(np.float32).reshape(E, env.act_stride)
+        done = a[o[3]:o[3] + E * env.n].view(np.bool_).reshape(E, env.n)
+        return dict(
+            joint_obs=obs,
+            obs=[obs[:, f:f + D] for f, D in zip(env.obs_off, env.obs_dims)],
+            rew=[rew[:, i] for i in range(env.n)],
+            act=[act[:, f:f + K] for f, K in zip(env.act_off, env.act_dims)],
+            done=[done[:, i] for i in range(env.n)])
+
+    def reset(self):
+        """``env.reset()`` (train.py:104,128) -> list of per-agent (E, D_i) host observations."""
+        env = self.env
+        env.reset_device()
+        v = self._views[self._slot]
+        t = torch.from_numpy(v["joint_obs"])
+        t.copy_(env.obs, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return v["obs"]
+
+    def step(self, obs_n):
+        env, core = self.env, self.core
+        cur = self._views[self._slot]
+        if obs_n is cur["obs"] or (len(obs_n) == env.n and all(a is b for a, b in zip(obs_n, cur["obs"]))):
+            h_in = cur["joint_obs"]  # the arrays this object handed out: already page-locked, no host copy
+        else:
+            h_in = self.h_in.numpy()
+            for i, o in enumerate(obs_n):
+                h_in[:, env.obs_off[i]:env.obs_off[i] + env.obs_dims[i]] = np.asarray(o, dtype=np.float32)
+        self._slot ^= 1
+        nxt = self._views[self._slot]
+        ring = core.ring if self.experience else None
+        cursor = ring.reserve_joint(env.num_envs) if ring is not None else 0
+        _lib.check(_lib.lib.mdp_host_step(env._h, core._h, env.num_envs, _lib.ptr(env.state),
+                                          C.c_void_p(h_in.ctypes.data), _lib.ptr(self.d_in), _lib.ptr(self.d_out),
+                                          C.c_void_p(self.h_out[self._slot].data_ptr()),
+                                          _lib.ptr(ring.ring) if ring is not None else None,
+                                          ring.capacity if ring is not None else 0,
+                                          ring.row_stride if ring is not None else 0, cursor, core.seed,
+                                          core.next_counter(), _lib.current_stream()), "mdp_host_step")
+        torch.cuda.current_stream().synchronize()
+        return nxt["act"], nxt["obs"], nxt["rew"], nxt["done"]
 
 
 class GraphedUpdateRound(object):

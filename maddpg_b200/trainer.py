@@ -160,6 +160,10 @@ class MADDPGCore(object):
         """Attach / detach (None) a device control block (include/maddpg_b200.h: mdp_core_set_ctl)."""
         _lib.check(_lib.lib.mdp_core_set_ctl(self._h, _lib.ptr(ctl)), "mdp_core_set_ctl")
 
+    def set_tensor_cores(self, mode):
+        """0 = automatic, 1 = tcgen05 kernels wherever supported, -1 = fp32 SIMT kernels only."""
+        _lib.check(_lib.lib.mdp_core_set_tensor_cores(self._h, int(mode)), "mdp_core_set_tensor_cores")
+
     def act(self, obs_joint, act_joint, agent_begin=0, agent_count=None, use_target=False, u=None, logits_out=None,
             counter=None):
         """Grouped actor inference + Gumbel-softmax on joint device arrays (see header).  ``counter``

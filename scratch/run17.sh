@@ -1,0 +1,3 @@
+SECONDS=0
+timeout 300 python -m pytest tests/test_tensor_core_gpu.py tests/test_host_step_gpu.py -x -q 2>&1 | tail -40
+echo "elapsed=${SECONDS}s"

@@ -1,0 +1,96 @@
+"""tcgen05 (tensor-core) kernels against the numpy oracle and against the fp32 SIMT kernels on identical inputs.
+The tensor path issues every GEMM as three kind::tf32 MMAs (hi/lo split), so it must hold the same 1e-4 bar
+on TD targets / Q values as the SIMT path (BASELINE.json north_star), and agree with it to ~1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import TRAINER_CASES, oracle_update_round, trainer_case
+from tests.test_trainer_gpu import _build, _close
+
+pytestmark = pytest.mark.gpu
+TC_CASES = [n for n, c in TRAINER_CASES.items() if c[2] == 64]
+
+
+def _ut(core, case, j, B):
+    ut = torch.zeros((B, core.act_stride), device="cuda")
+    ut[:, :core.act_sum] = torch.from_numpy(case["u_target"][j]).cuda()
+    return ut
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_td_target_tensor_cores_match_oracle_and_simt(name):
+    case = trainer_case(name, seed=2)
+    ref = oracle_update_round(trainer_case(name, seed=2))
+    trainers, core = _build(case)
+    B = case["B"]
+    for j in range(case["n"] if name != "simple_spread_6" else 2):
+        if j > 0:
+            break  # the oracle round steps agent 0 first; later agents see updated targets
+        idx = core.ring.index_tensor(case["idx"][j])
+        batch = core.ring.gather(idx)
+        ut = _ut(core, case, j, B)
+        core.set_tensor_cores(-1)
+        y_simt, ta_simt = core.td_target(j, batch, ut, want_target_act=True)
+        y_simt, ta_simt = y_simt.clone(), ta_simt.clone()
+        st_simt = core.stats.clone()
+        core.set_tensor_cores(1)
+        y_tc, ta_tc = core.td_target(j, batch, ut, want_target_act=True)
+        st_tc = core.stats.clone()
+        _close(y_tc.cpu().numpy(), ref[j]["y"], atol=2e-6, msg="td target vs oracle")
+        _close(y_tc.cpu().numpy(), y_simt.cpu().numpy(), rtol=2e-5, atol=2e-6, msg="td target vs SIMT")
+        _close(ta_tc.cpu().numpy(), ta_simt.cpu().numpy(), rtol=2e-5, atol=1e-6, msg="target actions vs SIMT")
+        _close(st_tc[8 * j:8 * j + 8].cpu().numpy(), st_simt[8 * j:8 * j + 8].cpu().numpy(), rtol=1e-5, atol=1e-6, msg="stats")
+        # fused gather: rows addressed through the index set straight from the ring
+        y_idx = core.td_target(j, core.ring.ring, ut, idx=idx)
+        assert torch.equal(y_idx, y_tc)
+
+
+@pytest.mark.parametrize("name", ["simple_spread", "simple_tag_ddpg_adv", "simple_spread_6"])
+def test_td_target_tensor_cores_many_tiles_philox(name):
+    """Several 128-row tiles with a ragged tail, in-kernel Philox noise (same stream as the SIMT kernel)."""
+    case = trainer_case(name, seed=3)
+    trainers, core = _build(case)
+    rows = case["rows"]
+    idx = torch.arange(rows, device="cuda", dtype=torch.int64).flip(0).contiguous()
+    for j in range(case["n"]):
+        c0 = core.counter
+        core.set_tensor_cores(-1)
+        y_simt = core.td_target(j, core.ring.ring, idx=idx).clone()
+        core.counter = c0  # same Philox counter for the second launch
+        core.set_tensor_cores(1)
+        y_tc = core.td_target(j, core.ring.ring, idx=idx)
+        _close(y_tc.cpu().numpy(), y_simt.cpu().numpy(), rtol=2e-5, atol=1e-5, msg="agent %d" % j)
+
+
+@pytest.mark.parametrize("name", ["simple_spread", "simple_tag"])
+def test_sequential_update_round_with_tensor_cores(name):
+    case = trainer_case(name, seed=4)
+    ref = oracle_update_round(trainer_case(name, seed=4))
+    trainers, core = _build(case)
+    core.set_tensor_cores(1)
+    for j, tr in enumerate(trainers):
+        tr.preupdate()
+        tr.inject_noise(u_target=case["u_target"][j], u_actor=case["u_actor"][j])
+        stats = tr.update(trainers, 100, index=case["idx"][j])
+        for k in range(6):
+            _close(stats[k], ref[j]["stats"][k], rtol=1e-4, atol=2e-6, msg="stat %d agent %d" % (k, j))
+
+
+def test_grouped_td_target_tensor_cores():
+    """grid.y = agent (mdp_update_all's launch shape): per-agent index sets, outputs equal the per-agent launches."""
+    case = trainer_case("simple_spread", seed=5)
+    trainers, core = _build(case)
+    B, n = case["B"], case["n"]
+    idx = torch.stack([core.ring.index_tensor(case["idx"][j]) for j in range(n)])
+    core.set_tensor_cores(1)
+    c0 = core.counter
+    ys = []
+    for j in range(n):
+        core.counter = c0
+        ys.append(core.td_target(j, core.ring.ring, idx=idx[j]).clone())
+    core.counter = c0
+    core.update_all(core.ring.ring, idx=idx)
+    y_all = core._y[("all", B)]
+    for j in range(n):
+        torch.testing.assert_close(y_all[j], ys[j], rtol=0, atol=0)
