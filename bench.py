@@ -271,9 +271,9 @@ def main():
         torch.cuda.synchronize()
         usL = a.elapsed_time(b) * 1e3 / 10
         bytesL = envL.env_bytes_per_step * EL
-        big = {"kernel": "k_env_step<float,32,true>", "envs": EL, "bound": "hbm", "achieved": bytesL / usL / 1e3, "peak": peak,
+        big = {"kernel": "k_env_step_spread<3>", "envs": EL, "bound": "hbm", "achieved": bytesL / usL / 1e3, "peak": peak,
                "unit": "GB/s", "frac": bytesL / usL / 1e3 / peak, "algorithmic_bytes_per_launch": bytesL, "avg_launch_us": usL,
-               "note": "issue-bound (about 170 warp instructions per env instance), see profiles/"}
+               "note": "register-resident one-thread-per-env kernel (simple_spread fast path); the table-driven kernel serves the other scenarios"}
         del envL
         torch.cuda.empty_cache()
 
@@ -451,7 +451,7 @@ def main():
                                             "agent with pageable host numpy arrays (the reference's call granularity)"}},
             "gpu_launches": int(launches_roll),
             "roofline": ep_roof,
-            "roofline_env_step_kernel": {"kernel": "k_env_step<float,32,true>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline_env_step_kernel": {"kernel": "k_env_step_spread<3>", "bound": "hbm", "achieved": achieved, "peak": peak,
                                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                                          "algorithmic_bytes_per_launch": env_bytes, "avg_launch_us": env_us,
                                          "note": "per-step kernel of the reference-shaped API at the bench size (1.7 MB per "

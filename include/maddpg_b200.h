@@ -89,6 +89,10 @@ int mdp_env_step(mdp_env* env, int32_t E, void* state, const float* act, float* 
                  uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
                  int32_t ring_row_stride, int64_t ring_cursor, void* stream);
 
+/* mdp_env_step picks a register-resident one-thread-per-env kernel for simple_spread with <= 6 agents and float32
+ * state; on = 1 forces the table-driven kernel that serves every scenario (tests compare the two). */
+int mdp_env_force_generic(mdp_env* env, int32_t on);
+
 /* ------------------------------------------------------------------------------------------ */
 /* replay ring (maddpg/trainer/replay_buffer.py)                                                */
 /* ------------------------------------------------------------------------------------------ */

@@ -63,6 +63,7 @@ SYMBOLS = {
     "mdp_env_create": (C.c_int, [C.POINTER(EnvCfg), C.POINTER(_P)]),
     "mdp_env_get_dims": (C.c_int, [_P, C.POINTER(EnvDims)]),
     "mdp_env_destroy": (None, [_P]),
+    "mdp_env_force_generic": (C.c_int, [_P, C.c_int32]),
     "mdp_env_reset": (C.c_int, [_P, C.c_int32, _P, _P, C.c_uint64, C.c_uint64, _P, _P]),
     "mdp_env_step": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, _P]),
     "mdp_ring_make_layout": (C.c_int, [C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(RingLayout)]),

@@ -51,6 +51,167 @@ __global__ void __launch_bounds__(1024) k_env_step(EnvParams P, int E, real* __r
   env_write_obs<real, EB>(P, T, cols, obs_out + (size_t)e0 * P.obs_stride, P.obs_stride, nE);
 }
 
+// --------------------------------------------------------------------------------------------
+// simple_spread fast path (float32 state, A <= 6): ONE THREAD PER ENV INSTANCE, everything in registers.
+// The generic kernel above is table-driven (runtime entity loops, per-column observation decode) and issue-bound
+// at ~170 warp instructions per env instance; with A known at compile time the whole step unrolls to ~15, which
+// leaves the kernel waiting on HBM only.  I/O: the SoA state is read/written coalesced straight from registers;
+// the AoS action row is the thread's own 4*AS4 floats (float4 loads); the joint observation rows of the CTA's
+// 128 env instances are assembled in shared memory and streamed out as one contiguous block of float4 stores.
+// Arithmetic and operation order follow env_physics / env_flags_rewards / env_obs_value exactly.
+// --------------------------------------------------------------------------------------------
+constexpr int SPREAD_EB = 128;
+
+template <int A>
+__global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int E, float* __restrict__ state,
+                                                               const float* __restrict__ act, float* __restrict__ obs_out,
+                                                               float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
+  constexpr int L = A, D = 6 * A, OS = (A * D + 3) / 4 * 4, AS = (5 * A + 3) / 4 * 4, OS4 = OS / 4;
+  constexpr int PITCH4 = OS4 | 1;  // odd pitch in float4 units
+  extern __shared__ __align__(16) float sObs[];  // [SPREAD_EB][PITCH4 float4]
+  const int tid = threadIdx.x;
+  const int e0 = blockIdx.x * SPREAD_EB;
+  const int nE = min(SPREAD_EB, E - e0);
+  const int e = e0 + tid;
+  if (tid < nE) {
+    float px[A], py[A], vx[A], vy[A], lx[L], ly[L], a[AS];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      px[i] = state[(size_t)(4 * i + 0) * E + e];
+      py[i] = state[(size_t)(4 * i + 1) * E + e];
+      vx[i] = state[(size_t)(4 * i + 2) * E + e];
+      vy[i] = state[(size_t)(4 * i + 3) * E + e];
+    }
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      lx[l] = state[(size_t)(4 * A + 2 * l + 0) * E + e];
+      ly[l] = state[(size_t)(4 * A + 2 * l + 1) * E + e];
+    }
+    const float4* arow = reinterpret_cast<const float4*>(act + (size_t)e * AS);
+#pragma unroll
+    for (int q = 0; q < AS / 4; ++q) {
+      const float4 v = arow[q];
+      a[4 * q + 0] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+    }
+    // World.step: action force, soft contact between agents (landmarks do not collide in simple_spread), integration
+    const float k = (float)P.contact_margin, cf = (float)P.contact_force, zmin = -104.0f;
+    const float damp = 1.0f - (float)P.damping, dt = (float)P.dt;
+    float nvx[A], nvy[A], npx[A], npy[A];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      float fx = a[5 * i + 1] - a[5 * i + 2];
+      float fy = a[5 * i + 3] - a[5 * i + 4];
+      const float sens = (float)P.sens[i];
+      fx *= sens;
+      fy *= sens;
+      const float si = P.sizef[i];
+#pragma unroll
+      for (int j = 0; j < A; ++j) {
+        if (j == i) continue;
+        const float dx = px[i] - px[j], dy = py[i] - py[j];
+        const float dist = sqrtf(dx * dx + dy * dy);
+        const float dmin = si + P.sizef[j];
+        const float z = -(dist - dmin) / k;
+        if (z < zmin) continue;
+        const float pen = logaddexp0<float>(z) * k;
+        fx = cf * dx / dist * pen + fx;
+        fy = cf * dy / dist * pen + fy;
+      }
+      float wx = vx[i] * damp, wy = vy[i] * damp;
+      wx += fx * dt;
+      wy += fy * dt;
+      const float ms = (float)P.max_speed[i];
+      if (ms > 0.f) {
+        const float speed = sqrtf(wx * wx + wy * wy);
+        if (speed > ms) {
+          wx = wx / speed * ms;
+          wy = wy / speed * ms;
+        }
+      }
+      nvx[i] = wx; nvy[i] = wy;
+      npx[i] = px[i] + wx * dt;
+      npy[i] = py[i] + wy * dt;
+    }
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      state[(size_t)(4 * i + 0) * E + e] = npx[i];
+      state[(size_t)(4 * i + 1) * E + e] = npy[i];
+      state[(size_t)(4 * i + 2) * E + e] = nvx[i];
+      state[(size_t)(4 * i + 3) * E + e] = nvy[i];
+    }
+    // Scenario.reward: per landmark the distance of the closest agent; per agent the collision count (self included);
+    // every agent receives the sum over agents (shared reward)
+    float r[A];
+    float msum = 0.f;
+    {
+      float m[L];
+#pragma unroll
+      for (int l = 0; l < L; ++l) {
+        float best = 0.f;
+#pragma unroll
+        for (int q = 0; q < A; ++q) {
+          const float dx = npx[q] - lx[l], dy = npy[q] - ly[l];
+          const float d = sqrtf(dx * dx + dy * dy);
+          best = (q == 0 || d < best) ? d : best;
+        }
+        m[l] = best;
+      }
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < A; ++q) {
+          const float dx = npx[q] - npx[i], dy = npy[q] - npy[i];
+          cnt += (sqrtf(dx * dx + dy * dy) < P.sizef[q] + P.sizef[i]) ? 1 : 0;
+        }
+        float ri = 0.f;
+#pragma unroll
+        for (int l = 0; l < L; ++l) ri -= m[l];
+        ri -= (float)cnt;
+        r[i] = ri;
+      }
+#pragma unroll
+      for (int i = 0; i < A; ++i) msum += r[i];
+    }
+#pragma unroll
+    for (int i = 0; i < A; ++i) rew_out[(size_t)e * A + i] = msum;
+    // Scenario.observation of every agent: [vel, pos, landmarks - pos, others - pos, silent comm zeros]
+    float o[OS];
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      o[i * D + 0] = nvx[i]; o[i * D + 1] = nvy[i]; o[i * D + 2] = npx[i]; o[i * D + 3] = npy[i];
+#pragma unroll
+      for (int l = 0; l < L; ++l) { o[i * D + 4 + 2 * l] = lx[l] - npx[i]; o[i * D + 5 + 2 * l] = ly[l] - npy[i]; }
+#pragma unroll
+      for (int q = 0; q < A; ++q) {
+        if (q == i) continue;
+        const int c = 4 + 2 * L + 2 * (q < i ? q : q - 1);
+        o[i * D + c] = npx[q] - npx[i];
+        o[i * D + c + 1] = npy[q] - npy[i];
+      }
+#pragma unroll
+      for (int c = 4 + 2 * L + 2 * (A - 1); c < D; ++c) o[i * D + c] = 0.f;
+    }
+#pragma unroll
+    for (int c = A * D; c < OS; ++c) o[c] = 0.f;
+    // row pitch OS4 + 1 float4 (odd for every A here, or made odd): conflict-free 16-byte stores and reads
+    float4* orow = reinterpret_cast<float4*>(sObs) + tid * PITCH4;
+#pragma unroll
+    for (int q = 0; q < OS4; ++q) orow[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
+  __syncthreads();
+  // the CTA's observation rows are contiguous in global memory: one flat float4 sweep
+  float4* dst = reinterpret_cast<float4*>(obs_out + (size_t)e0 * OS);
+  const float4* src = reinterpret_cast<const float4*>(sObs);
+  for (int i = tid; i < nE * OS4; i += SPREAD_EB) {
+    const int ee = i / OS4, q = i - ee * OS4;
+    dst[i] = src[ee * PITCH4 + q];
+  }
+  // done is identically False in MPE (no done callback)
+  uint8_t* dn = done_out + (size_t)e0 * A;
+  for (int i = tid; i < nE * A; i += SPREAD_EB) dn[i] = 0;
+}
+
 // scenario.reset_world: agents U(-1,1), velocities / comm 0, landmarks U(lo,hi)
 template <typename real>
 __global__ void k_env_reset(EnvParams P, int E, real* __restrict__ state, uint64_t seed, uint64_t episode,
@@ -216,9 +377,28 @@ static int launch_step_eb(mdp_env* env, int E, void* state, const float* act, fl
 }
 
 // threads per CTA >= EB * A with agent-uniform warps (EB % 32 == 0)
+template <int A>
+static int launch_spread(mdp_env* env, int E, float* state, const float* act, float* obs, float* rew, uint8_t* done, cudaStream_t st) {
+  const size_t smem = (size_t)SPREAD_EB * ((env->P.obs_stride / 4) | 1) * 16;
+  auto kern = k_env_step_spread<A>;
+  if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<cdiv(E, SPREAD_EB), SPREAD_EB, smem, st>>>(env->P, E, state, act, obs, rew, done);
+  return check_launch("k_env_step_spread");
+}
+
 template <typename real, bool DO_STEP>
 static int launch_step(mdp_env* env, int E, void* state, const float* act, float* obs, float* rew, uint8_t* done,
                        cudaStream_t st) {
+  if (DO_STEP && sizeof(real) == 4 && env->P.scenario == MDP_SIMPLE_SPREAD && !env->force_generic) {
+    switch (env->P.A) {
+      case 2: return launch_spread<2>(env, E, (float*)state, act, obs, rew, done, st);
+      case 3: return launch_spread<3>(env, E, (float*)state, act, obs, rew, done, st);
+      case 4: return launch_spread<4>(env, E, (float*)state, act, obs, rew, done, st);
+      case 5: return launch_spread<5>(env, E, (float*)state, act, obs, rew, done, st);
+      case 6: return launch_spread<6>(env, E, (float*)state, act, obs, rew, done, st);
+      default: break;
+    }
+  }
   if (env->P.A == 1) return launch_step_eb<real, 128, DO_STEP>(env, E, state, act, obs, rew, done, st);
   if (env->P.A == 2) return launch_step_eb<real, 64, DO_STEP>(env, E, state, act, obs, rew, done, st);
   return launch_step_eb<real, 32, DO_STEP>(env, E, state, act, obs, rew, done, st);
@@ -249,6 +429,12 @@ extern "C" void mdp_env_destroy(mdp_env* env) {
   if (!env) return;
   if (env->d_cols) cudaFree(env->d_cols);
   delete env;
+}
+
+extern "C" int mdp_env_force_generic(mdp_env* env, int32_t on) {
+  MDP_REQUIRE(env, "mdp_env_force_generic: null env");
+  env->force_generic = on ? 1 : 0;
+  return MDP_OK;
 }
 
 extern "C" int mdp_env_set_ctl(mdp_env* env, const uint64_t* ctl) {

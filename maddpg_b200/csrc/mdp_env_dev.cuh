@@ -403,6 +403,7 @@ struct mdp_env {
   int d_cols_device = -1;
   float reset_lo_lm, reset_hi_lm;
   const unsigned long long* ctl = nullptr;
+  int force_generic = 0;  // 1: always the table-driven kernel (tests compare the two)
 };
 
 

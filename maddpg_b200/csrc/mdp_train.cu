@@ -995,8 +995,11 @@ int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t co
 static bool want_tc(const mdp_core* c, int B, int count) {
   if (c->tc_mode < 0 || c->cfg.num_units != 64) return false;
   if (c->tc_mode > 0) return true;
-  (void)B; (void)count;
-  return false;
+  // automatic: the 128-row tensor-core tiles pay off once a launch fills most SMs with them, or when the critic input
+  // is wide enough that streaming it through the UMMA pipeline beats the SIMT K-loop (measured on B200)
+  int max_in = 0;
+  for (int i = 0; i < c->cfg.n_agents; ++i) max_in = std::max(max_in, c->lay.net_in[i][MDP_NET_TARGET_Q]);
+  return cdiv(B, 128) * count >= 96 || max_in >= 1024;
 }
 
 static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,

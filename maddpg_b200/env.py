@@ -130,6 +130,10 @@ class BatchedMultiAgentEnv(object):
         """Attach / detach (None) a device control block (include/maddpg_b200.h: mdp_env_set_ctl)."""
         _lib.check(_lib.lib.mdp_env_set_ctl(self._h, _lib.ptr(ctl)), "mdp_env_set_ctl")
 
+    def force_generic_kernel(self, on=True):
+        """Always use the table-driven env-step kernel (include/maddpg_b200.h: mdp_env_force_generic)."""
+        _lib.check(_lib.lib.mdp_env_force_generic(self._h, int(bool(on))), "mdp_env_force_generic")
+
     def reset_device(self, init_state=None, episode=None):
         """Device-only reset (no host copy of the observations); ``episode`` overrides the Philox
         episode id (a graph-relative offset while a control block is attached)."""

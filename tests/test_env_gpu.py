@@ -167,3 +167,26 @@ def test_step_with_fused_ring_insert():
     used = list(range(0, L.x_dim)) + list(range(L.nx_off, L.nx_off + L.obs_sum)) + list(range(L.rw_off, L.dn_off + 4))
     for k in range(384 - 250, 384):
         assert torch.equal(got[k % 250, used], allrows[k, used]), k
+
+
+@pytest.mark.parametrize("A,E", [(2, 77), (3, 4096 + 5), (4, 130), (5, 64), (6, 129)])
+def test_spread_register_kernel_matches_table_driven_kernel(A, E):
+    """simple_spread fast path (one thread per env, registers) vs the table-driven kernel on the same Philox
+    resets and action tape, 30 steps with contacts.  Both kernels start every step from the same state (the stiff
+    contact model amplifies last-bit differences ~100x per contact step), so the comparison
+    isolates one step of arithmetic."""
+    from maddpg_b200 import BatchedMultiAgentEnv
+    envs = [BatchedMultiAgentEnv("simple_spread", num_envs=E, num_agents=A, squeeze=False, seed=5) for _ in range(2)]
+    envs[1].force_generic_kernel(True)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for env in envs:
+        env.reset_device()
+    for t in range(30):
+        act = torch.softmax(3.0 * torch.randn((E, envs[0].act_stride), device="cuda", generator=g), -1)
+        envs[0].state.copy_(envs[1].state)
+        for env in envs:
+            env.step_device(act)
+        torch.testing.assert_close(envs[0].obs, envs[1].obs, rtol=1e-5, atol=1e-5, msg=lambda m: "obs t=%d %s" % (t, m))
+        torch.testing.assert_close(envs[0].rew, envs[1].rew, rtol=1e-5, atol=1e-5, msg=lambda m: "rew t=%d %s" % (t, m))
+        torch.testing.assert_close(envs[0].state, envs[1].state, rtol=1e-5, atol=1e-5, msg=lambda m: "state t=%d %s" % (t, m))
+        assert int(envs[0].done.sum()) == 0
