@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--rollout-mode", default="mega", choices=["mega", "graph", "eager"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-tensor-section", action="store_true")
     return ap.parse_args()
 
 
@@ -157,6 +158,48 @@ def measured_peak_hbm():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tensor_core_section(torch, dev):
+    """Grouped TD-target launch (maddpg.py:181-187 for all agents) at the simple_spread N=24 update shape, tcgen05 kernel
+    vs the fp32 SIMT kernel, CUDA events on the launching stream, L2 flushed before every launch."""
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
+    from maddpg_b200.rollout import BatchedRollout
+    NA, E, B, U = 24, 2048, 1024, 64
+    env = BatchedMultiAgentEnv("simple_spread", num_envs=E, num_agents=NA, device=dev, squeeze=False)
+    core = MADDPGCore(env.obs_dims, env.action_space, [False] * NA, num_units=U, device=dev, replay_capacity=E * 26)
+    roll = BatchedRollout(env, core, EP_LEN, mode="eager")
+    env.reset_device()
+    roll.run(EP_LEN)
+    g = torch.Generator(device="cpu").manual_seed(7)
+    idx = torch.randint(0, core.ring.length[0], (NA, B), generator=g).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    Fpi = sum(d * U + U * U + U * k for d, k in zip(env.obs_dims, env.act_dims))
+    Fq = (sum(env.obs_dims) + sum(env.act_dims)) * U + U * U + U
+    flops = 2 * (Fpi + Fq) * B * NA
+    out = {"workload": "simple_spread N=24 update shape per GPU (BASELINE.json configs[4]): grouped TD target of 24 agents, "
+                       "batch 1024, critic input 3576, num_units 64", "algorithmic_flops_per_launch": flops, "bound": "tensor",
+           "peak_tf32_dense_tflops_nominal": 1100.0, "mma_issue_multiplier": 3,
+           "note": "every GEMM is issued as 3 kind::tf32 MMAs (hi/lo split) to hold the 1e-4 parity bar; tensor-pipe "
+                   "activity from ncu: profiles/r1_td_target_tc_cfg5_grouped.txt"}
+    for name, mode in (("tcgen05", 1), ("simt_fp32", -1)):
+        core.set_tensor_cores(mode)
+        for _ in range(3):
+            core.td_target_all(core.ring.ring, idx=idx)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in evs:
+            flush.fill_(1.0)
+            a.record()
+            core.td_target_all(core.ring.ring, idx=idx)
+            b.record()
+        torch.cuda.synchronize()
+        us = sum(a.elapsed_time(b) for a, b in evs) * 1e3 / len(evs)
+        out[name] = {"avg_launch_us": us, "achieved_tflops": flops / us / 1e6}
+    out["speedup_vs_simt"] = out["simt_fp32"]["avg_launch_us"] / out["tcgen05"]["avg_launch_us"]
+    out["frac"] = 3 * out["tcgen05"]["achieved_tflops"] / 1100.0
+    del env, core, roll, flush
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -418,6 +461,14 @@ def main():
                          "(%.1f s)" % (cpu_steps, dt, cpu_rounds, A, udt),
                "critic_updates_per_sec": u_ps, "host_cores_available": os.cpu_count()}
 
+    # ---- (6) tensor-core TD-target kernel where the GEMMs are large enough to matter: BASELINE.json configs[4]'s
+    #          per-GPU update shape (simple_spread N=24: 24 critics of input width 3576, 576 actor passes, batch 1024) ----------
+    tensor = None
+    if rank == 0 and world == 1 and not args.no_tensor_section:
+        del flush_buf
+        torch.cuda.empty_cache()
+        tensor = tensor_core_section(torch, dev)
+
     # dominant kernel of the timed rollout region: the persistent episode kernel (one launch = 25 steps)
     row_bytes = 4 * sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
     ep_bytes = row_bytes * E * EP_LEN           # the replay rows are the only HBM traffic the algorithm needs
@@ -467,6 +518,8 @@ def main():
                                "e2e": {"value": Re * A * world / e2e_upd_s, "unit": "critic updates/s",
                                        "api": "MADDPGAgentTrainer.update (python index draw + H2D idx + D2H stats)"}},
         }
+        if tensor is not None:
+            line["tensor_core_td_target"] = tensor
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -192,6 +192,12 @@ int mdp_td_target(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int
                   const int64_t* idx, const float* u_target, int32_t u_stride, uint64_t seed, uint64_t counter,
                   float* y_out, float* target_act_out, void* stream);
 
+/* mdp_td_target for every agent in ONE grouped launch (grid.y = agent; the first stage of mdp_update_all): idx is NULL or
+ * int64 [n_agents][idx_agent_stride] index sets (stride 0 shares one set), y_out is float [n_agents][B]; in-kernel Philox
+ * noise only. */
+int mdp_td_target_all(mdp_core* core, const mdp_ring_layout* lay, int32_t B, const float* batch, const int64_t* idx,
+                      int64_t idx_agent_stride, uint64_t seed, uint64_t counter, float* y_out, void* stream);
+
 /* q_train forward/backward (maddpg.py:75-100): grads of mean((Q_j(x) - y)^2) wrt the critic's six
  * tensors are ACCUMULATED into the bound grad buffer (fused fwd + bwd kernel); sum((q-y)^2) -> stats. */
 int mdp_critic_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,

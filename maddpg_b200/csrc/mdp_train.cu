@@ -1047,6 +1047,13 @@ extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* 
   return launch_td_target(c, agent, 1, lay, B, batch, idx, 0, u_target, u_stride, seed, counter, y_out, 0, target_act_out, stream);
 }
 
+extern "C" int mdp_td_target_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B, const float* batch, const int64_t* idx,
+                                 int64_t idx_agent_stride, uint64_t seed, uint64_t counter, float* y_out, void* stream) {
+  MDP_REQUIRE(c && y_out, "mdp_td_target_all: null argument");
+  return launch_td_target(c, 0, c->cfg.n_agents, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, y_out, B, nullptr,
+                          stream);
+}
+
 static int launch_critic_grads(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
                                const int64_t* idx, long long idx_stride, const float* y, long long y_stride, float* q_out,
                                void* stream) {

@@ -218,6 +218,20 @@ class MADDPGCore(object):
                                           _lib.current_stream()), "mdp_td_target")
         return (y, ta) if want_target_act else y
 
+    def td_target_all(self, batch, idx=None, counter=None):
+        """TD targets of every agent in one grouped launch -> (n_agents, B) (include/maddpg_b200.h: mdp_td_target_all)."""
+        if idx is None:
+            B, stride = batch.shape[0], 0
+        else:
+            B, stride = idx.shape[-1], (idx.stride(0) if idx.dim() == 2 else 0)
+        key = ("all", B)
+        if key not in self._y:
+            self._y[key] = torch.empty((self.n, B), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.mdp_td_target_all(self._h, C.byref(self.ring.layout), B, _lib.ptr(batch), _lib.ptr(idx), stride,
+                                              self.seed, self.next_counter() if counter is None else counter,
+                                              _lib.ptr(self._y[key]), _lib.current_stream()), "mdp_td_target_all")
+        return self._y[key]
+
     def critic_grads(self, agent, batch, y, want_q=False, idx=None):
         B = batch.shape[0] if idx is None else idx.shape[0]
         q = torch.empty(B, dtype=torch.float32, device=self.device) if want_q else None

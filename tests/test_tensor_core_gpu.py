@@ -90,7 +90,9 @@ def test_grouped_td_target_tensor_cores():
         core.counter = c0
         ys.append(core.td_target(j, core.ring.ring, idx=idx[j]).clone())
     core.counter = c0
-    core.update_all(core.ring.ring, idx=idx)
-    y_all = core._y[("all", B)]
+    y_all = core.td_target_all(core.ring.ring, idx=idx).clone()
     for j in range(n):
         torch.testing.assert_close(y_all[j], ys[j], rtol=0, atol=0)
+    core.counter = c0
+    core.update_all(core.ring.ring, idx=idx)  # the Jacobi round starts from the same grouped launch
+    torch.testing.assert_close(core._y[("all", B)], y_all, rtol=0, atol=0)
