@@ -2,16 +2,21 @@
 //   a'_i = gumbel_softmax(target_p_i(o'_i)) for all i ; q' = target_q_j(o', a') ; y = r_j + gamma (1 - d_j) q'
 // (maddpg/trainer/maddpg.py:181-187, :70-71, :104,108) with every MLP layer as a UMMA GEMM.
 //
-// One CTA owns 128 batch rows (UMMA_M = 128, cta_group::1, N = num_units).  Operands are staged in shared memory
-// as SWIZZLE_128B K-major images (mdp_umma.cuh) by the CTA's own threads, because they are produced on the fly:
-// the layer-1 input is gathered row by row from the replay ring through the sampled indices (fused
-// ReplayBuffer.sample_index), the hidden activations come out of the previous epilogue, and every fp32 operand
-// is split into a TF32 "hi" image and an exact remainder "lo" image.  Each GEMM is then issued as THREE
-// kind::tf32 MMAs (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM), which restores ~fp32 products -- the
-// 1e-4 parity bar on Q values does not survive plain TF32.  Layer 1 streams K in 32-column chunks
-// through a two-stage ring (the MMAs of chunk c overlap the gather + split of chunk c+1; tcgen05.commit frees a
-// stage); accumulators live in TMEM and are read back with tcgen05.ld (one thread = one batch row x 32 units),
-// so bias + ReLU, the output head, the Gumbel-softmax and the TD combine are row-local epilogues in registers.
+// One CTA owns 128 batch rows (UMMA_M = 128, cta_group::1, N = num_units).  Every fp32 operand is split into a TF32
+// "hi" part and an exact remainder "lo" and each GEMM is issued as THREE kind::tf32 MMAs (lo*hi + hi*lo + hi*hi, fp32
+// accumulation in TMEM), which restores ~fp32 products -- the 1e-4 parity bar on Q values does not survive plain TF32
+// (SURVEY H4).  Operand placement:
+//   A (activations: gathered replay rows, h1)  -> TENSOR MEMORY.  One thread owns one batch row (TMEM lane): it gathers its
+//       row's 16 columns of a 32-column chunk from the replay ring through the sampled index (fused
+//       ReplayBuffer.sample_index), splits them in registers and writes them with tcgen05.st; the epilogue of layer 1 puts
+//       relu(acc + b1) straight back as layer 2's A operand the same way.  No shared-memory images, no swizzle, no proxy fence.
+//   B (weights) -> shared memory, SWIZZLE_128B K-major images streamed by a TMA producer warp (cp.async.bulk) from
+//       pre-split global images that k_build_images refreshes from the flat parameter buffer before every launch.
+//   D (accumulators) -> TMEM, read back with tcgen05.ld (thread = batch row x 32 units), so bias + ReLU, the output head, the
+//       Gumbel-softmax and the float64 TD combine are row-local register code.
+// Warp roles: 8 compute warps (gather/split/tcgen05.st, epilogues), 1 TMA producer warp, 1 MMA issuer warp; mbarriers carry
+// "stage filled" (compute -> MMA), "weights landed" (TMA -> MMA), "stage free" (tcgen05.commit -> compute, TMA) and
+// "accumulator ready" (tcgen05.commit -> compute).  Layer 1 streams K through a 4-stage ring of TMEM A slots + smem B slots.
 #include "mdp_mlp.cuh"
 #include "mdp_umma.cuh"
 
@@ -25,17 +30,20 @@ constexpr int TMR = 128;  // batch rows per CTA (UMMA M)
 constexpr int NTC = 256;  // compute threads: 8 warps; warp w reads TMEM lanes [32 (w & 3), +32), unit half w >> 2
 constexpr int NTT = 320;  // + a TMA producer warp (pre-split weight images) + an MMA issuer warp
 
+constexpr int NS = 4;      // layer-1 ring depth (TMEM A slots and shared-memory B slots)
+
 template <int U>
-struct Lay {  // byte offsets from the 1024-byte aligned base of dynamic shared memory
-  static constexpr uint32_t X_IMG = TMR * 128;           // [128 rows][32 cols]   16 KB
-  static constexpr uint32_t W_IMG = U * 128;             // [U rows][32 cols]
-  static constexpr uint32_t STAGE = 2 * X_IMG + 2 * W_IMG;
-  static constexpr uint32_t H_IMG = (U / 32) * X_IMG;    // [128][U]
-  static constexpr uint32_t W2_IMG = (U / 32) * W_IMG;   // [U][U]
-  static constexpr uint32_t OFF_H = 2 * STAGE;
-  static constexpr uint32_t OFF_W2 = OFF_H + 2 * H_IMG;
+struct Lay {
+  // shared memory (bytes from the 1024-byte aligned base): weight images only
+  static constexpr uint32_t W_IMG = U * 128;             // [U rows][32 cols] image
+  static constexpr uint32_t W2_IMG = (U / 32) * W_IMG;   // [U][U] image
+  static constexpr uint32_t OFF_W2 = NS * 2 * W_IMG;
   static constexpr uint32_t OFF_MISC = OFF_W2 + 2 * W2_IMG;
-  static constexpr int MISC_FLOATS = U + U + U * MAXK + 16 + TMR * KPAD + TMR + 2 * TMR + 2 * TMR;  // b1 b2 W3 b3 part q rd rowoff
+  static constexpr int MISC_FLOATS = U + U + U * MAXK + 16 + 2 * TMR * KPAD + TMR + 2 * TMR + 2 * TMR;  // b1 b2 W3 b3 part noise q rd rowoff
+  // tensor memory columns (512 allocated): accumulators, h1 (hi | lo), NS x-chunk slots (hi | lo, 32 columns each)
+  static constexpr uint32_t T_ACC1 = 0, T_ACC2 = U, T_H1 = 2 * U, T_X = 4 * U;
+  static constexpr uint32_t T_COLS = 512;
+  static_assert(4 * U + NS * 64 <= 512, "TMEM budget");
 };
 
 __device__ __forceinline__ void mbar_wait_bounded(unsigned long long* bar, uint32_t parity) {
@@ -110,76 +118,78 @@ struct XT {
 };
 
 struct XRegs {
-  float4 v[4];  // thread's four float4 units of a [128][32] chunk: unit e = j * 256 + tid -> row e >> 3, columns 4 (e & 7)..+3
+  float v[16];  // this thread's 16 columns (half of a 32-column chunk) of its batch row
 };
 
-__device__ __forceinline__ float x_get(const XT& xs, const long long* sRow, int r, int col) {
+__device__ __forceinline__ float x_get(const XT& xs, long long rowoff, int r, int col) {
   if (col >= xs.over_c0 && col < xs.over_c0 + xs.over_n) return xs.over[(size_t)r * xs.over_ld + (col - xs.over_c0)];
-  if (col < xs.n0) return __ldg(xs.g0 + sRow[r] + col);
+  if (col < xs.n0) return __ldg(xs.g0 + rowoff + col);
   return 0.f;
 }
 
-__device__ __forceinline__ void load_x(XRegs& x, const XT& xs, const long long* __restrict__ sRow, int k0, int tid) {
+// columns [k0, k0 + 16) of batch row r (row offset rowoff in the ring)
+__device__ __forceinline__ void load_x(XRegs& x, const XT& xs, long long rowoff, int r, int k0) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int e = j * NTC + tid, r = e >> 3, col = k0 + 4 * (e & 7);
+  for (int q = 0; q < 4; ++q) {
+    const int col = k0 + 4 * q;
     const bool in_over = col + 4 > xs.over_c0 && col < xs.over_c0 + xs.over_n;
     if (xs.vec_ok && col + 4 <= xs.n0 && !in_over) {
-      x.v[j] = __ldg(reinterpret_cast<const float4*>(xs.g0 + sRow[r] + col));
+      const float4 t = __ldg(reinterpret_cast<const float4*>(xs.g0 + rowoff + col));
+      x.v[4 * q + 0] = t.x; x.v[4 * q + 1] = t.y; x.v[4 * q + 2] = t.z; x.v[4 * q + 3] = t.w;
     } else {
-      x.v[j].x = x_get(xs, sRow, r, col);
-      x.v[j].y = x_get(xs, sRow, r, col + 1);
-      x.v[j].z = x_get(xs, sRow, r, col + 2);
-      x.v[j].w = x_get(xs, sRow, r, col + 3);
+      x.v[4 * q + 0] = x_get(xs, rowoff, r, col);
+      x.v[4 * q + 1] = x_get(xs, rowoff, r, col + 1);
+      x.v[4 * q + 2] = x_get(xs, rowoff, r, col + 2);
+      x.v[4 * q + 3] = x_get(xs, rowoff, r, col + 3);
     }
   }
 }
 
-template <int U>
-__device__ __forceinline__ void store_x(unsigned char* stage, const XRegs& x, int tid) {
-  unsigned char* xhi = stage;
-  unsigned char* xlo = stage + Lay<U>::X_IMG;
+// split and write the thread's 16 columns into TMEM slot `slot` (hi at +0, lo at +32), columns [c16, c16 + 16)
+__device__ __forceinline__ void store_x(uint32_t slot, uint32_t lane_base, int c16, const XRegs& x) {
+  float hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int e = j * NTC + tid, r = e >> 3;
-    float4 hi, lo;
-    umma::split_tf32(x.v[j].x, hi.x, lo.x);
-    umma::split_tf32(x.v[j].y, hi.y, lo.y);
-    umma::split_tf32(x.v[j].z, hi.z, lo.z);
-    umma::split_tf32(x.v[j].w, hi.w, lo.w);
-    const uint32_t off = umma::sw128_off(r, 4 * (e & 7));
-    *reinterpret_cast<float4*>(xhi + off) = hi;
-    *reinterpret_cast<float4*>(xlo + off) = lo;
-  }
+  for (int i = 0; i < 16; ++i) umma::split_tf32(x.v[i], hi[i], lo[i]);
+  umma::tmem_st16(slot + lane_base + c16, hi);
+  umma::tmem_st16(slot + lane_base + 32 + c16, lo);
 }
 
-// D[128 x U] (+)= A[128 x 8*nsteps] * B[U x 8*nsteps]^T as lo*hi + hi*lo + hi*hi (one elected thread)
-template <int U>
-__device__ __forceinline__ void issue_3x(uint32_t tacc, uint32_t a_hi, uint32_t a_lo, uint32_t a_panel, uint32_t b_hi, uint32_t b_lo,
-                                         uint32_t b_panel, int nsteps, bool accumulate) {
+// D[128 x U] (+)= A[128 x 8*NSTEPS] (TMEM, hi | lo `a_lo_off` columns apart) * B[U x 8*NSTEPS]^T (smem image pair, descriptors
+// of k-step 0 given) as lo*hi + hi*lo + hi*hi.  The issuing thread is the serial bottleneck of the whole pipeline, so the
+// loop is fully unrolled and a k-step only costs adds: +8 TMEM columns on A, +32 bytes (2 descriptor units) on B inside a
+// panel, +panel bytes across panels.
+template <int U, int NSTEPS>
+__device__ __forceinline__ void issue_3x(uint32_t tacc, uint32_t a_hi, uint32_t a_lo_off, uint64_t b_hi, uint64_t b_lo, uint32_t accumulate) {
   constexpr uint32_t idesc = umma::idesc_tf32(TMR, U, 0, 0);
-  for (int s = 0; s < nsteps; ++s) {
-    umma::mma_tf32(tacc, umma::desc_k(a_lo, a_panel, s), umma::desc_k(b_hi, b_panel, s), idesc, (accumulate || s > 0) ? 1u : 0u);
-    umma::mma_tf32(tacc, umma::desc_k(a_hi, a_panel, s), umma::desc_k(b_lo, b_panel, s), idesc, 1u);
-    umma::mma_tf32(tacc, umma::desc_k(a_hi, a_panel, s), umma::desc_k(b_hi, b_panel, s), idesc, 1u);
+  constexpr uint32_t PANEL16 = (U * 128) >> 4;  // panel stride of a [U][32] image in 16-byte descriptor units
+#pragma unroll
+  for (int s = 0; s < NSTEPS; ++s) {
+    const uint32_t bo = (uint32_t)(s >> 2) * PANEL16 + (uint32_t)(s & 3) * 2u;
+    umma::mma_tf32_ta(tacc, a_hi + a_lo_off + 8 * s, b_hi + bo, idesc, s == 0 ? accumulate : 1u);
+    umma::mma_tf32_ta(tacc, a_hi + 8 * s, b_lo + bo, idesc, 1u);
+    umma::mma_tf32_ta(tacc, a_hi + 8 * s, b_hi + bo, idesc, 1u);
   }
 }
 
-struct Pipe {       // uniform across the CTA (the producer warp keeps its own copy in step)
-  uint32_t chunks;  // layer-1 chunks so far (stage = chunks & 1)
+struct Pipe {       // every role keeps its own copy, advanced in lock step
+  uint32_t chunks;  // layer-1 chunks so far (slot = chunks % NS)
   uint32_t accs;    // completed waits on the accumulator barrier
   uint32_t nets;    // nets finished
 };
 
 struct Bars {
-  unsigned long long stage_w[2];     // TMA: W1^T chunk images landed in stage s
-  unsigned long long stage_x[2];     // compute warps (8 arrivals): X chunk images stored in stage s
-  unsigned long long h1_full;        // compute warps (8 arrivals): h1 images stored
-  unsigned long long stage_free[2];  // tcgen05.commit: the MMAs reading stage s are done
-  unsigned long long w2_full;        // TMA: W2^T images landed
-  unsigned long long w2_free;        // tcgen05.commit: layer-2 MMAs done, W2^T may be overwritten
-  unsigned long long acc;            // tcgen05.commit: accumulator complete
+  unsigned long long stage_w[NS];     // TMA: W1^T chunk images landed in smem slot s
+  unsigned long long stage_x[NS];     // compute warps (8 arrivals): X chunk written to TMEM slot s
+  unsigned long long stage_free[NS];  // tcgen05.commit: the MMAs reading slot s (TMEM A + smem B) are done
+  unsigned long long h1_full;         // compute warps (8 arrivals): h1 written to TMEM
+  unsigned long long w2_full;         // TMA: W2^T images landed
+  unsigned long long w2_free;         // tcgen05.commit: layer-2 MMAs done, W2^T may be overwritten
+  unsigned long long acc;             // tcgen05.commit: accumulator complete
 };
+
+__device__ __forceinline__ void wait_slot_free(Bars* bars, const Pipe& pipe) {
+  if (pipe.chunks >= NS) mbar_wait_bounded(&bars->stage_free[pipe.chunks % NS], ((pipe.chunks / NS) - 1u) & 1u);
+}
 
 // producer warp (one lane): streams one net's weight images; runs ahead of the compute warps, throttled by the
 // stage_free / w2_free barriers
@@ -191,34 +201,37 @@ __device__ __forceinline__ void produce_net(unsigned char* smem, Bars* bars, Pip
   bulk_g2s(smem + L::OFF_W2, img.w2, 2 * L::W2_IMG, &bars->w2_full);
   const int nchunks = (in_dim + 31) / 32;
   for (int c = 0; c < nchunks; ++c) {
-    const uint32_t s = pipe.chunks & 1u;
-    if (pipe.chunks >= 2) mbar_wait_bounded(&bars->stage_free[s], ((pipe.chunks >> 1) - 1u) & 1u);
+    const uint32_t s = pipe.chunks % NS;
+    wait_slot_free(bars, pipe);
     mbar_arrive_expect_tx(&bars->stage_w[s], 2 * L::W_IMG);
-    bulk_g2s(smem + s * L::STAGE + 2 * L::X_IMG, img.w1 + (size_t)c * (2 * L::W_IMG), 2 * L::W_IMG, &bars->stage_w[s]);
+    bulk_g2s(smem + s * (2 * L::W_IMG), img.w1 + (size_t)c * (2 * L::W_IMG), 2 * L::W_IMG, &bars->stage_w[s]);
     pipe.chunks++;
   }
   pipe.nets++;
 }
 
-__device__ __forceinline__ void warp_arrive(unsigned long long* bar, int lane) {
-  umma::fence_async_smem();  // this lane's generic-proxy stores -> async proxy
+// this warp's tcgen05.st writes are complete and ordered before the MMA warp's reads
+__device__ __forceinline__ void warp_arrive_tmem(unsigned long long* bar, int lane) {
+  umma::tmem_st_wait();
+  umma::fence_before();
   __syncwarp();
   if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // MMA issuer warp (one lane): both GEMMs of one net.  Waits for the operands (TMA weight images + the compute warps'
-// X / h1 images), issues the 3xTF32 MMAs and commits the barriers that free the buffers / publish the accumulators.
+// X / h1 writes), issues the 3xTF32 MMAs and commits the barriers that free the slots / publish the accumulators.
 template <int U>
 __device__ __forceinline__ void mma_net(unsigned char* smem, Bars* bars, Pipe& pipe, uint32_t tbase, int in_dim) {
   using L = Lay<U>;
   const int nchunks = (in_dim + 31) / 32;
+  const uint64_t w_hi0 = umma::desc_k(smem_u32(smem), L::W_IMG, 0), w_lo0 = umma::desc_k(smem_u32(smem) + L::W_IMG, L::W_IMG, 0);
   for (int c = 0; c < nchunks; ++c) {
-    const uint32_t s = pipe.chunks & 1u, ph = (pipe.chunks >> 1) & 1u;
+    const uint32_t s = pipe.chunks % NS, ph = (pipe.chunks / NS) & 1u;
     mbar_wait_bounded(&bars->stage_x[s], ph);
     mbar_wait_bounded(&bars->stage_w[s], ph);
     umma::fence_after();
-    const uint32_t sa = smem_u32(smem + s * L::STAGE);
-    issue_3x<U>(tbase, sa, sa + L::X_IMG, L::X_IMG, sa + 2 * L::X_IMG, sa + 2 * L::X_IMG + L::W_IMG, L::W_IMG, 4, c > 0);
+    const uint32_t so = s * ((2 * L::W_IMG) >> 4);  // smem slot offset in descriptor units
+    issue_3x<U, 4>(tbase + L::T_ACC1, tbase + L::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, c > 0 ? 1u : 0u);
     umma::commit(&bars->stage_free[s]);
     if (c == nchunks - 1) umma::commit(&bars->acc);
     pipe.chunks++;
@@ -226,8 +239,8 @@ __device__ __forceinline__ void mma_net(unsigned char* smem, Bars* bars, Pipe& p
   mbar_wait_bounded(&bars->h1_full, pipe.nets & 1u);
   mbar_wait_bounded(&bars->w2_full, pipe.nets & 1u);
   umma::fence_after();
-  const uint32_t ha = smem_u32(smem + L::OFF_H), wa = smem_u32(smem + L::OFF_W2);
-  issue_3x<U>(tbase + U, ha, ha + L::H_IMG, L::X_IMG, wa, wa + L::W2_IMG, L::W_IMG, U / 8, false);
+  const uint32_t wa = smem_u32(smem + L::OFF_W2);
+  issue_3x<U, U / 8>(tbase + L::T_ACC2, tbase + L::T_H1, U, umma::desc_k(wa, L::W_IMG, 0), umma::desc_k(wa + L::W2_IMG, L::W_IMG, 0), 0u);
   umma::commit(&bars->acc);
   umma::commit(&bars->w2_free);
   pipe.nets++;
@@ -235,62 +248,62 @@ __device__ __forceinline__ void mma_net(unsigned char* smem, Bars* bars, Pipe& p
 
 // h2 = relu(relu(X W1 + b1) W2 + b2) for the CTA's 128 rows (compute warps); thread (warp w, lane l) ends up with units
 // [32 (w >> 2) + 64 g, +32) of row 32 (w & 3) + l in h2[32 g ..].  Warps run decoupled: each one gathers, splits and
-// stores its 16 rows of a chunk and arrives on the stage barrier; nothing but the accumulator barrier joins them.
-template <int U>
-__device__ __forceinline__ void forward_hidden_tc(unsigned char* smem, Bars* bars, Pipe& pipe, uint32_t tbase, const XT& xs, const MlpW& w,
+// writes its rows of a chunk and arrives on the slot barrier; nothing but the accumulator barrier joins them.
+constexpr int PD = 3;  // register prefetch depth (chunks)
+
+template <int U, typename Overlap>
+__device__ __forceinline__ void forward_hidden_tc(Bars* bars, Pipe& pipe, uint32_t tbase, const XT& xs, const MlpW& w,
                                                   const long long* sRow, float* sB1, float* sB2, float* sW3, float* sB3,
-                                                  float (&h2)[U / 2]) {
+                                                  float (&h2)[U / 2], Overlap&& overlap) {
   using L = Lay<U>;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-  unsigned char* h1hi = smem + L::OFF_H;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  const long long rowoff = sRow[row];
   const int nchunks = (w.in + 31) / 32;
-  XRegs xr[2];  // register prefetch, two chunks deep
-  load_x(xr[0], xs, sRow, 0, tid);
-  if (nchunks > 1) load_x(xr[1], xs, sRow, 32, tid);
+  XRegs xr[PD];
+#pragma unroll
+  for (int b = 0; b < PD; ++b)
+    if (b < nchunks) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
   for (int i = tid; i < U; i += NTC) { sB1[i] = w.b1[i]; sB2[i] = w.b2[i]; }
   for (int i = tid; i < U * w.out; i += NTC) sW3[i] = w.W3[i];
   if (tid < w.out) sB3[tid] = w.b3[tid];
   named_sync();  // small tensors visible to every compute warp
-  // ---- layer 1: K chunks through the two-stage ring
-  for (int c = 0; c < nchunks; c += 2) {
+  // ---- layer 1: K chunks through the NS-slot ring
+  for (int c = 0; c < nchunks; c += PD) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < PD; ++b) {
       if (c + b < nchunks) {
-        const uint32_t s = pipe.chunks & 1u;
-        if (pipe.chunks >= 2) mbar_wait_bounded(&bars->stage_free[s], ((pipe.chunks >> 1) - 1u) & 1u);
-        store_x<U>(smem + s * L::STAGE, xr[b], tid);
-        warp_arrive(&bars->stage_x[s], lane);
-        if (c + b + 2 < nchunks) load_x(xr[b], xs, sRow, 32 * (c + b + 2), tid);
+        const uint32_t s = pipe.chunks % NS;
+        wait_slot_free(bars, pipe);
+        umma::fence_after();
+        store_x(tbase + L::T_X + s * 64, lane_base, 16 * half, xr[b]);
+        warp_arrive_tmem(&bars->stage_x[s], lane);
+        if (c + b + PD < nchunks) load_x(xr[b], xs, rowoff, row, 32 * (c + b + PD) + 16 * half);
         pipe.chunks++;
       }
     }
   }
+  overlap();  // work that does not depend on the net's output (the Gumbel noise) hides behind the layer-1 MMAs
   mbar_wait_bounded(&bars->acc, pipe.accs & 1u);
   pipe.accs++;
   umma::fence_after();
-  // ---- epilogue 1: h1 = relu(acc + b1) -> split -> K-major image pair (A operand of layer 2)
+  // ---- epilogue 1: h1 = relu(acc + b1) -> split -> TMEM (A operand of layer 2)
 #pragma unroll
   for (int g = 0; g < U / 64; ++g) {
     const int c0 = 32 * half + 64 * g;  // this thread's 32 units of the pass
     float v[32];
-    umma::tmem_ld32(tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0, v);
-    unsigned char* phi = h1hi + (uint32_t)(c0 >> 5) * L::X_IMG;
-    unsigned char* plo = phi + L::H_IMG;
+    umma::tmem_ld32(tbase + L::T_ACC1 + lane_base + (uint32_t)c0, v);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 hi, lo;
-      umma::split_tf32(fmaxf(v[4 * q + 0] + sB1[c0 + 4 * q + 0], 0.f), hi.x, lo.x);
-      umma::split_tf32(fmaxf(v[4 * q + 1] + sB1[c0 + 4 * q + 1], 0.f), hi.y, lo.y);
-      umma::split_tf32(fmaxf(v[4 * q + 2] + sB1[c0 + 4 * q + 2], 0.f), hi.z, lo.z);
-      umma::split_tf32(fmaxf(v[4 * q + 3] + sB1[c0 + 4 * q + 3], 0.f), hi.w, lo.w);
-      const uint32_t off = umma::sw128_off(row, 4 * q);
-      *reinterpret_cast<float4*>(phi + off) = hi;
-      *reinterpret_cast<float4*>(plo + off) = lo;
+    for (int q = 0; q < 2; ++q) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) umma::split_tf32(fmaxf(v[16 * q + i] + sB1[c0 + 16 * q + i], 0.f), hi[i], lo[i]);
+      umma::tmem_st16(tbase + L::T_H1 + lane_base + (uint32_t)(c0 + 16 * q), hi);
+      umma::tmem_st16(tbase + L::T_H1 + U + lane_base + (uint32_t)(c0 + 16 * q), lo);
     }
   }
-  umma::fence_before();
-  warp_arrive(&bars->h1_full, lane);
+  warp_arrive_tmem(&bars->h1_full, lane);
   pipe.nets++;
   // ---- layer 2 (issued by the MMA warp): acc2 = h1 W2
   mbar_wait_bounded(&bars->acc, pipe.accs & 1u);
@@ -301,7 +314,7 @@ __device__ __forceinline__ void forward_hidden_tc(unsigned char* smem, Bars* bar
   for (int g = 0; g < U / 64; ++g) {
     const int c0 = 32 * half + 64 * g;
     float v[32];
-    umma::tmem_ld32(tbase + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(U + c0), v);
+    umma::tmem_ld32(tbase + L::T_ACC2 + lane_base + (uint32_t)c0, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) h2[32 * g + i] = fmaxf(v[i] + sB2[c0 + i], 0.f);
   }
@@ -345,7 +358,8 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   float* sW3 = sB2 + U;
   float* sB3 = sW3 + U * MAXK;
   float* sPart = sB3 + 16;
-  float* sQ = sPart + TMR * KPAD;
+  float* sG = sPart + TMR * KPAD;  // Gumbel noise -log(-log u) of the current actor, [row][KPAD]
+  float* sQ = sG + TMR * KPAD;
   float* sRD = sQ + TMR;
   long long* sRow = reinterpret_cast<long long*>(sRD + 2 * TMR);
   const int ASP = C.act_stride | 1;
@@ -359,15 +373,14 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   // the sampled-action tile: shared memory when it fits, otherwise an L2-resident scratch (rows of this CTA only)
   float* actT = act_in_smem ? sAct : act_scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TMR * ASP;
 
-  if (warp == 0) umma::tmem_alloc(&tmem_slot, 2 * U);
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, LY::T_COLS);
   if (tid == 0) {
-    mbar_init(&bars.stage_w[0], 1);
-    mbar_init(&bars.stage_w[1], 1);
-    mbar_init(&bars.stage_x[0], NTC / 32);
-    mbar_init(&bars.stage_x[1], NTC / 32);
+    for (int k = 0; k < NS; ++k) {
+      mbar_init(&bars.stage_w[k], 1);
+      mbar_init(&bars.stage_x[k], NTC / 32);
+      mbar_init(&bars.stage_free[k], 1);
+    }
     mbar_init(&bars.h1_full, NTC / 32);
-    mbar_init(&bars.stage_free[0], 1);
-    mbar_init(&bars.stage_free[1], 1);
     mbar_init(&bars.w2_full, 1);
     mbar_init(&bars.w2_free, 1);
     mbar_init(&bars.acc, 1);
@@ -407,8 +420,15 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
       const AgentDev& ag = C.agents[i];
       const MlpW w = ag.net[MDP_NET_TARGET_P];
       XT xs{batch + L.nx_off + ag.obs_off, ag.obs_dim, nullptr, 0, 0, 0, ((L.nx_off + ag.obs_off) & 3) == 0};
-      forward_hidden_tc<U>(smem, &bars, pipe, tbase, xs, w, sRow, sB1, sB2, sW3, sB3, h2);
       const int K = ag.act_dim;
+      forward_hidden_tc<U>(&bars, pipe, tbase, xs, w, sRow, sB1, sB2, sW3, sB3, h2, [&]() {
+        // both unit-halves of a row share its K draws: half 0 takes the even actions, half 1 the odd ones
+        for (int a = half; a < K; a += 2) {
+          const float u = u_target ? u_target[(row0 + min(row, nrows - 1)) * u_stride + ag.act_off + a]
+                                   : philox_u(seed, counter, (uint32_t)(0x100 + i), row0 + row, a);
+          sG[row * KPAD + a] = gumbel_from_u(u);
+        }
+      });
       if (K == 5) head_partial<U, 5>(h2, sW3, half, part);
       else if (K == 9) head_partial<U, 9>(h2, sW3, half, part);
       else {
@@ -426,9 +446,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
         for (int a = 0; a < MAXK; ++a) {
           if (a < K) {
             const float logit = part[a] + sPart[row * KPAD + a] + sB3[a];
-            const float u = u_target ? u_target[(row0 + min(row, nrows - 1)) * u_stride + ag.act_off + a]
-                                     : philox_u(seed, counter, (uint32_t)(0x100 + i), row0 + row, a);
-            z[a] = logit + gumbel_from_u(u);
+            z[a] = logit + sG[row * KPAD + a];
           }
         }
         for (int h = 0; h < ag.n_heads; ++h) {
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
                             ((L.nx_off + me.obs_off) & 3) == 0};
     else xq = XT{batch + L.nx_off, C.obs_sum, actT, ASP, C.obs_sum, C.act_sum, (L.nx_off & 3) == 0};
     const MlpW tq = me.net[MDP_NET_TARGET_Q];
-    forward_hidden_tc<U>(smem, &bars, pipe, tbase, xq, tq, sRow, sB1, sB2, sW3, sB3, h2);
+    forward_hidden_tc<U>(&bars, pipe, tbase, xq, tq, sRow, sB1, sB2, sW3, sB3, h2, []() {});
     head_partial<U, 1>(h2, sW3, half, part);
     if (half == 1) sPart[row * KPAD] = part[0];
     named_sync();
@@ -490,7 +508,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   }
   umma::fence_before();
   __syncthreads();
-  if (warp == 0) umma::tmem_free(tbase, 2 * U);
+  if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
 }
 
 }  // namespace tc
@@ -536,10 +554,11 @@ int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t co
   const tc::AgentImg* imgs = reinterpret_cast<const tc::AgentImg*>(c->tc_imgs);
   const int n = c->cfg.n_agents, ASP = c->act_stride | 1;
   const size_t fixed = LY::OFF_MISC + (size_t)LY::MISC_FLOATS * 4 + 1024 + 64;
-  const size_t limit = 227 * 1024 - 256;  // static __shared__ (barriers, TMEM slot) comes on top
+  const size_t limit = 227 * 1024 - 512;  // static __shared__ (barriers, TMEM slot) comes on top
   const size_t act_bytes = (size_t)tc::TMR * ASP * 4;
   const int act_in_smem = fixed + act_bytes <= limit;
-  const size_t smem = fixed + (act_in_smem ? act_bytes : 0);
+  // a CTA owns all 512 TMEM columns of its SM: ask for more than half of the shared memory so that two never share one
+  const size_t smem = std::max(fixed + (act_in_smem ? act_bytes : 0), (size_t)116 * 1024);
   const int tiles = cdiv(B, tc::TMR);
   if (!act_in_smem) {
     const size_t need = (size_t)tiles * count * tc::TMR * ASP * sizeof(float);
