@@ -17,32 +17,51 @@ struct OptSeg {
   long long len[6];
 };
 
-__global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ param, float* __restrict__ target,
-                                                           float* __restrict__ grad, float* __restrict__ m,
-                                                           float* __restrict__ v, OptSeg seg, const int* __restrict__ t_ptr,
-                                                           float grad_scale, float clip, double lr, double beta1,
-                                                           double beta2, float eps, float polyak, int do_polyak) {
+// One CTA = one variable.  Latency matters more than bandwidth here (a cfg-2 net has 14 k parameters and the kernel sits
+// on the serial path of every agent update), so the second pass's operands (m, v, param, target) are loaded BEFORE the norm
+// reduction, and the bias-corrected step size (two double-precision pow) is computed by the last warp while the others reduce.
+constexpr int OPT_PF = 4;  // elements per thread held in registers across the reduction (covers len <= 4096 at 1024 threads)
+
+__device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, float* __restrict__ p, float* __restrict__ tg,
+                                                     float* __restrict__ mm, float* __restrict__ vv, long long len, int t,
+                                                     float grad_scale, float clip, double lr, double beta1, double beta2,
+                                                     float eps, float polyak, int do_polyak) {
   __shared__ float red[32];
   __shared__ float s_factor, s_lr_t;
-  const long long off = seg.off[blockIdx.x], len = seg.len[blockIdx.x];
-  float* g = grad + off;
+  const int nt = blockDim.x, tid = threadIdx.x;
+  if (tid == nt - 32)  // last warp, lane 0: overlaps with the loads / reduction of the other warps
+    s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+  float gr[OPT_PF], mr[OPT_PF], vr[OPT_PF], pr[OPT_PF], tr[OPT_PF];
+#pragma unroll
+  for (int k = 0; k < OPT_PF; ++k) {
+    const long long i = tid + (long long)k * nt;
+    const bool ok = i < len;
+    gr[k] = ok ? g[i] : 0.f;
+    mr[k] = ok ? mm[i] : 0.f;
+    vr[k] = ok ? vv[i] : 0.f;
+    pr[k] = ok ? p[i] : 0.f;
+    tr[k] = (ok && do_polyak) ? tg[i] : 0.f;
+  }
   // pass 1: ||scale * g||_2
   float ss = 0.f;
-  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+#pragma unroll
+  for (int k = 0; k < OPT_PF; ++k) {
+    const float x = gr[k] * grad_scale;
+    ss = fmaf(x, x, ss);
+  }
+  for (long long i = tid + (long long)OPT_PF * nt; i < len; i += nt) {
     const float x = g[i] * grad_scale;
     ss = fmaf(x, x, ss);
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  if (tid < 32) {
+    float s = tid < (nt >> 5) ? red[tid] : 0.f;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       const float norm = sqrtf(s);
       s_factor = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;  // tf.clip_by_norm: g * clip / max(||g||, clip)
-      const int t = *t_ptr;
-      s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
     }
   }
   __syncthreads();
@@ -50,11 +69,22 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
   const float lr_t = s_lr_t;
   const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2);
   const float opol = 1.0f - polyak;
-  float* p = param + off;
-  float* tg = target + off;
-  float* mm = m + off;
-  float* vv = v + off;
-  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+#pragma unroll
+  for (int k = 0; k < OPT_PF; ++k) {
+    const long long i = tid + (long long)k * nt;
+    if (i < len) {
+      const float gi = gr[k] * factor;
+      const float mi = b1 * mr[k] + ob1 * gi;
+      const float vi = b2 * vr[k] + ob2 * gi * gi;
+      const float pi = pr[k] - lr_t * mi / (sqrtf(vi) + eps);
+      mm[i] = mi;
+      vv[i] = vi;
+      p[i] = pi;
+      if (do_polyak) tg[i] = polyak * tr[k] + opol * pi;
+      g[i] = 0.f;  // the *_grads kernels accumulate with atomics: leave the bucket clean for the next round
+    }
+  }
+  for (long long i = tid + (long long)OPT_PF * nt; i < len; i += nt) {
     const float gi = g[i] * factor;
     const float mi = b1 * mm[i] + ob1 * gi;
     const float vi = b2 * vv[i] + ob2 * gi * gi;
@@ -63,8 +93,18 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
     vv[i] = vi;
     p[i] = pi;
     if (do_polyak) tg[i] = polyak * tg[i] + opol * pi;
-    g[i] = 0.f;  // the *_grads kernels accumulate with atomics: leave the bucket clean for the next round
+    g[i] = 0.f;
   }
+}
+
+__global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ param, float* __restrict__ target,
+                                                           float* __restrict__ grad, float* __restrict__ m,
+                                                           float* __restrict__ v, OptSeg seg, const int* __restrict__ t_ptr,
+                                                           float grad_scale, float clip, double lr, double beta1,
+                                                           double beta2, float eps, float polyak, int do_polyak) {
+  const long long off = seg.off[blockIdx.x], len = seg.len[blockIdx.x];
+  clip_adam_polyak_var(grad + off, param + off, target + off, m + off, v + off, len, *t_ptr, grad_scale, clip, lr, beta1, beta2,
+                       eps, polyak, do_polyak);
 }
 
 // all agents in one launch: grid = (6 variables, n_agents); pointers come from the device agent table
@@ -73,8 +113,6 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
                                                                float* __restrict__ v_base, const int* __restrict__ adam_t,
                                                                float grad_scale, float clip, double lr, double beta1,
                                                                double beta2, float eps, float polyak, int do_polyak) {
-  __shared__ float red[32];
-  __shared__ float s_factor, s_lr_t;
   const int j = blockIdx.y, var = blockIdx.x;
   const AgentDev& ag = agents[j];
   const MlpW& w = ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q];
@@ -86,43 +124,8 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
   const long long len = lens[var];
   float* g = ag.grad[which].W1 + off;
   const long long goff = g - grads_base;
-  float* p = const_cast<float*>(w.W1) + off;
-  float* tg = const_cast<float*>(wt.W1) + off;
-  float* mm = m_base + goff;
-  float* vv = v_base + goff;
-  float ss = 0.f;
-  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
-    const float x = g[i] * grad_scale;
-    ss = fmaf(x, x, ss);
-  }
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) {
-      const float norm = sqrtf(s);
-      s_factor = clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f;
-      const int t = adam_t[2 * j + which];
-      s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
-    }
-  }
-  __syncthreads();
-  const float factor = s_factor * grad_scale, lr_t = s_lr_t;
-  const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2);
-  const float opol = 1.0f - polyak;
-  for (long long i = threadIdx.x; i < len; i += blockDim.x) {
-    const float gi = g[i] * factor;
-    const float mi = b1 * mm[i] + ob1 * gi;
-    const float vi = b2 * vv[i] + ob2 * gi * gi;
-    const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
-    mm[i] = mi;
-    vv[i] = vi;
-    p[i] = pi;
-    if (do_polyak) tg[i] = polyak * tg[i] + opol * pi;
-    g[i] = 0.f;
-  }
+  clip_adam_polyak_var(g, const_cast<float*>(w.W1) + off, const_cast<float*>(wt.W1) + off, m_base + goff, v_base + goff, len,
+                       adam_t[2 * j + which], grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak);
 }
 
 }  // namespace mdp

@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j0, mdp_ring_
 // of the kernel never waits on global memory again.
 // =============================================================================================
 template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
+__global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                       const long long* __restrict__ ridx, const float* __restrict__ u_target,
                                                       int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
                                                       float* __restrict__ target_act_out, int XPf, long long idx_stride, long long y_stride) {
@@ -416,12 +416,15 @@ __global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j0, mdp_rin
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
-  const Grp G{(int)threadIdx.x, 0};
+  // the target actors are independent of each other: NG = blockDim / 256 thread groups run one actor each, concurrently
+  // (named barriers), then group 0 runs the target critic
+  const int NG = blockDim.x / NT, grp = threadIdx.x / NT;
+  const Grp G{(int)threadIdx.x % NT, NG > 1 ? grp + 1 : 0};
   SmemCarve sm(smem_raw);
   float* sXf = sm.take(TM * XPf);  // [next_obs_all | a'_all]
-  float* sH1 = sm.take(TM * HP);
-  float* sH2 = sm.take(TM * HP);
-  float* sL = sm.take(TM * KPAD);
+  float* sH1 = sm.take(NG * TM * HP) + grp * TM * HP;
+  float* sH2 = sm.take(NG * TM * HP) + grp * TM * HP;
+  float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
   float* sQ = sm.take(TM);
   float* sRD = sm.take(2 * TM);    // rew_j, done_j
   float* sNets = sm.p;
@@ -448,8 +451,8 @@ __global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j0, mdp_rin
     }
     bulk_g2s(q, me.net[MDP_NET_TARGET_Q].W1, net_floats_padded(me.net[MDP_NET_TARGET_Q].in, U, 1) * 4u, &bar);
   }
-  bulk_rows<TM>(G, sXf, XPf, batch, R, ridx, row0, nrows, L.nx_off, nx4, &bar);
-  for (int i = threadIdx.x; i < 2 * TM; i += NT) {
+  if (grp == 0) bulk_rows<TM>(G, sXf, XPf, batch, R, ridx, row0, nrows, L.nx_off, nx4, &bar);
+  for (int i = threadIdx.x; i < 2 * TM; i += blockDim.x) {
     const int r = i >> 1, which = i & 1;
     float v = 0.f;
     if (r < nrows) v = batch[(ridx ? ridx[row0 + r] : row0 + r) * R + (which ? L.dn_off : L.rw_off) + j];
@@ -465,17 +468,20 @@ __global__ void __launch_bounds__(NT) k_td_target_res(CoreDev C, int j0, mdp_rin
     const AgentDev& ag = C.agents[i];
     const MlpW w = net_at<U>(p, ag.obs_dim, ag.act_dim);
     p += net_floats_padded(ag.obs_dim, U, ag.act_dim);
+    if (i % NG != grp) continue;
     forward_hidden_res<U, TM>(G, sXf + ag.obs_off, XPf, w, sH1, sH2);
     actor_head<U, TM>(G, sH2, w, sL);
     gumbel_softmax_tile<TM>(G, sL, sXf + L.obs_sum + ag.act_off, XPf, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u_target,
                             u_stride, ag.act_off, row0, seed, counter, (uint32_t)(0x100 + i));
   }
+  if (NG > 1) __syncthreads();  // every group's a' is in the tile
   if (target_act_out) {
-    for (int idx = threadIdx.x; idx < nrows * C.act_sum; idx += NT) {
+    for (int idx = threadIdx.x; idx < nrows * C.act_sum; idx += blockDim.x) {
       const int r = idx / C.act_sum, c = idx - r * C.act_sum;
       target_act_out[(row0 + r) * u_stride + c] = sXf[r * XPf + L.obs_sum + c];
     }
   }
+  if (grp != 0) return;
   forward_hidden_res<U, TM>(G, sXf, XPf, tq, sH1, sH2);
   critic_head<U, TM>(G, sH2, tq, sQ);
   if (threadIdx.x < 32) {
@@ -958,6 +964,7 @@ struct ResPlan {
   bool ok;
   int XPf;                      // pitch of the X row tile
   size_t td, critic, actor;     // dynamic shared memory (bytes) of the three kernels
+  int td_groups;
 };
 
 static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
@@ -977,7 +984,8 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
     act_j = std::max(act_j, (size_t)net_floats_padded(c->cfg.obs_dim[i], U, c->cfg.act_dim[i]));
   }
   const size_t tile = r4((size_t)TMv * r.XPf);
-  r.td = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv * KPAD) + r4(TMv) + r4(2 * TMv) + actors + crit + 64) * 4;
+  r.td_groups = std::min(n, 3);  // concurrent target-actor groups of 256 threads (k_td_target_res)
+  r.td = (tile + r.td_groups * (2 * r4((size_t)TMv * HP) + r4(TMv * KPAD)) + r4(TMv) + r4(2 * TMv) + actors + crit + 64) * 4;
   r.critic = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv) + 32 + (size_t)U * U + crit + 64) * 4;
   r.actor = (tile + 4 * r4((size_t)TMv * HP) + 2 * r4(TMv * KPAD) + r4(TMv) + 2 * (size_t)U * U + crit + act_j + 64) * 4;
   const size_t limit = 200 * 1024;
@@ -1027,8 +1035,8 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
       auto kern = k_td_target_res<U, TMv>;
       int rc2 = set_smem(kern, rp.td);
       if (rc2) return rc2;
-      kern<<<dim3(cdiv(B, TMv), count), NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
-                                                         target_act_out, rp.XPf, idx_stride, y_stride);
+      kern<<<dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed,
+                                                                        counter, y_out, target_act_out, rp.XPf, idx_stride, y_stride);
       return check_launch("k_td_target_res");
     }
     auto kern = k_td_target<U, TMv, RES>;
