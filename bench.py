@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--rollout-mode", default="mega", choices=["mega", "graph", "eager"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-tensor-section", action="store_true")
+    ap.add_argument("--nccl-allreduce", action="store_true")
     return ap.parse_args()
 
 
@@ -247,7 +248,22 @@ def main():
     obs_shape_n = [env.observation_space[i].shape for i in range(env.n)]
     trainers = [MADDPGAgentTrainer("agent_%d" % i, None, obs_shape_n, env.action_space, i, arglist) for i in range(env.n)]
     core = trainers[0].core
-    dp = DataParallelUpdater(core)
+    # N > 1: the gradient all-reduce is fused into the clip+Adam+polyak kernel (peer loads over NVLink, PeerGradExchange),
+    # so update rounds are kernels only and replay from a CUDA graph; --nccl-allreduce keeps the NCCL collective path
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl"
+        if not args.nccl_allreduce:
+            try:
+                dp = DataParallelUpdater(core, peer=True)
+                exchange = "fused-peer"
+            except Exception as exc:  # symmetric memory unavailable: fall back to the NCCL collective
+                sys.stderr.write("peer exchange unavailable (%r), using NCCL all-reduce\n" % (exc,))
+                dp = DataParallelUpdater(core)
+        else:
+            dp = DataParallelUpdater(core)
+    else:
+        dp = DataParallelUpdater(core)
     dp.broadcast_params(core.params)
     roll = BatchedRollout(env, core, EP_LEN, mode=args.rollout_mode)
     env.reset()
@@ -332,7 +348,8 @@ def main():
     idx_pool = [[draw_idx() for _ in range(A)] for _ in range(8)]
     _, batch = core._scratch(BATCH)
 
-    gupd = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph) if world == 1 else None
+    fused = world == 1 or exchange == "fused-peer"
+    gupd = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph) if fused else None
 
     def update_round(r):
         if gupd is not None:  # single GPU: device-side index draw + gather + 5 update kernels per agent, graph-replayed
@@ -356,7 +373,7 @@ def main():
     upd_value = R * A * world / (upd_ms * 1e-3)
     # ---- (3b) grouped ("Jacobi") rounds: all agents per launch -- throughput mode, documented deviation ----------
     grp_value = grp_ms = None
-    if world == 1:
+    if fused:
         ggrp = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph, grouped=True)
         for r in range(3):
             ggrp.run(1)
@@ -368,8 +385,8 @@ def main():
             ggrp.run(1)
             b.record()
         barrier()
-        grp_ms = sum(a.elapsed_time(b) for a, b in gev)
-        grp_value = R * A / (grp_ms * 1e-3)
+        grp_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in gev))
+        grp_value = R * A * world / (grp_ms * 1e-3)
     clocks = sampler.stop()
 
     # ---- (4) end to end through the reference-shaped API with host buffers ------------------------------------
@@ -510,7 +527,8 @@ def main():
             "critic_updates": {"value": upd_value, "unit": "critic updates/s", "rounds": R, "ms_per_round": upd_ms / R,
                                "gpu_launches": int(launches_upd), "flops_per_round": flops_round,
                                "achieved_tflops": flops_round * R / (upd_ms * 1e-3) / 1e12,
-                               "allreduce_bytes_per_round": dp.allreduce_bytes // max(1, R + 3),
+                               "allreduce_bytes_per_round": 0 if world == 1 else 4 * int(core.layout.total_train),
+                               "gradient_exchange": exchange,
                                "order": "sequential agents (reference order, parity mode)",
                                "grouped": None if grp_value is None else {
                                    "value": grp_value, "unit": "critic updates/s", "ms_per_round": grp_ms / R,

@@ -216,6 +216,18 @@ int mdp_actor_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, i
 int mdp_clip_adam_polyak(mdp_core* core, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak,
                          void* stream);
 
+/* Multi-GPU, fused exchange: binds every rank's gradient buffer and flag words (mapped into this process, e.g. by
+ * torch.distributed._symmetric_memory; h_peer_grads[rank] must be the buffer given to mdp_core_bind) so that
+ * mdp_clip_adam_polyak[_all] sums the gradient over ranks itself -- peer loads over NVLink inside the clip+Adam+polyak
+ * kernel, flag barriers between the CTAs that own the same variable -- instead of expecting an all-reduced bucket.
+ * With peers bound grad_scale is still applied (pass 1/world).  flags: uint32 [6 * n_agents][8] per rank, zeroed;
+ * epoch_local: uint32 [6 * n_agents] device words of this rank, zeroed.  h_peer_recv (optional): every rank's low-latency
+ * receive buffer, uint32 pairs [2][world][total_train], zeroed -- when given, ranks PUSH (value, epoch) words into the peers'
+ * buffers and poll their own (one NVLink traversal, no barrier); when NULL the kernel uses flag barriers and peer loads.
+ * world <= 1 unbinds.  The gradient all-reduce is the only collective of the path. */
+int mdp_core_bind_peers(mdp_core* core, int32_t world, int32_t rank, const void* const* h_peer_grads, void* const* h_peer_flags,
+                        uint32_t* epoch_local, void* const* h_peer_recv);
+
 /* MADDPGAgentTrainer.update body for agent j on one stream (maddpg.py:181-194), single GPU:
  * td_target -> critic_grads -> clip_adam(Q) -> actor_grads -> clip_adam(P) + polyak(P) + polyak(Q). */
 int mdp_update_agent(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,

@@ -43,6 +43,13 @@ struct mdp_core {
   mdp::AgentDev* d_agents = nullptr;
   const unsigned long long* ctl = nullptr;
   std::vector<mdp::AgentDev> h_agents;
+  // peer (NVLink) gradient exchange: every rank's gradient bucket and flag words, mapped into this process
+  int peer_world = 0, peer_rank = 0;
+  const float* const* d_peer_grads = nullptr;  // device array [world] of gradient-buffer bases
+  unsigned* const* d_peer_flags = nullptr;     // device array [world] of flag-word bases
+  unsigned* peer_epoch = nullptr;              // local epoch counters, one per (agent, variable) slot
+  uint2* const* d_peer_recv = nullptr;         // device array [world] of low-latency receive buffers (or null: barrier mode)
+  void* d_peer_tables = nullptr;
   int tc_mode = 0;                 // tensor-core (tcgen05) kernels: 0 auto, 1 always where supported, -1 never
   float* tc_scratch = nullptr;     // sampled-action tiles of the tensor-core TD-target kernel when they exceed shared memory
   size_t tc_scratch_bytes = 0;

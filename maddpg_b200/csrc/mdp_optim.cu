@@ -21,14 +21,113 @@ struct OptSeg {
 // on the serial path of every agent update), so the second pass's operands (m, v, param, target) are loaded BEFORE the norm
 // reduction, and the bias-corrected step size (two double-precision pow) is computed by the last warp while the others reduce.
 constexpr int OPT_PF = 4;  // elements per thread held in registers across the reduction (covers len <= 4096 at 1024 threads)
+constexpr int PEER_MAXW = 8;  // flag words per slot: one per rank of an 8-GPU box
+
+// Fused all-reduce: when `world` > 1 the gradient of element i is the sum over ranks r = 0..world-1 (fixed order, so every
+// replica computes bit-identical parameters) of peer_grads[r][goff + i], read straight from the peers' HBM over NVLink
+// (buffers mapped by torch's symmetric memory).  Two flag barriers per CTA, scoped to the CTAs that own the same variable
+// on every rank: (1) before the reads -- a rank's flag implies its gradient kernels are complete (stream order);
+// (2) after the reads -- only then may a rank zero its own bucket.  Flags carry a monotonically growing epoch, so the
+// kernel is replayable from a CUDA graph without host involvement.
+//
+// Low-latency mode (recv != null; the default for the small MADDPG buckets): instead of barrier + pull, every rank PUSHES
+// its gradient values into the peers' receive buffers as 8-byte (value, epoch) words -- one posted NVLink store per element
+// and peer -- and each rank polls its own receive buffer until the epoch tag matches: data and flag travel together (the
+// protocol NCCL calls LL), so the exchange costs one NVLink traversal, no barrier, no fence, and a rank may zero its own
+// bucket immediately because nobody reads it remotely.  Receive buffers are double-buffered by epoch parity: a peer can run
+// at most one launch ahead of the slowest rank for a given variable.
+struct PeerCtx {
+  int world, rank;
+  const float* const* grads;  // [world] bases of the ranks' flat gradient buffers
+  unsigned* const* flags;     // [world] bases of the ranks' flag words ([slot][PEER_MAXW])
+  unsigned* epoch;            // local per-slot epoch counters
+  uint2* const* recv;         // [world] bases of the receive buffers [parity][source rank][total] of (value bits, epoch)
+  long long total;            // floats in the flat gradient buffer
+};
+
+__device__ __forceinline__ void ll_push(const PeerCtx& P, long long goff, long long i, float x, unsigned epoch) {
+  const long long at = ((long long)((epoch & 1u) * P.world + P.rank)) * P.total + goff + i;
+  for (int r = 0; r < P.world; ++r) {
+    if (r == P.rank) continue;
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(P.recv[r] + at), "r"(__float_as_uint(x)), "r"(epoch) : "memory");
+  }
+}
+// sum over ranks in rank order: own value from registers, the peers' from this rank's receive buffer (spins on the epoch tag)
+__device__ __forceinline__ float ll_sum(const PeerCtx& P, long long goff, long long i, float own, unsigned epoch) {
+  float s = 0.f;
+  for (int r = 0; r < P.world; ++r) {
+    if (r == P.rank) { s += own; continue; }
+    const uint2* src = P.recv[P.rank] + ((long long)((epoch & 1u) * P.world + r)) * P.total + goff + i;
+    unsigned v, e;
+    long long t0 = 0;
+    for (unsigned spins = 1;; ++spins) {
+      asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+      if (e == epoch) break;
+      if ((spins & 255u) == 0) {  // a missing peer must fail loudly (~4 s), never hang the box
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 8000000000ll) __trap();
+      }
+    }
+    s += __uint_as_float(v);
+  }
+  return s;
+}
+
+// flag = epoch on every peer (posted NVLink stores); relaxed: what the flag publishes is already complete when it is written
+// (gradient kernels finished in stream order / peer loads consumed by the norm reduction)
+__device__ __forceinline__ void peer_signal(const PeerCtx& P, int slot, unsigned epoch) {
+  if ((int)threadIdx.x < P.world) {
+    unsigned* dst = P.flags[threadIdx.x] + slot * PEER_MAXW + P.rank;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+  }
+}
+// every peer's flag in this rank's flag words has reached epoch (ends with a CTA barrier)
+__device__ __forceinline__ void peer_wait(const PeerCtx& P, int slot, unsigned epoch) {
+  if ((int)threadIdx.x < P.world) {
+    const unsigned* src = P.flags[P.rank] + slot * PEER_MAXW + threadIdx.x;
+    long long t0 = 0;
+    for (unsigned spins = 1;; ++spins) {
+      unsigned v;
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if ((spins & 255u) == 0) {  // a missing peer must fail loudly (~4 s), never hang the box
+        if (t0 == 0) t0 = clock64();
+        else if (clock64() - t0 > 8000000000ll) __trap();
+      }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float peer_grad(const PeerCtx& P, const float* g_local, long long goff, long long i) {
+  if (P.world <= 1) return g_local[i];
+  float s = 0.f;
+  for (int r = 0; r < P.world; ++r) s += __ldcv(P.grads[r] + goff + i);
+  return s;
+}
 
 __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, float* __restrict__ p, float* __restrict__ tg,
                                                      float* __restrict__ mm, float* __restrict__ vv, long long len, int t,
                                                      float grad_scale, float clip, double lr, double beta1, double beta2,
-                                                     float eps, float polyak, int do_polyak) {
+                                                     float eps, float polyak, int do_polyak, const PeerCtx& P, long long goff,
+                                                     int slot) {
   __shared__ float red[32];
   __shared__ float s_factor, s_lr_t;
   const int nt = blockDim.x, tid = threadIdx.x;
+  unsigned epoch = 0;
+  const bool small = len <= (long long)OPT_PF * nt;  // every peer read of this variable fits the register prefetch
+  const bool ll = P.world > 1 && P.recv != nullptr;
+  if (P.world > 1) {
+    epoch = P.epoch[slot] + (ll ? 1u : 1u);  // barrier mode uses epoch ("my gradients are complete") and epoch + 1 ("I have read yours")
+    if (ll) {
+      // push this rank's values first (posted stores), then everything below overlaps their flight
+      for (long long i = tid; i < len; i += nt) ll_push(P, goff, i, g[i], epoch);
+    } else {
+      peer_signal(P, slot, epoch);
+      peer_wait(P, slot, epoch);
+    }
+  }
   if (tid == nt - 32)  // last warp, lane 0: overlaps with the loads / reduction of the other warps
     s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
   float gr[OPT_PF], mr[OPT_PF], vr[OPT_PF], pr[OPT_PF], tr[OPT_PF];
@@ -36,11 +135,18 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
   for (int k = 0; k < OPT_PF; ++k) {
     const long long i = tid + (long long)k * nt;
     const bool ok = i < len;
-    gr[k] = ok ? g[i] : 0.f;
+    gr[k] = !ok ? 0.f : ll ? g[i] : peer_grad(P, g, goff, i);
     mr[k] = ok ? mm[i] : 0.f;
     vr[k] = ok ? vv[i] : 0.f;
     pr[k] = ok ? p[i] : 0.f;
     tr[k] = (ok && do_polyak) ? tg[i] : 0.f;
+  }
+  if (ll) {
+#pragma unroll
+    for (int k = 0; k < OPT_PF; ++k) {
+      const long long i = tid + (long long)k * nt;
+      if (i < len) gr[k] = ll_sum(P, goff, i, gr[k], epoch);
+    }
   }
   // pass 1: ||scale * g||_2
   float ss = 0.f;
@@ -50,12 +156,13 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
     ss = fmaf(x, x, ss);
   }
   for (long long i = tid + (long long)OPT_PF * nt; i < len; i += nt) {
-    const float x = g[i] * grad_scale;
+    const float x = (ll ? ll_sum(P, goff, i, g[i], epoch) : peer_grad(P, g, goff, i)) * grad_scale;
     ss = fmaf(x, x, ss);
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   if ((tid & 31) == 0) red[tid >> 5] = ss;
-  __syncthreads();
+  __syncthreads();  // every thread's peer loads have returned (their values fed the reduction)
+  if (P.world > 1 && !ll && small) peer_signal(P, slot, epoch + 1u);  // early: the peers' wait overlaps this rank's Adam math
   if (tid < 32) {
     float s = tid < (nt >> 5) ? red[tid] : 0.f;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -81,11 +188,11 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
       vv[i] = vi;
       p[i] = pi;
       if (do_polyak) tg[i] = polyak * tr[k] + opol * pi;
-      g[i] = 0.f;  // the *_grads kernels accumulate with atomics: leave the bucket clean for the next round
+      if (P.world <= 1 || ll) g[i] = 0.f;  // the *_grads kernels accumulate with atomics: leave the bucket clean for the next round
     }
   }
   for (long long i = tid + (long long)OPT_PF * nt; i < len; i += nt) {
-    const float gi = g[i] * factor;
+    const float gi = (ll ? ll_sum(P, goff, i, g[i], epoch) : peer_grad(P, g, goff, i)) * factor;
     const float mi = b1 * mm[i] + ob1 * gi;
     const float vi = b2 * vv[i] + ob2 * gi * gi;
     const float pi = p[i] - lr_t * mi / (sqrtf(vi) + eps);
@@ -93,7 +200,18 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
     vv[i] = vi;
     p[i] = pi;
     if (do_polyak) tg[i] = polyak * tg[i] + opol * pi;
-    g[i] = 0.f;
+    if (P.world <= 1 || ll) g[i] = 0.f;
+  }
+  if (ll) {
+    if (tid == 0) P.epoch[slot] = epoch;
+  } else if (P.world > 1) {
+    if (!small) {
+      __syncthreads();
+      peer_signal(P, slot, epoch + 1u);
+    }
+    peer_wait(P, slot, epoch + 1u);  // every rank has read this bucket
+    for (long long i = tid; i < len; i += nt) g[i] = 0.f;
+    if (tid == 0) P.epoch[slot] = epoch + 1u;
   }
 }
 
@@ -101,10 +219,11 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
                                                            float* __restrict__ grad, float* __restrict__ m,
                                                            float* __restrict__ v, OptSeg seg, const int* __restrict__ t_ptr,
                                                            float grad_scale, float clip, double lr, double beta1,
-                                                           double beta2, float eps, float polyak, int do_polyak) {
+                                                           double beta2, float eps, float polyak, int do_polyak, PeerCtx P,
+                                                           long long goff_net, int slot0) {
   const long long off = seg.off[blockIdx.x], len = seg.len[blockIdx.x];
   clip_adam_polyak_var(grad + off, param + off, target + off, m + off, v + off, len, *t_ptr, grad_scale, clip, lr, beta1, beta2,
-                       eps, polyak, do_polyak);
+                       eps, polyak, do_polyak, P, goff_net + off, slot0 + blockIdx.x);
 }
 
 // all agents in one launch: grid = (6 variables, n_agents); pointers come from the device agent table
@@ -112,7 +231,7 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
                                                                float* __restrict__ grads_base, float* __restrict__ m_base,
                                                                float* __restrict__ v_base, const int* __restrict__ adam_t,
                                                                float grad_scale, float clip, double lr, double beta1,
-                                                               double beta2, float eps, float polyak, int do_polyak) {
+                                                               double beta2, float eps, float polyak, int do_polyak, PeerCtx P) {
   const int j = blockIdx.y, var = blockIdx.x;
   const AgentDev& ag = agents[j];
   const MlpW& w = ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q];
@@ -125,19 +244,56 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
   float* g = ag.grad[which].W1 + off;
   const long long goff = g - grads_base;
   clip_adam_polyak_var(g, const_cast<float*>(w.W1) + off, const_cast<float*>(wt.W1) + off, m_base + goff, v_base + goff, len,
-                       adam_t[2 * j + which], grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak);
+                       adam_t[2 * j + which], grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak, P, goff, 6 * j + var);
 }
 
 }  // namespace mdp
 
 using namespace mdp;
 
+static PeerCtx peer_ctx(const mdp_core* c) {
+  PeerCtx P;
+  P.world = c->peer_world; P.rank = c->peer_rank;
+  P.grads = c->d_peer_grads; P.flags = c->d_peer_flags; P.epoch = c->peer_epoch;
+  P.recv = c->d_peer_recv; P.total = c->lay.total_train;
+  return P;
+}
+
+extern "C" int mdp_core_bind_peers(mdp_core* c, int32_t world, int32_t rank, const void* const* h_peer_grads,
+                                   void* const* h_peer_flags, uint32_t* epoch_local, void* const* h_peer_recv) {
+  MDP_REQUIRE(c, "mdp_core_bind_peers: null core");
+  if (c->d_peer_tables) cudaFree(c->d_peer_tables);
+  c->d_peer_tables = nullptr;
+  c->peer_world = 0;
+  c->d_peer_recv = nullptr;
+  if (world <= 1) return MDP_OK;
+  MDP_REQUIRE(world <= PEER_MAXW && rank >= 0 && rank < world && h_peer_grads && h_peer_flags && epoch_local,
+              "mdp_core_bind_peers: bad argument (world %d, rank %d)", world, rank);
+  MDP_REQUIRE(h_peer_grads[rank] == (const void*)c->grads,
+              "mdp_core_bind_peers: this rank's peer entry must be the gradient buffer bound with mdp_core_bind");
+  void* tab = nullptr;
+  MDP_CUDA(cudaMalloc(&tab, 3 * world * sizeof(void*)));
+  if (h_peer_recv) {
+    MDP_CUDA(cudaMemcpy((char*)tab + 2 * world * sizeof(void*), h_peer_recv, world * sizeof(void*), cudaMemcpyHostToDevice));
+    c->d_peer_recv = reinterpret_cast<uint2* const*>((char*)tab + 2 * world * sizeof(void*));
+  }
+  MDP_CUDA(cudaMemcpy(tab, h_peer_grads, world * sizeof(void*), cudaMemcpyHostToDevice));
+  MDP_CUDA(cudaMemcpy((char*)tab + world * sizeof(void*), h_peer_flags, world * sizeof(void*), cudaMemcpyHostToDevice));
+  c->d_peer_tables = tab;
+  c->d_peer_grads = reinterpret_cast<const float* const*>(tab);
+  c->d_peer_flags = reinterpret_cast<unsigned* const*>((char*)tab + world * sizeof(void*));
+  c->peer_epoch = epoch_local;
+  c->peer_world = world;
+  c->peer_rank = rank;
+  return MDP_OK;
+}
+
 extern "C" int mdp_clip_adam_polyak_all(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_clip_adam_polyak_all: core not bound");
   MDP_REQUIRE(which == 0 || which == 1, "mdp_clip_adam_polyak_all: bad argument");
   k_clip_adam_polyak_all<<<dim3(6, c->cfg.n_agents), 1024, 0, (cudaStream_t)stream>>>(
       c->d_agents, which, c->cfg.num_units, c->grads, c->adam_m, c->adam_v, c->adam_t, grad_scale, (float)c->cfg.grad_clip,
-      c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, do_polyak);
+      c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, do_polyak, peer_ctx(c));
   return check_launch("k_clip_adam_polyak_all");
 }
 
@@ -165,6 +321,6 @@ extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, f
   k_clip_adam_polyak<<<6, 1024, 0, (cudaStream_t)stream>>>(param, target, grad, m, v, seg, c->adam_t + 2 * agent + which,
                                                            grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
                                                            c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak,
-                                                           do_polyak);
+                                                           do_polyak, peer_ctx(c), c->lay.train_off[agent][which], 6 * agent);
   return check_launch("k_clip_adam_polyak");
 }

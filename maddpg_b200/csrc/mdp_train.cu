@@ -876,6 +876,7 @@ extern "C" void mdp_core_destroy(mdp_core* core) {
   if (core->d_agents) cudaFree(core->d_agents);
   if (core->tc_scratch) cudaFree(core->tc_scratch);
   if (core->tc_arena) cudaFree(core->tc_arena);
+  if (core->d_peer_tables) cudaFree(core->d_peer_tables);
   delete core;
 }
 
@@ -1164,9 +1165,10 @@ extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layou
   if (rc) return rc;
   rc = mdp_critic_grads(c, agent, lay, B, batch, idx, y_scratch, nullptr, stream);
   if (rc) return rc;
-  rc = mdp_clip_adam_polyak(c, agent, 1, 1.0f, 1, stream);
+  const float scale = c->peer_world > 1 ? 1.0f / (float)c->peer_world : 1.0f;  // fused peer all-reduce (mdp_core_bind_peers)
+  rc = mdp_clip_adam_polyak(c, agent, 1, scale, 1, stream);
   if (rc) return rc;
   rc = mdp_actor_grads(c, agent, lay, B, batch, idx, u_actor, u_stride, seed, counter, stream);
   if (rc) return rc;
-  return mdp_clip_adam_polyak(c, agent, 0, 1.0f, 1, stream);
+  return mdp_clip_adam_polyak(c, agent, 0, scale, 1, stream);
 }

@@ -12,8 +12,12 @@ j flows through the critic AFTER its Adam step, so one agent update needs two al
 (critic bucket, then actor bucket); per-variable clip_by_norm acts on the REDUCED gradient
 (grad_scale = 1/world_size inside the fused clip+Adam+polyak kernel).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_range(total, rank, world):
@@ -27,15 +31,68 @@ def rank_seed(seed, rank):
     return int(seed) + int(rank)
 
 
-class DataParallelUpdater(object):
-    """Drives MADDPGCore's split update entry points with an all-reduce between gradient and step."""
+class PeerGradExchange(object):
+    """Fused gradient exchange over NVLink peer memory (include/maddpg_b200.h: mdp_core_bind_peers).
 
-    def __init__(self, core=None, group=None, grads=None, segment_fn=None):
+    The core's gradient bucket is re-homed in a symmetric-memory allocation that every rank of the node maps
+    (torch.distributed._symmetric_memory); the clip+Adam+polyak kernel then sums the bucket over ranks itself with
+    peer loads and flag barriers, so an update round has NO separate collective launch and no host synchronisation --
+    it can be captured in a CUDA graph.  Replicas stay bit-identical (fixed summation order)."""
+
+    SLOT_WORDS = 8
+
+    LL_MAX_FLOATS = 1 << 21  # low-latency push mode up to 2 M gradient floats (receive buffers: 16 B x world per float)
+
+    def __init__(self, core, group=None, low_latency=None):
+        import torch.distributed._symmetric_memory as symm
+        self.core = core
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = core.device
+        n = int(core.layout.total_train)
+        self.grads = symm.empty(n, dtype=torch.float32, device=dev)
+        self.flags = symm.empty(6 * core.n * self.SLOT_WORDS, dtype=torch.int32, device=dev)
+        self.grads.zero_()
+        self.flags.zero_()
+        self.gh = symm.rendezvous(self.grads, group)
+        self.fh = symm.rendezvous(self.flags, group)
+        self.epoch = torch.zeros(6 * core.n, dtype=torch.int32, device=dev)
+        self.low_latency = (n <= self.LL_MAX_FLOATS) if low_latency is None else bool(low_latency)
+        self.recv = self.rh = None
+        if self.low_latency:
+            self.recv = symm.empty(2 * self.world * n * 2, dtype=torch.int32, device=dev)
+            self.recv.zero_()
+            self.rh = symm.rendezvous(self.recv, group)
+        # re-home the gradient bucket: same layout, symmetric allocation
+        core.grads = self.grads
+        _lib.check(_lib.lib.mdp_core_bind(core._h, _lib.ptr(core.params), _lib.ptr(core.grads), _lib.ptr(core.adam_m),
+                                          _lib.ptr(core.adam_v), _lib.ptr(core.adam_t), _lib.ptr(core.stats)), "mdp_core_bind")
+        gp = (C.c_void_p * self.world)(*[int(p) for p in self.gh.buffer_ptrs])
+        fp = (C.c_void_p * self.world)(*[int(p) for p in self.fh.buffer_ptrs])
+        assert int(self.gh.buffer_ptrs[self.rank]) == self.grads.data_ptr()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)  # every rank's buckets and flags are zero before anyone signals
+        rp = (C.c_void_p * self.world)(*[int(p) for p in self.rh.buffer_ptrs]) if self.low_latency else None
+        _lib.check(_lib.lib.mdp_core_bind_peers(core._h, self.world, self.rank, gp, fp, _lib.ptr(self.epoch), rp), "mdp_core_bind_peers")
+        core.peer_world = self.world
+
+    def close(self):
+        self.core.peer_world = 1
+        _lib.check(_lib.lib.mdp_core_bind_peers(self.core._h, 1, 0, None, None, None, None), "mdp_core_bind_peers")
+
+
+class DataParallelUpdater(object):
+    """Drives MADDPGCore's split update entry points with an all-reduce between gradient and step.
+    ``peer=True`` (NCCL process group on one NVLink node): the all-reduce is fused into the clip+Adam+polyak kernel
+    (PeerGradExchange) and ``update_agent`` issues kernels only."""
+
+    def __init__(self, core=None, group=None, grads=None, segment_fn=None, peer=False, low_latency=None):
         self.core = core
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.allreduce_bytes = 0
+        self.peer = PeerGradExchange(core, group, low_latency) if (peer and self.world > 1) else None
 
     def broadcast_params(self, params, adam_m=None, adam_v=None):
         """Replicas start from rank 0's weights (the reference initialises once, train.py:89)."""
@@ -53,6 +110,15 @@ class DataParallelUpdater(object):
     def update_agent(self, j, batch, u_target=None, u_actor=None, idx=None):
         c = self.core
         scale = 1.0 / self.world
+        if self.peer is not None:  # gradient sum over ranks happens inside the clip+Adam+polyak kernels
+            y = c.td_target(j, batch, u_target, idx=idx)
+            c.critic_grads(j, batch, y, idx=idx)
+            c.clip_adam_polyak(j, 1, grad_scale=scale)
+            c.actor_grads(j, batch, u_actor, idx=idx)
+            c.clip_adam_polyak(j, 0, grad_scale=scale)
+            seg = c.train_segment(c.grads, j, 1).numel() + c.train_segment(c.grads, j, 0).numel()
+            self.allreduce_bytes += 4 * seg
+            return
         y = c.td_target(j, batch, u_target, idx=idx)
         c.critic_grads(j, batch, y, idx=idx)
         self.allreduce_sum(c.train_segment(c.grads, j, 1))

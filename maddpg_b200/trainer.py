@@ -260,13 +260,15 @@ class MADDPGCore(object):
                                              self.next_counter() if counter is None else counter, _lib.ptr(y),
                                              _lib.current_stream()), "mdp_update_agent")
 
-    def update_all(self, batch, idx=None, counter=None, grad_scale=1.0):
+    def update_all(self, batch, idx=None, counter=None, grad_scale=None):
         """Grouped ("Jacobi") round for all agents in five launches (include/maddpg_b200.h: mdp_update_all).
         idx: None, (B,) shared index set or (n_agents, B) per-agent sets (int64 CUDA)."""
         if idx is None:
             B, stride = batch.shape[0], 0
         else:
             B, stride = idx.shape[-1], (idx.stride(0) if idx.dim() == 2 else 0)
+        if grad_scale is None:  # fused peer all-reduce bound (PeerGradExchange): average over ranks
+            grad_scale = 1.0 / getattr(self, "peer_world", 1)
         key = ("all", B)
         if key not in self._y:
             self._y[key] = torch.empty((self.n, B), dtype=torch.float32, device=self.device)

@@ -29,7 +29,7 @@ def _rows(core, B, seed):
     return batch
 
 
-def _worker(rank, world, port, B, out):
+def _worker(rank, world, port, B, out, peer=False, low_latency=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -37,16 +37,21 @@ def _worker(rank, world, port, B, out):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from maddpg_b200.distributed import DataParallelUpdater
     core = _build_core(dev, B)
-    dp = DataParallelUpdater(core)
+    dp = DataParallelUpdater(core, peer=peer, low_latency=low_latency)
     dp.broadcast_params(core.params)
     full = _rows(core, world * B, 1)
     ut = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(2)).clamp_(1e-6, 1 - 1e-6)
     ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6)
     sl = slice(rank * B, (rank + 1) * B)
-    for j in range(3):
-        dp.update_agent(j, full[sl].contiguous().to(dev), ut[sl].contiguous().to(dev), ua[sl].contiguous().to(dev))
+    for rnd in range(2 if peer else 1):  # two rounds: the flag epochs and the re-zeroed buckets are exercised
+        for j in range(3):
+            dp.update_agent(j, full[sl].contiguous().to(dev), ut[sl].contiguous().to(dev), ua[sl].contiguous().to(dev))
     torch.cuda.synchronize()
     out[rank] = core.params.cpu().numpy()
+    if peer:
+        assert float(core.grads.abs().max()) == 0.0
+        dist.barrier()
+        dp.peer.close()
     dist.destroy_process_group()
 
 
@@ -67,3 +72,25 @@ def test_two_rank_update_matches_union_batch():
         core.update_agent(j, full, ut, ua)
     ref = core.params.cpu().numpy()
     np.testing.assert_allclose(p0, ref, rtol=2e-3, atol=3e-4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("low_latency", [True, False])
+def test_two_rank_peer_exchange_matches_union_batch(low_latency):
+    """Fused peer-memory all-reduce inside the clip+Adam+polyak kernel, both protocols (low-latency push of (value, epoch)
+    words / flag barriers + peer loads): identical replicas after two rounds (epochs, re-zeroed buckets), matching a
+    single-process update on the union batch."""
+    B, world = 256, 2
+    mgr = mp.Manager()
+    out_p, out_n = mgr.dict(), mgr.dict()
+    mp.spawn(_worker, args=(world, 29900 + os.getpid() % 500 + int(low_latency), B, out_p, True, low_latency), nprocs=world, join=True)
+    assert np.array_equal(out_p[0], out_p[1]), "replicas diverged (peer exchange)"
+    # reference: a single process on the union batch (mean over 2B rows == average of the two rank-local means)
+    core = _build_core(torch.device("cuda", 0), B)
+    full = _rows(core, world * B, 1).cuda()
+    ut = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(2)).clamp_(1e-6, 1 - 1e-6).cuda()
+    ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6).cuda()
+    for rnd in range(2):
+        for j in range(3):
+            core.update_agent(j, full, ut, ua)
+    np.testing.assert_allclose(out_p[0], core.params.cpu().numpy(), rtol=3e-3, atol=5e-4)
