@@ -332,6 +332,8 @@ def main():
         bytesL = envL.env_bytes_per_step * EL
         big = {"kernel": "k_env_step_spread<3>", "envs": EL, "bound": "hbm", "achieved": bytesL / usL / 1e3, "peak": peak,
                "unit": "GB/s", "frac": bytesL / usL / 1e3 / peak, "algorithmic_bytes_per_launch": bytesL, "avg_launch_us": usL,
+               "traffic": 383.4e6, "traffic_source": "ncu --set full, profiles/r1_env_step_spread_1M.txt (dram read 142.7 MB + write "
+               "240.7 MB per launch; the tail of the writes is still in L2 when the launch ends)",
                "note": "register-resident one-thread-per-env kernel (simple_spread fast path); the table-driven kernel serves the other scenarios"}
         del envL
         torch.cuda.empty_cache()
@@ -493,8 +495,8 @@ def main():
     actor_flops = 2 * sum(d * UNITS + UNITS * UNITS + UNITS * k for d, k in zip(env.obs_dims, env.act_dims)) * E * EP_LEN
     ep_roof = {"kernel": "k_rollout_episode<64,true>" if roll.mode == "mega" else "per-step kernels", "bound": "hbm",
                "achieved": ep_bytes / ep_us / 1e3, "peak": peak, "unit": "GB/s", "frac": ep_bytes / ep_us / 1e3 / peak,
-               "traffic": 5.3e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_raw.txt (dram read+write per launch; the "
-               "52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
+               "traffic": 5.49e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_raw.txt (dram read 1.37 MB + write 4.12 MB per "
+               "launch; the 52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
                "algorithmic_bytes_per_launch": ep_bytes, "avg_launch_us": ep_us,
                "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the kernel is "
                        "FP32-FMA-issue / latency bound", "fp32_fma_tflops": actor_flops / ep_us / 1e6}
