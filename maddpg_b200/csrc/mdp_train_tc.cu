@@ -70,8 +70,9 @@ __device__ __forceinline__ void named_sync() { asm volatile("bar.sync 1, 256;" :
 // every tensor-core launch): per net, W1^T as nchunks x [hi | lo] chunk images of [U][32] and W2^T as a [hi | lo]
 // pair of [U][U] images, already in the SWIZZLE_128B byte order, so one cp.async.bulk drops them into place.
 struct NetImg {
-  const unsigned char* w1;
-  const unsigned char* w2;
+  const unsigned char* w1;   // W1^T chunk images: nchunks x [hi | lo] of [U][32]
+  const unsigned char* w2;   // W2^T image pair [u2][k1]   (B operand of h1 W2)
+  const unsigned char* w2n;  // W2 image pair [k1][u2]     (B operand of dz2 W2^T, the backward pass)
 };
 struct AgentImg {
   NetImg net[4];
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256) k_build_images(CoreDev C, const AgentImg*
   const MlpW w = C.agents[agent].net[net];
   unsigned char* w1 = const_cast<unsigned char*>(imgs[agent].net[net].w1);
   unsigned char* w2 = const_cast<unsigned char*>(imgs[agent].net[net].w2);
+  unsigned char* w2n = const_cast<unsigned char*>(imgs[agent].net[net].w2n);
   const int nchunks = (w.in + 31) / 32;
   const long long n1 = (long long)nchunks * 32 * U, n2 = (long long)U * U;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n1 + n2; t += (long long)gridDim.x * blockDim.x) {
@@ -101,6 +103,9 @@ __global__ void __launch_bounds__(256) k_build_images(CoreDev C, const AgentImg*
       const int e = (int)(t - n1), u2 = e % U, k1 = e / U;
       umma::split_tf32(w.W2[e], hi, lo);
       unsigned char* dst = w2 + (size_t)(k1 >> 5) * L::W_IMG + umma::sw128_off(u2, k1 & 31);
+      *reinterpret_cast<float*>(dst) = hi;
+      *reinterpret_cast<float*>(dst + L::W2_IMG) = lo;
+      dst = w2n + (size_t)(u2 >> 5) * L::W_IMG + umma::sw128_off(k1, u2 & 31);
       *reinterpret_cast<float*>(dst) = hi;
       *reinterpret_cast<float*>(dst + L::W2_IMG) = lo;
     }
@@ -511,6 +516,382 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
 }
 
+
+// =============================================================================================================
+// Fused critic forward + MSE + backward on tensor cores (q_train, maddpg.py:75-100), maddpg-mode critics, U = 64.
+//   forward   z1 = X W1            A = X (TMEM, gathered rows), B = W1^T chunk images (TMA)        -> acc1
+//             z2 = h1 W2           A = h1 (TMEM),               B = W2^T images (TMA)              -> acc2
+//   backward  dW2 = h1^T dz2       A = h1, B = dz2: MN-major SWIZZLE_128B_BASE32B smem images       -> acc1 (M = 64)
+//             dh1 = dz2 W2^T       A = dz2 (TMEM),              B = W2 images (TMA)                 -> acc2
+//             dW1^T = dz1^T X      A = dz1 (MN-major smem), B = X chunk (MN-major smem), per chunk  -> ring of 32-col slots
+// Every GEMM is 3xTF32.  Bias / W3 gradients and the loss are row-local register code plus a 31-shuffle column sum.
+// Weight-gradient tiles leave TMEM as fp32 RED atomics into the flat gradient bucket (8x fewer than the 16-row SIMT tiles).
+// Shared memory regions are recycled by phase: R1 = W1^T slots -> dz2 images -> X chunk slots; R2 = W2^T -> W2;
+// R3 = h1 images -> dz1 images.
+// =============================================================================================================
+template <int U>
+struct LayB {
+  using L = Lay<U>;
+  static constexpr uint32_t ACT_IMG = TMR * 128 * (U / 32);  // [128 rows][U] MN-major image            32 KB
+  static constexpr uint32_t XS_IMG = TMR * 128;               // [128 rows][32] MN-major X chunk image   16 KB
+  static constexpr uint32_t R1 = 0, R2 = L::OFF_W2, R3 = L::OFF_W2 + 2 * L::W2_IMG;
+  static constexpr uint32_t OFF_MISC = R3 + 2 * ACT_IMG;
+  static constexpr int MISC_FLOATS = U + U + U + 16 + 3 * TMR + 2 * TMR;  // b1 b2 W3 b3 | part dq y | rowoff
+  static_assert(2 * ACT_IMG <= NS * 2 * L::W_IMG, "dz2 images must fit the W1^T slot region");
+  static constexpr uint32_t T_DW = L::T_X;  // dW1 chunk accumulators: 4 slots x 32 columns
+};
+
+struct BarsB {
+  unsigned long long stage_w[NS], stage_x[NS], stage_free[NS];
+  unsigned long long w2_full, h1_full, acc, l2_done, w2n_full, dz2_full, dz1_full;
+  unsigned long long xs_full[2], xs_free[2], dw_full[4], dw_free[4];
+};
+
+// lane l returns the sum over the warp's 32 lanes of v[l] (butterfly transpose-reduce, 31 shuffles); v is clobbered
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = up ? v[i + s] : v[i];
+      const float send = up ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// D (+)= A * B^T, both operands MN-major smem image pairs (hi at +0, lo at +lo_off), k-step = 8 image rows = 1024 bytes
+template <int M, int N, int NSTEPS>
+__device__ __forceinline__ void issue_3x_mn(uint32_t tacc, uint32_t a_img, uint32_t a_lo_off, uint32_t a_panel, uint32_t b_img,
+                                            uint32_t b_lo_off, uint32_t b_panel) {
+  constexpr uint32_t idesc = umma::idesc_tf32(M, N, 1, 1);
+  const uint64_t ah = umma::desc_mn(a_img, a_panel, 0), al = umma::desc_mn(a_img + a_lo_off, a_panel, 0);
+  const uint64_t bh = umma::desc_mn(b_img, b_panel, 0), bl = umma::desc_mn(b_img + b_lo_off, b_panel, 0);
+#pragma unroll
+  for (int s = 0; s < NSTEPS; ++s) {
+    const uint32_t o = 64u * s;  // 1024 bytes in descriptor units
+    umma::mma_tf32(tacc, al + o, bh + o, idesc, s == 0 ? 0u : 1u);
+    umma::mma_tf32(tacc, ah + o, bl + o, idesc, 1u);
+    umma::mma_tf32(tacc, ah + o, bh + o, idesc, 1u);
+  }
+}
+
+// this thread's 32 units of batch row `row` -> MN-major image pair (panel = 32-unit group c0 / 32)
+__device__ __forceinline__ void store_act_mn(unsigned char* img_hi, uint32_t lo_off, int row, int c0, const float (&v)[32]) {
+  unsigned char* phi = img_hi + (uint32_t)(c0 >> 5) * (TMR * 128);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float4 hi, lo;
+    umma::split_tf32(v[4 * q + 0], hi.x, lo.x);
+    umma::split_tf32(v[4 * q + 1], hi.y, lo.y);
+    umma::split_tf32(v[4 * q + 2], hi.z, lo.z);
+    umma::split_tf32(v[4 * q + 3], hi.w, lo.w);
+    const uint32_t off = umma::sw128b32_off(row, 4 * q);
+    *reinterpret_cast<float4*>(phi + off) = hi;
+    *reinterpret_cast<float4*>(phi + lo_off + off) = lo;
+  }
+}
+// the same values as the A operand of a TMEM-sourced GEMM (hi at region + c0, lo at region + U + c0)
+template <int U>
+__device__ __forceinline__ void store_act_tmem(uint32_t region, uint32_t lane_base, int c0, const float (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) umma::split_tf32(v[16 * q + i], hi[i], lo[i]);
+    umma::tmem_st16(region + lane_base + (uint32_t)(c0 + 16 * q), hi);
+    umma::tmem_st16(region + U + lane_base + (uint32_t)(c0 + 16 * q), lo);
+  }
+}
+__device__ __forceinline__ void warp_arrive_both(unsigned long long* bar, int lane) {
+  umma::fence_async_smem();
+  umma::tmem_st_wait();
+  umma::fence_before();
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int U>
+__global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const AgentImg* __restrict__ imgs, int j0, mdp_ring_layout L, int B,
+                                                            const float* __restrict__ batch, const long long* __restrict__ ridx,
+                                                            const float* __restrict__ y, float* __restrict__ q_out, long long idx_stride,
+                                                            long long y_stride) {
+  using LY = Lay<U>;
+  using LB = LayB<U>;
+  const int j = j0 + blockIdx.y;
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  y += blockIdx.y * y_stride;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ BarsB bars;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  float* misc = reinterpret_cast<float*>(smem + LB::OFF_MISC);
+  float* sB1 = misc;
+  float* sB2 = sB1 + U;
+  float* sW3 = sB2 + U;
+  float* sB3 = sW3 + U;
+  float* sPart = sB3 + 16;
+  float* sDq = sPart + TMR;
+  float* sY = sDq + TMR;
+  long long* sRow = reinterpret_cast<long long*>(sY + TMR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const AgentDev& me = C.agents[j];
+  const MlpW w = me.net[MDP_NET_Q];
+  const MlpG& g = me.grad[1];
+  const long long row0 = (long long)blockIdx.x * TMR;
+  const int nrows = (int)min((long long)TMR, B - row0);
+  const int R = L.row_stride;
+  const int nchunks = (w.in + 31) / 32;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, LY::T_COLS);
+  if (tid == 0) {
+    for (int k = 0; k < NS; ++k) {
+      mbar_init(&bars.stage_w[k], 1);
+      mbar_init(&bars.stage_x[k], NTC / 32);
+      mbar_init(&bars.stage_free[k], 1);
+    }
+    mbar_init(&bars.w2_full, 1); mbar_init(&bars.h1_full, NTC / 32); mbar_init(&bars.acc, 1);
+    mbar_init(&bars.l2_done, 1); mbar_init(&bars.w2n_full, 1);
+    mbar_init(&bars.dz2_full, NTC / 32); mbar_init(&bars.dz1_full, NTC / 32);
+    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 32); mbar_init(&bars.xs_free[k], 1); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 32); }
+    if (blockIdx.x == 0) C.adam_t[2 * j + 1] += 1;  // one more Adam step for this net
+  }
+  if (tid < TMR) {
+    const long long rl = row0 + min(tid, nrows - 1);
+    const long long rg = ridx ? ridx[rl] : rl;
+    sRow[tid] = rg * R;
+    sY[tid] = y[rl];
+  }
+  for (int i = tid; i < U; i += NTT) { sB1[i] = w.b1[i]; sB2[i] = w.b2[i]; sW3[i] = w.W3[i]; }
+  if (tid == 0) sB3[0] = w.b3[0];
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == NTC / 32) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const NetImg img = imgs[j].net[MDP_NET_Q];
+      mbar_arrive_expect_tx(&bars.w2_full, 2 * LY::W2_IMG);
+      bulk_g2s(smem + LB::R2, img.w2, 2 * LY::W2_IMG, &bars.w2_full);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % NS;
+        if (c >= NS) mbar_wait_bounded(&bars.stage_free[s], ((c / NS) - 1) & 1);
+        mbar_arrive_expect_tx(&bars.stage_w[s], 2 * LY::W_IMG);
+        bulk_g2s(smem + LB::R1 + s * (2 * LY::W_IMG), img.w1 + (size_t)c * (2 * LY::W_IMG), 2 * LY::W_IMG, &bars.stage_w[s]);
+      }
+      mbar_wait_bounded(&bars.l2_done, 0);  // layer-2 MMAs have consumed W2^T: the region now takes W2 for the backward pass
+      mbar_arrive_expect_tx(&bars.w2n_full, 2 * LY::W2_IMG);
+      bulk_g2s(smem + LB::R2, img.w2n, 2 * LY::W2_IMG, &bars.w2n_full);
+    }
+  } else if (warp == NTC / 32 + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint64_t w_hi0 = umma::desc_k(sbase + LB::R1, LY::W_IMG, 0), w_lo0 = umma::desc_k(sbase + LB::R1 + LY::W_IMG, LY::W_IMG, 0);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c % NS, ph = (c / NS) & 1;
+        mbar_wait_bounded(&bars.stage_x[s], ph);
+        mbar_wait_bounded(&bars.stage_w[s], ph);
+        umma::fence_after();
+        const uint32_t so = s * ((2 * LY::W_IMG) >> 4);
+        issue_3x<U, 4>(tbase + LY::T_ACC1, tbase + LY::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, c > 0 ? 1u : 0u);
+        umma::commit(&bars.stage_free[s]);
+        if (c == nchunks - 1) umma::commit(&bars.acc);
+      }
+      mbar_wait_bounded(&bars.h1_full, 0);
+      mbar_wait_bounded(&bars.w2_full, 0);
+      umma::fence_after();
+      issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, umma::desc_k(sbase + LB::R2, LY::W_IMG, 0),
+                         umma::desc_k(sbase + LB::R2 + LY::W2_IMG, LY::W_IMG, 0), 0u);
+      umma::commit(&bars.acc);
+      umma::commit(&bars.l2_done);
+      // backward: dW2 = h1^T dz2 (acc1, M = 64) and dh1 = dz2 W2^T (acc2)
+      mbar_wait_bounded(&bars.dz2_full, 0);
+      mbar_wait_bounded(&bars.w2n_full, 0);
+      umma::fence_after();
+      issue_3x_mn<U, U, TMR / 8>(tbase + LY::T_ACC1, sbase + LB::R3, LB::ACT_IMG, TMR * 128, sbase + LB::R1, LB::ACT_IMG, TMR * 128);
+      issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, umma::desc_k(sbase + LB::R2, LY::W_IMG, 0),
+                         umma::desc_k(sbase + LB::R2 + LY::W2_IMG, LY::W_IMG, 0), 0u);
+      umma::commit(&bars.acc);
+      // dW1^T chunks: D[u][f] = sum_r dz1[r][u] X[r][f]
+      mbar_wait_bounded(&bars.dz1_full, 0);
+      for (int c = 0; c < nchunks; ++c) {
+        const int s = c & 1, t = c & 3;
+        mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
+        if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
+        umma::fence_after();
+        issue_3x_mn<U, 32, TMR / 8>(tbase + LB::T_DW + t * 32, sbase + LB::R3, LB::ACT_IMG, TMR * 128,
+                                   sbase + LB::R1 + s * (2 * LB::XS_IMG), LB::XS_IMG, TMR * 128);
+        umma::commit(&bars.xs_free[s]);
+        umma::commit(&bars.dw_full[t]);
+      }
+    }
+  } else {
+    // ===== compute warps: thread = (batch row, unit half) =====
+    const int row = 32 * (warp & 3) + lane, half = warp >> 2, c0 = 32 * half;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const long long rowoff = sRow[row];
+    const XT xs{batch, L.x_dim, nullptr, 0, 0, 0, 1};
+    XRegs xr[PD];
+#pragma unroll
+    for (int b = 0; b < PD; ++b)
+      if (b < nchunks) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
+    for (int c = 0; c < nchunks; c += PD) {
+#pragma unroll
+      for (int b = 0; b < PD; ++b) {
+        if (c + b < nchunks) {
+          const int cc = c + b, s = cc % NS;
+          if (cc >= NS) mbar_wait_bounded(&bars.stage_free[s], ((cc / NS) - 1) & 1);
+          umma::fence_after();
+          store_x(tbase + LY::T_X + s * 64, lane_base, 16 * half, xr[b]);
+          warp_arrive_tmem(&bars.stage_x[s], lane);
+          if (cc + PD < nchunks) load_x(xr[b], xs, rowoff, row, 32 * (cc + PD) + 16 * half);
+        }
+      }
+    }
+    // ---- epilogue 1: h1 -> TMEM (A of layer 2) and MN-major smem images (A of dW2); relu mask kept in a register
+    mbar_wait_bounded(&bars.acc, 0);
+    umma::fence_after();
+    uint32_t mask1 = 0, mask2 = 0;
+    float v[32];
+    umma::tmem_ld32(tbase + LY::T_ACC1 + lane_base + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = fmaxf(v[i] + sB1[c0 + i], 0.f);
+      mask1 |= (v[i] > 0.f ? 1u : 0u) << i;
+    }
+    store_act_tmem<U>(tbase + LY::T_H1, lane_base, c0, v);
+    store_act_mn(smem + LB::R3, LB::ACT_IMG, row, c0, v);
+    warp_arrive_both(&bars.h1_full, lane);
+    // ---- epilogue 2: h2, q, loss, dq, dW3/db3, dz2
+    mbar_wait_bounded(&bars.acc, 1);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = fmaxf(v[i] + sB2[c0 + i], 0.f);
+      mask2 |= (v[i] > 0.f ? 1u : 0u) << i;
+      part = fmaf(v[i], sW3[c0 + i], part);
+    }
+    if (half == 1) sPart[row] = part;
+    named_sync();
+    if (half == 0) {
+      float d = 0.f;
+      double se = 0.0;
+      if (row < nrows) {
+        const float q = part + sPart[row] + sB3[0];
+        const float diff = q - sY[row];
+        d = 2.0f * diff / (float)B;  // dL/dq of mean((q - y)^2)
+        se = (double)diff * (double)diff;
+        if (q_out) q_out[row0 + row] = q;
+      }
+      sDq[row] = d;
+      float ds = d;
+      for (int o = 16; o > 0; o >>= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, o);
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      }
+      if (lane == 0) {
+        atomicAdd(C.stats + 8 * j + 0, se);
+        atomicAdd(g.b3, ds);
+      }
+    }
+    named_sync();
+    const float dq = sDq[row];
+    {
+      float t[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = v[i] * dq;  // gW3[u] = sum_r h2[r][u] dq[r]
+      const float sum = warp_colsum32(t, lane);
+      atomicAdd(g.W3 + c0 + lane, sum);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((mask2 >> i) & 1u) ? dq * sW3[c0 + i] : 0.f;  // dz2 = dq W3^T relu'(h2)
+    store_act_tmem<U>(tbase + LY::T_H1, lane_base, c0, v);   // layer-2 MMAs are complete: the h1 operand region is free
+    store_act_mn(smem + LB::R1, LB::ACT_IMG, row, c0, v);    // layer-1 MMAs are complete: the W1^T slots are free
+    warp_arrive_both(&bars.dz2_full, lane);
+    {
+      const float sum = warp_colsum32(v, lane);  // gb2 = sum_r dz2
+      atomicAdd(g.b2 + c0 + lane, sum);
+    }
+    // ---- epilogue 3: dW2 tile -> gradient bucket; dz1 = dh1 relu'(h1) -> MN-major images (A of dW1^T)
+    mbar_wait_bounded(&bars.acc, 0);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC1 + lane_base + (uint32_t)c0, v);  // M = 64: row m lives on lane 32 (m / 16) + m % 16
+    if (lane < 16) {
+      float* dst = g.W2 + (size_t)(16 * (warp & 3) + lane) * U + c0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+    }
+    umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((mask1 >> i) & 1u) ? v[i] : 0.f;
+    umma::fence_before();
+    store_act_mn(smem + LB::R3, LB::ACT_IMG, row, c0, v);  // dW2's MMAs are complete: the h1 images are dead
+    warp_arrive_both(&bars.dz1_full, lane);
+    {
+      const float sum = warp_colsum32(v, lane);  // gb1 = sum_r dz1
+      atomicAdd(g.b1 + c0 + lane, sum);
+    }
+    // ---- dW1: stage X chunk c as an MN-major image pair, read out the accumulator of chunk c - 1
+    auto readout = [&](int cc) {
+      const int t = cc & 3;
+      mbar_wait_bounded(&bars.dw_full[t], (cc >> 2) & 1);
+      umma::fence_after();
+      float d[16];
+      umma::tmem_ld16(tbase + LB::T_DW + t * 32 + lane_base + (uint32_t)(16 * half), d);
+      umma::fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.dw_free[t])) : "memory");
+      if (lane < 16) {
+        const int u = 16 * (warp & 3) + lane, f0 = 32 * cc + 16 * half;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (f0 + i < w.in) atomicAdd(g.W1 + (size_t)(f0 + i) * U + u, d[i]);
+      }
+    };
+#pragma unroll
+    for (int b = 0; b < PD; ++b)
+      if (b < nchunks) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
+    for (int c = 0; c < nchunks; c += PD) {
+#pragma unroll
+      for (int b = 0; b < PD; ++b) {
+        if (c + b < nchunks) {
+          const int cc = c + b, s = cc & 1;
+          if (cc >= 2) mbar_wait_bounded(&bars.xs_free[s], ((cc >> 1) - 1) & 1);
+          unsigned char* img = smem + LB::R1 + s * (2 * LB::XS_IMG);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 hi, lo;
+            umma::split_tf32(xr[b].v[4 * q + 0], hi.x, lo.x);
+            umma::split_tf32(xr[b].v[4 * q + 1], hi.y, lo.y);
+            umma::split_tf32(xr[b].v[4 * q + 2], hi.z, lo.z);
+            umma::split_tf32(xr[b].v[4 * q + 3], hi.w, lo.w);
+            const uint32_t off = umma::sw128b32_off(row, 16 * half + 4 * q);
+            *reinterpret_cast<float4*>(img + off) = hi;
+            *reinterpret_cast<float4*>(img + LB::XS_IMG + off) = lo;
+          }
+          umma::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.xs_full[s])) : "memory");
+          if (cc + PD < nchunks) load_x(xr[b], xs, rowoff, row, 32 * (cc + PD) + 16 * half);
+          if (cc >= 1) readout(cc - 1);
+        }
+      }
+    }
+    readout(nchunks - 1);
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
+}
+
 }  // namespace tc
 
 // host side -------------------------------------------------------------------------------------------------
@@ -527,7 +908,7 @@ static int ensure_images(mdp_core* c) {
     for (int k = 0; k < 4; ++k) {
       const size_t nchunks = (size_t)(c->lay.net_in[i][k] + 31) / 32;
       off1[i * 4 + k] = total; total += nchunks * 2 * LY::W_IMG;
-      off2[i * 4 + k] = total; total += 2 * LY::W2_IMG;
+      off2[i * 4 + k] = total; total += 4 * LY::W2_IMG;  // W2^T pair + W2 pair
     }
   unsigned char* arena = nullptr;
   MDP_CUDA(cudaMalloc(&arena, total + n * sizeof(tc::AgentImg)));
@@ -535,6 +916,7 @@ static int ensure_images(mdp_core* c) {
     for (int k = 0; k < 4; ++k) {
       h[i].net[k].w1 = arena + off1[i * 4 + k];
       h[i].net[k].w2 = arena + off2[i * 4 + k];
+      h[i].net[k].w2n = arena + off2[i * 4 + k] + 2 * LY::W2_IMG;
     }
   MDP_CUDA(cudaMemcpy(arena + total, h.data(), n * sizeof(tc::AgentImg), cudaMemcpyHostToDevice));
   c->tc_arena = arena;
@@ -585,6 +967,33 @@ int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t co
   kern<<<dim3(tiles, count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
                                                    target_act_out, idx_stride, y_stride, c->tc_scratch, act_in_smem);
   return check_launch("k_td_target_tc");
+}
+
+
+// Returns MDP_ENOTSUP when the shape is outside the tensor-core path (local critics, num_units != 64).
+int launch_critic_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,
+                           const float* batch, const long long* ridx, long long idx_stride, const float* y, long long y_stride,
+                           float* q_out, cudaStream_t st) {
+  if (c->cfg.num_units != 64) return fail(MDP_ENOTSUP, "tensor-core path: num_units %d (64 only)", c->cfg.num_units);
+  for (int k = agent; k < agent + count; ++k)
+    if (c->cfg.local_q[k]) return fail(MDP_ENOTSUP, "tensor-core critic path: local critics use the SIMT kernels");
+  if ((lay->row_stride & 3) != 0) return fail(MDP_ENOTSUP, "tensor-core path: row stride");
+  constexpr int U = 64;
+  using LB = tc::LayB<U>;
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  const tc::AgentImg* imgs = reinterpret_cast<const tc::AgentImg*>(c->tc_imgs);
+  int max_in = 0;
+  for (int k = agent; k < agent + count; ++k) max_in = std::max(max_in, c->lay.net_in[k][MDP_NET_Q]);
+  const int bx = std::min(64, cdiv(((max_in + 31) / 32 * 32 + U) * U, 256 * 4));
+  tc::k_build_images<U><<<dim3(bx, count), 256, 0, st>>>(d, imgs, 0, 0, agent, MDP_NET_P, MDP_NET_Q);
+  rc = check_launch("k_build_images");
+  if (rc) return rc;
+  const size_t smem = LB::OFF_MISC + (size_t)LB::MISC_FLOATS * 4 + 1024 + 64;
+  auto kern = tc::k_critic_grads_tc<U>;
+  MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(cdiv(B, tc::TMR), count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, y, q_out, idx_stride, y_stride);
+  return check_launch("k_critic_grads_tc");
 }
 
 }  // namespace mdp
