@@ -198,6 +198,23 @@ def tensor_core_section(torch, dev):
         out[name] = {"avg_launch_us": us, "achieved_tflops": flops / us / 1e6}
     out["speedup_vs_simt"] = out["simt_fp32"]["avg_launch_us"] / out["tcgen05"]["avg_launch_us"]
     out["frac"] = 3 * out["tcgen05"]["achieved_tflops"] / 1100.0
+    # the whole grouped (Jacobi) round at the same shape: TD target + critic forward/backward on tcgen05, actor step on SIMT
+    rnd = {}
+    for name, mode in (("tcgen05", 1), ("simt_fp32", -1)):
+        core.set_tensor_cores(mode)
+        for _ in range(2):
+            core.update_all(core.ring.ring, idx=idx)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in evs:
+            flush.fill_(1.0)
+            a.record()
+            core.update_all(core.ring.ring, idx=idx)
+            b.record()
+        torch.cuda.synchronize()
+        rnd[name + "_us"] = sum(a.elapsed_time(b) for a, b in evs) * 1e3 / len(evs)
+    rnd["critic_updates_per_s_tcgen05"] = NA / (rnd["tcgen05_us"] * 1e-6)
+    rnd["critic_updates_per_s_simt"] = NA / (rnd["simt_fp32_us"] * 1e-6)
+    out["grouped_update_round"] = rnd
     del env, core, roll, flush
     torch.cuda.empty_cache()
     return out

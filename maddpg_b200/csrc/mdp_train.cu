@@ -1007,9 +1007,10 @@ int launch_critic_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t
 }
 
 // tensor-core path policy: forced on (1), forced off (-1), or automatic (0)
-static bool want_tc(const mdp_core* c, int B, int count) {
+static bool want_tc(const mdp_core* c, int B, int count, bool backward = false) {
   if (c->tc_mode < 0 || c->cfg.num_units != 64) return false;
   if (c->tc_mode > 0) return true;
+  if (backward) return cdiv(B, 128) * count >= 96;  // the backward kernel only wins once its 128-row tiles fill the SMs
   // automatic: the 128-row tensor-core tiles pay off once a launch fills most SMs with them, or when the critic input
   // is wide enough that streaming it through the UMMA pipeline beats the SIMT K-loop (measured on B200)
   int max_in = 0;
@@ -1081,7 +1082,7 @@ static int launch_critic_grads(mdp_core* c, int32_t agent, int32_t count, const 
   const Plan p = make_plan(c, B);
   const ResPlan rp = make_res_plan(c, p, agent);
   const long long* ridx = (const long long*)idx;
-  if (want_tc(c, B, count)) {
+  if (want_tc(c, B, count, true)) {
     rc = launch_critic_grads_tc(c, d, agent, count, lay, B, batch, ridx, idx_stride, y, y_stride, q_out, st);
     if (rc != MDP_ENOTSUP) return rc;
   }
