@@ -1006,6 +1006,12 @@ int launch_critic_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t
                            float* q_out, cudaStream_t st);
 }
 
+namespace mdp {
+int launch_actor_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,
+                          const float* batch, const long long* ridx, long long idx_stride, const float* u_actor, int32_t u_stride,
+                          uint64_t seed, uint64_t counter, cudaStream_t st);
+}
+
 // tensor-core path policy: forced on (1), forced off (-1), or automatic (0)
 static bool want_tc(const mdp_core* c, int B, int count, bool backward = false) {
   if (c->tc_mode < 0 || c->cfg.num_units != 64) return false;
@@ -1122,6 +1128,10 @@ static int launch_actor_grads(mdp_core* c, int32_t agent, int32_t count, const m
   const Plan p = make_plan(c, B);
   const ResPlan rp = make_res_plan(c, p, agent);
   const long long* ridx = (const long long*)idx;
+  if (want_tc(c, B, count, true)) {
+    rc = launch_actor_grads_tc(c, d, agent, count, lay, B, batch, ridx, idx_stride, u_actor, u_stride, seed, counter, st);
+    if (rc != MDP_ENOTSUP) return rc;
+  }
   return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
     constexpr bool RES = decltype(res_)::value;

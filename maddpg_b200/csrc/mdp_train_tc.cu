@@ -892,6 +892,454 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
   if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
 }
 
+// =============================================================================================================
+// Fused actor update on tensor cores (p_train, maddpg.py:28-61), maddpg-mode critics, U = 64:
+//   actor forward (2 GEMMs) -> Gumbel-softmax sample -> running critic forward on [o, a_-j, a_hat_j] (2 GEMMs) ->
+//   critic backward to the action columns (dh1q = dz2q W2q^T on tensor cores, dQ/da in registers) -> softmax Jacobian +
+//   logit regulariser -> actor backward (dW2p = h1p^T dz2p, dh1p = dz2p W2p^T, dW1p^T = dz1p^T X_p per chunk).
+// Same operand placement as k_critic_grads_tc; the weight-image region R2 is reloaded four times by the TMA producer
+// (W2p^T, W2q^T, W2q, W2p), gated by commit barriers.
+// =============================================================================================================
+template <int U>
+struct LayA {
+  using L = Lay<U>;
+  static constexpr uint32_t ACT_IMG = TMR * 128 * (U / 32);
+  static constexpr uint32_t XS_IMG = TMR * 128;
+  static constexpr uint32_t R1 = 0, R2 = L::OFF_W2, S1 = L::OFF_W2 + 2 * L::W2_IMG;
+  static constexpr uint32_t OFF_MISC = S1 + 2 * ACT_IMG;
+  // b1p b2p W3p b3p | b1q b2q W3q b3q | W1q action rows | part dl act noise | rowoff
+  static constexpr int MISC_FLOATS = (2 * U + U * MAXK + 16) + (3 * U + 16) + MAXK * U + 4 * TMR * KPAD + 2 * TMR;
+  static constexpr uint32_t T_DW = L::T_X;
+};
+
+struct BarsA {
+  unsigned long long stage_w[NS], stage_x[NS], stage_free[NS];
+  unsigned long long a_full, r2_full, r2_free, acc, dz1_full;
+  unsigned long long xs_full[2], xs_free[2], dw_full[4], dw_free[4];
+};
+
+template <int U>
+__global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const AgentImg* __restrict__ imgs, int j0, mdp_ring_layout L, int B,
+                                                           const float* __restrict__ batch, const long long* __restrict__ ridx,
+                                                           const float* __restrict__ u_actor, int u_stride, uint64_t seed,
+                                                           uint64_t counter, long long idx_stride) {
+  using LY = Lay<U>;
+  using LA = LayA<U>;
+  const int j = j0 + blockIdx.y;
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  if (C.ctl) counter += C.ctl[0];
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ BarsA bars;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  float* misc = reinterpret_cast<float*>(smem + LA::OFF_MISC);
+  float* sB1p = misc;
+  float* sB2p = sB1p + U;
+  float* sW3p = sB2p + U;
+  float* sB3p = sW3p + U * MAXK;
+  float* sB1q = sB3p + 16;
+  float* sB2q = sB1q + U;
+  float* sW3q = sB2q + U;
+  float* sB3q = sW3q + U;
+  float* sW1a = sB3q + 16;             // [K][U]: critic W1 rows of agent j's action columns
+  float* sPart = sW1a + MAXK * U;      // [TMR][KPAD] half-1 partial sums
+  float* sDl = sPart + TMR * KPAD;     // [TMR][KPAD] dL/dlogits
+  float* sAct = sDl + TMR * KPAD;      // [TMR][KPAD] fresh action sample
+  float* sG = sAct + TMR * KPAD;       // [TMR][KPAD] Gumbel noise
+  long long* sRow = reinterpret_cast<long long*>(sG + TMR * KPAD);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const AgentDev& me = C.agents[j];
+  const MlpW pw = me.net[MDP_NET_P], qw = me.net[MDP_NET_Q];
+  const MlpG& pg = me.grad[0];
+  const long long row0 = (long long)blockIdx.x * TMR;
+  const int nrows = (int)min((long long)TMR, B - row0);
+  const int R = L.row_stride, K = me.act_dim;
+  const int a_col0 = L.obs_sum + me.act_off;
+  const int np = (pw.in + 31) / 32, nq = (qw.in + 31) / 32;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, LY::T_COLS);
+  if (tid == 0) {
+    for (int k = 0; k < NS; ++k) {
+      mbar_init(&bars.stage_w[k], 1);
+      mbar_init(&bars.stage_x[k], NTC / 32);
+      mbar_init(&bars.stage_free[k], 1);
+    }
+    mbar_init(&bars.a_full, NTC / 32); mbar_init(&bars.r2_full, 1); mbar_init(&bars.r2_free, 1);
+    mbar_init(&bars.acc, 1); mbar_init(&bars.dz1_full, NTC / 32);
+    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 32); mbar_init(&bars.xs_free[k], 1); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 32); }
+    if (blockIdx.x == 0) C.adam_t[2 * j + 0] += 1;
+  }
+  if (tid < TMR) {
+    const long long rl = row0 + min(tid, nrows - 1);
+    sRow[tid] = (ridx ? ridx[rl] : rl) * R;
+  }
+  for (int i = tid; i < U; i += NTT) {
+    sB1p[i] = pw.b1[i]; sB2p[i] = pw.b2[i];
+    sB1q[i] = qw.b1[i]; sB2q[i] = qw.b2[i]; sW3q[i] = qw.W3[i];
+  }
+  for (int i = tid; i < U * K; i += NTT) sW3p[i] = pw.W3[i];
+  for (int i = tid; i < K * U; i += NTT) sW1a[i] = qw.W1[(size_t)(a_col0 + i / U) * U + (i % U)];
+  if (tid < K) sB3p[tid] = pw.b3[tid];
+  if (tid == 0) sB3q[0] = qw.b3[0];
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == NTC / 32) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const NetImg ip = imgs[j].net[MDP_NET_P], iq = imgs[j].net[MDP_NET_Q];
+      auto load_r2 = [&](const unsigned char* src) {
+        mbar_arrive_expect_tx(&bars.r2_full, 2 * LY::W2_IMG);
+        bulk_g2s(smem + LA::R2, src, 2 * LY::W2_IMG, &bars.r2_full);
+      };
+      auto chunks = [&](const unsigned char* w1, int n, int cbase) {
+        for (int k = 0; k < n; ++k) {
+          const int c = cbase + k, s = c % NS;
+          if (c >= NS) mbar_wait_bounded(&bars.stage_free[s], ((c / NS) - 1) & 1);
+          mbar_arrive_expect_tx(&bars.stage_w[s], 2 * LY::W_IMG);
+          bulk_g2s(smem + LA::R1 + s * (2 * LY::W_IMG), w1 + (size_t)k * (2 * LY::W_IMG), 2 * LY::W_IMG, &bars.stage_w[s]);
+        }
+      };
+      load_r2(ip.w2);
+      chunks(ip.w1, np, 0);
+      mbar_wait_bounded(&bars.r2_free, 0);
+      load_r2(iq.w2);
+      chunks(iq.w1, nq, np);
+      mbar_wait_bounded(&bars.r2_free, 1);
+      load_r2(iq.w2n);
+      mbar_wait_bounded(&bars.r2_free, 0);
+      load_r2(ip.w2n);
+    }
+  } else if (warp == NTC / 32 + 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint64_t w_hi0 = umma::desc_k(sbase + LA::R1, LY::W_IMG, 0), w_lo0 = umma::desc_k(sbase + LA::R1 + LY::W_IMG, LY::W_IMG, 0);
+      const uint64_t r2_hi = umma::desc_k(sbase + LA::R2, LY::W_IMG, 0), r2_lo = umma::desc_k(sbase + LA::R2 + LY::W2_IMG, LY::W_IMG, 0);
+      auto layer1 = [&](int n, int cbase) {
+        for (int k = 0; k < n; ++k) {
+          const int c = cbase + k, s = c % NS, ph = (c / NS) & 1;
+          mbar_wait_bounded(&bars.stage_x[s], ph);
+          mbar_wait_bounded(&bars.stage_w[s], ph);
+          umma::fence_after();
+          const uint32_t so = s * ((2 * LY::W_IMG) >> 4);
+          issue_3x<U, 4>(tbase + LY::T_ACC1, tbase + LY::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, k > 0 ? 1u : 0u);
+          umma::commit(&bars.stage_free[s]);
+        }
+        umma::commit(&bars.acc);
+      };
+      auto from_h1 = [&](int a_phase, int r2_phase) {  // acc2 = (TMEM H1 region) x (R2 images)^T
+        mbar_wait_bounded(&bars.a_full, a_phase);
+        mbar_wait_bounded(&bars.r2_full, r2_phase);
+        umma::fence_after();
+        issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, r2_hi, r2_lo, 0u);
+      };
+      layer1(np, 0);                                   // acc phase 0: z1p
+      from_h1(0, 0);                                   // z2p = h1p W2p
+      umma::commit(&bars.acc); umma::commit(&bars.r2_free);
+      layer1(nq, np);                                  // acc phase 2: z1q
+      from_h1(1, 1);                                   // z2q = h1q W2q
+      umma::commit(&bars.acc); umma::commit(&bars.r2_free);
+      from_h1(0, 0);                                   // dh1q = dz2q W2q^T
+      umma::commit(&bars.acc); umma::commit(&bars.r2_free);
+      mbar_wait_bounded(&bars.a_full, 1);              // dz2p: TMEM operand + MN-major images
+      mbar_wait_bounded(&bars.r2_full, 1);
+      umma::fence_after();
+      issue_3x_mn<U, U, TMR / 8>(tbase + LY::T_ACC1, sbase + LA::S1, LA::ACT_IMG, TMR * 128, sbase + LA::R1, LA::ACT_IMG, TMR * 128);
+      issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, r2_hi, r2_lo, 0u);  // dh1p = dz2p W2p^T
+      umma::commit(&bars.acc);
+      mbar_wait_bounded(&bars.dz1_full, 0);
+      for (int c = 0; c < np; ++c) {  // dW1p^T chunks
+        const int s = c & 1, t = c & 3;
+        mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
+        if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
+        umma::fence_after();
+        issue_3x_mn<U, 32, TMR / 8>(tbase + LA::T_DW + t * 32, sbase + LA::S1, LA::ACT_IMG, TMR * 128,
+                                   sbase + LA::R1 + s * (2 * LA::XS_IMG), LA::XS_IMG, TMR * 128);
+        umma::commit(&bars.xs_free[s]);
+        umma::commit(&bars.dw_full[t]);
+      }
+    }
+  } else {
+    // ===== compute warps: thread = (batch row, unit half) =====
+    const int row = 32 * (warp & 3) + lane, half = warp >> 2, c0 = 32 * half;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+    const long long rowoff = sRow[row];
+    const bool valid = row < nrows;
+    int chunk = 0;  // running layer-1 chunk counter (actor pass, then critic pass)
+    XRegs xr[PD];
+    auto layer1 = [&](const XT& xs, int n) {
+#pragma unroll
+      for (int b = 0; b < PD; ++b)
+        if (b < n) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
+      for (int c = 0; c < n; c += PD) {
+#pragma unroll
+        for (int b = 0; b < PD; ++b) {
+          if (c + b < n) {
+            const int cc = chunk, s = cc % NS;
+            if (cc >= NS) mbar_wait_bounded(&bars.stage_free[s], ((cc / NS) - 1) & 1);
+            umma::fence_after();
+            store_x(tbase + LY::T_X + s * 64, lane_base, 16 * half, xr[b]);
+            warp_arrive_tmem(&bars.stage_x[s], lane);
+            if (c + b + PD < n) load_x(xr[b], xs, rowoff, row, 32 * (c + b + PD) + 16 * half);
+            ++chunk;
+          }
+        }
+      }
+    };
+    float v[32];
+    uint32_t mask1p = 0, mask2p = 0, mask1q = 0, mask2q = 0;
+    // ---- actor forward on o_j
+    const XT xp{batch + me.obs_off, me.obs_dim, nullptr, 0, 0, 0, (me.obs_off & 3) == 0};
+    layer1(xp, np);
+    for (int a = half; a < K; a += 2) {  // Gumbel noise of this row, hidden behind the layer-1 MMAs
+      const float u = u_actor ? u_actor[(row0 + min(row, nrows - 1)) * u_stride + me.act_off + a]
+                              : philox_u(seed, counter, (uint32_t)(0x200 + j), row0 + row, a);
+      sG[row * KPAD + a] = gumbel_from_u(u);
+    }
+    mbar_wait_bounded(&bars.acc, 0);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC1 + lane_base + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = fmaxf(v[i] + sB1p[c0 + i], 0.f);
+      mask1p |= (v[i] > 0.f ? 1u : 0u) << i;
+    }
+    store_act_tmem<U>(tbase + LY::T_H1, lane_base, c0, v);
+    store_act_mn(smem + LA::S1, LA::ACT_IMG, row, c0, v);  // h1p: A operand of dW2p
+    warp_arrive_both(&bars.a_full, lane);                  // a_full phase 0
+    mbar_wait_bounded(&bars.acc, 1);
+    umma::fence_after();
+    float h2p[32];
+    umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, h2p);
+    float part[MAXK];
+#pragma unroll
+    for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      h2p[i] = fmaxf(h2p[i] + sB2p[c0 + i], 0.f);
+      mask2p |= (h2p[i] > 0.f ? 1u : 0u) << i;
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a)
+        if (a < K) part[a] = fmaf(h2p[i], sW3p[(c0 + i) * K + a], part[a]);
+    }
+    umma::fence_before();
+    if (half == 1)
+      for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+    named_sync();
+    float logit[MAXK], act[MAXK];
+    if (half == 0) {  // logits -> fresh Gumbel-softmax sample (maddpg.py:49), per head
+      double sl = 0.0;
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a) {
+        logit[a] = 0.f; act[a] = 0.f;
+        if (a < K) {
+          logit[a] = part[a] + sPart[row * KPAD + a] + sB3p[a];
+          act[a] = logit[a] + sG[row * KPAD + a];
+          if (valid) sl += (double)logit[a] * (double)logit[a];
+        }
+      }
+      for (int h = 0; h < me.n_heads; ++h) {
+        const int o = h ? me.head_dim[0] : 0, n = me.head_dim[h];
+        float m = -INFINITY, ssum = 0.f;
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) m = fmaxf(m, act[a]);
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) { act[a] = expf(act[a] - m); ssum += act[a]; }
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) act[a] = act[a] / ssum;
+      }
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a)
+        if (a < K) sAct[row * KPAD + a] = act[a];
+      for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+      if (lane == 0) atomicAdd(C.stats + 8 * j + 2, sl);
+    }
+    named_sync();  // the sample is visible to the critic's gather
+    // ---- running critic on [o, a_-j, a_hat_j]
+    const XT xq{batch, L.x_dim, sAct, KPAD, a_col0, K, 1};
+    layer1(xq, nq);
+    mbar_wait_bounded(&bars.acc, 0);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC1 + lane_base + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = fmaxf(v[i] + sB1q[c0 + i], 0.f);
+      mask1q |= (v[i] > 0.f ? 1u : 0u) << i;
+    }
+    store_act_tmem<U>(tbase + LY::T_H1, lane_base, c0, v);
+    warp_arrive_tmem(&bars.a_full, lane);  // a_full phase 1
+    mbar_wait_bounded(&bars.acc, 1);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
+    float qpart = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float h = fmaxf(v[i] + sB2q[c0 + i], 0.f);
+      mask2q |= (h > 0.f ? 1u : 0u) << i;
+      qpart = fmaf(h, sW3q[c0 + i], qpart);
+    }
+    if (half == 1) sPart[row * KPAD] = qpart;
+    // dz2q = (-1/B) W3q^T relu'(h2q) for valid rows  (the actor loss is -mean(q))
+    const float dq = valid ? -1.0f / (float)B : 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((mask2q >> i) & 1u) ? dq * sW3q[c0 + i] : 0.f;
+    store_act_tmem<U>(tbase + LY::T_H1, lane_base, c0, v);
+    warp_arrive_tmem(&bars.a_full, lane);  // a_full phase 2
+    named_sync();
+    if (half == 0) {
+      double sq = valid ? -(double)(qpart + sPart[row * KPAD] + sB3q[0]) : 0.0;
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      if (lane == 0) atomicAdd(C.stats + 8 * j + 1, sq);
+    }
+    // ---- critic backward to agent j's action columns
+    mbar_wait_bounded(&bars.acc, 0);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
+    umma::fence_before();
+#pragma unroll
+    for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float dz = ((mask1q >> i) & 1u) ? v[i] : 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a)
+        if (a < K) part[a] = fmaf(dz, sW1a[a * U + c0 + i], part[a]);  // dQ/da = dz1q . W1q[a_col0 + a, :]
+    }
+    named_sync();  // the q partials in sPart have been consumed
+    if (half == 1)
+      for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+    named_sync();
+    if (half == 0) {  // softmax Jacobian per head + logit regulariser (maddpg.py:55-58)
+      const float regc = (float)(2.0 * C.actor_reg / ((double)B * (double)K));
+      float dqa[MAXK];
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a) dqa[a] = a < K ? part[a] + sPart[row * KPAD + a] : 0.f;
+      for (int h = 0; h < me.n_heads; ++h) {
+        const int o = h ? me.head_dim[0] : 0, n = me.head_dim[h];
+        float dot = 0.f;
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) dot = fmaf(act[a], dqa[a], dot);
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) {
+            const float dl = act[a] * (dqa[a] - dot) + regc * logit[a];
+            sDl[row * KPAD + a] = valid ? dl : 0.f;
+          }
+      }
+    }
+    named_sync();
+    float dl[MAXK];
+#pragma unroll
+    for (int a = 0; a < MAXK; ++a) dl[a] = a < K ? sDl[row * KPAD + a] : 0.f;
+    // ---- actor head backward: gW3p, gb3p, dz2p
+    for (int a = 0; a < K; ++a) {
+      float t[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) t[i] = h2p[i] * dl[a];
+      const float sum = warp_colsum32(t, lane);
+      atomicAdd(pg.W3 + (size_t)(c0 + lane) * K + a, sum);
+    }
+    if (half == 0)
+      for (int a = 0; a < K; ++a) {
+        float sb = dl[a];
+        for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        if (lane == 0) atomicAdd(pg.b3 + a, sb);
+      }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a)
+        if (a < K) sacc = fmaf(dl[a], sW3p[(c0 + i) * K + a], sacc);
+      v[i] = ((mask2p >> i) & 1u) ? sacc : 0.f;  // dz2p
+    }
+    store_act_tmem<U>(tbase + LY::T_H1, lane_base, c0, v);   // A operand of dh1p
+    store_act_mn(smem + LA::R1, LA::ACT_IMG, row, c0, v);    // B operand of dW2p (the W1^T slots are idle)
+    warp_arrive_both(&bars.a_full, lane);                    // a_full phase 3
+    {
+      const float sum = warp_colsum32(v, lane);
+      atomicAdd(pg.b2 + c0 + lane, sum);
+    }
+    // ---- dW2p tile out, dz1p images in
+    mbar_wait_bounded(&bars.acc, 1);
+    umma::fence_after();
+    umma::tmem_ld32(tbase + LY::T_ACC1 + lane_base + (uint32_t)c0, v);
+    if (lane < 16) {
+      float* dst = pg.W2 + (size_t)(16 * (warp & 3) + lane) * U + c0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+    }
+    umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = ((mask1p >> i) & 1u) ? v[i] : 0.f;
+    umma::fence_before();
+    store_act_mn(smem + LA::S1, LA::ACT_IMG, row, c0, v);  // dz1p over the dead h1p images
+    warp_arrive_both(&bars.dz1_full, lane);
+    {
+      const float sum = warp_colsum32(v, lane);
+      atomicAdd(pg.b1 + c0 + lane, sum);
+    }
+    // ---- dW1p: stage X_p chunk c as an MN-major image pair, read out the accumulator of chunk c - 1
+    auto readout = [&](int cc) {
+      const int t = cc & 3;
+      mbar_wait_bounded(&bars.dw_full[t], (cc >> 2) & 1);
+      umma::fence_after();
+      float d[16];
+      umma::tmem_ld16(tbase + LA::T_DW + t * 32 + lane_base + (uint32_t)(16 * half), d);
+      umma::fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.dw_free[t])) : "memory");
+      if (lane < 16) {
+        const int u = 16 * (warp & 3) + lane, f0 = 32 * cc + 16 * half;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (f0 + i < pw.in) atomicAdd(pg.W1 + (size_t)(f0 + i) * U + u, d[i]);
+      }
+    };
+#pragma unroll
+    for (int b = 0; b < PD; ++b)
+      if (b < np) load_x(xr[b], xp, rowoff, row, 32 * b + 16 * half);
+    for (int c = 0; c < np; c += PD) {
+#pragma unroll
+      for (int b = 0; b < PD; ++b) {
+        if (c + b < np) {
+          const int cc = c + b, s = cc & 1;
+          if (cc >= 2) mbar_wait_bounded(&bars.xs_free[s], ((cc >> 1) - 1) & 1);
+          unsigned char* img = smem + LA::R1 + s * (2 * LA::XS_IMG);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 hi, lo;
+            umma::split_tf32(xr[b].v[4 * q + 0], hi.x, lo.x);
+            umma::split_tf32(xr[b].v[4 * q + 1], hi.y, lo.y);
+            umma::split_tf32(xr[b].v[4 * q + 2], hi.z, lo.z);
+            umma::split_tf32(xr[b].v[4 * q + 3], hi.w, lo.w);
+            const uint32_t off = umma::sw128b32_off(row, 16 * half + 4 * q);
+            *reinterpret_cast<float4*>(img + off) = hi;
+            *reinterpret_cast<float4*>(img + LA::XS_IMG + off) = lo;
+          }
+          umma::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.xs_full[s])) : "memory");
+          if (cc + PD < np) load_x(xr[b], xp, rowoff, row, 32 * (cc + PD) + 16 * half);
+          if (cc >= 1) readout(cc - 1);
+        }
+      }
+    }
+    readout(np - 1);
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
+}
+
 }  // namespace tc
 
 // host side -------------------------------------------------------------------------------------------------
@@ -994,6 +1442,32 @@ int launch_critic_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t
   MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<dim3(cdiv(B, tc::TMR), count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, y, q_out, idx_stride, y_stride);
   return check_launch("k_critic_grads_tc");
+}
+
+int launch_actor_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,
+                          const float* batch, const long long* ridx, long long idx_stride, const float* u_actor, int32_t u_stride,
+                          uint64_t seed, uint64_t counter, cudaStream_t st) {
+  if (c->cfg.num_units != 64) return fail(MDP_ENOTSUP, "tensor-core path: num_units %d (64 only)", c->cfg.num_units);
+  for (int k = agent; k < agent + count; ++k)
+    if (c->cfg.local_q[k]) return fail(MDP_ENOTSUP, "tensor-core actor path: local critics use the SIMT kernels");
+  constexpr int U = 64;
+  using LA = tc::LayA<U>;
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  const tc::AgentImg* imgs = reinterpret_cast<const tc::AgentImg*>(c->tc_imgs);
+  int max_in = 0;
+  for (int k = agent; k < agent + count; ++k) max_in = std::max(max_in, c->lay.net_in[k][MDP_NET_Q]);
+  const int bx = std::min(64, cdiv(((max_in + 31) / 32 * 32 + U) * U, 256 * 4));
+  // images of the running actor and the running critic of every agent in the slice
+  tc::k_build_images<U><<<dim3(bx, 2 * count), 256, 0, st>>>(d, imgs, count, agent, agent, MDP_NET_P, MDP_NET_Q);
+  rc = check_launch("k_build_images");
+  if (rc) return rc;
+  const size_t smem = LA::OFF_MISC + (size_t)LA::MISC_FLOATS * 4 + 1024 + 64;
+  auto kern = tc::k_actor_grads_tc<U>;
+  MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(cdiv(B, tc::TMR), count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter,
+                                                             idx_stride);
+  return check_launch("k_actor_grads_tc");
 }
 
 }  // namespace mdp

@@ -147,3 +147,54 @@ def test_critic_grads_tensor_cores_many_tiles_grouped():
         outs.append(core.grads.clone())
     scale = float(outs[0].abs().max())
     _close(outs[1].cpu().numpy(), outs[0].cpu().numpy(), rtol=1e-4, atol=2e-5 * scale, msg="grouped critic grads")
+
+
+@pytest.mark.parametrize("name", [n for n in TC_CASES if "ddpg" not in n])
+def test_actor_grads_tensor_cores_match_oracle_and_simt(name):
+    """p_train on tcgen05 (actor forward, Gumbel sample, running-critic forward/backward to the action columns, actor
+    backward) after the critic's Adam step, vs the oracle's actor gradients and vs the SIMT kernel."""
+    case = trainer_case(name, seed=2)
+    ref = oracle_update_round(trainer_case(name, seed=2))
+    trainers, core = _build(case)
+    j, B = 0, case["B"]
+    idx = core.ring.index_tensor(case["idx"][j])
+    core.set_tensor_cores(-1)
+    y = core.td_target(j, core.ring.ring, _ut(core, case, j, B), idx=idx)
+    core.critic_grads(j, core.ring.ring, y, idx=idx)
+    core.clip_adam_polyak(j, 1)
+    ua = torch.zeros((B, core.act_stride), device="cuda")
+    o = core.act_off[j]
+    ua[:, o:o + core.act_dims[j]] = torch.from_numpy(case["u_actor"][j]).cuda()
+    outs, stats = [], []
+    for mode in (-1, 1):
+        core.grads.zero_()
+        s0 = core.stats[8 * j:8 * j + 3].clone()
+        core.set_tensor_cores(mode)
+        core.actor_grads(j, core.ring.ring, ua, idx=idx)
+        outs.append([g.clone() for g in core.train_view(core.grads, j, 0)])
+        stats.append((core.stats[8 * j:8 * j + 3] - s0).cpu().numpy())
+    _close(stats[1][1:], stats[0][1:], rtol=1e-4, atol=1e-6, msg="sum(-q), sum(logits^2)")
+    names = ["W1", "b1", "W2", "b2", "W3", "b3"]
+    for k, (a, b, r) in enumerate(zip(outs[1], outs[0], ref[j]["p_grads"])):
+        scale = float(np.abs(r).max())
+        _close(a.cpu().numpy(), r, rtol=2e-3, atol=1e-7 + 2e-4 * scale, msg="actor grad %s vs oracle" % names[k])
+        _close(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-4, atol=1e-8 + 5e-5 * scale, msg="actor grad %s vs SIMT" % names[k])
+
+
+def test_actor_grads_tensor_cores_many_tiles_philox():
+    """Several tiles with a ragged tail, in-kernel Philox noise, every agent of simple_spread N=6 and simple_tag."""
+    for name in ("simple_spread_6", "simple_tag"):
+        case = trainer_case(name, seed=8)
+        trainers, core = _build(case)
+        rows, n = case["rows"], case["n"]
+        idx = torch.randperm(rows, device="cuda")[:rows - 5].contiguous()
+        for j in range(n):
+            outs = []
+            for mode in (-1, 1):
+                core.grads.zero_()
+                core.counter = 50
+                core.set_tensor_cores(mode)
+                core.actor_grads(j, core.ring.ring, idx=idx)
+                outs.append(core.grads.clone())
+            scale = float(outs[0].abs().max())
+            _close(outs[1].cpu().numpy(), outs[0].cpu().numpy(), rtol=2e-4, atol=5e-5 * scale, msg="%s agent %d" % (name, j))
