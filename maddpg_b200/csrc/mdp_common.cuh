@@ -117,6 +117,16 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   }
 }
 
+// Fire-and-forget fp32 reductions into the gradient bucket.  `atomicAdd(float*)` on a pointer the compiler cannot prove to be
+// global (the gradient pointers come out of a device-side table) lowers to a RETURNING generic atomic plus shared/local CAS-spin
+// fallbacks (ATOM.E.ADD + ATOM.CAST.SPIN); the explicit .global RED forms are one instruction, non-blocking, and vectorisable.
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {  // p 16-byte aligned
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Gumbel-softmax noise term -log(-log(u)) in float32 (distributions.py:264-266)
 __device__ __forceinline__ float gumbel_from_u(float u) { return -logf(-logf(u)); }
 

@@ -400,8 +400,8 @@ __device__ __forceinline__ void grad_w_hidden(const Grp& G, const float* __restr
 #pragma unroll
   for (int a = 0; a < RN; ++a)
 #pragma unroll
-    for (int b = 0; b < RN; ++b)
-      atomicAdd(gW + (size_t)(ty * RN + a) * U + (b / 4) * 64 + 4 * tx + (b & 3), acc[a][b]);
+    for (int b = 0; b < RN; b += 4)
+      red_add4(gW + (size_t)(ty * RN + a) * U + (b / 4) * 64 + 4 * tx, acc[a][b], acc[a][b + 1], acc[a][b + 2], acc[a][b + 3]);
 }
 
 // gW1 rows [k0, k0+KC) += sX^T (TM x KC chunk) * sD (TM x U)
@@ -437,7 +437,8 @@ __device__ __forceinline__ void grad_w_chunk(const Grp& G, const float* __restri
     const int k = k0 + 2 * ty + rr;
     if (k < K) {
 #pragma unroll
-      for (int b = 0; b < RN; ++b) atomicAdd(gW1 + (size_t)k * U + (b / 4) * 64 + 4 * tx + (b & 3), acc[rr][b]);
+      for (int b = 0; b < RN; b += 4)
+        red_add4(gW1 + (size_t)k * U + (b / 4) * 64 + 4 * tx, acc[rr][b], acc[rr][b + 1], acc[rr][b + 2], acc[rr][b + 3]);
     }
   }
 }
@@ -448,7 +449,7 @@ __device__ __forceinline__ void grad_bias(const Grp& G, const float* __restrict_
   if (G.tid < U) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s += sD[r * HP + G.tid];
-    atomicAdd(gb + G.tid, s);
+    red_add(gb + G.tid, s);
   }
 }
 

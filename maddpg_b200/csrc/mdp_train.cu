@@ -244,11 +244,11 @@ __global__ void __launch_bounds__(NT) k_critic_grads(CoreDev C, int j0, mdp_ring
   if (threadIdx.x < U) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s = fmaf(sH2[r * HP + threadIdx.x], sDq[r], s);
-    atomicAdd(g.W3 + threadIdx.x, s);
+    red_add(g.W3 + threadIdx.x, s);
   } else if (threadIdx.x == U) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s += sDq[r];
-    atomicAdd(g.b3, s);
+    red_add(g.b3, s);
   }
   __syncthreads();
   // dz2 = dq * W3^T * relu'(h2), in place over h2
@@ -379,12 +379,12 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j0, mdp_ring_
     const int u = idx / K, a = idx - u * K;
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s = fmaf(sP2[r * HP + u], sDa[r * KPAD + a], s);
-    atomicAdd(pg.W3 + idx, s);
+    red_add(pg.W3 + idx, s);
   }
   if (threadIdx.x < K) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s += sDa[r * KPAD + threadIdx.x];
-    atomicAdd(pg.b3 + threadIdx.x, s);
+    red_add(pg.b3 + threadIdx.x, s);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
@@ -566,11 +566,11 @@ __global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j0, mdp_
   if (threadIdx.x < U) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s = fmaf(sH2[r * HP + threadIdx.x], sDq[r], s);
-    atomicAdd(g.W3 + threadIdx.x, s);
+    red_add(g.W3 + threadIdx.x, s);
   } else if (threadIdx.x == U) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s += sDq[r];
-    atomicAdd(g.b3, s);
+    red_add(g.b3, s);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
@@ -685,12 +685,12 @@ __global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j0, mdp_r
     const int u = idx / K, a = idx - u * K;
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s = fmaf(sP2[r * HP + u], sDa[r * KPAD + a], s);
-    atomicAdd(pg.W3 + idx, s);
+    red_add(pg.W3 + idx, s);
   }
   if (threadIdx.x < K) {
     float s = 0.f;
     for (int r = 0; r < TM; ++r) s += sDa[r * KPAD + threadIdx.x];
-    atomicAdd(pg.b3 + threadIdx.x, s);
+    red_add(pg.b3 + threadIdx.x, s);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < TM * U; idx += NT) {

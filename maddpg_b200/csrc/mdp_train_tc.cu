@@ -236,18 +236,24 @@ __device__ __forceinline__ void mma_net(unsigned char* smem, Bars* bars, Pipe& p
     mbar_wait_bounded(&bars->stage_w[s], ph);
     umma::fence_after();
     const uint32_t so = s * ((2 * L::W_IMG) >> 4);  // smem slot offset in descriptor units
-    issue_3x<U, 4>(tbase + L::T_ACC1, tbase + L::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, c > 0 ? 1u : 0u);
-    umma::commit(&bars->stage_free[s]);
-    if (c == nchunks - 1) umma::commit(&bars->acc);
+    if (umma::elect_one()) {
+      issue_3x<U, 4>(tbase + L::T_ACC1, tbase + L::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, c > 0 ? 1u : 0u);
+      umma::commit(&bars->stage_free[s]);
+      if (c == nchunks - 1) umma::commit(&bars->acc);
+    }
+    __syncwarp();
     pipe.chunks++;
   }
   mbar_wait_bounded(&bars->h1_full, pipe.nets & 1u);
   mbar_wait_bounded(&bars->w2_full, pipe.nets & 1u);
   umma::fence_after();
   const uint32_t wa = smem_u32(smem + L::OFF_W2);
-  issue_3x<U, U / 8>(tbase + L::T_ACC2, tbase + L::T_H1, U, umma::desc_k(wa, L::W_IMG, 0), umma::desc_k(wa + L::W2_IMG, L::W_IMG, 0), 0u);
-  umma::commit(&bars->acc);
-  umma::commit(&bars->w2_free);
+  if (umma::elect_one()) {
+    issue_3x<U, U / 8>(tbase + L::T_ACC2, tbase + L::T_H1, U, umma::desc_k(wa, L::W_IMG, 0), umma::desc_k(wa + L::W2_IMG, L::W_IMG, 0), 0u);
+    umma::commit(&bars->acc);
+    umma::commit(&bars->w2_free);
+  }
+  __syncwarp();
   pipe.nets++;
 }
 
@@ -411,11 +417,10 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
       produce_net<U>(smem, &bars, pipe, imgs[j].net[MDP_NET_TARGET_Q], me.net[MDP_NET_TARGET_Q].in);
     }
   } else if (warp == NTC / 32 + 1) {
-    // ===== MMA issuer warp =====
-    if (lane == 0) {
-      for (int i = i_begin; i < i_end; ++i) mma_net<U>(smem, &bars, pipe, tbase, C.agents[i].obs_dim);
-      mma_net<U>(smem, &bars, pipe, tbase, me.net[MDP_NET_TARGET_Q].in);
-    }
+    // ===== MMA issuer warp (all lanes run the loops; one elected lane issues) =====
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    for (int i = i_begin; i < i_end; ++i) mma_net<U>(smem, &bars, pipe, tb, C.agents[i].obs_dim);
+    mma_net<U>(smem, &bars, pipe, tb, me.net[MDP_NET_TARGET_Q].in);
   } else {
     // ===== compute warps =====
     float h2[U / 2];
@@ -690,46 +695,56 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
       bulk_g2s(smem + LB::R2, img.w2n, 2 * LY::W2_IMG, &bars.w2n_full);
     }
   } else if (warp == NTC / 32 + 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint64_t w_hi0 = umma::desc_k(sbase + LB::R1, LY::W_IMG, 0), w_lo0 = umma::desc_k(sbase + LB::R1 + LY::W_IMG, LY::W_IMG, 0);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % NS, ph = (c / NS) & 1;
-        mbar_wait_bounded(&bars.stage_x[s], ph);
-        mbar_wait_bounded(&bars.stage_w[s], ph);
-        umma::fence_after();
-        const uint32_t so = s * ((2 * LY::W_IMG) >> 4);
-        issue_3x<U, 4>(tbase + LY::T_ACC1, tbase + LY::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, c > 0 ? 1u : 0u);
+    // ===== MMA issuer (all lanes run the loops; one elected lane issues) =====
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint64_t w_hi0 = umma::desc_k(sbase + LB::R1, LY::W_IMG, 0), w_lo0 = umma::desc_k(sbase + LB::R1 + LY::W_IMG, LY::W_IMG, 0);
+    const uint64_t r2_hi = umma::desc_k(sbase + LB::R2, LY::W_IMG, 0), r2_lo = umma::desc_k(sbase + LB::R2 + LY::W2_IMG, LY::W_IMG, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % NS, ph = (c / NS) & 1;
+      mbar_wait_bounded(&bars.stage_x[s], ph);
+      mbar_wait_bounded(&bars.stage_w[s], ph);
+      umma::fence_after();
+      const uint32_t so = s * ((2 * LY::W_IMG) >> 4);
+      if (umma::elect_one()) {
+        issue_3x<U, 4>(tb + LY::T_ACC1, tb + LY::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, c > 0 ? 1u : 0u);
         umma::commit(&bars.stage_free[s]);
         if (c == nchunks - 1) umma::commit(&bars.acc);
       }
-      mbar_wait_bounded(&bars.h1_full, 0);
-      mbar_wait_bounded(&bars.w2_full, 0);
-      umma::fence_after();
-      issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, umma::desc_k(sbase + LB::R2, LY::W_IMG, 0),
-                         umma::desc_k(sbase + LB::R2 + LY::W2_IMG, LY::W_IMG, 0), 0u);
+      __syncwarp();
+    }
+    mbar_wait_bounded(&bars.h1_full, 0);
+    mbar_wait_bounded(&bars.w2_full, 0);
+    umma::fence_after();
+    if (umma::elect_one()) {
+      issue_3x<U, U / 8>(tb + LY::T_ACC2, tb + LY::T_H1, U, r2_hi, r2_lo, 0u);
       umma::commit(&bars.acc);
       umma::commit(&bars.l2_done);
-      // backward: dW2 = h1^T dz2 (acc1, M = 64) and dh1 = dz2 W2^T (acc2)
-      mbar_wait_bounded(&bars.dz2_full, 0);
-      mbar_wait_bounded(&bars.w2n_full, 0);
-      umma::fence_after();
-      issue_3x_mn<U, U, TMR / 8>(tbase + LY::T_ACC1, sbase + LB::R3, LB::ACT_IMG, TMR * 128, sbase + LB::R1, LB::ACT_IMG, TMR * 128);
-      issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, umma::desc_k(sbase + LB::R2, LY::W_IMG, 0),
-                         umma::desc_k(sbase + LB::R2 + LY::W2_IMG, LY::W_IMG, 0), 0u);
+    }
+    __syncwarp();
+    // backward: dW2 = h1^T dz2 (acc1, M = 64) and dh1 = dz2 W2^T (acc2)
+    mbar_wait_bounded(&bars.dz2_full, 0);
+    mbar_wait_bounded(&bars.w2n_full, 0);
+    umma::fence_after();
+    if (umma::elect_one()) {
+      issue_3x_mn<U, U, TMR / 8>(tb + LY::T_ACC1, sbase + LB::R3, LB::ACT_IMG, TMR * 128, sbase + LB::R1, LB::ACT_IMG, TMR * 128);
+      issue_3x<U, U / 8>(tb + LY::T_ACC2, tb + LY::T_H1, U, r2_hi, r2_lo, 0u);
       umma::commit(&bars.acc);
-      // dW1^T chunks: D[u][f] = sum_r dz1[r][u] X[r][f]
-      mbar_wait_bounded(&bars.dz1_full, 0);
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c & 1, t = c & 3;
-        mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
-        if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
-        umma::fence_after();
-        issue_3x_mn<U, 32, TMR / 8>(tbase + LB::T_DW + t * 32, sbase + LB::R3, LB::ACT_IMG, TMR * 128,
+    }
+    __syncwarp();
+    // dW1^T chunks: D[u][f] = sum_r dz1[r][u] X[r][f]
+    mbar_wait_bounded(&bars.dz1_full, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, t = c & 3;
+      mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
+      if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
+      umma::fence_after();
+      if (umma::elect_one()) {
+        issue_3x_mn<U, 32, TMR / 8>(tb + LB::T_DW + t * 32, sbase + LB::R3, LB::ACT_IMG, TMR * 128,
                                    sbase + LB::R1 + s * (2 * LB::XS_IMG), LB::XS_IMG, TMR * 128);
         umma::commit(&bars.xs_free[s]);
         umma::commit(&bars.dw_full[t]);
       }
+      __syncwarp();
     }
   } else {
     // ===== compute warps: thread = (batch row, unit half) =====
@@ -799,7 +814,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
       }
       if (lane == 0) {
         atomicAdd(C.stats + 8 * j + 0, se);
-        atomicAdd(g.b3, ds);
+        red_add(g.b3, ds);
       }
     }
     named_sync();
@@ -809,7 +824,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
 #pragma unroll
       for (int i = 0; i < 32; ++i) t[i] = v[i] * dq;  // gW3[u] = sum_r h2[r][u] dq[r]
       const float sum = warp_colsum32(t, lane);
-      atomicAdd(g.W3 + c0 + lane, sum);
+      red_add(g.W3 + c0 + lane, sum);
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = ((mask2 >> i) & 1u) ? dq * sW3[c0 + i] : 0.f;  // dz2 = dq W3^T relu'(h2)
@@ -818,7 +833,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
     warp_arrive_both(&bars.dz2_full, lane);
     {
       const float sum = warp_colsum32(v, lane);  // gb2 = sum_r dz2
-      atomicAdd(g.b2 + c0 + lane, sum);
+      red_add(g.b2 + c0 + lane, sum);
     }
     // ---- epilogue 3: dW2 tile -> gradient bucket; dz1 = dh1 relu'(h1) -> MN-major images (A of dW1^T)
     mbar_wait_bounded(&bars.acc, 0);
@@ -837,7 +852,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
     warp_arrive_both(&bars.dz1_full, lane);
     {
       const float sum = warp_colsum32(v, lane);  // gb1 = sum_r dz1
-      atomicAdd(g.b1 + c0 + lane, sum);
+      red_add(g.b1 + c0 + lane, sum);
     }
     // ---- dW1: stage X chunk c as an MN-major image pair, read out the accumulator of chunk c - 1
     auto readout = [&](int cc) {
@@ -853,7 +868,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
         const int u = 16 * (warp & 3) + lane, f0 = 32 * cc + 16 * half;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (f0 + i < w.in) atomicAdd(g.W1 + (size_t)(f0 + i) * U + u, d[i]);
+          if (f0 + i < w.in) red_add(g.W1 + (size_t)(f0 + i) * U + u, d[i]);
       }
     };
 #pragma unroll
@@ -1015,53 +1030,63 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
       load_r2(ip.w2n);
     }
   } else if (warp == NTC / 32 + 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint64_t w_hi0 = umma::desc_k(sbase + LA::R1, LY::W_IMG, 0), w_lo0 = umma::desc_k(sbase + LA::R1 + LY::W_IMG, LY::W_IMG, 0);
-      const uint64_t r2_hi = umma::desc_k(sbase + LA::R2, LY::W_IMG, 0), r2_lo = umma::desc_k(sbase + LA::R2 + LY::W2_IMG, LY::W_IMG, 0);
-      auto layer1 = [&](int n, int cbase) {
-        for (int k = 0; k < n; ++k) {
-          const int c = cbase + k, s = c % NS, ph = (c / NS) & 1;
-          mbar_wait_bounded(&bars.stage_x[s], ph);
-          mbar_wait_bounded(&bars.stage_w[s], ph);
-          umma::fence_after();
-          const uint32_t so = s * ((2 * LY::W_IMG) >> 4);
-          issue_3x<U, 4>(tbase + LY::T_ACC1, tbase + LY::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, k > 0 ? 1u : 0u);
+    // ===== MMA issuer (all lanes run the loops; one elected lane issues) =====
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    const uint64_t w_hi0 = umma::desc_k(sbase + LA::R1, LY::W_IMG, 0), w_lo0 = umma::desc_k(sbase + LA::R1 + LY::W_IMG, LY::W_IMG, 0);
+    const uint64_t r2_hi = umma::desc_k(sbase + LA::R2, LY::W_IMG, 0), r2_lo = umma::desc_k(sbase + LA::R2 + LY::W2_IMG, LY::W_IMG, 0);
+    auto layer1 = [&](int n, int cbase) {
+      for (int k = 0; k < n; ++k) {
+        const int c = cbase + k, s = c % NS, ph = (c / NS) & 1;
+        mbar_wait_bounded(&bars.stage_x[s], ph);
+        mbar_wait_bounded(&bars.stage_w[s], ph);
+        umma::fence_after();
+        const uint32_t so = s * ((2 * LY::W_IMG) >> 4);
+        if (umma::elect_one()) {
+          issue_3x<U, 4>(tb + LY::T_ACC1, tb + LY::T_X + s * 64, 32, w_hi0 + so, w_lo0 + so, k > 0 ? 1u : 0u);
           umma::commit(&bars.stage_free[s]);
+          if (k == n - 1) umma::commit(&bars.acc);
         }
-        umma::commit(&bars.acc);
-      };
-      auto from_h1 = [&](int a_phase, int r2_phase) {  // acc2 = (TMEM H1 region) x (R2 images)^T
-        mbar_wait_bounded(&bars.a_full, a_phase);
-        mbar_wait_bounded(&bars.r2_full, r2_phase);
-        umma::fence_after();
-        issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, r2_hi, r2_lo, 0u);
-      };
-      layer1(np, 0);                                   // acc phase 0: z1p
-      from_h1(0, 0);                                   // z2p = h1p W2p
-      umma::commit(&bars.acc); umma::commit(&bars.r2_free);
-      layer1(nq, np);                                  // acc phase 2: z1q
-      from_h1(1, 1);                                   // z2q = h1q W2q
-      umma::commit(&bars.acc); umma::commit(&bars.r2_free);
-      from_h1(0, 0);                                   // dh1q = dz2q W2q^T
-      umma::commit(&bars.acc); umma::commit(&bars.r2_free);
-      mbar_wait_bounded(&bars.a_full, 1);              // dz2p: TMEM operand + MN-major images
-      mbar_wait_bounded(&bars.r2_full, 1);
+        __syncwarp();
+      }
+    };
+    auto from_h1 = [&](int a_phase, int r2_phase, bool frees_r2) {  // acc2 = (TMEM H1 region) x (R2 images)^T
+      mbar_wait_bounded(&bars.a_full, a_phase);
+      mbar_wait_bounded(&bars.r2_full, r2_phase);
       umma::fence_after();
-      issue_3x_mn<U, U, TMR / 8>(tbase + LY::T_ACC1, sbase + LA::S1, LA::ACT_IMG, TMR * 128, sbase + LA::R1, LA::ACT_IMG, TMR * 128);
-      issue_3x<U, U / 8>(tbase + LY::T_ACC2, tbase + LY::T_H1, U, r2_hi, r2_lo, 0u);  // dh1p = dz2p W2p^T
-      umma::commit(&bars.acc);
-      mbar_wait_bounded(&bars.dz1_full, 0);
-      for (int c = 0; c < np; ++c) {  // dW1p^T chunks
-        const int s = c & 1, t = c & 3;
-        mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
-        if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
-        umma::fence_after();
-        issue_3x_mn<U, 32, TMR / 8>(tbase + LA::T_DW + t * 32, sbase + LA::S1, LA::ACT_IMG, TMR * 128,
+      if (umma::elect_one()) {
+        issue_3x<U, U / 8>(tb + LY::T_ACC2, tb + LY::T_H1, U, r2_hi, r2_lo, 0u);
+        umma::commit(&bars.acc);
+        if (frees_r2) umma::commit(&bars.r2_free);
+      }
+      __syncwarp();
+    };
+    layer1(np, 0);            // acc phase 0: z1p
+    from_h1(0, 0, true);      // acc phase 1: z2p = h1p W2p
+    layer1(nq, np);           // acc phase 2: z1q
+    from_h1(1, 1, true);      // acc phase 3: z2q = h1q W2q
+    from_h1(0, 0, true);      // acc phase 4: dh1q = dz2q W2q^T
+    mbar_wait_bounded(&bars.a_full, 1);  // dz2p: TMEM operand + MN-major images
+    mbar_wait_bounded(&bars.r2_full, 1);
+    umma::fence_after();
+    if (umma::elect_one()) {
+      issue_3x_mn<U, U, TMR / 8>(tb + LY::T_ACC1, sbase + LA::S1, LA::ACT_IMG, TMR * 128, sbase + LA::R1, LA::ACT_IMG, TMR * 128);
+      issue_3x<U, U / 8>(tb + LY::T_ACC2, tb + LY::T_H1, U, r2_hi, r2_lo, 0u);  // dh1p = dz2p W2p^T
+      umma::commit(&bars.acc);  // acc phase 5
+    }
+    __syncwarp();
+    mbar_wait_bounded(&bars.dz1_full, 0);
+    for (int c = 0; c < np; ++c) {  // dW1p^T chunks
+      const int s = c & 1, t = c & 3;
+      mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
+      if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
+      umma::fence_after();
+      if (umma::elect_one()) {
+        issue_3x_mn<U, 32, TMR / 8>(tb + LA::T_DW + t * 32, sbase + LA::S1, LA::ACT_IMG, TMR * 128,
                                    sbase + LA::R1 + s * (2 * LA::XS_IMG), LA::XS_IMG, TMR * 128);
         umma::commit(&bars.xs_free[s]);
         umma::commit(&bars.dw_full[t]);
       }
+      __syncwarp();
     }
   } else {
     // ===== compute warps: thread = (batch row, unit half) =====
@@ -1245,13 +1270,13 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
 #pragma unroll
       for (int i = 0; i < 32; ++i) t[i] = h2p[i] * dl[a];
       const float sum = warp_colsum32(t, lane);
-      atomicAdd(pg.W3 + (size_t)(c0 + lane) * K + a, sum);
+      red_add(pg.W3 + (size_t)(c0 + lane) * K + a, sum);
     }
     if (half == 0)
       for (int a = 0; a < K; ++a) {
         float sb = dl[a];
         for (int o = 16; o > 0; o >>= 1) sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        if (lane == 0) atomicAdd(pg.b3 + a, sb);
+        if (lane == 0) red_add(pg.b3 + a, sb);
       }
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -1266,7 +1291,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     warp_arrive_both(&bars.a_full, lane);                    // a_full phase 3
     {
       const float sum = warp_colsum32(v, lane);
-      atomicAdd(pg.b2 + c0 + lane, sum);
+      red_add(pg.b2 + c0 + lane, sum);
     }
     // ---- dW2p tile out, dz1p images in
     mbar_wait_bounded(&bars.acc, 1);
@@ -1285,7 +1310,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     warp_arrive_both(&bars.dz1_full, lane);
     {
       const float sum = warp_colsum32(v, lane);
-      atomicAdd(pg.b1 + c0 + lane, sum);
+      red_add(pg.b1 + c0 + lane, sum);
     }
     // ---- dW1p: stage X_p chunk c as an MN-major image pair, read out the accumulator of chunk c - 1
     auto readout = [&](int cc) {
@@ -1301,7 +1326,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
         const int u = 16 * (warp & 3) + lane, f0 = 32 * cc + 16 * half;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (f0 + i < pw.in) atomicAdd(pg.W1 + (size_t)(f0 + i) * U + u, d[i]);
+          if (f0 + i < pw.in) red_add(pg.W1 + (size_t)(f0 + i) * U + u, d[i]);
       }
     };
 #pragma unroll

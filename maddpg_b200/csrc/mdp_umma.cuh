@@ -74,6 +74,15 @@ __device__ __forceinline__ void mma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, ui
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of a converged warp (always the same one).  The MMA issuer warps run their loops with ALL lanes and put only
+// the tcgen05.mma / tcgen05.commit under this predicate: the descriptors are then warp-uniform values that ptxas keeps in
+// uniform registers (0-1 SASS instructions between MMAs), whereas an `if (lane == 0)` region makes them per-thread values that
+// need an ELECT / R2UR sequence per operand (5-15 instructions per MMA -- the issuing thread was the bottleneck of the pipeline).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // arrives on `bar` once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
