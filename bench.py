@@ -182,7 +182,7 @@ def tensor_core_section(torch, dev):
                        "batch 1024, critic input 3576, num_units 64", "algorithmic_flops_per_launch": flops, "bound": "tensor",
            "peak_tf32_dense_tflops_nominal": 1100.0, "mma_issue_multiplier": 3,
            "note": "every GEMM is issued as 3 kind::tf32 MMAs (hi/lo split) to hold the 1e-4 parity bar; tensor-pipe "
-                   "activity from ncu: profiles/r1_td_target_tc_cfg5_grouped.txt"}
+                   "activity from ncu: profiles/r1_update_tc_cfg5_grouped.txt"}
     for name, mode in (("tcgen05", 1), ("simt_fp32", -1)):
         core.set_tensor_cores(mode)
         for _ in range(3):
