@@ -105,7 +105,7 @@ SYMBOLS = {
     "mdp_launch_count": (C.c_int64, []),
 }
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libmaddpg_b200.so")
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.environ.get("MDP_LIB_NAME", "libmaddpg_b200.so"))
 
 
 def _load():

@@ -618,6 +618,74 @@ __device__ __forceinline__ void warp_arrive_both(unsigned long long* bar, int la
   if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// dW1^T = dz1^T X, the chunk loop of the weight-gradient phase, with the eight compute warps split into two roles so that
+// neither sits on the other's latency chain: warps 0-3 ("stagers", thread = batch row) gather all 32 columns of a chunk,
+// split them and store the MN-major image pair; warps 4-7 ("readers") pull the finished 64 x 32 accumulator of the previous
+// chunks out of TMEM and reduce it into the gradient bucket.  xs_full / dw_free therefore count four warp arrivals.
+template <int U, typename BarsT>
+__device__ __forceinline__ void dw1_chunk_loop(BarsT& bars, unsigned char* x_slots, uint32_t xs_img_bytes, uint32_t tdw, const XT& xs,
+                                               long long rowoff, int nchunks, int in_dim, float* __restrict__ gW1, int warp, int lane) {
+  const int row = 32 * (warp & 3) + lane;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  if (warp < 4) {
+    XRegs xa[2][2];  // two chunks in flight, 2 x 16 columns each
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+      if (b < nchunks) {
+        load_x(xa[b][0], xs, rowoff, row, 32 * b);
+        load_x(xa[b][1], xs, rowoff, row, 32 * b + 16);
+      }
+    for (int c = 0; c < nchunks; c += 2) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (c + b < nchunks) {
+          const int cc = c + b, s = cc & 1;
+          if (cc >= 2) mbar_wait_bounded(&bars.xs_free[s], ((cc >> 1) - 1) & 1);
+          unsigned char* img = x_slots + s * (2 * xs_img_bytes);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float4 hi, lo;
+              umma::split_tf32(xa[b][h].v[4 * q + 0], hi.x, lo.x);
+              umma::split_tf32(xa[b][h].v[4 * q + 1], hi.y, lo.y);
+              umma::split_tf32(xa[b][h].v[4 * q + 2], hi.z, lo.z);
+              umma::split_tf32(xa[b][h].v[4 * q + 3], hi.w, lo.w);
+              const uint32_t off = umma::sw128b32_off(row, 16 * h + 4 * q);
+              *reinterpret_cast<float4*>(img + off) = hi;
+              *reinterpret_cast<float4*>(img + xs_img_bytes + off) = lo;
+            }
+          umma::fence_async_smem();
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.xs_full[s])) : "memory");
+          if (cc + 2 < nchunks) {
+            load_x(xa[b][0], xs, rowoff, row, 32 * (cc + 2));
+            load_x(xa[b][1], xs, rowoff, row, 32 * (cc + 2) + 16);
+          }
+        }
+      }
+    }
+  } else {
+    for (int cc = 0; cc < nchunks; ++cc) {
+      const int t = cc & 3;
+      mbar_wait_bounded(&bars.dw_full[t], (cc >> 2) & 1);
+      umma::fence_after();
+      float d[32];
+      umma::tmem_ld32(tdw + t * 32 + lane_base, d);  // M = 64: unit u = 16 (w & 3) + lane lives on lanes < 16 of each quarter
+      umma::fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.dw_free[t])) : "memory");
+      if (lane < 16) {
+        const int u = 16 * (warp & 3) + lane, f0 = 32 * cc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (f0 + i < in_dim) red_add(gW1 + (size_t)(f0 + i) * U + u, d[i]);
+      }
+    }
+  }
+}
+
 template <int U>
 __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const AgentImg* __restrict__ imgs, int j0, mdp_ring_layout L, int B,
                                                             const float* __restrict__ batch, const long long* __restrict__ ridx,
@@ -660,8 +728,8 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
     mbar_init(&bars.w2_full, 1); mbar_init(&bars.h1_full, NTC / 32); mbar_init(&bars.acc, 1);
     mbar_init(&bars.l2_done, 1); mbar_init(&bars.w2n_full, 1);
     mbar_init(&bars.dz2_full, NTC / 32); mbar_init(&bars.dz1_full, NTC / 32);
-    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 32); mbar_init(&bars.xs_free[k], 1); }
-    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 32); }
+    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 64); mbar_init(&bars.xs_free[k], 1); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 64); }
     if (blockIdx.x == 0) C.adam_t[2 * j + 1] += 1;  // one more Adam step for this net
   }
   if (tid < TMR) {
@@ -854,53 +922,8 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
       const float sum = warp_colsum32(v, lane);  // gb1 = sum_r dz1
       red_add(g.b1 + c0 + lane, sum);
     }
-    // ---- dW1: stage X chunk c as an MN-major image pair, read out the accumulator of chunk c - 1
-    auto readout = [&](int cc) {
-      const int t = cc & 3;
-      mbar_wait_bounded(&bars.dw_full[t], (cc >> 2) & 1);
-      umma::fence_after();
-      float d[16];
-      umma::tmem_ld16(tbase + LB::T_DW + t * 32 + lane_base + (uint32_t)(16 * half), d);
-      umma::fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.dw_free[t])) : "memory");
-      if (lane < 16) {
-        const int u = 16 * (warp & 3) + lane, f0 = 32 * cc + 16 * half;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (f0 + i < w.in) red_add(g.W1 + (size_t)(f0 + i) * U + u, d[i]);
-      }
-    };
-#pragma unroll
-    for (int b = 0; b < PD; ++b)
-      if (b < nchunks) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
-    for (int c = 0; c < nchunks; c += PD) {
-#pragma unroll
-      for (int b = 0; b < PD; ++b) {
-        if (c + b < nchunks) {
-          const int cc = c + b, s = cc & 1;
-          if (cc >= 2) mbar_wait_bounded(&bars.xs_free[s], ((cc >> 1) - 1) & 1);
-          unsigned char* img = smem + LB::R1 + s * (2 * LB::XS_IMG);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 hi, lo;
-            umma::split_tf32(xr[b].v[4 * q + 0], hi.x, lo.x);
-            umma::split_tf32(xr[b].v[4 * q + 1], hi.y, lo.y);
-            umma::split_tf32(xr[b].v[4 * q + 2], hi.z, lo.z);
-            umma::split_tf32(xr[b].v[4 * q + 3], hi.w, lo.w);
-            const uint32_t off = umma::sw128b32_off(row, 16 * half + 4 * q);
-            *reinterpret_cast<float4*>(img + off) = hi;
-            *reinterpret_cast<float4*>(img + LB::XS_IMG + off) = lo;
-          }
-          umma::fence_async_smem();
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.xs_full[s])) : "memory");
-          if (cc + PD < nchunks) load_x(xr[b], xs, rowoff, row, 32 * (cc + PD) + 16 * half);
-          if (cc >= 1) readout(cc - 1);
-        }
-      }
-    }
-    readout(nchunks - 1);
+    // ---- dW1^T chunks: stager warps / reader warps
+    dw1_chunk_loop<U>(bars, smem + LB::R1, LB::XS_IMG, tbase + LB::T_DW, xs, rowoff, nchunks, w.in, g.W1, warp, lane);
   }
   umma::fence_before();
   __syncthreads();
@@ -981,8 +1004,8 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     }
     mbar_init(&bars.a_full, NTC / 32); mbar_init(&bars.r2_full, 1); mbar_init(&bars.r2_free, 1);
     mbar_init(&bars.acc, 1); mbar_init(&bars.dz1_full, NTC / 32);
-    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 32); mbar_init(&bars.xs_free[k], 1); }
-    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 32); }
+    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 64); mbar_init(&bars.xs_free[k], 1); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 64); }
     if (blockIdx.x == 0) C.adam_t[2 * j + 0] += 1;
   }
   if (tid < TMR) {
@@ -1312,53 +1335,8 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
       const float sum = warp_colsum32(v, lane);
       red_add(pg.b1 + c0 + lane, sum);
     }
-    // ---- dW1p: stage X_p chunk c as an MN-major image pair, read out the accumulator of chunk c - 1
-    auto readout = [&](int cc) {
-      const int t = cc & 3;
-      mbar_wait_bounded(&bars.dw_full[t], (cc >> 2) & 1);
-      umma::fence_after();
-      float d[16];
-      umma::tmem_ld16(tbase + LA::T_DW + t * 32 + lane_base + (uint32_t)(16 * half), d);
-      umma::fence_before();
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.dw_free[t])) : "memory");
-      if (lane < 16) {
-        const int u = 16 * (warp & 3) + lane, f0 = 32 * cc + 16 * half;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (f0 + i < pw.in) red_add(pg.W1 + (size_t)(f0 + i) * U + u, d[i]);
-      }
-    };
-#pragma unroll
-    for (int b = 0; b < PD; ++b)
-      if (b < np) load_x(xr[b], xp, rowoff, row, 32 * b + 16 * half);
-    for (int c = 0; c < np; c += PD) {
-#pragma unroll
-      for (int b = 0; b < PD; ++b) {
-        if (c + b < np) {
-          const int cc = c + b, s = cc & 1;
-          if (cc >= 2) mbar_wait_bounded(&bars.xs_free[s], ((cc >> 1) - 1) & 1);
-          unsigned char* img = smem + LA::R1 + s * (2 * LA::XS_IMG);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 hi, lo;
-            umma::split_tf32(xr[b].v[4 * q + 0], hi.x, lo.x);
-            umma::split_tf32(xr[b].v[4 * q + 1], hi.y, lo.y);
-            umma::split_tf32(xr[b].v[4 * q + 2], hi.z, lo.z);
-            umma::split_tf32(xr[b].v[4 * q + 3], hi.w, lo.w);
-            const uint32_t off = umma::sw128b32_off(row, 16 * half + 4 * q);
-            *reinterpret_cast<float4*>(img + off) = hi;
-            *reinterpret_cast<float4*>(img + LA::XS_IMG + off) = lo;
-          }
-          umma::fence_async_smem();
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.xs_full[s])) : "memory");
-          if (cc + PD < np) load_x(xr[b], xp, rowoff, row, 32 * (cc + PD) + 16 * half);
-          if (cc >= 1) readout(cc - 1);
-        }
-      }
-    }
-    readout(np - 1);
+    // ---- dW1p^T chunks: stager warps / reader warps
+    dw1_chunk_loop<U>(bars, smem + LA::R1, LA::XS_IMG, tbase + LA::T_DW, xp, rowoff, np, pw.in, pg.W1, warp, lane);
   }
   umma::fence_before();
   __syncthreads();
