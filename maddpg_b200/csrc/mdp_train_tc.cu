@@ -257,10 +257,48 @@ __device__ __forceinline__ void mma_net(unsigned char* smem, Bars* bars, Pipe& p
   pipe.nets++;
 }
 
+
+// Layer-1 staging loop shared by the three kernels: the gathered X chunk goes to TMEM slot (chunk % NS) as a hi | lo pair.
+// Warps 0-3 stage the even chunks of a net, warps 4-7 the odd ones (a chunk needs all 128 TMEM lanes = four warps, each
+// thread writing its row's 32 columns), so a warp's wait -> split -> tcgen05.st -> arrive chain is only on the critical path
+// of every second chunk.  stage_x counts four warp arrivals.  `chunk0` = chunks staged before this net (ring position).
+template <typename BarsT>
+__device__ __forceinline__ void l1_stage_loop(BarsT& bars, uint32_t t_x, const XT& xs, long long rowoff, int n, uint32_t chunk0,
+                                              int warp, int lane) {
+  const int par = warp >> 2, row = 32 * (warp & 3) + lane;
+  const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+  XRegs xa[2][2];  // two of this warp's chunks in flight, 2 x 16 columns each
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    const int k = par + 2 * b;
+    if (k < n) {
+      load_x(xa[b][0], xs, rowoff, row, 32 * k);
+      load_x(xa[b][1], xs, rowoff, row, 32 * k + 16);
+    }
+  }
+  for (int k0 = par; k0 < n; k0 += 4) {
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int k = k0 + 2 * b;
+      if (k < n) {
+        const uint32_t cc = chunk0 + (uint32_t)k, s = cc % NS;
+        if (cc >= NS) mbar_wait_bounded(&bars.stage_free[s], ((cc / NS) - 1u) & 1u);
+        umma::fence_after();
+        store_x(t_x + s * 64, lane_base, 0, xa[b][0]);
+        store_x(t_x + s * 64, lane_base, 16, xa[b][1]);
+        warp_arrive_tmem(&bars.stage_x[s], lane);
+        if (k + 4 < n) {
+          load_x(xa[b][0], xs, rowoff, row, 32 * (k + 4));
+          load_x(xa[b][1], xs, rowoff, row, 32 * (k + 4) + 16);
+        }
+      }
+    }
+  }
+}
+
 // h2 = relu(relu(X W1 + b1) W2 + b2) for the CTA's 128 rows (compute warps); thread (warp w, lane l) ends up with units
 // [32 (w >> 2) + 64 g, +32) of row 32 (w & 3) + l in h2[32 g ..].  Warps run decoupled: each one gathers, splits and
 // writes its rows of a chunk and arrives on the slot barrier; nothing but the accumulator barrier joins them.
-constexpr int PD = 3;  // register prefetch depth (chunks)
 
 template <int U, typename Overlap>
 __device__ __forceinline__ void forward_hidden_tc(Bars* bars, Pipe& pipe, uint32_t tbase, const XT& xs, const MlpW& w,
@@ -272,29 +310,13 @@ __device__ __forceinline__ void forward_hidden_tc(Bars* bars, Pipe& pipe, uint32
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
   const long long rowoff = sRow[row];
   const int nchunks = (w.in + 31) / 32;
-  XRegs xr[PD];
-#pragma unroll
-  for (int b = 0; b < PD; ++b)
-    if (b < nchunks) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
   for (int i = tid; i < U; i += NTC) { sB1[i] = w.b1[i]; sB2[i] = w.b2[i]; }
   for (int i = tid; i < U * w.out; i += NTC) sW3[i] = w.W3[i];
   if (tid < w.out) sB3[tid] = w.b3[tid];
-  named_sync();  // small tensors visible to every compute warp
   // ---- layer 1: K chunks through the NS-slot ring
-  for (int c = 0; c < nchunks; c += PD) {
-#pragma unroll
-    for (int b = 0; b < PD; ++b) {
-      if (c + b < nchunks) {
-        const uint32_t s = pipe.chunks % NS;
-        wait_slot_free(bars, pipe);
-        umma::fence_after();
-        store_x(tbase + L::T_X + s * 64, lane_base, 16 * half, xr[b]);
-        warp_arrive_tmem(&bars->stage_x[s], lane);
-        if (c + b + PD < nchunks) load_x(xr[b], xs, rowoff, row, 32 * (c + b + PD) + 16 * half);
-        pipe.chunks++;
-      }
-    }
-  }
+  l1_stage_loop(*bars, tbase + L::T_X, xs, rowoff, nchunks, pipe.chunks, warp, lane);
+  pipe.chunks += (uint32_t)nchunks;
+  named_sync();  // small tensors visible to every compute warp
   overlap();  // work that does not depend on the net's output (the Gumbel noise) hides behind the layer-1 MMAs
   mbar_wait_bounded(&bars->acc, pipe.accs & 1u);
   pipe.accs++;
@@ -388,7 +410,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   if (tid == 0) {
     for (int k = 0; k < NS; ++k) {
       mbar_init(&bars.stage_w[k], 1);
-      mbar_init(&bars.stage_x[k], NTC / 32);
+      mbar_init(&bars.stage_x[k], NTC / 64);
       mbar_init(&bars.stage_free[k], 1);
     }
     mbar_init(&bars.h1_full, NTC / 32);
@@ -722,7 +744,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
   if (tid == 0) {
     for (int k = 0; k < NS; ++k) {
       mbar_init(&bars.stage_w[k], 1);
-      mbar_init(&bars.stage_x[k], NTC / 32);
+      mbar_init(&bars.stage_x[k], NTC / 64);
       mbar_init(&bars.stage_free[k], 1);
     }
     mbar_init(&bars.w2_full, 1); mbar_init(&bars.h1_full, NTC / 32); mbar_init(&bars.acc, 1);
@@ -820,23 +842,7 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const long long rowoff = sRow[row];
     const XT xs{batch, L.x_dim, nullptr, 0, 0, 0, 1};
-    XRegs xr[PD];
-#pragma unroll
-    for (int b = 0; b < PD; ++b)
-      if (b < nchunks) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
-    for (int c = 0; c < nchunks; c += PD) {
-#pragma unroll
-      for (int b = 0; b < PD; ++b) {
-        if (c + b < nchunks) {
-          const int cc = c + b, s = cc % NS;
-          if (cc >= NS) mbar_wait_bounded(&bars.stage_free[s], ((cc / NS) - 1) & 1);
-          umma::fence_after();
-          store_x(tbase + LY::T_X + s * 64, lane_base, 16 * half, xr[b]);
-          warp_arrive_tmem(&bars.stage_x[s], lane);
-          if (cc + PD < nchunks) load_x(xr[b], xs, rowoff, row, 32 * (cc + PD) + 16 * half);
-        }
-      }
-    }
+    l1_stage_loop(bars, tbase + LY::T_X, xs, rowoff, nchunks, 0u, warp, lane);
     // ---- epilogue 1: h1 -> TMEM (A of layer 2) and MN-major smem images (A of dW2); relu mask kept in a register
     mbar_wait_bounded(&bars.acc, 0);
     umma::fence_after();
@@ -999,7 +1005,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
   if (tid == 0) {
     for (int k = 0; k < NS; ++k) {
       mbar_init(&bars.stage_w[k], 1);
-      mbar_init(&bars.stage_x[k], NTC / 32);
+      mbar_init(&bars.stage_x[k], NTC / 64);
       mbar_init(&bars.stage_free[k], 1);
     }
     mbar_init(&bars.a_full, NTC / 32); mbar_init(&bars.r2_full, 1); mbar_init(&bars.r2_free, 1);
@@ -1117,26 +1123,10 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const long long rowoff = sRow[row];
     const bool valid = row < nrows;
-    int chunk = 0;  // running layer-1 chunk counter (actor pass, then critic pass)
-    XRegs xr[PD];
+    uint32_t chunk = 0;  // running layer-1 chunk counter (actor pass, then critic pass)
     auto layer1 = [&](const XT& xs, int n) {
-#pragma unroll
-      for (int b = 0; b < PD; ++b)
-        if (b < n) load_x(xr[b], xs, rowoff, row, 32 * b + 16 * half);
-      for (int c = 0; c < n; c += PD) {
-#pragma unroll
-        for (int b = 0; b < PD; ++b) {
-          if (c + b < n) {
-            const int cc = chunk, s = cc % NS;
-            if (cc >= NS) mbar_wait_bounded(&bars.stage_free[s], ((cc / NS) - 1) & 1);
-            umma::fence_after();
-            store_x(tbase + LY::T_X + s * 64, lane_base, 16 * half, xr[b]);
-            warp_arrive_tmem(&bars.stage_x[s], lane);
-            if (c + b + PD < n) load_x(xr[b], xs, rowoff, row, 32 * (c + b + PD) + 16 * half);
-            ++chunk;
-          }
-        }
-      }
+      l1_stage_loop(bars, tbase + LY::T_X, xs, rowoff, n, chunk, warp, lane);
+      chunk += (uint32_t)n;
     };
     float v[32];
     uint32_t mask1p = 0, mask2p = 0, mask1q = 0, mask2q = 0;
