@@ -375,7 +375,11 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
                                                          const float* __restrict__ u_target, int u_stride, uint64_t seed,
                                                          uint64_t counter, float* __restrict__ y_out, float* __restrict__ target_act_out,
                                                          long long idx_stride, long long y_stride, float* __restrict__ act_scratch,
-                                                         int act_in_smem) {
+                                                         int act_in_smem, int phase) {
+  // phase 0: all target actors, then the target critic, in one CTA (a' stays in shared memory when it fits).
+  // phase 1 / 2 (split launch, many agents): grid.z actor groups each compute their share of a' into the L2-resident scratch
+  // (phase 1), then one CTA per tile runs the critic on it (phase 2) -- the actor passes of a tile are independent, so the
+  // split turns 25 serial nets per CTA into <= 5 and fills the SMs even for a single-agent launch.
   using LY = Lay<U>;
   const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
   if (ridx) ridx += blockIdx.y * idx_stride;
@@ -430,19 +434,27 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   umma::fence_after();
   const uint32_t tbase = tmem_slot;
   Pipe pipe{0u, 0u, 0u};
-  const int i_begin = me.local_q ? j : 0, i_end = me.local_q ? j + 1 : C.n_agents;
+  int i_begin = me.local_q ? j : 0, i_end = me.local_q ? j + 1 : C.n_agents;
+  if (phase == 1) {  // this CTA's contiguous share of the actors
+    const int per = (i_end - i_begin + (int)gridDim.z - 1) / (int)gridDim.z;
+    i_begin += (int)blockIdx.z * per;
+    i_end = min(i_end, i_begin + per);
+  } else if (phase == 2) {
+    i_end = i_begin;  // no actor passes
+  }
+  const bool do_critic = phase != 1;
 
   if (warp == NTC / 32) {
     // ===== producer warp: weight images of every net of this CTA's job list, in order =====
     if (lane == 0) {
       for (int i = i_begin; i < i_end; ++i) produce_net<U>(smem, &bars, pipe, imgs[i].net[MDP_NET_TARGET_P], C.agents[i].obs_dim);
-      produce_net<U>(smem, &bars, pipe, imgs[j].net[MDP_NET_TARGET_Q], me.net[MDP_NET_TARGET_Q].in);
+      if (do_critic) produce_net<U>(smem, &bars, pipe, imgs[j].net[MDP_NET_TARGET_Q], me.net[MDP_NET_TARGET_Q].in);
     }
   } else if (warp == NTC / 32 + 1) {
     // ===== MMA issuer warp (all lanes run the loops; one elected lane issues) =====
     const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
     for (int i = i_begin; i < i_end; ++i) mma_net<U>(smem, &bars, pipe, tb, C.agents[i].obs_dim);
-    mma_net<U>(smem, &bars, pipe, tb, me.net[MDP_NET_TARGET_Q].in);
+    if (do_critic) mma_net<U>(smem, &bars, pipe, tb, me.net[MDP_NET_TARGET_Q].in);
   } else {
     // ===== compute warps =====
     float h2[U / 2];
@@ -505,6 +517,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
       named_sync();  // a' visible to the critic's gather; sPart / small tensors free for the next net
     }
 
+    if (do_critic) {
     // q' = target_q_j([next_obs | a'])
     XT xq;
     if (me.local_q) xq = XT{batch + L.nx_off + me.obs_off, me.obs_dim, actT + me.act_off, ASP, me.obs_dim, me.act_dim,
@@ -537,6 +550,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
         atomicAdd(st + 7, (double)max(0, min(32, nrows - 32 * warp)));
       }
     }
+    }  // do_critic
   }
   umma::fence_before();
   __syncthreads();
@@ -1379,7 +1393,11 @@ int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t co
   const size_t fixed = LY::OFF_MISC + (size_t)LY::MISC_FLOATS * 4 + 1024 + 64;
   const size_t limit = 227 * 1024 - 512;  // static __shared__ (barriers, TMEM slot) comes on top
   const size_t act_bytes = (size_t)tc::TMR * ASP * 4;
-  const int act_in_smem = fixed + act_bytes <= limit;
+  // split launch (actor groups, then critics) once there are enough actor passes per tile to be worth a second launch
+  bool any_local = false;
+  for (int k = agent; k < agent + count; ++k) any_local |= c->cfg.local_q[k] != 0;
+  const int groups = (!any_local && n >= 8) ? std::min(8, (n + 2) / 3) : 1;
+  const int act_in_smem = groups == 1 && fixed + act_bytes <= limit;
   // a CTA owns all 512 TMEM columns of its SM: ask for more than half of the shared memory so that two never share one
   const size_t smem = std::max(fixed + (act_in_smem ? act_bytes : 0), (size_t)116 * 1024);
   const int tiles = cdiv(B, tc::TMR);
@@ -1405,8 +1423,17 @@ int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t co
   if (rc) return rc;
   auto kern = tc::k_td_target_tc<U>;
   MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (groups > 1) {
+    kern<<<dim3(tiles, count, groups), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter,
+                                                             y_out, target_act_out, idx_stride, y_stride, c->tc_scratch, 0, 1);
+    rc = check_launch("k_td_target_tc (actors)");
+    if (rc) return rc;
+    kern<<<dim3(tiles, count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
+                                                     target_act_out, idx_stride, y_stride, c->tc_scratch, 0, 2);
+    return check_launch("k_td_target_tc (critic)");
+  }
   kern<<<dim3(tiles, count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, u_target, u_stride, seed, counter, y_out,
-                                                   target_act_out, idx_stride, y_stride, c->tc_scratch, act_in_smem);
+                                                   target_act_out, idx_stride, y_stride, c->tc_scratch, act_in_smem, 0);
   return check_launch("k_td_target_tc");
 }
 
