@@ -1016,9 +1016,9 @@ int launch_actor_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t 
 static bool want_tc(const mdp_core* c, int B, int count, bool backward = false) {
   if (c->tc_mode < 0 || c->cfg.num_units != 64) return false;
   if (c->tc_mode > 0) return true;
-  if (backward) return cdiv(B, 128) * count >= 96;  // the backward kernel only wins once its 128-row tiles fill the SMs
   // automatic: the 128-row tensor-core tiles pay off once a launch fills most SMs with them, or when the critic input
   // is wide enough that streaming it through the UMMA pipeline beats the SIMT K-loop (measured on B200)
+  (void)backward;
   int max_in = 0;
   for (int i = 0; i < c->cfg.n_agents; ++i) max_in = std::max(max_in, c->lay.net_in[i][MDP_NET_TARGET_Q]);
   return cdiv(B, 128) * count >= 96 || max_in >= 1024;

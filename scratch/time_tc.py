@@ -38,7 +38,9 @@ for scen, na, E, B in [("simple_spread", 3, 4096, 1024), ("simple_tag", None, 16
         y0 = core.td_target(0, ring, idx=idx[0]).clone()
         f3, reps3 = graph_of(lambda: core.critic_grads(0, ring, y0, idx=idx[0]))
         t3 = timeit(f3) / reps3
-        print("   critic_grads(agent 0) %.2f us" % t3, flush=True)
+        f4, reps4 = graph_of(lambda: core.actor_grads(0, ring, idx=idx[0]))
+        t4 = timeit(f4) / reps4
+        print("   critic_grads(agent 0) %.2f us   actor_grads(agent 0) %.2f us" % (t3, t4), flush=True)
         f2, reps2 = graph_of(lambda: core.update_all(ring, idx=idx), 5)
         t2 = timeit(f2) / reps2
         print("%s n=%d B=%d mode=%+d: td_target(agent 0) %.2f us ; grouped update_all round %.2f us" % (scen, n, B, mode, t1, t2), flush=True)
