@@ -7,6 +7,10 @@
 #pragma once
 #include "mdp_core.cuh"
 
+#ifndef MDP_KUNROLL
+#define MDP_KUNROLL 2  // k-loop unroll of the SIMT tile GEMMs (shared-memory loads in flight per thread)
+#endif
+
 namespace mdp {
 
 // A "group" is the NT = 256 threads that cooperate on one MLP tile.  The update kernels run one group per
@@ -22,6 +26,7 @@ struct Grp {
 };
 
 constexpr int NT = 256;   // threads per group: 16 (row groups) x 16 (column quads)
+constexpr int KUNROLL = MDP_KUNROLL;
 constexpr int KC = 32;    // K-chunk streamed through shared memory
 constexpr int XP = KC + 4;
 constexpr int KPAD = 12;  // pitch of per-row action/logit scratch (max act_dim 9)
@@ -64,7 +69,7 @@ __device__ __forceinline__ void mma_tile(const Grp& G, float2 (&acc)[TM / 16][U 
   constexpr int RM = TM / 16;
   const int ty = G.tid >> 4, tx = G.tid & 15;
   const float* ap = sA + (RM * ty) * lda;
-#pragma unroll 2
+#pragma unroll KUNROLL
   for (int k = 0; k < kc; k += 4) {
     float av[RM][4];
 #pragma unroll
@@ -95,7 +100,7 @@ __device__ __forceinline__ void mma_tile_sa(const Grp& G, float2 (&acc)[TM / 16]
   constexpr int RM = TM / 16;
   const int ty = G.tid >> 4, tx = G.tid & 15;
   const float* ap = sA + (RM * ty) * lda;
-#pragma unroll 2
+#pragma unroll KUNROLL
   for (int k = 0; k < kc; ++k) {
     float av[RM];
 #pragma unroll
@@ -544,7 +549,7 @@ __device__ __forceinline__ void mma_tile_swz(const Grp& G, float2 (&acc)[TM / 16
   constexpr int RM = TM / 16, GM = U / 4 - 1;
   const int ty = G.tid >> 4, tx = G.tid & 15;
   const float* ap = sA + (RM * ty) * lda;
-#pragma unroll 2
+#pragma unroll KUNROLL
   for (int k = 0; k < U; k += 4) {
     float av[RM][4];
 #pragma unroll
