@@ -308,10 +308,13 @@ class _Group(object):
         self.core = None
 
     @classmethod
-    def get(cls, obs_shape_n, act_space_n, args):
-        key = (id(act_space_n), tuple(int(s[0]) for s in obs_shape_n))
+    def get(cls, obs_shape_n, act_space_n, args, agent_index):
+        """The group a new trainer joins: same spaces (by structure, not object identity -- callers often rebuild the
+        list), same observation dims, same ``args`` object, still collecting members.  A group whose core already exists,
+        or that already has this agent index, belongs to an earlier experiment: start a new one."""
+        key = (tuple((type(s).__name__,) + tuple(act_heads(s)) for s in act_space_n), tuple(int(s[0]) for s in obs_shape_n))
         g = cls.registry.get(key)
-        if g is None or g.core is not None and g.args is not args:
+        if g is None or g.args is not args or g.core is not None or agent_index in g.members:
             g = cls(obs_shape_n, act_space_n, args)
             cls.registry[key] = g
         return g
@@ -342,7 +345,7 @@ class MADDPGAgentTrainer(AgentTrainer):
         self.local_q_func = bool(local_q_func)
         for s in act_space_n:
             act_heads(s)  # NotImplementedError for unsupported spaces, like make_pdtype (distributions.py:422)
-        self._group = _Group.get(obs_shape_n, act_space_n, args)
+        self._group = _Group.get(obs_shape_n, act_space_n, args, agent_index)
         self._group.members[agent_index] = self
         self.max_replay_buffer_len = args.batch_size * args.max_episode_len
         self.replay_sample_index = None
