@@ -45,7 +45,7 @@ def test_spread_translation_invariance_full_size(name):
     env, E, B, U = _env(name)
     env.reset_device()
     s0 = env.state.clone()
-    act = torch.softmax(torch.randn((E, env.act_stride), device="cuda"), -1)
+    act = torch.softmax(torch.randn((E, env.act_stride), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)), -1)
     env.step_device(act)
     obs_a, rew_a = env.obs.clone(), env.rew.clone()
     A = env.n
@@ -64,7 +64,12 @@ def test_spread_translation_invariance_full_size(name):
     for i in range(A):
         rel[env.obs_off[i] + 2:env.obs_off[i] + 4] = False  # p_pos columns are absolute
     torch.testing.assert_close(obs_b[:, rel], obs_a[:, rel], rtol=1e-4, atol=2e-5)
-    torch.testing.assert_close(rew_b, rew_a, rtol=1e-4, atol=1e-4)
+    # rewards contain hard collision counts (dist < 0.3): a translation may move a borderline pair across the threshold in
+    # float32, which changes the shared reward by a whole number -- allow that for a vanishing fraction of env instances
+    dr = (rew_b - rew_a).abs()
+    flipped = dr > 1e-3
+    assert float(flipped.float().mean()) < 1e-3
+    assert float((dr[flipped] - dr[flipped].round()).abs().max() if flipped.any() else 0.0) < 1e-3
     for i in range(A):
         o = env.obs_off[i]
         torch.testing.assert_close(obs_b[:, o + 2] - obs_a[:, o + 2], torch.full((E,), 0.25, device="cuda"), rtol=0, atol=1e-5)
@@ -82,7 +87,7 @@ def test_rollout_insert_gather_round_trip_full_size(name):
     prev = env.obs.clone()
     roll.step()
     L = core.ring.layout
-    idx = torch.randint(0, E, (B,), device="cuda")
+    idx = torch.randint(0, E, (B,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(11))
     rows = core.ring.gather(idx)
     torch.testing.assert_close(rows[:, :L.obs_sum], prev[idx][:, :L.obs_sum], rtol=0, atol=0)
     torch.testing.assert_close(rows[:, L.obs_sum:L.x_dim], env.act[idx][:, :L.act_sum], rtol=0, atol=0)
@@ -113,7 +118,7 @@ def test_grouped_round_tensor_cores_vs_simt_full_size(name):
     cores[1].ring.ring.copy_(cores[0].ring.ring)
     cores[1].ring.next_idx, cores[1].ring.length = list(cores[0].ring.next_idx), list(cores[0].ring.length)
     cores[1].params.copy_(cores[0].params)
-    idx = torch.randint(0, cores[0].ring.length[0], (env.n, B), device="cuda")
+    idx = torch.randint(0, cores[0].ring.length[0], (env.n, B), device="cuda", generator=torch.Generator(device="cuda").manual_seed(12))
     ys = []
     for core, mode in zip(cores, (-1, 1)):
         core.counter = 100
