@@ -661,7 +661,8 @@ __device__ __forceinline__ void warp_arrive_both(unsigned long long* bar, int la
 // chunks out of TMEM and reduce it into the gradient bucket.  xs_full / dw_free therefore count four warp arrivals.
 template <int U, typename BarsT>
 __device__ __forceinline__ void dw1_chunk_loop(BarsT& bars, unsigned char* x_slots, uint32_t xs_img_bytes, uint32_t tdw, const XT& xs,
-                                               long long rowoff, int nchunks, int in_dim, float* __restrict__ gW1, int warp, int lane) {
+                                               long long rowoff, int nchunks, int in_dim, float* __restrict__ gW1, int warp, int lane,
+                                               int chunk0 = 0) {
   const int row = 32 * (warp & 3) + lane;
   const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
   if (warp < 4) {
@@ -669,8 +670,8 @@ __device__ __forceinline__ void dw1_chunk_loop(BarsT& bars, unsigned char* x_slo
 #pragma unroll
     for (int b = 0; b < 2; ++b)
       if (b < nchunks) {
-        load_x(xa[b][0], xs, rowoff, row, 32 * b);
-        load_x(xa[b][1], xs, rowoff, row, 32 * b + 16);
+        load_x(xa[b][0], xs, rowoff, row, 32 * (chunk0 + b));
+        load_x(xa[b][1], xs, rowoff, row, 32 * (chunk0 + b) + 16);
       }
     for (int c = 0; c < nchunks; c += 2) {
 #pragma unroll
@@ -696,8 +697,8 @@ __device__ __forceinline__ void dw1_chunk_loop(BarsT& bars, unsigned char* x_slo
           __syncwarp();
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.xs_full[s])) : "memory");
           if (cc + 2 < nchunks) {
-            load_x(xa[b][0], xs, rowoff, row, 32 * (cc + 2));
-            load_x(xa[b][1], xs, rowoff, row, 32 * (cc + 2) + 16);
+            load_x(xa[b][0], xs, rowoff, row, 32 * (chunk0 + cc + 2));
+            load_x(xa[b][1], xs, rowoff, row, 32 * (chunk0 + cc + 2) + 16);
           }
         }
       }
@@ -713,7 +714,7 @@ __device__ __forceinline__ void dw1_chunk_loop(BarsT& bars, unsigned char* x_slo
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bars.dw_free[t])) : "memory");
       if (lane < 16) {
-        const int u = 16 * (warp & 3) + lane, f0 = 32 * cc;
+        const int u = 16 * (warp & 3) + lane, f0 = 32 * (chunk0 + cc);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (f0 + i < in_dim) red_add(gW1 + (size_t)(f0 + i) * U + u, d[i]);
@@ -726,7 +727,9 @@ template <int U>
 __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const AgentImg* __restrict__ imgs, int j0, mdp_ring_layout L, int B,
                                                             const float* __restrict__ batch, const long long* __restrict__ ridx,
                                                             const float* __restrict__ y, float* __restrict__ q_out, long long idx_stride,
-                                                            long long y_stride) {
+                                                            long long y_stride, float* __restrict__ dz1_scratch) {
+  // dz1_scratch != null (wide critics): the dW1 phase runs in k_dw1_tc with the K range spread over many CTAs; this kernel
+  // then ends by writing the tile's dz1 (fp32) to the scratch.
   using LY = Lay<U>;
   using LB = LayB<U>;
   const int j = j0 + blockIdx.y;
@@ -836,8 +839,8 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
     }
     __syncwarp();
     // dW1^T chunks: D[u][f] = sum_r dz1[r][u] X[r][f]
-    mbar_wait_bounded(&bars.dz1_full, 0);
-    for (int c = 0; c < nchunks; ++c) {
+    if (!dz1_scratch) mbar_wait_bounded(&bars.dz1_full, 0);
+    for (int c = 0; c < (dz1_scratch ? 0 : nchunks); ++c) {
       const int s = c & 1, t = c & 3;
       mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
       if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
@@ -930,24 +933,110 @@ __global__ void __launch_bounds__(NTT, 1) k_critic_grads_tc(CoreDev C, const Age
     if (lane < 16) {
       float* dst = g.W2 + (size_t)(16 * (warp & 3) + lane) * U + c0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+      for (int i = 0; i < 32; i += 4) red_add4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
     umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = ((mask1 >> i) & 1u) ? v[i] : 0.f;
     umma::fence_before();
-    store_act_mn(smem + LB::R3, LB::ACT_IMG, row, c0, v);  // dW2's MMAs are complete: the h1 images are dead
-    warp_arrive_both(&bars.dz1_full, lane);
+    if (dz1_scratch) {
+      float4* dst = reinterpret_cast<float4*>(dz1_scratch + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TMR + row) * U + c0);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      store_act_mn(smem + LB::R3, LB::ACT_IMG, row, c0, v);  // dW2's MMAs are complete: the h1 images are dead
+      warp_arrive_both(&bars.dz1_full, lane);
+    }
     {
       const float sum = warp_colsum32(v, lane);  // gb1 = sum_r dz1
       red_add(g.b1 + c0 + lane, sum);
     }
     // ---- dW1^T chunks: stager warps / reader warps
-    dw1_chunk_loop<U>(bars, smem + LB::R1, LB::XS_IMG, tbase + LB::T_DW, xs, rowoff, nchunks, w.in, g.W1, warp, lane);
+    if (!dz1_scratch)
+      dw1_chunk_loop<U>(bars, smem + LB::R1, LB::XS_IMG, tbase + LB::T_DW, xs, rowoff, nchunks, w.in, g.W1, warp, lane);
   }
   umma::fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
+}
+
+
+// dW1^T = dz1^T X for wide critics, spread over grid.z K-ranges: every CTA rebuilds the tile's dz1 images from the fp32
+// scratch that k_critic_grads_tc left behind and then runs the same stager / MMA / reader pipeline on its share of the chunks.
+struct BarsD {
+  unsigned long long xs_full[2], xs_free[2], dw_full[4], dw_free[4];
+};
+constexpr int NTD = NTC + 32;  // 8 compute warps + the MMA issuer warp
+
+template <int U>
+__global__ void __launch_bounds__(NTD, 1) k_dw1_tc(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
+                                                   const long long* __restrict__ ridx, long long idx_stride,
+                                                   const float* __restrict__ dz1_scratch, int chunks_per_cta) {
+  constexpr uint32_t ACT_IMG = TMR * 128 * (U / 32), XS_IMG = TMR * 128;
+  constexpr uint32_t R_DZ = 0, R_X = 2 * ACT_IMG, OFF_MISC = R_X + 4 * XS_IMG;
+  const int j = j0 + blockIdx.y;
+  if (ridx) ridx += blockIdx.y * idx_stride;
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ BarsD bars;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  long long* sRow = reinterpret_cast<long long*>(smem + OFF_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const AgentDev& me = C.agents[j];
+  const MlpW w = me.net[MDP_NET_Q];
+  const long long row0 = (long long)blockIdx.x * TMR;
+  const int nrows = (int)min((long long)TMR, B - row0);
+  const int nchunks_all = (w.in + 31) / 32;
+  const int chunk0 = (int)blockIdx.z * chunks_per_cta;
+  const int nchunks = max(0, min(chunks_per_cta, nchunks_all - chunk0));
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, 128);
+  if (tid == 0) {
+    for (int k = 0; k < 2; ++k) { mbar_init(&bars.xs_full[k], NTC / 64); mbar_init(&bars.xs_free[k], 1); }
+    for (int k = 0; k < 4; ++k) { mbar_init(&bars.dw_full[k], 1); mbar_init(&bars.dw_free[k], NTC / 64); }
+  }
+  if (tid < TMR) {
+    const long long rl = row0 + min(tid, nrows - 1);
+    sRow[tid] = (ridx ? ridx[rl] : rl) * L.row_stride;
+  }
+  if (warp < NTC / 32) {  // dz1 (fp32 scratch) -> MN-major image pair
+    const int row = 32 * (warp & 3) + lane, c0 = 32 * (warp >> 2);
+    const float4* src = reinterpret_cast<const float4*>(dz1_scratch + (((size_t)blockIdx.y * gridDim.x + blockIdx.x) * TMR + row) * U + c0);
+    float v[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = src[q];
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+    store_act_mn(smem + R_DZ, ACT_IMG, row, c0, v);
+    umma::fence_async_smem();
+  }
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tbase = tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+  if (warp == NTC / 32) {
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c & 1, t = c & 3;
+      mbar_wait_bounded(&bars.xs_full[s], (c >> 1) & 1);
+      if (c >= 4) mbar_wait_bounded(&bars.dw_free[t], ((c >> 2) - 1) & 1);
+      umma::fence_after();
+      if (umma::elect_one()) {
+        issue_3x_mn<U, 32, TMR / 8>(tb + t * 32, sbase + R_DZ, ACT_IMG, TMR * 128, sbase + R_X + s * (2 * XS_IMG), XS_IMG, TMR * 128);
+        umma::commit(&bars.xs_free[s]);
+        umma::commit(&bars.dw_full[t]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int row = 32 * (warp & 3) + lane;
+    const XT xs{batch, L.x_dim, nullptr, 0, 0, 0, 1};
+    dw1_chunk_loop<U>(bars, smem + R_X, XS_IMG, tbase, xs, sRow[row], nchunks, w.in, me.grad[1].W1, warp, lane, chunk0);
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tbase, 128);
 }
 
 // =============================================================================================================
@@ -1327,7 +1416,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     if (lane < 16) {
       float* dst = pg.W2 + (size_t)(16 * (warp & 3) + lane) * U + c0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i]);
+      for (int i = 0; i < 32; i += 4) red_add4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
     umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
 #pragma unroll
@@ -1460,8 +1549,29 @@ int launch_critic_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t
   const size_t smem = LB::OFF_MISC + (size_t)LB::MISC_FLOATS * 4 + 1024 + 64;
   auto kern = tc::k_critic_grads_tc<U>;
   MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3(cdiv(B, tc::TMR), count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, y, q_out, idx_stride, y_stride);
-  return check_launch("k_critic_grads_tc");
+  const int tiles = cdiv(B, tc::TMR), nchunks = (max_in + 31) / 32;
+  // wide critics: the dW1 phase (as long as the forward pass, but embarrassingly parallel over K) moves to its own launch
+  const int ksplit = nchunks >= 16 ? std::min(8, nchunks / 8) : 1;
+  float* dz1 = nullptr;
+  if (ksplit > 1) {
+    const size_t need = (size_t)tiles * count * tc::TMR * U * sizeof(float);
+    if (need > c->tc_dz1_bytes) {
+      if (c->tc_dz1) cudaFree(c->tc_dz1);
+      c->tc_dz1 = nullptr;
+      c->tc_dz1_bytes = 0;
+      MDP_CUDA(cudaMalloc(&c->tc_dz1, need));
+      c->tc_dz1_bytes = need;
+    }
+    dz1 = c->tc_dz1;
+  }
+  kern<<<dim3(tiles, count), tc::NTT, smem, st>>>(d, imgs, agent, *lay, B, batch, ridx, y, q_out, idx_stride, y_stride, dz1);
+  rc = check_launch("k_critic_grads_tc");
+  if (rc || ksplit == 1) return rc;
+  auto kd = tc::k_dw1_tc<U>;
+  const size_t smem_d = 2 * (size_t)tc::TMR * 128 * (U / 32) + 4 * (size_t)tc::TMR * 128 + tc::TMR * 8 + 1024 + 64;
+  MDP_CUDA(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+  kd<<<dim3(tiles, count, ksplit), tc::NTD, smem_d, st>>>(d, agent, *lay, B, batch, ridx, idx_stride, dz1, cdiv(nchunks, ksplit));
+  return check_launch("k_dw1_tc");
 }
 
 int launch_actor_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,
