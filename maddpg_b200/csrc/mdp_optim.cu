@@ -10,6 +10,8 @@
 // HBM bound: 7 floats read + 5 written per parameter.
 #include "mdp_core.cuh"
 
+#include <algorithm>
+
 namespace mdp {
 
 struct OptSeg {
@@ -220,10 +222,80 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
                                                            float* __restrict__ v, OptSeg seg, const int* __restrict__ t_ptr,
                                                            float grad_scale, float clip, double lr, double beta1,
                                                            double beta2, float eps, float polyak, int do_polyak, PeerCtx P,
-                                                           long long goff_net, int slot0) {
-  const long long off = seg.off[blockIdx.x], len = seg.len[blockIdx.x];
+                                                           long long goff_net, int slot0, int var0) {
+  const int var = blockIdx.x + var0;
+  const long long off = seg.off[var], len = seg.len[var];
   clip_adam_polyak_var(grad + off, param + off, target + off, m + off, v + off, len, *t_ptr, grad_scale, clip, lr, beta1, beta2,
-                       eps, polyak, do_polyak, P, goff_net + off, slot0 + blockIdx.x);
+                       eps, polyak, do_polyak, P, goff_net + off, slot0 + var);
+}
+
+
+// Wide layer-1 weights (simple_spread N=24: 3576 x 64 per critic): one CTA per variable would stream 229 k parameters through
+// 1024 threads (455 us for 24 critics, the longest kernel of the round), so W1 gets a two-kernel path on a single GPU:
+// squared norm by many CTAs (one float atomic per CTA), then the clip + Adam + polyak sweep by many CTAs.
+__global__ void __launch_bounds__(256) k_w1_sqnorm(const AgentDev* __restrict__ agents, int which, int units, int a0, float grad_scale,
+                                                   float* __restrict__ norm2) {
+  __shared__ float red[8];
+  const int j = a0 + blockIdx.y;
+  const AgentDev& ag = agents[j];
+  const long long len = (long long)ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q].in * units;
+  const float4* g4 = reinterpret_cast<const float4*>(ag.grad[which].W1);
+  float ss = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len / 4; i += (long long)gridDim.x * blockDim.x) {
+    float4 x = g4[i];
+    x.x *= grad_scale; x.y *= grad_scale; x.z *= grad_scale; x.w *= grad_scale;
+    ss = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ss))));
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float s = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(norm2 + j, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_w1_adam(const AgentDev* __restrict__ agents, int which, int units, int a0,
+                                                 float* __restrict__ grads_base, float* __restrict__ m_base, float* __restrict__ v_base,
+                                                 const int* __restrict__ adam_t, const float* __restrict__ norm2, float grad_scale,
+                                                 float clip, double lr, double beta1, double beta2, float eps, float polyak,
+                                                 int do_polyak) {
+  __shared__ float s_lr_t;
+  const int j = a0 + blockIdx.y;
+  const AgentDev& ag = agents[j];
+  const MlpW& w = ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q];
+  const MlpW& wt = ag.net[which == 0 ? MDP_NET_TARGET_P : MDP_NET_TARGET_Q];
+  const long long len = (long long)w.in * units;
+  if (threadIdx.x == 0) {
+    const int t = adam_t[2 * j + which];
+    s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
+  }
+  __syncthreads();
+  const float norm = sqrtf(norm2[j]);
+  const float factor = (clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f) * grad_scale, lr_t = s_lr_t;
+  const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2), opol = 1.0f - polyak;
+  float4* g4 = reinterpret_cast<float4*>(ag.grad[which].W1);
+  const long long goff4 = (ag.grad[which].W1 - grads_base) / 4;
+  float4* m4 = reinterpret_cast<float4*>(m_base) + goff4;
+  float4* v4 = reinterpret_cast<float4*>(v_base) + goff4;
+  float4* p4 = reinterpret_cast<float4*>(const_cast<float*>(w.W1));
+  float4* t4 = reinterpret_cast<float4*>(const_cast<float*>(wt.W1));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len / 4; i += (long long)gridDim.x * blockDim.x) {
+    float4 g = g4[i], m = m4[i], v = v4[i], p = p4[i];
+    float4 t = do_polyak ? t4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto step = [&](float gi, float& mi, float& vi, float& pi, float& ti) {
+      gi *= factor;
+      mi = b1 * mi + ob1 * gi;
+      vi = b2 * vi + ob2 * gi * gi;
+      pi = pi - lr_t * mi / (sqrtf(vi) + eps);
+      ti = polyak * ti + opol * pi;
+    };
+    step(g.x, m.x, v.x, p.x, t.x); step(g.y, m.y, v.y, p.y, t.y); step(g.z, m.z, v.z, p.z, t.z); step(g.w, m.w, v.w, p.w, t.w);
+    m4[i] = m; v4[i] = v; p4[i] = p;
+    if (do_polyak) t4[i] = t;
+    g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 // all agents in one launch: grid = (6 variables, n_agents); pointers come from the device agent table
@@ -231,8 +303,9 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
                                                                float* __restrict__ grads_base, float* __restrict__ m_base,
                                                                float* __restrict__ v_base, const int* __restrict__ adam_t,
                                                                float grad_scale, float clip, double lr, double beta1,
-                                                               double beta2, float eps, float polyak, int do_polyak, PeerCtx P) {
-  const int j = blockIdx.y, var = blockIdx.x;
+                                                               double beta2, float eps, float polyak, int do_polyak, PeerCtx P,
+                                                               int a0, int var0) {
+  const int j = a0 + blockIdx.y, var = blockIdx.x + var0;
   const AgentDev& ag = agents[j];
   const MlpW& w = ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q];
   const MlpW& wt = ag.net[which == 0 ? MDP_NET_TARGET_P : MDP_NET_TARGET_Q];
@@ -288,12 +361,42 @@ extern "C" int mdp_core_bind_peers(mdp_core* c, int32_t world, int32_t rank, con
   return MDP_OK;
 }
 
+// W1 of agents [a0, a0 + count) through the many-CTA path when it is wide (single GPU only: with peers bound the gradient sum
+// happens inside the per-variable kernel).  Returns 1 if it handled W1 (the caller then starts at variable 1), 0 if not.
+static int wide_w1_step(mdp_core* c, int which, int a0, int count, float grad_scale, int do_polyak, cudaStream_t st, int* handled) {
+  *handled = 0;
+  if (c->peer_world > 1) return MDP_OK;
+  const int U = c->cfg.num_units, net = which == 0 ? MDP_NET_P : MDP_NET_Q;
+  long long min_len = 1ll << 60, max_len = 0;
+  for (int j = a0; j < a0 + count; ++j) {
+    const long long len = (long long)c->lay.net_in[j][net] * U;
+    min_len = std::min(min_len, len); max_len = std::max(max_len, len);
+  }
+  if (min_len < 32768) return MDP_OK;
+  if (!c->norm2) MDP_CUDA(cudaMalloc(&c->norm2, MDP_MAX_AGENTS * sizeof(float)));
+  MDP_CUDA(cudaMemsetAsync(c->norm2 + a0, 0, count * sizeof(float), st));
+  const int nb = (int)std::min<long long>(128, (max_len / 4 + 1023) / 1024);
+  k_w1_sqnorm<<<dim3(nb, count), 256, 0, st>>>(c->d_agents, which, U, a0, grad_scale, c->norm2);
+  int rc = check_launch("k_w1_sqnorm");
+  if (rc) return rc;
+  k_w1_adam<<<dim3(nb, count), 256, 0, st>>>(c->d_agents, which, U, a0, c->grads, c->adam_m, c->adam_v, c->adam_t, c->norm2, grad_scale,
+                                             (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps,
+                                             (float)c->cfg.polyak, do_polyak);
+  rc = check_launch("k_w1_adam");
+  if (rc) return rc;
+  *handled = 1;
+  return MDP_OK;
+}
+
 extern "C" int mdp_clip_adam_polyak_all(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_clip_adam_polyak_all: core not bound");
   MDP_REQUIRE(which == 0 || which == 1, "mdp_clip_adam_polyak_all: bad argument");
-  k_clip_adam_polyak_all<<<dim3(6, c->cfg.n_agents), 1024, 0, (cudaStream_t)stream>>>(
+  int wide = 0;
+  int rc = wide_w1_step(c, which, 0, c->cfg.n_agents, grad_scale, do_polyak, (cudaStream_t)stream, &wide);
+  if (rc) return rc;
+  k_clip_adam_polyak_all<<<dim3(6 - wide, c->cfg.n_agents), 1024, 0, (cudaStream_t)stream>>>(
       c->d_agents, which, c->cfg.num_units, c->grads, c->adam_m, c->adam_v, c->adam_t, grad_scale, (float)c->cfg.grad_clip,
-      c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, do_polyak, peer_ctx(c));
+      c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, do_polyak, peer_ctx(c), 0, wide);
   return check_launch("k_clip_adam_polyak_all");
 }
 
@@ -318,9 +421,13 @@ extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, f
   float* grad = c->grads + c->lay.train_off[agent][which];
   float* m = c->adam_m + c->lay.train_off[agent][which];
   float* v = c->adam_v + c->lay.train_off[agent][which];
-  k_clip_adam_polyak<<<6, 1024, 0, (cudaStream_t)stream>>>(param, target, grad, m, v, seg, c->adam_t + 2 * agent + which,
-                                                           grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
-                                                           c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak,
-                                                           do_polyak, peer_ctx(c), c->lay.train_off[agent][which], 6 * agent);
+  int wide = 0;
+  int rc = wide_w1_step(c, which, agent, 1, grad_scale, do_polyak, (cudaStream_t)stream, &wide);
+  if (rc) return rc;
+  k_clip_adam_polyak<<<6 - wide, 1024, 0, (cudaStream_t)stream>>>(param, target, grad, m, v, seg, c->adam_t + 2 * agent + which,
+                                                                  grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
+                                                                  c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak,
+                                                                  do_polyak, peer_ctx(c), c->lay.train_off[agent][which], 6 * agent,
+                                                                  wide);
   return check_launch("k_clip_adam_polyak");
 }

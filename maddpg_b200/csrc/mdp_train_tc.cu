@@ -90,24 +90,29 @@ __global__ void __launch_bounds__(256) k_build_images(CoreDev C, const AgentImg*
   unsigned char* w2 = const_cast<unsigned char*>(imgs[agent].net[net].w2);
   unsigned char* w2n = const_cast<unsigned char*>(imgs[agent].net[net].w2n);
   const int nchunks = (w.in + 31) / 32;
-  const long long n1 = (long long)nchunks * 32 * U, n2 = (long long)U * U;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n1 + n2; t += (long long)gridDim.x * blockDim.x) {
-    float hi, lo;
-    if (t < n1) {
-      const int u = (int)(t % U), col = (int)(t / U);
-      umma::split_tf32(col < w.in ? w.W1[(size_t)col * U + u] : 0.f, hi, lo);
-      unsigned char* dst = w1 + (size_t)(col >> 5) * (2 * L::W_IMG) + umma::sw128_off(u, col & 31);
-      *reinterpret_cast<float*>(dst) = hi;
-      *reinterpret_cast<float*>(dst + L::W_IMG) = lo;
-    } else {
-      const int e = (int)(t - n1), u2 = e % U, k1 = e / U;
-      umma::split_tf32(w.W2[e], hi, lo);
-      unsigned char* dst = w2 + (size_t)(k1 >> 5) * L::W_IMG + umma::sw128_off(u2, k1 & 31);
-      *reinterpret_cast<float*>(dst) = hi;
-      *reinterpret_cast<float*>(dst + L::W2_IMG) = lo;
-      dst = w2n + (size_t)(u2 >> 5) * L::W_IMG + umma::sw128_off(k1, u2 & 31);
-      *reinterpret_cast<float*>(dst) = hi;
-      *reinterpret_cast<float*>(dst + L::W2_IMG) = lo;
+  // one thread = four consecutive K columns of one image row: 16-byte image stores (hi and lo), coalesced weight reads
+  const long long n1 = (long long)nchunks * 8 * U, n2 = (long long)(U / 4) * U;
+  auto put = [](unsigned char* dst, uint32_t lo_off, float a, float b, float c, float d) {
+    float4 hi, lo;
+    umma::split_tf32(a, hi.x, lo.x); umma::split_tf32(b, hi.y, lo.y); umma::split_tf32(c, hi.z, lo.z); umma::split_tf32(d, hi.w, lo.w);
+    *reinterpret_cast<float4*>(dst) = hi;
+    *reinterpret_cast<float4*>(dst + lo_off) = lo;
+  };
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n1 + 2 * n2; t += (long long)gridDim.x * blockDim.x) {
+    if (t < n1) {  // W1^T chunk images: row u, columns col0..col0+3
+      const int u = (int)(t % U), col0 = 4 * (int)(t / U);
+      float x[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x[q] = col0 + q < w.in ? w.W1[(size_t)(col0 + q) * U + u] : 0.f;
+      put(w1 + (size_t)(col0 >> 5) * (2 * L::W_IMG) + umma::sw128_off(u, col0 & 31), L::W_IMG, x[0], x[1], x[2], x[3]);
+    } else if (t < n1 + n2) {  // W2^T images: row u2, columns k1..k1+3
+      const int e = (int)(t - n1), u2 = e % U, k1 = 4 * (e / U);
+      put(w2 + (size_t)(k1 >> 5) * L::W_IMG + umma::sw128_off(u2, k1 & 31), L::W2_IMG, w.W2[(size_t)k1 * U + u2],
+          w.W2[(size_t)(k1 + 1) * U + u2], w.W2[(size_t)(k1 + 2) * U + u2], w.W2[(size_t)(k1 + 3) * U + u2]);
+    } else {  // W2 images: row k1, columns u2..u2+3
+      const int e = (int)(t - n1 - n2), u2 = 4 * (e % (U / 4)), k1 = e / (U / 4);
+      const float4 x = *reinterpret_cast<const float4*>(w.W2 + (size_t)k1 * U + u2);
+      put(w2n + (size_t)(u2 >> 5) * L::W_IMG + umma::sw128_off(k1, u2 & 31), L::W2_IMG, x.x, x.y, x.z, x.w);
     }
   }
 }
