@@ -165,6 +165,11 @@ int mdp_core_bind(mdp_core* core, float* params, float* grads, float* adam_m, fl
  * compute the same functions (mlp_model, train.py:39-46) to ~fp32 accuracy. */
 int mdp_core_set_tensor_cores(mdp_core* core, int32_t mode);
 
+/* mdp_update_agent / mdp_update_all run the TD target (maddpg.py:181-189) and the critic step (q_train, :75-100)
+ * of the same sampled rows in ONE launch when the row tile fits in shared memory (on = 1, the default); on = 0 keeps
+ * the two launches.  Same arithmetic either way. */
+int mdp_core_set_fused_update(mdp_core* core, int32_t on);
+
 /* MADDPGAgentTrainer.action (maddpg.py:151-152) / p_debug['target_act'] (:70-71) for agents
  * [agent_begin, agent_begin+agent_count): act_i = gumbel_softmax(mlp(obs_i)) in one grouped launch.
  * obs/act are joint arrays.  u (optional, joint act layout): injected U[0,1) draws; when null the

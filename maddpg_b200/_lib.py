@@ -74,6 +74,7 @@ SYMBOLS = {
     "mdp_core_get_layout": (C.c_int, [_P, C.POINTER(CoreLayout)]),
     "mdp_core_destroy": (None, [_P]),
     "mdp_core_set_tensor_cores": (C.c_int, [_P, C.c_int32]),
+    "mdp_core_set_fused_update": (C.c_int, [_P, C.c_int32]),
     "mdp_core_bind_peers": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "mdp_core_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "mdp_actor_act": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P,

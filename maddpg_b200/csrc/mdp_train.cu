@@ -405,7 +405,57 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j0, mdp_ring_
 // through ridx straight from the replay ring) and every net the kernel touches into shared memory; the rest
 // of the kernel never waits on global memory again.
 // =============================================================================================
+// q_train on one resident row tile (maddpg.py:75-100): forward, MSE gradient, backward; `ytile` = TD targets of the tile's rows
+// (global or shared memory).  Runs on the 256 threads of group G.
 template <int U, int TM>
+__device__ __forceinline__ void critic_grads_body(const Grp& G, const CoreDev& C, int j, int B, const float* sXf, int XPf, const MlpW& w,
+                                                  float* sWT, float* sH1, float* sH2, float* sQ, float* sDq,
+                                                  const float* __restrict__ ytile, float* __restrict__ q_out_tile, int nrows) {
+  constexpr int HP = U + 4;
+  const MlpG& g = C.agents[j].grad[1];
+  const int tid = G.tid;
+  build_wT_swz<U>(G, sWT, w.W2);  // published by the barriers inside forward_hidden_res
+  forward_hidden_res<U, TM>(G, sXf, XPf, w, sH1, sH2);
+  critic_head<U, TM>(G, sH2, w, sQ);
+  if (tid < 32) {
+    const int r = tid;
+    float d = 0.f;
+    double se = 0.0;
+    if (r < nrows && r < TM) {
+      const float q = sQ[r];
+      const float diff = q - ytile[r];
+      d = 2.0f * diff / (float)B;
+      se = (double)diff * (double)diff;
+      if (q_out_tile) q_out_tile[r] = q;
+    }
+    sDq[r] = d;
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    if (r == 0) atomicAdd(C.stats + 8 * j + 0, se);
+  }
+  G.sync();
+  if (tid < U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s = fmaf(sH2[r * HP + tid], sDq[r], s);
+    red_add(g.W3 + tid, s);
+  } else if (tid == U) {
+    float s = 0.f;
+    for (int r = 0; r < TM; ++r) s += sDq[r];
+    red_add(g.b3, s);
+  }
+  G.sync();
+  for (int idx = tid; idx < TM * U; idx += NT) {
+    const int r = idx / U, u = idx - r * U;
+    const float h = sH2[r * HP + u];
+    sH2[r * HP + u] = h > 0.f ? sDq[r] * w.W3[u] : 0.f;
+  }
+  G.sync();
+  backward_hidden_res<U, TM>(G, sXf, XPf, w, sWT, &g, sH1, sH2);
+}
+
+// FUSE: group 0 continues with the critic step (q_train) of the same rows -- y never leaves shared memory, the critic net and
+// the [obs | act] columns of the rows ride in the same TMA prologue, and one launch + one prologue disappear from the serial
+// chain of an agent update.
+template <int U, int TM, bool FUSE>
 __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                       const long long* __restrict__ ridx, const float* __restrict__ u_target,
                                                       int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
@@ -427,11 +477,19 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
   float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
   float* sQ = sm.take(TM);
   float* sRD = sm.take(2 * TM);    // rew_j, done_j
-  float* sNets = sm.p;
   const AgentDev& me = C.agents[j];
+  const MlpW gq = me.net[MDP_NET_Q];
+  const int x4 = (L.x_dim + 3) & ~3;
+  float* sXc = FUSE ? sm.take(TM * XPf) : nullptr;  // [obs_all | act_all] of the same rows
+  float* sY = FUSE ? sm.take(TM) : nullptr;
+  float* sDq = FUSE ? sm.take(32) : nullptr;
+  float* sWT = FUSE ? sm.take(U * U) : nullptr;
+  float* sNetQ = FUSE ? sm.take(net_floats_padded(gq.in, U, 1)) : nullptr;
+  float* sNets = sm.p;
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   const int R = L.row_stride, n = C.n_agents;
+  if (FUSE && blockIdx.x == 0 && threadIdx.x == 0) C.adam_t[2 * j + 1] += 1;
   // prologue: ONE burst of TMA bulk copies (all target actors, the target critic, the gathered next_obs rows)
   __shared__ __align__(8) unsigned long long bar;
   if (threadIdx.x == 0) mbar_init(&bar, 1);
@@ -440,6 +498,10 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
   float* p = sNets;
   if (threadIdx.x == 0) {
     uint32_t total = (uint32_t)nrows * nx4 * 4u;
+    if (FUSE) {
+      total += (uint32_t)nrows * x4 * 4u + net_floats_padded(gq.in, U, 1) * 4u;
+      bulk_g2s(sNetQ, gq.W1, net_floats_padded(gq.in, U, 1) * 4u, &bar);
+    }
     for (int i = 0; i < n; ++i) total += net_floats_padded(C.agents[i].obs_dim, U, C.agents[i].act_dim) * 4u;
     total += net_floats_padded(me.net[MDP_NET_TARGET_Q].in, U, 1) * 4u;
     mbar_arrive_expect_tx(&bar, total);
@@ -452,6 +514,7 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
     bulk_g2s(q, me.net[MDP_NET_TARGET_Q].W1, net_floats_padded(me.net[MDP_NET_TARGET_Q].in, U, 1) * 4u, &bar);
   }
   if (grp == 0) bulk_rows<TM>(G, sXf, XPf, batch, R, ridx, row0, nrows, L.nx_off, nx4, &bar);
+  if (FUSE && grp == NG - 1) bulk_rows<TM>(G, sXc, XPf, batch, R, ridx, row0, nrows, 0, x4, &bar);
   for (int i = threadIdx.x; i < 2 * TM; i += blockDim.x) {
     const int r = i >> 1, which = i & 1;
     float v = 0.f;
@@ -492,6 +555,7 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
       const float qn = sQ[r];
       const double y = rew + C.gamma * (1.0 - done) * (double)qn;
       y_out[row0 + r] = (float)y;
+      if (FUSE) sY[r] = (float)y;
       sy = y; syy = y * y; sr = rew; sq = (double)qn;
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -505,6 +569,11 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
       atomicAdd(st + 3, sy); atomicAdd(st + 4, syy); atomicAdd(st + 5, sr); atomicAdd(st + 6, sq);
       atomicAdd(st + 7, (double)nrows);
     }
+  }
+  if (FUSE) {
+    G.sync();  // y of the tile is in shared memory
+    const MlpW wq = net_at<U>(sNetQ, gq.in, 1);
+    critic_grads_body<U, TM>(G, C, j, B, sXc, XPf, wq, sWT, sH1, sH2, sQ, sDq, sY, nullptr, nrows);
   }
 }
 
@@ -544,42 +613,7 @@ __global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j0, mdp_
   const MlpW w = net_at<U>(sNet, gq.in, 1);
   mbar_wait(&bar, 0);
   __syncthreads();
-  build_wT_swz<U>(G, sWT, w.W2);  // published by the barriers inside forward_hidden_res
-  forward_hidden_res<U, TM>(G, sXf, XPf, w, sH1, sH2);
-  critic_head<U, TM>(G, sH2, w, sQ);
-  if (threadIdx.x < 32) {
-    const int r = threadIdx.x;
-    float d = 0.f;
-    double se = 0.0;
-    if (r < nrows && r < TM) {
-      const float q = sQ[r];
-      const float diff = q - y[row0 + r];
-      d = 2.0f * diff / (float)B;
-      se = (double)diff * (double)diff;
-      if (q_out) q_out[row0 + r] = q;
-    }
-    sDq[r] = d;
-    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-    if (r == 0) atomicAdd(C.stats + 8 * j + 0, se);
-  }
-  __syncthreads();
-  if (threadIdx.x < U) {
-    float s = 0.f;
-    for (int r = 0; r < TM; ++r) s = fmaf(sH2[r * HP + threadIdx.x], sDq[r], s);
-    red_add(g.W3 + threadIdx.x, s);
-  } else if (threadIdx.x == U) {
-    float s = 0.f;
-    for (int r = 0; r < TM; ++r) s += sDq[r];
-    red_add(g.b3, s);
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
-    const int r = idx / U, u = idx - r * U;
-    const float h = sH2[r * HP + u];
-    sH2[r * HP + u] = h > 0.f ? sDq[r] * w.W3[u] : 0.f;
-  }
-  __syncthreads();
-  backward_hidden_res<U, TM>(G, sXf, XPf, w, sWT, &g, sH1, sH2);
+  critic_grads_body<U, TM>(G, C, j, B, sXf, XPf, w, sWT, sH1, sH2, sQ, sDq, y + row0, q_out ? q_out + row0 : nullptr, nrows);
 }
 
 template <int U, int TM>
@@ -894,6 +928,12 @@ extern "C" int mdp_core_set_tensor_cores(mdp_core* c, int32_t mode) {
   return MDP_OK;
 }
 
+extern "C" int mdp_core_set_fused_update(mdp_core* c, int32_t on) {
+  MDP_REQUIRE(c, "mdp_core_set_fused_update: null core");
+  c->no_fuse = on ? 0 : 1;
+  return MDP_OK;
+}
+
 extern "C" int mdp_core_bind(mdp_core* c, float* params, float* grads, float* adam_m, float* adam_v, int32_t* adam_t,
                              double* stats) {
   MDP_REQUIRE(c && params && grads && adam_m && adam_v && adam_t && stats, "mdp_core_bind: null argument");
@@ -967,6 +1007,8 @@ struct ResPlan {
   bool ok;
   int XPf;                      // pitch of the X row tile
   size_t td, critic, actor;     // dynamic shared memory (bytes) of the three kernels
+  size_t td_fused;              // TD target with the critic step fused in
+  bool fuse_ok;
   int td_groups;
 };
 
@@ -991,8 +1033,10 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   r.td = (tile + r.td_groups * (2 * r4((size_t)TMv * HP) + r4(TMv * KPAD)) + r4(TMv) + r4(2 * TMv) + actors + crit + 64) * 4;
   r.critic = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv) + 32 + (size_t)U * U + crit + 64) * 4;
   r.actor = (tile + 4 * r4((size_t)TMv * HP) + 2 * r4(TMv * KPAD) + r4(TMv) + 2 * (size_t)U * U + crit + act_j + 64) * 4;
+  r.td_fused = r.td + (tile + r4(TMv) + 32 + (size_t)U * U + crit) * 4;  // k_td_target_res<FUSE>: + critic tile, y, dq, W2^T, q net
   const size_t limit = 200 * 1024;
   r.ok = r.td <= limit && r.critic <= limit && r.actor <= limit;
+  r.fuse_ok = r.ok && r.td_fused <= limit;
   return r;
 }
 
@@ -1048,7 +1092,7 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
     constexpr bool RES = decltype(res_)::value;
     if (rp.ok) {
-      auto kern = k_td_target_res<U, TMv>;
+      auto kern = k_td_target_res<U, TMv, false>;
       int rc2 = set_smem(kern, rp.td);
       if (rc2) return rc2;
       kern<<<dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed,
@@ -1063,6 +1107,42 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
                                                      target_act_out, p.max_net, idx_stride, y_stride);
     return check_launch("k_td_target");
   });
+}
+
+static int launch_critic_grads(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                               const int64_t* idx, long long idx_stride, const float* y, long long y_stride, float* q_out,
+                               void* stream);
+
+// TD target + critic gradients of the same rows in ONE launch (k_td_target_res<FUSE>) when the fused tile fits in shared memory
+// and the SIMT path is the one selected; otherwise the two launches.
+static int launch_td_critic(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
+                            const int64_t* idx, long long idx_stride, const float* u_target, int32_t u_stride, uint64_t seed,
+                            uint64_t counter, float* y_scratch, long long y_stride, void* stream) {
+  MDP_REQUIRE(c && c->d_agents, "mdp_update: core not bound");
+  int rc = check_lay(c, lay);
+  if (rc) return rc;
+  MDP_REQUIRE(batch && y_scratch && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_update: bad argument");
+  const Plan p = make_plan(c, B);
+  const ResPlan rp = make_res_plan(c, p, agent);
+  if (rp.fuse_ok && !c->no_fuse && !want_tc(c, B, count) && !want_tc(c, B, count, true)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
+    CoreDev d = core_dev(c);
+    return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto) -> int {
+      constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
+      auto kern = k_td_target_res<U, TMv, true>;
+      int rc2 = set_smem(kern, rp.td_fused);
+      if (rc2) return rc2;
+      kern<<<dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td_fused, st>>>(d, agent, *lay, B, batch, (const long long*)idx, u_target,
+                                                                              u_stride, seed, counter, y_scratch, nullptr, rp.XPf,
+                                                                              idx_stride, y_stride);
+      return check_launch("k_td_target_res<fused critic>");
+    });
+  }
+  rc = launch_td_target(c, agent, count, lay, B, batch, idx, idx_stride, u_target, u_stride, seed, counter, y_scratch, y_stride, nullptr,
+                        stream);
+  if (rc) return rc;
+  return launch_critic_grads(c, agent, count, lay, B, batch, idx, idx_stride, y_scratch, y_stride, nullptr, stream);
 }
 
 extern "C" int mdp_td_target(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
@@ -1170,9 +1250,7 @@ extern "C" int mdp_update_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B
                               void* stream) {
   MDP_REQUIRE(c && y_scratch, "mdp_update_all: null argument");
   const int n = c->cfg.n_agents;
-  int rc = launch_td_target(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, y_scratch, B, nullptr, stream);
-  if (rc) return rc;
-  rc = launch_critic_grads(c, 0, n, lay, B, batch, idx, idx_agent_stride, y_scratch, B, nullptr, stream);
+  int rc = launch_td_critic(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, y_scratch, B, stream);
   if (rc) return rc;
   rc = mdp_clip_adam_polyak_all(c, 1, grad_scale, 1, stream);
   if (rc) return rc;
@@ -1184,9 +1262,7 @@ extern "C" int mdp_update_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B
 extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
                                 const int64_t* idx, const float* u_target, const float* u_actor, int32_t u_stride,
                                 uint64_t seed, uint64_t counter, float* y_scratch, void* stream) {
-  int rc = mdp_td_target(c, agent, lay, B, batch, idx, u_target, u_stride, seed, counter, y_scratch, nullptr, stream);
-  if (rc) return rc;
-  rc = mdp_critic_grads(c, agent, lay, B, batch, idx, y_scratch, nullptr, stream);
+  int rc = launch_td_critic(c, agent, 1, lay, B, batch, idx, 0, u_target, u_stride, seed, counter, y_scratch, 0, stream);
   if (rc) return rc;
   const float scale = c->peer_world > 1 ? 1.0f / (float)c->peer_world : 1.0f;  // fused peer all-reduce (mdp_core_bind_peers)
   rc = mdp_clip_adam_polyak(c, agent, 1, scale, 1, stream);

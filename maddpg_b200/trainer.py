@@ -164,6 +164,10 @@ class MADDPGCore(object):
         """0 = automatic, 1 = tcgen05 kernels wherever supported, -1 = fp32 SIMT kernels only."""
         _lib.check(_lib.lib.mdp_core_set_tensor_cores(self._h, int(mode)), "mdp_core_set_tensor_cores")
 
+    def set_fused_update(self, on):
+        """TD target + critic step in one launch (default) or two (include/maddpg_b200.h: mdp_core_set_fused_update)."""
+        _lib.check(_lib.lib.mdp_core_set_fused_update(self._h, int(bool(on))), "mdp_core_set_fused_update")
+
     def act(self, obs_joint, act_joint, agent_begin=0, agent_count=None, use_target=False, u=None, logits_out=None,
             counter=None):
         """Grouped actor inference + Gumbel-softmax on joint device arrays (see header).  ``counter``

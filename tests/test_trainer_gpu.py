@@ -103,14 +103,17 @@ def test_gradients_match_oracle(name):
     assert core.adam_t.cpu().tolist()[:2] == [1, 1]
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("name", list(TRAINER_CASES))
-def test_sequential_update_round_matches_oracle(name):
+def test_sequential_update_round_matches_oracle(name, fused):
     """agent.update(trainers, t) for every agent in order (train.py:160-161), injected index sets and
-    uniforms: returned statistics, post-update Q-values and parameters."""
+    uniforms: returned statistics, post-update Q-values and parameters.  ``fused``: TD target and critic
+    step in one launch (the default) or two (mdp_core_set_fused_update)."""
     case = trainer_case(name, seed=4)
     ref = oracle_update_round(trainer_case(name, seed=4))
     oracle_after = trainer_case(name, seed=4)
     trainers, core = _build(case)
+    core.set_fused_update(fused)
     n = case["n"]
     assert trainers[0].update(trainers, 99, index=case["idx"][0]) is None  # off-period gate (maddpg.py:164)
     for j, tr in enumerate(trainers):
