@@ -19,9 +19,10 @@ namespace mdp {
 struct Grp {
   int tid;     // thread index inside the group
   int bar_id;  // 0: whole CTA, else named barrier id
+  int nthr = 256;  // threads synchronising on the named barrier
   __device__ __forceinline__ void sync() const {
     if (bar_id == 0) __syncthreads();
-    else asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthr) : "memory");
   }
 };
 

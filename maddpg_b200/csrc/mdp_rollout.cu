@@ -20,6 +20,161 @@ __host__ __device__ inline int actor_net_floats(int D, int U, int K) {
   return ((D * U + U + U * U + U + U * K + K) + 3) & ~3;
 }
 
+// ---- actor tile of the episode kernel: 32 env rows x U units per group of GTH threads ----------------------------------
+// Thread (ty, tx) = (tid >> 4, tid & 15) owns rows {RM*ty .. +RM-1}, RM = 512 / GTH, and columns {64g + 4tx .. +3}.  With
+// resident weights a group is 128 threads (RM = 4, 16 outputs per thread): per 4 k-steps a thread issues 8 LDS.128 for 32
+// FFMA2 -- half the shared-memory wavefronts per FMA of the 256-thread 2x4 tile, which ran at 38 % of the FMA pipe
+// (125 cycles per k-step of layer 2 against 48; clock64 phase profile in DESIGN.md).  Every output still accumulates
+// k = 0, 1, ... in order with fused multiply-adds, so the results are bit-identical to the per-step kernels.
+template <int U, int GTH>
+struct EpTile {
+  static constexpr int RM = 512 / GTH, HP = U + 4;
+  typedef float2 Acc[RM][U / 32];
+
+  static __device__ __forceinline__ void zero(Acc& acc) {
+#pragma unroll
+    for (int r = 0; r < RM; ++r)
+#pragma unroll
+      for (int c = 0; c < U / 32; ++c) acc[r][c] = make_float2(0.f, 0.f);
+  }
+  // acc += sA[rows][0..kc) * sW[0..kc)[cols]; scalar A loads (any alignment, any kc)
+  static __device__ __forceinline__ void mma_sa(int tid, Acc& acc, const float* __restrict__ sA, int lda, const float* __restrict__ sW,
+                                                int kc) {
+    const int ty = tid >> 4, tx = tid & 15;
+    const float* ap = sA + (RM * ty) * lda;
+#pragma unroll 2
+    for (int k = 0; k < kc; ++k) {
+      float av[RM];
+#pragma unroll
+      for (int rr = 0; rr < RM; ++rr) av[rr] = ap[rr * lda + k];
+#pragma unroll
+      for (int g = 0; g < U / 64; ++g) {
+        const float4 w = *reinterpret_cast<const float4*>(sW + k * U + g * 64 + 4 * tx);
+#pragma unroll
+        for (int rr = 0; rr < RM; ++rr) {
+          const float2 a2 = make_float2(av[rr], av[rr]);
+          acc[rr][2 * g + 0] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[rr][2 * g + 0]);
+          acc[rr][2 * g + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[rr][2 * g + 1]);
+        }
+      }
+    }
+  }
+  // same with float4 A loads (lda % 4 == 0, kc % 4 == 0, 16-byte aligned rows)
+  static __device__ __forceinline__ void mma(int tid, Acc& acc, const float* __restrict__ sA, int lda, const float* __restrict__ sW,
+                                             int kc) {
+    const int ty = tid >> 4, tx = tid & 15;
+    const float* ap = sA + (RM * ty) * lda;
+#pragma unroll 2
+    for (int k = 0; k < kc; k += 4) {
+      float av[RM][4];
+#pragma unroll
+      for (int rr = 0; rr < RM; ++rr) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + rr * lda + k);
+        av[rr][0] = a.x; av[rr][1] = a.y; av[rr][2] = a.z; av[rr][3] = a.w;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int g = 0; g < U / 64; ++g) {
+          const float4 w = *reinterpret_cast<const float4*>(sW + (k + kk) * U + g * 64 + 4 * tx);
+#pragma unroll
+          for (int rr = 0; rr < RM; ++rr) {
+            const float2 a2 = make_float2(av[rr][kk], av[rr][kk]);
+            acc[rr][2 * g + 0] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[rr][2 * g + 0]);
+            acc[rr][2 * g + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[rr][2 * g + 1]);
+          }
+        }
+      }
+    }
+  }
+  // sH[r][c] = relu(acc + bias[c])   (caller synchronises)
+  static __device__ __forceinline__ void store_bias_relu(int tid, const Acc& acc, const float* __restrict__ bias, float* sH) {
+    const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+    for (int g = 0; g < U / 64; ++g) {
+      const int c = g * 64 + 4 * tx;
+      const float4 b = *reinterpret_cast<const float4*>(bias + c);
+#pragma unroll
+      for (int rr = 0; rr < RM; ++rr) {
+        float4 v;
+        v.x = fmaxf(acc[rr][2 * g + 0].x + b.x, 0.f);
+        v.y = fmaxf(acc[rr][2 * g + 0].y + b.y, 0.f);
+        v.z = fmaxf(acc[rr][2 * g + 1].x + b.z, 0.f);
+        v.w = fmaxf(acc[rr][2 * g + 1].y + b.w, 0.f);
+        *reinterpret_cast<float4*>(sH + (RM * ty + rr) * HP + c) = v;
+      }
+    }
+  }
+  // output head, same arithmetic as actor_head_k (mdp_mlp.cuh): 8 threads per row, strided units, xor-shuffle tree
+  template <int KK>
+  static __device__ __forceinline__ void head_k(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* sL) {
+    for (int r = G.tid >> 3; r < TM; r += GTH / 8) {
+      const int part = G.tid & 7;
+      float s[KK];
+#pragma unroll
+      for (int a = 0; a < KK; ++a) s[a] = 0.f;
+      for (int u = part; u < U; u += 8) {
+        const float h = sH2[r * HP + u];
+        const float* w3 = w.W3 + u * KK;
+#pragma unroll
+        for (int a = 0; a < KK; ++a) s[a] = fmaf(h, w3[a], s[a]);
+      }
+#pragma unroll
+      for (int a = 0; a < KK; ++a) {
+        float v = s[a];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (part == 0) sL[r * KPAD + a] = v + w.b3[a];
+      }
+    }
+    G.sync();
+  }
+  static __device__ __forceinline__ void head(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* sL) {
+    if (w.out == 5) return head_k<5>(G, sH2, w, sL);
+    if (w.out == 9) return head_k<9>(G, sH2, w, sL);
+    const int K = w.out;
+    for (int idx = G.tid; idx < TM * K; idx += GTH) {
+      const int r = idx / K, a = idx - r * K;
+      float s = 0.f;
+      for (int u = 0; u < U; ++u) s = fmaf(sH2[r * HP + u], w.W3[u * K + a], s);
+      sL[r * KPAD + a] = s + w.b3[a];
+    }
+    G.sync();
+  }
+  // gumbel_softmax_tile (mdp_mlp.cuh) for a GTH-thread group, in-kernel Philox draws only
+  static __device__ __forceinline__ void gumbel_softmax(const Grp& G, const float* __restrict__ sL, float* __restrict__ sOut, int out_ld,
+                                                        int nrows, int K, int n_heads, const int* head_dim, long long row0,
+                                                        uint64_t seed, uint64_t counter, uint32_t tag) {
+    for (int idx = G.tid; idx < TM * K; idx += GTH) {
+      const int r = idx / K, a = idx - r * K;
+      if (r >= nrows) continue;
+      sOut[r * out_ld + a] = sL[r * KPAD + a] + gumbel_from_u(philox_u(seed, counter, tag, row0 + r, a));
+    }
+    G.sync();
+    for (int idx = G.tid; idx < TM * n_heads; idx += GTH) {
+      const int r = idx / n_heads, h = idx - r * n_heads;
+      if (r >= nrows) continue;
+      const int o = h ? head_dim[0] : 0, n = head_dim[h];
+      float m = -INFINITY;
+      for (int a = 0; a < n; ++a) m = fmaxf(m, sOut[r * out_ld + o + a]);
+      float z[MAXK];
+      float s = 0.f;
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a) {
+        if (a < n) {
+          z[a] = expf(sOut[r * out_ld + o + a] - m);
+          s += z[a];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a)
+        if (a < n) sOut[r * out_ld + o + a] = z[a] / s;
+    }
+    G.sync();
+  }
+};
+
 struct RolloutArgs {
   int E, steps, reset_after;
   float* state;
@@ -32,8 +187,8 @@ struct RolloutArgs {
   float* ep_return;  // optional (E, A): sum of rewards over the launch
 };
 
-// NG groups of NT = 256 threads; group g runs the actor MLPs of agents g, g+NG, ... concurrently with the
-// other groups (named barriers 1..NG); the env phases use all NG*256 threads.
+// NG groups of GTH threads (128 with resident weights, else 256); group g runs the actor MLPs of agents g, g+NG, ...
+// concurrently with the other groups (named barriers 1..NG); the env phases use all NG*GTH threads.
 //
 // Replay rows are ASSEMBLED IN PLACE: the CTA owns two [32][row_stride] row buffers (ping-pong).  In the buffer
 // of step s the actors read obs_t from columns [0, sum D), the Gumbel-softmax writes act_t into [sum D, C), the
@@ -41,14 +196,16 @@ struct RolloutArgs {
 // columns); then ONE thread streams the 32 finished rows to the ring with a TMA bulk store
 // (cp.async.bulk.global.shared::cta) that overlaps with the next step's compute.
 template <int U, bool RESIDENT>
-__global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
+__global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
                                                           mdp_ring_layout L, RolloutArgs R, int NG) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4, EBP = REB + 1;
   const int tid = threadIdx.x, NTB = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nwarps = NTB >> 5;
-  const int grp = tid / NT;
-  const Grp G{tid - grp * NT, grp + 1};
+  constexpr int GTH = RESIDENT ? 128 : NT;
+  typedef EpTile<U, GTH> Tile;
+  const int grp = tid / GTH;
+  const Grp G{tid - grp * GTH, grp + 1, GTH};
   const int OS = P.obs_stride, A = P.A, RS = L.row_stride;
   const int e0 = blockIdx.x * REB;
   const int nE = min(REB, R.E - e0);
@@ -104,6 +261,12 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
   __syncthreads();
 
   // ---- the episode -----------------------------------------------------------------------------------
+#ifdef MDP_EPISODE_PROF
+  long long prof_t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_c = clock64();
+#define PROF_MARK(k) { const long long t_ = clock64(); prof_t[k] += t_ - prof_c; prof_c = t_; }
+#else
+#define PROF_MARK(k)
+#endif
   for (int s = 0; s < R.steps; ++s) {
     float* buf = sRow + (s & 1) * TM * RS;        // rows of this step
     float* nxt = sRow + ((s & 1) ^ 1) * TM * RS;  // rows of the next step (receive obs_{t+1} as their obs_t)
@@ -114,38 +277,50 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
       const int D = ag.obs_dim, K = ag.act_dim;
       MlpW w = ag.net[MDP_NET_P];
       if (RESIDENT) w = net_at<U>(sWts + sOff[i], D, K);
-      float2 acc[TM / 16][U / 32];
-      zero_acc<U, TM>(acc);
+      typename Tile::Acc acc;
+      Tile::zero(acc);
       if (RESIDENT) {
-        mma_tile_sa<U, TM>(G, acc, buf + ag.obs_off, RS, w.W1, D);
+        Tile::mma_sa(G.tid, acc, buf + ag.obs_off, RS, w.W1, D);
       } else {
         for (int k0 = 0; k0 < D; k0 += KC) {
           load_w_rows<U>(G, sWts, w.W1, k0, D);
           G.sync();
-          mma_tile_sa<U, TM>(G, acc, buf + ag.obs_off + k0, RS, sWts, min(KC, D - k0));
+          Tile::mma_sa(G.tid, acc, buf + ag.obs_off + k0, RS, sWts, min(KC, D - k0));
           G.sync();
         }
       }
-      store_bias_relu<U, TM>(G, acc, w.b1, sH1);
+      Tile::store_bias_relu(G.tid, acc, w.b1, sH1);
       G.sync();
+      PROF_MARK(5)
+      Tile::zero(acc);
       if (RESIDENT) {
-        zero_acc<U, TM>(acc);
-        mma_tile<U, TM>(G, acc, sH1, HP, w.W2, U);
+        Tile::mma(G.tid, acc, sH1, HP, w.W2, U);
       } else {
-        layer_h<U, TM, false>(G, acc, sH1, w.W2, sWts);
+        for (int k0 = 0; k0 < U; k0 += KC) {
+          load_w_rows<U>(G, sWts, w.W2, k0, U);
+          G.sync();
+          Tile::mma(G.tid, acc, sH1 + k0, HP, sWts, KC);
+          G.sync();
+        }
       }
-      store_bias_relu<U, TM>(G, acc, w.b2, sH2);
+      Tile::store_bias_relu(G.tid, acc, w.b2, sH2);
       G.sync();
-      actor_head<U, TM>(G, sH2, w, sL);
-      gumbel_softmax_tile<TM>(G, sL, buf + L.obs_sum + ag.act_off, RS, nE, K, ag.n_heads, ag.head_dim, nullptr, 0, 0, (long long)e0,
-                              R.seed, counter + (unsigned long long)s + 1ull, (uint32_t)i);
+      PROF_MARK(6)
+      Tile::head(G, sH2, w, sL);
+      PROF_MARK(7)
+      Tile::gumbel_softmax(G, sL, buf + L.obs_sum + ag.act_off, RS, nE, K, ag.n_heads, ag.head_dim, (long long)e0, R.seed,
+                           counter + (unsigned long long)s + 1ull, (uint32_t)i);
+      PROF_MARK(8)
     }
     // the bulk store of step s-1 must have finished READING `nxt` before phase (4) overwrites its obs columns
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();  // all groups' actions are in the row buffer
+    PROF_MARK(0)
     // (3) World.step and rewards (both CTA-collective, synchronised on return)
     env_physics<float, REB>(P, T, nE);
+    PROF_MARK(1)
     env_flags_rewards<float, REB, true>(P, T, nE);
+    PROF_MARK(2)
     // (4) next observations: into this row's next_obs columns and into the next row buffer's obs columns
     for (int c = lane; c < L.obs_sum; c += 32) {
       const ObsCol d = sCols[c];
@@ -164,6 +339,7 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
     // (5) hand the finished rows to the TMA engine: generic-proxy writes -> async proxy, then one bulk store
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
+    PROF_MARK(3)
     if (tid == 0) {
       const long long r0 = (cursor + (long long)s * R.E + e0) % R.capacity;
       const long long first = min((long long)nE, R.capacity - r0);  // rows before the ring wraps
@@ -176,7 +352,12 @@ __global__ void __launch_bounds__(1024) k_rollout_episode(CoreDev C, EnvParams P
                      : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
+    PROF_MARK(4)
   }
+#ifdef MDP_EPISODE_PROF
+  if (R.ep_return && blockIdx.x == 0 && tid == 0)
+    for (int k = 0; k < 10; ++k) R.ep_return[(size_t)R.E * A + k] = (float)prof_t[k];  // caller over-allocates ep_return by 16 floats
+#endif
 
   // ---- epilogue: optional reset_world, then hand state and observations back ----------------------------
   float* fin = sRow + (R.steps & 1) * TM * RS;  // obs_{T} lives in the obs columns of the next buffer
@@ -242,13 +423,13 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   bool resident = false;
   size_t smem = 0;
   for (int ng = P.A < 4 ? P.A : 4; ng >= 1 && NG == 0; --ng) {
-    if (ng * NT < REB * P.A) break;  // the physics phase needs one thread per (env, agent)
     const size_t base = 2 * r4((size_t)ng * TM * HP) + r4((size_t)ng * TM * KPAD) + r4(2 * (size_t)TM * lay.row_stride) +
                         r4((size_t)P.A * (REB + 1)) + r4(MDP_MAX_AGENTS + 1) +
                         r4(2 * (size_t)P.obs_stride) + r4(EnvTile<float, REB>::bytes(P.scomp, P.A, P.act_stride, false) / 4);
     const size_t smem_res = (base + wts + 16) * 4, smem_str = (base + (size_t)ng * KC * U + 16) * 4;
-    if (smem_res <= limit) { NG = ng; resident = true; smem = smem_res; }
-    else if (smem_str <= limit) { NG = ng; resident = false; smem = smem_str; }
+    // the physics phase needs one thread per (env, agent); resident groups are 128 threads, streaming groups 256
+    if (smem_res <= limit && ng * 128 >= REB * P.A) { NG = ng; resident = true; smem = smem_res; }
+    else if (smem_str <= limit && ng * NT >= REB * P.A) { NG = ng; resident = false; smem = smem_str; }
   }
   if (NG == 0)
     return fail(MDP_ENOTSUP, "mdp_rollout_episode: %d agents x %d observation floats do not fit one CTA's shared memory",
@@ -265,7 +446,7 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   cudaStream_t st = (cudaStream_t)stream;
   auto go = [&](auto kern) -> int {
     if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<cdiv(E, REB), NG * NT, smem, st>>>(d, P, env->d_cols, lay, R, NG);
+    kern<<<cdiv(E, REB), NG * (resident ? 128 : NT), smem, st>>>(d, P, env->d_cols, lay, R, NG);
     return check_launch("k_rollout_episode");
   };
   if (U == 64) return resident ? go(k_rollout_episode<64, true>) : go(k_rollout_episode<64, false>);
