@@ -74,18 +74,19 @@ __global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int 
   const int nE = min(SPREAD_EB, E - e0);
   const int e = e0 + tid;
   if (tid < nE) {
-    float px[A], py[A], vx[A], vy[A], lx[L], ly[L], a[AS];
+    SpreadRegs<A> S;
+    float a[AS];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      px[i] = state[(size_t)(4 * i + 0) * E + e];
-      py[i] = state[(size_t)(4 * i + 1) * E + e];
-      vx[i] = state[(size_t)(4 * i + 2) * E + e];
-      vy[i] = state[(size_t)(4 * i + 3) * E + e];
+      S.px[i] = state[(size_t)(4 * i + 0) * E + e];
+      S.py[i] = state[(size_t)(4 * i + 1) * E + e];
+      S.vx[i] = state[(size_t)(4 * i + 2) * E + e];
+      S.vy[i] = state[(size_t)(4 * i + 3) * E + e];
     }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      lx[l] = state[(size_t)(4 * A + 2 * l + 0) * E + e];
-      ly[l] = state[(size_t)(4 * A + 2 * l + 1) * E + e];
+      S.lx[l] = state[(size_t)(4 * A + 2 * l + 0) * E + e];
+      S.ly[l] = state[(size_t)(4 * A + 2 * l + 1) * E + e];
     }
     const float4* arow = reinterpret_cast<const float4*>(act + (size_t)e * AS);
 #pragma unroll
@@ -93,105 +94,18 @@ __global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int 
       const float4 v = arow[q];
       a[4 * q + 0] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
     }
-    // World.step: action force, soft contact between agents (landmarks do not collide in simple_spread), integration
-    const float k = (float)P.contact_margin, cf = (float)P.contact_force, zmin = -104.0f;
-    const float damp = 1.0f - (float)P.damping, dt = (float)P.dt;
-    float nvx[A], nvy[A], npx[A], npy[A];
+    const float msum = spread_step<A>(P, S, a);
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      float fx = a[5 * i + 1] - a[5 * i + 2];
-      float fy = a[5 * i + 3] - a[5 * i + 4];
-      const float sens = (float)P.sens[i];
-      fx *= sens;
-      fy *= sens;
-      const float si = P.sizef[i];
-#pragma unroll
-      for (int j = 0; j < A; ++j) {
-        if (j == i) continue;
-        const float dx = px[i] - px[j], dy = py[i] - py[j];
-        const float dist = sqrtf(dx * dx + dy * dy);
-        const float dmin = si + P.sizef[j];
-        const float z = -(dist - dmin) / k;
-        if (z < zmin) continue;
-        const float pen = logaddexp0<float>(z) * k;
-        fx = cf * dx / dist * pen + fx;
-        fy = cf * dy / dist * pen + fy;
-      }
-      float wx = vx[i] * damp, wy = vy[i] * damp;
-      wx += fx * dt;
-      wy += fy * dt;
-      const float ms = (float)P.max_speed[i];
-      if (ms > 0.f) {
-        const float speed = sqrtf(wx * wx + wy * wy);
-        if (speed > ms) {
-          wx = wx / speed * ms;
-          wy = wy / speed * ms;
-        }
-      }
-      nvx[i] = wx; nvy[i] = wy;
-      npx[i] = px[i] + wx * dt;
-      npy[i] = py[i] + wy * dt;
-    }
-#pragma unroll
-    for (int i = 0; i < A; ++i) {
-      state[(size_t)(4 * i + 0) * E + e] = npx[i];
-      state[(size_t)(4 * i + 1) * E + e] = npy[i];
-      state[(size_t)(4 * i + 2) * E + e] = nvx[i];
-      state[(size_t)(4 * i + 3) * E + e] = nvy[i];
-    }
-    // Scenario.reward: per landmark the distance of the closest agent; per agent the collision count (self included);
-    // every agent receives the sum over agents (shared reward)
-    float r[A];
-    float msum = 0.f;
-    {
-      float m[L];
-#pragma unroll
-      for (int l = 0; l < L; ++l) {
-        float best = 0.f;
-#pragma unroll
-        for (int q = 0; q < A; ++q) {
-          const float dx = npx[q] - lx[l], dy = npy[q] - ly[l];
-          const float d = sqrtf(dx * dx + dy * dy);
-          best = (q == 0 || d < best) ? d : best;
-        }
-        m[l] = best;
-      }
-#pragma unroll
-      for (int i = 0; i < A; ++i) {
-        int cnt = 0;
-#pragma unroll
-        for (int q = 0; q < A; ++q) {
-          const float dx = npx[q] - npx[i], dy = npy[q] - npy[i];
-          cnt += (sqrtf(dx * dx + dy * dy) < P.sizef[q] + P.sizef[i]) ? 1 : 0;
-        }
-        float ri = 0.f;
-#pragma unroll
-        for (int l = 0; l < L; ++l) ri -= m[l];
-        ri -= (float)cnt;
-        r[i] = ri;
-      }
-#pragma unroll
-      for (int i = 0; i < A; ++i) msum += r[i];
+      state[(size_t)(4 * i + 0) * E + e] = S.px[i];
+      state[(size_t)(4 * i + 1) * E + e] = S.py[i];
+      state[(size_t)(4 * i + 2) * E + e] = S.vx[i];
+      state[(size_t)(4 * i + 3) * E + e] = S.vy[i];
     }
 #pragma unroll
     for (int i = 0; i < A; ++i) rew_out[(size_t)e * A + i] = msum;
-    // Scenario.observation of every agent: [vel, pos, landmarks - pos, others - pos, silent comm zeros]
     float o[OS];
-#pragma unroll
-    for (int i = 0; i < A; ++i) {
-      o[i * D + 0] = nvx[i]; o[i * D + 1] = nvy[i]; o[i * D + 2] = npx[i]; o[i * D + 3] = npy[i];
-#pragma unroll
-      for (int l = 0; l < L; ++l) { o[i * D + 4 + 2 * l] = lx[l] - npx[i]; o[i * D + 5 + 2 * l] = ly[l] - npy[i]; }
-#pragma unroll
-      for (int q = 0; q < A; ++q) {
-        if (q == i) continue;
-        const int c = 4 + 2 * L + 2 * (q < i ? q : q - 1);
-        o[i * D + c] = npx[q] - npx[i];
-        o[i * D + c + 1] = npy[q] - npy[i];
-      }
-#pragma unroll
-      for (int c = 4 + 2 * L + 2 * (A - 1); c < D; ++c) o[i * D + c] = 0.f;
-    }
+    spread_obs<A>(S, o);
 #pragma unroll
     for (int c = A * D; c < OS; ++c) o[c] = 0.f;
     // row pitch OS4 + 1 float4 (odd for every A here, or made odd): conflict-free 16-byte stores and reads

@@ -392,6 +392,150 @@ __device__ __forceinline__ real env_reset_value(const EnvParams& P, int comp, lo
   return lo + (hi - lo) * u;
 }
 
+// --------------------------------------------------------------------------------------------
+// simple_spread in registers (float32 state, A agents == A landmarks known at compile time): one thread owns one env
+// instance.  Used by k_env_step_spread (mdp_env.cu) and by the persistent episode kernel (mdp_rollout.cu).
+// Arithmetic and operation order follow env_physics / env_flags_rewards / env_obs_value exactly.
+// --------------------------------------------------------------------------------------------
+template <int A>
+struct SpreadRegs {
+  float px[A], py[A], vx[A], vy[A], lx[A], ly[A];
+};
+
+// dx*dx + dy*dy with the contraction pinned (one multiply, one fused multiply-add): the pieces below are inlined into
+// different kernels and must round identically in all of them
+__device__ __forceinline__ float sq_norm2(float dx, float dy) { return __fmaf_rn(dx, dx, __fmul_rn(dy, dy)); }
+
+// The step is written as per-agent pieces so that it can run either entirely in one thread (k_env_step_spread: i is a
+// compile-time constant after unrolling) or spread over one thread per (env instance, agent) (episode kernel: i = warp index).
+
+// World.step for agent i: action force, soft contact with the other agents (landmarks do not collide in simple_spread),
+// damping, integration.  px/py = positions of ALL agents BEFORE the step; (pxi, pyi, vxi, vyi) = agent i, updated in place;
+// a = agent i's 5 action floats.
+template <int A, typename ActT>
+__device__ __forceinline__ void spread_agent_step(const EnvParams& P, int i, const float (&px)[A], const float (&py)[A], float& pxi,
+                                                  float& pyi, float& vxi, float& vyi, const ActT& a) {
+  const float k = (float)P.contact_margin, cf = (float)P.contact_force, zmin = -104.0f;
+  const float damp = 1.0f - (float)P.damping, dt = (float)P.dt;
+  const float sens = (float)P.sens[i];
+  float fx = __fmul_rn(__fsub_rn(a[1], a[2]), sens);
+  float fy = __fmul_rn(__fsub_rn(a[3], a[4]), sens);
+  const float si = P.sizef[i];
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    if (j == i) continue;
+    const float dx = __fsub_rn(pxi, px[j]), dy = __fsub_rn(pyi, py[j]);
+    const float dist = __fsqrt_rn(sq_norm2(dx, dy));
+    const float dmin = __fadd_rn(si, P.sizef[j]);
+    const float z = __fdiv_rn(-__fsub_rn(dist, dmin), k);
+    if (z < zmin) continue;
+    const float pen = __fmul_rn(logaddexp0<float>(z), k);
+    fx = __fmaf_rn(__fdiv_rn(__fmul_rn(cf, dx), dist), pen, fx);
+    fy = __fmaf_rn(__fdiv_rn(__fmul_rn(cf, dy), dist), pen, fy);
+  }
+  float wx = __fmaf_rn(fx, dt, __fmul_rn(vxi, damp));
+  float wy = __fmaf_rn(fy, dt, __fmul_rn(vyi, damp));
+  const float ms = (float)P.max_speed[i];
+  if (ms > 0.f) {
+    const float speed = __fsqrt_rn(sq_norm2(wx, wy));
+    if (speed > ms) {
+      wx = __fmul_rn(__fdiv_rn(wx, speed), ms);
+      wy = __fmul_rn(__fdiv_rn(wy, speed), ms);
+    }
+  }
+  vxi = wx; vyi = wy;
+  pxi = __fmaf_rn(wx, dt, pxi);
+  pyi = __fmaf_rn(wy, dt, pyi);
+}
+
+// Scenario.reward pieces (positions AFTER the step): distance of the closest agent to one landmark ...
+template <int A>
+__device__ __forceinline__ float spread_landmark_min(const float (&px)[A], const float (&py)[A], float lx, float ly) {
+  float best = 0.f;
+#pragma unroll
+  for (int q = 0; q < A; ++q) {
+    const float dx = __fsub_rn(px[q], lx), dy = __fsub_rn(py[q], ly);
+    const float d = __fsqrt_rn(sq_norm2(dx, dy));
+    best = (q == 0 || d < best) ? d : best;
+  }
+  return best;
+}
+// ... the collision count of agent i (self included) ...
+template <int A>
+__device__ __forceinline__ int spread_collisions(const EnvParams& P, int i, const float (&px)[A], const float (&py)[A], float pxi,
+                                                 float pyi) {
+  int cnt = 0;
+#pragma unroll
+  for (int q = 0; q < A; ++q) {
+    const float dx = __fsub_rn(px[q], pxi), dy = __fsub_rn(py[q], pyi);
+    cnt += (__fsqrt_rn(sq_norm2(dx, dy)) < __fadd_rn(P.sizef[q], P.sizef[i])) ? 1 : 0;
+  }
+  return cnt;
+}
+// ... and the shared reward: every agent receives the sum over agents of (-sum_l m[l] - cnt[i])
+template <int A>
+__device__ __forceinline__ float spread_reward_sum(const float (&m)[A], const int (&cnt)[A]) {
+  float msum = 0.f;
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    float ri = 0.f;
+#pragma unroll
+    for (int l = 0; l < A; ++l) ri -= m[l];
+    ri -= (float)cnt[i];
+    msum += ri;
+  }
+  return msum;
+}
+
+// Scenario.observation of agent i: [vel, pos, landmarks - pos, others - pos, silent comm zeros], 6A floats through out(c, v)
+template <int A, typename Out>
+__device__ __forceinline__ void spread_obs_agent(int i, const float (&px)[A], const float (&py)[A], float pxi, float pyi, float vxi,
+                                                 float vyi, const float (&lx)[A], const float (&ly)[A], Out&& out) {
+  constexpr int L = A, D = 6 * A;
+  out(0, vxi); out(1, vyi); out(2, pxi); out(3, pyi);
+#pragma unroll
+  for (int l = 0; l < L; ++l) { out(4 + 2 * l, lx[l] - pxi); out(5 + 2 * l, ly[l] - pyi); }
+#pragma unroll
+  for (int q = 0; q < A; ++q) {
+    if (q == i) continue;
+    const int c = 4 + 2 * L + 2 * (q < i ? q : q - 1);
+    out(c, px[q] - pxi);
+    out(c + 1, py[q] - pyi);
+  }
+#pragma unroll
+  for (int c = 4 + 2 * L + 2 * (A - 1); c < D; ++c) out(c, 0.f);
+}
+
+// World.step + Scenario.reward in one thread: advances S in place, returns the shared reward.
+// a = the joint action row, 5 floats per agent.
+template <int A, typename ActT>
+__device__ __forceinline__ float spread_step(const EnvParams& P, SpreadRegs<A>& S, const ActT& a) {
+  float npx[A], npy[A], nvx[A], nvy[A];
+#pragma unroll
+  for (int i = 0; i < A; ++i) {
+    npx[i] = S.px[i]; npy[i] = S.py[i]; nvx[i] = S.vx[i]; nvy[i] = S.vy[i];
+    const float ai[5] = {a[5 * i], a[5 * i + 1], a[5 * i + 2], a[5 * i + 3], a[5 * i + 4]};
+    spread_agent_step<A>(P, i, S.px, S.py, npx[i], npy[i], nvx[i], nvy[i], ai);
+  }
+#pragma unroll
+  for (int i = 0; i < A; ++i) { S.px[i] = npx[i]; S.py[i] = npy[i]; S.vx[i] = nvx[i]; S.vy[i] = nvy[i]; }
+  float m[A];
+  int cnt[A];
+#pragma unroll
+  for (int l = 0; l < A; ++l) m[l] = spread_landmark_min<A>(S.px, S.py, S.lx[l], S.ly[l]);
+#pragma unroll
+  for (int i = 0; i < A; ++i) cnt[i] = spread_collisions<A>(P, i, S.px, S.py, S.px[i], S.py[i]);
+  return spread_reward_sum<A>(m, cnt);
+}
+
+// every agent's observation; o holds >= A * 6A floats
+template <int A, typename ObsT>
+__device__ __forceinline__ void spread_obs(const SpreadRegs<A>& S, ObsT& o) {
+#pragma unroll
+  for (int i = 0; i < A; ++i)
+    spread_obs_agent<A>(i, S.px, S.py, S.px[i], S.py[i], S.vx[i], S.vy[i], S.lx, S.ly, [&](int c, float v) { o[i * 6 * A + c] = v; });
+}
+
 }  // namespace mdp
 
 struct mdp_env {

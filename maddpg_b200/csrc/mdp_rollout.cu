@@ -142,6 +142,57 @@ struct EpTile {
     }
     G.sync();
   }
+  // Single-head actors with KK <= 8 outputs: head + Gumbel-softmax fused, 8 lanes per row, no shared-memory round trip and no
+  // group barrier in between.  noise[p] = -log(-log u) of element (row (tid >> 3) + p * GTH / 8, column tid & 7), drawn by the
+  // caller BEFORE layer 1 so the Philox / log chains overlap the GEMM loads.  Same arithmetic, in the same order, as
+  // head_k + gumbel_softmax below: strided partial sums, xor-shuffle tree, sequential softmax sum.
+  static constexpr int NP = TM * 8 / GTH;
+  template <int KK>
+  static __device__ __forceinline__ void head_gumbel(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* __restrict__ sOut,
+                                                     int out_ld, int nrows, const float (&noise)[NP]) {
+    const int part = G.tid & 7, lane_base = (G.tid & 31) & ~7;
+    float s[NP][KK];
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int a = 0; a < KK; ++a) s[p][a] = 0.f;
+#pragma unroll
+    for (int j = 0; j < U / 8; ++j) {
+      const int u = part + 8 * j;
+      float h[NP];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) h[p] = sH2[((G.tid >> 3) + p * (GTH / 8)) * HP + u];
+      const float* w3 = w.W3 + u * KK;
+#pragma unroll
+      for (int a = 0; a < KK; ++a) {
+        const float wv = w3[a];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) s[p][a] = fmaf(h[p], wv, s[p][a]);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      const int r = (G.tid >> 3) + p * (GTH / 8);
+      float mine = -INFINITY;  // perturbed logit of column `part`
+#pragma unroll
+      for (int a = 0; a < KK; ++a) {
+        float v = s[p][a];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (part == a) mine = (v + w.b3[a]) + noise[p];
+      }
+      float m = -INFINITY;
+#pragma unroll
+      for (int a = 0; a < KK; ++a) m = fmaxf(m, __shfl_sync(0xffffffffu, mine, lane_base + a));
+      const float z = part < KK ? expf(mine - m) : 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int a = 0; a < KK; ++a) sum += __shfl_sync(0xffffffffu, z, lane_base + a);
+      if (part < KK && r < nrows) sOut[r * out_ld + part] = z / sum;
+    }
+    G.sync();
+  }
   // gumbel_softmax_tile (mdp_mlp.cuh) for a GTH-thread group, in-kernel Philox draws only
   static __device__ __forceinline__ void gumbel_softmax(const Grp& G, const float* __restrict__ sL, float* __restrict__ sOut, int out_ld,
                                                         int nrows, int K, int n_heads, const int* head_dim, long long row0,
@@ -195,7 +246,11 @@ struct RolloutArgs {
 // env phase writes next_obs / rew / done into their columns (and next_obs also into the OTHER buffer's obs_t
 // columns); then ONE thread streams the 32 finished rows to the ring with a TMA bulk store
 // (cp.async.bulk.global.shared::cta) that overlaps with the next step's compute.
-template <int U, bool RESIDENT>
+//
+// SA > 0: simple_spread with SA agents -- the env phase of a step runs in REGISTERS on warp 0 (thread = env instance,
+// spread_step / spread_obs of mdp_env_dev.cuh, the code of k_env_step_spread) instead of the table-driven CTA-collective
+// phases: the state never leaves the 32 threads' registers between the prologue and the epilogue.
+template <int U, bool RESIDENT, int SA>
 __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
                                                           mdp_ring_layout L, RolloutArgs R, int NG) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -217,6 +272,7 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
   float* sH2 = sm.take(NG * TM * HP) + grp * TM * HP;
   float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
   float* sRet = sm.take(A * EBP);
+  float* sPart = sm.take(2 * 8 * 32);  // SA > 0: per-agent reward partials (landmark minima, collision counts)
   int* sOff = reinterpret_cast<int*>(sm.take(MDP_MAX_AGENTS + 1));
   ObsCol* sCols = reinterpret_cast<ObsCol*>(sm.take(2 * OS));
   float* sEnv = sm.take((int)(EnvTile<float, REB>::bytes(P.scomp, A, P.act_stride, false) / 4));
@@ -260,7 +316,22 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
   }
   __syncthreads();
 
+  // SA > 0: thread (warp i < SA, lane) owns agent i of env instance `lane`: its state and the landmarks stay in registers;
+  // positions are exchanged through the state tile (T.sS rows 4j, 4j+1), reward partials through sPart
+  constexpr int SAc = SA > 0 ? SA : 1;
+  float pxi = 0.f, pyi = 0.f, vxi = 0.f, vyi = 0.f, lxi = 0.f, lyi = 0.f, ret_reg = 0.f;
+  float lx[SAc], ly[SAc];
+  if (SA > 0 && warp < SA) {
+    pxi = T.sS[(4 * warp + 0) * EBP + lane]; pyi = T.sS[(4 * warp + 1) * EBP + lane];
+    vxi = T.sS[(4 * warp + 2) * EBP + lane]; vyi = T.sS[(4 * warp + 3) * EBP + lane];
+    lxi = T.sS[(4 * SA + 2 * warp + 0) * EBP + lane]; lyi = T.sS[(4 * SA + 2 * warp + 1) * EBP + lane];
+#pragma unroll
+    for (int l = 0; l < SAc; ++l) { lx[l] = T.sS[(4 * SA + 2 * l + 0) * EBP + lane]; ly[l] = T.sS[(4 * SA + 2 * l + 1) * EBP + lane]; }
+  }
+  auto env_bar = [] { asm volatile("bar.sync 8, %0;" ::"r"(32 * SAc) : "memory"); };
+
   // ---- the episode -----------------------------------------------------------------------------------
+  long long ring_row = (cursor + e0) % R.capacity;  // ring row of this CTA's first env at step s (thread 0 keeps it current)
 #ifdef MDP_EPISODE_PROF
   long long prof_t[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_c = clock64();
 #define PROF_MARK(k) { const long long t_ = clock64(); prof_t[k] += t_ - prof_c; prof_c = t_; }
@@ -277,6 +348,17 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       const int D = ag.obs_dim, K = ag.act_dim;
       MlpW w = ag.net[MDP_NET_P];
       if (RESIDENT) w = net_at<U>(sWts + sOff[i], D, K);
+      const bool fused_head = ag.n_heads == 1 && K == 5;  // Discrete(5): every MPE movement head
+      float noise[Tile::NP];
+      if (fused_head) {
+#pragma unroll
+        for (int p = 0; p < Tile::NP; ++p) {
+          const int r = (G.tid >> 3) + p * (GTH / 8), a = G.tid & 7;
+          noise[p] = (a < K && r < nE)
+                         ? gumbel_from_u(philox_u(R.seed, counter + (unsigned long long)s + 1ull, (uint32_t)i, (long long)e0 + r, a))
+                         : 0.f;
+        }
+      }
       typename Tile::Acc acc;
       Tile::zero(acc);
       if (RESIDENT) {
@@ -306,16 +388,52 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       Tile::store_bias_relu(G.tid, acc, w.b2, sH2);
       G.sync();
       PROF_MARK(6)
-      Tile::head(G, sH2, w, sL);
-      PROF_MARK(7)
-      Tile::gumbel_softmax(G, sL, buf + L.obs_sum + ag.act_off, RS, nE, K, ag.n_heads, ag.head_dim, (long long)e0, R.seed,
-                           counter + (unsigned long long)s + 1ull, (uint32_t)i);
+      if (fused_head) {
+        Tile::template head_gumbel<5>(G, sH2, w, buf + L.obs_sum + ag.act_off, RS, nE, noise);
+      } else {
+        Tile::head(G, sH2, w, sL);
+        PROF_MARK(7)
+        Tile::gumbel_softmax(G, sL, buf + L.obs_sum + ag.act_off, RS, nE, K, ag.n_heads, ag.head_dim, (long long)e0, R.seed,
+                             counter + (unsigned long long)s + 1ull, (uint32_t)i);
+      }
       PROF_MARK(8)
     }
     // the bulk store of step s-1 must have finished READING `nxt` before phase (4) overwrites its obs columns
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();  // all groups' actions are in the row buffer
     PROF_MARK(0)
+    if (SA > 0) {
+      // (3)+(4) in registers: World.step, shared reward and observation of agent `warp` of env instance `lane`
+      if (warp < SA) {
+        const int i = warp, D = 6 * SAc;
+        float px[SAc], py[SAc];
+#pragma unroll
+        for (int j = 0; j < SAc; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + lane]; py[j] = T.sS[(4 * j + 1) * EBP + lane]; }
+        const float* arow = buf + lane * RS + L.obs_sum + 5 * i;
+        const float a[5] = {arow[0], arow[1], arow[2], arow[3], arow[4]};
+        spread_agent_step<SAc>(P, i, px, py, pxi, pyi, vxi, vyi, a);
+        env_bar();  // every agent has read the old positions
+        T.sS[(4 * i + 0) * EBP + lane] = pxi;
+        T.sS[(4 * i + 1) * EBP + lane] = pyi;
+        env_bar();
+#pragma unroll
+        for (int j = 0; j < SAc; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + lane]; py[j] = T.sS[(4 * j + 1) * EBP + lane]; }
+        sPart[i * 32 + lane] = spread_landmark_min<SAc>(px, py, lxi, lyi);
+        sPart[(SAc + i) * 32 + lane] = __int_as_float(spread_collisions<SAc>(P, i, px, py, pxi, pyi));
+        float* nx = buf + lane * RS + L.nx_off + i * D;
+        float* ob = nxt + lane * RS + i * D;
+        spread_obs_agent<SAc>(i, px, py, pxi, pyi, vxi, vyi, lx, ly, [&](int c, float v) { nx[c] = v; ob[c] = v; });
+        env_bar();
+        float m[SAc];
+        int cnt[SAc];
+#pragma unroll
+        for (int j = 0; j < SAc; ++j) { m[j] = sPart[j * 32 + lane]; cnt[j] = __float_as_int(sPart[(SAc + j) * 32 + lane]); }
+        const float msum = spread_reward_sum<SAc>(m, cnt);
+        buf[lane * RS + L.rw_off + i] = msum;
+        ret_reg += msum;
+      }
+      PROF_MARK(1)
+    } else {
     // (3) World.step and rewards (both CTA-collective, synchronised on return)
     env_physics<float, REB>(P, T, nE);
     PROF_MARK(1)
@@ -336,12 +454,15 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       buf[ee * RS + L.rw_off + ii] = r;
       sRet[ii * EBP + ee] += r;
     }
+    }
     // (5) hand the finished rows to the TMA engine: generic-proxy writes -> async proxy, then one bulk store
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     PROF_MARK(3)
     if (tid == 0) {
-      const long long r0 = (cursor + (long long)s * R.E + e0) % R.capacity;
+      const long long r0 = ring_row;
+      ring_row += R.E;
+      if (ring_row >= R.capacity) ring_row -= R.capacity;  // capacity >= E * steps (checked on the host)
       const long long first = min((long long)nE, R.capacity - r0);  // rows before the ring wraps
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(R.ring + r0 * RS), "r"(smem_u32(buf)),
                    "r"((uint32_t)(first * RS * 4))
@@ -362,6 +483,11 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
   // ---- epilogue: optional reset_world, then hand state and observations back ----------------------------
   float* fin = sRow + (R.steps & 1) * TM * RS;  // obs_{T} lives in the obs columns of the next buffer
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (SA > 0 && warp < SA) {  // registers -> state tile (positions are current there already)
+    T.sS[(4 * warp + 2) * EBP + lane] = vxi;
+    T.sS[(4 * warp + 3) * EBP + lane] = vyi;
+    sRet[warp * EBP + lane] = ret_reg;
+  }
   __syncthreads();
   if (R.reset_after) {
     for (int idx = tid; idx < P.scomp * REB; idx += NTB) {
@@ -424,7 +550,7 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   size_t smem = 0;
   for (int ng = P.A < 4 ? P.A : 4; ng >= 1 && NG == 0; --ng) {
     const size_t base = 2 * r4((size_t)ng * TM * HP) + r4((size_t)ng * TM * KPAD) + r4(2 * (size_t)TM * lay.row_stride) +
-                        r4((size_t)P.A * (REB + 1)) + r4(MDP_MAX_AGENTS + 1) +
+                        r4((size_t)P.A * (REB + 1)) + r4(2 * 8 * 32) + r4(MDP_MAX_AGENTS + 1) +
                         r4(2 * (size_t)P.obs_stride) + r4(EnvTile<float, REB>::bytes(P.scomp, P.A, P.act_stride, false) / 4);
     const size_t smem_res = (base + wts + 16) * 4, smem_str = (base + (size_t)ng * KC * U + 16) * 4;
     // the physics phase needs one thread per (env, agent); resident groups are 128 threads, streaming groups 256
@@ -449,6 +575,14 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
     kern<<<cdiv(E, REB), NG * (resident ? 128 : NT), smem, st>>>(d, P, env->d_cols, lay, R, NG);
     return check_launch("k_rollout_episode");
   };
-  if (U == 64) return resident ? go(k_rollout_episode<64, true>) : go(k_rollout_episode<64, false>);
-  return resident ? go(k_rollout_episode<128, true>) : go(k_rollout_episode<128, false>);
+  if (U == 64 && resident && P.scenario == MDP_SIMPLE_SPREAD && !env->force_generic && !env->cfg.state_f64) {
+    switch (P.A) {  // register-resident env phase (as mdp_env_step picks k_env_step_spread)
+      case 2: return go(k_rollout_episode<64, true, 2>);
+      case 3: return go(k_rollout_episode<64, true, 3>);
+      case 4: return go(k_rollout_episode<64, true, 4>);
+      default: break;  // A >= 5: 6*A*A observation floats per thread no longer fit the register file
+    }
+  }
+  if (U == 64) return resident ? go(k_rollout_episode<64, true, 0>) : go(k_rollout_episode<64, false, 0>);
+  return resident ? go(k_rollout_episode<128, true, 0>) : go(k_rollout_episode<128, false, 0>);
 }

@@ -251,9 +251,10 @@ def test_graph_rollout_and_update_round_match_eager_semantics():
     assert not torch.equal(p1, core.params)
 
 
-@pytest.mark.parametrize("scenario,units", [("simple_spread", 64), ("simple_tag", 64), ("simple", 64),
-                                            ("simple_world_comm", 128)])
-def test_episode_kernel_matches_per_step_kernels(scenario, units):
+@pytest.mark.parametrize("scenario,units,generic", [("simple_spread", 64, True), ("simple_spread", 64, False),
+                                                    ("simple_tag", 64, True), ("simple", 64, True),
+                                                    ("simple_world_comm", 128, True)])
+def test_episode_kernel_matches_per_step_kernels(scenario, units, generic):
     """mdp_rollout_episode (persistent episode kernel) against the per-step path on the same seeds and
     Philox counters: identical replay rows, final state and observations (incl. the device reset)."""
     from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
@@ -262,9 +263,10 @@ def test_episode_kernel_matches_per_step_kernels(scenario, units):
     rings, finals = [], []
     for mode in ("eager", "mega"):
         env = BatchedMultiAgentEnv(scenario, num_envs=E, squeeze=False, seed=11)
-        # the episode kernel shares its physics code with the table-driven per-step kernel; simple_spread's register
-        # kernel is compared with that one step by step in test_env_gpu.py (last-bit differences grow over 75 free steps)
-        env.force_generic_kernel(True)
+        # generic: both paths run the table-driven physics; not generic (simple_spread): both run the register-resident
+        # spread_step / spread_obs.  Register vs table code is compared step by step in test_env_gpu.py (last-bit
+        # differences grow over 75 free steps).
+        env.force_generic_kernel(generic)
         core = MADDPGCore(env.obs_dims, env.action_space, [False] * env.n, num_units=units,
                           replay_capacity=E * T * 2 + 13, seed=3)
         roll = BatchedRollout(env, core, T, mode=mode)
