@@ -406,6 +406,29 @@ struct SpreadRegs {
 // different kernels and must round identically in all of them
 __device__ __forceinline__ float sq_norm2(float dx, float dy) { return __fmaf_rn(dx, dx, __fmul_rn(dy, dy)); }
 
+// scenario constants as floats, converted once per kernel (EnvParams keeps the reference's float64 values)
+template <int A>
+struct SpreadConsts {
+  float k, cf, damp, dt, size[A];
+};
+struct SpreadAgentConsts {
+  float sens, ms, size;
+};
+template <int A>
+__device__ __forceinline__ SpreadConsts<A> spread_consts(const EnvParams& P) {
+  SpreadConsts<A> c;
+  c.k = (float)P.contact_margin; c.cf = (float)P.contact_force;
+  c.damp = 1.0f - (float)P.damping; c.dt = (float)P.dt;
+#pragma unroll
+  for (int j = 0; j < A; ++j) c.size[j] = P.sizef[j];
+  return c;
+}
+__device__ __forceinline__ SpreadAgentConsts spread_agent_consts(const EnvParams& P, int i) {
+  SpreadAgentConsts a;
+  a.sens = (float)P.sens[i]; a.ms = (float)P.max_speed[i]; a.size = P.sizef[i];
+  return a;
+}
+
 // The step is written as per-agent pieces so that it can run either entirely in one thread (k_env_step_spread: i is a
 // compile-time constant after unrolling) or spread over one thread per (env instance, agent) (episode kernel: i = warp index).
 
@@ -413,20 +436,21 @@ __device__ __forceinline__ float sq_norm2(float dx, float dy) { return __fmaf_rn
 // damping, integration.  px/py = positions of ALL agents BEFORE the step; (pxi, pyi, vxi, vyi) = agent i, updated in place;
 // a = agent i's 5 action floats.
 template <int A, typename ActT>
-__device__ __forceinline__ void spread_agent_step(const EnvParams& P, int i, const float (&px)[A], const float (&py)[A], float& pxi,
-                                                  float& pyi, float& vxi, float& vyi, const ActT& a) {
-  const float k = (float)P.contact_margin, cf = (float)P.contact_force, zmin = -104.0f;
-  const float damp = 1.0f - (float)P.damping, dt = (float)P.dt;
-  const float sens = (float)P.sens[i];
+__device__ __forceinline__ void spread_agent_step(const SpreadConsts<A>& Cn, const SpreadAgentConsts& Ai, int i, const float (&px)[A],
+                                                  const float (&py)[A], float& pxi, float& pyi, float& vxi, float& vyi,
+                                                  const ActT& a) {
+  const float k = Cn.k, cf = Cn.cf, zmin = -104.0f;
+  const float damp = Cn.damp, dt = Cn.dt;
+  const float sens = Ai.sens;
   float fx = __fmul_rn(__fsub_rn(a[1], a[2]), sens);
   float fy = __fmul_rn(__fsub_rn(a[3], a[4]), sens);
-  const float si = P.sizef[i];
+  const float si = Ai.size;
 #pragma unroll
   for (int j = 0; j < A; ++j) {
     if (j == i) continue;
     const float dx = __fsub_rn(pxi, px[j]), dy = __fsub_rn(pyi, py[j]);
     const float dist = __fsqrt_rn(sq_norm2(dx, dy));
-    const float dmin = __fadd_rn(si, P.sizef[j]);
+    const float dmin = __fadd_rn(si, Cn.size[j]);
     const float z = __fdiv_rn(-__fsub_rn(dist, dmin), k);
     if (z < zmin) continue;
     const float pen = __fmul_rn(logaddexp0<float>(z), k);
@@ -435,7 +459,7 @@ __device__ __forceinline__ void spread_agent_step(const EnvParams& P, int i, con
   }
   float wx = __fmaf_rn(fx, dt, __fmul_rn(vxi, damp));
   float wy = __fmaf_rn(fy, dt, __fmul_rn(vyi, damp));
-  const float ms = (float)P.max_speed[i];
+  const float ms = Ai.ms;
   if (ms > 0.f) {
     const float speed = __fsqrt_rn(sq_norm2(wx, wy));
     if (speed > ms) {
@@ -462,13 +486,13 @@ __device__ __forceinline__ float spread_landmark_min(const float (&px)[A], const
 }
 // ... the collision count of agent i (self included) ...
 template <int A>
-__device__ __forceinline__ int spread_collisions(const EnvParams& P, int i, const float (&px)[A], const float (&py)[A], float pxi,
-                                                 float pyi) {
+__device__ __forceinline__ int spread_collisions(const SpreadConsts<A>& Cn, const SpreadAgentConsts& Ai, const float (&px)[A],
+                                                 const float (&py)[A], float pxi, float pyi) {
   int cnt = 0;
 #pragma unroll
   for (int q = 0; q < A; ++q) {
     const float dx = __fsub_rn(px[q], pxi), dy = __fsub_rn(py[q], pyi);
-    cnt += (__fsqrt_rn(sq_norm2(dx, dy)) < __fadd_rn(P.sizef[q], P.sizef[i])) ? 1 : 0;
+    cnt += (__fsqrt_rn(sq_norm2(dx, dy)) < __fadd_rn(Cn.size[q], Ai.size)) ? 1 : 0;
   }
   return cnt;
 }
@@ -510,12 +534,13 @@ __device__ __forceinline__ void spread_obs_agent(int i, const float (&px)[A], co
 // a = the joint action row, 5 floats per agent.
 template <int A, typename ActT>
 __device__ __forceinline__ float spread_step(const EnvParams& P, SpreadRegs<A>& S, const ActT& a) {
+  const SpreadConsts<A> Cn = spread_consts<A>(P);
   float npx[A], npy[A], nvx[A], nvy[A];
 #pragma unroll
   for (int i = 0; i < A; ++i) {
     npx[i] = S.px[i]; npy[i] = S.py[i]; nvx[i] = S.vx[i]; nvy[i] = S.vy[i];
     const float ai[5] = {a[5 * i], a[5 * i + 1], a[5 * i + 2], a[5 * i + 3], a[5 * i + 4]};
-    spread_agent_step<A>(P, i, S.px, S.py, npx[i], npy[i], nvx[i], nvy[i], ai);
+    spread_agent_step<A>(Cn, spread_agent_consts(P, i), i, S.px, S.py, npx[i], npy[i], nvx[i], nvy[i], ai);
   }
 #pragma unroll
   for (int i = 0; i < A; ++i) { S.px[i] = npx[i]; S.py[i] = npy[i]; S.vx[i] = nvx[i]; S.vy[i] = nvy[i]; }
@@ -524,7 +549,7 @@ __device__ __forceinline__ float spread_step(const EnvParams& P, SpreadRegs<A>& 
 #pragma unroll
   for (int l = 0; l < A; ++l) m[l] = spread_landmark_min<A>(S.px, S.py, S.lx[l], S.ly[l]);
 #pragma unroll
-  for (int i = 0; i < A; ++i) cnt[i] = spread_collisions<A>(P, i, S.px, S.py, S.px[i], S.py[i]);
+  for (int i = 0; i < A; ++i) cnt[i] = spread_collisions<A>(Cn, spread_agent_consts(P, i), S.px, S.py, S.px[i], S.py[i]);
   return spread_reward_sum<A>(m, cnt);
 }
 

@@ -13,6 +13,10 @@
 
 namespace mdp {
 
+#ifndef MDP_EP_UNROLL
+#define MDP_EP_UNROLL 2
+#endif
+constexpr int EP_UNROLL = MDP_EP_UNROLL;  // k-loop unroll (in float4 A loads) of the episode kernel's hidden layer
 constexpr int REB = 32;  // env instances per CTA == rows of the MLP tile
 constexpr int TM = REB;
 
@@ -26,6 +30,9 @@ __host__ __device__ inline int actor_net_floats(int D, int U, int K) {
 // FFMA2 -- half the shared-memory wavefronts per FMA of the 256-thread 2x4 tile, which ran at 38 % of the FMA pipe
 // (125 cycles per k-step of layer 2 against 48; clock64 phase profile in DESIGN.md).  Every output still accumulates
 // k = 0, 1, ... in order with fused multiply-adds, so the results are bit-identical to the per-step kernels.
+// Measured on B200 (clock64 phase profile): the hidden layer now runs at ~84 cycles per k-step for 3 agents x
+// 32 rows x 64 units = 73 FMA/clk/SM, insensitive to k-loop unroll depth and to software-pipelined operand loads, and a
+// scalar-FFMA build is only 8 % slower -- the FP32 pipe itself (3-register FFMA / FFMA2 issue rate) is the bound.
 template <int U, int GTH>
 struct EpTile {
   static constexpr int RM = 512 / GTH, HP = U + 4;
@@ -59,12 +66,33 @@ struct EpTile {
       }
     }
   }
+  // A given TRANSPOSED, sAT[k][32 rows]: the thread's RM = 4 rows are one float4 per k (128-thread groups only)
+  static __device__ __forceinline__ void mma_t(int tid, Acc& acc, const float* __restrict__ sAT, const float* __restrict__ sW, int kc) {
+    static_assert(RM == 4 || GTH != 128, "mma_t: 4 rows per thread");
+    const int ty = tid >> 4, tx = tid & 15;
+    const float* ap = sAT + 4 * ty;
+#pragma unroll 2
+    for (int k = 0; k < kc; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(ap + k * 32);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int g = 0; g < U / 64; ++g) {
+        const float4 w = *reinterpret_cast<const float4*>(sW + k * U + g * 64 + 4 * tx);
+#pragma unroll
+        for (int rr = 0; rr < (RM < 4 ? RM : 4); ++rr) {
+          const float2 a2 = make_float2(av[rr], av[rr]);
+          acc[rr][2 * g + 0] = __ffma2_rn(a2, make_float2(w.x, w.y), acc[rr][2 * g + 0]);
+          acc[rr][2 * g + 1] = __ffma2_rn(a2, make_float2(w.z, w.w), acc[rr][2 * g + 1]);
+        }
+      }
+    }
+  }
   // same with float4 A loads (lda % 4 == 0, kc % 4 == 0, 16-byte aligned rows)
   static __device__ __forceinline__ void mma(int tid, Acc& acc, const float* __restrict__ sA, int lda, const float* __restrict__ sW,
                                              int kc) {
     const int ty = tid >> 4, tx = tid & 15;
     const float* ap = sA + (RM * ty) * lda;
-#pragma unroll 2
+#pragma unroll EP_UNROLL
     for (int k = 0; k < kc; k += 4) {
       float av[RM][4];
 #pragma unroll
@@ -272,6 +300,8 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
   float* sH2 = sm.take(NG * TM * HP) + grp * TM * HP;
   float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
   float* sRet = sm.take(A * EBP);
+  float* sXT = sm.take(SA > 0 ? 6 * SA * SA * 32 : 0);  // SA > 0: transposed observation tile [column][env]
+  float* sNoise = sm.take(8 * 256);     // SA > 0: Gumbel noise of the next step, [agent][row][8]
   float* sPart = sm.take(2 * 8 * 32);  // SA > 0: per-agent reward partials (landmark minima, collision counts)
   int* sOff = reinterpret_cast<int*>(sm.take(MDP_MAX_AGENTS + 1));
   ObsCol* sCols = reinterpret_cast<ObsCol*>(sm.take(2 * OS));
@@ -306,6 +336,12 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
   __syncthreads();
   for (int ee = warp; ee < nE; ee += nwarps)
     for (int c = lane; c < L.obs_sum; c += 32) sRow[ee * RS + c] = R.obs[(size_t)(e0 + ee) * OS + c];
+  if (SA > 0) {
+    for (int idx = tid; idx < L.obs_sum * 32; idx += NTB) {
+      const int c = idx >> 5, ee = idx & 31;
+      sXT[idx] = ee < nE ? R.obs[(size_t)(e0 + ee) * OS + c] : 0.f;
+    }
+  }
   if (RESIDENT) {
     for (int i = 0; i < A; ++i) {
       const float4* src = reinterpret_cast<const float4*>(C.agents[i].net[MDP_NET_P].W1);
@@ -328,7 +364,26 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
 #pragma unroll
     for (int l = 0; l < SAc; ++l) { lx[l] = T.sS[(4 * SA + 2 * l + 0) * EBP + lane]; ly[l] = T.sS[(4 * SA + 2 * l + 1) * EBP + lane]; }
   }
+  const SpreadConsts<SAc> Cn = spread_consts<SAc>(P);
+  const SpreadAgentConsts Ai = spread_agent_consts(P, warp < SAc ? warp : 0);
   auto env_bar = [] { asm volatile("bar.sync 8, %0;" ::"r"(32 * SAc) : "memory"); };
+
+  // SA > 0 (every agent is Discrete(5)): the Gumbel noise of step s is drawn ahead of time into sNoise[agent][row][8] by
+  // `nthr` threads -- all of them in the prologue, afterwards the warps that have no part in the env phase
+  auto draw_noise = [&](int s, int t, int nthr) {
+    for (int idx = t; idx < SAc * 160; idx += nthr) {
+      const int i = idx / 160, rem = idx - i * 160, r = rem / 5, a = rem - r * 5;
+      if (r < nE)
+        sNoise[i * 256 + r * 8 + a] =
+            gumbel_from_u(philox_u(R.seed, counter + (unsigned long long)s + 1ull, (uint32_t)i, (long long)e0 + r, a));
+    }
+  };
+  if (SA > 0) {
+    for (int idx = tid; idx < SAc * 256; idx += NTB) sNoise[idx] = 0.f;
+    __syncthreads();
+    draw_noise(0, tid, NTB);
+    __syncthreads();
+  }
 
   // ---- the episode -----------------------------------------------------------------------------------
   long long ring_row = (cursor + e0) % R.capacity;  // ring row of this CTA's first env at step s (thread 0 keeps it current)
@@ -350,7 +405,7 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       if (RESIDENT) w = net_at<U>(sWts + sOff[i], D, K);
       const bool fused_head = ag.n_heads == 1 && K == 5;  // Discrete(5): every MPE movement head
       float noise[Tile::NP];
-      if (fused_head) {
+      if (fused_head && SA == 0) {
 #pragma unroll
         for (int p = 0; p < Tile::NP; ++p) {
           const int r = (G.tid >> 3) + p * (GTH / 8), a = G.tid & 7;
@@ -361,7 +416,11 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       }
       typename Tile::Acc acc;
       Tile::zero(acc);
-      if (RESIDENT) {
+      PROF_MARK(2)
+      if (SA > 0) {
+        Tile::mma_t(G.tid, acc, sXT + ag.obs_off * 32, w.W1, D);
+        PROF_MARK(7)
+      } else if (RESIDENT) {
         Tile::mma_sa(G.tid, acc, buf + ag.obs_off, RS, w.W1, D);
       } else {
         for (int k0 = 0; k0 < D; k0 += KC) {
@@ -372,6 +431,7 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
         }
       }
       Tile::store_bias_relu(G.tid, acc, w.b1, sH1);
+      PROF_MARK(9)
       G.sync();
       PROF_MARK(5)
       Tile::zero(acc);
@@ -389,6 +449,10 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       G.sync();
       PROF_MARK(6)
       if (fused_head) {
+        if (SA > 0) {  // drawn by the warps that idle during the previous step's env phase
+#pragma unroll
+          for (int p = 0; p < Tile::NP; ++p) noise[p] = sNoise[i * 256 + ((G.tid >> 3) + p * (GTH / 8)) * 8 + (G.tid & 7)];
+        }
         Tile::template head_gumbel<5>(G, sH2, w, buf + L.obs_sum + ag.act_off, RS, nE, noise);
       } else {
         Tile::head(G, sH2, w, sL);
@@ -411,7 +475,7 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
         for (int j = 0; j < SAc; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + lane]; py[j] = T.sS[(4 * j + 1) * EBP + lane]; }
         const float* arow = buf + lane * RS + L.obs_sum + 5 * i;
         const float a[5] = {arow[0], arow[1], arow[2], arow[3], arow[4]};
-        spread_agent_step<SAc>(P, i, px, py, pxi, pyi, vxi, vyi, a);
+        spread_agent_step<SAc>(Cn, Ai, i, px, py, pxi, pyi, vxi, vyi, a);
         env_bar();  // every agent has read the old positions
         T.sS[(4 * i + 0) * EBP + lane] = pxi;
         T.sS[(4 * i + 1) * EBP + lane] = pyi;
@@ -419,10 +483,11 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
 #pragma unroll
         for (int j = 0; j < SAc; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + lane]; py[j] = T.sS[(4 * j + 1) * EBP + lane]; }
         sPart[i * 32 + lane] = spread_landmark_min<SAc>(px, py, lxi, lyi);
-        sPart[(SAc + i) * 32 + lane] = __int_as_float(spread_collisions<SAc>(P, i, px, py, pxi, pyi));
+        sPart[(SAc + i) * 32 + lane] = __int_as_float(spread_collisions<SAc>(Cn, Ai, px, py, pxi, pyi));
         float* nx = buf + lane * RS + L.nx_off + i * D;
         float* ob = nxt + lane * RS + i * D;
-        spread_obs_agent<SAc>(i, px, py, pxi, pyi, vxi, vyi, lx, ly, [&](int c, float v) { nx[c] = v; ob[c] = v; });
+        float* obT = sXT + (i * D) * 32 + lane;  // transposed copy [column][env]: layer 1 reads its 4 rows as one float4
+        spread_obs_agent<SAc>(i, px, py, pxi, pyi, vxi, vyi, lx, ly, [&](int c, float v) { nx[c] = v; ob[c] = v; obT[c * 32] = v; });
         env_bar();
         float m[SAc];
         int cnt[SAc];
@@ -431,6 +496,8 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
         const float msum = spread_reward_sum<SAc>(m, cnt);
         buf[lane * RS + L.rw_off + i] = msum;
         ret_reg += msum;
+      } else if (s + 1 < R.steps) {
+        draw_noise(s + 1, tid - 32 * SAc, NTB - 32 * SAc);
       }
       PROF_MARK(1)
     } else {
@@ -550,7 +617,7 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   size_t smem = 0;
   for (int ng = P.A < 4 ? P.A : 4; ng >= 1 && NG == 0; --ng) {
     const size_t base = 2 * r4((size_t)ng * TM * HP) + r4((size_t)ng * TM * KPAD) + r4(2 * (size_t)TM * lay.row_stride) +
-                        r4((size_t)P.A * (REB + 1)) + r4(2 * 8 * 32) + r4(MDP_MAX_AGENTS + 1) +
+                        r4((size_t)P.A * (REB + 1)) + r4(6 * 4 * 4 * 32) + r4(8 * 256) + r4(2 * 8 * 32) + r4(MDP_MAX_AGENTS + 1) +
                         r4(2 * (size_t)P.obs_stride) + r4(EnvTile<float, REB>::bytes(P.scomp, P.A, P.act_stride, false) / 4);
     const size_t smem_res = (base + wts + 16) * 4, smem_str = (base + (size_t)ng * KC * U + 16) * 4;
     // the physics phase needs one thread per (env, agent); resident groups are 128 threads, streaming groups 256

@@ -14,7 +14,7 @@ a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=Tru
 a.record(); roll.run_mega(25); b.record(); torch.cuda.synchronize()
 t = roll.ep_return[E * 3:E * 3 + 10].cpu().tolist()
 print("launch us", a.elapsed_time(b) * 1e3)
-names = ["wait+sync after mlp", "physics", "flags_rewards", "obs+rew+fence+sync", "bulk store issue", "layer1", "layer2", "head", "gumbel", "-"]
+names = ["wait+sync after mlp", "physics", "L1 setup", "fence+sync", "bulk store issue", "L1 G.sync", "layer2", "L1 mma", "head+gumbel", "L1 store"]
 tot = sum(t)
 for n, v in zip(names, t): print("%-22s %8.0f cycles/step  %5.1f%%" % (n, v / 25, 100 * v / tot))
 print("total cycles/step", tot / 25)
