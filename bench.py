@@ -510,13 +510,18 @@ def main():
     ep_bytes = row_bytes * E * EP_LEN           # the replay rows are the only HBM traffic the algorithm needs
     ep_us = roll_ms * 1e3 / max(1, n_eps)
     actor_flops = 2 * sum(d * UNITS + UNITS * UNITS + UNITS * k for d, k in zip(env.obs_dims, env.act_dims)) * E * EP_LEN
-    ep_roof = {"kernel": "k_rollout_episode<64,true>" if roll.mode == "mega" else "per-step kernels", "bound": "hbm",
+    sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+    fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e-6  # 128 FP32 lanes per SM
+    ep_roof = {"kernel": "k_rollout_episode<64,true,3>" if roll.mode == "mega" else "per-step kernels", "bound": "hbm",
                "achieved": ep_bytes / ep_us / 1e3, "peak": peak, "unit": "GB/s", "frac": ep_bytes / ep_us / 1e3 / peak,
-               "traffic": 5.49e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_raw.txt (dram read 1.37 MB + write 4.12 MB per "
+               "traffic": 4.62e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_v3.txt (dram read 1.36 MB + write 3.26 MB per "
                "launch; the 52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
                "algorithmic_bytes_per_launch": ep_bytes, "avg_launch_us": ep_us,
-               "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the kernel is "
-                       "FP32-FMA-issue / latency bound", "fp32_fma_tflops": actor_flops / ep_us / 1e6}
+               "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the actor "
+                       "layers run at the FP32 pipe's register-operand issue rate (clock64 phase profile in DESIGN.md), the "
+                       "rest of a step is dependent-latency chains (head + Gumbel-softmax, physics)",
+               "fp32_fma_tflops": actor_flops / ep_us / 1e6, "fp32_peak_tflops": fp32_peak_tflops,
+               "fp32_frac": actor_flops / ep_us / 1e6 / fp32_peak_tflops}
     if rank == 0:
         flops_round = sum(int(core.layout.update_flops_critic[j]) + int(core.layout.update_flops_actor[j]) for j in range(A)) * BATCH
         line = {
@@ -530,8 +535,12 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Kh, "ms_per_step": 1e3 * e2e_s / Kh,
-                    "api": "maddpg_b200.rollout.HostRollout.step -> C ABI mdp_host_step: train.py:112-120 (action, env.step, "
-                           "experience for all agents) per call with page-locked host numpy buffers; env.reset every 25 steps",
+                    "api": "maddpg_b200.rollout.HostRollout.step -> C ABI mdp_host_step_pipelined: train.py:112-120 (action, "
+                           "env.step, experience for all agents) per call with page-locked host numpy buffers; env.reset every "
+                           "25 steps; %d ranges of env instances on forked streams, host buffers moved by %s, the whole call "
+                           "replayed as one CUDA graph per result slot (%d kernels per step)"
+                           % (host.chunks, "copy kernels (SMs over the unified address space)" if host.copy_kernels
+                              else "the copy engines", host.launches_per_graph),
                     "per_call_api": {"value": percall_value, "unit": UNIT, "steps": Ke, "ms_per_step": 1e3 * percall_s / Ke,
                                      "h2d_bytes_per_step": percall_h2d, "d2h_bytes_per_step": percall_d2h,
                                      "api": "MADDPGAgentTrainer.action / BatchedMultiAgentEnv.step / .experience, one call per "

@@ -285,6 +285,18 @@ int mdp_host_step_layout(const mdp_env* env, int32_t E, int64_t* offs4, int64_t*
 int mdp_host_step(mdp_env* env, mdp_core* core, int32_t E, void* state, const float* h_obs_in, float* d_obs_in,
                   void* d_out, void* h_out, float* ring, int64_t ring_capacity, int32_t ring_row_stride,
                   int64_t ring_cursor, uint64_t seed, uint64_t counter, void* stream);
+/* Same call with the E env instances split into n_chunks equal ranges (E % n_chunks == 0, n_chunks <= 8), each on a
+ * library-owned stream forked from / joined to `stream`: the host->device copy of range c+1 and the device->host copy
+ * of range c-1 overlap the kernels of range c.  Same results bit for bit (the Philox streams are keyed by the env
+ * index).  Capturable into a CUDA graph after one uncaptured call (which creates the streams and events). */
+int mdp_host_step_pipelined(mdp_env* env, mdp_core* core, int32_t E, int32_t n_chunks, void* state, const float* h_obs_in,
+                            float* d_obs_in, void* d_out, void* h_out, float* ring, int64_t ring_capacity,
+                            int32_t ring_row_stride, int64_t ring_cursor, uint64_t seed, uint64_t counter, void* stream);
+
+/* How mdp_host_step moves its two buffers: mode 0 = the copy engines (cudaMemcpyAsync), mode 1 = copy kernels (the SMs
+ * read / write the page-locked host buffers through the unified address space; falls back to mode 0 when a buffer is
+ * not device-accessible).  Same bytes either way; mode 1 avoids the copy engines' fixed per-transfer latency. */
+int mdp_host_copy_mode(mdp_env* env, int32_t mode);
 
 /* ------------------------------------------------------------------------------------------ */
 /* device control block: lets a captured CUDA graph advance its own counters                    */

@@ -81,6 +81,14 @@ struct Philox {
 };
 
 // mdp_replay_insert with an optional device control block (see mdp_env_set_ctl)
+int env_step_range(mdp_env* env, int32_t E, int32_t e_base, int32_t n, void* state, const float* act, float* obs_out,
+                   float* rew_out, uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
+                   int32_t ring_row_stride, int64_t ring_cursor, void* stream);
+// mdp_actor_act for rows [row_base, row_base + E) of a larger population (obs / act point at row row_base): the Philox
+// streams are keyed by the population row, so a chunked launch draws the same numbers as one launch over all rows
+int actor_act_range(mdp_core* c, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E, const float* obs,
+                    int32_t obs_stride, float* act, int32_t act_stride, const float* u, uint64_t seed, uint64_t counter,
+                    float* logits_out, int64_t row_base, void* stream);
 int replay_insert_ctl(const mdp_ring_layout* lay, float* ring, int64_t capacity, int64_t cursor, int32_t E, int32_t agent,
                       const float* obs, int32_t obs_stride, const float* act, int32_t act_stride, const float* rew,
                       int32_t rew_stride, const float* next_obs, int32_t next_obs_stride, const uint8_t* done,

@@ -22,7 +22,7 @@ namespace mdp {
 // One CTA = EB env instances.  Threads [0, EB*A) run the physics (one per (env, agent)); ALL threads
 // (at least 256) take part in the load / store phases.
 template <typename real, int EB, bool DO_STEP>
-__global__ void __launch_bounds__(1024) k_env_step(EnvParams P, int E, real* __restrict__ state,
+__global__ void __launch_bounds__(1024) k_env_step(EnvParams P, int E, int ES, real* __restrict__ state,
                                                    const float* __restrict__ act, const ObsCol* __restrict__ cols,
                                                    float* __restrict__ obs_out, float* __restrict__ rew_out,
                                                    uint8_t* __restrict__ done_out) {
@@ -33,14 +33,15 @@ __global__ void __launch_bounds__(1024) k_env_step(EnvParams P, int E, real* __r
   const int e0 = blockIdx.x * EB;
   const int nE = min(EB, E - e0);
 
-  env_load_state<real, EB>(P, T, state, E, e0, nE);
+  // E = env instances of this launch, ES = stride of the SoA state arrays (the whole population; a launch may cover a range)
+  env_load_state<real, EB>(P, T, state, ES, e0, nE);
   if (DO_STEP) env_load_actions<real, EB>(P, T, act, e0, nE);
   __syncthreads();
   if (DO_STEP) env_physics<real, EB>(P, T, nE);
   env_flags_rewards<real, EB, DO_STEP>(P, T, nE);
 
   if (DO_STEP) {
-    env_store_state<real, EB>(P, T, state, E, e0, nE, false);
+    env_store_state<real, EB>(P, T, state, ES, e0, nE, false);
     for (int idx = tid; idx < nE * P.A; idx += NT) {
       const int ee = idx / P.A, ii = idx - ee * P.A;
       rew_out[(size_t)(e0 + ee) * P.A + ii] = env_reward_out<real, EB>(P, T, ee, ii);
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(1024) k_env_step(EnvParams P, int E, real* __r
 constexpr int SPREAD_EB = 128;
 
 template <int A>
-__global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int E, float* __restrict__ state,
+__global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int E, int ES, float* __restrict__ state,
                                                                const float* __restrict__ act, float* __restrict__ obs_out,
                                                                float* __restrict__ rew_out, uint8_t* __restrict__ done_out) {
   constexpr int L = A, D = 6 * A, OS = (A * D + 3) / 4 * 4, AS = (5 * A + 3) / 4 * 4, OS4 = OS / 4;
@@ -78,15 +79,15 @@ __global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int 
     float a[AS];
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      S.px[i] = state[(size_t)(4 * i + 0) * E + e];
-      S.py[i] = state[(size_t)(4 * i + 1) * E + e];
-      S.vx[i] = state[(size_t)(4 * i + 2) * E + e];
-      S.vy[i] = state[(size_t)(4 * i + 3) * E + e];
+      S.px[i] = state[(size_t)(4 * i + 0) * ES + e];
+      S.py[i] = state[(size_t)(4 * i + 1) * ES + e];
+      S.vx[i] = state[(size_t)(4 * i + 2) * ES + e];
+      S.vy[i] = state[(size_t)(4 * i + 3) * ES + e];
     }
 #pragma unroll
     for (int l = 0; l < L; ++l) {
-      S.lx[l] = state[(size_t)(4 * A + 2 * l + 0) * E + e];
-      S.ly[l] = state[(size_t)(4 * A + 2 * l + 1) * E + e];
+      S.lx[l] = state[(size_t)(4 * A + 2 * l + 0) * ES + e];
+      S.ly[l] = state[(size_t)(4 * A + 2 * l + 1) * ES + e];
     }
     const float4* arow = reinterpret_cast<const float4*>(act + (size_t)e * AS);
 #pragma unroll
@@ -97,10 +98,10 @@ __global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int 
     const float msum = spread_step<A>(P, S, a);
 #pragma unroll
     for (int i = 0; i < A; ++i) {
-      state[(size_t)(4 * i + 0) * E + e] = S.px[i];
-      state[(size_t)(4 * i + 1) * E + e] = S.py[i];
-      state[(size_t)(4 * i + 2) * E + e] = S.vx[i];
-      state[(size_t)(4 * i + 3) * E + e] = S.vy[i];
+      state[(size_t)(4 * i + 0) * ES + e] = S.px[i];
+      state[(size_t)(4 * i + 1) * ES + e] = S.py[i];
+      state[(size_t)(4 * i + 2) * ES + e] = S.vx[i];
+      state[(size_t)(4 * i + 3) * ES + e] = S.vy[i];
     }
 #pragma unroll
     for (int i = 0; i < A; ++i) rew_out[(size_t)e * A + i] = msum;
@@ -278,7 +279,7 @@ int env_ensure_cols(mdp_env* env) {
 }
 
 template <typename real, int EB, bool DO_STEP>
-static int launch_step_eb(mdp_env* env, int E, void* state, const float* act, float* obs, float* rew, uint8_t* done,
+static int launch_step_eb(mdp_env* env, int E, int ES, void* state, const float* act, float* obs, float* rew, uint8_t* done,
                           cudaStream_t st) {
   const EnvParams& P = env->P;
   int NT = round_up(EB * P.A, 32);
@@ -286,36 +287,37 @@ static int launch_step_eb(mdp_env* env, int E, void* state, const float* act, fl
   const size_t smem = EnvTile<real, EB>::bytes(P.scomp, P.A, P.act_stride, true);
   auto kern = k_env_step<real, EB, DO_STEP>;
   if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<cdiv(E, EB), NT, smem, st>>>(P, E, (real*)state, act, env->d_cols, obs, rew, done);
+  kern<<<cdiv(E, EB), NT, smem, st>>>(P, E, ES, (real*)state, act, env->d_cols, obs, rew, done);
   return check_launch("k_env_step");
 }
 
 // threads per CTA >= EB * A with agent-uniform warps (EB % 32 == 0)
 template <int A>
-static int launch_spread(mdp_env* env, int E, float* state, const float* act, float* obs, float* rew, uint8_t* done, cudaStream_t st) {
+static int launch_spread(mdp_env* env, int E, int ES, float* state, const float* act, float* obs, float* rew, uint8_t* done,
+                         cudaStream_t st) {
   const size_t smem = (size_t)SPREAD_EB * ((env->P.obs_stride / 4) | 1) * 16;
   auto kern = k_env_step_spread<A>;
   if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<cdiv(E, SPREAD_EB), SPREAD_EB, smem, st>>>(env->P, E, state, act, obs, rew, done);
+  kern<<<cdiv(E, SPREAD_EB), SPREAD_EB, smem, st>>>(env->P, E, ES, state, act, obs, rew, done);
   return check_launch("k_env_step_spread");
 }
 
 template <typename real, bool DO_STEP>
-static int launch_step(mdp_env* env, int E, void* state, const float* act, float* obs, float* rew, uint8_t* done,
+static int launch_step(mdp_env* env, int E, int ES, void* state, const float* act, float* obs, float* rew, uint8_t* done,
                        cudaStream_t st) {
   if (DO_STEP && sizeof(real) == 4 && env->P.scenario == MDP_SIMPLE_SPREAD && !env->force_generic) {
     switch (env->P.A) {
-      case 2: return launch_spread<2>(env, E, (float*)state, act, obs, rew, done, st);
-      case 3: return launch_spread<3>(env, E, (float*)state, act, obs, rew, done, st);
-      case 4: return launch_spread<4>(env, E, (float*)state, act, obs, rew, done, st);
-      case 5: return launch_spread<5>(env, E, (float*)state, act, obs, rew, done, st);
-      case 6: return launch_spread<6>(env, E, (float*)state, act, obs, rew, done, st);
+      case 2: return launch_spread<2>(env, E, ES, (float*)state, act, obs, rew, done, st);
+      case 3: return launch_spread<3>(env, E, ES, (float*)state, act, obs, rew, done, st);
+      case 4: return launch_spread<4>(env, E, ES, (float*)state, act, obs, rew, done, st);
+      case 5: return launch_spread<5>(env, E, ES, (float*)state, act, obs, rew, done, st);
+      case 6: return launch_spread<6>(env, E, ES, (float*)state, act, obs, rew, done, st);
       default: break;
     }
   }
-  if (env->P.A == 1) return launch_step_eb<real, 128, DO_STEP>(env, E, state, act, obs, rew, done, st);
-  if (env->P.A == 2) return launch_step_eb<real, 64, DO_STEP>(env, E, state, act, obs, rew, done, st);
-  return launch_step_eb<real, 32, DO_STEP>(env, E, state, act, obs, rew, done, st);
+  if (env->P.A == 1) return launch_step_eb<real, 128, DO_STEP>(env, E, ES, state, act, obs, rew, done, st);
+  if (env->P.A == 2) return launch_step_eb<real, 64, DO_STEP>(env, E, ES, state, act, obs, rew, done, st);
+  return launch_step_eb<real, 32, DO_STEP>(env, E, ES, state, act, obs, rew, done, st);
 }
 
 }  // namespace mdp
@@ -342,6 +344,13 @@ extern "C" int mdp_env_get_dims(const mdp_env* env, mdp_env_dims* out) {
 extern "C" void mdp_env_destroy(mdp_env* env) {
   if (!env) return;
   if (env->d_cols) cudaFree(env->d_cols);
+  if (env->pipeline_ready) {
+    for (int i = 0; i < mdp_env::kMaxChunks; ++i) {
+      cudaStreamDestroy(env->chunk_stream[i]);
+      cudaEventDestroy(env->chunk_done[i]);
+    }
+    cudaEventDestroy(env->fork_ev);
+  }
   delete env;
 }
 
@@ -377,32 +386,47 @@ extern "C" int mdp_env_reset(mdp_env* env, int32_t E, void* state, const void* i
     rc = check_launch("k_env_reset");
     if (rc) return rc;
   }
-  if (env->cfg.state_f64) return launch_step<double, false>(env, E, state, nullptr, obs_out, nullptr, nullptr, st);
-  return launch_step<float, false>(env, E, state, nullptr, obs_out, nullptr, nullptr, st);
+  if (env->cfg.state_f64) return launch_step<double, false>(env, E, E, state, nullptr, obs_out, nullptr, nullptr, st);
+  return launch_step<float, false>(env, E, E, state, nullptr, obs_out, nullptr, nullptr, st);
+}
+
+// env instances [e_base, e_base + n) of a population of E (SoA state stride E): the pointers are those of the whole
+// population.  Chunks of one step may run on different streams (mdp_host_step pipelines its copies against them).
+int mdp::env_step_range(mdp_env* env, int32_t E, int32_t e_base, int32_t n, void* state, const float* act, float* obs_out,
+                        float* rew_out, uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
+                        int32_t ring_row_stride, int64_t ring_cursor, void* stream) {
+  MDP_REQUIRE(env && state && act && obs_out && rew_out && done_out && E > 0 && e_base >= 0 && n > 0 && e_base + n <= E,
+              "mdp_env_step: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = env_ensure_cols(env);
+  if (rc) return rc;
+  const mdp_env_dims& d = env->dims;
+  act += (size_t)e_base * d.act_stride;
+  obs_out += (size_t)e_base * d.obs_stride;
+  rew_out += (size_t)e_base * d.n_agents;
+  done_out += (size_t)e_base * d.n_agents;
+  if (env->cfg.state_f64)
+    rc = launch_step<double, true>(env, n, E, (double*)state + e_base, act, obs_out, rew_out, done_out, st);
+  else
+    rc = launch_step<float, true>(env, n, E, (float*)state + e_base, act, obs_out, rew_out, done_out, st);
+  if (rc) return rc;
+  if (ring) {
+    MDP_REQUIRE(obs_prev && obs_prev != obs_out, "mdp_env_step: ring insert needs a distinct obs_prev buffer");
+    mdp_ring_layout lay;
+    rc = mdp_ring_make_layout(d.n_agents, d.obs_dim, d.act_dim, &lay);
+    if (rc) return rc;
+    MDP_REQUIRE(lay.row_stride == ring_row_stride, "mdp_env_step: ring_row_stride %d != layout %d", ring_row_stride,
+                lay.row_stride);
+    return mdp::replay_insert_ctl(&lay, ring, ring_capacity, (ring_cursor + e_base) % ring_capacity, n, -1,
+                                  obs_prev + (size_t)e_base * d.obs_stride, d.obs_stride, act, d.act_stride, rew_out, d.n_agents,
+                                  obs_out, d.obs_stride, done_out, d.n_agents, env->ctl, stream);
+  }
+  return MDP_OK;
 }
 
 extern "C" int mdp_env_step(mdp_env* env, int32_t E, void* state, const float* act, float* obs_out, float* rew_out,
                             uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
                             int32_t ring_row_stride, int64_t ring_cursor, void* stream) {
-  MDP_REQUIRE(env && state && act && obs_out && rew_out && done_out && E > 0, "mdp_env_step: bad argument");
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = env_ensure_cols(env);
-  if (rc) return rc;
-  if (env->cfg.state_f64)
-    rc = launch_step<double, true>(env, E, state, act, obs_out, rew_out, done_out, st);
-  else
-    rc = launch_step<float, true>(env, E, state, act, obs_out, rew_out, done_out, st);
-  if (rc) return rc;
-  if (ring) {
-    MDP_REQUIRE(obs_prev && obs_prev != obs_out, "mdp_env_step: ring insert needs a distinct obs_prev buffer");
-    mdp_ring_layout lay;
-    rc = mdp_ring_make_layout(env->dims.n_agents, env->dims.obs_dim, env->dims.act_dim, &lay);
-    if (rc) return rc;
-    MDP_REQUIRE(lay.row_stride == ring_row_stride, "mdp_env_step: ring_row_stride %d != layout %d", ring_row_stride,
-                lay.row_stride);
-    return mdp::replay_insert_ctl(&lay, ring, ring_capacity, ring_cursor, E, -1, obs_prev, env->dims.obs_stride, act,
-                                  env->dims.act_stride, rew_out, env->dims.n_agents, obs_out, env->dims.obs_stride,
-                                  done_out, env->dims.n_agents, env->ctl, stream);
-  }
-  return MDP_OK;
+  return mdp::env_step_range(env, E, 0, E, state, act, obs_out, rew_out, done_out, obs_prev, ring, ring_capacity, ring_row_stride,
+                             ring_cursor, stream);
 }

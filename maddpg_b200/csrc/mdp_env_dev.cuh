@@ -573,6 +573,13 @@ struct mdp_env {
   float reset_lo_lm, reset_hi_lm;
   const unsigned long long* ctl = nullptr;
   int force_generic = 0;  // 1: always the table-driven kernel (tests compare the two)
+  // mdp_host_step pipeline: one stream per chunk of env instances, fork / join events (created on first use)
+  static constexpr int kMaxChunks = 8;
+  cudaStream_t chunk_stream[kMaxChunks] = {};
+  cudaEvent_t chunk_done[kMaxChunks] = {};
+  cudaEvent_t fork_ev = nullptr;
+  int pipeline_ready = 0;
+  int host_copy_mode = 0;  // mdp_host_step: 0 = copy engines (cudaMemcpyAsync), 1 = copy kernels over the unified address space
 };
 
 

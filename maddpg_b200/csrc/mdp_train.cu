@@ -33,7 +33,8 @@ template <int U, int TM, bool RES>
 __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, int use_target, int E,
                                                   const float* __restrict__ obs, int obs_stride, float* __restrict__ act,
                                                   int act_stride, const float* __restrict__ u, uint64_t seed,
-                                                  uint64_t counter, float* __restrict__ logits_out, int max_net) {
+                                                  uint64_t counter, float* __restrict__ logits_out, int max_net,
+                                                  long long rng_row_base) {
   if (C.ctl) counter += C.ctl[0];
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
@@ -53,8 +54,8 @@ __global__ void __launch_bounds__(NT) k_actor_act(CoreDev C, int agent_begin, in
   XSrc xs = make_xsrc(obs + ag.obs_off, obs_stride, ag.obs_dim);
   forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
   actor_head<U, TM>(G, sH2, w, sL);
-  gumbel_softmax_tile<TM>(G, sL, sA, KPAD, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off, row0, seed,
-                          counter, (uint32_t)i);
+  gumbel_softmax_tile<TM>(G, sL, sA, KPAD, nrows, ag.act_dim, ag.n_heads, ag.head_dim, u, act_stride, ag.act_off,
+                          u ? row0 : row0 + rng_row_base, seed, counter, (uint32_t)i);
   for (int idx = threadIdx.x; idx < nrows * ag.act_dim; idx += NT) {
     const int r = idx / ag.act_dim, a = idx - r * ag.act_dim;
     act[(row0 + r) * act_stride + ag.act_off + a] = sA[r * KPAD + a];
@@ -963,6 +964,13 @@ extern "C" int mdp_core_bind(mdp_core* c, float* params, float* grads, float* ad
 extern "C" int mdp_actor_act(mdp_core* c, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
                              const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u,
                              uint64_t seed, uint64_t counter, float* logits_out, void* stream) {
+  return mdp::actor_act_range(c, agent_begin, agent_count, use_target, E, obs, obs_stride, act, act_stride, u, seed, counter,
+                              logits_out, 0, stream);
+}
+
+int mdp::actor_act_range(mdp_core* c, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E, const float* obs,
+                         int32_t obs_stride, float* act, int32_t act_stride, const float* u, uint64_t seed, uint64_t counter,
+                         float* logits_out, int64_t row_base, void* stream) {
   MDP_REQUIRE(c && c->d_agents, "mdp_actor_act: core not bound");
   MDP_REQUIRE(obs && act && E > 0 && agent_count > 0 && agent_begin >= 0 && agent_begin + agent_count <= c->cfg.n_agents,
               "mdp_actor_act: bad argument");
@@ -977,7 +985,7 @@ extern "C" int mdp_actor_act(mdp_core* c, int32_t agent_begin, int32_t agent_cou
     int rc = set_smem(kern, smem);
     if (rc) return rc;
     kern<<<dim3(cdiv(E, TMv), agent_count), NT, smem, st>>>(d, agent_begin, use_target, E, obs, obs_stride, act, act_stride, u,
-                                                          seed, counter, logits_out, p.max_net);
+                                                          seed, counter, logits_out, p.max_net, (long long)row_base);
     return check_launch("k_actor_act");
   });
 }

@@ -1,0 +1,2 @@
+timeout 600 python -m pytest tests/test_host_step_gpu.py -m gpu -x -q 2>&1 | tail -5
+timeout 300 python scratch/e2e_var.py

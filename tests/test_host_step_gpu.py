@@ -21,14 +21,22 @@ def _build(scenario, E, capacity):
     return env, trainers[0].core
 
 
-@pytest.mark.parametrize("scenario,E", [("simple_spread", 300), ("simple_tag", 64), ("simple_world_comm", 33), ("simple", 1)])
-def test_host_step_equals_device_api(scenario, E):
+@pytest.mark.parametrize("scenario,E,chunks,graph,copy_kernels", [
+    ("simple_spread", 300, 1, False, False), ("simple_spread", 300, 1, True, False), ("simple_spread", 300, 4, False, False),
+    ("simple_spread", 300, 4, True, False), ("simple_spread", 300, 1, False, True), ("simple_spread", 300, 4, True, True),
+    ("simple_spread", 2048, None, True, True),
+    ("simple_tag", 64, 2, True, True), ("simple_world_comm", 33, 3, True, False), ("simple", 1, 1, True, True)])
+def test_host_step_equals_device_api(scenario, E, chunks, graph, copy_kernels):
+    """chunks > 1: the pipelined call (ranges of env instances on separate streams); graph: the call replayed as a CUDA
+    graph with device-side counters; copy_kernels: host buffers moved by copy kernels instead of the copy engines.
+    Every variant must reproduce the per-call device API bit for bit."""
     from maddpg_b200.rollout import HostRollout
     cap = 5 * E + 7  # forces a wrap-around inside the test
     env_a, core_a = _build(scenario, E, cap)
     env_b, core_b = _build(scenario, E, cap)
     core_b.params.copy_(core_a.params)
-    host = HostRollout(env_a, core_a)
+    host = HostRollout(env_a, core_a, chunks=chunks, use_graph=graph, copy_kernels=copy_kernels)
+    assert host.chunks == (chunks or 8)
     obs_n = host.reset()
     env_b.reset_device()
     np.testing.assert_array_equal(np.concatenate(obs_n, 1), env_b.obs[:, :sum(env_b.obs_dims)].cpu().numpy())
@@ -48,6 +56,8 @@ def test_host_step_equals_device_api(scenario, E):
             assert done_n[i].dtype == np.bool_ and not done_n[i].any()
         obs_n = new_obs_n
     assert core_a.ring.next_idx == core_b.ring.next_idx and core_a.ring.length == core_b.ring.length
+    assert core_a.counter == core_b.counter
+    assert (host.graph_launches > 0) == graph
     n = core_a.ring.length[0]
     for i in range(env_b.n):  # every field of every agent (the padding columns of a row are never written)
         for name, cols in core_a.ring.cols(i).items():
