@@ -1,0 +1,5 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 > gpurun_out/bench_n8_v3.log 2> gpurun_out/bench_n8_v3_err.log; echo "rc=$?"
+tail -1 gpurun_out/bench_n8_v3.log | python -c "
+import json,sys; d=json.loads(sys.stdin.read())
+print('N', d['n_gpus'], 'value', d['value'], 'e2e', d['e2e']['value'], 'upd', d['critic_updates']['value'])
+"
