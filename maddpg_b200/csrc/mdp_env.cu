@@ -348,7 +348,6 @@ extern "C" void mdp_env_destroy(mdp_env* env) {
     for (int i = 0; i < mdp_env::kMaxChunks; ++i) {
       cudaStreamDestroy(env->chunk_stream[i]);
       cudaEventDestroy(env->chunk_done[i]);
-      cudaEventDestroy(env->upload_done[i]);
     }
     cudaEventDestroy(env->fork_ev);
   }

@@ -577,7 +577,6 @@ struct mdp_env {
   static constexpr int kMaxChunks = 8;
   cudaStream_t chunk_stream[kMaxChunks] = {};
   cudaEvent_t chunk_done[kMaxChunks] = {};
-  cudaEvent_t upload_done[kMaxChunks] = {};
   cudaEvent_t fork_ev = nullptr;
   int pipeline_ready = 0;
   int host_copy_mode = 0;  // mdp_host_step: 0 = copy engines (cudaMemcpyAsync), 1 = copy kernels over the unified address space

@@ -51,7 +51,6 @@ static int ensure_pipeline(mdp_env* env) {
   for (int i = 0; i < mdp_env::kMaxChunks; ++i) {
     MDP_CUDA(cudaStreamCreateWithFlags(&env->chunk_stream[i], cudaStreamNonBlocking));
     MDP_CUDA(cudaEventCreateWithFlags(&env->chunk_done[i], cudaEventDisableTiming));
-    MDP_CUDA(cudaEventCreateWithFlags(&env->upload_done[i], cudaEventDisableTiming));
   }
   MDP_CUDA(cudaEventCreateWithFlags(&env->fork_ev, cudaEventDisableTiming));
   env->pipeline_ready = 1;
@@ -93,16 +92,12 @@ static int host_step_impl(mdp_env* env, mdp_core* core, int32_t E, int32_t n_chu
     const size_t obs_off = (size_t)e0 * d.obs_stride, obs_bytes = 4ull * n * d.obs_stride;
     if (n_chunks > 1) MDP_CUDA(cudaStreamWaitEvent(cs, env->fork_ev, 0));
     // obs_n (host) -> device: the argument of agent.action(obs), train.py:112
-    // uploads go one after the other (range c+1's waits for range c's): started together they would share the link and all
-    // finish at the end, and no range could start computing early
-    if (n_chunks > 1 && c > 0) MDP_CUDA(cudaStreamWaitEvent(cs, env->upload_done[c - 1], 0));
     if (sm_copies) {
       rc = copy_kernel(d_obs_in + obs_off, h_obs_in + obs_off, obs_bytes, cs);
       if (rc) return rc;
     } else {
       MDP_CUDA(cudaMemcpyAsync(d_obs_in + obs_off, h_obs_in + obs_off, obs_bytes, cudaMemcpyHostToDevice, cs));
     }
-    if (n_chunks > 1) MDP_CUDA(cudaEventRecord(env->upload_done[c], cs));
     // action_n = [agent.action(obs) ...]: grouped actor inference + Gumbel-softmax sampling
     rc = mdp::actor_act_range(core, 0, d.n_agents, 0, n, d_obs_in + obs_off, d.obs_stride, d_act + (size_t)e0 * d.act_stride,
                               d.act_stride, nullptr, seed, counter, nullptr, e0, cs);
