@@ -518,8 +518,8 @@ def main():
                "launch; the 52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
                "algorithmic_bytes_per_launch": ep_bytes, "avg_launch_us": ep_us,
                "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the actor "
-                       "layers run at the FP32 pipe's register-operand issue rate (clock64 phase profile in DESIGN.md), the "
-                       "rest of a step is dependent-latency chains (head + Gumbel-softmax, physics)",
+                       "layers run at 65 % of the FP32 pipe's measured FMA rate (clock64 phase profile in DESIGN.md, "
+                       "tools/fp32_probe.cu), the rest of a step is dependent-latency chains (head + Gumbel-softmax, physics)",
                "fp32_fma_tflops": actor_flops / ep_us / 1e6, "fp32_peak_tflops": fp32_peak_tflops,
                "fp32_frac": actor_flops / ep_us / 1e6 / fp32_peak_tflops}
     if rank == 0:

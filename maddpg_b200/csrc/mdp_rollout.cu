@@ -31,8 +31,8 @@ __host__ __device__ inline int actor_net_floats(int D, int U, int K) {
 // (125 cycles per k-step of layer 2 against 48; clock64 phase profile in DESIGN.md).  Every output still accumulates
 // k = 0, 1, ... in order with fused multiply-adds, so the results are bit-identical to the per-step kernels.
 // Measured on B200 (clock64 phase profile): the hidden layer now runs at ~84 cycles per k-step for 3 agents x
-// 32 rows x 64 units = 73 FMA/clk/SM, insensitive to k-loop unroll depth and to software-pipelined operand loads, and a
-// scalar-FFMA build is only 8 % slower -- the FP32 pipe itself (3-register FFMA / FFMA2 issue rate) is the bound.
+// 32 rows x 64 units = 73 FMA/clk/SM, insensitive to k-loop unroll depth and to software-pipelined operand loads; a pure
+// register-operand FMA stream sustains 113 FMA/clk/SM (tools/fp32_probe.cu), FFMA2 halving the instruction count only.
 template <int U, int GTH>
 struct EpTile {
   static constexpr int RM = 512 / GTH, HP = U + 4;
