@@ -93,6 +93,13 @@ int mdp_env_step(mdp_env* env, int32_t E, void* state, const float* act, float* 
  * state; on = 1 forces the table-driven kernel that serves every scenario (tests compare the two). */
 int mdp_env_force_generic(mdp_env* env, int32_t on);
 
+/* Scenario.benchmark_data(agent, world) for every (env instance, agent): the info_n tape of `train.py --benchmark`
+ * (experiments/train.py:139-148, MultiAgentEnv info_callback).  out: DEVICE (E, n_agents, 4) f32 --
+ * simple_spread (reward, collisions, sum of the landmarks' closest-agent distances, occupied landmarks);
+ * simple_tag / simple_world_comm (collisions with good agents, 0, 0, 0) for adversaries and zeros for good agents;
+ * simple: zeros (the scenario defines no benchmark_data). */
+int mdp_env_benchmark(mdp_env* env, int32_t E, const void* state, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* replay ring (maddpg/trainer/replay_buffer.py)                                                */
 /* ------------------------------------------------------------------------------------------ */

@@ -100,6 +100,7 @@ SYMBOLS = {
     "mdp_host_step_pipelined": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32,
                                           C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "mdp_host_copy_mode": (C.c_int, [_P, C.c_int32]),
+    "mdp_env_benchmark": (C.c_int, [_P, C.c_int32, _P, _P, _P]),
     "mdp_env_set_ctl": (C.c_int, [_P, _P]),
     "mdp_core_set_ctl": (C.c_int, [_P, _P]),
     "mdp_ctl_advance": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, _P]),

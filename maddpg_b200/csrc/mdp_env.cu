@@ -127,6 +127,50 @@ __global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int 
   for (int i = tid; i < nE * A; i += SPREAD_EB) dn[i] = 0;
 }
 
+// Scenario.benchmark_data(agent, world) (the info_n tape of `train.py --benchmark`, train.py:139-148) for every (env, agent):
+// four floats.  simple_spread: (reward, collisions, sum over landmarks of the closest agent's distance, occupied landmarks);
+// simple_tag / simple_world_comm: (collisions with good agents, 0, 0, 0) for adversaries, zeros for good agents; simple: zeros.
+template <typename real>
+__global__ void k_env_benchmark(EnvParams P, int E, const real* __restrict__ state, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= E * P.A) return;
+  const int e = idx / P.A, i = idx - e * P.A;
+  auto px = [&](int ent) { return state[(size_t)(ent_comp(P, ent) + 0) * E + e]; };
+  auto py = [&](int ent) { return state[(size_t)(ent_comp(P, ent) + 1) * E + e]; };
+  auto collides = [&](int a, int b) {
+    const real dx = px(a) - px(b), dy = py(a) - py(b);
+    return r_sqrt<real>(dx * dx + dy * dy) < ent_size<real>(P, a) + ent_size<real>(P, b);
+  };
+  float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+  if (P.scenario == MDP_SIMPLE_SPREAD) {
+    real rew = 0, min_dists = 0;
+    int occupied = 0, collisions = 0;
+    for (int l = 0; l < P.L; ++l) {
+      real best = 0;
+      for (int a = 0; a < P.A; ++a) {
+        const real dx = px(a) - px(P.A + l), dy = py(a) - py(P.A + l);
+        const real d = r_sqrt<real>(dx * dx + dy * dy);
+        best = (a == 0 || d < best) ? d : best;
+      }
+      min_dists += best;
+      rew -= best;
+      if (best < (real)0.1) ++occupied;
+    }
+    if ((P.collide_mask >> i) & 1ull)
+      for (int a = 0; a < P.A; ++a)
+        if (collides(a, i)) { rew -= 1; ++collisions; }
+    o0 = (float)rew; o1 = (float)collisions; o2 = (float)min_dists; o3 = (float)occupied;
+  } else if (P.scenario == MDP_SIMPLE_TAG || P.scenario == MDP_SIMPLE_WORLD_COMM) {
+    if (i < P.n_adv) {
+      int collisions = 0;
+      for (int a = P.n_adv; a < P.A; ++a)
+        if (collides(a, i)) ++collisions;
+      o0 = (float)collisions;
+    }
+  }
+  reinterpret_cast<float4*>(out)[idx] = make_float4(o0, o1, o2, o3);
+}
+
 // scenario.reset_world: agents U(-1,1), velocities / comm 0, landmarks U(lo,hi)
 template <typename real>
 __global__ void k_env_reset(EnvParams P, int E, real* __restrict__ state, uint64_t seed, uint64_t episode,
@@ -358,6 +402,17 @@ extern "C" int mdp_env_force_generic(mdp_env* env, int32_t on) {
   MDP_REQUIRE(env, "mdp_env_force_generic: null env");
   env->force_generic = on ? 1 : 0;
   return MDP_OK;
+}
+
+extern "C" int mdp_env_benchmark(mdp_env* env, int32_t E, const void* state, float* out, void* stream) {
+  MDP_REQUIRE(env && state && out && E > 0, "mdp_env_benchmark: bad argument");
+  const int n = E * env->P.A;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (env->cfg.state_f64)
+    k_env_benchmark<double><<<cdiv(n, 256), 256, 0, st>>>(env->P, E, (const double*)state, out);
+  else
+    k_env_benchmark<float><<<cdiv(n, 256), 256, 0, st>>>(env->P, E, (const float*)state, out);
+  return check_launch("k_env_benchmark");
 }
 
 extern "C" int mdp_env_set_ctl(mdp_env* env, const uint64_t* ctl) {

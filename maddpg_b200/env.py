@@ -33,7 +33,7 @@ def _dims_for(scenario, num_agents=None, state_f64=False):
 
 class BatchedMultiAgentEnv(object):
     def __init__(self, scenario, num_envs=1, num_agents=None, device="cuda", state_dtype=torch.float32, seed=0,
-                 squeeze=None):
+                 squeeze=None, benchmark=False):
         if scenario.endswith(".py"):
             scenario = scenario[:-3]
         if scenario not in _lib.SCENARIO_IDS:
@@ -45,6 +45,7 @@ class BatchedMultiAgentEnv(object):
         self.state_dtype = state_dtype
         self.seed = int(seed)
         self.squeeze = (self.num_envs == 1) if squeeze is None else bool(squeeze)
+        self.benchmark = bool(benchmark)  # make_env(..., benchmark=True): step() fills info_n (train.py:56-58)
         self._h, d = _dims_for(scenario, num_agents, state_dtype == torch.float64)
         self.dims = d
         self.n = int(d.n_agents)
@@ -194,7 +195,7 @@ class BatchedMultiAgentEnv(object):
         host_io = self.squeeze or not (isinstance(action_n[0], torch.Tensor) and action_n[0].is_cuda)
         if not host_io:
             obs_n = self._split_obs(self.obs)
-            return obs_n, [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)], {"n": [{}] * self.n}
+            return obs_n, [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)], self._info_n()
         # one packed D2H copy: [obs | rew]; done is identically False in MPE (no done callback)
         self._d_out[:, :self.obs_stride].copy_(self.obs)
         self._d_out[:, self.obs_stride:].copy_(self.rew)
@@ -209,7 +210,31 @@ class BatchedMultiAgentEnv(object):
             obs_n = [host[:, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]
             rew_n = [host[:, self.obs_stride + i].copy() for i in range(self.n)]
             done_n = [np.zeros(self.num_envs, dtype=bool) for _ in range(self.n)]
-        return obs_n, rew_n, done_n, {"n": [{} for _ in range(self.n)]}
+        return obs_n, rew_n, done_n, self._info_n()
+
+    def benchmark_data(self):
+        """``scenario.benchmark_data(agent, world)`` for every (env instance, agent): device (E, n, 4) float32
+        (include/maddpg_b200.h: mdp_env_benchmark)."""
+        out = torch.empty((self.num_envs, self.n, 4), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.mdp_env_benchmark(self._h, self.num_envs, _lib.ptr(self.state), _lib.ptr(out),
+                                              _lib.current_stream()), "mdp_env_benchmark")
+        return out
+
+    def _info_n(self):
+        """info_n of ``MultiAgentEnv.step`` in the reference's shapes: {'n': [benchmark_data(agent_i)]}; a tuple of four per
+        agent for simple_spread, a collision count for simple_tag / simple_world_comm (arrays over env instances
+        unless squeezed)."""
+        if not self.benchmark or self.scenario_name == "simple":
+            return {"n": [{} for _ in range(self.n)]}
+        b = self.benchmark_data().cpu().numpy()
+        if self.scenario_name == "simple_spread":
+            if self.squeeze:
+                return {"n": [(float(b[0, i, 0]), int(b[0, i, 1]), float(b[0, i, 2]), int(b[0, i, 3])) for i in range(self.n)]}
+            return {"n": [(b[:, i, 0].copy(), b[:, i, 1].astype(np.int64), b[:, i, 2].copy(), b[:, i, 3].astype(np.int64))
+                          for i in range(self.n)]}
+        if self.squeeze:
+            return {"n": [int(b[0, i, 0]) for i in range(self.n)]}
+        return {"n": [b[:, i, 0].astype(np.int64) for i in range(self.n)]}
 
     def render(self, mode="human"):
         raise NotImplementedError("rendering is out of scope for the batched device environment")
@@ -220,4 +245,4 @@ def make_env(scenario_name, arglist=None, benchmark=False, **kw):
     if arglist is not None:
         kw.setdefault("num_envs", getattr(arglist, "num_envs", 1))
         kw.setdefault("seed", getattr(arglist, "seed", 0))
-    return BatchedMultiAgentEnv(scenario_name, **kw)
+    return BatchedMultiAgentEnv(scenario_name, benchmark=benchmark, **kw)

@@ -324,6 +324,25 @@ class SimpleSpreadScenario(BaseScenario):
             other_pos.append(other.state.p_pos - agent.state.p_pos)
         return np.concatenate([agent.state.p_vel] + [agent.state.p_pos] + entity_pos + other_pos + comm)
 
+    def benchmark_data(self, agent, world):
+        # upstream simple_spread.benchmark_data: (reward, collisions, sum of min distances, occupied landmarks)
+        rew = 0
+        collisions = 0
+        occupied_landmarks = 0
+        min_dists = 0
+        for l in world.landmarks:
+            dists = [_dist(a, l) for a in world.agents]
+            min_dists += min(dists)
+            rew -= min(dists)
+            if min(dists) < 0.1:
+                occupied_landmarks += 1
+        if agent.collide:
+            for a in world.agents:
+                if _is_collision(a, agent):
+                    rew -= 1
+                    collisions += 1
+        return (rew, collisions, min_dists, occupied_landmarks)
+
 
 class SimpleTagScenario(BaseScenario):
     name = "simple_tag"
@@ -369,6 +388,16 @@ class SimpleTagScenario(BaseScenario):
 
     def adversaries(self, world):
         return [a for a in world.agents if a.adversary]
+
+    def benchmark_data(self, agent, world):
+        # upstream simple_tag / simple_world_comm: adversaries report their collisions with good agents, good agents 0
+        if agent.adversary:
+            collisions = 0
+            for a in self.good_agents(world):
+                if _is_collision(a, agent):
+                    collisions += 1
+            return collisions
+        return 0
 
     def reward(self, agent, world):
         return self.adversary_reward(agent, world) if agent.adversary else self.agent_reward(agent, world)
@@ -473,6 +502,16 @@ class SimpleWorldCommScenario(BaseScenario):
 
     def adversaries(self, world):
         return [a for a in world.agents if a.adversary]
+
+    def benchmark_data(self, agent, world):
+        # upstream simple_tag / simple_world_comm: adversaries report their collisions with good agents, good agents 0
+        if agent.adversary:
+            collisions = 0
+            for a in self.good_agents(world):
+                if _is_collision(a, agent):
+                    collisions += 1
+            return collisions
+        return 0
 
     def reward(self, agent, world):
         return self.adversary_reward(agent, world) if agent.adversary else self.agent_reward(agent, world)

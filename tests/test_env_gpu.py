@@ -190,3 +190,52 @@ def test_spread_register_kernel_matches_table_driven_kernel(A, E):
         torch.testing.assert_close(envs[0].rew, envs[1].rew, rtol=1e-5, atol=1e-5, msg=lambda m: "rew t=%d %s" % (t, m))
         torch.testing.assert_close(envs[0].state, envs[1].state, rtol=1e-5, atol=1e-5, msg=lambda m: "state t=%d %s" % (t, m))
         assert int(envs[0].done.sum()) == 0
+
+
+@pytest.mark.parametrize("name", ["simple", "simple_spread", "simple_tag", "simple_world_comm"])
+def test_benchmark_data_matches_oracle(name):
+    """scenario.benchmark_data (the info_n tape of train.py --benchmark, train.py:139-148) for every (env, agent) after a
+    few crowded steps, float64 state: exact counts, distances to 1e-9."""
+    case = env_case(name, seed=5, crowd=0.3)
+    oenv = case["env"]
+    oenv.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    env = _make(case, torch.float64)
+    env.reset(init_state=env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"]))
+    saw_collision = False
+    for t, acts in enumerate(case["tape"][:6]):
+        oenv.step(acts)
+        env.step_device(_joint_act(env, acts))
+        got = env.benchmark_data().cpu().numpy()
+        assert got.shape == (case["E"], env.n, 4)
+        for e, oe in enumerate(oenv.envs):
+            for i, ag in enumerate(oe.agents):
+                ref = oe.scenario.benchmark_data(ag, oe.world)
+                if name == "simple":
+                    assert ref == {} and not got[e, i].any()
+                elif name == "simple_spread":
+                    np.testing.assert_allclose(got[e, i, [0, 2]], [ref[0], ref[2]], rtol=1e-6, atol=1e-6)
+                    assert int(got[e, i, 1]) == ref[1] and int(got[e, i, 3]) == ref[3]
+                    saw_collision |= ref[1] > 1
+                else:
+                    assert int(got[e, i, 0]) == ref and not got[e, i, 1:].any()
+                    saw_collision |= ref > 0
+    assert saw_collision or name == "simple"
+
+
+def test_benchmark_env_fills_info_n():
+    """make_env(..., benchmark=True) (train.py:56-58): step() returns the reference's info_n shapes."""
+    from maddpg_b200.env import make_env
+    env = make_env("simple_spread", benchmark=True, num_envs=1)
+    obs_n = env.reset()
+    act_n = [np.eye(5, dtype=np.float32)[1] for _ in range(env.n)]
+    obs_n, rew_n, done_n, info_n = env.step(act_n)
+    assert len(info_n["n"]) == env.n
+    rew, collisions, min_dists, occupied = info_n["n"][0]
+    assert isinstance(collisions, int) and collisions >= 1 and isinstance(occupied, int) and min_dists > 0
+    # shared reward = sum over agents of the per-agent benchmark reward (simple_spread is collaborative)
+    np.testing.assert_allclose(sum(x[0] for x in info_n["n"]), rew_n[0], rtol=1e-5)
+    env2 = make_env("simple_tag", benchmark=True, num_envs=4, squeeze=False)
+    env2.reset()
+    _, _, _, info2 = env2.step([np.tile(np.eye(5, dtype=np.float32)[0], (4, 1)) for _ in range(env2.n)])
+    assert all(x.shape == (4,) and x.dtype == np.int64 for x in info2["n"])
+    assert make_env("simple_spread", num_envs=1).step(act_n)[3] == {"n": [{} for _ in range(3)]}
