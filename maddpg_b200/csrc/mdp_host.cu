@@ -30,6 +30,19 @@ __global__ void __launch_bounds__(256) k_copy16(uint4* __restrict__ dst, const u
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
 }
 
+// up to four regions in one launch (a range's next observations, rewards, actions and done flags)
+struct CopyRegions {
+  uint4* dst[4];
+  const uint4* src[4];
+  unsigned n16[4];
+};
+__global__ void __launch_bounds__(256) k_copy16x4(CopyRegions R) {
+  const unsigned stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    for (unsigned i = t; i < R.n16[r]; i += stride) R.dst[r][i] = R.src[r][i];
+}
+
 static int copy_kernel(void* dst, const void* src, size_t bytes, cudaStream_t st) {
   MDP_REQUIRE(bytes % 16 == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)src & 15) == 0, "host copy kernel: 16-byte alignment");
   const size_t n16 = bytes / 16;
@@ -86,6 +99,8 @@ static int host_step_impl(mdp_env* env, mdp_core* core, int32_t E, int32_t n_chu
     MDP_CUDA(cudaEventRecord(env->fork_ev, st));
   }
   const int n = E / n_chunks;
+  // copy kernels move 16-byte words: a range's slices of the small arrays qualify when n * n_agents is a multiple of 16
+  const bool tail_in_chunks = sm_copies && n_chunks > 1 && (n * d.n_agents) % 16 == 0 && (n * d.act_stride) % 4 == 0;
   for (int c = 0; c < n_chunks; ++c) {
     cudaStream_t cs = n_chunks > 1 ? env->chunk_stream[c] : st;
     const int e0 = c * n;
@@ -108,7 +123,22 @@ static int host_step_impl(mdp_env* env, mdp_core* core, int32_t E, int32_t n_chu
     if (rc) return rc;
     if (n_chunks > 1) {
       // the range's next observations go home as soon as they exist; the small arrays follow in one copy after the join
-      if (sm_copies) {
+      if (sm_copies && tail_in_chunks) {
+        // everything the range produced goes home in one launch: next observations, rewards, actions, done flags
+        CopyRegions R;
+        const size_t o4[4] = {4 * obs_off, 4ull * e0 * d.n_agents, 4ull * e0 * d.act_stride, 1ull * e0 * d.n_agents};
+        const size_t b4[4] = {obs_bytes, 4ull * n * d.n_agents, 4ull * n * d.act_stride, 1ull * n * d.n_agents};
+        for (int r = 0; r < 4; ++r) {
+          R.dst[r] = reinterpret_cast<uint4*>(hout + off[r] + o4[r]);
+          R.src[r] = reinterpret_cast<const uint4*>(dout + off[r] + o4[r]);
+          R.n16[r] = (unsigned)(b4[r] / 16);
+        }
+        int grid = (int)((obs_bytes / 16 + 255) / 256);
+        if (grid > 148 * 4) grid = 148 * 4;
+        k_copy16x4<<<grid, 256, 0, cs>>>(R);
+        rc = check_launch("k_copy16x4");
+        if (rc) return rc;
+      } else if (sm_copies) {
         rc = copy_kernel(hout + off[0] + 4 * obs_off, dout + off[0] + 4 * obs_off, obs_bytes, cs);
         if (rc) return rc;
       } else {
@@ -119,6 +149,7 @@ static int host_step_impl(mdp_env* env, mdp_core* core, int32_t E, int32_t n_chu
   }
   if (n_chunks > 1) {
     for (int c = 0; c < n_chunks; ++c) MDP_CUDA(cudaStreamWaitEvent(st, env->chunk_done[c], 0));
+    if (tail_in_chunks) return MDP_OK;
     if (sm_copies) return copy_kernel(hout + off[1], dout + off[1], (size_t)(total - off[1]), st);
     MDP_CUDA(cudaMemcpyAsync(hout + off[1], dout + off[1], (size_t)(total - off[1]), cudaMemcpyDeviceToHost, st));
   } else {
