@@ -184,7 +184,7 @@ class HostRollout(object):
         (include/maddpg_b200.h: mdp_host_step_pipelined; default 8 from 2048 instances up with copy kernels, else 1).
         use_graph: replay the whole call (copies, kernels, counter advance) as one CUDA graph per result slot.
         copy_kernels: move the two host buffers with copy kernels instead of the copy engines (mdp_host_copy_mode).
-        Measured on B200, 4096 instances of simple_spread (scratch/e2e_var.py): engines, eager 104 us/step; engines +
+        Measured on B200, 4096 instances of simple_spread (tools/e2e_var.py): engines, eager 104 us/step; engines +
         graph 94; copy kernels + graph 84; + 8 chunks 72 (copy-engine transfers do NOT pipeline: 4 chunks 108 us;
         serialising the ranges' uploads so that the first range can start early: 83 us, worse)."""
         assert env.obs_dims == core.obs_dims and env.act_dims == core.act_dims
