@@ -171,10 +171,13 @@ struct EpTile {
     G.sync();
   }
   // Single-head actors with KK <= 8 outputs: head + Gumbel-softmax fused, 8 lanes per row, no shared-memory round trip and no
-  // group barrier in between.  noise[p] = -log(-log u) of element (row (tid >> 3) + p * GTH / 8, column tid & 7), drawn by the
+  // group barrier in between.  noise[p] = -log(-log u) of element (row head_row(tid, p), column tid & 7), drawn by the
   // caller BEFORE layer 1 so the Philox / log chains overlap the GEMM loads.  Same arithmetic, in the same order, as
   // head_k + gumbel_softmax below: strided partial sums, xor-shuffle tree, sequential softmax sum.
   static constexpr int NP = TM * 8 / GTH;
+  // head row p of thread tid: the rows a warp takes here are the rows its own layer-2 tile produced (a warp of the GEMM tile
+  // owns ty = 2w, 2w+1, i.e. rows [2*RM*w, 2*RM*(w+1)) ), so layer 1 -> layer 2 -> head hand-offs are warp-local
+  static __device__ __forceinline__ int head_row(int tid, int p) { return 2 * RM * (tid >> 5) + ((tid & 31) >> 3) + 4 * p; }
   template <int KK>
   static __device__ __forceinline__ void head_gumbel(const Grp& G, const float* __restrict__ sH2, const MlpW& w, float* __restrict__ sOut,
                                                      int out_ld, int nrows, const float (&noise)[NP]) {
@@ -189,7 +192,7 @@ struct EpTile {
       const int u = part + 8 * j;
       float h[NP];
 #pragma unroll
-      for (int p = 0; p < NP; ++p) h[p] = sH2[((G.tid >> 3) + p * (GTH / 8)) * HP + u];
+      for (int p = 0; p < NP; ++p) h[p] = sH2[head_row(G.tid, p) * HP + u];
       const float* w3 = w.W3 + u * KK;
 #pragma unroll
       for (int a = 0; a < KK; ++a) {
@@ -200,7 +203,7 @@ struct EpTile {
     }
 #pragma unroll
     for (int p = 0; p < NP; ++p) {
-      const int r = (G.tid >> 3) + p * (GTH / 8);
+      const int r = head_row(G.tid, p);
       float mine = -INFINITY;  // perturbed logit of column `part`
 #pragma unroll
       for (int a = 0; a < KK; ++a) {
@@ -219,7 +222,6 @@ struct EpTile {
       for (int a = 0; a < KK; ++a) sum += __shfl_sync(0xffffffffu, z, lane_base + a);
       if (part < KK && r < nrows) sOut[r * out_ld + part] = z / sum;
     }
-    G.sync();
   }
   // gumbel_softmax_tile (mdp_mlp.cuh) for a GTH-thread group, in-kernel Philox draws only
   static __device__ __forceinline__ void gumbel_softmax(const Grp& G, const float* __restrict__ sL, float* __restrict__ sOut, int out_ld,
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       if (fused_head && SA == 0) {
 #pragma unroll
         for (int p = 0; p < Tile::NP; ++p) {
-          const int r = (G.tid >> 3) + p * (GTH / 8), a = G.tid & 7;
+          const int r = Tile::head_row(G.tid, p), a = G.tid & 7;
           noise[p] = (a < K && r < nE)
                          ? gumbel_from_u(philox_u(R.seed, counter + (unsigned long long)s + 1ull, (uint32_t)i, (long long)e0 + r, a))
                          : 0.f;
@@ -432,7 +434,9 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       }
       Tile::store_bias_relu(G.tid, acc, w.b1, sH1);
       PROF_MARK(9)
-      G.sync();
+      // a warp's layer-2 rows are the rows its own lanes just wrote (thread (ty, tx): rows RM*ty.., ty = tid >> 4): with resident
+      // weights nothing else is shared between the warps of a group, so the hand-offs need a warp barrier only
+      if (RESIDENT) __syncwarp(); else G.sync();
       PROF_MARK(5)
       Tile::zero(acc);
       if (RESIDENT) {
@@ -446,14 +450,15 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
         }
       }
       Tile::store_bias_relu(G.tid, acc, w.b2, sH2);
-      G.sync();
+      if (RESIDENT && fused_head) __syncwarp(); else G.sync();
       PROF_MARK(6)
       if (fused_head) {
         if (SA > 0) {  // drawn by the warps that idle during the previous step's env phase
 #pragma unroll
-          for (int p = 0; p < Tile::NP; ++p) noise[p] = sNoise[i * 256 + ((G.tid >> 3) + p * (GTH / 8)) * 8 + (G.tid & 7)];
+          for (int p = 0; p < Tile::NP; ++p) noise[p] = sNoise[i * 256 + Tile::head_row(G.tid, p) * 8 + (G.tid & 7)];
         }
         Tile::template head_gumbel<5>(G, sH2, w, buf + L.obs_sum + ag.act_off, RS, nE, noise);
+        if (!RESIDENT) G.sync();  // streaming groups reuse their weight staging chunk for the next agent
       } else {
         Tile::head(G, sH2, w, sL);
         PROF_MARK(7)
