@@ -366,9 +366,20 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
 #pragma unroll
     for (int l = 0; l < SAc; ++l) { lx[l] = T.sS[(4 * SA + 2 * l + 0) * EBP + lane]; ly[l] = T.sS[(4 * SA + 2 * l + 1) * EBP + lane]; }
   }
+  // The rewards run on a second set of warps (RW0 + i, the first warps of the next actor group) next to the observation
+  // writes of the physics warps: barrier 8 = physics warps only, barrier 9 = both sets ("new positions are in the state
+  // tile"), barrier 10 = reward warps only.
+  constexpr int RW0 = 4;
+  const bool phys_warp = SA > 0 && warp < SA, rew_warp = SA > 0 && warp >= RW0 && warp < RW0 + SA;
+  if (rew_warp) {
+    lxi = T.sS[(4 * SA + 2 * (warp - RW0) + 0) * EBP + lane];
+    lyi = T.sS[(4 * SA + 2 * (warp - RW0) + 1) * EBP + lane];
+  }
   const SpreadConsts<SAc> Cn = spread_consts<SAc>(P);
-  const SpreadAgentConsts Ai = spread_agent_consts(P, warp < SAc ? warp : 0);
+  const SpreadAgentConsts Ai = spread_agent_consts(P, phys_warp ? warp : rew_warp ? warp - RW0 : 0);
   auto env_bar = [] { asm volatile("bar.sync 8, %0;" ::"r"(32 * SAc) : "memory"); };
+  auto pos_bar = [] { asm volatile("bar.sync 9, %0;" ::"r"(64 * SAc) : "memory"); };
+  auto rew_bar = [] { asm volatile("bar.sync 10, %0;" ::"r"(32 * SAc) : "memory"); };
 
   // SA > 0 (every agent is Discrete(5)): the Gumbel noise of step s is drawn ahead of time into sNoise[agent][row][8] by
   // `nthr` threads -- all of them in the prologue, afterwards the warps that have no part in the env phase
@@ -473,7 +484,7 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
     PROF_MARK(0)
     if (SA > 0) {
       // (3)+(4) in registers: World.step, shared reward and observation of agent `warp` of env instance `lane`
-      if (warp < SA) {
+      if (phys_warp) {
         const int i = warp, D = 6 * SAc;
         float px[SAc], py[SAc];
 #pragma unroll
@@ -484,25 +495,34 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
         env_bar();  // every agent has read the old positions
         T.sS[(4 * i + 0) * EBP + lane] = pxi;
         T.sS[(4 * i + 1) * EBP + lane] = pyi;
-        env_bar();
+        pos_bar();  // new positions of all agents are in the state tile
 #pragma unroll
         for (int j = 0; j < SAc; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + lane]; py[j] = T.sS[(4 * j + 1) * EBP + lane]; }
-        sPart[i * 32 + lane] = spread_landmark_min<SAc>(px, py, lxi, lyi);
-        sPart[(SAc + i) * 32 + lane] = __int_as_float(spread_collisions<SAc>(Cn, Ai, px, py, pxi, pyi));
         float* nx = buf + lane * RS + L.nx_off + i * D;
         float* ob = nxt + lane * RS + i * D;
         float* obT = sXT + (i * D) * 32 + lane;  // transposed copy [column][env]: layer 1 reads its 4 rows as one float4
         spread_obs_agent<SAc>(i, px, py, pxi, pyi, vxi, vyi, lx, ly, [&](int c, float v) { nx[c] = v; ob[c] = v; obT[c * 32] = v; });
-        env_bar();
-        float m[SAc];
-        int cnt[SAc];
+      } else {
+        if (s + 1 < R.steps) draw_noise(s + 1, tid - 32 * SAc, NTB - 32 * SAc);
+        if (rew_warp) {
+          // Scenario.reward of agent i (shared: every agent receives the sum) from the new positions
+          const int i = warp - RW0;
+          pos_bar();
+          float px[SAc], py[SAc];
 #pragma unroll
-        for (int j = 0; j < SAc; ++j) { m[j] = sPart[j * 32 + lane]; cnt[j] = __float_as_int(sPart[(SAc + j) * 32 + lane]); }
-        const float msum = spread_reward_sum<SAc>(m, cnt);
-        buf[lane * RS + L.rw_off + i] = msum;
-        ret_reg += msum;
-      } else if (s + 1 < R.steps) {
-        draw_noise(s + 1, tid - 32 * SAc, NTB - 32 * SAc);
+          for (int j = 0; j < SAc; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + lane]; py[j] = T.sS[(4 * j + 1) * EBP + lane]; }
+          const float pxn = T.sS[(4 * i + 0) * EBP + lane], pyn = T.sS[(4 * i + 1) * EBP + lane];
+          sPart[i * 32 + lane] = spread_landmark_min<SAc>(px, py, lxi, lyi);
+          sPart[(SAc + i) * 32 + lane] = __int_as_float(spread_collisions<SAc>(Cn, Ai, px, py, pxn, pyn));
+          rew_bar();
+          float m[SAc];
+          int cnt[SAc];
+#pragma unroll
+          for (int j = 0; j < SAc; ++j) { m[j] = sPart[j * 32 + lane]; cnt[j] = __float_as_int(sPart[(SAc + j) * 32 + lane]); }
+          const float msum = spread_reward_sum<SAc>(m, cnt);
+          buf[lane * RS + L.rw_off + i] = msum;
+          ret_reg += msum;
+        }
       }
       PROF_MARK(1)
     } else {
@@ -555,11 +575,11 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
   // ---- epilogue: optional reset_world, then hand state and observations back ----------------------------
   float* fin = sRow + (R.steps & 1) * TM * RS;  // obs_{T} lives in the obs columns of the next buffer
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-  if (SA > 0 && warp < SA) {  // registers -> state tile (positions are current there already)
+  if (phys_warp) {  // registers -> state tile (positions are current there already)
     T.sS[(4 * warp + 2) * EBP + lane] = vxi;
     T.sS[(4 * warp + 3) * EBP + lane] = vyi;
-    sRet[warp * EBP + lane] = ret_reg;
   }
+  if (rew_warp) sRet[(warp - RW0) * EBP + lane] = ret_reg;
   __syncthreads();
   if (R.reset_after) {
     for (int idx = tid; idx < P.scomp * REB; idx += NTB) {
