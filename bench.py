@@ -514,7 +514,7 @@ def main():
     fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e-6  # 128 FP32 lanes per SM
     ep_roof = {"kernel": "k_rollout_episode<64,true,3>" if roll.mode == "mega" else "per-step kernels", "bound": "hbm",
                "achieved": ep_bytes / ep_us / 1e3, "peak": peak, "unit": "GB/s", "frac": ep_bytes / ep_us / 1e3 / peak,
-               "traffic": 6.24e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_v3.txt (dram read 1.36 MB + write 4.88 MB per "
+               "traffic": 5.28e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_v3.txt (dram read 1.37 MB + write 3.91 MB per "
                "launch; the 52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
                "algorithmic_bytes_per_launch": ep_bytes, "avg_launch_us": ep_us,
                "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the actor "
