@@ -281,7 +281,7 @@ struct RolloutArgs {
 // spread_step / spread_obs of mdp_env_dev.cuh, the code of k_env_step_spread) instead of the table-driven CTA-collective
 // phases: the state never leaves the 32 threads' registers between the prologue and the epilogue.
 template <int U, bool RESIDENT, int SA>
-__global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
+__global__ void __launch_bounds__(!RESIDENT ? 1024 : SA == 2 ? 256 : SA == 3 ? 384 : 512) k_rollout_episode(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
                                                           mdp_ring_layout L, RolloutArgs R, int NG) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4, EBP = REB + 1;
@@ -398,6 +398,13 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
     __syncthreads();
   }
 
+  // descriptor of the group's first agent (its only one when A <= NG), loaded once
+  const int ag_first = grp < A ? grp : 0;
+  const int D0 = C.agents[ag_first].obs_dim, K0 = C.agents[ag_first].act_dim, nh0 = C.agents[ag_first].n_heads;
+  const int obs_off0 = C.agents[ag_first].obs_off, act_off0 = C.agents[ag_first].act_off;
+  MlpW w0 = C.agents[ag_first].net[MDP_NET_P];
+  if (RESIDENT) w0 = net_at<U>(sWts + sOff[ag_first], D0, K0);
+
   // ---- the episode -----------------------------------------------------------------------------------
   long long ring_row = (cursor + e0) % R.capacity;  // ring row of this CTA's first env at step s (thread 0 keeps it current)
 #ifdef MDP_EPISODE_PROF
@@ -413,10 +420,15 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
     // (1) actions: a_i = gumbel_softmax(mlp_i(obs_i)) for every agent, written into the row's act columns
     for (int i = grp; i < A; i += NG) {
       const AgentDev& ag = C.agents[i];
-      const int D = ag.obs_dim, K = ag.act_dim;
-      MlpW w = ag.net[MDP_NET_P];
-      if (RESIDENT) w = net_at<U>(sWts + sOff[i], D, K);
-      const bool fused_head = ag.n_heads == 1 && K == 5;  // Discrete(5): every MPE movement head
+      const bool first = i == grp;  // the group's first agent: descriptor cached in registers before the step loop
+      const int D = first ? D0 : ag.obs_dim, K = first ? K0 : ag.act_dim;
+      const int obs_off_i = first ? obs_off0 : ag.obs_off, act_off_i = first ? act_off0 : ag.act_off;
+      MlpW w = w0;
+      if (!first) {
+        w = ag.net[MDP_NET_P];
+        if (RESIDENT) w = net_at<U>(sWts + sOff[i], D, K);
+      }
+      const bool fused_head = (first ? nh0 : ag.n_heads) == 1 && K == 5;  // Discrete(5): every MPE movement head
       float noise[Tile::NP];
       if (fused_head && SA == 0) {
 #pragma unroll
@@ -431,15 +443,15 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
       Tile::zero(acc);
       PROF_MARK(2)
       if (SA > 0) {
-        Tile::mma_t(G.tid, acc, sXT + ag.obs_off * 32, w.W1, D);
+        Tile::mma_t(G.tid, acc, sXT + obs_off_i * 32, w.W1, D);
         PROF_MARK(7)
       } else if (RESIDENT) {
-        Tile::mma_sa(G.tid, acc, buf + ag.obs_off, RS, w.W1, D);
+        Tile::mma_sa(G.tid, acc, buf + obs_off_i, RS, w.W1, D);
       } else {
         for (int k0 = 0; k0 < D; k0 += KC) {
           load_w_rows<U>(G, sWts, w.W1, k0, D);
           G.sync();
-          Tile::mma_sa(G.tid, acc, buf + ag.obs_off + k0, RS, sWts, min(KC, D - k0));
+          Tile::mma_sa(G.tid, acc, buf + obs_off_i + k0, RS, sWts, min(KC, D - k0));
           G.sync();
         }
       }
@@ -468,12 +480,12 @@ __global__ void __launch_bounds__(RESIDENT ? 512 : 1024) k_rollout_episode(CoreD
 #pragma unroll
           for (int p = 0; p < Tile::NP; ++p) noise[p] = sNoise[i * 256 + Tile::head_row(G.tid, p) * 8 + (G.tid & 7)];
         }
-        Tile::template head_gumbel<5>(G, sH2, w, buf + L.obs_sum + ag.act_off, RS, nE, noise);
+        Tile::template head_gumbel<5>(G, sH2, w, buf + L.obs_sum + act_off_i, RS, nE, noise);
         if (!RESIDENT) G.sync();  // streaming groups reuse their weight staging chunk for the next agent
       } else {
         Tile::head(G, sH2, w, sL);
         PROF_MARK(7)
-        Tile::gumbel_softmax(G, sL, buf + L.obs_sum + ag.act_off, RS, nE, K, ag.n_heads, ag.head_dim, (long long)e0, R.seed,
+        Tile::gumbel_softmax(G, sL, buf + L.obs_sum + act_off_i, RS, nE, K, ag.n_heads, ag.head_dim, (long long)e0, R.seed,
                              counter + (unsigned long long)s + 1ull, (uint32_t)i);
       }
       PROF_MARK(8)
