@@ -8,8 +8,7 @@
 // weights stay resident in shared memory; per step the only global traffic is the joint replay row
 // (obs_t, act_t, next_obs, rew, done) streaming out to the ring.  Results are identical to the
 // per-step path (mdp_actor_act + mdp_env_step with ring + mdp_env_reset) on the same Philox counters.
-#include "mdp_env_dev.cuh"
-#include "mdp_mlp.cuh"
+#include "mdp_rollout.cuh"
 
 namespace mdp {
 
@@ -17,12 +16,7 @@ namespace mdp {
 #define MDP_EP_UNROLL 2
 #endif
 constexpr int EP_UNROLL = MDP_EP_UNROLL;  // k-loop unroll (in float4 A loads) of the episode kernel's hidden layer
-constexpr int REB = 32;  // env instances per CTA == rows of the MLP tile
 constexpr int TM = REB;
-
-__host__ __device__ inline int actor_net_floats(int D, int U, int K) {
-  return ((D * U + U + U * U + U + U * K + K) + 3) & ~3;
-}
 
 // ---- actor tile of the episode kernel: 32 env rows x U units per group of GTH threads ----------------------------------
 // Thread (ty, tx) = (tid >> 4, tid & 15) owns rows {RM*ty .. +RM-1}, RM = 512 / GTH, and columns {64g + 4tx .. +3}.  With
@@ -256,17 +250,6 @@ struct EpTile {
   }
 };
 
-struct RolloutArgs {
-  int E, steps, reset_after;
-  float* state;
-  float* obs;  // (E, obs_stride) joint current observations, in/out
-  float* ring;
-  long long capacity, cursor;
-  unsigned long long seed, counter, env_seed, episode;
-  float lm_lo, lm_hi;
-  const unsigned long long* ctl;
-  float* ep_return;  // optional (E, A): sum of rewards over the launch
-};
 
 // NG groups of GTH threads (128 with resident weights, else 256); group g runs the actor MLPs of agents g, g+NG, ...
 // concurrently with the other groups (named barriers 1..NG); the env phases use all NG*GTH threads.
@@ -323,7 +306,7 @@ __global__ void __launch_bounds__(!RESIDENT ? 1024 : SA == 2 ? 256 : SA == 3 ? 3
   }
 
   // ---- prologue: state tile, observation tile, column table, actor weights -------------------------
-  env_load_state<float, REB>(P, T, R.state, R.E, e0, nE);
+  env_load_state<float, REB>(P, T, (const float*)R.state, R.E, e0, nE);
   for (int i = tid; i < 2 * TM * RS; i += NTB) sRow[i] = 0.f;  // padding / done columns stay zero for good
   for (int c = tid; c < OS; c += NTB) sCols[c] = cols[c];
   for (int idx = tid; idx < A * EBP; idx += NTB) sRet[idx] = 0.f;
@@ -606,7 +589,7 @@ __global__ void __launch_bounds__(!RESIDENT ? 1024 : SA == 2 ? 256 : SA == 3 ? 3
     }
     __syncthreads();
   }
-  env_store_state<float, REB>(P, T, R.state, R.E, e0, nE, R.reset_after != 0);
+  env_store_state<float, REB>(P, T, (float*)R.state, R.E, e0, nE, R.reset_after != 0);
   for (int ee = warp; ee < nE; ee += nwarps)
     for (int c = lane; c < OS; c += 32) R.obs[(size_t)(e0 + ee) * OS + c] = (c < L.obs_sum) ? fin[ee * RS + c] : 0.f;
   if (R.ep_return)
@@ -620,9 +603,6 @@ __global__ void __launch_bounds__(!RESIDENT ? 1024 : SA == 2 ? 256 : SA == 3 ? 3
 
 using namespace mdp;
 
-namespace mdp {
-CoreDev core_dev_for_rollout(const mdp_core* c);
-}
 
 extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
                                    int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
@@ -631,7 +611,6 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   MDP_REQUIRE(env && core && core->d_agents, "mdp_rollout_episode: env/core not ready");
   MDP_REQUIRE(state && obs && ring && E > 0 && steps > 0 && ring_capacity >= (int64_t)E * steps,
               "mdp_rollout_episode: bad argument (E %d, steps %d, capacity %lld)", E, steps, (long long)ring_capacity);
-  if (env->cfg.state_f64) return fail(MDP_ENOTSUP, "mdp_rollout_episode: float64 state is served by the per-step kernels");
   const EnvParams& P = env->P;
   MDP_REQUIRE(P.A == core->cfg.n_agents, "mdp_rollout_episode: env has %d agents, core %d", P.A, core->cfg.n_agents);
   for (int i = 0; i < P.A; ++i)
@@ -643,6 +622,21 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   MDP_REQUIRE(lay.row_stride == ring_row_stride, "mdp_rollout_episode: ring_row_stride %d != layout %d", ring_row_stride, lay.row_stride);
   rc = env_ensure_cols(env);
   if (rc) return rc;
+  RolloutArgs R;
+  R.E = E; R.steps = steps; R.reset_after = reset_after;
+  R.state = state; R.obs = obs; R.ring = ring;
+  R.capacity = ring_capacity; R.cursor = ring_cursor;
+  R.seed = seed; R.counter = counter; R.env_seed = env_seed; R.episode = episode;
+  R.lm_lo = env->reset_lo_lm; R.lm_hi = env->reset_hi_lm;
+  R.ctl = env->ctl ? env->ctl : core->ctl;
+  R.ep_return = ep_return;
+  cudaStream_t st = (cudaStream_t)stream;
+  // tcgen05 actor tiles (mdp_rollout_tc.cu) unless the core is pinned to the SIMT kernels (mdp_core_set_tensor_cores(core, -1))
+  if (core->tc_mode >= 0) {
+    rc = rollout_episode_tc(env, core, lay, R, st);
+    if (rc != MDP_ENOTSUP) return rc;
+  }
+  if (env->cfg.state_f64) return fail(MDP_ENOTSUP, "mdp_rollout_episode: float64 state needs the tensor-core episode kernel (simple_spread, 2-4 agents, 64 units)");
   const int U = core->cfg.num_units, HP = U + 4;
   size_t wts = 0;
   for (int i = 0; i < P.A; ++i) wts += actor_net_floats(core->cfg.obs_dim[i], U, core->cfg.act_dim[i]);
@@ -664,16 +658,7 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   if (NG == 0)
     return fail(MDP_ENOTSUP, "mdp_rollout_episode: %d agents x %d observation floats do not fit one CTA's shared memory",
                 P.A, P.obs_stride);
-  RolloutArgs R;
-  R.E = E; R.steps = steps; R.reset_after = reset_after;
-  R.state = (float*)state; R.obs = obs; R.ring = ring;
-  R.capacity = ring_capacity; R.cursor = ring_cursor;
-  R.seed = seed; R.counter = counter; R.env_seed = env_seed; R.episode = episode;
-  R.lm_lo = env->reset_lo_lm; R.lm_hi = env->reset_hi_lm;
-  R.ctl = env->ctl ? env->ctl : core->ctl;
-  R.ep_return = ep_return;
   CoreDev d = core_dev_for_rollout(core);
-  cudaStream_t st = (cudaStream_t)stream;
   auto go = [&](auto kern) -> int {
     if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<cdiv(E, REB), NG * (resident ? 128 : NT), smem, st>>>(d, P, env->d_cols, lay, R, NG);

@@ -49,8 +49,7 @@ class BatchedRollout(object):
         self.episode_step = 0
         self.total_steps = 0
         self.mode = mode or ("mega" if use_graph else "eager")
-        if self.mode == "mega" and env.state_dtype != torch.float32:
-            self.mode = "graph"
+        # float64 state: only the tensor-core episode kernel serves it; run_mega() falls back to "graph" when it declines
         use_graph = self.mode != "eager"
         self.mega_launches = 0
         self.ep_return = None
