@@ -266,12 +266,24 @@ int mdp_clip_adam_polyak_all(mdp_core* core, int32_t which, float grad_scale, in
  * `counter + s + 1`, so the result equals `steps` x (mdp_actor_act(counter+s+1), mdp_env_step with ring)
  * [+ mdp_env_reset(env_seed, episode)].  obs: joint current observations (E, obs_stride), read at entry and
  * replaced by the final (post-reset) observations.  ep_return (optional, (E, n_agents)): += sum of rewards.
- * float32 state only; MDP_ENOTSUP when the observation tile does not fit in shared memory (callers then use
- * the per-step kernels). */
+ * Two kernels serve the call.  simple_spread with 2-4 agents, num_units = 64, float32 OR float64 state: the actor MLP
+ * (train.py:39-46) runs on the tcgen05 tensor cores -- weights resident in tensor memory, 3xTF32 split, fp32 accumulate;
+ * actions agree with the fp32 SIMT kernels to ~5e-7 (csrc/mdp_rollout_tc.cu).  Everything else, and every core pinned
+ * with mdp_core_set_tensor_cores(core, -1): fp32 SIMT actor tiles, bit-identical to the per-step kernels, float32 state only.
+ * MDP_ENOTSUP when neither applies (callers then use the per-step kernels). */
 int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
                         int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
                         uint64_t seed, uint64_t counter, int32_t reset_after, uint64_t env_seed, uint64_t episode,
                         float* ep_return, void* stream);
+
+/* `episodes` consecutive episodes of `steps` steps, each followed by env.reset() (train.py:110-133 run for
+ * episodes * steps iterations with max_episode_len = steps): identical to `episodes` calls of mdp_rollout_episode with
+ * reset_after = 1, counter + k*steps, ring_cursor + k*steps*E and episode + k -- the tcgen05 kernel loops over the episodes
+ * inside ONE launch (weights stay in tensor memory, no per-episode prologue), other configurations launch per episode.
+ * ring_capacity >= E * steps * episodes. */
+int mdp_rollout_episodes(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
+                         int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps, int32_t episodes,
+                         uint64_t seed, uint64_t counter, uint64_t env_seed, uint64_t episode, float* ep_return, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* host-buffer loop body                                                                        */
@@ -327,6 +339,12 @@ const char* mdp_last_error(void);
 const char* mdp_version(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */
 int64_t mdp_launch_count(void);
+
+/* HOST helper for parity tests: the U[0,1) draws behind the kernels' Gumbel noise (SoftCategoricalPd.sample,
+ * distributions.py:264-266, u = random_uniform): h_out[r * ncols + a] = Philox4x32-10 keyed by (seed, counter, agent tag,
+ * row0 + r, a), exactly what mdp_actor_act / mdp_rollout_episode draw for population row row0 + r.  No device work. */
+int mdp_philox_uniform(uint64_t seed, uint64_t counter, uint32_t tag, int64_t row0, int32_t nrows, int32_t ncols,
+                       float* h_out);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,9 @@ SYMBOLS = {
     "mdp_clip_adam_polyak_all": (C.c_int, [_P, C.c_int32, C.c_float, C.c_int32, _P]),
     "mdp_rollout_episode": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32,
                                       C.c_uint64, C.c_uint64, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
+    "mdp_philox_uniform": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, C.c_int32, C.c_int32, _P]),
+    "mdp_rollout_episodes": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, _P, _P]),
     "mdp_host_step_layout": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mdp_host_step": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int32, C.c_int64,
                                 C.c_uint64, C.c_uint64, _P]),

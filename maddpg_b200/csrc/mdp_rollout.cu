@@ -604,13 +604,44 @@ __global__ void __launch_bounds__(!RESIDENT ? 1024 : SA == 2 ? 256 : SA == 3 ? 3
 using namespace mdp;
 
 
+static int rollout_launch(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring, int64_t ring_capacity,
+                          int32_t ring_row_stride, int64_t ring_cursor, int32_t steps, int32_t episodes, uint64_t seed,
+                          uint64_t counter, int32_t reset_after, uint64_t env_seed, uint64_t episode, float* ep_return,
+                          void* stream);
+
 extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
                                    int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
                                    uint64_t seed, uint64_t counter, int32_t reset_after, uint64_t env_seed,
                                    uint64_t episode, float* ep_return, void* stream) {
+  return rollout_launch(env, core, E, state, obs, ring, ring_capacity, ring_row_stride, ring_cursor, steps, 1, seed, counter,
+                        reset_after, env_seed, episode, ep_return, stream);
+}
+
+extern "C" int mdp_rollout_episodes(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring,
+                                    int64_t ring_capacity, int32_t ring_row_stride, int64_t ring_cursor, int32_t steps,
+                                    int32_t episodes, uint64_t seed, uint64_t counter, uint64_t env_seed, uint64_t episode,
+                                    float* ep_return, void* stream) {
+  MDP_REQUIRE(episodes > 0, "mdp_rollout_episodes: episodes %d", episodes);
+  int rc = rollout_launch(env, core, E, state, obs, ring, ring_capacity, ring_row_stride, ring_cursor, steps, episodes, seed, counter,
+                          1, env_seed, episode, ep_return, stream);
+  if (rc != MDP_ENOTSUP || episodes == 1) return rc;
+  // kernels without the in-kernel episode loop: one launch per episode (the ring cursor / counters advance like the kernel's)
+  for (int ep = 0; ep < episodes; ++ep) {
+    rc = rollout_launch(env, core, E, state, obs, ring, ring_capacity, ring_row_stride,
+                        (ring_cursor + (int64_t)ep * steps * E) % ring_capacity, steps, 1, seed, counter + (uint64_t)ep * steps, 1,
+                        env_seed, episode + ep, ep_return, stream);
+    if (rc) return rc;
+  }
+  return MDP_OK;
+}
+
+static int rollout_launch(mdp_env* env, mdp_core* core, int32_t E, void* state, float* obs, float* ring, int64_t ring_capacity,
+                          int32_t ring_row_stride, int64_t ring_cursor, int32_t steps, int32_t episodes, uint64_t seed,
+                          uint64_t counter, int32_t reset_after, uint64_t env_seed, uint64_t episode, float* ep_return,
+                          void* stream) {
   MDP_REQUIRE(env && core && core->d_agents, "mdp_rollout_episode: env/core not ready");
-  MDP_REQUIRE(state && obs && ring && E > 0 && steps > 0 && ring_capacity >= (int64_t)E * steps,
-              "mdp_rollout_episode: bad argument (E %d, steps %d, capacity %lld)", E, steps, (long long)ring_capacity);
+  MDP_REQUIRE(state && obs && ring && E > 0 && steps > 0 && ring_capacity >= (int64_t)E * steps * episodes,
+              "mdp_rollout_episode: bad argument (E %d, steps %d x %d, capacity %lld)", E, steps, episodes, (long long)ring_capacity);
   const EnvParams& P = env->P;
   MDP_REQUIRE(P.A == core->cfg.n_agents, "mdp_rollout_episode: env has %d agents, core %d", P.A, core->cfg.n_agents);
   for (int i = 0; i < P.A; ++i)
@@ -623,7 +654,7 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
   rc = env_ensure_cols(env);
   if (rc) return rc;
   RolloutArgs R;
-  R.E = E; R.steps = steps; R.reset_after = reset_after;
+  R.E = E; R.steps = steps; R.reset_after = reset_after; R.episodes = episodes;
   R.state = state; R.obs = obs; R.ring = ring;
   R.capacity = ring_capacity; R.cursor = ring_cursor;
   R.seed = seed; R.counter = counter; R.env_seed = env_seed; R.episode = episode;
@@ -636,6 +667,7 @@ extern "C" int mdp_rollout_episode(mdp_env* env, mdp_core* core, int32_t E, void
     rc = rollout_episode_tc(env, core, lay, R, st);
     if (rc != MDP_ENOTSUP) return rc;
   }
+  if (episodes != 1) return MDP_ENOTSUP;  // the caller loops (mdp_rollout_episodes)
   if (env->cfg.state_f64) return fail(MDP_ENOTSUP, "mdp_rollout_episode: float64 state needs the tensor-core episode kernel (simple_spread, 2-4 agents, 64 units)");
   const int U = core->cfg.num_units, HP = U + 4;
   size_t wts = 0;

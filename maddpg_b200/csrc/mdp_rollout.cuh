@@ -13,6 +13,7 @@ __host__ __device__ inline int actor_net_floats(int D, int U, int K) {
 
 struct RolloutArgs {
   int E, steps, reset_after;
+  int episodes;  // tcgen05 kernel: `episodes` x (steps, then reset_world when reset_after) in one launch
   void* state;  // SoA [state_comps][E], float32 or float64 (mdp_env_cfg.state_f64)
   float* obs;   // (E, obs_stride) joint current observations, in/out
   float* ring;

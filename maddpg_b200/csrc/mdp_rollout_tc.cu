@@ -15,17 +15,19 @@
 //     split side by side.  An MMA for agent i therefore also produces 64 garbage lanes (the pair partner's weights applied to
 //     agent i's activations) -- the UMMA cost floor is max(M, 128) * N / 256 cycles anyway.
 //   * B operand = the activations of the CTA's 32 env instances, a K-major SWIZZLE_128B image [32 env][32 k] per 32-wide k panel
-//     in shared memory, written by the epilogue threads (hi = the fp32 value itself -- kind::tf32 reads its upper 19 bits --
-//     and lo = x - trunc(x), exact).  Every product is issued as lo*hi + hi*lo + hi*hi (fp32 accumulate in TMEM): measured
-//     fp32-class, ~2e-6 relative (tools/umma_probe.cu).
+//     in shared memory, written by the epilogue threads as hi = rna_tf32(x) and lo = x - hi (exact).  Every product is issued
+//     as lo*hi + hi*lo + hi*hi (fp32 accumulate in TMEM): fp32-class, actions within ~2e-7 of the fp32 SIMT kernels.
 //   * D (32 fp32 columns per agent in TMEM) comes back with tcgen05.ld 32x32b: thread = one hidden unit, 32 env instances in
 //     registers, bias + ReLU + split, stores to the next layer's image.  N = 32: 16 cycles per MMA.
 // The 64 x 5 output head and the Gumbel-softmax run on two threads per (env, agent) row straight from the fp32 h2 image, and
 // the SAME thread continues into World.step for its (env, agent) -- an agent's chain never waits for the other agents'
-// actions, only for their positions.
+// actions, only for their positions.  The two threads of a row then write the x / y halves of the new observation straight
+// into the next step's layer-1 operand images; the replay rows are assembled from those images by the reward warps, off the
+// critical path, and leave through one TMA bulk store per row and step.
 //
-// Warp roles (A agents): warps [0, 2A) actor warps (agent w/2; TMEM lane quadrant w%4 == the quadrant its units land in),
-// warps [2A, 3A) reward warps (Scenario.reward, next step's Gumbel noise, the replay-row TMA bulk store), warp 3A MMA issuer.
+// Warp roles (A agents): warps [0, 2A) actor warps (agent w/2; TMEM lane quadrant w%4 == the quadrant its units land in; the
+// even warp of an agent also issues that agent's MMAs -- no issuer warp, no cross-agent serialisation of the issue loops),
+// warps [2A, 3A) reward warps (Scenario.reward, next step's Gumbel noise, the replay-row TMA bulk store).
 #include "mdp_rollout.cuh"
 #include "mdp_umma.cuh"
 
@@ -68,7 +70,20 @@ __device__ __forceinline__ float4 ld_s128(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// 3xTF32 split with ROUND-TO-NEAREST on the high part: hi = rna_tf32(x) (low 13 mantissa bits zero), lo = x - hi (exact,
+// signed, |lo| <= 2^-11 |x|; x == hi + lo exactly).  kind::tf32 reads the upper 19 bits of lo, i.e. truncates it toward zero:
+// a sign-symmetric error <= 2^-21 |x|.  With the truncating split (hi = x & 0xFFFFE000) lo is one-sided and twice as large,
+// and both the dropped lo*lo term and the truncation of lo become BIASED errors that add up along K: measured against the
+// float64 oracle the free-running 25-step rollout drifted 5x more (actions 5e-7 instead of 1-2e-7).
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split_rn(float x, float& hi, float& lo) {
+  hi = tf32_rn(x);
+  lo = x - hi;
+}
 
 // ---- simple_spread pieces for a state precision `real` -----------------------------------------------------------------------
 // float: the pinned-rounding pieces of mdp_env_dev.cuh (bit-identical to k_env_step_spread); double: the arithmetic of
@@ -162,31 +177,12 @@ struct Spread<A, double> {
   }
 };
 
-// Scenario.observation of agent i (simple_spread): [vel, pos, landmarks - pos, others - pos, silent comm zeros]
-// out(c, v): c known at compile time; out_rt(c, v): c depends on the (runtime) agent index
-template <int A, typename real, typename Out, typename OutRt>
-__device__ __forceinline__ void obs_agent(int i, const real (&px)[A], const real (&py)[A], real pxi, real pyi, real vxi, real vyi,
-                                          const real (&lx)[A], const real (&ly)[A], Out&& out, OutRt&& out_rt) {
-  constexpr int L = A, D = 6 * A;
-  out(0, (float)vxi); out(1, (float)vyi); out(2, (float)pxi); out(3, (float)pyi);
-#pragma unroll
-  for (int l = 0; l < L; ++l) { out(4 + 2 * l, (float)(lx[l] - pxi)); out(5 + 2 * l, (float)(ly[l] - pyi)); }
-#pragma unroll
-  for (int q = 0; q < A; ++q) {
-    if (q == i) continue;
-    const int c = 4 + 2 * L + 2 * (q < i ? q : q - 1);
-    out_rt(c, (float)(px[q] - pxi));
-    out_rt(c + 1, (float)(py[q] - pyi));
-  }
-#pragma unroll
-  for (int c = 4 + 2 * L + 2 * (A - 1); c < D; ++c) out(c, 0.f);
-}
 
 template <int SA>
 struct Cfg {
   static constexpr int A = SA, D = 6 * SA, NPAIR = (SA + 1) / 2;
   static constexpr int K1 = (D + 7) / 8 * 8;  // layer-1 K padded to whole kind::tf32 MMAs (8 per instruction)
-  static constexpr int NW = 3 * SA + 1, NTB = 32 * NW;
+  static constexpr int NW = 3 * SA, NTB = 32 * NW;
   // tensor-memory columns
   static constexpr uint32_t T_W2 = 0;                        // pair p: hi at 128 p, lo at 128 p + 64
   static constexpr uint32_t T_W1 = 128 * NPAIR;              // pair p: hi at T_W1 + 2 K1 p, lo K1 further
@@ -199,11 +195,26 @@ struct Cfg {
   static constexpr uint32_t OFF_REST = OFF_H + SA * 4 * IMG;
 };
 
+// pitch of the shared-memory replay rows: a multiple of 4 floats (TMA bulk source alignment) that is 4 mod 8, so that the
+// 16 rows a warp touches per access fall on 8 different 4-bank groups (2-way instead of 4-way conflicts at pitch = 136)
+__host__ __device__ inline int row_pitch(int RS) { return (RS & 7) == 0 ? RS + 4 : RS; }
+
 __host__ __device__ inline size_t rest_floats(int A, int RS, int OS, size_t env_tile_bytes) {
   auto r4 = [](size_t x) { return (x + 3) & ~(size_t)3; };
-  return r4(2 * (size_t)EB * RS) + r4((size_t)A * (5 * W3A + 8)) + r4(2 * (size_t)A * EB * 8) + r4(2 * (size_t)A * EB) +
+  return r4(2 * (size_t)EB * row_pitch(RS)) + r4((size_t)A * (5 * W3A + 8)) + r4(2 * (size_t)A * EB * 8) + r4(2 * (size_t)A * EB) + r4((size_t)A * EB) +
          r4((size_t)A * (EB + 1)) + r4(2 * (size_t)OS) + r4(env_tile_bytes / 4) + r4(2 * 4 * (size_t)A) + 16;
 }
+
+#ifdef MDP_EPISODE_PROF
+#ifndef MDP_PROF_AGENT
+#define MDP_PROF_AGENT 0
+#endif
+#define TPROF_DECL long long prof_t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, prof_c = clock64();
+#define TPROF(k) { const long long t_ = clock64(); prof_t[k] += t_ - prof_c; prof_c = t_; }
+#else
+#define TPROF_DECL
+#define TPROF(k)
+#endif
 
 template <int SA, typename real>
 __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev C, EnvParams P, const ObsCol* __restrict__ cols,
@@ -215,27 +226,27 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
   unsigned char* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
   const uint32_t sbase = smem_u32(smem);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int OS = P.obs_stride, RS = L.row_stride;
+  const int OS = P.obs_stride, RS = L.row_stride, RSP = row_pitch(RS);
   const int e0 = blockIdx.x * EB;
   const int nE = min(EB, R.E - e0);
+  const int nwarps = NTB >> 5;
 
   // ---- shared memory carve-up ---------------------------------------------------------------------------------------------
   SmemCarve sm(smem + CF::OFF_REST);
-  float* sRow = sm.take(2 * EB * RS);       // two replay-row buffers (ping-pong), assembled in place
+  float* sRow = sm.take(2 * EB * RSP);      // two replay-row buffers (ping-pong by step parity), assembled in place
   float* sW3 = sm.take(A * (5 * W3A + 8));  // per agent: W3 transposed [5][2 x 36] + b3
   float* sNoise = sm.take(2 * A * EB * 8);  // Gumbel noise, [step parity][agent][env][8]
-  float* sPart = sm.take(2 * A * EB);       // reward partials (landmark minima, collision counts)
+  float* sPart = sm.take(2 * A * EB);       // reward partials: landmark minima (room for float64)
+  int* sCnt = reinterpret_cast<int*>(sm.take(A * EB));  // ... and collision counts
   float* sRet = sm.take(A * EBP);
   ObsCol* sCols = reinterpret_cast<ObsCol*>(sm.take(2 * OS));
   real* sEnvBase = reinterpret_cast<real*>(sm.take((int)(EnvTile<real, EB>::bytes(P.scomp, A, P.act_stride, false) / 4)));
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(sm.take(2 * 4 * A));
-  unsigned long long* bar_obs = bars;          // [A] count 2: agent i's observation images of the next step are written
-  unsigned long long* bar_l1 = bars + A;       // [A] tcgen05.commit: layer-1 accumulator of agent i complete
-  unsigned long long* bar_h1 = bars + 2 * A;   // [A] count 2: agent i's h1 images are written
-  unsigned long long* bar_l2 = bars + 3 * A;   // [A] tcgen05.commit: layer-2 accumulator complete
+  unsigned long long* bar_l1 = bars;           // [A] tcgen05.commit: layer-1 accumulator of agent i complete
+  unsigned long long* bar_l2 = bars + 2 * A;   // [A] tcgen05.commit: layer-2 accumulator complete
   EnvTile<real, EB> T;
   T.carve(sEnvBase, P, sRow + L.obs_sum);
-  T.ASP = RS;
+  T.ASP = RSP;
 
   unsigned long long counter = R.counter, episode = R.episode;
   long long cursor = R.cursor;
@@ -244,16 +255,19 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
     cursor = (cursor + (long long)R.ctl[1]) % R.capacity;
     episode += R.ctl[2];
   }
+  const int total_steps = R.steps * R.episodes;
 
+#ifdef MDP_EPISODE_PROF
+  const long long k_t0 = clock64();
+  long long k_loop = 0;
+#endif
   // ---- prologue ---------------------------------------------------------------------------------------------------------------
-  if (warp == CF::NW - 1) umma::tmem_alloc(&tmem_slot, CF::T_COLS);
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, CF::T_COLS);
   if (tid == 0) {
-    for (int i = 0; i < A; ++i) {
-      mbar_init(&bar_obs[i], 2); mbar_init(&bar_l1[i], 1); mbar_init(&bar_h1[i], 2); mbar_init(&bar_l2[i], 1);
-    }
+    for (int i = 0; i < 2 * A; ++i) { mbar_init(&bar_l1[i], 1); mbar_init(&bar_l2[i], 1); }
   }
   env_load_state<real, EB>(P, T, (const real*)R.state, R.E, e0, nE);
-  for (int i = tid; i < 2 * EB * RS; i += NTB) sRow[i] = 0.f;  // padding / done columns stay zero for good
+  for (int i = tid; i < 2 * EB * RSP; i += NTB) sRow[i] = 0.f;  // padding / done / silent-comm columns stay zero for good
   for (int i = tid; i < (int)(CF::OFF_H / 16); i += NTB) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int c = tid; c < OS; c += NTB) sCols[c] = cols[c];
   for (int idx = tid; idx < A * EBP; idx += NTB) sRet[idx] = 0.f;
@@ -272,24 +286,24 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
       const int ag = 2 * p + half;
       const MlpW w = C.agents[ag < A ? ag : 0].net[MDP_NET_P];
       const bool live = ag < A;
-#pragma unroll 1
+#pragma unroll 2
       for (int k0 = 0; k0 < U; k0 += 16) {
         float hi[16], lo[16];
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
           const float x = live ? w.W2[(k0 + kk) * U + u] : 0.f;
-          umma::split_tf32(x, hi[kk], lo[kk]);
+          split_rn(x, hi[kk], lo[kk]);
         }
         umma::tmem_st16(tbase + lane_base + CF::T_W2 + 128 * p + k0, hi);
         umma::tmem_st16(tbase + lane_base + CF::T_W2 + 128 * p + 64 + k0, lo);
       }
-#pragma unroll 1
+#pragma unroll
       for (int k0 = 0; k0 < K1; k0 += 8) {
         float hi[8], lo[8];
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const float x = (live && k0 + kk < D) ? w.W1[(k0 + kk) * U + u] : 0.f;
-          umma::split_tf32(x, hi[kk], lo[kk]);
+          split_rn(x, hi[kk], lo[kk]);
         }
         umma::tmem_st8(tbase + lane_base + CF::T_W1 + 2 * K1 * p + k0, hi);
         umma::tmem_st8(tbase + lane_base + CF::T_W1 + 2 * K1 * p + K1 + k0, lo);
@@ -309,11 +323,13 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
   for (int idx = tid; idx < EB * L.obs_sum; idx += NTB) {
     const int ee = idx / L.obs_sum, c = idx - ee * L.obs_sum;
     const float v = ee < nE ? R.obs[(size_t)(e0 + ee) * OS + c] : 0.f;
-    sRow[ee * RS + c] = v;
+    sRow[ee * RSP + c] = v;
     const int i = c / D, cc = c - i * D;
     unsigned char* img = smem + CF::OFF_OBS + i * 2 * IMG;
-    *reinterpret_cast<float*>(img + umma::sw128_off(ee, cc)) = v;
-    *reinterpret_cast<float*>(img + IMG + umma::sw128_off(ee, cc)) = tf32_lo(v);
+    float vh, vl;
+    split_rn(v, vh, vl);
+    *reinterpret_cast<float*>(img + umma::sw128_off(ee, cc)) = vh;
+    *reinterpret_cast<float*>(img + IMG + umma::sw128_off(ee, cc)) = vl;
   }
   // Gumbel noise of step 0 (afterwards the reward warps draw one step ahead)
   for (int idx = tid; idx < A * EB * 5; idx += NTB) {
@@ -329,225 +345,57 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
   auto pos_bar = [] { asm volatile("bar.sync 9, %0;" ::"r"(96 * A) : "memory"); };    // actor + reward warps: new positions are in the tile
   auto rew_bar = [] { asm volatile("bar.sync 10, %0;" ::"r"(32 * A) : "memory"); };   // reward warps only
   auto row_arrive = [] { asm volatile("bar.arrive 11, %0;" ::"r"(96 * A) : "memory"); };
-  auto row_sync = [] { asm volatile("bar.sync 11, %0;" ::"r"(96 * A) : "memory"); };  // the step's replay rows are complete
+  auto row_sync = [] { asm volatile("bar.sync 11, %0;" ::"r"(96 * A) : "memory"); };  // the step's observation images are written
 
-  if (warp < 2 * A) {
-    // =================================== actor warps =========================================================================
-    const int i = warp >> 1, h = warp & 1;
-    const int e = 16 * h + (lane >> 1), par = lane & 1, e7 = e & 7;
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    const uint32_t tD = tbase + lane_base + CF::T_D + 32 * i;
-    const MlpW wg = C.agents[i].net[MDP_NET_P];
-    const float b1u = wg.b1[32 * h + lane], b2u = wg.b2[32 * h + lane];
-    // unit role: element (env n, unit 32 h + lane) of the hidden images
-    const uint32_t hU = sbase + CF::OFF_H + i * 4 * IMG + h * IMG;
-    uint32_t xo[8];
+  for (int ep = 0; ep < R.episodes; ++ep) {
+    const int g0 = ep * R.steps;  // global step index of the episode's first step: row-buffer / noise / mbarrier parities follow it
+#ifdef MDP_EPISODE_PROF
+    const long long k_t1 = clock64();
+#endif
+    if (warp < 2 * A) {
+      // =================================== actor warps =======================================================================
+      const int i = warp >> 1, h = warp & 1;
+      const int e = 16 * h + (lane >> 1), par = lane & 1, e7 = e & 7;
+      const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+      const uint32_t tD = tbase + lane_base + CF::T_D + 32 * i;
+      const MlpW wg = C.agents[i].net[MDP_NET_P];
+      const float b1u = wg.b1[32 * h + lane], b2u = wg.b2[32 * h + lane];
+      // unit role: element (env n, unit 32 h + lane) of the hidden images
+      const uint32_t hU = sbase + CF::OFF_H + i * 4 * IMG + h * IMG;
+      uint32_t xo[8];
 #pragma unroll
-    for (int n7 = 0; n7 < 8; ++n7) xo[n7] = (uint32_t)((((lane >> 2) ^ n7) << 4) | ((lane & 3) << 2));
-    // row role: (env e, half `par` of the units)
-    const uint32_t hR = sbase + CF::OFF_H + i * 4 * IMG + par * IMG + (uint32_t)((e >> 3) << 10) + (uint32_t)(e7 << 7);
-    const float* w3 = sW3 + i * (5 * W3A + 8) + W3P * par;
-    float b3[5];
+      for (int n7 = 0; n7 < 8; ++n7) xo[n7] = (uint32_t)((((lane >> 2) ^ n7) << 4) | ((lane & 3) << 2));
+      // row role: (env e, half `par` of the units)
+      const uint32_t rowoff = (uint32_t)((e >> 3) << 10) + (uint32_t)(e7 << 7);
+      const uint32_t hR = sbase + CF::OFF_H + i * 4 * IMG + par * IMG + rowoff;
+      const float* w3 = sW3 + i * (5 * W3A + 8) + W3P * par;
+      float b3[5];
 #pragma unroll
-    for (int a = 0; a < 5; ++a) b3[a] = sW3[i * (5 * W3A + 8) + 5 * W3A + a];
-    // observation writes: parity 0 -> the replay row (next_obs of this step, obs_t of the next), parity 1 -> hi | lo images
-    const uint32_t rowoff = (uint32_t)((e >> 3) << 10) + (uint32_t)(e7 << 7);
-    uint32_t cofs[(D + 3) / 4];
+      for (int a = 0; a < 5; ++a) b3[a] = sW3[i * (5 * W3A + 8) + 5 * W3A + a];
+      // observation writes: lane parity 0 owns the x components, parity 1 the y components of every (x, y) column pair
+      constexpr int NPR = 2 + A;  // compile-time pairs: velocity, position, landmarks; then A - 1 pairs of the other agents
+      uint32_t cofs[(NPR + A) / 2 + 1];
 #pragma unroll
-    for (int j = 0; j < (D + 3) / 4; ++j) cofs[j] = par ? (uint32_t)((j ^ e7) << 4) : (uint32_t)(j << 4);
-    const int x7 = par ? e7 : 0;
-    const uint32_t oImg = sbase + CF::OFF_OBS + i * 2 * IMG + rowoff;
-    // state of (env e, agent i) in registers for the whole episode (both lanes of a row keep identical copies)
-    Spread<A, real> S;
-    S.init(P, i);
-    real pxi = T.sS[(4 * i + 0) * EBP + e], pyi = T.sS[(4 * i + 1) * EBP + e];
-    real vxi = T.sS[(4 * i + 2) * EBP + e], vyi = T.sS[(4 * i + 3) * EBP + e];
-    real lx[A], ly[A];
+      for (int j = 0; j < (NPR + A) / 2 + 1; ++j) cofs[j] = (uint32_t)(((j ^ e7) << 4) | (par << 2));
+      const uint32_t oImg = sbase + CF::OFF_OBS + i * 2 * IMG + rowoff;
+      // state of (env e, agent i) in registers for the whole episode (both lanes of a row keep identical copies)
+      Spread<A, real> S;
+      S.init(P, i);
+      real pxi = T.sS[(4 * i + 0) * EBP + e], pyi = T.sS[(4 * i + 1) * EBP + e];
+      real vxi = T.sS[(4 * i + 2) * EBP + e], vyi = T.sS[(4 * i + 3) * EBP + e];
+      real ml[A];  // this lane's component of the landmark positions
 #pragma unroll
-    for (int l = 0; l < A; ++l) { lx[l] = T.sS[(4 * A + 2 * l + 0) * EBP + e]; ly[l] = T.sS[(4 * A + 2 * l + 1) * EBP + e]; }
+      for (int l = 0; l < A; ++l) ml[l] = T.sS[(4 * A + 2 * l + par) * EBP + e];
 
-    for (int s = 0; s < R.steps; ++s) {
-      float* buf = sRow + (s & 1) * EB * RS;
-      float* nxt = sRow + ((s & 1) ^ 1) * EB * RS;
-      const uint32_t ph = (uint32_t)(s & 1);
-      // ---- epilogue 1: h1 = relu(acc + b1) -> hi | lo images (B operand of layer 2)
-      mbar_wait_b(&bar_l1[i], ph);
-      umma::fence_after();
-      {
-        float v[32];
-        umma::tmem_ld32(tD, v);
-#pragma unroll
-        for (int n = 0; n < 32; ++n) {
-          const float x = fmaxf(v[n] + b1u, 0.f);
-          const uint32_t a = hU + (uint32_t)(((n >> 3) << 10) + ((n & 7) << 7)) + xo[n & 7];
-          st_s32(a, x);
-          st_s32(a + 2 * IMG, tf32_lo(x));
-        }
-      }
-      umma::fence_before();
-      umma::fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_h1[i]);
-      // ---- epilogue 2: h2 = relu(acc + b2) -> fp32 image (read by the head below)
-      mbar_wait_b(&bar_l2[i], ph);
-      umma::fence_after();
-      {
-        float v[32];
-        umma::tmem_ld32(tD, v);
-#pragma unroll
-        for (int n = 0; n < 32; ++n) {
-          const float x = fmaxf(v[n] + b2u, 0.f);
-          st_s32(hU + (uint32_t)(((n >> 3) << 10) + ((n & 7) << 7)) + xo[n & 7], x);
-        }
-      }
-      umma::fence_before();
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + i) : "memory");  // both warps of the agent: h2 rows are complete
-      // ---- output head on two threads per row (32 units each), then Gumbel-softmax (distributions.py:264-266)
-      float act[5];
-      {
-        float sa[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int jj = j ^ (par << 2);  // the two lanes of a row walk the 16-byte chunks in different orders: no bank conflicts
-          const float4 hv = ld_s128(hR + (uint32_t)((jj ^ e7) << 4));
-#pragma unroll
-          for (int a = 0; a < 5; ++a) {
-            const float4 wv = *reinterpret_cast<const float4*>(w3 + a * W3A + 4 * jj);
-            sa[a] = fmaf(hv.x, wv.x, sa[a]);
-            sa[a] = fmaf(hv.y, wv.y, sa[a]);
-            sa[a] = fmaf(hv.z, wv.z, sa[a]);
-            sa[a] = fmaf(hv.w, wv.w, sa[a]);
-          }
-        }
-        const float* nz = sNoise + ((s & 1) * A * EB + i * EB + e) * 8;
-        float m = -INFINITY;
-#pragma unroll
-        for (int a = 0; a < 5; ++a) {
-          const float o = __shfl_xor_sync(0xffffffffu, sa[a], 1);
-          act[a] = ((sa[a] + o) + b3[a]) + nz[a];  // units [0, 32) + units [32, 64): the same value on both lanes
-          m = fmaxf(m, act[a]);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int a = 0; a < 5; ++a) { act[a] = expf(act[a] - m); sum += act[a]; }
-#pragma unroll
-        for (int a = 0; a < 5; ++a) act[a] = act[a] / sum;
-        if (par == 0 && e < nE) {
-          float* arow = buf + e * RS + L.obs_sum + 5 * i;
-#pragma unroll
-          for (int a = 0; a < 5; ++a) arow[a] = act[a];
-        }
-      }
-      // ---- World.step for (env e, agent i): needs the other agents' OLD positions only
-      {
-        real px[A], py[A];
-#pragma unroll
-        for (int j = 0; j < A; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + e]; py[j] = T.sS[(4 * j + 1) * EBP + e]; }
-        S.step(i, px, py, pxi, pyi, vxi, vyi, act);
-        phys_bar();
-        if (par == 0) { T.sS[(4 * i + 0) * EBP + e] = pxi; T.sS[(4 * i + 1) * EBP + e] = pyi; }
-        pos_bar();
-#pragma unroll
-        for (int j = 0; j < A; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + e]; py[j] = T.sS[(4 * j + 1) * EBP + e]; }
-        // ---- Scenario.observation: parity 0 writes the replay-row copies, parity 1 the layer-1 operand images of step s+1
-        const uint32_t p1 = par ? oImg : smem_u32(buf + e * RS + L.nx_off + i * D);
-        const uint32_t p2 = par ? oImg + IMG : smem_u32(nxt + e * RS + i * D);
-        obs_agent<A, real>(
-            i, px, py, pxi, pyi, vxi, vyi, lx, ly,
-            [&](int c, float v) {
-              const uint32_t o = cofs[c >> 2] + (uint32_t)((c & 3) << 2);
-              st_s32(p1 + o, v);
-              st_s32(p2 + o, par ? tf32_lo(v) : v);
-            },
-            [&](int c, float v) {
-              const uint32_t o = (uint32_t)((((c >> 2) ^ x7) << 4) | ((c & 3) << 2));
-              st_s32(p1 + o, v);
-              st_s32(p2 + o, par ? tf32_lo(v) : v);
-            });
-      }
-      umma::fence_async_smem();  // images -> UMMA (async proxy), replay rows -> TMA bulk store
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_obs[i]);
-      row_arrive();
-    }
-    // registers -> state tile (positions are current there already)
-    if (par == 0) { T.sS[(4 * i + 2) * EBP + e] = vxi; T.sS[(4 * i + 3) * EBP + e] = vyi; }
-  } else if (warp < 3 * A) {
-    // =================================== reward warps ========================================================================
-    const int i = warp - 2 * A, e = lane;
-    Spread<A, real> S;
-    S.init(P, i);
-    const real lxi = T.sS[(4 * A + 2 * i + 0) * EBP + e], lyi = T.sS[(4 * A + 2 * i + 1) * EBP + e];
-    float ret_reg = 0.f;
-    long long ring_row = (cursor + e0) % R.capacity;  // ring row of this CTA's first env at step s
-    const bool storer = warp == 2 * A && lane == 0;
-    for (int s = 0; s < R.steps; ++s) {
-      float* buf = sRow + (s & 1) * EB * RS;
-      if (s + 1 < R.steps && e < nE) {  // Gumbel noise of the next step, agent i
-        float* nz = sNoise + (((s + 1) & 1) * A * EB + i * EB + e) * 8;
-#pragma unroll
-        for (int a = 0; a < 5; ++a)
-          nz[a] = gumbel_from_u(philox_u(R.seed, counter + (unsigned long long)s + 2ull, (uint32_t)i, (long long)e0 + e, a));
-      }
-      // the bulk store of step s-1 must have finished READING the other buffer before the actor warps overwrite its obs columns
-      if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      pos_bar();
-      real px[A], py[A];
-#pragma unroll
-      for (int j = 0; j < A; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + e]; py[j] = T.sS[(4 * j + 1) * EBP + e]; }
-      const real mine = S.landmark_min(px, py, lxi, lyi);
-      const int cn = S.collisions(px, py, T.sS[(4 * i + 0) * EBP + e], T.sS[(4 * i + 1) * EBP + e]);
-      // partials through shared memory as float pairs (double: split into two words)
-      real* sp = reinterpret_cast<real*>(sPart);
-      if (sizeof(real) == 4) {
-        sPart[i * EB + e] = (float)mine;
-        sPart[(A + i) * EB + e] = __int_as_float(cn);
-      } else {
-        sp[i * EB + e] = mine;  // sPart holds 2 A EB floats = A EB doubles; counts go to sRet's tail below
-        reinterpret_cast<int*>(sRet)[i * EBP + e] = cn;
-      }
-      rew_bar();
-      real m[A];
-      int cnt[A];
-#pragma unroll
-      for (int j = 0; j < A; ++j) {
-        if (sizeof(real) == 4) { m[j] = (real)sPart[j * EB + e]; cnt[j] = __float_as_int(sPart[(A + j) * EB + e]); }
-        else { m[j] = sp[j * EB + e]; cnt[j] = reinterpret_cast<int*>(sRet)[j * EBP + e]; }
-      }
-      const float rsum = S.reward_sum(m, cnt);
-      if (e < nE) buf[e * RS + L.rw_off + i] = rsum;
-      ret_reg += rsum;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      row_sync();
-      if (storer) {
-        const long long r0 = ring_row;
-        ring_row += R.E;
-        if (ring_row >= R.capacity) ring_row -= R.capacity;  // capacity >= E * steps (checked on the host)
-        const long long first = min((long long)nE, R.capacity - r0);  // rows before the ring wraps
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(R.ring + r0 * RS), "r"(smem_u32(buf)),
-                     "r"((uint32_t)(first * RS * 4))
-                     : "memory");
-        if (first < nE)
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(R.ring), "r"(smem_u32(buf + first * RS)),
-                       "r"((uint32_t)((nE - first) * RS * 4))
-                       : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    }
-    if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncwarp();
-    rew_bar();
-    sRet[i * EBP + e] = ret_reg;
-  } else {
-    // =================================== MMA issuer ==========================================================================
-    constexpr uint32_t idesc = umma::idesc_tf32(128, EB, 0, 0);
-    for (int s = 0; s < R.steps; ++s) {
-#pragma unroll 1
-      for (int i = 0; i < A; ++i) {  // layer 1: D_i = W1_i^T x obs_i^T
-        if (s > 0) mbar_wait_b(&bar_obs[i], (uint32_t)((s - 1) & 1));
+      // The agent's even warp issues its MMAs (one elected lane): D_i = W^T x act^T as lo*hi + hi*lo + hi*hi, N = 32.
+      // (Splitting every GEMM into two N = 16 halves to overlap one half's epilogue with the other half's MMAs was measured
+      // and bought nothing: an N = 16 MMA is not faster than an N = 32 one here, the step got 2 % slower.)
+      constexpr uint32_t idesc = umma::idesc_tf32(128, EB, 0, 0);
+      const uint32_t tacc = tbase + CF::T_D + 32 * i;
+      auto pair_bar = [&] { asm volatile("bar.sync %0, 64;" ::"r"(1 + i) : "memory"); };
+      auto issue_l1 = [&] {  // layer 1: B = the observation images
         umma::fence_after();
         const uint32_t a_hi = tbase + CF::T_W1 + 2 * K1 * (i >> 1), a_lo = a_hi + K1;
-        const uint32_t tacc = tbase + CF::T_D + 32 * i;
         const uint64_t b_hi = umma::desc_k(sbase + CF::OFF_OBS + i * 2 * IMG, IMG, 0);
         const uint64_t b_lo = umma::desc_k(sbase + CF::OFF_OBS + i * 2 * IMG + IMG, IMG, 0);
         if (umma::elect_one()) {
@@ -560,13 +408,10 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
           umma::commit(&bar_l1[i]);
         }
         __syncwarp();
-      }
-#pragma unroll 1
-      for (int i = 0; i < A; ++i) {  // layer 2: D_i = W2_i^T x h1_i^T
-        mbar_wait_b(&bar_h1[i], (uint32_t)(s & 1));
+      };
+      auto issue_l2 = [&] {  // layer 2: B = the h1 images
         umma::fence_after();
         const uint32_t a_hi = tbase + CF::T_W2 + 128 * (i >> 1), a_lo = a_hi + 64;
-        const uint32_t tacc = tbase + CF::T_D + 32 * i;
         const uint64_t b_hi = umma::desc_k(sbase + CF::OFF_H + i * 4 * IMG, IMG, 0);
         const uint64_t b_lo = umma::desc_k(sbase + CF::OFF_H + i * 4 * IMG + 2 * IMG, IMG, 0);
         if (umma::elect_one()) {
@@ -580,40 +425,274 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
           umma::commit(&bar_l2[i]);
         }
         __syncwarp();
+      };
+      // epilogue: relu(acc + bias) of this thread's unit for the 32 env instances -> the hidden images
+      uint32_t hx[8];
+#pragma unroll
+      for (int n7 = 0; n7 < 8; ++n7) hx[n7] = hU + xo[n7];
+      auto epilogue = [&](float bias, bool with_lo) {
+        float v[32];
+        umma::tmem_ld32(tD, v);
+#pragma unroll
+        for (int n = 0; n < 32; ++n) {
+          const float x = fmaxf(v[n] + bias, 0.f);
+          const uint32_t a = hx[n & 7] + (uint32_t)(((n >> 3) << 10) + ((n & 7) << 7));
+          if (with_lo) {  // layer-2 operand: hi | lo images
+            float xh, xl;
+            split_rn(x, xh, xl);
+            st_s32(a, xh);
+            st_s32(a + 2 * IMG, xl);
+          } else {  // h2: plain fp32 for the head
+            st_s32(a, x);
+          }
+        }
+      };
+      if (h == 0) issue_l1();
+      TPROF_DECL
+      for (int s = 0; s < R.steps; ++s) {
+        const int g = g0 + s;
+        float* buf = sRow + (g & 1) * EB * RSP;
+        const uint32_t ph = (uint32_t)(g & 1);
+        // ---- epilogue 1: h1 = relu(acc + b1) -> hi | lo images (B operand of layer 2)
+        mbar_wait_b(&bar_l1[i], ph);
+        TPROF(0)
+        umma::fence_after();
+        epilogue(b1u, true);
+        umma::fence_before();
+        umma::fence_async_smem();
+        TPROF(1)
+        pair_bar();
+        if (h == 0) issue_l2();
+        TPROF(8)
+        // ---- epilogue 2: h2 = relu(acc + b2) -> fp32 image (read by the head below)
+        mbar_wait_b(&bar_l2[i], ph);
+        TPROF(2)
+        umma::fence_after();
+        epilogue(b2u, false);
+        umma::fence_before();
+        pair_bar();  // both warps of the agent: h2 rows are complete
+        TPROF(3)
+        // ---- output head on two threads per row (32 units each), then Gumbel-softmax (distributions.py:264-266)
+        float act[5];
+        {
+          float2 sa[5];
+#pragma unroll
+          for (int a = 0; a < 5; ++a) sa[a] = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int jj = j ^ (par << 2);  // the two lanes of a row walk the 16-byte chunks in different orders: no bank conflicts
+            const float4 hv = ld_s128(hR + (uint32_t)((jj ^ e7) << 4));
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+              const float4 wv = *reinterpret_cast<const float4*>(w3 + a * W3A + 4 * jj);
+              sa[a] = __ffma2_rn(make_float2(hv.x, hv.y), make_float2(wv.x, wv.y), sa[a]);
+              sa[a] = __ffma2_rn(make_float2(hv.z, hv.w), make_float2(wv.z, wv.w), sa[a]);
+            }
+          }
+          TPROF(11)
+          const float* nz = sNoise + ((g & 1) * A * EB + i * EB + e) * 8;
+          const float4 n4 = *reinterpret_cast<const float4*>(nz);
+          const float nzv[5] = {n4.x, n4.y, n4.z, n4.w, nz[4]};
+          float m = -INFINITY;
+#pragma unroll
+          for (int a = 0; a < 5; ++a) {
+            const float mine = sa[a].x + sa[a].y;
+            const float o = __shfl_xor_sync(0xffffffffu, mine, 1);
+            act[a] = ((par ? o + mine : mine + o) + b3[a]) + nzv[a];  // units [0, 32) + units [32, 64): the same value on both lanes
+            m = fmaxf(m, act[a]);
+          }
+          float sum = 0.f;
+#pragma unroll
+          for (int a = 0; a < 5; ++a) { act[a] = __expf(act[a] - m); sum += act[a]; }  // arguments <= 0: ex2.approx, ~2 ulp near 0
+          const float inv = 1.0f / sum;
+#pragma unroll
+          for (int a = 0; a < 5; ++a) act[a] = act[a] * inv;
+          if (par == 0 && e < nE) {
+            float* arow = buf + e * RSP + L.obs_sum + 5 * i;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) arow[a] = act[a];
+          }
+        }
+        TPROF(4)
+        // ---- World.step for (env e, agent i): needs the other agents' OLD positions only
+        {
+          real px[A], py[A];
+#pragma unroll
+          for (int j = 0; j < A; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + e]; py[j] = T.sS[(4 * j + 1) * EBP + e]; }
+          S.step(i, px, py, pxi, pyi, vxi, vyi, act);
+          TPROF(5)
+          phys_bar();
+          if (par == 0) { T.sS[(4 * i + 0) * EBP + e] = pxi; T.sS[(4 * i + 1) * EBP + e] = pyi; }
+          pos_bar();
+          TPROF(6)
+        }
+        // ---- Scenario.observation of agent i, this lane's component of every pair: [vel, pos, landmarks - pos, others - pos]
+        // (the silent agents' comm columns stay zero), straight into the layer-1 operand images of the next step
+        {
+          const real mp = par ? pyi : pxi, mv = par ? vyi : vxi;
+          auto put = [&](uint32_t off, float v) {
+            float vh, vl;
+            split_rn(v, vh, vl);
+            st_s32(oImg + off, vh);
+            st_s32(oImg + IMG + off, vl);
+          };
+          put(cofs[0], (float)mv);
+          put(cofs[0] + 8u, (float)mp);
+#pragma unroll
+          for (int l = 0; l < A; ++l) put(cofs[(2 + l) >> 1] + (uint32_t)(((2 + l) & 1) << 3), (float)(ml[l] - mp));
+#pragma unroll
+          for (int q = 0; q < A; ++q) {
+            if (q == i) continue;
+            const int k = NPR + (q < i ? q : q - 1);  // runtime pair index
+            const real oq = T.sS[(4 * q + par) * EBP + e];
+            put((uint32_t)((((k >> 1) ^ e7) << 4) | ((k & 1) << 3) | (par << 2)), (float)(oq - mp));
+          }
+        }
+        TPROF(7)
+        umma::fence_async_smem();  // images -> UMMA (async proxy)
+        TPROF(9)
+        pair_bar();
+        if (h == 0 && s + 1 < R.steps) issue_l1();
+        row_arrive();
+        TPROF(10)
       }
+      // registers -> state tile (positions are current there already)
+      if (par == 0) { T.sS[(4 * i + 2) * EBP + e] = vxi; T.sS[(4 * i + 3) * EBP + e] = vyi; }
+#ifdef MDP_EPISODE_PROF
+      if (R.ep_return && blockIdx.x == 0 && warp == 2 * MDP_PROF_AGENT && lane == 0)
+        for (int k = 0; k < 12; ++k) R.ep_return[(size_t)R.E * A + k] += (float)prof_t[k];  // caller over-allocates ep_return by 16 floats
+#endif
+    } else {
+      // =================================== reward warps ======================================================================
+      const int i = warp - 2 * A, e = lane, e7 = e & 7;
+      Spread<A, real> S;
+      S.init(P, i);
+      const real lxi = T.sS[(4 * A + 2 * i + 0) * EBP + e], lyi = T.sS[(4 * A + 2 * i + 1) * EBP + e];
+      float ret_reg = 0.f;
+      const bool storer = warp == 2 * A;  // lane e of this warp streams row e of every step to the ring
+      long long ring_row = (cursor + (long long)g0 * R.E + e0 + e) % R.capacity;
+      const uint32_t oImg = sbase + CF::OFF_OBS + i * 2 * IMG + (uint32_t)((e >> 3) << 10) + (uint32_t)(e7 << 7);
+      for (int s = 0; s < R.steps; ++s) {
+        const int g = g0 + s;
+        float* buf = sRow + (g & 1) * EB * RSP;
+        float* nxt = sRow + ((g & 1) ^ 1) * EB * RSP;
+        if (g + 1 < total_steps && e < nE) {  // Gumbel noise of the next step, agent i
+          float* nz = sNoise + (((g + 1) & 1) * A * EB + i * EB + e) * 8;
+#pragma unroll
+          for (int a = 0; a < 5; ++a)
+            nz[a] = gumbel_from_u(philox_u(R.seed, counter + (unsigned long long)g + 2ull, (uint32_t)i, (long long)e0 + e, a));
+        }
+        // the bulk stores of step g-1 must have finished READING the other buffer before its obs columns are overwritten below
+        if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        pos_bar();
+        real px[A], py[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) { px[j] = T.sS[(4 * j + 0) * EBP + e]; py[j] = T.sS[(4 * j + 1) * EBP + e]; }
+        const real mine = S.landmark_min(px, py, lxi, lyi);
+        const int cn = S.collisions(px, py, T.sS[(4 * i + 0) * EBP + e], T.sS[(4 * i + 1) * EBP + e]);
+        real* sp = reinterpret_cast<real*>(sPart);
+        sp[i * EB + e] = mine;
+        sCnt[i * EB + e] = cn;
+        rew_bar();
+        real m[A];
+        int cnt[A];
+#pragma unroll
+        for (int j = 0; j < A; ++j) { m[j] = sp[j * EB + e]; cnt[j] = sCnt[j * EB + e]; }
+        const float rsum = S.reward_sum(m, cnt);
+        buf[e * RSP + L.rw_off + i] = rsum;
+        ret_reg += rsum;
+        row_sync();  // every actor warp has written its observation images of step g + 1
+        // replay rows: next_obs of this step and obs_t of the next one are copies of agent i's observation image row
+        {
+          float* d1 = buf + e * RSP + L.nx_off + i * D;
+          float* d2 = nxt + e * RSP + i * D;
+#pragma unroll
+          for (int j = 0; j < (D + 3) / 4; ++j) {
+            const float4 vh = ld_s128(oImg + (uint32_t)((j ^ e7) << 4)), vl = ld_s128(oImg + IMG + (uint32_t)((j ^ e7) << 4));
+            const float4 v = make_float4(vh.x + vl.x, vh.y + vl.y, vh.z + vl.z, vh.w + vl.w);  // hi + lo == the observation, exactly
+            if (4 * j < D) {
+              *reinterpret_cast<float2*>(d1 + 4 * j) = make_float2(v.x, v.y);
+              *reinterpret_cast<float2*>(d2 + 4 * j) = make_float2(v.x, v.y);
+            }
+            if (4 * j + 2 < D) {
+              *reinterpret_cast<float2*>(d1 + 4 * j + 2) = make_float2(v.z, v.w);
+              *reinterpret_cast<float2*>(d2 + 4 * j + 2) = make_float2(v.z, v.w);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // replay rows -> TMA bulk store (async proxy)
+        rew_bar();
+        if (storer) {
+          if (e < nE)
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(R.ring + ring_row * RS),
+                         "r"(smem_u32(buf + e * RSP)), "r"((uint32_t)(RS * 4))
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          ring_row += R.E;
+          if (ring_row >= R.capacity) ring_row -= R.capacity;  // capacity >= E * steps * episodes (checked on the host)
+        }
+      }
+      if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      sRet[i * EBP + e] += ret_reg;
+    }
+
+    // ---- end of the episode: optional reset_world; after the last one hand state and observations back ------------------------
+    umma::fence_before();
+    __syncthreads();
+#ifdef MDP_EPISODE_PROF
+    k_loop += clock64() - k_t1;
+#endif
+    const int gn = g0 + R.steps;
+    float* fin = sRow + (gn & 1) * EB * RSP;  // obs of the next step lives in the obs_t columns of the next buffer
+    const bool last = ep + 1 == R.episodes;
+    if (R.reset_after) {
+      for (int idx = tid; idx < P.scomp * EB; idx += NTB) {
+        const int comp = idx / EB, e = idx % EB;
+        T.sS[comp * EBP + e] = env_reset_value<real>(P, comp, e0 + e, R.env_seed, episode + (unsigned long long)ep, R.lm_lo, R.lm_hi);
+      }
+      __syncthreads();
+      env_flags_rewards<real, EB, false>(P, T, nE);
+      for (int c = lane; c < L.obs_sum; c += 32) {
+        const ObsCol d = sCols[c];
+        const int i = c / D, cc = c - i * D;
+        unsigned char* img = smem + CF::OFF_OBS + i * 2 * IMG;
+        for (int ee = warp; ee < EB; ee += nwarps) {
+          const float v = ee < nE ? env_obs_value<real, EB>(T, d, ee) : 0.f;
+          fin[ee * RSP + c] = v;
+          if (!last) {
+            float vh, vl;
+            split_rn(v, vh, vl);
+            *reinterpret_cast<float*>(img + umma::sw128_off(ee, cc)) = vh;
+            *reinterpret_cast<float*>(img + IMG + umma::sw128_off(ee, cc)) = vl;
+          }
+        }
+      }
+      umma::fence_async_smem();
+      __syncthreads();
+    }
+    if (last) {
+      env_store_state<real, EB>(P, T, (real*)R.state, R.E, e0, nE, R.reset_after != 0);
+      for (int ee = warp; ee < nE; ee += nwarps)
+        for (int c = lane; c < OS; c += 32) R.obs[(size_t)(e0 + ee) * OS + c] = (c < L.obs_sum) ? fin[ee * RSP + c] : 0.f;
+      if (R.ep_return)
+        for (int idx = tid; idx < nE * A; idx += NTB) {
+          const int ee = idx / A, ii = idx - ee * A;
+          R.ep_return[(size_t)(e0 + ee) * A + ii] += sRet[ii * EBP + ee];
+        }
     }
   }
-
-  // ---- epilogue: optional reset_world, then hand state and observations back --------------------------------------------------
   umma::fence_before();
   __syncthreads();
-  if (warp == CF::NW - 1) {
+  if (warp == 0) {
     umma::fence_after();
     umma::tmem_free(tbase, CF::T_COLS);
   }
-  const int nwarps = NTB >> 5;
-  float* fin = sRow + (R.steps & 1) * EB * RS;  // obs_T lives in the obs columns of the next buffer
-  if (R.reset_after) {
-    for (int idx = tid; idx < P.scomp * EB; idx += NTB) {
-      const int comp = idx / EB, e = idx % EB;
-      T.sS[comp * EBP + e] = env_reset_value<real>(P, comp, e0 + e, R.env_seed, episode, R.lm_lo, R.lm_hi);
-    }
-    __syncthreads();
-    env_flags_rewards<real, EB, false>(P, T, nE);
-    for (int c = lane; c < L.obs_sum; c += 32) {
-      const ObsCol d = sCols[c];
-      for (int ee = warp; ee < nE; ee += nwarps) fin[ee * RS + c] = env_obs_value<real, EB>(T, d, ee);
-    }
-    __syncthreads();
+#ifdef MDP_EPISODE_PROF
+  if (R.ep_return && blockIdx.x == 0 && tid == 0) {
+    R.ep_return[(size_t)R.E * A + 12] = (float)(clock64() - k_t0 - k_loop);
+    R.ep_return[(size_t)R.E * A + 13] = (float)k_loop;
   }
-  env_store_state<real, EB>(P, T, (real*)R.state, R.E, e0, nE, R.reset_after != 0);
-  for (int ee = warp; ee < nE; ee += nwarps)
-    for (int c = lane; c < OS; c += 32) R.obs[(size_t)(e0 + ee) * OS + c] = (c < L.obs_sum) ? fin[ee * RS + c] : 0.f;
-  if (R.ep_return)
-    for (int idx = tid; idx < nE * A; idx += NTB) {
-      const int ee = idx / A, ii = idx - ee * A;
-      R.ep_return[(size_t)(e0 + ee) * A + ii] += sRet[ii * EBP + ee];
-    }
+#endif
 }
 
 template <int SA, typename real>

@@ -52,6 +52,7 @@ class BatchedRollout(object):
         # float64 state: only the tensor-core episode kernel serves it; run_mega() falls back to "graph" when it declines
         use_graph = self.mode != "eager"
         self.mega_launches = 0
+        self.episodes_per_launch = 1  # > 1: consecutive episodes share one launch (mdp_rollout_episodes)
         self.ep_return = None
         self.use_graph = use_graph
         self._graph = None
@@ -132,12 +133,39 @@ class BatchedRollout(object):
         self.ctl.dirty = True
         return True
 
+    def run_mega_episodes(self, n):
+        """n episodes (each followed by env.reset()) through mdp_rollout_episodes: ONE launch of the tcgen05 episode
+        kernel where it applies, else one launch per episode.  At most ``episodes_per_launch`` per call."""
+        env, core = self.env, self.core
+        ring, T = core.ring, self.max_episode_len
+        if not ring.aligned():
+            raise RuntimeError("the episode kernel needs index-aligned agents")
+        rc = _lib.lib.mdp_rollout_episodes(env._h, core._h, env.num_envs, _lib.ptr(env.state), _lib.ptr(env.obs),
+                                           _lib.ptr(ring.ring), ring.capacity, ring.row_stride, ring.next_idx[0], T, n,
+                                           core.seed, core.counter, env.seed, env.episode, _lib.ptr(self.ep_return),
+                                           _lib.current_stream())
+        if rc == _lib.MDP_ENOTSUP:
+            return False
+        _lib.check(rc, "mdp_rollout_episodes")
+        core.counter += T * n
+        ring.advance_all(env.num_envs * T * n)
+        env.episode += n
+        self.total_steps += T * n
+        self.mega_launches += 1
+        self.ctl.dirty = True
+        return True
+
     def run_episodes(self, n):
         if self.mode == "mega" and self.episode_step == 0:
-            for k in range(n):
-                if not self.run_mega(self.max_episode_len, True):
+            per = max(1, min(self.episodes_per_launch, self.core.ring.capacity // (self.env.num_envs * self.max_episode_len)))
+            k = 0
+            while k < n:
+                m = min(per, n - k)
+                ok = self.run_mega_episodes(m) if m > 1 else self.run_mega(self.max_episode_len, True)
+                if not ok:
                     self.mode = "graph"  # scenario does not fit the episode kernel
                     return self.run_episodes(n - k)
+                k += m
             return
         if not self.use_graph or self.episode_step != 0:
             return self.run_eager(n * self.max_episode_len)

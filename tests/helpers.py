@@ -158,3 +158,44 @@ def oracle_update_round(case):
                         q=[x.copy() for x in tr.q.p], p=[x.copy() for x in tr.p.p],
                         target_q=[x.copy() for x in tr.target_q.p], target_p=[x.copy() for x in tr.target_p.p]))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+def philox_uniform(seed, counter, tag, row0, nrows, ncols):
+    """The U[0,1) draws of the device kernels' Gumbel noise, on the host (include/maddpg_b200.h: mdp_philox_uniform)."""
+    import ctypes as C
+    from maddpg_b200 import _lib
+    out = np.empty((nrows, ncols), np.float32)
+    _lib.check(_lib.lib.mdp_philox_uniform(int(seed), int(counter), int(tag), int(row0), int(nrows), int(ncols),
+                                           out.ctypes.data_as(C.c_void_p)), "mdp_philox_uniform")
+    return out
+
+
+def oracle_free_rollout(scenario, num_agents, state, weights, seed, counter0, T):
+    """Free-running CPU replay of a device rollout: oracle MPE (float64) stepped with the oracle actor
+    (numpy float32 mlp_model + SoftCategoricalPd.sample) on the device's own Philox uniforms.
+    state: dict(agent_pos, agent_vel, landmark_pos) (E, ., 2) float64; weights[i] = [W1, b1, W2, b2, W3, b3].
+    Returns obs (T + 1, E, sum D) float64, act (T, E, sum K) float32, rew (T, E, A) float64."""
+    E = state["agent_pos"].shape[0]
+    env = ompe.BatchedOracleEnv(scenario, E, num_agents, seed=0)
+    env.set_state(state["agent_pos"], state["agent_vel"], state["landmark_pos"], None)
+    nets = []
+    for i, w in enumerate(weights):
+        m = omaddpg.MLP(w[0].shape[0], w[0].shape[1], w[4].shape[1], np.random.RandomState(0))
+        m.p = [np.asarray(x, np.float32) for x in w]
+        nets.append(m)
+    heads = [omaddpg.act_heads(s) for s in env.action_space]
+    obs_n = env.observe()
+    obs_t, act_t, rew_t = [np.concatenate(obs_n, axis=1)], [], []
+    for t in range(T):
+        acts = []
+        for i, m in enumerate(nets):
+            logits, _ = m.forward(obs_n[i].astype(np.float32))  # BatchInput feed cast (tf_util.py:98-112)
+            u = philox_uniform(seed, counter0 + t + 1, i, 0, E, env.act_dims[i])
+            acts.append(omaddpg.gumbel_softmax(logits, u, heads[i]))
+        obs_n, r, d = env.step(acts)
+        assert not d.any()
+        obs_t.append(np.concatenate(obs_n, axis=1))
+        act_t.append(np.concatenate(acts, axis=1))
+        rew_t.append(r)
+    return dict(obs=np.stack(obs_t), act=np.stack(act_t), rew=np.stack(rew_t))
