@@ -2,8 +2,10 @@
 """Benchmark of the MADDPG hot path on B200 (contract in the task statement; metric from BASELINE.json:
 "agent-env-steps/sec + critic updates/sec at 1/2/4/8 B200 vs CPU ref").
 
-Workload (BASELINE.json configs[1]): simple_spread N=3, 4096 lockstep env instances PER GPU (weak
+Workload (BASELINE.json configs[1], `--config 2`): simple_spread N=3, 4096 lockstep env instances PER GPU (weak
 scaling: env instances and replay shards are rank-local), batch 1024, num_units 64, maddpg/maddpg.
+`--config 3|4|5` runs configs[2..4] (simple_tag 16384 envs / batch 4096; simple_world_comm 65536 envs / num_units 128;
+simple_spread N=24 32768 envs per GPU) through the same sections.
 
   step            one lockstep rollout step of all env instances of a rank: grouped actor inference +
                   Gumbel-softmax sampling, fused MPE step, replay insert; device reset every 25 steps
@@ -15,10 +17,13 @@ scaling: env instances and replay shards are rank-local), batch 1024, num_units 
                   BatchedMultiAgentEnv.step / .experience / .update) with HOST numpy buffers: every H2D/D2H
                   copy is inside the timed region.
 
-Timing protocol: CUDA events on the launching stream; the timed region is cut into episodes (25 steps) /
-update rounds and the L2 is flushed (256 MB write, untimed) before each, so every episode starts cold; within
-an episode the 1.7 MB env state is re-read from L2 exactly as in a real rollout.  Multi-GPU numbers take the
-max over ranks of the summed device time, bracketed by barrier + synchronize.
+Timing protocol: CUDA events on the launching stream.  ONE timed repetition = exactly `--steps` lockstep steps
+(whole 25-step episodes, up to --episodes-per-launch of them per launch of the persistent episode kernel, plus one
+partial launch for the remainder), bracketed by barrier + synchronize, L2 flushed (256 MB write, untimed) before it;
+the repetition is run `reps` times and the MEDIAN is reported (max over ranks per repetition).  Update rounds: L2
+flushed before each round, median over rounds.
+
+`--impl reference` times the restated reference loop; one bench step of that arm = 100 env steps per replica.
 
 `--impl reference` times the restated reference loop (oracle/train_loop.py: numpy MPE + numpy trainer, one
 env, batch-1 actor calls) as `os.cpu_count()` independent single-threaded replicas on the host cores.
@@ -35,23 +40,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SCENARIO, N_AGENTS, ENVS_PER_GPU, BATCH, UNITS, EP_LEN = "simple_spread", 3, 4096, 1024, 64, 25
-WORKLOAD = "simple_spread N=3, 4096 envs per GPU, batch 1024, num_units 64, maddpg/maddpg (BASELINE.json configs[1])"
+EP_LEN = 25
+# BASELINE.json configs[1..4] (configs[0] is the reference's own 1-env CPU case: the reference arm's shape, not a bench line)
+CONFIGS = {
+    2: dict(scenario="simple_spread", agents=3, envs=4096, batch=1024, units=64,
+            name="simple_spread N=3, 4096 envs per GPU, batch 1024, num_units 64, maddpg/maddpg (BASELINE.json configs[1])"),
+    3: dict(scenario="simple_tag", agents=None, envs=16384, batch=4096, units=64,
+            name="simple_tag 3 adversaries + 1 good + 2 obstacles, 16384 envs per GPU, batch 4096, num_units 64 (BASELINE.json configs[2])"),
+    4: dict(scenario="simple_world_comm", agents=None, envs=65536, batch=1024, units=128,
+            name="simple_world_comm 6 agents (leader comm), 65536 envs per GPU, batch 1024, num_units 128 (BASELINE.json configs[3])"),
+    5: dict(scenario="simple_spread", agents=24, envs=32768, batch=1024, units=64,
+            name="simple_spread N=24, 32768 envs per GPU (262144 over 8 GPUs), batch 1024, num_units 64 (BASELINE.json configs[4])"),
+}
 METRIC, UNIT = "agent-env-steps/sec", "agent-env-steps/s"
+REF_ENV_STEPS_PER_STEP = 100  # reference arm: one bench "step" = this many env steps of the restated train.py loop per replica
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=2000, help="lockstep rollout steps in ONE timed repetition (honoured exactly)")
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[N-1]; 2 = the headline")
+    ap.add_argument("--reps", type=int, default=0, help="timed repetitions of the --steps region (median reported); 0 = auto")
+    ap.add_argument("--episodes-per-launch", type=int, default=8)
     ap.add_argument("--update-rounds", type=int, default=100)
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--rollout-mode", default="mega", choices=["mega", "graph", "eager"])
-    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--no-tensor-section", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true")
     return ap.parse_args()
@@ -67,21 +86,25 @@ def run_reference(args):
     for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[k] = "1"
     from oracle import train_loop as tl
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     steps, warm = max(1, args.steps), max(0, args.warmup)
+    per = REF_ENV_STEPS_PER_STEP  # a bench step of this arm = `per` env steps per replica (bounded sample of the workload)
     if warm:
-        tl.time_parallel("rollout", SCENARIO, N_AGENTS, warm, cores, BATCH, UNITS)
-    value, wall = tl.time_parallel("rollout", SCENARIO, N_AGENTS, steps, cores, BATCH, UNITS)
-    rounds = max(2, min(20, steps // 100))
-    upd, upd_wall = tl.time_parallel("updates", SCENARIO, N_AGENTS, rounds, cores, BATCH, UNITS)
-    sample = ("%d single-threaded replicas of the restated train.py loop (numpy MPE + numpy trainer, 1 env each), "
-              "%d env steps each after %d warm-up; updates: %d forced rounds x %d agents each" %
-              (cores, steps, warm, rounds, N_AGENTS))
+        tl.time_parallel("rollout", cfg["scenario"], cfg["agents"], warm * per, cores, cfg["batch"], cfg["units"])
+    value, wall = tl.time_parallel("rollout", cfg["scenario"], cfg["agents"], steps * per, cores, cfg["batch"], cfg["units"])
+    rounds = max(2, min(20, steps))
+    upd, upd_wall = tl.time_parallel("updates", cfg["scenario"], cfg["agents"], rounds, cores, cfg["batch"], cfg["units"])
+    n_ag = {2: 3, 3: 4, 4: 6, 5: 24}[args.config]
+    sample = ("%d single-threaded replicas of the restated train.py loop (numpy MPE + numpy trainer, 1 env each; the reference "
+              "is single-threaded by construction, tf_util.py:202-204), %d steps x %d env steps each after %d x %d warm-up; "
+              "updates: %d forced rounds x %d agents per replica" % (cores, steps, per, warm, per, rounds, n_ag))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": 1e3 * N_AGENTS * cores / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 env / f32 nets", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_path": "oracle/train_loop.py (TF-free restatement; real train.py "
+        "config": {"workload": cfg["name"], "env_steps_per_bench_step_per_replica": per,
+                   "reference_path": "oracle/train_loop.py (TF-free restatement; real train.py "
                    "needs tensorflow 1.8 + gym + MPE, not installable here)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -161,6 +184,33 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_from_profile(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the newest tracked `ncu --set full` summary (profiles/*.txt, written by
+    tools/ncu_summary.py) that holds a launch of `kernel_substr`.  Returns (bytes or None, source)."""
+    import glob
+    import re
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    best = (None, "no tracked ncu summary holds this kernel")
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*.txt"))):
+        try:
+            text = open(path).read()
+        except OSError:
+            continue
+        for blk in text.split("\nkernel: ")[1:]:
+            if kernel_substr not in blk.splitlines()[0]:
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                m = re.search(r"^\s*%s\s+([0-9.,]+)\s+(\w+)" % re.escape(key), blk, re.M)
+                if not m:
+                    tot = None
+                    break
+                tot += float(m.group(1).replace(",", "")) * mult.get(m.group(2), 1.0)
+            if tot is not None:
+                best = (tot, "ncu --set full, %s (dram__bytes_read.sum + dram__bytes_write.sum of one launch)" % os.path.relpath(path, ROOT))
+    return best
+
+
 def tensor_core_section(torch, dev):
     """Grouped TD-target launch (maddpg.py:181-187 for all agents) at the simple_spread N=24 update shape, tcgen05 kernel
     vs the fp32 SIMT kernel, CUDA events on the launching stream, L2 flushed before every launch."""
@@ -180,7 +230,7 @@ def tensor_core_section(torch, dev):
     flops = 2 * (Fpi + Fq) * B * NA
     out = {"workload": "simple_spread N=24 update shape per GPU (BASELINE.json configs[4]): grouped TD target of 24 agents, "
                        "batch 1024, critic input 3576, num_units 64", "algorithmic_flops_per_launch": flops, "bound": "tensor",
-           "peak_tf32_dense_tflops_nominal": 1100.0, "mma_issue_multiplier": 3,
+           "mma_issue_multiplier": 3,
            "note": "every GEMM is issued as 3 kind::tf32 MMAs (hi/lo split) to hold the 1e-4 parity bar; tensor-pipe "
                    "activity from ncu: profiles/r1_update_tc_cfg5_grouped.txt"}
     for name, mode in (("tcgen05", 1), ("simt_fp32", -1)):
@@ -197,7 +247,15 @@ def tensor_core_section(torch, dev):
         us = sum(a.elapsed_time(b) for a, b in evs) * 1e3 / len(evs)
         out[name] = {"avg_launch_us": us, "achieved_tflops": flops / us / 1e6}
     out["speedup_vs_simt"] = out["simt_fp32"]["avg_launch_us"] / out["tcgen05"]["avg_launch_us"]
-    out["frac"] = 3 * out["tcgen05"]["achieved_tflops"] / 1100.0
+    # kind::tf32 runs at half the bf16 rate: the roofline is MEASURED_PEAKS.json's cuBLAS bf16 burst figure / 2
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        src = "measured bf16 burst / 2 (MEASURED_PEAKS.json)"
+    except Exception:
+        bf16, src = 2250.0, "fallback: nominal bf16 / 2 (B200_PROFILING.md)"
+    out["peak_tf32_tflops"], out["peak_source"] = bf16 / 2, src
+    out["frac_algorithmic"] = out["tcgen05"]["achieved_tflops"] / (bf16 / 2)
+    out["frac"] = 3 * out["tcgen05"]["achieved_tflops"] / (bf16 / 2)  # issued MMA work (3 per product) over the tf32 peak
     # the whole grouped (Jacobi) round at the same shape: TD target + critic forward/backward on tcgen05, actor step on SIMT
     rnd = {}
     for name, mode in (("tcgen05", 1), ("simt_fp32", -1)):
@@ -225,6 +283,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import math
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -232,6 +291,9 @@ def main():
     from maddpg_b200.distributed import DataParallelUpdater, rank_seed
     from maddpg_b200.rollout import BatchedRollout, GraphedUpdateRound
 
+    cfg = CONFIGS[args.config]
+    SCENARIO, N_AGENTS, BATCH, UNITS, WORKLOAD = cfg["scenario"], cfg["agents"], cfg["batch"], cfg["units"], cfg["name"]
+    headline = args.config == 2
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -239,19 +301,25 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    E, A = args.envs, N_AGENTS
-    K, W = max(EP_LEN, args.steps // EP_LEN * EP_LEN), max(3, args.warmup)
+    E = args.envs or cfg["envs"]
+    K, W = max(1, args.steps), max(3, args.warmup)
+    reps = args.reps or min(50, max(5, int(math.ceil(1000.0 / K))))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
+    def max_over_ranks(xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return t.cpu().tolist()
+
+    def median(xs):
+        xs = sorted(xs)
+        n = len(xs)
+        return xs[n // 2] if n % 2 else 0.5 * (xs[n // 2 - 1] + xs[n // 2])
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -259,9 +327,12 @@ def main():
         flush_buf.fill_(1.0)
 
     # ---- build the experiment exactly like train.py:80-85 (env, trainers) on this rank's shard -------------
+    eps_launch = max(1, args.episodes_per_launch)
+    cap = max(1000000, E * EP_LEN * (eps_launch + 1))  # the reference's 1e6 rows (maddpg.py:147), at least one launch deep
     arglist = argparse.Namespace(lr=1e-2, gamma=0.95, batch_size=BATCH, num_units=UNITS, max_episode_len=EP_LEN,
-                                 seed=0, device=str(dev))
+                                 seed=0, device=str(dev), replay_capacity=cap)
     env = BatchedMultiAgentEnv(SCENARIO, num_envs=E, num_agents=N_AGENTS, device=dev, seed=rank_seed(0, rank), squeeze=False)
+    A = env.n
     obs_shape_n = [env.observation_space[i].shape for i in range(env.n)]
     trainers = [MADDPGAgentTrainer("agent_%d" % i, None, obs_shape_n, env.action_space, i, arglist) for i in range(env.n)]
     core = trainers[0].core
@@ -282,32 +353,72 @@ def main():
     else:
         dp = DataParallelUpdater(core)
     dp.broadcast_params(core.params)
-    roll = BatchedRollout(env, core, EP_LEN, mode=args.rollout_mode)
-    env.reset()
 
-    # ---- (1) device-resident rollout -----------------------------------------------------------------------
+    # ---- (1) device-resident rollout: exactly K lockstep steps per repetition, median over repetitions ---------
+    def run_steps(roll, n):
+        """n lockstep steps: whole episodes (each ends with env.reset(), train.py:127-129) + a partial episode."""
+        full, rem = divmod(n, EP_LEN)
+        if roll.mode == "mega":
+            if full:
+                roll.run_episodes(full)
+            if rem and roll.mode == "mega":
+                if not roll.run_mega(rem, reset_after=False):
+                    roll.mode = "graph"
+                    roll.run_eager(rem)
+            elif rem:
+                roll.run_eager(rem)
+        else:
+            roll.run(full * EP_LEN)
+            if rem:
+                roll.run_eager(rem)
+
+    def time_rollout(roll):
+        run_steps(roll, max(W, EP_LEN))
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        l0 = _lib.launch_count() + roll.graph_launches
+        for e0, e1 in evs:
+            flush_l2()
+            barrier()
+            e0.record()
+            run_steps(roll, K)
+            e1.record()
+        barrier()
+        launches = (_lib.launch_count() + roll.graph_launches - l0) // reps
+        ms = max_over_ranks(a.elapsed_time(b) for a, b in evs)
+        return median(ms), ms, launches
+
+    roll = BatchedRollout(env, core, EP_LEN, mode=args.rollout_mode)
+    roll.episodes_per_launch = eps_launch
+    env.reset()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    roll.run(max(W, EP_LEN) // EP_LEN * EP_LEN)
-    barrier()
     sampler.wait_first(3.0)
-    n_eps = K // EP_LEN
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_eps)]
-    l0 = _lib.launch_count() + roll.graph_launches
-    barrier()
-    for e0, e1 in evs:
-        flush_l2()
-        e0.record()
-        roll.run(EP_LEN)
-        e1.record()
-    barrier()
-    launches_roll = _lib.launch_count() + roll.graph_launches - l0
-    roll_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    roll_ms, roll_all_ms, launches_roll = time_rollout(roll)
     value = E * A * K * world / (roll_ms * 1e-3)
+    ep_kernel = "per-step kernels (CUDA graph)" if roll.mode != "mega" else \
+        ("k_rollout_episode_tc<%d,float>" % A if (SCENARIO == "simple_spread" and 2 <= A <= 4 and UNITS == 64) else "k_rollout_episode")
+
+    # ---- (1b) the same rollout with the reference's float64 env state (the mode of the 1e-5 parity contract) ----
+    f64 = None
+    if headline:
+        env64 = BatchedMultiAgentEnv(SCENARIO, num_envs=E, num_agents=N_AGENTS, device=dev, seed=rank_seed(0, rank),
+                                     squeeze=False, state_dtype=torch.float64)
+        roll64 = BatchedRollout(env64, core, EP_LEN, mode="mega")
+        roll64.episodes_per_launch = eps_launch
+        env64.reset()
+        ms64, all64, l64 = time_rollout(roll64)
+        f64 = {"value": E * A * K * world / (ms64 * 1e-3), "unit": UNIT, "ms_per_step": ms64 / K, "rollout_mode": roll64.mode,
+               "kernel": "k_rollout_episode_tc<%d,double>" % A if roll64.mode == "mega" else "per-step kernels",
+               "note": "positions / velocities / contact forces / rewards in float64 like MPE's numpy state, observations emitted "
+                       "as float32 (the reference's placeholder cast); tests/test_rollout_tc_gpu.py replays this mode free-running "
+                       "against the float64 oracle"}
+        del env64, roll64
+        torch.cuda.empty_cache()
 
     # ---- (2) env-step kernel alone (roofline) ----------------------------------------------------------------
-    reps, per = 20, EP_LEN - 1  # an even number of launches keeps the observation double buffer in phase
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    reps_k, per = 20, EP_LEN - 1  # an even number of launches keeps the observation double buffer in phase
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps_k)]
     env_graph = None
     if not args.no_graph:
         env_graph = torch.cuda.CUDAGraph()
@@ -325,13 +436,14 @@ def main():
                 env.step_device()
         b.record()
     torch.cuda.synchronize()
-    env_us = sum(a.elapsed_time(b) for a, b in kev) * 1e3 / (reps * per)
+    env_us = median([a.elapsed_time(b) for a, b in kev]) * 1e3 / per
     peak, peak_src = measured_peak_hbm()
     env_bytes = env.env_bytes_per_step * E
     achieved = env_bytes / (env_us * 1e-6) / 1e9
+    env_kernel = "k_env_step_spread<%d>" % A if (SCENARIO == "simple_spread" and A <= 6) else "k_env_step<float> (table-driven)"
     # the same per-step kernel where it is actually HBM-sized: 2^20 env instances (431 MB per step)
     big = None
-    if rank == 0 and not args.no_graph:
+    if headline and rank == 0 and not args.no_graph:
         EL = 1 << 20
         envL = BatchedMultiAgentEnv(SCENARIO, num_envs=EL, num_agents=N_AGENTS, device=dev, squeeze=False)
         envL.reset_device()
@@ -347,17 +459,17 @@ def main():
         torch.cuda.synchronize()
         usL = a.elapsed_time(b) * 1e3 / 10
         bytesL = envL.env_bytes_per_step * EL
+        trafficL, trafficL_src = traffic_from_profile("k_env_step_spread")
         big = {"kernel": "k_env_step_spread<3>", "envs": EL, "bound": "hbm", "achieved": bytesL / usL / 1e3, "peak": peak,
                "unit": "GB/s", "frac": bytesL / usL / 1e3 / peak, "algorithmic_bytes_per_launch": bytesL, "avg_launch_us": usL,
-               "traffic": 383.4e6, "traffic_source": "ncu --set full, profiles/r1_env_step_spread_1M.txt (dram read 142.7 MB + write "
-               "240.7 MB per launch; the tail of the writes is still in L2 when the launch ends)",
+               "traffic": trafficL, "traffic_source": trafficL_src,
                "note": "register-resident one-thread-per-env kernel (simple_spread fast path); the table-driven kernel serves the other scenarios"}
         del envL
         torch.cuda.empty_cache()
 
     # ---- (3) critic updates: sequential agent updates on gathered batches ------------------------------------
     while core.ring.length[0] < BATCH * EP_LEN:  # the reference's warm-up gate (maddpg.py:148,162)
-        roll.run(EP_LEN)
+        run_steps(roll, EP_LEN)
     R = max(1, args.update_rounds)
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
 
@@ -368,48 +480,59 @@ def main():
     _, batch = core._scratch(BATCH)
 
     fused = world == 1 or exchange == "fused-peer"
-    gupd = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph) if fused else None
 
-    def update_round(r):
-        if gupd is not None:  # single GPU: device-side index draw + gather + 5 update kernels per agent, graph-replayed
-            return gupd.run(1)
-        for j in range(A):
-            dp.update_agent(j, core.ring.ring, idx=idx_pool[r % 8][j])  # gather fused into the kernels
-
-    for r in range(3):
-        update_round(r)
-    barrier()
-    uev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
-    l0 = _lib.launch_count() + (gupd.graph_launches if gupd else 0)
-    for r, (a, b) in enumerate(uev):
-        flush_l2()
-        a.record()
-        update_round(r)
-        b.record()
-    barrier()
-    launches_upd = _lib.launch_count() + (gupd.graph_launches if gupd else 0) - l0
-    upd_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in uev))
-    upd_value = R * A * world / (upd_ms * 1e-3)
-    # ---- (3b) grouped ("Jacobi") rounds: all agents per launch -- throughput mode, documented deviation ----------
-    grp_value = grp_ms = None
-    if fused:
-        ggrp = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph, grouped=True)
+    def time_updates(make_round, rounds):
+        rnd = make_round()
         for r in range(3):
-            ggrp.run(1)
+            rnd(r)
         barrier()
-        gev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(R)]
-        for a, b in gev:
+        uev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(rounds)]
+        l0 = _lib.launch_count()
+        for r, (a, b) in enumerate(uev):
             flush_l2()
             a.record()
-            ggrp.run(1)
+            rnd(r)
             b.record()
         barrier()
-        grp_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in gev))
-        grp_value = R * A * world / (grp_ms * 1e-3)
+        ms = max_over_ranks(a.elapsed_time(b) for a, b in uev)
+        return median(ms), sum(ms)
+
+    gupd = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph) if fused else None
+
+    def seq_round():
+        if gupd is not None:  # device-side index draw + gather + update kernels per agent, graph-replayed
+            return lambda r: gupd.run(1)
+        return lambda r: [dp.update_agent(j, core.ring.ring, idx=idx_pool[r % 8][j]) for j in range(A)]
+
+    upd_med_ms, upd_sum_ms = time_updates(seq_round, R)
+    launches_upd = (gupd.launches_per_graph if gupd is not None and gupd.use_graph else 0)
+    upd_value = A * world / (upd_med_ms * 1e-3)
+    # ---- (3b) grouped ("Jacobi") rounds: all agents per launch -- throughput mode, documented deviation ----------
+    grp_value = grp_ms = None
+    ggrp = None
+    if fused:
+        ggrp = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph, grouped=True)
+        grp_ms, _ = time_updates(lambda: (lambda r: ggrp.run(1)), R)
+        grp_value = A * world / (grp_ms * 1e-3)
+    # ---- (3c) N > 1: the same rounds with the exchange switched off (every rank steps on its own gradients): the
+    #      single-GPU rate on THIS rank and therefore the efficiency of the gradient exchange --------------------------
+    noex = None
+    if world > 1 and fused:
+        dp.set_exchange(False)
+        g1 = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph)
+        m1, _ = time_updates(lambda: (lambda r: g1.run(1)), max(10, R // 2))
+        g2 = GraphedUpdateRound(core, BATCH, ctl=roll.ctl, use_graph=not args.no_graph, grouped=True)
+        m2, _ = time_updates(lambda: (lambda r: g2.run(1)), max(10, R // 2))
+        dp.set_exchange(True)
+        dp.broadcast_params(core.params)  # the replicas diverged while the exchange was off
+        noex = {"sequential_ms_per_round": m1, "grouped_ms_per_round": m2,
+                "sequential_efficiency": m1 / upd_med_ms, "grouped_efficiency": m2 / grp_ms,
+                "note": "the same update rounds on the same GPUs with the gradient exchange off (every rank steps on its local "
+                        "gradients): efficiency = time without / time with the exchange = N-GPU rate / (N x single-GPU rate)"}
     clocks = sampler.stop()
 
     # ---- (4) end to end through the reference-shaped API with host buffers ------------------------------------
-    Ke = max(EP_LEN, args.e2e_steps // EP_LEN * EP_LEN)
+    Ke = max(EP_LEN, args.e2e_steps // EP_LEN * EP_LEN) if headline else EP_LEN
     obs_n = [o.cpu().numpy() for o in env.reset()]
     h2d = d2h = 0
 
@@ -434,7 +557,7 @@ def main():
     for _ in range(Ke):
         obs_n, ep = e2e_step(obs_n, ep)
     barrier()
-    percall_s = max_over_ranks(time.perf_counter() - t0)
+    percall_s = max_over_ranks([time.perf_counter() - t0])[0]
     percall_value = E * A * Ke * world / percall_s
     row_f = sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
     percall_h2d = 4 * E * (sum(env.obs_dims) + env.act_stride + row_f)   # action() obs, step() actions, experience() rows
@@ -443,7 +566,7 @@ def main():
     # observations, actors + env step + replay insert, one packed D2H of (actions, next obs, rewards, done)
     from maddpg_b200.rollout import HostRollout
     host = HostRollout(env, core)
-    Kh = max(EP_LEN, (4 * args.e2e_steps) // EP_LEN * EP_LEN)
+    Kh = max(EP_LEN, (4 * args.e2e_steps) // EP_LEN * EP_LEN) if headline else 2 * EP_LEN
 
     def host_loop(n_steps):
         obs_n = host.reset()
@@ -461,10 +584,10 @@ def main():
     t0 = time.perf_counter()
     host_loop(Kh)
     barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_s = max_over_ranks([time.perf_counter() - t0])[0]
     e2e_value = E * A * Kh * world / e2e_s
     h2d, d2h = host.h2d_bytes_per_step, host.d2h_bytes_per_step
-    # e2e updates: trainer.update() per agent incl. python index draw, H2D of indices, D2H of the statistics
+    # e2e updates: MADDPGAgentTrainer.update() per agent through the reference-shaped API
     for tr in trainers:
         tr.max_replay_buffer_len = BATCH * EP_LEN
     import random
@@ -474,14 +597,16 @@ def main():
         tr.update(trainers, 100)
     barrier()
     t0 = time.perf_counter()
+    out = None
     for r in range(Re):
         for tr in trainers:
             tr.preupdate()
         for tr in trainers:
             out = tr.update(trainers, 100)
             assert out is not None
+    last_stats = [float(x) for x in out]  # the last update's statistics are read on the host (one D2H)
     barrier()
-    e2e_upd_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_upd_s = max_over_ranks([time.perf_counter() - t0])[0]
 
     # ---- (5) CPU baseline: the restated reference loop on this box's host cores (rank 0, N=1 only) -------------
     cpu = None
@@ -489,9 +614,9 @@ def main():
         for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
             os.environ[k] = "1"
         from oracle import train_loop as tl
-        cpu_steps, cpu_rounds = 40000, 150  # ~10-15 s of single-core work
-        a_sps, e_sps, dt = tl.time_rollout(SCENARIO, N_AGENTS, cpu_steps)
-        u_ps, udt = tl.time_updates(SCENARIO, N_AGENTS, cpu_rounds)
+        cpu_steps, cpu_rounds = (40000, 150) if headline else (4000, 10)  # ~10-15 s of single-core work
+        a_sps, e_sps, dt = tl.time_rollout(SCENARIO, N_AGENTS, cpu_steps, arglist=tl.make_arglist(SCENARIO, BATCH, UNITS))
+        u_ps, udt = tl.time_updates(SCENARIO, N_AGENTS, cpu_rounds, arglist=tl.make_arglist(SCENARIO, BATCH, UNITS))
         cpu = {"value": a_sps, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "%d env steps of the restated train.py loop (1 env, %.1f s) ; %d forced update rounds x %d agents "
                          "(%.1f s)" % (cpu_steps, dt, cpu_rounds, A, udt),
@@ -500,38 +625,60 @@ def main():
     # ---- (6) tensor-core TD-target kernel where the GEMMs are large enough to matter: BASELINE.json configs[4]'s
     #          per-GPU update shape (simple_spread N=24: 24 critics of input width 3576, 576 actor passes, batch 1024) ----------
     tensor = None
-    if rank == 0 and world == 1 and not args.no_tensor_section:
+    if headline and rank == 0 and world == 1 and not args.no_tensor_section:
         del flush_buf
         torch.cuda.empty_cache()
         tensor = tensor_core_section(torch, dev)
 
-    # dominant kernel of the timed rollout region: the persistent episode kernel (one launch = 25 steps)
+    # dominant kernel of the timed rollout region: the persistent episode kernel
     row_bytes = 4 * sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
-    ep_bytes = row_bytes * E * EP_LEN           # the replay rows are the only HBM traffic the algorithm needs
-    ep_us = roll_ms * 1e3 / max(1, n_eps)
-    actor_flops = 2 * sum(d * UNITS + UNITS * UNITS + UNITS * k for d, k in zip(env.obs_dims, env.act_dims)) * E * EP_LEN
+    launch_steps = min(K, EP_LEN * eps_launch) if roll.mode == "mega" else 1
+    step_us = roll_ms * 1e3 / K
+    ep_bytes = row_bytes * E * launch_steps     # the replay rows are the only HBM traffic the algorithm needs
+    actor_flops_step = 2 * sum(d * UNITS + UNITS * UNITS + UNITS * k for d, k in zip(env.obs_dims, env.act_dims)) * E
     sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
-    fp32_peak_tflops = 148 * 128 * 2 * sm_mhz * 1e-6  # 128 FP32 lanes per SM
-    ep_roof = {"kernel": "k_rollout_episode<64,true,3>" if roll.mode == "mega" else "per-step kernels", "bound": "hbm",
-               "achieved": ep_bytes / ep_us / 1e3, "peak": peak, "unit": "GB/s", "frac": ep_bytes / ep_us / 1e3 / peak,
-               "traffic": 5.28e6, "traffic_source": "ncu --set full, profiles/r1_episode_kernel_v3.txt (dram read 1.37 MB + write 3.91 MB per "
-               "launch; the 52.8 MB of ring rows stay in the 126 MB L2 past the end of the launch)", "peak_source": peak_src,
-               "algorithmic_bytes_per_launch": ep_bytes, "avg_launch_us": ep_us,
-               "note": "not HBM-bound: state, observations, actions and actor weights never leave shared memory; the actor "
-                       "layers run at 65 % of the FP32 pipe's measured FMA rate (clock64 phase profile in DESIGN.md, "
-                       "tools/fp32_probe.cu), the rest of a step is dependent-latency chains (head + Gumbel-softmax, physics)",
-               "fp32_fma_tflops": actor_flops / ep_us / 1e6, "fp32_peak_tflops": fp32_peak_tflops,
-               "fp32_frac": actor_flops / ep_us / 1e6 / fp32_peak_tflops}
+    fp32_peak_tflops = 148 * 113 * 2 * sm_mhz * 1e-6  # 113 FMA/clk/SM measured (tools/fp32_probe.cu), not the nominal 128
+    try:
+        bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        bf16 = 2250.0
+    traffic, traffic_src = traffic_from_profile("k_rollout_episode_tc" if "_tc" in ep_kernel else "k_rollout_episode")
+    ep_roof = {"kernel": ep_kernel, "bound": "hbm", "achieved": row_bytes * E / step_us / 1e3, "peak": peak, "unit": "GB/s",
+               "frac": row_bytes * E / step_us / 1e3 / peak, "traffic": traffic, "traffic_source": traffic_src,
+               "peak_source": peak_src, "algorithmic_bytes_per_launch": ep_bytes, "steps_per_launch": launch_steps,
+               "avg_launch_us": step_us * launch_steps,
+               "note": "not HBM-bound by construction: state, observations, actions and actor weights never leave the SM "
+                       "(shared / tensor memory); the replay rows are the only algorithmic HBM traffic.  The step is a dependent "
+                       "chain (MMA -> epilogue -> MMA -> epilogue -> head -> Gumbel-softmax -> World.step -> observation) over 32 "
+                       "env instances per SM -- see the clock64 phase table in DESIGN.md",
+               "actor_tflops": actor_flops_step / step_us / 1e6,
+               "tensor": {"bound": "tensor", "achieved": 3 * actor_flops_step / step_us / 1e6, "peak": bf16 / 2, "unit": "TFLOP/s",
+                          "frac": 3 * actor_flops_step / step_us / 1e6 / (bf16 / 2),
+                          "note": "issued kind::tf32 MMA work (3 per product, incl. the 64 x 5 head that runs on CUDA cores: upper "
+                                  "bound) over MEASURED_PEAKS.json bf16 / 2; tensor-pipe activity from ncu in profiles/"}
+               if "_tc" in ep_kernel else None,
+               "fp32_peak_tflops": fp32_peak_tflops}
     if rank == 0:
         flops_round = sum(int(core.layout.update_flops_critic[j]) + int(core.layout.update_flops_actor[j]) for j in range(A)) * BATCH
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": roll_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": E, "agents": A, "batch": BATCH, "episode_len": EP_LEN,
-                       "replay_capacity_rows": core.ring.capacity, "rollout_mode": roll.mode, "cuda_graph_updates": bool(gupd is not None and gupd.use_graph),
-                       "l2": "flushed (256 MB write) before every 25-step episode / update round; inside an episode the "
-                             "1.7 MB env state is L2-resident as in a real rollout"},
+            "dtype": "f32 (env state and nets; actor GEMMs as 3xTF32 on tcgen05 with fp32 accumulate) -- `value`; "
+                     "`value_f64_state` is the same rollout with the reference's float64 env state",
+            "data": "synthetic",
+            "value_f64_state": None if f64 is None else f64["value"],
+            "f64_state": f64,
+            "config": {"workload": WORKLOAD, "bench_config": args.config, "envs_per_gpu": E, "agents": A, "batch": BATCH,
+                       "num_units": UNITS, "episode_len": EP_LEN,
+                       "replay_capacity_rows": core.ring.capacity, "rollout_mode": roll.mode,
+                       "episodes_per_launch": eps_launch if roll.mode == "mega" else None,
+                       "cuda_graph_updates": bool(gupd is not None and gupd.use_graph),
+                       "timing": "one repetition = exactly `steps` lockstep steps (whole episodes incl. env.reset, + a partial "
+                                 "episode), CUDA events, barrier + synchronize on both sides; %d repetitions, median reported, max "
+                                 "over ranks per repetition" % reps,
+                       "repetitions_ms": roll_all_ms,
+                       "l2": "flushed (256 MB write) before every repetition / update round; inside a repetition the env state "
+                             "never leaves the SM"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Kh, "ms_per_step": 1e3 * e2e_s / Kh,
@@ -547,22 +694,23 @@ def main():
                                             "agent with pageable host numpy arrays (the reference's call granularity)"}},
             "gpu_launches": int(launches_roll),
             "roofline": ep_roof,
-            "roofline_env_step_kernel": {"kernel": "k_env_step_spread<3>", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline_env_step_kernel": {"kernel": env_kernel, "bound": "hbm", "achieved": achieved, "peak": peak,
                                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                                          "algorithmic_bytes_per_launch": env_bytes, "avg_launch_us": env_us,
-                                         "note": "per-step kernel of the reference-shaped API at the bench size (1.7 MB per "
-                                                 "launch: latency-bound, lives in L2)", "at_1M_envs": big},
-            "critic_updates": {"value": upd_value, "unit": "critic updates/s", "rounds": R, "ms_per_round": upd_ms / R,
+                                         "note": "per-step kernel of the reference-shaped API at the config's size",
+                                         "at_1M_envs": big},
+            "critic_updates": {"value": upd_value, "unit": "critic updates/s", "rounds": R, "ms_per_round": upd_med_ms,
                                "gpu_launches": int(launches_upd), "flops_per_round": flops_round,
-                               "achieved_tflops": flops_round * R / (upd_ms * 1e-3) / 1e12,
+                               "achieved_tflops": flops_round / (upd_med_ms * 1e-3) / 1e12,
                                "allreduce_bytes_per_round": 0 if world == 1 else 4 * int(core.layout.total_train),
-                               "gradient_exchange": exchange,
-                               "order": "sequential agents (reference order, parity mode)",
+                               "gradient_exchange": exchange, "exchange_efficiency": noex,
+                               "order": "sequential agents (reference order, parity mode); median over rounds",
                                "grouped": None if grp_value is None else {
-                                   "value": grp_value, "unit": "critic updates/s", "ms_per_round": grp_ms / R,
+                                   "value": grp_value, "unit": "critic updates/s", "ms_per_round": grp_ms,
                                    "order": "all agents per launch (Jacobi order; deviation documented in DESIGN.md)"},
-                               "e2e": {"value": Re * A * world / e2e_upd_s, "unit": "critic updates/s",
-                                       "api": "MADDPGAgentTrainer.update (python index draw + H2D idx + D2H stats)"}},
+                               "e2e": {"value": Re * A * world / e2e_upd_s, "unit": "critic updates/s", "last_stats": last_stats,
+                                       "api": "MADDPGAgentTrainer.update for every agent, %d rounds; statistics stay on the device "
+                                              "until read (the last round's are read on the host inside the timed region)" % Re}},
         }
         if tensor is not None:
             line["tensor_core_td_target"] = tensor

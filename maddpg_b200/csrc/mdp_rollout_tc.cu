@@ -277,37 +277,36 @@ __global__ void __launch_bounds__(Cfg<SA>::NTB, 1) k_rollout_episode_tc(CoreDev 
   __syncthreads();
   umma::fence_after();
   const uint32_t tbase = tmem_slot;
-  // the actors' weights: W1^T / W2^T into tensor memory (hi | lo), W3 transposed into shared memory
-  if (warp < 4) {
-    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-    const int half = warp >> 1, u = 32 * (warp & 1) + lane;
-#pragma unroll 1
-    for (int p = 0; p < CF::NPAIR; ++p) {
-      const int ag = 2 * p + half;
-      const MlpW w = C.agents[ag < A ? ag : 0].net[MDP_NET_P];
-      const bool live = ag < A;
-#pragma unroll 2
-      for (int k0 = 0; k0 < U; k0 += 16) {
-        float hi[16], lo[16];
+  // the actors' weights: W1^T / W2^T into tensor memory (hi | lo), W3 transposed into shared memory.  Warps [4p, 4p + 4) load
+  // agent pair p (lane quadrant = warp % 4); every thread first issues ALL its global loads (one unit column of W2 and W1:
+  // 64 + D independent loads, coalesced across the warp), so the whole image costs one memory round trip.
+  if (warp < 4 * CF::NPAIR) {
+    const int p = warp >> 2, q = warp & 3;
+    const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+    const int half = q >> 1, u = 32 * (q & 1) + lane;
+    const int ag = 2 * p + half;
+    const MlpW w = C.agents[ag < A ? ag : 0].net[MDP_NET_P];
+    const bool live = ag < A;
+    float x2[U], x1[K1];
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          const float x = live ? w.W2[(k0 + kk) * U + u] : 0.f;
-          split_rn(x, hi[kk], lo[kk]);
-        }
-        umma::tmem_st16(tbase + lane_base + CF::T_W2 + 128 * p + k0, hi);
-        umma::tmem_st16(tbase + lane_base + CF::T_W2 + 128 * p + 64 + k0, lo);
-      }
+    for (int k = 0; k < U; ++k) x2[k] = live ? w.W2[k * U + u] : 0.f;
 #pragma unroll
-      for (int k0 = 0; k0 < K1; k0 += 8) {
-        float hi[8], lo[8];
+    for (int k = 0; k < K1; ++k) x1[k] = (live && k < D) ? w.W1[k * U + u] : 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const float x = (live && k0 + kk < D) ? w.W1[(k0 + kk) * U + u] : 0.f;
-          split_rn(x, hi[kk], lo[kk]);
-        }
-        umma::tmem_st8(tbase + lane_base + CF::T_W1 + 2 * K1 * p + k0, hi);
-        umma::tmem_st8(tbase + lane_base + CF::T_W1 + 2 * K1 * p + K1 + k0, lo);
-      }
+    for (int k0 = 0; k0 < U; k0 += 16) {
+      float hi[16], lo[16];
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) split_rn(x2[k0 + kk], hi[kk], lo[kk]);
+      umma::tmem_st16(tbase + lane_base + CF::T_W2 + 128 * p + k0, hi);
+      umma::tmem_st16(tbase + lane_base + CF::T_W2 + 128 * p + 64 + k0, lo);
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < K1; k0 += 8) {
+      float hi[8], lo[8];
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) split_rn(x1[k0 + kk], hi[kk], lo[kk]);
+      umma::tmem_st8(tbase + lane_base + CF::T_W1 + 2 * K1 * p + k0, hi);
+      umma::tmem_st8(tbase + lane_base + CF::T_W1 + 2 * K1 * p + K1 + k0, lo);
     }
     umma::tmem_st_wait();
   }

@@ -73,10 +73,20 @@ class PeerGradExchange(object):
         torch.cuda.synchronize(dev)
         dist.barrier(group)  # every rank's buckets and flags are zero before anyone signals
         rp = (C.c_void_p * self.world)(*[int(p) for p in self.rh.buffer_ptrs]) if self.low_latency else None
-        _lib.check(_lib.lib.mdp_core_bind_peers(core._h, self.world, self.rank, gp, fp, _lib.ptr(self.epoch), rp), "mdp_core_bind_peers")
-        core.peer_world = self.world
+        self._tables = (gp, fp, rp)
+        self.open()
+
+    def open(self):
+        """(Re)binds the peer tables: from here on the optimizer kernels sum the gradient bucket over the ranks.  CUDA graphs
+        captured before a close()/open() pair hold stale table pointers and must be re-captured."""
+        gp, fp, rp = self._tables
+        _lib.check(_lib.lib.mdp_core_bind_peers(self.core._h, self.world, self.rank, gp, fp, _lib.ptr(self.epoch), rp),
+                   "mdp_core_bind_peers")
+        self.core.peer_world = self.world
 
     def close(self):
+        """Unbinds the peers: every rank steps on its own gradients (lock-step across ranks is the caller's business: all
+        ranks must close and re-open at the same point of their update sequence)."""
         self.core.peer_world = 1
         _lib.check(_lib.lib.mdp_core_bind_peers(self.core._h, 1, 0, None, None, None, None), "mdp_core_bind_peers")
 
@@ -93,6 +103,13 @@ class DataParallelUpdater(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.allreduce_bytes = 0
         self.peer = PeerGradExchange(core, group, low_latency) if (peer and self.world > 1) else None
+
+    def set_exchange(self, on):
+        """Fused peer exchange on / off (bench.py measures the same update rounds without it)."""
+        if self.peer is not None:
+            torch.cuda.synchronize(self.core.device)
+            dist.barrier(self.group)
+            (self.peer.open if on else self.peer.close)()
 
     def broadcast_params(self, params, adam_m=None, adam_v=None):
         """Replicas start from rank 0's weights (the reference initialises once, train.py:89)."""

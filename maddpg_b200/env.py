@@ -31,6 +31,27 @@ def _dims_for(scenario, num_agents=None, state_f64=False):
     return h, d
 
 
+class EnvBatchFloat(float):
+    """A per-agent reward of E lockstep env instances as the reference's loop needs it (train.py:123-125 adds it to python
+    floats): the float value is the mean over env instances, ``values`` the per-instance (E,) vector for ``experience``."""
+
+    def __new__(cls, mean, values):
+        x = float.__new__(cls, mean)
+        x.values = values
+        return x
+
+
+class EnvBatchFlag(object):
+    """A per-agent ``done`` of E env instances: truth value "every instance is done" (train.py:116 ``all(done_n)``; MPE
+    installs no done callback, so it is identically False), ``values`` the per-instance (E,) vector."""
+
+    def __init__(self, values):
+        self.values = values
+
+    def __bool__(self):
+        return False
+
+
 class BatchedMultiAgentEnv(object):
     def __init__(self, scenario, num_envs=1, num_agents=None, device="cuda", state_dtype=torch.float32, seed=0,
                  squeeze=None, benchmark=False):
@@ -46,6 +67,7 @@ class BatchedMultiAgentEnv(object):
         self.seed = int(seed)
         self.squeeze = (self.num_envs == 1) if squeeze is None else bool(squeeze)
         self.benchmark = bool(benchmark)  # make_env(..., benchmark=True): step() fills info_n (train.py:56-58)
+        self.reference_loop = False  # True: batched step() results are wrapped for the reference's unmodified loop
         self._h, d = _dims_for(scenario, num_agents, state_dtype == torch.float64)
         self.dims = d
         self.n = int(d.n_agents)
@@ -195,7 +217,12 @@ class BatchedMultiAgentEnv(object):
         host_io = self.squeeze or not (isinstance(action_n[0], torch.Tensor) and action_n[0].is_cuda)
         if not host_io:
             obs_n = self._split_obs(self.obs)
-            return obs_n, [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)], self._info_n()
+            rew_n, done_n = [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)]
+            if self.reference_loop:  # scalars for the loop's bookkeeping (one (n,) device-to-host copy), vectors for experience()
+                m = self.rew.mean(0).cpu().tolist()
+                rew_n = [EnvBatchFloat(m[i], rew_n[i]) for i in range(self.n)]
+                done_n = [EnvBatchFlag(d) for d in done_n]
+            return obs_n, rew_n, done_n, self._info_n()
         # one packed D2H copy: [obs | rew]; done is identically False in MPE (no done callback)
         self._d_out[:, :self.obs_stride].copy_(self.obs)
         self._d_out[:, self.obs_stride:].copy_(self.rew)

@@ -1,207 +1,209 @@
-"""experiments/train.py on the B200 kernels: same flags, same loop (reference train.py:78-189), with the
-environment and the trainers replaced by the device-backed drop-ins of this package.
+"""Runs the reference's OWN ``experiments/train.py`` -- unmodified, straight from the reference checkout -- on the B200
+kernels.  Nothing of that file is restated here: this module only installs stand-ins for the four imports the file makes and
+then executes it with ``runpy``:
 
-    python -m maddpg_b200.train --scenario simple_spread --num-episodes 1000            # reference shape (1 env)
-    python -m maddpg_b200.train --scenario simple_spread --num-envs 4096 --num-episodes 40960   # batched
+    reference import (experiments/train.py)                      stand-in
+    -----------------------------------------------------------  -------------------------------------------------------
+    import tensorflow as tf                    (:3)              inert module: tf.train.Saver() (:101) is a token object;
+    import tensorflow.contrib.layers as layers (:9)              mlp_model (:39-46) is never called -- the MLP is in the kernels
+    import maddpg.common.tf_util as U          (:7)              single_threaded_session / initialize (:79,89) no-ops,
+                                                                 save_state / load_state (:95,164) -> the .pt checkpoint below
+    from maddpg.trainer.maddpg import MADDPGAgentTrainer (:8)    maddpg_b200.MADDPGAgentTrainer
+    from multiagent.environment import MultiAgentEnv (:49)       maddpg_b200.BatchedMultiAgentEnv behind the same constructor
+    import multiagent.scenarios as scenarios   (:50)             scenarios.load(name + ".py").Scenario() -> a scenario token
 
-With ``--num-envs 1`` every call below has the reference's shapes (numpy in / numpy out).  With
-``--num-envs E > 1`` the same loop runs on CUDA tensors with a leading env axis: one loop iteration is E
-transitions, ``terminal`` is shared by all env instances, and rewards are summed over env instances for the
-episode statistics.
+    python -m maddpg_b200.train --reference-train /path/to/maddpg/experiments/train.py -- --scenario simple_spread --num-episodes 1000
+    python -m maddpg_b200.train --num-envs 4096 -- --scenario simple_spread --num-episodes 40960      # batched superset
+
+Options of this shim come BEFORE ``--``; everything after it is the reference's own command line (train.py:11-37).  With
+``--num-envs 1`` every call in the loop has the reference's shapes (numpy in / numpy out).  With ``--num-envs E > 1`` one
+loop iteration is E lockstep transitions: rewards reach the loop as floats (the mean over env instances) that carry the
+per-instance vector for ``experience``, ``done`` flags as objects whose truth value is "all instances done" (SURVEY H9).
 """
 import argparse
 import os
-import pickle
-import time
+import runpy
+import sys
+import types
 
 import numpy as np
 import torch
 
-from .env import make_env as _make_env
+from .env import BatchedMultiAgentEnv, SCENARIOS
 from .trainer import MADDPGAgentTrainer
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CANDIDATES = ("/root/reference/experiments/train.py", os.path.join(ROOT, "baseline", "_ref", "experiments", "train.py"))
 
-def parse_args(argv=None):
-    # experiments/train.py:11-37 (same names and defaults) + device-side knobs
-    parser = argparse.ArgumentParser("Reinforcement Learning experiments for multiagent environments")
-    parser.add_argument("--scenario", type=str, default="simple", help="name of the scenario script")
-    parser.add_argument("--max-episode-len", type=int, default=25, help="maximum episode length")
-    parser.add_argument("--num-episodes", type=int, default=60000, help="number of episodes")
-    parser.add_argument("--num-adversaries", type=int, default=0, help="number of adversaries")
-    parser.add_argument("--good-policy", type=str, default="maddpg", help="policy for good agents")
-    parser.add_argument("--adv-policy", type=str, default="maddpg", help="policy of adversaries")
-    parser.add_argument("--lr", type=float, default=1e-2, help="learning rate for Adam optimizer")
-    parser.add_argument("--gamma", type=float, default=0.95, help="discount factor")
-    parser.add_argument("--batch-size", type=int, default=1024, help="number of episodes to optimize at the same time")
-    parser.add_argument("--num-units", type=int, default=64, help="number of units in the mlp")
-    parser.add_argument("--exp-name", type=str, default=None, help="name of the experiment")
-    parser.add_argument("--save-dir", type=str, default="/tmp/policy/", help="directory in which training state and model should be saved")
-    parser.add_argument("--save-rate", type=int, default=1000, help="save model once every time this many episodes are completed")
-    parser.add_argument("--load-dir", type=str, default="", help="directory in which training state and model are loaded")
-    parser.add_argument("--restore", action="store_true", default=False)
-    parser.add_argument("--display", action="store_true", default=False)
-    parser.add_argument("--benchmark", action="store_true", default=False)
-    parser.add_argument("--benchmark-iters", type=int, default=100000, help="number of iterations run for benchmarking")
-    parser.add_argument("--benchmark-dir", type=str, default="./benchmark_files/", help="directory where benchmark data is saved")
-    parser.add_argument("--plots-dir", type=str, default="./learning_curves/", help="directory where plot data is saved")
-    # new (not in the reference)
-    parser.add_argument("--num-envs", type=int, default=1, help="lockstep env instances on the GPU")
-    parser.add_argument("--num-agents", type=int, default=None, help="simple_spread only: N agents = N landmarks")
-    parser.add_argument("--device", type=str, default="cuda")
-    parser.add_argument("--seed", type=int, default=0)
-    parser.add_argument("--replay-capacity", type=int, default=int(1e6))
-    return parser.parse_args(argv)
+# shim options (set by main() / run_reference_train); trainers and envs created by the reference's code read them
+OPTIONS = {"num_envs": 1, "num_agents": None, "device": "cuda", "seed": 0, "replay_capacity": int(1e6)}
+_LIVE = []  # trainers constructed by the running reference script (for U.save_state / U.load_state)
 
 
-def mlp_model(input, num_outputs, scope, reuse=False, num_units=64, rnn_cell=None):
-    """Signature placeholder of train.py:39-46: the 3-layer ReLU MLP lives in the CUDA kernels
-    (csrc/mdp_mlp.cuh); trainers accept this callable for signature parity and never call it."""
-    raise NotImplementedError("the MLP is evaluated by libmaddpg_b200; this callable only marks the architecture")
+def reference_train_path(path=None):
+    for p in ([path] if path else []) + [os.environ.get("MADDPG_REFERENCE_TRAIN", "")] + list(CANDIDATES):
+        if p and os.path.isfile(p):
+            return p
+    raise FileNotFoundError("the reference's experiments/train.py was not found; pass --reference-train PATH or set "
+                            "MADDPG_REFERENCE_TRAIN (looked in %s)" % (CANDIDATES,))
 
 
-def make_env(scenario_name, arglist, benchmark=False):
-    # train.py:48-61
-    return _make_env(scenario_name, arglist, benchmark, num_agents=getattr(arglist, "num_agents", None),
-                     device=getattr(arglist, "device", "cuda"))
-
-
-def get_trainers(env, num_adversaries, obs_shape_n, arglist):
-    # train.py:63-75 (adversaries first; local_q_func == ddpg)
-    trainers = []
-    model = mlp_model
-    trainer = MADDPGAgentTrainer
-    for i in range(num_adversaries):
-        trainers.append(trainer("agent_%d" % i, model, obs_shape_n, env.action_space, i, arglist,
-                                local_q_func=(arglist.adv_policy == "ddpg")))
-    for i in range(num_adversaries, env.n):
-        trainers.append(trainer("agent_%d" % i, model, obs_shape_n, env.action_space, i, arglist,
-                                local_q_func=(arglist.good_policy == "ddpg")))
-    return trainers
-
-
-def save_state(save_dir, trainers):
-    """U.save_state (tf_util.py:267-273): all variables incl. Adam slots (the replay ring is not saved,
-    like the reference)."""
-    core = trainers[0].core
+# -- checkpoints: U.save_state / U.load_state (tf_util.py:259-273) ---------------------------------------------------------------
+def save_state(save_dir, trainers=None, saver=None):
+    """All variables incl. Adam slots and the Philox stream position (the replay ring is not saved, like the reference)."""
+    core = (trainers or _LIVE)[0].core
     os.makedirs(save_dir, exist_ok=True)
     torch.save({"params": core.params.cpu(), "adam_m": core.adam_m.cpu(), "adam_v": core.adam_v.cpu(),
                 "adam_t": core.adam_t.cpu(), "obs_dims": core.obs_dims, "act_dims": core.act_dims,
-                "num_units": core.num_units}, os.path.join(save_dir, "maddpg_b200.pt"))
+                "num_units": core.num_units, "counter": core.counter, "seed": core.seed},
+               os.path.join(save_dir, "maddpg_b200.pt"))
 
 
-def load_state(load_dir, trainers):
-    """U.load_state (tf_util.py:259-265)."""
-    core = trainers[0].core
+def load_state(load_dir, trainers=None, saver=None):
+    core = (trainers or _LIVE)[0].core
     st = torch.load(os.path.join(load_dir, "maddpg_b200.pt"), map_location="cpu")
     assert st["obs_dims"] == core.obs_dims and st["act_dims"] == core.act_dims and st["num_units"] == core.num_units
     core.params.copy_(st["params"])
     core.adam_m.copy_(st["adam_m"])
     core.adam_v.copy_(st["adam_v"])
     core.adam_t.copy_(st["adam_t"])
+    core.counter = int(st.get("counter", 0))  # a restored run continues the noise stream instead of replaying it
+    core.seed = int(st.get("seed", core.seed))
 
 
-def _rew_scalar(r):
-    return float(r.sum().item()) if isinstance(r, torch.Tensor) else float(np.sum(r))
+# -- stand-in modules ---------------------------------------------------------------------------------------------------------
+class _ShimTrainer(MADDPGAgentTrainer):
+    """maddpg.trainer.maddpg.MADDPGAgentTrainer as the reference constructs it (train.py:63-75); the shim's device options
+    are attached to the reference's ``arglist`` namespace, which has no such flags."""
+
+    def __init__(self, name, model, obs_shape_n, act_space_n, agent_index, args, local_q_func=False):
+        for k in ("device", "seed", "replay_capacity"):
+            if not hasattr(args, k):
+                setattr(args, k, OPTIONS[k])
+        MADDPGAgentTrainer.__init__(self, name, model, obs_shape_n, act_space_n, agent_index, args, local_q_func=local_q_func)
+        _LIVE.append(self)
 
 
-def train(arglist):
-    # train.py:78-189
-    env = make_env(arglist.scenario, arglist, arglist.benchmark)
-    obs_shape_n = [env.observation_space[i].shape for i in range(env.n)]
-    num_adversaries = min(env.n, arglist.num_adversaries)
-    trainers = get_trainers(env, num_adversaries, obs_shape_n, arglist)
-    print("Using good policy {} and adv policy {}".format(arglist.good_policy, arglist.adv_policy))
-    if arglist.load_dir == "":
-        arglist.load_dir = arglist.save_dir
-    if arglist.display or arglist.restore or arglist.benchmark:
-        print("Loading previous state...")
-        load_state(arglist.load_dir, trainers)
+class _World(object):
+    def __init__(self, scenario_name):
+        self.scenario_name = scenario_name
 
-    episode_rewards = [0.0]
-    agent_rewards = [[0.0] for _ in range(env.n)]
-    final_ep_rewards = []
-    final_ep_ag_rewards = []
-    agent_info = [[[]]]
-    obs_n = env.reset()
-    episode_step = 0
-    train_step = 0
-    t_start = time.time()
 
-    print("Starting iterations...")
-    while True:
-        action_n = [agent.action(obs) for agent, obs in zip(trainers, obs_n)]
-        new_obs_n, rew_n, done_n, info_n = env.step(action_n)
-        episode_step += 1
-        done = all(bool(np.all(d.cpu().numpy())) if isinstance(d, torch.Tensor) else bool(np.all(d)) for d in done_n)
-        terminal = (episode_step >= arglist.max_episode_len)
-        for i, agent in enumerate(trainers):
-            agent.experience(obs_n[i], action_n[i], rew_n[i], new_obs_n[i], done_n[i], terminal)
-        obs_n = new_obs_n
+class _Scenario(object):
+    """multiagent.scenarios.<name>.Scenario as train.py:53-60 uses it: the callbacks are tokens, the physics, rewards
+    and observations they stand for run inside the env kernels (csrc/mdp_env_dev.cuh)."""
 
-        for i, rew in enumerate(rew_n):
-            r = _rew_scalar(rew)
-            episode_rewards[-1] += r
-            agent_rewards[i][-1] += r
+    def __init__(self, scenario_name):
+        self.scenario_name = scenario_name
 
-        if done or terminal:
-            obs_n = env.reset()
-            episode_step = 0
-            episode_rewards.append(0)
-            for a in agent_rewards:
-                a.append(0)
-            agent_info.append([[]])
+    def make_world(self):
+        return _World(self.scenario_name)
 
-        train_step += 1
+    def reset_world(self, world):
+        raise NotImplementedError("evaluated on the device by BatchedMultiAgentEnv.reset")
 
-        if arglist.benchmark:
-            for i, info in enumerate(info_n):
-                agent_info[-1][i].append(info_n["n"])
-            if train_step > arglist.benchmark_iters and (done or terminal):
-                file_name = arglist.benchmark_dir + arglist.exp_name + ".pkl"
-                print("Finished benchmarking, now saving...")
-                with open(file_name, "wb") as fp:
-                    pickle.dump(agent_info[:-1], fp)
-                break
-            continue
+    reward = observation = benchmark_data = reset_world
 
-        if arglist.display:
-            time.sleep(0.1)
-            env.render()
-            continue
 
-        loss = None
-        for agent in trainers:
-            agent.preupdate()
-        for agent in trainers:
-            loss = agent.update(trainers, train_step)
+def _multi_agent_env(world, reset_callback=None, reward_callback=None, observation_callback=None, info_callback=None,
+                     done_callback=None, shared_viewer=True):
+    """multiagent.environment.MultiAgentEnv(world, reset, reward, observation[, benchmark_data]) (train.py:57-60)."""
+    env = BatchedMultiAgentEnv(world.scenario_name, num_envs=OPTIONS["num_envs"], num_agents=OPTIONS["num_agents"],
+                               device=OPTIONS["device"], seed=OPTIONS["seed"], benchmark=info_callback is not None)
+    env.reference_loop = True
+    return env
 
-        if terminal and (len(episode_rewards) % arglist.save_rate == 0):
-            save_state(arglist.save_dir, trainers)
-            if num_adversaries == 0:
-                print("steps: {}, episodes: {}, mean episode reward: {}, time: {}".format(
-                    train_step, len(episode_rewards), np.mean(episode_rewards[-arglist.save_rate:]),
-                    round(time.time() - t_start, 3)))
-            else:
-                print("steps: {}, episodes: {}, mean episode reward: {}, agent episode reward: {}, time: {}".format(
-                    train_step, len(episode_rewards), np.mean(episode_rewards[-arglist.save_rate:]),
-                    [np.mean(rew[-arglist.save_rate:]) for rew in agent_rewards], round(time.time() - t_start, 3)))
-            t_start = time.time()
-            final_ep_rewards.append(np.mean(episode_rewards[-arglist.save_rate:]))
-            for rew in agent_rewards:
-                final_ep_ag_rewards.append(np.mean(rew[-arglist.save_rate:]))
 
-        if len(episode_rewards) > arglist.num_episodes:
-            os.makedirs(arglist.plots_dir, exist_ok=True)
-            rew_file_name = arglist.plots_dir + str(arglist.exp_name) + "_rewards.pkl"
-            with open(rew_file_name, "wb") as fp:
-                pickle.dump(final_ep_rewards, fp)
-            agrew_file_name = arglist.plots_dir + str(arglist.exp_name) + "_agrewards.pkl"
-            with open(agrew_file_name, "wb") as fp:
-                pickle.dump(final_ep_ag_rewards, fp)
-            print("...Finished total of {} episodes.".format(len(episode_rewards)))
-            break
-    return trainers, episode_rewards
+class _Session(object):
+    def __enter__(self):
+        del _LIVE[:]
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _module(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    m.__path__ = []  # importable as a package
+    return m
+
+
+def install_stubs():
+    """Puts the stand-ins into sys.modules (replacing a real tensorflow / maddpg / multiagent if one is importable).
+    Returns the previous entries so that remove_stubs can restore them."""
+    def unavailable(*a, **k):
+        raise NotImplementedError("TensorFlow graph construction is not part of the B200 path: the MLP of train.py:39-46 "
+                                  "is evaluated by libmaddpg_b200")
+    layers = _module("tensorflow.contrib.layers", fully_connected=unavailable)
+    contrib = _module("tensorflow.contrib", layers=layers)
+    tf = _module("tensorflow", contrib=contrib, variable_scope=unavailable,
+                 nn=types.SimpleNamespace(relu=unavailable), train=types.SimpleNamespace(Saver=lambda *a, **k: object()))
+    tf_util = _module("maddpg.common.tf_util", single_threaded_session=_Session, initialize=lambda: None,
+                      save_state=lambda fname, saver=None: save_state(fname, None, saver),
+                      load_state=lambda fname, saver=None: load_state(fname, None, saver))
+    common = _module("maddpg.common", tf_util=tf_util)
+    trainer_mod = _module("maddpg.trainer.maddpg", MADDPGAgentTrainer=_ShimTrainer)
+    trainer_pkg = _module("maddpg.trainer", maddpg=trainer_mod)
+    maddpg = _module("maddpg", common=common, trainer=trainer_pkg)
+    scen = _module("multiagent.scenarios")
+
+    def load(name):  # scenarios.load(scenario_name + ".py") (train.py:53)
+        base = name[:-3] if name.endswith(".py") else name
+        if base not in SCENARIOS:
+            raise NotImplementedError("scenario %r is not implemented (have %s)" % (base, SCENARIOS))
+        return types.SimpleNamespace(Scenario=lambda: _Scenario(base))
+    scen.load = load
+    environment = _module("multiagent.environment", MultiAgentEnv=_multi_agent_env)
+    multiagent = _module("multiagent", scenarios=scen, environment=environment)
+    mods = {"tensorflow": tf, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers, "maddpg": maddpg,
+            "maddpg.common": common, "maddpg.common.tf_util": tf_util, "maddpg.trainer": trainer_pkg,
+            "maddpg.trainer.maddpg": trainer_mod, "multiagent": multiagent, "multiagent.scenarios": scen,
+            "multiagent.environment": environment}
+    saved = {k: sys.modules.get(k) for k in mods}
+    sys.modules.update(mods)
+    return saved
+
+
+def remove_stubs(saved):
+    for k, v in saved.items():
+        if v is None:
+            sys.modules.pop(k, None)
+        else:
+            sys.modules[k] = v
+
+
+def run_reference_train(ref_argv, path=None, **options):
+    """Executes the reference's experiments/train.py as ``__main__`` with ``ref_argv`` as its command line.
+    options: num_envs, num_agents, device, seed, replay_capacity.  Returns the trainers the script constructed."""
+    path = reference_train_path(path)
+    OPTIONS.update({k: v for k, v in options.items() if v is not None})
+    saved = install_stubs()
+    argv0 = sys.argv
+    sys.argv = [path] + list(ref_argv)
+    try:
+        runpy.run_path(path, run_name="__main__")
+    finally:
+        sys.argv = argv0
+        remove_stubs(saved)
+    return list(_LIVE)
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    own, ref = (argv[:argv.index("--")], argv[argv.index("--") + 1:]) if "--" in argv else ([], argv)
+    ap = argparse.ArgumentParser("maddpg_b200.train", description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--reference-train", default=None, help="path of the reference's experiments/train.py")
+    ap.add_argument("--num-envs", type=int, default=1, help="lockstep env instances on the GPU")
+    ap.add_argument("--num-agents", type=int, default=None, help="simple_spread only: N agents = N landmarks")
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--replay-capacity", type=int, default=int(1e6))
+    o = ap.parse_args(own)
+    run_reference_train(ref, o.reference_train, num_envs=o.num_envs, num_agents=o.num_agents, device=o.device, seed=o.seed,
+                        replay_capacity=o.replay_capacity)
 
 
 if __name__ == "__main__":
-    train(parse_args())
+    main()

@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .env import EnvBatchFlag, EnvBatchFloat
 from .replay import DeviceReplayBuffer, JointReplayRing
 from .spaces import act_heads
 
@@ -288,9 +289,14 @@ class MADDPGCore(object):
                                                   self.next_counter() if counter is None else counter, _lib.ptr(ctl),
                                                   _lib.current_stream()), "mdp_replay_make_index")
 
-    def read_stats(self, agent, B=None):
+    def snapshot_stats(self, agent, B=None):
+        """The agent's statistics accumulators copied on the DEVICE (no synchronisation): a LazyStats that turns into the six
+        numbers of maddpg.py:196 when it is first read."""
+        return LazyStats(self, agent, self.stats[8 * agent:8 * agent + 8].clone(), B)
+
+    def read_stats(self, agent, B=None, raw=None):
         """[q_loss, p_loss, mean(target_q), mean(rew), mean(target_q_next), std(target_q)] (maddpg.py:196)."""
-        s = self.stats[8 * agent:8 * agent + 8].cpu().numpy()
+        s = (self.stats[8 * agent:8 * agent + 8] if raw is None else raw).cpu().numpy()
         n = s[7] if s[7] > 0 else float(B or 1)
         K = self.act_dims[agent]
         mean_y = s[3] / n
@@ -298,6 +304,36 @@ class MADDPGCore(object):
         q_loss = s[0] / n
         p_loss = s[1] / n + float(self.cfg.actor_reg) * s[2] / (n * K)
         return [np.float32(q_loss), np.float32(p_loss), mean_y, s[5] / n, s[6] / n, math.sqrt(var_y)]
+
+
+class LazyStats(object):
+    """What ``MADDPGAgentTrainer.update`` returns: the reference's list of six statistics (maddpg.py:196), materialised
+    (one device-to-host copy + synchronisation) only when it is indexed, iterated or converted -- experiments/train.py:161
+    discards the value, so the training loop itself never synchronises on it."""
+
+    def __init__(self, core, agent, raw, B):
+        self._core, self._agent, self._raw, self._B, self._v = core, agent, raw, B, None
+
+    def _get(self):
+        if self._v is None:
+            self._v = self._core.read_stats(self._agent, self._B, raw=self._raw)
+            self._raw = None
+        return self._v
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __len__(self):
+        return 6
+
+    def __getitem__(self, k):
+        return self._get()[k]
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self._get(), dtype=dtype)
+
+    def __repr__(self):
+        return repr(self._get())
 
 
 class _Group(object):
@@ -336,6 +372,10 @@ class _Group(object):
                                num_units=a.num_units, lr=a.lr, gamma=a.gamma,
                                device=getattr(a, "device", "cuda"), seed=getattr(a, "seed", 0),
                                replay_capacity=int(getattr(a, "replay_capacity", REPLAY_CAPACITY)))
+        # a finalized group only lives through its trainers: the registry must not keep the core (and its replay ring,
+        # 0.5 GB for simple_spread N=3, 28 GB for N=24 at 1e6 rows) alive after the experiment's trainers are gone
+        for k in [k for k, g in _Group.registry.items() if g is self]:
+            del _Group.registry[k]
         return self.core
 
 
@@ -354,6 +394,7 @@ class MADDPGAgentTrainer(AgentTrainer):
         self.max_replay_buffer_len = args.batch_size * args.max_episode_len
         self.replay_sample_index = None
         self._replay = None
+        self._idx_dev = None
         self._noise = {}
         self.p_debug = {"p_values": self._p_values, "target_act": self._target_act}
         self.q_debug = {"q_values": self._q_values, "target_q_values": self._target_q_values}
@@ -423,6 +464,10 @@ class MADDPGAgentTrainer(AgentTrainer):
 
     def experience(self, obs, act, rew, new_obs, done, terminal):
         """maddpg.py:154-156 (``terminal`` is ignored by the reference too)."""
+        if isinstance(rew, EnvBatchFloat):  # the batched loop's scalar wrappers carry the per-instance vectors
+            rew = rew.values
+        if isinstance(done, EnvBatchFlag):
+            done = done.values
         self.replay_buffer.add(obs, act, rew, new_obs, done if isinstance(done, torch.Tensor) or np.ndim(done) else float(done))
 
     def process_experience(self, obs, act, rew, new_obs, done, terminal):
@@ -442,8 +487,17 @@ class MADDPGAgentTrainer(AgentTrainer):
             raise NotImplementedError("update() needs index-aligned replay buffers (every agent inserts every step, "
                                       "maddpg.py:173-178 relies on the same)")
         B = self.args.batch_size
-        self.replay_sample_index = self.replay_buffer.make_index(B) if index is None else index
-        idx = core.ring.index_tensor(self.replay_sample_index)
+        if index is None and not getattr(self.args, "python_index_stream", False):
+            # ReplayBuffer.make_index (replay_buffer.py:46-47) on the device: B uniform draws in [0, len) from the core's
+            # Philox stream, no host round trip.  args.python_index_stream = True keeps the reference's python `random`
+            # stream (bit-identical index lists for a seeded `random`); an explicit ``index`` is always honoured.
+            if self._idx_dev is None or self._idx_dev.shape[0] != B:
+                self._idx_dev = torch.zeros(B, dtype=torch.int64, device=core.device)
+            core.make_index(self._idx_dev)
+            self.replay_sample_index = idx = self._idx_dev
+        else:
+            self.replay_sample_index = self.replay_buffer.make_index(B) if index is None else index
+            idx = core.ring.index_tensor(self.replay_sample_index)
         ut, ua = self._noise.get("u_target"), self._noise.get("u_actor")
         self._noise = {}
         if ut is not None:
@@ -456,4 +510,4 @@ class MADDPGAgentTrainer(AgentTrainer):
             ua_j[:, o:o + core.act_dims[self.agent_index]] = self._dev(ua)
             ua = ua_j
         core.update_agent(self.agent_index, core.ring.ring, ut, ua, idx=idx)  # gather fused into the kernels
-        return core.read_stats(self.agent_index, idx.shape[0])
+        return core.snapshot_stats(self.agent_index, idx.shape[0])

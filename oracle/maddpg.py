@@ -159,7 +159,9 @@ class OracleAgentTrainer:
         self.args = args
         self.local_q_func = local_q_func
         rng = rng if rng is not None else np.random.RandomState(agent_index)
-        self.noise = noise if noise is not None else (lambda shape: rng.uniform(size=shape).astype(F32))
+        # tf.random_uniform(float32) is in [0, 1): a float64 draw cast to float32 may round up to 1.0 -> clamp below 1
+        self.noise = noise if noise is not None else (
+            lambda shape: np.minimum(rng.uniform(size=shape).astype(F32), np.nextafter(F32(1), F32(0))))
         self.obs_dims = [int(s[0]) for s in obs_shape_n]
         self.heads_n = [act_heads(s) for s in act_space_n]
         self.act_dims = [sum(h) for h in self.heads_n]

@@ -61,9 +61,29 @@ def test_single_steps_f32_state_match_oracle(name):
         env.step_device(_joint_act(env, acts))
         obs = env.obs[:, :sum(env.obs_dims)].cpu().numpy()
         np.testing.assert_allclose(obs, np.concatenate(o, 1), rtol=1e-4, atol=2e-5, err_msg="obs step %d" % t)
-        # rewards jump by +-1/5/10 at contact thresholds; float32 may legitimately flip an exact tie
-        bad = ~np.isclose(env.rew.cpu().numpy(), r, rtol=1e-4, atol=1e-4)
-        assert bad.mean() < 0.02, "rew step %d: %d mismatches" % (t, bad.sum())
+        # rewards jump by +-1/5/10 at contact thresholds: a float32 state could only differ there by flipping an exact tie,
+        # which these seeded cases do not contain
+        np.testing.assert_allclose(env.rew.cpu().numpy(), r, rtol=1e-4, atol=1e-4, err_msg="rew step %d" % t)
+
+
+@pytest.mark.parametrize("name", list(ENV_CASES))
+def test_rollout_f32_state_free_running_matches_oracle(name):
+    """The benchmarked precision mode (float32 state), FREE-RUNNING for the whole action tape (25 steps; 4 for
+    simple_spread N = 24) from one injected state: observations and rewards against the float64 oracle at the north-star
+    tolerance 1e-5 relative (|x| < 1 entries: 1e-5 absolute).  Measured drift on B200: observations <= 3e-6, rewards
+    <= 5e-6 for the four scenarios; the 24-agent case reaches 2e-5 on a few relative positions inside its 276-pair
+    contact cluster and gets 5e-5."""
+    tol = 5e-5 if name == "simple_spread_24" else 1e-5
+    for seed in (11, 5):
+        case = env_case(name, seed=seed)
+        ref = run_oracle_rollout(case)
+        env = _make(case, torch.float32)
+        env.reset(init_state=env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"]))
+        for t, acts in enumerate(case["tape"]):
+            env.step_device(_joint_act(env, acts))
+            obs = env.obs[:, :sum(env.obs_dims)].cpu().numpy()
+            np.testing.assert_allclose(obs, ref["obs"][t], rtol=tol, atol=tol, err_msg="obs step %d" % t)
+            np.testing.assert_allclose(env.rew.cpu().numpy(), ref["rew"][t], rtol=1e-5, atol=1e-5, err_msg="rew step %d" % t)
 
 
 @pytest.mark.parametrize("name", ["simple_spread", "simple_tag", "simple_world_comm"])

@@ -3,6 +3,7 @@ against the numpy oracle on the same weights, replay rows, index sets and unifor
 Tolerance from BASELINE.json north_star: Q-values and losses within 1e-4 relative after a
 fixed-seed update."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -147,6 +148,7 @@ def test_warmup_gate_and_index_stream():
     its indices from python ``random`` like replay_buffer.py:46-47."""
     import random
     case = trainer_case("simple", seed=0)
+    case["args"].python_index_stream = True  # the reference's python `random` stream (default: device-side Philox draws)
     trainers, core = _build(case)
     tr = trainers[0]
     tr.max_replay_buffer_len = case["rows"] + 1
@@ -157,7 +159,17 @@ def test_warmup_gate_and_index_stream():
     random.seed(77)
     out = tr.update(trainers, 100)
     assert out is not None and tr.replay_sample_index == expect
-    assert all(np.isfinite(out))
+    assert len(out) == 6 and all(np.isfinite(out))
+    # default: ReplayBuffer.make_index on the device -- in range, fresh per update, no host round trip; the statistics are
+    # materialised lazily (train.py:161 discards them)
+    case["args"].python_index_stream = False
+    a = tr.update(trainers, 100)
+    i1 = tr.replay_sample_index.clone()
+    b = tr.update(trainers, 100)
+    i2 = tr.replay_sample_index
+    assert i1.is_cuda and i1.shape == (case["B"],) and int(i1.min()) >= 0 and int(i1.max()) < case["rows"]
+    assert not torch.equal(i1, i2) and i1.unique().numel() > case["B"] // 2
+    assert a._v is None and np.isfinite(np.asarray(a, np.float64)).all() and np.isfinite(list(b)).all()
 
 
 def test_polyak_tau_invariants():
@@ -255,8 +267,8 @@ def test_graph_rollout_and_update_round_match_eager_semantics():
                                                     ("simple_tag", 64, True), ("simple", 64, True),
                                                     ("simple_world_comm", 128, True)])
 def test_episode_kernel_matches_per_step_kernels(scenario, units, generic):
-    """mdp_rollout_episode (persistent episode kernel) against the per-step path on the same seeds and
-    Philox counters: identical replay rows, final state and observations (incl. the device reset)."""
+    """mdp_rollout_episode (persistent episode kernel, fp32 SIMT actor tiles) against the per-step path on the same
+    seeds and Philox counters: identical replay rows, final state and observations (incl. the device reset)."""
     from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
     from maddpg_b200.rollout import BatchedRollout
     E, T = 80, 25  # 80 = 2.5 tiles of 32 env instances: exercises the ragged last CTA
@@ -269,6 +281,7 @@ def test_episode_kernel_matches_per_step_kernels(scenario, units, generic):
         env.force_generic_kernel(generic)
         core = MADDPGCore(env.obs_dims, env.action_space, [False] * env.n, num_units=units,
                           replay_capacity=E * T * 2 + 13, seed=3)
+        core.set_tensor_cores(-1)  # the fp32 SIMT episode kernel; the tcgen05 one is covered in tests/test_rollout_tc_gpu.py
         roll = BatchedRollout(env, core, T, mode=mode)
         if mode == "mega":
             roll.ep_return = torch.zeros((E, env.n), device="cuda")
@@ -293,25 +306,36 @@ def test_episode_kernel_matches_per_step_kernels(scenario, units, generic):
 
 @pytest.mark.parametrize("num_envs", [1, 64])
 def test_train_loop_drop_in(tmp_path, num_envs):
-    """experiments/train.py's loop on the drop-ins: reference shapes (1 env, numpy) and the batched superset;
-    passes the warm-up gate, performs updates at t % 100 == 0, saves and restores parameters."""
+    """The reference's OWN experiments/train.py, unmodified, executed through maddpg_b200.train's stand-in modules
+    (tensorflow / maddpg.common.tf_util / maddpg.trainer.maddpg / multiagent.*): reference shapes (1 env, numpy) and the
+    batched superset; passes the warm-up gate, performs updates at t % 100 == 0, saves and restores parameters.
+    The file is read from /root/reference (build container) or baseline/_ref/experiments (the copy __graft_entry__.build()
+    leaves for the GPU box; git-ignored, never part of the repo's history)."""
+    import pickle
     from maddpg_b200 import train as T
+    try:
+        path = T.reference_train_path()
+    except FileNotFoundError:
+        pytest.skip("the reference's experiments/train.py is not available on this machine")
     argv = ["--scenario", "simple_tag", "--num-adversaries", "3", "--adv-policy", "ddpg", "--num-episodes", "12",
             "--batch-size", "8", "--save-rate", "4", "--save-dir", str(tmp_path) + "/", "--plots-dir", str(tmp_path) + "/",
-            "--exp-name", "t", "--num-envs", str(num_envs), "--replay-capacity", "50000"]
-    arglist = T.parse_args(argv)
-    trainers, ep_rewards = T.train(arglist)
+            "--exp-name", "t"]
+    trainers = T.run_reference_train(argv, path, num_envs=num_envs, replay_capacity=50000, seed=0)
+    assert len(trainers) == 4 and "maddpg.trainer.maddpg" not in sys.modules  # the stand-ins are gone again
     core = trainers[0].core
-    assert len(ep_rewards) == 13 and all(np.isfinite(ep_rewards))
-    assert core.local_q == [True, True, True, False]
+    ep_rewards = pickle.load(open(os.path.join(str(tmp_path), "t_rewards.pkl"), "rb"))
+    assert len(ep_rewards) == 3 and all(np.isfinite(ep_rewards))  # mean episode reward at episodes 4, 8, 12 (train.py:172-176)
+    assert core.local_q == [True, True, True, False]  # get_trainers: adversaries first, ddpg -> local_q_func (train.py:63-75)
     assert len(trainers[0].replay_buffer) == 300 * num_envs
     # warm-up gate needs 200 rows: reached at t = 200 with one env (updates at t = 200, 300), at t = 4 with 64
     assert core.adam_t.cpu().tolist() == [2 if num_envs == 1 else 3] * 8
-    assert os.path.exists(os.path.join(str(tmp_path), "maddpg_b200.pt")) and os.path.exists(os.path.join(str(tmp_path), "t_rewards.pkl"))
+    assert os.path.exists(os.path.join(str(tmp_path), "maddpg_b200.pt")) and os.path.exists(os.path.join(str(tmp_path), "t_agrewards.pkl"))
     saved = torch.load(os.path.join(str(tmp_path), "maddpg_b200.pt"))
+    assert saved["counter"] > 0
     core.params.zero_()
+    core.counter = 0
     T.load_state(str(tmp_path), trainers)
-    assert torch.equal(core.params.cpu(), saved["params"])
+    assert torch.equal(core.params.cpu(), saved["params"]) and core.counter == saved["counter"]
 
 
 def test_grouped_update_all_equals_jacobi_order_of_per_agent_kernels():
