@@ -378,8 +378,8 @@ def main():
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         l0 = _lib.launch_count() + roll.graph_launches
         for e0, e1 in evs:
-            flush_l2()
-            barrier()
+            barrier()      # every repetition is bracketed by barrier + synchronize (this one and the next iteration's / the final one)
+            flush_l2()     # untimed: enqueued ahead of the first event, so the timed launches do not start on an idle queue
             e0.record()
             run_steps(roll, K)
             e1.record()

@@ -80,11 +80,12 @@ int mdp_env_reset(mdp_env* env, int32_t E, void* state, const void* init_state, 
                   uint64_t episode, float* obs_out, void* stream);
 
 /* MultiAgentEnv.step(action_n) -> World.step() -> per-agent observation()/reward() (train.py:114;
- * SURVEY Appendix A.2): one fused kernel.  state is updated in place.  ring_row0 (optional, may be
- * null): when non-null the kernel also writes the joint replay rows of this transition
- * (obs_t, act_t, next_obs, rew, done) to ring rows (ring_cursor + e) % ring_capacity, fusing
- * MADDPGAgentTrainer.experience / ReplayBuffer.add (maddpg.py:154-156, replay_buffer.py:25-32)
- * into the step; obs_prev (joint obs_t) must then be non-null. */
+ * SURVEY Appendix A.2): one fused kernel.  state is updated in place.  ring (optional, may be null): when non-null the
+ * SAME CALL also writes the joint replay rows of this transition (obs_t, act_t, next_obs, rew, done) to ring rows
+ * (ring_cursor + e) % ring_capacity -- MADDPGAgentTrainer.experience / ReplayBuffer.add (maddpg.py:154-156,
+ * replay_buffer.py:25-32) for all agents -- with a second launch (the joint insert kernel) on the same stream; only the
+ * persistent episode kernels (mdp_rollout_episode) write the rows from inside the step.  obs_prev (joint obs_t) must then
+ * be non-null. */
 int mdp_env_step(mdp_env* env, int32_t E, void* state, const float* act, float* obs_out, float* rew_out,
                  uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
                  int32_t ring_row_stride, int64_t ring_cursor, void* stream);
@@ -232,8 +233,8 @@ int mdp_clip_adam_polyak(mdp_core* core, int32_t agent, int32_t which, float gra
  * torch.distributed._symmetric_memory; h_peer_grads[rank] must be the buffer given to mdp_core_bind) so that
  * mdp_clip_adam_polyak[_all] sums the gradient over ranks itself -- peer loads over NVLink inside the clip+Adam+polyak
  * kernel, flag barriers between the CTAs that own the same variable -- instead of expecting an all-reduced bucket.
- * With peers bound grad_scale is still applied (pass 1/world).  flags: uint32 [6 * n_agents][8] per rank, zeroed;
- * epoch_local: uint32 [6 * n_agents] device words of this rank, zeroed.  h_peer_recv (optional): every rank's low-latency
+ * With peers bound grad_scale is still applied (pass 1/world).  flags: uint32 [12 * n_agents][8] per rank (slot = 12 * agent + 6 * net + variable), zeroed;
+ * epoch_local: uint32 [12 * n_agents] device words of this rank, zeroed.  h_peer_recv (optional): every rank's low-latency
  * receive buffer, uint32 pairs [2][world][total_train], zeroed -- when given, ranks PUSH (value, epoch) words into the peers'
  * buffers and poll their own (one NVLink traversal, no barrier); when NULL the kernel uses flag barriers and peer loads.
  * world <= 1 unbinds.  The gradient all-reduce is the only collective of the path. */

@@ -121,7 +121,10 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
   const bool small = len <= (long long)OPT_PF * nt;  // every peer read of this variable fits the register prefetch
   const bool ll = P.world > 1 && P.recv != nullptr;
   if (P.world > 1) {
-    epoch = P.epoch[slot] + (ll ? 1u : 1u);  // barrier mode uses epoch ("my gradients are complete") and epoch + 1 ("I have read yours")
+    // one slot (flag words + epoch counter) per (agent, net, variable): the actor and critic steps of an agent never share
+    // epochs, so a critic-only or reordered step sequence cannot alias another net's exchange (all ranks must still issue the
+    // SAME sequence of optimizer launches).  Barrier mode uses epoch ("my gradients are complete") and epoch + 1 ("I have read yours")
+    epoch = P.epoch[slot] + 1u;
     if (ll) {
       // push this rank's values first (posted stores), then everything below overlaps their flight
       for (long long i = tid; i < len; i += nt) ll_push(P, goff, i, g[i], epoch);
@@ -317,7 +320,7 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
   float* g = ag.grad[which].W1 + off;
   const long long goff = g - grads_base;
   clip_adam_polyak_var(g, const_cast<float*>(w.W1) + off, const_cast<float*>(wt.W1) + off, m_base + goff, v_base + goff, len,
-                       adam_t[2 * j + which], grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak, P, goff, 6 * j + var);
+                       adam_t[2 * j + which], grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak, P, goff, 12 * j + 6 * which + var);
 }
 
 }  // namespace mdp
@@ -427,7 +430,7 @@ extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, f
   k_clip_adam_polyak<<<6 - wide, 1024, 0, (cudaStream_t)stream>>>(param, target, grad, m, v, seg, c->adam_t + 2 * agent + which,
                                                                   grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
                                                                   c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak,
-                                                                  do_polyak, peer_ctx(c), c->lay.train_off[agent][which], 6 * agent,
+                                                                  do_polyak, peer_ctx(c), c->lay.train_off[agent][which], 12 * agent + 6 * which,
                                                                   wide);
   return check_launch("k_clip_adam_polyak");
 }

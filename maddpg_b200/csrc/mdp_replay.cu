@@ -144,7 +144,8 @@ __global__ void k_replay_make_index(long long* __restrict__ idx_out, int B, long
   if (length <= 0) length = (long long)ctl[3];
   uint4 r = Philox::gen(seed, (uint32_t)b, 0x1D3Au, (uint32_t)counter, (uint32_t)(counter >> 32));
   long long i = (long long)(Philox::u01d(r.x, r.y) * (double)length);
-  idx_out[b] = i < length ? i : length - 1;
+  i = i < length ? i : length - 1;
+  idx_out[b] = i > 0 ? i : 0;  // an empty ring (length 0) yields row 0, never a negative row (callers gate on the ring length)
 }
 
 }  // namespace mdp

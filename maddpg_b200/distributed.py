@@ -51,12 +51,12 @@ class PeerGradExchange(object):
         dev = core.device
         n = int(core.layout.total_train)
         self.grads = symm.empty(n, dtype=torch.float32, device=dev)
-        self.flags = symm.empty(6 * core.n * self.SLOT_WORDS, dtype=torch.int32, device=dev)
+        self.flags = symm.empty(12 * core.n * self.SLOT_WORDS, dtype=torch.int32, device=dev)  # slot = 12 * agent + 6 * net + variable
         self.grads.zero_()
         self.flags.zero_()
         self.gh = symm.rendezvous(self.grads, group)
         self.fh = symm.rendezvous(self.flags, group)
-        self.epoch = torch.zeros(6 * core.n, dtype=torch.int32, device=dev)
+        self.epoch = torch.zeros(12 * core.n, dtype=torch.int32, device=dev)
         self.low_latency = (n <= self.LL_MAX_FLOATS) if low_latency is None else bool(low_latency)
         self.recv = self.rh = None
         if self.low_latency:
@@ -93,6 +93,8 @@ class PeerGradExchange(object):
 
 class DataParallelUpdater(object):
     """Drives MADDPGCore's split update entry points with an all-reduce between gradient and step.
+    Lock-step contract of the fused peer exchange: every rank issues the SAME sequence of optimizer launches (same agents,
+    same nets, same order); a rank that skips one makes its peers wait for the matching epoch and trap after ~4 s.
     ``peer=True`` (NCCL process group on one NVLink node): the all-reduce is fused into the clip+Adam+polyak kernel
     (PeerGradExchange) and ``update_agent`` issues kernels only."""
 

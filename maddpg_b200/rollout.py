@@ -373,6 +373,9 @@ class GraphedUpdateRound(object):
 
     def run(self, rounds=1):
         core = self.core
+        if core.ring.length[0] < self.B:  # the reference's gate is batch_size * max_episode_len rows (maddpg.py:162-163)
+            raise RuntimeError("GraphedUpdateRound.run: the replay ring holds %d rows, fewer than one batch of %d"
+                               % (core.ring.length[0], self.B))
         if not self.use_graph:
             for _ in range(rounds):
                 self._body(False)

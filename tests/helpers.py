@@ -69,6 +69,10 @@ TRAINER_CASES = {
     "simple_world_comm": ("simple_world_comm", None, 128, 64, None),
     "simple_tag_ddpg_adv": ("simple_tag", None, 64, 64, [True, True, True, False]),
     "simple_spread_6": ("simple_spread", 6, 64, 48, None),
+    # BASELINE.json batch sizes: configs[1] (batch 1024), configs[2] (batch 4096), configs[3] (num_units 128, batch 1024)
+    "simple_spread_b1024": ("simple_spread", 3, 64, 1024, None),
+    "simple_tag_b4096": ("simple_tag", None, 64, 4096, None),
+    "simple_world_comm_b1024": ("simple_world_comm", None, 128, 1024, None),
 }
 
 

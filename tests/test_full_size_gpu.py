@@ -1,5 +1,6 @@
-"""BASELINE.json configs at their full per-GPU sizes, checked through size-independent properties (there is no oracle at
-these sizes): duplicated env instances give duplicated results anywhere in the batch, simple_spread's shared reward is equal
+"""BASELINE.json configs at their full per-GPU sizes: the env kernels of configs[1] / configs[2] against the CPU oracle at
+4096 / 16384 env instances (the update path at batch 1024 / 4096 is in tests/helpers.TRAINER_CASES *_b1024 / *_b4096), and
+all configs through size-independent properties: duplicated env instances give duplicated results anywhere in the batch, simple_spread's shared reward is equal
 across agents, a rigid translation of every entity leaves relative observations and rewards unchanged, the fused ring insert
 round-trips bit-exactly through the gather, and the tensor-core and SIMT update paths agree after a full grouped round."""
 import pytest
@@ -19,6 +20,32 @@ def _env(name, **kw):
     from maddpg_b200 import BatchedMultiAgentEnv
     scen, na, E, B, U = CONFIGS[name]
     return BatchedMultiAgentEnv(scen, num_envs=E, num_agents=na, squeeze=False, seed=9, **kw), E, B, U
+
+
+@pytest.mark.parametrize("name,dtype", [("cfg2_spread3", torch.float64), ("cfg2_spread3", torch.float32),
+                                        ("cfg3_tag", torch.float64), ("cfg3_tag", torch.float32)])
+def test_env_steps_match_oracle_at_config_size(name, dtype):
+    """3 free-running steps of every env instance of the config (device reset draws, softmax-of-gaussian actions) against
+    oracle/mpe.py: observations and rewards within 1e-5 relative (float64 AND float32 state)."""
+    import numpy as np
+    from oracle import mpe
+    env, E, B, U = _env(name, state_dtype=dtype)
+    env.reset_device()
+    st = env.state_to_arrays()
+    oenv = mpe.BatchedOracleEnv(CONFIGS[name][0], E, CONFIGS[name][1])
+    oenv.set_state(st["agent_pos"], st["agent_vel"], st["landmark_pos"])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    nobs = sum(env.obs_dims)
+    for t in range(3):
+        act = torch.zeros((E, env.act_stride), device="cuda")
+        for i in range(env.n):
+            o, K = env.act_off[i], env.act_dims[i]
+            act[:, o:o + K] = torch.softmax(2.0 * torch.randn((E, K), device="cuda", generator=g), -1)
+        env.step_device(act)
+        a = act.cpu().numpy()
+        o, r, d = oenv.step([a[:, env.act_off[i]:env.act_off[i] + env.act_dims[i]] for i in range(env.n)])
+        np.testing.assert_allclose(env.obs[:, :nobs].cpu().numpy(), np.concatenate(o, 1), rtol=1e-5, atol=1e-5, err_msg="obs step %d" % t)
+        np.testing.assert_allclose(env.rew.cpu().numpy(), r, rtol=1e-5, atol=1e-5, err_msg="rew step %d" % t)
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))

@@ -65,7 +65,7 @@ def test_td_target_tensor_cores_many_tiles_philox(name):
         _close(y_tc.cpu().numpy(), y_simt.cpu().numpy(), rtol=2e-5, atol=1e-5, msg="agent %d" % j)
 
 
-@pytest.mark.parametrize("name", ["simple_spread", "simple_tag"])
+@pytest.mark.parametrize("name", ["simple_spread", "simple_tag", "simple_spread_b1024", "simple_tag_b4096"])
 def test_sequential_update_round_with_tensor_cores(name):
     case = trainer_case(name, seed=4)
     ref = oracle_update_round(trainer_case(name, seed=4))

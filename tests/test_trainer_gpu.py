@@ -30,9 +30,14 @@ def _build(case):
         core.set_weights(i, _lib.NET_Q, o.q.p)
         core.set_weights(i, _lib.NET_TARGET_Q, o.target_q.p)
     p = case["pool"]
-    for r in range(case["rows"]):  # every agent inserts every step, like train.py:119-120
+    if case["rows"] > 1000:  # BASELINE batch sizes: all rows of an agent through ONE batched experience() call
+        dev = lambda x: torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).cuda()
         for i, tr in enumerate(trainers):
-            tr.experience(p["obs"][i][r], p["act"][i][r], float(p["rew"][i][r]), p["nobs"][i][r], bool(p["done"][i][r]), False)
+            tr.experience(dev(p["obs"][i]), dev(p["act"][i]), dev(p["rew"][i]), dev(p["nobs"][i]), dev(p["done"][i]), False)
+    else:
+        for r in range(case["rows"]):  # every agent inserts every step, like train.py:119-120
+            for i, tr in enumerate(trainers):
+                tr.experience(p["obs"][i][r], p["act"][i][r], float(p["rew"][i][r]), p["nobs"][i][r], bool(p["done"][i][r]), False)
     for tr in trainers:
         tr.max_replay_buffer_len = 0
     return trainers, core
