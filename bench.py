@@ -69,7 +69,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--rollout-mode", default="mega", choices=["mega", "graph", "eager"])
+    ap.add_argument("--rollout-mode", default="auto", choices=["auto", "mega", "graph", "eager"],
+                    help="auto: the persistent episode kernel or the CUDA graph of per-step kernels, whichever is faster on a probe")
     ap.add_argument("--envs", type=int, default=0)
     ap.add_argument("--no-tensor-section", action="store_true")
     ap.add_argument("--nccl-allreduce", action="store_true")
@@ -328,6 +329,9 @@ def main():
 
     # ---- build the experiment exactly like train.py:80-85 (env, trainers) on this rank's shard -------------
     eps_launch = max(1, args.episodes_per_launch)
+    tc_episode = SCENARIO == "simple_spread" and N_AGENTS in (2, 3, 4) and UNITS == 64  # mdp_rollout_episodes loops in-kernel
+    if not tc_episode:
+        eps_launch = 1
     cap = max(1000000, E * EP_LEN * (eps_launch + 1))  # the reference's 1e6 rows (maddpg.py:147), at least one launch deep
     arglist = argparse.Namespace(lr=1e-2, gamma=0.95, batch_size=BATCH, num_units=UNITS, max_episode_len=EP_LEN,
                                  seed=0, device=str(dev), replay_capacity=cap)
@@ -388,7 +392,30 @@ def main():
         ms = max_over_ranks(a.elapsed_time(b) for a, b in evs)
         return median(ms), ms, launches
 
-    roll = BatchedRollout(env, core, EP_LEN, mode=args.rollout_mode)
+    mode, probe = args.rollout_mode, None
+    if mode == "auto":
+        # probe: 2 episodes through each path after one warm-up episode (device time); the headline config always takes the
+        # persistent kernel (it wins by > 3x there), the larger configs may not fit it or may run it from streamed weights
+        mode, probe = "mega", {}
+        if not tc_episode:
+            for m in ("mega", "graph"):
+                r = BatchedRollout(env, core, EP_LEN, mode=m)
+                env.reset()
+                r.run(2 * EP_LEN)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                r.run(2 * EP_LEN)
+                b.record()
+                torch.cuda.synchronize()
+                probe[r.mode if m == "mega" else m] = a.elapsed_time(b) / (2 * EP_LEN)
+                del r
+            mode = min(probe, key=probe.get)
+            t = torch.tensor([0 if mode == "mega" else 1], device=dev)
+            if world > 1:  # every rank must run the same path
+                dist.broadcast(t, src=0)
+            mode = "mega" if int(t.item()) == 0 else "graph"
+    roll = BatchedRollout(env, core, EP_LEN, mode=mode)
     roll.episodes_per_launch = eps_launch
     env.reset()
     sampler = ClockSampler(local_rank)
@@ -670,7 +697,7 @@ def main():
             "f64_state": f64,
             "config": {"workload": WORKLOAD, "bench_config": args.config, "envs_per_gpu": E, "agents": A, "batch": BATCH,
                        "num_units": UNITS, "episode_len": EP_LEN,
-                       "replay_capacity_rows": core.ring.capacity, "rollout_mode": roll.mode,
+                       "replay_capacity_rows": core.ring.capacity, "rollout_mode": roll.mode, "rollout_mode_probe_ms_per_step": probe,
                        "episodes_per_launch": eps_launch if roll.mode == "mega" else None,
                        "cuda_graph_updates": bool(gupd is not None and gupd.use_graph),
                        "timing": "one repetition = exactly `steps` lockstep steps (whole episodes incl. env.reset, + a partial "

@@ -961,6 +961,12 @@ extern "C" int mdp_core_bind(mdp_core* c, float* params, float* grads, float* ad
 }
 
 
+namespace mdp {
+int launch_actor_act_tc(mdp_core* c, const CoreDev& d, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
+                        const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u, uint64_t seed,
+                        uint64_t counter, float* logits_out, long long row_base, cudaStream_t st);
+}
+
 extern "C" int mdp_actor_act(mdp_core* c, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
                              const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u,
                              uint64_t seed, uint64_t counter, float* logits_out, void* stream) {
@@ -976,6 +982,12 @@ int mdp::actor_act_range(mdp_core* c, int32_t agent_begin, int32_t agent_count, 
               "mdp_actor_act: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
+  // tensor-core kernel (128-row tiles) once a launch has at least one tile per SM (tc_mode 1: always; -1: never)
+  if (c->cfg.num_units == 64 && c->tc_mode >= 0 && (c->tc_mode > 0 || (long long)cdiv(E, 128) * agent_count >= 148)) {
+    int rc = launch_actor_act_tc(c, d, agent_begin, agent_count, use_target, E, obs, obs_stride, act, act_stride, u, seed, counter,
+                                 logits_out, (long long)row_base, st);
+    if (rc != MDP_ENOTSUP) return rc;
+  }
   const Plan p = make_plan(c, E >= 4096 ? 4096 : E);
   return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto res_) -> int {
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;

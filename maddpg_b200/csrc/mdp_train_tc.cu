@@ -564,6 +564,129 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
 
 
 // =============================================================================================================
+// Grouped actor inference + Gumbel-softmax on tensor cores: MADDPGAgentTrainer.action for E lockstep env instances
+// (maddpg/trainer/maddpg.py:151-152 -> act :62 -> mlp_model train.py:39-46 + SoftCategoricalPd.sample distributions.py:264-266).
+// The per-step rollout of the larger configs spends most of its time here (measured on B200, fp32 SIMT kernel: 55 of 70 us
+// per lockstep step for simple_tag with 16384 env instances, 1.2 of 2.0 ms for simple_spread N=24 with 32768).
+// grid = (ceil(E / 128), agent_count): one CTA = 128 env instances of one agent, same building blocks as the TD-target
+// kernel above (observation rows -> TMEM A operand, W^T images by TMA, 3xTF32, head + Gumbel-softmax as row-local register
+// code); same Philox keys as k_actor_act, so the two kernels draw the same noise.
+template <int U>
+__global__ void __launch_bounds__(NTT, 1) k_actor_act_tc(CoreDev C, const AgentImg* __restrict__ imgs, int agent_begin, int net,
+                                                         int E, const float* __restrict__ obs, int obs_stride,
+                                                         float* __restrict__ act, int act_stride, const float* __restrict__ u,
+                                                         uint64_t seed, uint64_t counter, float* __restrict__ logits_out,
+                                                         long long rng_row_base) {
+  using LY = Lay<U>;
+  const int i = agent_begin + blockIdx.y;
+  if (C.ctl) counter += C.ctl[0];
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ Bars bars;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* smem = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+  float* misc = reinterpret_cast<float*>(smem + LY::OFF_MISC);
+  float* sB1 = misc;
+  float* sB2 = sB1 + U;
+  float* sW3 = sB2 + U;
+  float* sB3 = sW3 + U * MAXK;
+  float* sPart = sB3 + 16;
+  float* sG = sPart + TMR * KPAD;
+  float* sQ = sG + TMR * KPAD;
+  float* sRD = sQ + TMR;
+  long long* sRow = reinterpret_cast<long long*>(sRD + 2 * TMR);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+  const AgentDev& ag = C.agents[i];
+  const long long row0 = (long long)blockIdx.x * TMR;
+  const int nrows = (int)min((long long)TMR, E - row0);
+
+  if (warp == 0) umma::tmem_alloc(&tmem_slot, LY::T_COLS);
+  if (tid == 0) {
+    for (int k = 0; k < NS; ++k) {
+      mbar_init(&bars.stage_w[k], 1);
+      mbar_init(&bars.stage_x[k], NTC / 64);
+      mbar_init(&bars.stage_free[k], 1);
+    }
+    mbar_init(&bars.h1_full, NTC / 32);
+    mbar_init(&bars.w2_full, 1);
+    mbar_init(&bars.w2_free, 1);
+    mbar_init(&bars.acc, 1);
+  }
+  if (tid < TMR) sRow[tid] = (row0 + min(tid, nrows - 1)) * (long long)obs_stride;  // tail rows replay the last valid row
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tbase = tmem_slot;
+  Pipe pipe{0u, 0u, 0u};
+  if (warp == NTC / 32) {
+    if (lane == 0) produce_net<U>(smem, &bars, pipe, imgs[i].net[net], ag.obs_dim);
+  } else if (warp == NTC / 32 + 1) {
+    const uint32_t tb = __shfl_sync(0xffffffffu, tbase, 0);
+    mma_net<U>(smem, &bars, pipe, tb, ag.obs_dim);
+  } else {
+    float h2[U / 2];
+    float part[MAXK];
+    const MlpW w = ag.net[net];
+    XT xs{obs + ag.obs_off, ag.obs_dim, nullptr, 0, 0, 0, ((ag.obs_off & 3) == 0 && (obs_stride & 3) == 0) ? 1 : 0};
+    const int K = ag.act_dim;
+    forward_hidden_tc<U>(&bars, pipe, tbase, xs, w, sRow, sB1, sB2, sW3, sB3, h2, [&]() {
+      // both unit-halves of a row share its K draws: half 0 takes the even actions, half 1 the odd ones
+      for (int a = half; a < K; a += 2) {
+        const long long r = row0 + min(row, nrows - 1);
+        const float uu = u ? u[r * act_stride + ag.act_off + a] : philox_u(seed, counter, (uint32_t)i, r + rng_row_base, a);
+        sG[row * KPAD + a] = gumbel_from_u(uu);
+      }
+    });
+    if (K == 5) head_partial<U, 5>(h2, sW3, half, part);
+    else if (K == 9) head_partial<U, 9>(h2, sW3, half, part);
+    else {
+      for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+      for (int a = 0; a < K; ++a)
+        for (int g = 0; g < U / 64; ++g)
+          for (int t = 0; t < 32; ++t) part[a] = fmaf(h2[32 * g + t], sW3[(32 * half + 64 * g + t) * K + a], part[a]);
+    }
+    if (half == 1)
+      for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+    named_sync();
+    if (half == 0 && row < nrows) {  // one thread per env instance: logits -> Gumbel-softmax per head
+      float z[MAXK], lg[MAXK];
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a) {
+        if (a < K) {
+          lg[a] = part[a] + sPart[row * KPAD + a] + sB3[a];
+          z[a] = lg[a] + sG[row * KPAD + a];
+        }
+      }
+      for (int h = 0; h < ag.n_heads; ++h) {
+        const int o = h ? ag.head_dim[0] : 0, n = ag.head_dim[h];
+        float m = -INFINITY;
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) m = fmaxf(m, z[a]);
+        float ssum = 0.f;
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) { z[a] = expf(z[a] - m); ssum += z[a]; }
+#pragma unroll
+        for (int a = 0; a < MAXK; ++a)
+          if (a >= o && a < o + n) z[a] = z[a] / ssum;
+      }
+      float* arow = act + (row0 + row) * (long long)act_stride + ag.act_off;
+#pragma unroll
+      for (int a = 0; a < MAXK; ++a)
+        if (a < K) {
+          arow[a] = z[a];
+          if (logits_out) logits_out[(row0 + row) * (long long)act_stride + ag.act_off + a] = lg[a];
+        }
+    }
+  }
+  umma::fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_free(tbase, LY::T_COLS);
+}
+
+
+// =============================================================================================================
 // Fused critic forward + MSE + backward on tensor cores (q_train, maddpg.py:75-100), maddpg-mode critics, U = 64.
 //   forward   z1 = X W1            A = X (TMEM, gathered rows), B = W1^T chunk images (TMA)        -> acc1
 //             z2 = h1 W2           A = h1 (TMEM),               B = W2^T images (TMA)              -> acc2
@@ -1472,6 +1595,33 @@ static int ensure_images(mdp_core* c) {
   c->tc_imgs = arena + total;
   return MDP_OK;
 }
+
+// mdp_actor_act on tensor cores (num_units 64).  MDP_ENOTSUP -> the caller uses k_actor_act.
+int launch_actor_act_tc(mdp_core* c, const CoreDev& d, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
+                        const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u, uint64_t seed,
+                        uint64_t counter, float* logits_out, long long row_base, cudaStream_t st) {
+  if (c->cfg.num_units != 64) return MDP_ENOTSUP;
+  constexpr int U = 64;
+  using LY = tc::Lay<U>;
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  const tc::AgentImg* imgs = reinterpret_cast<const tc::AgentImg*>(c->tc_imgs);
+  const int net = use_target ? MDP_NET_TARGET_P : MDP_NET_P;
+  int max_in = 0;
+  for (int k = agent_begin; k < agent_begin + agent_count; ++k) max_in = std::max(max_in, c->cfg.obs_dim[k]);
+  const int bx = std::min(64, cdiv(((max_in + 31) / 32 * 32 + U) * U, 256 * 4));
+  tc::k_build_images<U><<<dim3(bx, agent_count), 256, 0, st>>>(d, imgs, agent_count, agent_begin, 0, net, MDP_NET_Q);
+  rc = check_launch("k_build_images");
+  if (rc) return rc;
+  // a CTA owns all 512 TMEM columns of its SM: ask for more than half of the shared memory so that two never share one
+  const size_t smem = std::max(LY::OFF_MISC + (size_t)LY::MISC_FLOATS * 4 + 1024 + 64, (size_t)116 * 1024);
+  auto kern = tc::k_actor_act_tc<U>;
+  MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3(cdiv(E, tc::TMR), agent_count), tc::NTT, smem, st>>>(d, imgs, agent_begin, net, E, obs, obs_stride, act, act_stride, u,
+                                                                  seed, counter, logits_out, row_base);
+  return check_launch("k_actor_act_tc");
+}
+
 
 // Returns MDP_ENOTSUP when the shape is outside the tensor-core path (the caller then uses the SIMT kernels).
 int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,

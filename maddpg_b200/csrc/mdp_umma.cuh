@@ -26,9 +26,14 @@ __device__ __forceinline__ uint32_t sw128b32_off(int r, int c) {
   return (uint32_t)(((r >> 2) << 9) + ((r & 3) << 7) + ((((c >> 3) ^ (r & 3)) << 5) | ((c & 7) << 2)));
 }
 
-// split for 3xTF32: hi = x with the 13 low mantissa bits cleared (exactly what kind::tf32 reads), lo = x - hi (exact)
+// split for 3xTF32: hi = x rounded to NEAREST tf32 (13 low mantissa bits zero: exactly what kind::tf32 reads), lo = x - hi
+// (exact, signed, |lo| <= 2^-11 |x|; the MMA truncates lo toward zero: a sign-symmetric 2^-21 |x| error).  Round 1 cleared the
+// low bits instead (truncation): lo was one-sided and twice as large, so the dropped lo*lo term and the truncation of lo were
+// biased errors that add up along K -- measured 4x the error of this split on the rollout's actions against the oracle.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  hi = __uint_as_float(r);
   lo = x - hi;
 }
 

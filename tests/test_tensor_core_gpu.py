@@ -201,3 +201,45 @@ def test_actor_grads_tensor_cores_many_tiles_philox():
                 outs.append(core.grads.clone())
             scale = float(outs[0].abs().max())
             _close(outs[1].cpu().numpy(), outs[0].cpu().numpy(), rtol=1e-3, atol=2e-4 * scale, msg="%s agent %d" % (name, j))
+
+
+@pytest.mark.parametrize("scenario,na,E", [("simple_tag", None, 4096 + 37), ("simple_spread", 24, 300), ("simple_spread", 3, 129),
+                                           ("simple", None, 128)])
+def test_actor_act_tensor_cores_match_simt_and_oracle(scenario, na, E):
+    """mdp_actor_act: the tcgen05 kernel (128-row tiles, 3xTF32) against the fp32 SIMT kernel on the same Philox counter and
+    against the oracle's numpy actor (logits) -- MADDPGAgentTrainer.action, maddpg.py:151-152."""
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore, _lib
+    from oracle import maddpg as omaddpg
+    env = BatchedMultiAgentEnv(scenario, num_envs=E, num_agents=na, squeeze=False, seed=3)
+    core = MADDPGCore(env.obs_dims, env.action_space, [False] * env.n, num_units=64, replay_capacity=64, seed=9)
+    rng = np.random.RandomState(1)
+    for i in range(env.n):
+        w = core.get_weights(i, _lib.NET_P)
+        for k in (1, 3, 5):
+            w[k] = rng.uniform(-0.2, 0.2, size=w[k].shape).astype(np.float32)
+        core.set_weights(i, _lib.NET_P, w)
+    obs = torch.zeros((E, core.obs_stride), device="cuda")
+    obs[:, :core.obs_sum] = torch.randn((E, core.obs_sum), generator=torch.Generator().manual_seed(0)).cuda()
+    out = {}
+    for mode in (-1, 1):
+        core.set_tensor_cores(mode)
+        act, lg = torch.zeros((E, core.act_stride), device="cuda"), torch.zeros((E, core.act_stride), device="cuda")
+        core.act(obs, act, logits_out=lg, counter=5)
+        out[mode] = (act.cpu().numpy(), lg.cpu().numpy())
+    np.testing.assert_allclose(out[1][1], out[-1][1], rtol=2e-5, atol=1e-5, err_msg="logits tcgen05 vs SIMT")
+    np.testing.assert_allclose(out[1][0], out[-1][0], rtol=0, atol=3e-6, err_msg="actions tcgen05 vs SIMT (same Philox draws)")
+    for i in range(env.n):
+        m = omaddpg.MLP(env.obs_dims[i], 64, env.act_dims[i], np.random.RandomState(0))
+        m.p = core.get_weights(i, _lib.NET_P)
+        o, K = core.obs_off[i], env.act_dims[i]
+        ref, _ = m.forward(obs[:, o:o + env.obs_dims[i]].cpu().numpy())
+        np.testing.assert_allclose(out[1][1][:, core.act_off[i]:core.act_off[i] + K], ref, rtol=1e-4, atol=1e-5)
+    # injected uniforms (parity hook) take the same path
+    u = torch.rand((E, core.act_stride), generator=torch.Generator().manual_seed(2)).clamp_(1e-6, 1 - 1e-6).cuda()
+    acts = []
+    for mode in (-1, 1):
+        core.set_tensor_cores(mode)
+        a = torch.zeros((E, core.act_stride), device="cuda")
+        core.act(obs, a, u=u)
+        acts.append(a.cpu().numpy())
+    np.testing.assert_allclose(acts[1], acts[0], rtol=0, atol=3e-6)
