@@ -55,6 +55,7 @@ struct mdp_core {
   float* tc_scratch = nullptr;     // sampled-action tiles of the tensor-core TD-target kernel when they exceed shared memory
   size_t tc_scratch_bytes = 0;
   float* norm2 = nullptr;             // squared gradient norms of wide W1 variables (mdp_optim.cu)
+  float* peer_reduced = nullptr;      // rank-summed gradients of wide W1 variables (fused peer exchange, many-CTA path)
   float* tc_dz1 = nullptr;            // dz1 tiles handed from k_critic_grads_tc to k_dw1_tc (wide critics)
   size_t tc_dz1_bytes = 0;
   unsigned char* tc_arena = nullptr;  // pre-split UMMA weight images of every net (csrc/mdp_train_tc.cu)

@@ -75,6 +75,57 @@ __device__ __forceinline__ float ll_sum(const PeerCtx& P, long long goff, long l
   return s;
 }
 
+// ll_sum for the OPT_PF register-prefetched elements of a thread (tid + k nt), with the polls of two source ranks x OPT_PF
+// elements in flight at once.  One poll is an L2 round trip of a system-scope load (~0.7 us); polling element after element and
+// rank after rank (the first version) serialised 7 x 4 of them per thread: ~19 us of a 27 us exchange on 8 GPUs.
+// The sum still runs over the ranks in rank order (own value at its rank's position): replicas stay bit-identical.
+template <int PF>
+__device__ __forceinline__ void ll_sum_pf(const PeerCtx& P, long long goff, int tid, int nt, long long len, float (&gr)[PF], unsigned epoch) {
+  float own[PF];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) { own[k] = gr[k]; gr[k] = 0.f; }
+  for (int r0 = 0; r0 < P.world; r0 += 2) {
+    unsigned v[2][PF], e[2][PF];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int r = r0 + d;
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        const long long i = tid + (long long)k * nt;
+        e[d][k] = epoch; v[d][k] = 0u;
+        if (r < P.world && r != P.rank && i < len) {
+          const uint2* src = P.recv[P.rank] + ((long long)((epoch & 1u) * P.world + r)) * P.total + goff + i;
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[d][k]), "=r"(e[d][k]) : "l"(src) : "memory");
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int r = r0 + d;
+      if (r >= P.world) break;
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        const long long i = tid + (long long)k * nt;
+        if (i >= len) continue;
+        if (r == P.rank) { gr[k] += own[k]; continue; }
+        if (e[d][k] != epoch) {  // not there yet: spin on this word
+          const uint2* src = P.recv[P.rank] + ((long long)((epoch & 1u) * P.world + r)) * P.total + goff + i;
+          long long t0 = 0;
+          for (unsigned spins = 1;; ++spins) {
+            asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v[d][k]), "=r"(e[d][k]) : "l"(src) : "memory");
+            if (e[d][k] == epoch) break;
+            if ((spins & 255u) == 0) {  // a missing peer must fail loudly (~4 s), never hang the box
+              if (t0 == 0) t0 = clock64();
+              else if (clock64() - t0 > 8000000000ll) __trap();
+            }
+          }
+        }
+        gr[k] += __uint_as_float(v[d][k]);
+      }
+    }
+  }
+}
+
 // flag = epoch on every peer (posted NVLink stores); relaxed: what the flag publishes is already complete when it is written
 // (gradient kernels finished in stream order / peer loads consumed by the norm reduction)
 __device__ __forceinline__ void peer_signal(const PeerCtx& P, int slot, unsigned epoch) {
@@ -146,13 +197,7 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
     pr[k] = ok ? p[i] : 0.f;
     tr[k] = (ok && do_polyak) ? tg[i] : 0.f;
   }
-  if (ll) {
-#pragma unroll
-    for (int k = 0; k < OPT_PF; ++k) {
-      const long long i = tid + (long long)k * nt;
-      if (i < len) gr[k] = ll_sum(P, goff, i, gr[k], epoch);
-    }
-  }
+  if (ll) ll_sum_pf(P, goff, tid, nt, len, gr, epoch);
   // pass 1: ||scale * g||_2
   float ss = 0.f;
 #pragma unroll
@@ -233,19 +278,43 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
 }
 
 
+constexpr int W1_MAXB = 128;  // CTAs per variable of the wide-W1 path (norm partials per agent)
+
 // Wide layer-1 weights (simple_spread N=24: 3576 x 64 per critic): one CTA per variable would stream 229 k parameters through
 // 1024 threads (455 us for 24 critics, the longest kernel of the round), so W1 gets a two-kernel path on a single GPU:
 // squared norm by many CTAs (one float atomic per CTA), then the clip + Adam + polyak sweep by many CTAs.
+// With peers bound (barrier protocol, large buckets): every CTA first joins the flag barrier "all ranks' gradients are complete",
+// then sums its chunk over the ranks with peer loads (rank order: bit-identical replicas) and leaves the SUM in the local
+// scratch `reduced` for k_w1_adam -- the single-CTA-per-variable kernel pulled the 229 k-float W1 of a simple_spread N=24 critic
+// through one CTA (~1.1 ms per agent on 8 GPUs; the whole sequential round ran at 34 % of the exchange-free rate).
 __global__ void __launch_bounds__(256) k_w1_sqnorm(const AgentDev* __restrict__ agents, int which, int units, int a0, float grad_scale,
-                                                   float* __restrict__ norm2) {
+                                                   float* __restrict__ norm2, PeerCtx P, const float* __restrict__ grads_base,
+                                                   float* __restrict__ reduced) {
   __shared__ float red[8];
   const int j = a0 + blockIdx.y;
   const AgentDev& ag = agents[j];
   const long long len = (long long)ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q].in * units;
   const float4* g4 = reinterpret_cast<const float4*>(ag.grad[which].W1);
+  const long long goff = ag.grad[which].W1 - grads_base;
+  if (P.world > 1) {
+    const int slot = 12 * j + 6 * which;
+    const unsigned epoch = P.epoch[slot] + 1u;
+    peer_signal(P, slot, epoch);
+    peer_wait(P, slot, epoch);
+  }
   float ss = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len / 4; i += (long long)gridDim.x * blockDim.x) {
-    float4 x = g4[i];
+    float4 x;
+    if (P.world > 1) {
+      x = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < P.world; ++r) {
+        const float4 y = __ldcv(reinterpret_cast<const float4*>(P.grads[r] + goff) + i);
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+      }
+      reinterpret_cast<float4*>(reduced + goff)[i] = x;
+    } else {
+      x = g4[i];
+    }
     x.x *= grad_scale; x.y *= grad_scale; x.z *= grad_scale; x.w *= grad_scale;
     ss = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, ss))));
   }
@@ -255,17 +324,23 @@ __global__ void __launch_bounds__(256) k_w1_sqnorm(const AgentDev* __restrict__ 
   if (threadIdx.x < 32) {
     float s = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
     for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) atomicAdd(norm2 + j, s);
-  }
+    if (threadIdx.x == 0) norm2[j * W1_MAXB + blockIdx.x] = s;  // per-CTA partial: k_w1_adam adds them in a fixed order, so the
+  }                                                              // norm (and with it every replica's parameters) is reproducible
 }
 
 __global__ void __launch_bounds__(256) k_w1_adam(const AgentDev* __restrict__ agents, int which, int units, int a0,
                                                  float* __restrict__ grads_base, float* __restrict__ m_base, float* __restrict__ v_base,
                                                  const int* __restrict__ adam_t, const float* __restrict__ norm2, float grad_scale,
                                                  float clip, double lr, double beta1, double beta2, float eps, float polyak,
-                                                 int do_polyak) {
-  __shared__ float s_lr_t;
+                                                 int do_polyak, PeerCtx P, const float* __restrict__ reduced) {
+  __shared__ float s_lr_t, s_norm2;
   const int j = a0 + blockIdx.y;
+  const int slot = 12 * j + 6 * which;
+  unsigned epoch = 0;
+  if (P.world > 1) {  // k_w1_sqnorm has completed (stream order): this rank has read every peer's bucket
+    epoch = P.epoch[slot] + 1u;
+    peer_signal(P, slot, epoch + 1u);
+  }
   const AgentDev& ag = agents[j];
   const MlpW& w = ag.net[which == 0 ? MDP_NET_P : MDP_NET_Q];
   const MlpW& wt = ag.net[which == 0 ? MDP_NET_TARGET_P : MDP_NET_TARGET_Q];
@@ -274,18 +349,24 @@ __global__ void __launch_bounds__(256) k_w1_adam(const AgentDev* __restrict__ ag
     const int t = adam_t[2 * j + which];
     s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
   }
+  if (threadIdx.x == 32) {
+    float n2 = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) n2 += norm2[j * W1_MAXB + b];
+    s_norm2 = n2;
+  }
   __syncthreads();
-  const float norm = sqrtf(norm2[j]);
+  const float norm = sqrtf(s_norm2);
   const float factor = (clip > 0.f ? clip / fmaxf(norm, clip) : 1.0f) * grad_scale, lr_t = s_lr_t;
   const float b1 = (float)beta1, b2 = (float)beta2, ob1 = (float)(1.0 - beta1), ob2 = (float)(1.0 - beta2), opol = 1.0f - polyak;
   float4* g4 = reinterpret_cast<float4*>(ag.grad[which].W1);
   const long long goff4 = (ag.grad[which].W1 - grads_base) / 4;
+  const float4* gs4 = P.world > 1 ? reinterpret_cast<const float4*>(reduced) + goff4 : g4;  // the rank-summed gradient
   float4* m4 = reinterpret_cast<float4*>(m_base) + goff4;
   float4* v4 = reinterpret_cast<float4*>(v_base) + goff4;
   float4* p4 = reinterpret_cast<float4*>(const_cast<float*>(w.W1));
   float4* t4 = reinterpret_cast<float4*>(const_cast<float*>(wt.W1));
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len / 4; i += (long long)gridDim.x * blockDim.x) {
-    float4 g = g4[i], m = m4[i], v = v4[i], p = p4[i];
+    float4 g = gs4[i], m = m4[i], v = v4[i], p = p4[i];
     float4 t = do_polyak ? t4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     auto step = [&](float gi, float& mi, float& vi, float& pi, float& ti) {
       gi *= factor;
@@ -297,8 +378,18 @@ __global__ void __launch_bounds__(256) k_w1_adam(const AgentDev* __restrict__ ag
     step(g.x, m.x, v.x, p.x, t.x); step(g.y, m.y, v.y, p.y, t.y); step(g.z, m.z, v.z, p.z, t.z); step(g.w, m.w, v.w, p.w, t.w);
     m4[i] = m; v4[i] = v; p4[i] = p;
     if (do_polyak) t4[i] = t;
-    g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.world <= 1) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (P.world > 1) {  // every rank has read this rank's bucket: only now may it be re-zeroed for the next round
+    peer_wait(P, slot, epoch + 1u);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len / 4; i += (long long)gridDim.x * blockDim.x)
+      g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+// the epoch counters of the W1 slots advance by 2 once every CTA of k_w1_adam is done (stream order)
+__global__ void k_w1_epoch_bump(unsigned* __restrict__ epoch, int which, int a0, int count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < count) epoch[12 * (a0 + k) + 6 * which] += 2u;
 }
 
 // all agents in one launch: grid = (6 variables, n_agents); pointers come from the device agent table
@@ -364,11 +455,13 @@ extern "C" int mdp_core_bind_peers(mdp_core* c, int32_t world, int32_t rank, con
   return MDP_OK;
 }
 
-// W1 of agents [a0, a0 + count) through the many-CTA path when it is wide (single GPU only: with peers bound the gradient sum
-// happens inside the per-variable kernel).  Returns 1 if it handled W1 (the caller then starts at variable 1), 0 if not.
+// W1 of agents [a0, a0 + count) through the many-CTA path when it is wide.  With peers bound this applies to the barrier protocol
+// only (the low-latency protocol keeps small buckets in the per-variable kernel); the rank-summed gradient goes through the
+// local scratch c->peer_reduced.  Returns 1 if it handled W1 (the caller then starts at variable 1), 0 if not.
 static int wide_w1_step(mdp_core* c, int which, int a0, int count, float grad_scale, int do_polyak, cudaStream_t st, int* handled) {
   *handled = 0;
-  if (c->peer_world > 1) return MDP_OK;
+  const bool peers = c->peer_world > 1;
+  if (peers && c->d_peer_recv) return MDP_OK;
   const int U = c->cfg.num_units, net = which == 0 ? MDP_NET_P : MDP_NET_Q;
   long long min_len = 1ll << 60, max_len = 0;
   for (int j = a0; j < a0 + count; ++j) {
@@ -376,17 +469,24 @@ static int wide_w1_step(mdp_core* c, int which, int a0, int count, float grad_sc
     min_len = std::min(min_len, len); max_len = std::max(max_len, len);
   }
   if (min_len < 32768) return MDP_OK;
-  if (!c->norm2) MDP_CUDA(cudaMalloc(&c->norm2, MDP_MAX_AGENTS * sizeof(float)));
-  MDP_CUDA(cudaMemsetAsync(c->norm2 + a0, 0, count * sizeof(float), st));
-  const int nb = (int)std::min<long long>(128, (max_len / 4 + 1023) / 1024);
-  k_w1_sqnorm<<<dim3(nb, count), 256, 0, st>>>(c->d_agents, which, U, a0, grad_scale, c->norm2);
+  if (!c->norm2) MDP_CUDA(cudaMalloc(&c->norm2, MDP_MAX_AGENTS * W1_MAXB * sizeof(float)));
+  if (peers && !c->peer_reduced) MDP_CUDA(cudaMalloc(&c->peer_reduced, (size_t)c->lay.total_train * sizeof(float)));
+  // with peers every CTA spins on the flag barrier: all CTAs of a launch must be co-resident (<= 148 x 8 of 256 threads)
+  const int nb = (int)std::min<long long>(peers ? std::min(W1_MAXB, std::max(1, 592 / count)) : W1_MAXB, (max_len / 4 + 1023) / 1024);
+  const PeerCtx P = peer_ctx(c);
+  k_w1_sqnorm<<<dim3(nb, count), 256, 0, st>>>(c->d_agents, which, U, a0, grad_scale, c->norm2, P, c->grads, c->peer_reduced);
   int rc = check_launch("k_w1_sqnorm");
   if (rc) return rc;
   k_w1_adam<<<dim3(nb, count), 256, 0, st>>>(c->d_agents, which, U, a0, c->grads, c->adam_m, c->adam_v, c->adam_t, c->norm2, grad_scale,
                                              (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps,
-                                             (float)c->cfg.polyak, do_polyak);
+                                             (float)c->cfg.polyak, do_polyak, P, c->peer_reduced);
   rc = check_launch("k_w1_adam");
   if (rc) return rc;
+  if (peers) {
+    k_w1_epoch_bump<<<cdiv(count, 32), 32, 0, st>>>(c->peer_epoch, which, a0, count);
+    rc = check_launch("k_w1_epoch_bump");
+    if (rc) return rc;
+  }
   *handled = 1;
   return MDP_OK;
 }

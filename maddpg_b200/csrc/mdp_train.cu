@@ -913,6 +913,7 @@ extern "C" void mdp_core_destroy(mdp_core* core) {
   if (core->tc_arena) cudaFree(core->tc_arena);
   if (core->tc_dz1) cudaFree(core->tc_dz1);
   if (core->norm2) cudaFree(core->norm2);
+  if (core->peer_reduced) cudaFree(core->peer_reduced);
   if (core->d_peer_tables) cudaFree(core->d_peer_tables);
   delete core;
 }

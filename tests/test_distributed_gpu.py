@@ -12,31 +12,33 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _build_core(dev, B):
+def _build_core(dev, B, n=3):
+    """n = 3: simple_spread N=3 shapes; n = 10: simple_spread N=10 shapes, whose critic W1 (650 x 64 = 41.6 k floats) takes the
+    many-CTA path of the optimizer (mdp_optim.cu: wide_w1_step)."""
     from maddpg_b200 import MADDPGCore
     from maddpg_b200.spaces import Discrete
-    core = MADDPGCore([18, 18, 18], [Discrete(5)] * 3, [False] * 3, device=dev, replay_capacity=4 * B, seed=5)
+    core = MADDPGCore([6 * n] * n, [Discrete(5)] * n, [False] * n, device=dev, replay_capacity=4 * B, seed=5)
     return core
 
 
 def _rows(core, B, seed):
     g = torch.Generator().manual_seed(seed)
-    L = core.ring.layout
+    L, n = core.ring.layout, core.n
     batch = torch.randn(B, core.ring.row_stride, generator=g)
-    act = torch.softmax(torch.randn(B, 3, 5, generator=g), -1).reshape(B, 15)
+    act = torch.softmax(torch.randn(B, n, 5, generator=g), -1).reshape(B, 5 * n)
     batch[:, L.obs_sum:L.x_dim] = act
-    batch[:, L.dn_off:L.dn_off + 3] = (torch.rand(B, 3, generator=g) < 0.1).float()
+    batch[:, L.dn_off:L.dn_off + n] = (torch.rand(B, n, generator=g) < 0.1).float()
     return batch
 
 
-def _worker(rank, world, port, B, out, peer=False, low_latency=None):
+def _worker(rank, world, port, B, out, peer=False, low_latency=None, n=3):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from maddpg_b200.distributed import DataParallelUpdater
-    core = _build_core(dev, B)
+    core = _build_core(dev, B, n)
     dp = DataParallelUpdater(core, peer=peer, low_latency=low_latency)
     dp.broadcast_params(core.params)
     full = _rows(core, world * B, 1)
@@ -44,7 +46,7 @@ def _worker(rank, world, port, B, out, peer=False, low_latency=None):
     ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6)
     sl = slice(rank * B, (rank + 1) * B)
     for rnd in range(2 if peer else 1):  # two rounds: the flag epochs and the re-zeroed buckets are exercised
-        for j in range(3):
+        for j in range(n):
             dp.update_agent(j, full[sl].contiguous().to(dev), ut[sl].contiguous().to(dev), ua[sl].contiguous().to(dev))
     torch.cuda.synchronize()
     out[rank] = core.params.cpu().numpy()
@@ -92,5 +94,24 @@ def test_two_rank_peer_exchange_matches_union_batch(low_latency):
     ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6).cuda()
     for rnd in range(2):
         for j in range(3):
+            core.update_agent(j, full, ut, ua)
+    np.testing.assert_allclose(out_p[0], core.params.cpu().numpy(), rtol=3e-3, atol=5e-4)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_peer_exchange_wide_critic_many_cta_path():
+    """Barrier protocol with a critic W1 wide enough for the many-CTA optimizer path (k_w1_sqnorm sums the ranks' buckets with
+    peer loads into a local scratch, k_w1_adam steps from it): identical replicas after two rounds, matching the union batch."""
+    B, world, n = 128, 2, 10
+    mgr = mp.Manager()
+    out_p = mgr.dict()
+    mp.spawn(_worker, args=(world, 28700 + os.getpid() % 500, B, out_p, True, False, n), nprocs=world, join=True)
+    assert np.array_equal(out_p[0], out_p[1]), "replicas diverged (peer exchange, wide W1)"
+    core = _build_core(torch.device("cuda", 0), B, n)
+    full = _rows(core, world * B, 1).cuda()
+    ut = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(2)).clamp_(1e-6, 1 - 1e-6).cuda()
+    ua = torch.rand(world * B, core.act_stride, generator=torch.Generator().manual_seed(3)).clamp_(1e-6, 1 - 1e-6).cuda()
+    for rnd in range(2):
+        for j in range(n):
             core.update_agent(j, full, ut, ua)
     np.testing.assert_allclose(out_p[0], core.params.cpu().numpy(), rtol=3e-3, atol=5e-4)
