@@ -336,6 +336,34 @@ int mdp_ctl_advance(uint64_t* ctl, uint64_t d_counter, int64_t d_rows, int64_t c
 int mdp_replay_make_index(int64_t* idx_out, int32_t B, int64_t length, uint64_t seed, uint64_t counter,
                           const uint64_t* ctl, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* prioritized replay: SumTree / PrioritizedReplayMemory on the device */
+/* ------------------------------------------------------------------------------------------ */
+/* Replaces /root/reference/maddpg/trainer/prioritized_replay_buffer.py: SumTree (:19-146) and the tree side of
+ * PrioritizedReplayMemory.sample / batch_update (:171-201).  The tree is the reference's array -- 2^(k+1) - 1 float64 nodes,
+ * k = ceil(log2(capacity)), the leaf of data slot d at index d + 2^k - 2 -- caller-owned, zero-initialised; `scratch` is a
+ * caller-owned device array of `scratch_doubles` float64.  Rows are stored by mdp_replay_insert and read back by
+ * mdp_replay_gather at the returned data indices.  Every float64 rounding follows the reference (sums of the children's deltas
+ * in update_all, one delta per ancestor in batch order in update), so sampled indices are bit-exact given the same uniforms. */
+int mdp_sumtree_layout(int64_t capacity, int64_t* tree_size, int32_t* k_out, int64_t* scratch_doubles);
+/* SumTree.update_all (:58-100) for the adds still pending: data slots [start, start + count) (circular) take priority `value`
+ * (SumTree.add (:45-56) defers its tree update to the next get_leaf; callers keep the pending range and pass it here or to
+ * mdp_sumtree_sample). */
+int mdp_sumtree_flush(double* tree, int64_t capacity, int64_t start, int64_t count, double value, double* scratch, void* stream);
+/* PrioritizedReplayMemory.sample(n) (:171-194): reads total_p and the minimum over the last `capacity` tree entries, flushes the
+ * pending adds (the first get_leaf does), then n stratified descents with v_i = a_i + (b_i - a_i) * uniforms[i] (numpy's
+ * uniform(a, b)).  Outputs: tree index, data index, IS weight (prob / min_prob) ^ -beta per draw.  *flag |= 1 when a descent
+ * ends on a data index >= capacity, where the reference raises IndexError (slot 0's node, see oracle/prioritized.py). */
+int mdp_sumtree_sample(double* tree, int64_t capacity, int64_t dirty_start, int64_t dirty_count, double dirty_value, int32_t n,
+                       const double* uniforms, double beta, int64_t* tree_idx_out, int64_t* data_idx_out, double* weights_out,
+                       int32_t* flag, double* scratch, void* stream);
+/* PrioritizedReplayMemory.batch_update(tree_idx, abs_errors) (:196-201): p = min(|err| + epsilon, abs_err_upper) ^ alpha (or the
+ * caller's `priorities` when not NULL), then SumTree.update (:102-109) per element in batch order; B <= 4096.  *flag |= 2 when
+ * the batch names a node that is not a true leaf (the one-thread reference loop ran instead of the parallel kernels). */
+int mdp_sumtree_update(double* tree, int64_t capacity, const int64_t* tree_idx, int32_t B, const double* abs_errors,
+                       const double* priorities, double epsilon, double abs_err_upper, double alpha, int32_t* flag,
+                       double* scratch, void* stream);
+
 const char* mdp_last_error(void);
 const char* mdp_version(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */

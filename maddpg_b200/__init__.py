@@ -10,8 +10,8 @@ the library has not been built.
 """
 from . import _lib  # noqa: F401  (raises ImportError when the CUDA library is missing)
 from .env import BatchedMultiAgentEnv, make_env  # noqa: F401
-from .replay import DeviceReplayBuffer, JointReplayRing  # noqa: F401
+from .replay import DevicePrioritizedReplayMemory, DeviceReplayBuffer, JointReplayRing  # noqa: F401
 from .trainer import AgentTrainer, MADDPGAgentTrainer, MADDPGCore  # noqa: F401
 
-__all__ = ["BatchedMultiAgentEnv", "make_env", "DeviceReplayBuffer", "JointReplayRing", "AgentTrainer",
+__all__ = ["BatchedMultiAgentEnv", "make_env", "DeviceReplayBuffer", "DevicePrioritizedReplayMemory", "JointReplayRing", "AgentTrainer",
            "MADDPGAgentTrainer", "MADDPGCore"]

@@ -108,6 +108,11 @@ SYMBOLS = {
     "mdp_core_set_ctl": (C.c_int, [_P, _P]),
     "mdp_ctl_advance": (C.c_int, [_P, C.c_uint64, C.c_int64, C.c_int64, C.c_uint64, _P]),
     "mdp_replay_make_index": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
+    "mdp_sumtree_layout": (C.c_int, [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "mdp_sumtree_flush": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_double, _P, _P]),
+    "mdp_sumtree_sample": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_int32, _P, C.c_double, _P, _P, _P,
+                                     _P, _P, _P]),
+    "mdp_sumtree_update": (C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "mdp_last_error": (C.c_char_p, []),
     "mdp_version": (C.c_char_p, []),
     "mdp_launch_count": (C.c_int64, []),

@@ -127,6 +127,178 @@ __global__ void __launch_bounds__(SPREAD_EB) k_env_step_spread(EnvParams P, int 
   for (int i = tid; i < nE * A; i += SPREAD_EB) dn[i] = 0;
 }
 
+// --------------------------------------------------------------------------------------------
+// simple_spread with 7..32 agents (float32 state): ONE WARP PER ENV INSTANCE, lane = agent = landmark.  BASELINE.json
+// configs[4] (N = 24: 48 entities, 276 collidable pairs, 15 384 B per env step) is the one configuration whose env step is
+// genuinely HBM-sized (504 MB per step at 32 768 env instances).  A lane keeps its agent's state and its landmark in
+// registers; every pairwise term (soft-contact forces, landmark minima, collision counts) runs as a shuffle loop over the
+// entities -- in entity order, with the pinned roundings of spread_agent_step, so the results equal the register kernel's
+// -- and the observation rows are produced column-major across the lanes (lane = column: the partner a column needs is one
+// shuffle away), so every store is a full 128-byte line.  RING: the same warp also writes the joint replay row of the
+// transition (obs_t copied from obs_prev, act_t, next_obs, rew, done) -- ReplayBuffer.add for all agents fused into the
+// step: one pass over the observations instead of the separate insert kernel's re-read (1.85 GB instead of 2.9 GB of traffic
+// per step at the configs[4] size).
+// --------------------------------------------------------------------------------------------
+template <int AT, bool RING>
+__global__ void __launch_bounds__(256) k_env_step_spread_warp(EnvParams P, int E, int ES, float* __restrict__ state,
+                                                              const float* __restrict__ act, float* __restrict__ obs_out,
+                                                              float* __restrict__ rew_out, uint8_t* __restrict__ done_out,
+                                                              const float* __restrict__ obs_prev, float* __restrict__ ring,
+                                                              long long capacity, long long cursor, mdp_ring_layout L,
+                                                              const unsigned long long* __restrict__ ctl) {
+  // positions of the warp's env instance: [0, A) agents, [32, 32 + A) landmarks, as (x, y) pairs; velocities at [64, 64 + A)
+  __shared__ float2 sPos[8][96];
+  const int e = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (e >= E) return;  // warp-uniform
+  float2* sp = sPos[threadIdx.x >> 5];
+  const float* spf = reinterpret_cast<const float*>(sp);
+  const unsigned FULL = 0xffffffffu;
+  // AT > 0: the agent count is a template constant -- every loop over the entities unrolls, the per-agent values a lane needs
+  // for its observation columns live in registers and the row offsets become store immediates (BASELINE configs[4]: 24)
+  const int A = AT ? AT : P.A, D = 6 * A, OS = P.obs_stride, AS = P.act_stride;
+  const bool live = lane < A;
+  const int li = live ? lane : 0;
+  float px = state[(size_t)(4 * li + 0) * ES + e], py = state[(size_t)(4 * li + 1) * ES + e];
+  float vx = state[(size_t)(4 * li + 2) * ES + e], vy = state[(size_t)(4 * li + 3) * ES + e];
+  const float lx = state[(size_t)(4 * A + 2 * li + 0) * ES + e], ly = state[(size_t)(4 * A + 2 * li + 1) * ES + e];
+  const float* arow = act + (size_t)e * AS + 5 * li;
+  const float a1 = arow[1], a2 = arow[2], a3 = arow[3], a4 = arow[4];
+  const float k = (float)P.contact_margin, cf = (float)P.contact_force, damp = 1.0f - (float)P.damping, dt = (float)P.dt;
+  const float si = P.sizef[li], sens = (float)P.sens[li], ms = (float)P.max_speed[li];
+  sp[lane] = make_float2(px, py);
+  sp[32 + lane] = make_float2(lx, ly);
+  __syncwarp();
+  // World.step: action force, then the soft contact with every other agent in agent order (landmarks do not collide).
+  // A pair further apart than dmin + 0.11 has z = -(dist - dmin) / k < -104: exp(z) underflows and the penetration is exactly 0
+  // -- decided on the squared distance, so that far pairs (nearly all of them) cost neither the sqrt nor the division.
+  float fx = __fmul_rn(__fsub_rn(a1, a2), sens), fy = __fmul_rn(__fsub_rn(a3, a4), sens);
+  unsigned near = 0;  // pass 1 (unrolled, branch-free): which agents are close enough for a non-zero force
+#pragma unroll
+  for (int j = 0; j < A; ++j) {
+    const float2 pj = sp[j];
+    const float d2 = sq_norm2(__fsub_rn(px, pj.x), __fsub_rn(py, pj.y));
+    const float far = __fadd_rn(si, P.sizef[j]) + 0.11f;
+    near |= (d2 <= far * far ? 1u : 0u) << j;
+  }
+  near &= ~(1u << lane);
+  while (near) {  // pass 2: the few contact pairs, in agent order (one copy of the IEEE sqrt / div / exp / log1p code)
+    const int j = __ffs(near) - 1;
+    near &= near - 1;
+    const float2 pj = sp[j];
+    const float dx = __fsub_rn(px, pj.x), dy = __fsub_rn(py, pj.y);
+    const float dmin = __fadd_rn(si, P.sizef[j]);
+    const float dist = __fsqrt_rn(sq_norm2(dx, dy));
+    const float z = __fdiv_rn(-__fsub_rn(dist, dmin), k);
+    if (z < -104.0f) continue;
+    const float pen = __fmul_rn(logaddexp0<float>(z), k);
+    fx = __fmaf_rn(__fdiv_rn(__fmul_rn(cf, dx), dist), pen, fx);
+    fy = __fmaf_rn(__fdiv_rn(__fmul_rn(cf, dy), dist), pen, fy);
+  }
+  float wx = __fmaf_rn(fx, dt, __fmul_rn(vx, damp)), wy = __fmaf_rn(fy, dt, __fmul_rn(vy, damp));
+  if (ms > 0.f) {
+    const float speed = __fsqrt_rn(sq_norm2(wx, wy));
+    if (speed > ms) { wx = __fmul_rn(__fdiv_rn(wx, speed), ms); wy = __fmul_rn(__fdiv_rn(wy, speed), ms); }
+  }
+  vx = wx; vy = wy;
+  px = __fmaf_rn(wx, dt, px);
+  py = __fmaf_rn(wy, dt, py);
+  __syncwarp();  // every lane has read the old positions
+  sp[lane] = make_float2(px, py);
+  sp[64 + lane] = make_float2(vx, vy);
+  if (live) {
+    state[(size_t)(4 * lane + 0) * ES + e] = px; state[(size_t)(4 * lane + 1) * ES + e] = py;
+    state[(size_t)(4 * lane + 2) * ES + e] = vx; state[(size_t)(4 * lane + 3) * ES + e] = vy;
+  }
+  __syncwarp();
+  // Scenario.reward from the new positions: lane l = landmark l's closest agent (sqrt is monotone: the minimum of the distances
+  // is the sqrt of the minimum squared distance, bit for bit), lane i = agent i's collision count (sqrt only near the threshold)
+  float best2 = 0.f;
+  int cnt = 0;
+#pragma unroll
+  for (int q = 0; q < A; ++q) {
+    const float2 pq = sp[q];
+    const float d2l = sq_norm2(__fsub_rn(pq.x, lx), __fsub_rn(pq.y, ly));
+    best2 = (q == 0 || d2l < best2) ? d2l : best2;
+    const float d2a = sq_norm2(__fsub_rn(pq.x, px), __fsub_rn(pq.y, py));
+    const float s = __fadd_rn(P.sizef[q], si), s2 = s * s;
+    cnt += d2a < 0.999f * s2 ? 1 : d2a > 1.001f * s2 ? 0 : (__fsqrt_rn(d2a) < s ? 1 : 0);
+  }
+  const float best = __fsqrt_rn(best2);
+  float ri = 0.f;
+#pragma unroll
+  for (int l = 0; l < A; ++l) ri -= __shfl_sync(FULL, best, l);
+  ri -= (float)cnt;
+  float msum = 0.f;  // shared reward: every agent receives the sum over agents, accumulated in agent order
+#pragma unroll
+  for (int i = 0; i < A; ++i) msum += __shfl_sync(FULL, ri, i);
+  if (live) {
+    rew_out[(size_t)e * A + lane] = msum;
+    done_out[(size_t)e * A + lane] = 0;
+  }
+  // replay row of this transition (RING): obs_t | act_t from the caller's arrays, rew / done here, next_obs below
+  float* row = nullptr;
+  if (RING) {
+    if (ctl) cursor = (cursor + (long long)ctl[1]) % capacity;
+    row = ring + ((cursor + e) % capacity) * (long long)L.row_stride;
+    const float* op = obs_prev + (size_t)e * OS;
+    if ((L.obs_sum & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(op);
+      float4* d4 = reinterpret_cast<float4*>(row);
+      const int n4 = L.obs_sum >> 2;
+      int c = lane;
+      for (; c + 96 < n4; c += 128) {  // four independent 16-byte loads in flight per lane
+        const float4 v0 = __ldcs(s4 + c), v1 = __ldcs(s4 + c + 32), v2 = __ldcs(s4 + c + 64), v3 = __ldcs(s4 + c + 96);
+        __stcs(d4 + c, v0); __stcs(d4 + c + 32, v1); __stcs(d4 + c + 64, v2); __stcs(d4 + c + 96, v3);
+      }
+      for (; c < n4; c += 32) __stcs(d4 + c, __ldcs(s4 + c));
+    } else {
+      for (int c = lane; c < L.obs_sum; c += 32) row[c] = op[c];
+    }
+    const float* ap = act + (size_t)e * AS;
+    for (int c = lane; c < L.act_sum; c += 32) row[L.obs_sum + c] = ap[c];
+    if (live) { row[L.rw_off + lane] = msum; row[L.dn_off + lane] = 0.f; }
+  }
+  // Scenario.observation; lane = column (mod 32), so a lane's component (x / y) is its parity in every 32-column chunk:
+  //   [vel(2) pos(2) | landmarks - pos (2A) | other agents - pos (2(A-1)) | silent comm zeros (2(A-1))]
+  // A column of row i is  base - m * p_i  with (base, m) fixed per chunk and lane: landmark columns base = the landmark's
+  // component; "other agent" columns base = agent t's component for rows i > t and agent t+1's for rows i <= t; comm columns
+  // base = m = 0.  So a row costs one select, one FFMA (exactly base - p_i: one rounding) and the store.
+  float* orow = obs_out + (size_t)e * OS;
+  float* nrow = RING ? row + L.nx_off : nullptr;
+  const int c_lm = 4, c_ot = 4 + 2 * A, c_cm = c_ot + 2 * (A - 1);
+  const int comp = lane & 1;
+  float pc[AT ? AT : 1];  // this lane's component of every agent's position
+  if (AT) {
+#pragma unroll
+    for (int i = 0; i < (AT ? AT : 1); ++i) pc[i] = spf[2 * i + comp];
+  }
+#pragma unroll
+  for (int c0 = 0; c0 < D; c0 += 32) {
+    const int c = c0 + lane;
+    const int kind = c < c_lm ? 0 : c < c_ot ? 1 : c < c_cm ? 2 : 3;
+    const int t = kind == 1 ? (c - c_lm) >> 1 : kind == 2 ? (c - c_ot) >> 1 : 0;
+    const float b_hi = kind == 1 ? spf[64 + 2 * t + comp] : kind == 2 ? spf[2 * (t + 1) + comp] : 0.f;  // rows i <= t
+    const float b_lo = kind == 2 ? spf[2 * t + comp] : b_hi;                                            // rows i > t
+    const float m = (kind == 1 || kind == 2) ? -1.0f : 0.0f;
+    const int thr = kind == 2 ? t : 1 << 30;
+    const bool on = c < D;
+    const int k0 = (c < 2 ? 128 : 0) + comp;  // kind 0: velocity (columns 0, 1) or position (2, 3) of the row's agent
+    float* o = orow + c;
+    float* n = RING ? nrow + c : nullptr;
+#pragma unroll
+    for (int i = 0; i < A; ++i) {
+      const float pci = AT ? pc[AT ? i : 0] : spf[2 * i + comp];
+      float v = __fmaf_rn(pci, m, i > thr ? b_lo : b_hi);
+      if (c0 == 0 && kind == 0) v = spf[k0 + 2 * i];
+      if (on) {
+        o[i * D] = v;
+        if (RING) n[i * D] = v;
+      }
+    }
+  }
+  for (int c = A * D + lane; c < OS; c += 32) orow[c] = 0.f;
+}
+
 // Scenario.benchmark_data(agent, world) (the info_n tape of `train.py --benchmark`, train.py:139-148) for every (env, agent):
 // four floats.  simple_spread: (reward, collisions, sum over landmarks of the closest agent's distance, occupied landmarks);
 // simple_tag / simple_world_comm: (collisions with good agents, 0, 0, 0) for adversaries, zeros for good agents; simple: zeros.
@@ -346,9 +518,36 @@ static int launch_spread(mdp_env* env, int E, int ES, float* state, const float*
   return check_launch("k_env_step_spread");
 }
 
+// simple_spread, 7..32 agents, float32 state: warp-per-env kernel; lay != null fuses the joint replay insert into the step
+static bool spread_warp_ok(const mdp_env* env) {
+  return !env->cfg.state_f64 && env->P.scenario == MDP_SIMPLE_SPREAD && !env->force_generic && env->P.A > 6 && env->P.A <= 32;
+}
+static int launch_spread_warp(mdp_env* env, int E, int ES, float* state, const float* act, float* obs, float* rew, uint8_t* done,
+                              const float* obs_prev, float* ring, long long capacity, long long cursor, const mdp_ring_layout* lay,
+                              cudaStream_t st) {
+  const int grid = cdiv(E, 8);
+  mdp_ring_layout none;
+  memset(&none, 0, sizeof(none));
+#define MDP_WARP_LAUNCH(AT)                                                                                                 \
+  do {                                                                                                                      \
+    if (lay)                                                                                                                \
+      k_env_step_spread_warp<AT, true><<<grid, 256, 0, st>>>(env->P, E, ES, state, act, obs, rew, done, obs_prev, ring, capacity, \
+                                                             cursor, *lay, env->ctl);                                      \
+    else                                                                                                                    \
+      k_env_step_spread_warp<AT, false><<<grid, 256, 0, st>>>(env->P, E, ES, state, act, obs, rew, done, nullptr, nullptr, 1, 0,  \
+                                                              none, nullptr);                                              \
+  } while (0)
+  if (env->P.A == 24) MDP_WARP_LAUNCH(24);  // BASELINE configs[4]: every entity loop unrolled
+  else MDP_WARP_LAUNCH(0);
+#undef MDP_WARP_LAUNCH
+  return check_launch("k_env_step_spread_warp");
+}
+
 template <typename real, bool DO_STEP>
 static int launch_step(mdp_env* env, int E, int ES, void* state, const float* act, float* obs, float* rew, uint8_t* done,
                        cudaStream_t st) {
+  if (DO_STEP && sizeof(real) == 4 && spread_warp_ok(env))
+    return launch_spread_warp(env, E, ES, (float*)state, act, obs, rew, done, nullptr, nullptr, 1, 0, nullptr, st);
   if (DO_STEP && sizeof(real) == 4 && env->P.scenario == MDP_SIMPLE_SPREAD && !env->force_generic) {
     switch (env->P.A) {
       case 2: return launch_spread<2>(env, E, ES, (float*)state, act, obs, rew, done, st);
@@ -460,6 +659,19 @@ int mdp::env_step_range(mdp_env* env, int32_t E, int32_t e_base, int32_t n, void
   obs_out += (size_t)e_base * d.obs_stride;
   rew_out += (size_t)e_base * d.n_agents;
   done_out += (size_t)e_base * d.n_agents;
+  if (ring && spread_warp_ok(env)) {  // the step kernel writes the replay rows itself
+    MDP_REQUIRE(obs_prev && obs_prev != obs_out, "mdp_env_step: ring insert needs a distinct obs_prev buffer");
+    mdp_ring_layout lay;
+    rc = mdp_ring_make_layout(d.n_agents, d.obs_dim, d.act_dim, &lay);
+    if (rc) return rc;
+    MDP_REQUIRE(lay.row_stride == ring_row_stride, "mdp_env_step: ring_row_stride %d != layout %d", ring_row_stride,
+                lay.row_stride);
+    MDP_REQUIRE(ring_capacity > 0 && n <= ring_capacity && ring_cursor >= 0 && ring_cursor < ring_capacity,
+                "mdp_env_step: bad ring sizes (capacity %lld, cursor %lld, E %d)", (long long)ring_capacity, (long long)ring_cursor, n);
+    return launch_spread_warp(env, n, E, (float*)state + e_base, act, obs_out, rew_out, done_out,
+                              obs_prev + (size_t)e_base * d.obs_stride, ring, ring_capacity, (ring_cursor + e_base) % ring_capacity,
+                              &lay, st);
+  }
   if (env->cfg.state_f64)
     rc = launch_step<double, true>(env, n, E, (double*)state + e_base, act, obs_out, rew_out, done_out, st);
   else

@@ -226,3 +226,147 @@ class DeviceReplayBuffer(object):
 
     def collect(self):
         return self.sample(-1)
+
+
+class DevicePrioritizedReplayMemory(object):
+    """Device-resident mirror of ``PrioritizedReplayMemory`` (maddpg/trainer/prioritized_replay_buffer.py:149-201; SumTree :19-146).
+
+    Same surface: ``add(obs_t, action, reward, obs_tp1, done)``, ``sample(n) -> (b_idx, b_memory, ISWeights)``,
+    ``batch_update(tree_idx, abs_errors)`` and the class constants.  The rows live in a one-agent ``JointReplayRing`` (the same
+    insert / gather kernels as the uniform buffer), the sum tree is the reference's float64 array on the GPU
+    (``mdp_sumtree_*``, csrc/mdp_prio.cu).  Given the same uniforms the returned tree indices are bit-exact, quirks included
+    (oracle/prioritized.py lists them; tests/golden/prioritized_ref.npz pins them to the real class):
+
+    * ``add`` defers the tree update to the next ``sample`` exactly like ``SumTree.add(update=False)``;
+    * ``sample`` raises ``IndexError`` where the reference does (a descent through data slot 0's node) when ``strict``;
+    * ``sample`` draws its uniforms from ``np.random`` like the reference (one ``random_sample`` per stratum: the same global
+      stream as the reference's ``np.random.uniform(a, b)`` calls) unless ``uniforms`` is passed;
+    * ``batch_update`` adds ``epsilon`` IN PLACE to a numpy ``abs_errors`` argument, as the reference does.
+
+    Differences kept visible: ``b_idx`` / ``ISWeights`` are arrays instead of python lists, ``b_memory`` is
+    ``[obs (n, D), act (n, K), rew (n,), obs_tp1 (n, D), done (n,)]`` (float32 rows) instead of tuples of the stored python
+    objects, and ``add`` also accepts device tensors with a leading env axis (E lockstep transitions = E consecutive adds).
+    Priorities: host inputs are converted with numpy's ``power`` (bit-identical to the reference); device inputs use CUDA's
+    ``pow`` (<= 2 ulp, so tree values may differ from the reference's in the last bit)."""
+    epsilon = 0.01
+    alpha = 0.6
+    beta = 0.4
+    beta_increment_per_sampling = 0.001
+    abs_err_upper = 1.0
+    max_p = 1e6  # :165
+
+    def __init__(self, capacity, device="cuda", numpy_io=True, strict=True):
+        self.capacity = int(capacity)
+        self.device = torch.device(device)
+        self.numpy_io = numpy_io
+        self.strict = strict
+        size, k, scratch = C.c_int64(), C.c_int32(), C.c_int64()
+        _lib.check(_lib.lib.mdp_sumtree_layout(self.capacity, C.byref(size), C.byref(k), C.byref(scratch)), "mdp_sumtree_layout")
+        self.k, self.tree_size = int(k.value), int(size.value)
+        self.parent_nodes = 2 ** self.k - 1
+        self.tree = torch.zeros(self.tree_size, dtype=torch.float64, device=self.device)
+        self._scratch = torch.zeros(int(scratch.value), dtype=torch.float64, device=self.device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ring = None            # allocated at the first add (row shapes are the caller's)
+        self._buf = None
+        self.dirty_start, self.dirty_count = 0, 0
+
+    @property
+    def data_pointer(self):
+        return 0 if self.ring is None else self.ring.next_idx[0]
+
+    @property
+    def total_p(self):
+        return float(self.tree[0].item())
+
+    def _ensure_ring(self, D, K):
+        if self.ring is None:
+            self.ring = JointReplayRing([D], [K], capacity=self.capacity, device=self.device)
+            self._buf = DeviceReplayBuffer(self.ring, 0, numpy_io=self.numpy_io)
+
+    def add(self, obs_t, action, reward, obs_tp1, done):
+        if isinstance(obs_t, torch.Tensor) and obs_t.is_cuda:
+            E, D, K = obs_t.shape[0], obs_t.shape[1], action.shape[1]
+        else:
+            o = np.asarray(obs_t)
+            E = 1 if o.ndim <= 1 else o.shape[0]
+            D, K = o.size // E, np.asarray(action).size // E
+            if o.ndim == 0:
+                obs_t, obs_tp1 = o.reshape(1), np.asarray(obs_tp1).reshape(1)
+            if np.asarray(action).ndim == 0:
+                action = np.asarray(action).reshape(1)
+        if E > self.capacity:  # more rows than slots: consecutive adds, the later rows overwrite the earlier ones
+            sl = lambda x, a, b: x[a:b] if (isinstance(x, (torch.Tensor, np.ndarray)) and x.ndim > 0) else x
+            for lo in range(0, E, self.capacity):
+                hi = min(E, lo + self.capacity)
+                self.add(sl(obs_t, lo, hi), sl(action, lo, hi), sl(reward, lo, hi), sl(obs_tp1, lo, hi), sl(done, lo, hi))
+            return
+        self._ensure_ring(D, K)
+        if self.dirty_count == 0:
+            self.dirty_start = self.ring.next_idx[0]
+        self._buf.add(obs_t, action, reward, obs_tp1, done)
+        self.dirty_count = min(self.capacity, self.dirty_count + E)
+        if self.dirty_count == self.capacity:
+            self.dirty_start = 0
+
+    def flush(self):
+        """SumTree.update_all for the pending adds (sample() does this itself, like the reference's get_leaf)."""
+        if self.dirty_count:
+            _lib.check(_lib.lib.mdp_sumtree_flush(_lib.ptr(self.tree), self.capacity, self.dirty_start, self.dirty_count,
+                                                  self.max_p, _lib.ptr(self._scratch), _lib.current_stream()), "mdp_sumtree_flush")
+            self.dirty_count = 0
+
+    def sample(self, n, uniforms=None):
+        n = int(n)
+        if uniforms is None:
+            uniforms = np.random.random_sample(n)
+        if isinstance(uniforms, torch.Tensor):
+            u = uniforms.to(device=self.device, dtype=torch.float64)
+        else:
+            u = torch.as_tensor(np.ascontiguousarray(uniforms, dtype=np.float64)).to(self.device)
+        self.beta = float(np.min([1.0, self.beta + self.beta_increment_per_sampling]))
+        tidx = torch.empty(n, dtype=torch.int64, device=self.device)
+        didx = torch.empty(n, dtype=torch.int64, device=self.device)
+        isw = torch.empty(n, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib.mdp_sumtree_sample(_lib.ptr(self.tree), self.capacity, self.dirty_start, self.dirty_count, self.max_p,
+                                               n, _lib.ptr(u), self.beta, _lib.ptr(tidx), _lib.ptr(didx), _lib.ptr(isw),
+                                               _lib.ptr(self.flag), _lib.ptr(self._scratch), _lib.current_stream()),
+                   "mdp_sumtree_sample")
+        self.dirty_count = 0
+        if self.strict:
+            if int(self.flag.item()) & 1:
+                raise IndexError("list index out of range")  # prioritized_replay_buffer.py:142 (self.data[data_idx])
+        else:
+            didx = didx.clamp(max=self.capacity - 1)
+        self.last_data_idx = didx
+        if self.ring is None:
+            raise IndexError("sample from an empty memory")
+        b_memory = list(self._buf.sample_index(didx))
+        if self.numpy_io:
+            return tidx.cpu().numpy(), b_memory, isw.cpu().numpy()
+        return tidx, b_memory, isw
+
+    def priorities(self, abs_errors):
+        """:197-199 on the host (numpy's power: bit-identical to the reference)."""
+        e = np.asarray(abs_errors, dtype=np.float64) + self.epsilon
+        return np.power(np.minimum(e, self.abs_err_upper), self.alpha)
+
+    def batch_update(self, tree_idx, abs_errors):
+        if isinstance(tree_idx, torch.Tensor):
+            ti = tree_idx.to(device=self.device, dtype=torch.int64)
+        else:
+            ti_h = np.asarray(tree_idx, dtype=np.int64)
+            if ti_h.size and (ti_h.max() >= self.tree_size or ti_h.min() < -self.tree_size):
+                raise IndexError("list index out of range")
+            ti = torch.as_tensor(ti_h).to(self.device)
+        B = int(ti.shape[0])
+        if isinstance(abs_errors, torch.Tensor) and abs_errors.is_cuda:
+            err, prio = abs_errors.to(torch.float64).contiguous(), None
+        else:
+            ps = self.priorities(abs_errors)
+            if isinstance(abs_errors, np.ndarray) and abs_errors.dtype == np.float64:
+                abs_errors += self.epsilon  # the reference's in-place side effect (:197)
+            err, prio = None, torch.as_tensor(ps).to(self.device)
+        _lib.check(_lib.lib.mdp_sumtree_update(_lib.ptr(self.tree), self.capacity, _lib.ptr(ti), B, _lib.ptr(err), _lib.ptr(prio),
+                                               self.epsilon, self.abs_err_upper, self.alpha, _lib.ptr(self.flag),
+                                               _lib.ptr(self._scratch), _lib.current_stream()), "mdp_sumtree_update")

@@ -189,9 +189,10 @@ def test_step_with_fused_ring_insert():
         assert torch.equal(got[k % 250, used], allrows[k, used]), k
 
 
-@pytest.mark.parametrize("A,E", [(2, 77), (3, 4096 + 5), (4, 130), (5, 64), (6, 129)])
+@pytest.mark.parametrize("A,E", [(2, 77), (3, 4096 + 5), (4, 130), (5, 64), (6, 129), (7, 67), (24, 263), (32, 40)])
 def test_spread_register_kernel_matches_table_driven_kernel(A, E):
-    """simple_spread fast path (one thread per env, registers) vs the table-driven kernel on the same Philox
+    """simple_spread fast paths (A <= 6: one thread per env, registers; A = 7..32: one warp per env, lane = agent, shuffle
+    loops over the entities) vs the table-driven kernel on the same Philox
     resets and action tape, 30 steps with contacts.  Both kernels start every step from the same state (the stiff
     contact model amplifies last-bit differences ~100x per contact step), so the comparison
     isolates one step of arithmetic."""
@@ -259,3 +260,32 @@ def test_benchmark_env_fills_info_n():
     _, _, _, info2 = env2.step([np.tile(np.eye(5, dtype=np.float32)[0], (4, 1)) for _ in range(env2.n)])
     assert all(x.shape == (4,) and x.dtype == np.int64 for x in info2["n"])
     assert make_env("simple_spread", num_envs=1).step(act_n)[3] == {"n": [{} for _ in range(3)]}
+
+
+@pytest.mark.parametrize("A,E", [(24, 101), (8, 300)])
+def test_spread_warp_kernel_fused_ring_insert_matches_separate_insert(A, E):
+    """simple_spread, one warp per env instance: the step kernel writes the joint replay rows itself (ReplayBuffer.add fused
+    into env.step); the table-driven kernel + the separate insert kernel must produce the same ring, incl. the wrap-around."""
+    from maddpg_b200 import BatchedMultiAgentEnv, MADDPGCore
+    rings = []
+    for generic in (False, True):
+        env = BatchedMultiAgentEnv("simple_spread", num_envs=E, num_agents=A, squeeze=False, seed=5)
+        env.force_generic_kernel(generic)
+        core = MADDPGCore(env.obs_dims, env.action_space, [False] * A, replay_capacity=2 * E + 7, seed=1)
+        core.ring.ring.zero_()
+        env.reset_device()
+        g = torch.Generator(device="cuda").manual_seed(3)
+        states = []
+        for t in range(3):  # 3 E rows into a ring of 2 E + 7: wraps
+            act = torch.softmax(3.0 * torch.randn((E, env.act_stride), device="cuda", generator=g), -1)
+            if rings:
+                env.state.copy_(rings[0][2][t])  # same pre-step state as the fast path (isolates one step of arithmetic)
+            states.append(env.state.clone())
+            env.step_device(act, ring=core.ring)
+        rings.append((core.ring.ring.cpu(), list(core.ring.next_idx), states))
+    (r0, n0, _), (r1, n1, _) = rings
+    assert n0 == n1
+    L = core.ring.layout
+    used = list(range(0, L.x_dim)) + list(range(L.nx_off, L.nx_off + L.obs_sum)) + list(range(L.rw_off, L.dn_off + A))
+    torch.testing.assert_close(r0[:, used], r1[:, used], rtol=1e-5, atol=1e-5)
+    assert torch.equal(r0[:, L.obs_sum:L.x_dim], r1[:, L.obs_sum:L.x_dim])  # act_t is a copy of the same tape: bit-identical
