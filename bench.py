@@ -467,7 +467,7 @@ def main():
     peak, peak_src = measured_peak_hbm()
     env_bytes = env.env_bytes_per_step * E
     achieved = env_bytes / (env_us * 1e-6) / 1e9
-    env_kernel = ("k_env_step_spread<%d>" % A if A <= 6 else "k_env_step_spread_warp<false>") if SCENARIO == "simple_spread" \
+    env_kernel = ("k_env_step_spread<%d>" % A if A <= 6 else "k_env_step_spread_warp<%d,false>" % (A if A == 24 else 0)) if SCENARIO == "simple_spread" \
         else "k_env_step<float> (table-driven)"
     # the same per-step kernel where it is actually HBM-sized: 2^20 env instances (431 MB per step)
     big = None
