@@ -45,7 +45,10 @@ extern "C" {
 enum { MDP_OK = 0, MDP_EINVAL = -1, MDP_ECUDA = -2, MDP_ENOTSUP = -3 };
 
 /* scenario ids: multiagent/scenarios/<name>.py, loaded at experiments/train.py:53 */
-enum { MDP_SIMPLE = 0, MDP_SIMPLE_SPREAD = 1, MDP_SIMPLE_TAG = 2, MDP_SIMPLE_WORLD_COMM = 3 };
+enum { MDP_SIMPLE = 0, MDP_SIMPLE_SPREAD = 1, MDP_SIMPLE_TAG = 2, MDP_SIMPLE_WORLD_COMM = 3,
+       /* the other scenarios `train.py --scenario` can name (simple_reference is not built: its
+        * MultiDiscrete([5, 10]) action block is wider than the 9 action columns the update kernels carry per agent) */
+       MDP_SIMPLE_ADVERSARY = 4, MDP_SIMPLE_PUSH = 5, MDP_SIMPLE_SPEAKER_LISTENER = 6, MDP_SIMPLE_CRYPTO = 7 };
 
 typedef struct mdp_env_cfg {
   int32_t scenario;   /* MDP_SIMPLE ... */
@@ -59,9 +62,15 @@ typedef struct mdp_env_dims {
   int32_t obs_off[MDP_MAX_AGENTS], act_off[MDP_MAX_AGENTS];
   int32_t n_heads[MDP_MAX_AGENTS], head_dim[MDP_MAX_AGENTS][MDP_MAX_HEADS];
   int32_t obs_sum, act_sum, obs_stride, act_stride;
-  int32_t state_comps;     /* 4*n_agents + comm_dim + 2*n_landmarks */
+  int32_t state_comps;     /* 4*n_agents + comm_dim + 2*n_landmarks + n_goal */
   int32_t state_elem_size; /* 4 or 8 */
   int32_t env_bytes_per_step; /* algorithmic bytes of one env step, SURVEY 8(d) formula (fp32 state) */
+  /* SoA state rows: [4i .. 4i+3] = agent i's (x, y, vx, vy); [4A + comm_off[i], + comm_len[i]) = agent i's state.c (speaking
+   * agents only; comm_dim is the sum); then 2 rows per landmark; then n_goal rows holding the landmark indices reset_world
+   * drew with np.random.choice (agent.goal_a / goal_b / key), stored as numbers of the state's type */
+  int32_t n_goal;
+  int32_t comm_off[MDP_MAX_AGENTS], comm_len[MDP_MAX_AGENTS];
+  int32_t movable[MDP_MAX_AGENTS];
 } mdp_env_dims;
 
 typedef struct mdp_env mdp_env;

@@ -11,7 +11,8 @@ MAX_AGENTS = 32
 MAX_HEADS = 2
 
 MDP_OK, MDP_EINVAL, MDP_ECUDA, MDP_ENOTSUP = 0, -1, -2, -3
-SCENARIO_IDS = {"simple": 0, "simple_spread": 1, "simple_tag": 2, "simple_world_comm": 3}
+SCENARIO_IDS = {"simple": 0, "simple_spread": 1, "simple_tag": 2, "simple_world_comm": 3,
+                "simple_adversary": 4, "simple_push": 5, "simple_speaker_listener": 6, "simple_crypto": 7}
 NET_P, NET_TARGET_P, NET_Q, NET_TARGET_Q = 0, 1, 2, 3
 
 _I32A = C.c_int32 * MAX_AGENTS
@@ -32,7 +33,8 @@ class EnvDims(C.Structure):
                 ("obs_dim", _I32A), ("act_dim", _I32A), ("obs_off", _I32A), ("act_off", _I32A),
                 ("n_heads", _I32A), ("head_dim", _I32AH),
                 ("obs_sum", C.c_int32), ("act_sum", C.c_int32), ("obs_stride", C.c_int32), ("act_stride", C.c_int32),
-                ("state_comps", C.c_int32), ("state_elem_size", C.c_int32), ("env_bytes_per_step", C.c_int32)]
+                ("state_comps", C.c_int32), ("state_elem_size", C.c_int32), ("env_bytes_per_step", C.c_int32),
+                ("n_goal", C.c_int32), ("comm_off", _I32A), ("comm_len", _I32A), ("movable", _I32A)]
 
 
 class RingLayout(C.Structure):

@@ -375,8 +375,8 @@ static int build_env(mdp_env* env) {
   P.scenario = sc;
   P.dt = 0.1; P.damping = 0.25; P.contact_force = 1e+2; P.contact_margin = 1e-3;
   int A = 0, L = 0;
+  uint32_t movable = 0xffffffffu;
   env->reset_lo_lm = -1.f; env->reset_hi_lm = 1.f;
-  P.silent_mask = 0xffffffffu;
   if (sc == MDP_SIMPLE) {
     A = 1; L = 1; P.cdim = 0; P.collide_mask = 0;
     P.size[0] = 0.05; P.size[1] = 0.05; P.sens[0] = 5.0; P.max_speed[0] = -1;
@@ -403,17 +403,50 @@ static int build_env(mdp_env* env) {
       P.size[i] = adv ? 0.075 : 0.045; P.sens[i] = adv ? 3.0 : 4.0; P.max_speed[i] = adv ? 1.0 : 1.3;
       P.collide_mask |= 1ull << i;
     }
-    P.silent_mask &= ~1u;  // agent 0 (leader) speaks
+    // agent 0 (leader) speaks: c_dim[0] below
     P.size[A + 0] = 0.2; P.collide_mask |= 1ull << (A + 0);
     P.size[A + 1] = P.size[A + 2] = 0.03;
     P.size[A + 3] = P.size[A + 4] = 0.3;
     env->reset_lo_lm = -0.9f; env->reset_hi_lm = 0.9f;
+    P.c_dim[0] = 4;
+  } else if (sc == MDP_SIMPLE_ADVERSARY) {
+    // physical deception: agent 0 is the adversary, N = 2 good agents, N landmarks, one of them the goal; nothing collides
+    A = 3; L = 2; P.n_adv = 1; P.n_goal = 1; P.collide_mask = 0;
+    for (int i = 0; i < A; ++i) { P.size[i] = 0.15; P.sens[i] = 5.0; P.max_speed[i] = -1; }
+    for (int l = 0; l < L; ++l) P.size[A + l] = 0.08;
+  } else if (sc == MDP_SIMPLE_PUSH) {
+    // keep-away: agent 0 adversary, agent 1 good; the two agents collide, the landmarks do not
+    A = 2; L = 2; P.n_adv = 1; P.n_goal = 1;
+    for (int i = 0; i < A; ++i) { P.size[i] = 0.05; P.sens[i] = 5.0; P.max_speed[i] = -1; P.collide_mask |= 1ull << i; }
+    for (int l = 0; l < L; ++l) P.size[A + l] = 0.05;
+  } else if (sc == MDP_SIMPLE_SPEAKER_LISTENER) {
+    // cooperative communication: agent 0 = speaker (not movable, dim_c = 3), agent 1 = listener (silent); shared reward
+    A = 2; L = 3; P.n_goal = 1; P.collide_mask = 0; P.collaborative = 1;
+    for (int i = 0; i < A; ++i) { P.size[i] = 0.075; P.sens[i] = 5.0; P.max_speed[i] = -1; }
+    for (int l = 0; l < L; ++l) P.size[A + l] = 0.04;
+    movable = 0x2u; P.c_dim[0] = 3;
+  } else if (sc == MDP_SIMPLE_CRYPTO) {
+    // covert communication: agent 0 = adversary (Eve), agent 1 = listener (Bob), agent 2 = speaker (Alice); nobody moves, everybody
+    // speaks (dim_c = 4); goal slot 0 = the goal landmark, slot 1 = the key
+    A = 3; L = 2; P.n_adv = 1; P.n_goal = 2; P.collide_mask = 0;
+    for (int i = 0; i < A; ++i) { P.size[i] = 0.05; P.sens[i] = 5.0; P.max_speed[i] = -1; P.c_dim[i] = 4; }
+    for (int l = 0; l < L; ++l) P.size[A + l] = 0.05;
+    movable = 0;
   } else {
     return fail(MDP_ENOTSUP, "unknown scenario id %d", sc);
   }
   P.A = A; P.L = L; P.NE = A + L;
+  P.movable_mask = movable;
+  P.cdim = 0;
+  P.silent_mask = 0xffffffffu;
+  for (int i = 0; i < A; ++i) {
+    P.c_off[i] = P.cdim;
+    P.cdim += P.c_dim[i];
+    if (P.c_dim[i]) P.silent_mask &= ~(1u << i);
+  }
   for (int j = 0; j < MAX_ENT; ++j) P.sizef[j] = (float)P.size[j];
-  P.scomp = 4 * A + P.cdim + 2 * L;
+  P.gcomp0 = 4 * A + P.cdim + 2 * L;
+  P.scomp = P.gcomp0 + P.n_goal;
   auto pc = [&](int ent, int c) { return (ent < A ? 4 * ent : 4 * A + P.cdim + 2 * (ent - A)) + c; };
   auto vc = [&](int ag, int c) { return 4 * ag + 2 + c; };
 
@@ -428,6 +461,64 @@ static int build_env(mdp_env* env) {
     if (sc == MDP_SIMPLE_WORLD_COMM && i == 0) { D.n_heads[i] = 2; D.head_dim[i][1] = 4; }
     D.act_dim[i] = D.head_dim[i][0] + D.head_dim[i][1];
     aoff += D.act_dim[i];
+    if (sc >= MDP_SIMPLE_ADVERSARY) {
+      // head layout of MultiAgentEnv.__init__: Discrete(5) if movable, Discrete(dim_c) if not silent (never both here)
+      D.head_dim[i][0] = ((movable >> i) & 1u) ? 5 : P.c_dim[i];
+      D.act_dim[i] = D.head_dim[i][0];
+      aoff += D.act_dim[i] - 5;
+      const int lm0 = pc(A, 0), g0 = P.gcomp0;
+      auto vel = [&]() { for (int c = 0; c < 2; ++c) push_col(cols, OK_DIRECT, i, 0, 0, vc(i, c), 0); };
+      auto entity_pos = [&]() {
+        for (int l = 0; l < L; ++l)
+          for (int c = 0; c < 2; ++c) push_col(cols, OK_REL, i, 0, 0, pc(A + l, c), pc(i, c));
+      };
+      auto other_pos = [&]() {
+        for (int o = 0; o < A; ++o) if (o != i)
+          for (int c = 0; c < 2; ++c) push_col(cols, OK_REL, i, o, 0, pc(o, c), pc(i, c));
+      };
+      auto goal_rel = [&]() { for (int c = 0; c < 2; ++c) push_col(cols, OK_REL_GOAL, 0, lm0, g0, c, pc(i, c)); };
+      // colour channel that depends on a goal slot: LUT index per goal value 0..3, one nibble each
+      auto goal_lut = [&](int slot, int v0, int v1, int v2, int v3) {
+        const unsigned pack = (unsigned)v0 | ((unsigned)v1 << 4) | ((unsigned)v2 << 8) | ((unsigned)v3 << 12);
+        push_col(cols, OK_GOAL_LUT, (int)(pack & 0xff), (int)(pack >> 8), g0 + slot, 0, 0);
+      };
+      auto comm_of = [&](int o) { for (int c = 0; c < P.c_dim[o]; ++c) push_col(cols, OK_DIRECT, i, o, 0, 4 * A + P.c_off[o] + c, 0); };
+      if (sc == MDP_SIMPLE_ADVERSARY) {
+        if (i >= P.n_adv) goal_rel();
+        entity_pos(); other_pos();
+      } else if (sc == MDP_SIMPLE_PUSH) {
+        vel();
+        if (i >= P.n_adv) {
+          goal_rel();
+          push_col(cols, OK_CONST, 0, 0, 0, LUT_025, 0);      // agent.color = [0.25, 0.25, 0.25]; [goal.index + 1] += 0.5
+          goal_lut(0, LUT_075, LUT_025, LUT_025, LUT_025);
+          goal_lut(0, LUT_025, LUT_075, LUT_025, LUT_025);
+          entity_pos();
+          for (int l = 0; l < L; ++l)                         // landmark.color = [0.1, 0.1, 0.1]; [l + 1] += 0.8
+            for (int ch = 0; ch < 3; ++ch) push_col(cols, OK_CONST, 0, 0, 0, ch == l + 1 ? LUT_090 : LUT_010, 0);
+          other_pos();
+        } else {
+          entity_pos(); other_pos();
+        }
+      } else if (sc == MDP_SIMPLE_SPEAKER_LISTENER) {
+        if (i == 0) {  // speaker: the goal landmark's colour (0.65 on its own channel, 0.15 elsewhere)
+          for (int ch = 0; ch < 3; ++ch)
+            goal_lut(0, ch == 0 ? LUT_065 : LUT_015, ch == 1 ? LUT_065 : LUT_015, ch == 2 ? LUT_065 : LUT_015, LUT_015);
+        } else {       // listener
+          vel(); entity_pos(); comm_of(0);
+        }
+      } else {  // MDP_SIMPLE_CRYPTO: one-hot "colours" in dim_c = 4 channels
+        auto onehot = [&](int slot) {
+          for (int ch = 0; ch < 4; ++ch)
+            goal_lut(slot, ch == 0 ? LUT_1 : LUT_0, ch == 1 ? LUT_1 : LUT_0, ch == 2 ? LUT_1 : LUT_0, ch == 3 ? LUT_1 : LUT_0);
+        };
+        if (i == A - 1) { onehot(0); onehot(1); }     // speaker: [goal colour, key]
+        else if (i >= P.n_adv) { onehot(1); comm_of(A - 1); }  // listener: [key, speaker's message]
+        else comm_of(A - 1);                            // adversary: the message only
+      }
+      D.obs_dim[i] = (int)cols.size() - D.obs_off[i];
+      continue;
+    }
     for (int c = 0; c < 2; ++c) push_col(cols, OK_DIRECT, i, 0, 0, vc(i, c), 0);                  // p_vel
     if (sc != MDP_SIMPLE)
       for (int c = 0; c < 2; ++c) push_col(cols, OK_DIRECT, i, 0, 0, pc(i, c), 0);                // p_pos
@@ -476,6 +567,8 @@ static int build_env(mdp_env* env) {
   P.as4_magic = (uint32_t)((0x100000000ull + (uint64_t)(D.act_stride / 4) - 1) / (uint64_t)(D.act_stride / 4));
   D.n_agents = A; D.n_landmarks = L; D.comm_dim = P.cdim; D.collaborative = P.collaborative;
   D.state_comps = P.scomp;
+  D.n_goal = P.n_goal;
+  for (int i = 0; i < A; ++i) { D.comm_off[i] = P.c_off[i]; D.comm_len[i] = P.c_dim[i]; D.movable[i] = (int)((movable >> i) & 1u); }
   D.state_elem_size = env->cfg.state_f64 ? 8 : 4;
   // bytes_env = 4(4A + c + 2L + sum K) + 4(4A + c + sum D + A) + A
   D.env_bytes_per_step = 4 * (4 * A + P.cdim + 2 * L + D.act_sum) + 4 * (4 * A + P.cdim + D.obs_sum + A) + A;

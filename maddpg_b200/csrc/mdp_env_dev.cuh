@@ -24,7 +24,14 @@ enum ObsKind : uint8_t {
   OK_REL_MASK = 4,  // visible(i,o) ? S[a] - S[b] : 0        (simple_world_comm)
   OK_DIR_MASK = 5,  // visible(i,o) ? S[a] : 0
   OK_FOREST = 6,    // in_forest(i, k) ? +1 : -1
+  OK_REL_GOAL = 7,  // S[o + 2 * goal + a] - S[b]: goal = (int)S[k], o = first landmark component   (agent.goal_a.state.p_pos - p_pos)
+  OK_GOAL_LUT = 8,  // kColorLut[nibble `goal` of (i | o << 8)], goal = (int)S[k]                     (goal-dependent colour channel)
+  OK_CONST = 9,     // kColorLut[a]                                                                 (fixed colour channel)
 };
+
+// every colour value the scenarios' observations contain (entity.color channels, one-hot "colours" of simple_crypto)
+__device__ __constant__ float kColorLut[8] = {0.0f, 0.1f, 0.15f, 0.25f, 0.65f, 0.75f, 0.9f, 1.0f};
+enum { LUT_0 = 0, LUT_010 = 1, LUT_015 = 2, LUT_025 = 3, LUT_065 = 4, LUT_075 = 5, LUT_090 = 6, LUT_1 = 7 };
 
 struct ObsCol {
   uint8_t kind, i, o, k;
@@ -46,6 +53,10 @@ struct EnvParams {
   uint64_t collide_mask;             // bit per entity
   uint32_t silent_mask;              // bit per agent
   int has_mask;                      // scenario has visibility-masked / flag columns (simple_world_comm)
+  uint32_t movable_mask;             // bit per agent: World.integrate_state skips the others (speakers, simple_crypto)
+  int n_goal, gcomp0;                // goal landmark indices drawn by reset_world, stored as state components [gcomp0, gcomp0 + n_goal)
+  int c_off[MDP_MAX_AGENTS];         // agent.state.c of a speaking agent: components [4A + c_off, 4A + c_off + c_dim)
+  int c_dim[MDP_MAX_AGENTS];         // 0 for silent agents; cdim = sum
   uint32_t as4_magic;                // ceil(2^32 / (act_stride/4)): row = (i * magic) >> 32 for i < 2^15
   uint32_t os4_magic;                // same for obs_stride/4
   double dt, damping, contact_force, contact_margin;
@@ -157,12 +168,16 @@ __device__ __forceinline__ void env_physics(const EnvParams& P, EnvTile<real, EB
   const int e = tid % EB, i = tid / EB;
   const bool live = (i < P.A) && (e < nE);
   real px = 0, py = 0, vx = 0, vy = 0;
+  const bool movable = (P.movable_mask >> i) & 1u;
   if (live) {
     real* sS = T.sS;
     px = sS[(4 * i + 0) * EBP + e];
     py = sS[(4 * i + 1) * EBP + e];
     vx = sS[(4 * i + 2) * EBP + e];
     vy = sS[(4 * i + 3) * EBP + e];
+  }
+  if (live && movable) {
+    real* sS = T.sS;
     const float* a = T.sA + e * T.ASP + P.act_off[i];
     // _set_action: float32 differences, then scaling by accel / 5.0 in the state precision
     real fx = (real)(a[1] - a[2]);
@@ -215,9 +230,9 @@ __device__ __forceinline__ void env_physics(const EnvParams& P, EnvTile<real, EB
     sS[(4 * i + 2) * EBP + e] = vx;
     sS[(4 * i + 3) * EBP + e] = vy;
     // update_agent_state: non-silent agents publish their comm head (simple_world_comm leader)
-    if (P.cdim > 0 && !((P.silent_mask >> i) & 1u)) {
-      const float* a = T.sA + e * T.ASP + P.act_off[i] + 5;
-      for (int c = 0; c < P.cdim; ++c) sS[(4 * P.A + c) * EBP + e] = (real)a[c];
+    if (P.c_dim[i] > 0) {  // the communication head follows the movement head (if the agent has one) in its action block
+      const float* a = T.sA + e * T.ASP + P.act_off[i] + (movable ? 5 : 0);
+      for (int c = 0; c < P.c_dim[i]; ++c) sS[(4 * P.A + P.c_off[i] + c) * EBP + e] = (real)a[c];
     }
   }
   __syncthreads();
@@ -274,6 +289,62 @@ __device__ __forceinline__ void env_flags_rewards(const EnvParams& P, EnvTile<re
           const real ax = PX(i), ay = PY(i);
           r -= bound_pen<real>(ax < 0 ? -ax : ax);
           r -= bound_pen<real>(ay < 0 ? -ay : ay);
+        }
+      } else if (P.scenario == MDP_SIMPLE_ADVERSARY) {
+        const int ge = P.A + (int)sS[P.gcomp0 * EBP + e];  // agent.goal_a
+        if (i < P.n_adv) {  // adversary_reward (shaped): -sum(square(p_pos - goal))
+          const real dx = PX(i) - PX(ge), dy = PY(i) - PY(ge);
+          r = -(dx * dx + dy * dy);
+        } else {            // agent_reward (shaped): -min over good agents of dist + sum over adversaries of dist
+          real adv = 0;
+          for (int a = 0; a < P.n_adv; ++a) adv += dist_ee(a, ge);
+          real m = dist_ee(P.n_adv, ge);
+          for (int g = P.n_adv + 1; g < P.A; ++g) {
+            const real d = dist_ee(g, ge);
+            m = d < m ? d : m;
+          }
+          r = -m + adv;
+        }
+      } else if (P.scenario == MDP_SIMPLE_PUSH) {
+        const int ge = P.A + (int)sS[P.gcomp0 * EBP + e];
+        if (i < P.n_adv) {  // keep the nearest good agent away from the goal, stay close to it
+          real m = dist_ee(P.n_adv, ge);
+          for (int g = P.n_adv + 1; g < P.A; ++g) {
+            const real d = dist_ee(g, ge);
+            m = d < m ? d : m;
+          }
+          r = m - dist_ee(ge, i);
+        } else {
+          r = -dist_ee(i, ge);
+        }
+      } else if (P.scenario == MDP_SIMPLE_SPEAKER_LISTENER) {
+        const int ge = P.A + (int)sS[P.gcomp0 * EBP + e];  // the speaker's goal_b; goal_a is the listener (agent 1)
+        const real dx = PX(1) - PX(ge), dy = PY(1) - PY(ge);
+        r = -(dx * dx + dy * dy);
+      } else if (P.scenario == MDP_SIMPLE_CRYPTO) {
+        const int g = (int)sS[P.gcomp0 * EBP + e];  // goal landmark: its "colour" is the one-hot of its index in dim_c channels
+        auto all_zero = [&](int a) -> bool {
+          bool z = true;
+          for (int c = 0; c < P.c_dim[a]; ++c) z = z && (sS[(4 * P.A + P.c_off[a] + c) * EBP + e] == (real)0);
+          return z;
+        };
+        auto sq_err = [&](int a) -> real {
+          real s = 0;
+          for (int c = 0; c < P.c_dim[a]; ++c) {
+            const real d = sS[(4 * P.A + P.c_off[a] + c) * EBP + e] - (c == g ? (real)1 : (real)0);
+            s += d * d;
+          }
+          return s;
+        };
+        if (i < P.n_adv) {
+          if (!all_zero(i)) r -= sq_err(i);
+        } else {  // good listeners: not adversary, not speaker (the speaker is the last agent)
+          real good = 0, adv = 0;
+          for (int a = P.n_adv; a < P.A - 1; ++a)
+            if (!all_zero(a)) good -= sq_err(a);
+          for (int a = 0; a < P.n_adv; ++a)
+            if (!all_zero(a)) adv += sq_err(a);
+          r = adv + good;
         }
       } else {  // MDP_SIMPLE_WORLD_COMM
         if (i < P.n_adv) {
@@ -349,6 +420,16 @@ __device__ __forceinline__ float env_obs_value(const EnvTile<real, EB>& T, const
       break;
     }
     case OK_FOREST: v = ((T.sF[d.i * EBP + ee] >> d.k) & 1) ? (real)1 : (real)-1; break;
+    case OK_REL_GOAL: {
+      const int g = (int)sS[d.k * EBP + ee];
+      v = sS[(d.o + 2 * g + d.a) * EBP + ee] - sS[d.b * EBP + ee];
+      break;
+    }
+    case OK_GOAL_LUT: {
+      const int g = (int)sS[d.k * EBP + ee];
+      return kColorLut[(((unsigned)d.i | ((unsigned)d.o << 8)) >> (4 * g)) & 7u];
+    }
+    case OK_CONST: return kColorLut[d.a & 7];
     default: break;
   }
   return (float)v;
@@ -384,10 +465,15 @@ template <typename real>
 __device__ __forceinline__ real env_reset_value(const EnvParams& P, int comp, long long e_global, uint64_t seed,
                                                 uint64_t episode, float lm_lo, float lm_hi) {
   const bool agent_pos = comp < 4 * P.A && (comp & 3) < 2;
-  const bool lm_pos = comp >= 4 * P.A + P.cdim;
-  if (!(agent_pos || lm_pos)) return (real)0;
+  const bool lm_pos = comp >= 4 * P.A + P.cdim && comp < 4 * P.A + P.cdim + 2 * P.L;
+  const bool goal = P.n_goal > 0 && comp >= P.gcomp0;
+  if (!(agent_pos || lm_pos || goal)) return (real)0;
   uint4 r = Philox::gen(seed, (uint32_t)e_global, (uint32_t)comp, (uint32_t)episode, (uint32_t)(episode >> 32) ^ 0x5EEDu);
   const real u = sizeof(real) == 4 ? (real)Philox::u01(r.x) : (real)Philox::u01d(r.x, r.y);
+  if (goal) {  // np.random.choice(world.landmarks): a uniform landmark index
+    const int g = (int)(u * (real)P.L);
+    return (real)(g < P.L ? g : P.L - 1);
+  }
   const real lo = agent_pos ? (real)-1 : (real)lm_lo, hi = agent_pos ? (real)1 : (real)lm_hi;
   return lo + (hi - lo) * u;
 }

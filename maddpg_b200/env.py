@@ -19,7 +19,8 @@ import torch
 from . import _lib
 from .spaces import Box, Discrete, MultiDiscrete
 
-SCENARIOS = ("simple", "simple_spread", "simple_tag", "simple_world_comm")
+SCENARIOS = ("simple", "simple_spread", "simple_tag", "simple_world_comm",
+             "simple_adversary", "simple_push", "simple_speaker_listener", "simple_crypto")
 
 
 def _dims_for(scenario, num_agents=None, state_f64=False):
@@ -78,6 +79,10 @@ class BatchedMultiAgentEnv(object):
         self.obs_stride, self.act_stride = int(d.obs_stride), int(d.act_stride)
         self.state_comps = int(d.state_comps)
         self.comm_dim = int(d.comm_dim)
+        self.n_goal = int(d.n_goal)
+        self.comm_off = [int(d.comm_off[i]) for i in range(self.n)]
+        self.comm_len = [int(d.comm_len[i]) for i in range(self.n)]
+        self.movable = [bool(d.movable[i]) for i in range(self.n)]
         self.n_landmarks = int(d.n_landmarks)
         self.env_bytes_per_step = int(d.env_bytes_per_step)
         self.observation_space = [Box(-np.inf, np.inf, (D,)) for D in self.obs_dims]
@@ -123,8 +128,9 @@ class BatchedMultiAgentEnv(object):
         return [host[0, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]
 
     # -- state injection (parity tests) ------------------------------------------------------
-    def state_from_arrays(self, agent_pos, agent_vel, landmark_pos, agent_c=None):
-        """(E,A,2), (E,A,2), (E,L,2)[, (E,A,dim_c)] -> SoA state tensor [comp][E] (see header)."""
+    def state_from_arrays(self, agent_pos, agent_vel, landmark_pos, agent_c=None, goal=None):
+        """(E,A,2), (E,A,2), (E,L,2)[, (E,A,dim_c) state.c of every agent][, (E,n_goal) landmark indices drawn by
+        reset_world] -> SoA state tensor [comp][E] (row layout: include/maddpg_b200.h, mdp_env_dims)."""
         A, L, E = self.n, self.n_landmarks, self.num_envs
         s = np.zeros((self.state_comps, E), dtype=np.float64)
         ap, av, lp = (np.asarray(x, np.float64) for x in (agent_pos, agent_vel, landmark_pos))
@@ -132,11 +138,19 @@ class BatchedMultiAgentEnv(object):
             s[4 * i + 0], s[4 * i + 1] = ap[:, i, 0], ap[:, i, 1]
             s[4 * i + 2], s[4 * i + 3] = av[:, i, 0], av[:, i, 1]
         if self.comm_dim and agent_c is not None:
-            for k in range(self.comm_dim):
-                s[4 * A + k] = np.asarray(agent_c, np.float64)[:, 0, k]  # the only speaker is agent 0
+            c = np.asarray(agent_c, np.float64)
+            for i in range(A):  # only speaking agents have state.c rows
+                for k in range(self.comm_len[i]):
+                    s[4 * A + self.comm_off[i] + k] = c[:, i, k]
         for l in range(L):
             s[4 * A + self.comm_dim + 2 * l + 0] = lp[:, l, 0]
             s[4 * A + self.comm_dim + 2 * l + 1] = lp[:, l, 1]
+        if self.n_goal:
+            if goal is None:
+                raise ValueError("scenario %s needs the goal landmark indices (E, %d)" % (self.scenario_name, self.n_goal))
+            g = np.asarray(goal, np.float64).reshape(E, self.n_goal)
+            for k in range(self.n_goal):
+                s[4 * A + self.comm_dim + 2 * L + k] = g[:, k]
         return torch.from_numpy(s).to(self.state_dtype).to(self.device)
 
     def state_to_arrays(self):
@@ -146,7 +160,8 @@ class BatchedMultiAgentEnv(object):
         av = np.stack([np.stack([s[4 * i + 2], s[4 * i + 3]], -1) for i in range(A)], 1)
         b = 4 * A + self.comm_dim
         lp = np.stack([np.stack([s[b + 2 * l], s[b + 2 * l + 1]], -1) for l in range(L)], 1)
-        return dict(agent_pos=ap, agent_vel=av, landmark_pos=lp, comm=s[4 * A:b].T.copy())
+        g = s[b + 2 * L:b + 2 * L + self.n_goal].T.astype(np.int64)
+        return dict(agent_pos=ap, agent_vel=av, landmark_pos=lp, comm=s[4 * A:b].T.copy(), goal=g)
 
     # -- reference surface -------------------------------------------------------------------
     def set_ctl(self, ctl):

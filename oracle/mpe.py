@@ -577,6 +577,281 @@ class SimpleWorldCommScenario(BaseScenario):
                               + in_forest + other_vel)
 
 
+# --------------------------------------------------------------------------------------------
+# the other scenarios `train.py --scenario` can name.  Restated from the published upstream
+# files multiagent/scenarios/{simple_adversary,simple_push,simple_speaker_listener,simple_crypto}.py (PARITY UNPINNED like the
+# rest of this module: the package is absent from /root/reference and from this container).  reset_world is split into the
+# goal draw (np.random.choice(world.landmarks), kept first like upstream) and ``apply_goals`` -- the goal pointers and the
+# colours upstream derives from them -- so that parity tests can inject the drawn indices.
+# --------------------------------------------------------------------------------------------
+class _GoalScenario(BaseScenario):
+    n_goal = 1
+
+    def draw_goals(self, world):
+        return [int(self.rng.randint(len(world.landmarks))) for _ in range(self.n_goal)]
+
+    def reset_world(self, world):
+        self.apply_goals(world, self.draw_goals(world))
+        for agent in world.agents:
+            agent.state.p_pos = self.rng.uniform(-1, +1, world.dim_p)
+            agent.state.p_vel = np.zeros(world.dim_p)
+            agent.state.c = np.zeros(world.dim_c)
+        for landmark in world.landmarks:
+            landmark.state.p_pos = self.rng.uniform(-1, +1, world.dim_p)
+            landmark.state.p_vel = np.zeros(world.dim_p)
+
+    def good_agents(self, world):
+        return [agent for agent in world.agents if not agent.adversary]
+
+    def adversaries(self, world):
+        return [agent for agent in world.agents if agent.adversary]
+
+
+class SimpleAdversaryScenario(_GoalScenario):
+    name = "simple_adversary"
+
+    def make_world(self):
+        world = World()
+        world.dim_c = 2
+        num_agents = 3
+        num_adversaries = 1
+        num_landmarks = num_agents - 1
+        world.agents = [Agent() for _ in range(num_agents)]
+        for i, agent in enumerate(world.agents):
+            agent.name = 'agent %d' % i
+            agent.collide = False
+            agent.silent = True
+            agent.adversary = True if i < num_adversaries else False
+            agent.size = 0.15
+        world.landmarks = [Landmark() for _ in range(num_landmarks)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = 'landmark %d' % i
+            landmark.collide = False
+            landmark.movable = False
+            landmark.size = 0.08
+        self.reset_world(world)
+        return world
+
+    def apply_goals(self, world, goals):
+        world.goals = list(goals)
+        goal = world.landmarks[goals[0]]
+        for agent in world.agents:
+            agent.goal_a = goal
+
+    def reward(self, agent, world):
+        return self.adversary_reward(agent, world) if agent.adversary else self.agent_reward(agent, world)
+
+    def agent_reward(self, agent, world):
+        # shaped_reward = shaped_adv_reward = True upstream
+        adv_rew = sum([np.sqrt(np.sum(np.square(a.state.p_pos - a.goal_a.state.p_pos))) for a in self.adversaries(world)])
+        pos_rew = -min([np.sqrt(np.sum(np.square(a.state.p_pos - a.goal_a.state.p_pos))) for a in self.good_agents(world)])
+        return pos_rew + adv_rew
+
+    def adversary_reward(self, agent, world):
+        return -np.sum(np.square(agent.state.p_pos - agent.goal_a.state.p_pos))
+
+    def observation(self, agent, world):
+        entity_pos = [entity.state.p_pos - agent.state.p_pos for entity in world.landmarks]
+        other_pos = [other.state.p_pos - agent.state.p_pos for other in world.agents if other is not agent]
+        if not agent.adversary:
+            return np.concatenate([agent.goal_a.state.p_pos - agent.state.p_pos] + entity_pos + other_pos)
+        return np.concatenate(entity_pos + other_pos)
+
+
+class SimplePushScenario(_GoalScenario):
+    name = "simple_push"
+
+    def make_world(self):
+        world = World()
+        world.dim_c = 2
+        num_agents = 2
+        num_adversaries = 1
+        num_landmarks = 2
+        world.agents = [Agent() for _ in range(num_agents)]
+        for i, agent in enumerate(world.agents):
+            agent.name = 'agent %d' % i
+            agent.collide = True
+            agent.silent = True
+            agent.adversary = True if i < num_adversaries else False
+        world.landmarks = [Landmark() for _ in range(num_landmarks)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = 'landmark %d' % i
+            landmark.collide = False
+            landmark.movable = False
+        self.reset_world(world)
+        return world
+
+    def apply_goals(self, world, goals):
+        world.goals = list(goals)
+        for i, landmark in enumerate(world.landmarks):
+            landmark.color = np.array([0.1, 0.1, 0.1])
+            landmark.color[i + 1] += 0.8
+            landmark.index = i
+        goal = world.landmarks[goals[0]]
+        for agent in world.agents:
+            agent.goal_a = goal
+            agent.color = np.array([0.25, 0.25, 0.25])
+            if agent.adversary:
+                agent.color = np.array([0.75, 0.25, 0.25])
+            else:
+                agent.color[goal.index + 1] += 0.5
+
+    def reward(self, agent, world):
+        return self.adversary_reward(agent, world) if agent.adversary else self.agent_reward(agent, world)
+
+    def agent_reward(self, agent, world):
+        return -np.sqrt(np.sum(np.square(agent.state.p_pos - agent.goal_a.state.p_pos)))
+
+    def adversary_reward(self, agent, world):
+        agent_dist = [np.sqrt(np.sum(np.square(a.state.p_pos - a.goal_a.state.p_pos))) for a in world.agents if not a.adversary]
+        pos_rew = min(agent_dist)
+        neg_rew = np.sqrt(np.sum(np.square(agent.goal_a.state.p_pos - agent.state.p_pos)))
+        return pos_rew - neg_rew
+
+    def observation(self, agent, world):
+        entity_pos = [entity.state.p_pos - agent.state.p_pos for entity in world.landmarks]
+        entity_color = [entity.color for entity in world.landmarks]
+        other_pos = [other.state.p_pos - agent.state.p_pos for other in world.agents if other is not agent]
+        if not agent.adversary:
+            return np.concatenate([agent.state.p_vel] + [agent.goal_a.state.p_pos - agent.state.p_pos] + [agent.color] +
+                                  entity_pos + entity_color + other_pos)
+        return np.concatenate([agent.state.p_vel] + entity_pos + other_pos)
+
+
+class SimpleSpeakerListenerScenario(_GoalScenario):
+    name = "simple_speaker_listener"
+
+    def make_world(self):
+        world = World()
+        world.dim_c = 3
+        num_landmarks = 3
+        world.collaborative = True
+        world.agents = [Agent() for _ in range(2)]
+        for i, agent in enumerate(world.agents):
+            agent.name = 'agent %d' % i
+            agent.collide = False
+            agent.size = 0.075
+        world.agents[0].movable = False  # speaker
+        world.agents[1].silent = True    # listener
+        world.landmarks = [Landmark() for _ in range(num_landmarks)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = 'landmark %d' % i
+            landmark.collide = False
+            landmark.movable = False
+            landmark.size = 0.04
+        self.reset_world(world)
+        return world
+
+    def apply_goals(self, world, goals):
+        world.goals = list(goals)
+        for agent in world.agents:
+            agent.goal_a = None
+            agent.goal_b = None
+        world.agents[0].goal_a = world.agents[1]
+        world.agents[0].goal_b = world.landmarks[goals[0]]
+        world.landmarks[0].color = np.array([0.65, 0.15, 0.15])
+        world.landmarks[1].color = np.array([0.15, 0.65, 0.15])
+        world.landmarks[2].color = np.array([0.15, 0.15, 0.65])
+
+    def reward(self, agent, world):
+        a = world.agents[0]
+        dist2 = np.sum(np.square(a.goal_a.state.p_pos - a.goal_b.state.p_pos))
+        return -dist2
+
+    def observation(self, agent, world):
+        goal_color = np.zeros(3)
+        if agent.goal_b is not None:
+            goal_color = agent.goal_b.color
+        entity_pos = [entity.state.p_pos - agent.state.p_pos for entity in world.landmarks]
+        comm = []
+        for other in world.agents:
+            if other is agent or (other.state.c is None):
+                continue
+            comm.append(other.state.c)
+        if not agent.movable:   # speaker
+            return np.concatenate([goal_color])
+        return np.concatenate([agent.state.p_vel] + entity_pos + comm)  # listener (agent.silent)
+
+
+class SimpleCryptoScenario(_GoalScenario):
+    name = "simple_crypto"
+    n_goal = 2  # goal landmark, key landmark
+
+    def make_world(self):
+        world = World()
+        num_agents = 3
+        num_adversaries = 1
+        num_landmarks = 2
+        world.dim_c = 4
+        world.agents = [Agent() for _ in range(num_agents)]
+        for i, agent in enumerate(world.agents):
+            agent.name = 'agent %d' % i
+            agent.collide = False
+            agent.adversary = True if i < num_adversaries else False
+            agent.speaker = True if i == 2 else False
+            agent.movable = False
+        world.landmarks = [Landmark() for _ in range(num_landmarks)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = 'landmark %d' % i
+            landmark.collide = False
+            landmark.movable = False
+        self.reset_world(world)
+        return world
+
+    def apply_goals(self, world, goals):
+        world.goals = list(goals)
+        color_list = [np.zeros(world.dim_c) for _ in world.landmarks]
+        for i, color in enumerate(color_list):
+            color[i] += 1
+        for color, landmark in zip(color_list, world.landmarks):
+            landmark.color = color
+        goal = world.landmarks[goals[0]]
+        for agent in world.agents:
+            agent.key = None
+            agent.goal_a = goal
+        world.agents[2].key = world.landmarks[goals[1]].color
+
+    def good_listeners(self, world):
+        return [agent for agent in world.agents if not agent.adversary and not agent.speaker]
+
+    def reward(self, agent, world):
+        return self.adversary_reward(agent, world) if agent.adversary else self.agent_reward(agent, world)
+
+    def agent_reward(self, agent, world):
+        good_rew, adv_rew = 0, 0
+        for a in self.good_listeners(world):
+            if (a.state.c == np.zeros(world.dim_c)).all():
+                continue
+            good_rew -= np.sum(np.square(a.state.c - agent.goal_a.color))
+        for a in self.adversaries(world):
+            if (a.state.c == np.zeros(world.dim_c)).all():
+                continue
+            adv_rew += np.sum(np.square(a.state.c - agent.goal_a.color))
+        return adv_rew + good_rew
+
+    def adversary_reward(self, agent, world):
+        rew = 0
+        if not (agent.state.c == np.zeros(world.dim_c)).all():
+            rew -= np.sum(np.square(agent.state.c - agent.goal_a.color))
+        return rew
+
+    def observation(self, agent, world):
+        goal_color = np.zeros(world.dim_c)
+        if agent.goal_a is not None:
+            goal_color = agent.goal_a.color
+        comm = []
+        for other in world.agents:
+            if other is agent or (other.state.c is None) or not other.speaker:
+                continue
+            comm.append(other.state.c)
+        key = world.agents[2].key
+        if agent.speaker:
+            return np.concatenate([goal_color] + [key])
+        if not agent.adversary:
+            return np.concatenate([key] + comm)
+        return np.concatenate(comm)
+
+
 def make_scenario(name, rng=None, num_agents=None):
     """``scenarios.load(name + ".py").Scenario()`` (train.py:53)."""
     if name == "simple":
@@ -587,6 +862,10 @@ def make_scenario(name, rng=None, num_agents=None):
         return SimpleTagScenario(rng)
     if name == "simple_world_comm":
         return SimpleWorldCommScenario(rng)
+    extra = {"simple_adversary": SimpleAdversaryScenario, "simple_push": SimplePushScenario,
+             "simple_speaker_listener": SimpleSpeakerListenerScenario, "simple_crypto": SimpleCryptoScenario}
+    if name in extra:
+        return extra[name](rng)
     raise NotImplementedError(name)
 
 
@@ -714,10 +993,13 @@ def get_world_state(world):
         agent_vel=np.array([a.state.p_vel for a in world.agents], dtype=np.float64),
         agent_c=np.array([a.state.c for a in world.agents], dtype=np.float64).reshape(len(world.agents), world.dim_c),
         landmark_pos=np.array([l.state.p_pos for l in world.landmarks], dtype=np.float64),
+        goal=np.array(getattr(world, "goals", []), dtype=np.int64),
     )
 
 
-def set_world_state(world, agent_pos, agent_vel, landmark_pos, agent_c=None):
+def set_world_state(world, agent_pos, agent_vel, landmark_pos, agent_c=None, goal=None, scenario=None):
+    if goal is not None and len(goal):
+        scenario.apply_goals(world, [int(g) for g in goal])
     for i, a in enumerate(world.agents):
         a.state.p_pos = np.array(agent_pos[i], dtype=np.float64)
         a.state.p_vel = np.array(agent_vel[i], dtype=np.float64)
@@ -747,10 +1029,10 @@ class BatchedOracleEnv:
         st = [get_world_state(e.world) for e in self.envs]
         return {k: np.stack([s[k] for s in st]) for k in st[0]}
 
-    def set_state(self, agent_pos, agent_vel, landmark_pos, agent_c=None):
+    def set_state(self, agent_pos, agent_vel, landmark_pos, agent_c=None, goal=None):
         for e, env in enumerate(self.envs):
             set_world_state(env.world, agent_pos[e], agent_vel[e], landmark_pos[e],
-                            None if agent_c is None else agent_c[e])
+                            None if agent_c is None else agent_c[e], None if goal is None else goal[e], env.scenario)
 
     def observe(self):
         return [np.stack([env._get_obs(env.agents[i]) for env in self.envs]) for i in range(self.n)]

@@ -23,15 +23,21 @@ ENV_SEED, UPD_SEED = 21, 6
 
 
 def main():
+    force = "--force" in sys.argv
     for name in ENV_CASES:
+        if os.path.exists(os.path.join(HERE, "env_%s.npz" % name)) and not force:
+            continue  # committed fixtures stay byte-identical; --force regenerates everything
         case = env_case(name, seed=ENV_SEED)
         ref = run_oracle_rollout(case)
         tape = np.stack([np.concatenate(a, axis=1) for a in case["tape"]])
         np.savez_compressed(os.path.join(HERE, "env_%s.npz" % name), agent_pos=case["agent_pos"], agent_vel=case["agent_vel"],
                             landmark_pos=case["landmark_pos"], tape=tape.astype(np.float32), obs0=ref["obs0"].astype(np.float32),
                             obs=ref["obs"].astype(np.float32), rew=ref["rew"].astype(np.float32),
-                            final_pos=ref["final"]["agent_pos"], final_vel=ref["final"]["agent_vel"])
+                            final_pos=ref["final"]["agent_pos"], final_vel=ref["final"]["agent_vel"],
+                            goal=np.zeros((case["E"], 0), np.int64) if case["goal"] is None else case["goal"])
     for name in TRAINER_CASES:
+        if os.path.exists(os.path.join(HERE, "update_%s.npz" % name)) and not force:
+            continue
         ref = oracle_update_round(trainer_case(name, seed=UPD_SEED))
         out = {}
         for j, r in enumerate(ref):

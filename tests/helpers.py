@@ -14,6 +14,11 @@ ENV_CASES = {
     "simple_tag": ("simple_tag", None, 16, 25),
     "simple_world_comm": ("simple_world_comm", None, 8, 25),
     "simple_spread_24": ("simple_spread", 24, 2, 4),
+    # SURVEY 8(f) rank 2
+    "simple_adversary": ("simple_adversary", None, 16, 25),
+    "simple_push": ("simple_push", None, 16, 25),
+    "simple_speaker_listener": ("simple_speaker_listener", None, 16, 25),
+    "simple_crypto": ("simple_crypto", None, 16, 25),
 }
 
 
@@ -41,15 +46,17 @@ def env_case(name, seed=0, crowd=0.45):
     landmark_pos = rng.uniform(-crowd, crowd, size=(E, L, 2))
     dim_c = env.envs[0].world.dim_c
     agent_c = np.zeros((E, A, dim_c))
+    n_goal = getattr(env.envs[0].scenario, "n_goal", 0)
+    goal = rng.randint(L, size=(E, n_goal)) if n_goal else None
     heads = [omaddpg.act_heads(s) for s in env.action_space]
     tape = [[soft_actions(rng, E, env.act_dims[i], heads[i]) for i in range(A)] for _ in range(T)]
     return dict(scenario=scenario, num_agents=na, E=E, T=T, env=env, agent_pos=agent_pos, agent_vel=agent_vel,
-                landmark_pos=landmark_pos, agent_c=agent_c, tape=tape, heads=heads)
+                landmark_pos=landmark_pos, agent_c=agent_c, goal=goal, tape=tape, heads=heads)
 
 
 def run_oracle_rollout(case):
     env = case["env"]
-    env.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    env.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"], case.get("goal"))
     obs0 = env.observe()
     obs_t, rew_t = [], []
     for acts in case["tape"]:
@@ -73,6 +80,10 @@ TRAINER_CASES = {
     "simple_spread_b1024": ("simple_spread", 3, 64, 1024, None),
     "simple_tag_b4096": ("simple_tag", None, 64, 4096, None),
     "simple_world_comm_b1024": ("simple_world_comm", None, 128, 1024, None),
+    # SURVEY 8(f) rank 2 shapes: a 3-wide observation and a Discrete(3) / Discrete(4) communication head
+    "simple_speaker_listener": ("simple_speaker_listener", None, 64, 96, None),
+    "simple_crypto": ("simple_crypto", None, 64, 80, None),
+    "simple_adversary_ddpg_good": ("simple_adversary", None, 64, 64, [False, True, True]),
 }
 
 

@@ -31,7 +31,7 @@ def test_rollout_f64_state_matches_oracle(name):
     case = env_case(name, seed=11)
     ref = run_oracle_rollout(case)
     env = _make(case, torch.float64)
-    init = env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    init = env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"], case.get("goal"))
     obs0 = torch.cat(env.reset(init_state=init), dim=1).cpu().numpy()
     np.testing.assert_allclose(obs0, ref["obs0"], rtol=RTOL, atol=ATOL)
     for t, acts in enumerate(case["tape"]):
@@ -51,11 +51,11 @@ def test_single_steps_f32_state_match_oracle(name):
     comparison isolates one step of float32 arithmetic."""
     case = env_case(name, seed=5)
     oenv = case["env"]
-    oenv.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    oenv.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"], case.get("goal"))
     env = _make(case, torch.float32)
     for t, acts in enumerate(case["tape"][:10]):
         st = oenv.get_state()
-        init = env.state_from_arrays(st["agent_pos"], st["agent_vel"], st["landmark_pos"], st["agent_c"])
+        init = env.state_from_arrays(st["agent_pos"], st["agent_vel"], st["landmark_pos"], st["agent_c"], st["goal"])
         env.reset(init_state=init)
         o, r, d = oenv.step(acts)
         env.step_device(_joint_act(env, acts))
@@ -78,7 +78,7 @@ def test_rollout_f32_state_free_running_matches_oracle(name):
         case = env_case(name, seed=seed)
         ref = run_oracle_rollout(case)
         env = _make(case, torch.float32)
-        env.reset(init_state=env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"]))
+        env.reset(init_state=env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"], case.get("goal")))
         for t, acts in enumerate(case["tape"]):
             env.step_device(_joint_act(env, acts))
             obs = env.obs[:, :sum(env.obs_dims)].cpu().numpy()
@@ -219,9 +219,9 @@ def test_benchmark_data_matches_oracle(name):
     few crowded steps, float64 state: exact counts, distances to 1e-9."""
     case = env_case(name, seed=5, crowd=0.3)
     oenv = case["env"]
-    oenv.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"])
+    oenv.set_state(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"], case.get("goal"))
     env = _make(case, torch.float64)
-    env.reset(init_state=env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"]))
+    env.reset(init_state=env.state_from_arrays(case["agent_pos"], case["agent_vel"], case["landmark_pos"], case["agent_c"], case.get("goal")))
     saw_collision = False
     for t, acts in enumerate(case["tape"][:6]):
         oenv.step(acts)
@@ -289,3 +289,58 @@ def test_spread_warp_kernel_fused_ring_insert_matches_separate_insert(A, E):
     used = list(range(0, L.x_dim)) + list(range(L.nx_off, L.nx_off + L.obs_sum)) + list(range(L.rw_off, L.dn_off + A))
     torch.testing.assert_close(r0[:, used], r1[:, used], rtol=1e-5, atol=1e-5)
     assert torch.equal(r0[:, L.obs_sum:L.x_dim], r1[:, L.obs_sum:L.x_dim])  # act_t is a copy of the same tape: bit-identical
+
+
+@pytest.mark.parametrize("name", ["simple_adversary", "simple_push", "simple_speaker_listener", "simple_crypto"])
+def test_goal_scenarios_device_reset(name):
+    """reset_world of the goal scenarios: the goal landmark index (np.random.choice(world.landmarks)) is drawn on the device per
+    env instance and episode, uniformly; observations of the fresh state equal the oracle's with the same goals injected."""
+    from maddpg_b200 import BatchedMultiAgentEnv
+    from oracle import mpe
+    E = 512
+    env = BatchedMultiAgentEnv(name, num_envs=E, state_dtype=torch.float64, squeeze=False, seed=9)
+    obs = torch.cat(env.reset(), 1).cpu().numpy()
+    st = env.state_to_arrays()
+    L = env.n_landmarks
+    assert st["goal"].shape == (E, env.n_goal) and st["goal"].min() == 0 and st["goal"].max() == L - 1
+    counts = np.bincount(st["goal"][:, 0], minlength=L)
+    assert counts.min() > E / L * 0.7, counts
+    assert np.all(st["agent_vel"] == 0) and np.all(st["comm"] == 0)
+    oenv = mpe.BatchedOracleEnv(name, E)
+    oenv.set_state(st["agent_pos"], st["agent_vel"], st["landmark_pos"], None, st["goal"])
+    np.testing.assert_allclose(obs[:, :sum(env.obs_dims)], np.concatenate(oenv.observe(), 1), rtol=RTOL, atol=ATOL)
+    g2 = None
+    for _ in range(3):
+        env.reset()
+        g2 = env.state_to_arrays()["goal"]
+        if not np.array_equal(g2, st["goal"]):
+            break
+    assert not np.array_equal(g2, st["goal"])  # a new episode draws new goals
+    # immovable agents stay where reset put them; speakers publish their action as state.c
+    env.act.copy_(torch.softmax(torch.randn_like(env.act), -1))
+    before = env.state_to_arrays()
+    env.step_device()
+    after = env.state_to_arrays()
+    for i in range(env.n):
+        if not env.movable[i]:
+            assert np.array_equal(before["agent_pos"][:, i], after["agent_pos"][:, i])
+        if env.comm_len[i]:
+            lo = env.act_off[i] + (5 if env.movable[i] else 0)
+            np.testing.assert_array_equal(after["comm"][:, env.comm_off[i]:env.comm_off[i] + env.comm_len[i]],
+                                          env.act[:, lo:lo + env.comm_len[i]].double().cpu().numpy())
+
+
+def test_goal_scenarios_numpy_surface_and_spaces():
+    """The reference-shaped surface of the new scenarios: Discrete(3) speaker / Discrete(5) listener, Discrete(4) crypto agents."""
+    from maddpg_b200 import make_env
+    env = make_env("simple_speaker_listener")
+    assert [s.n for s in env.action_space] == [3, 5] and [s.shape for s in env.observation_space] == [(3,), (11,)]
+    obs_n = env.reset()
+    assert [o.shape for o in obs_n] == [(3,), (11,)] and sorted(np.round(obs_n[0], 2).tolist()) == [0.15, 0.15, 0.65]
+    obs_n, rew_n, done_n, info_n = env.step([np.asarray([0.2, 0.5, 0.3], np.float32), np.eye(5, dtype=np.float32)[1]])
+    np.testing.assert_allclose(obs_n[1][-3:], [0.2, 0.5, 0.3], rtol=1e-6)   # the listener hears the speaker's message
+    assert rew_n[0] == rew_n[1] and done_n == [False, False]                # collaborative: shared reward
+    env = make_env("simple_crypto")
+    assert [s.n for s in env.action_space] == [4, 4, 4] and [s.shape for s in env.observation_space] == [(4,), (8,), (8,)]
+    with pytest.raises(NotImplementedError):
+        make_env("simple_reference")

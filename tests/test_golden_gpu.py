@@ -19,7 +19,7 @@ def test_env_rollout_matches_golden(name):
     g = np.load(os.path.join(G, "env_%s.npz" % name))
     scenario, na, E, T = ENV_CASES[name]
     env = BatchedMultiAgentEnv(scenario, num_envs=E, num_agents=na, state_dtype=torch.float64, squeeze=False)
-    init = env.state_from_arrays(g["agent_pos"], g["agent_vel"], g["landmark_pos"])
+    init = env.state_from_arrays(g["agent_pos"], g["agent_vel"], g["landmark_pos"], goal=g["goal"] if "goal" in g.files else None)
     obs0 = torch.cat(env.reset(init_state=init), dim=1).cpu().numpy()
     np.testing.assert_allclose(obs0, g["obs0"], rtol=1e-5, atol=1e-5)
     nobs = sum(env.obs_dims)

@@ -343,6 +343,27 @@ def test_train_loop_drop_in(tmp_path, num_envs):
     assert torch.equal(core.params.cpu(), saved["params"]) and core.counter == saved["counter"]
 
 
+@pytest.mark.parametrize("scenario,num_envs", [("simple_speaker_listener", 1), ("simple_crypto", 32), ("simple_push", 32),
+                                               ("simple_adversary", 1)])
+def test_train_loop_drop_in_goal_scenarios(tmp_path, scenario, num_envs):
+    """the reference's own experiments/train.py on the other MPE scenarios (Discrete(3) / Discrete(4)
+    communication heads, immovable agents, goal landmarks drawn by reset_world), reference shapes and the batched superset."""
+    import pickle
+    from maddpg_b200 import train as T
+    try:
+        path = T.reference_train_path()
+    except FileNotFoundError:
+        pytest.skip("the reference's experiments/train.py is not available on this machine")
+    argv = ["--scenario", scenario, "--num-adversaries", "1", "--num-episodes", "12", "--batch-size", "8", "--save-rate", "4",
+            "--save-dir", str(tmp_path) + "/", "--plots-dir", str(tmp_path) + "/", "--exp-name", "g"]
+    trainers = T.run_reference_train(argv, path, num_envs=num_envs, replay_capacity=20000, seed=1)
+    core = trainers[0].core
+    ep_rewards = pickle.load(open(os.path.join(str(tmp_path), "g_rewards.pkl"), "rb"))
+    assert len(ep_rewards) == 3 and all(np.isfinite(ep_rewards))
+    assert len(trainers[0].replay_buffer) == 300 * num_envs
+    assert min(core.adam_t.cpu().tolist()) >= 2 and torch.isfinite(core.params).all()
+
+
 def test_grouped_update_all_equals_jacobi_order_of_per_agent_kernels():
     """mdp_update_all (all agents per launch) == the per-agent entry points called in Jacobi order with the
     same index sets and Philox counter; and it differs from the sequential order only slightly."""
