@@ -336,7 +336,7 @@ def test_goal_scenarios_numpy_surface_and_spaces():
     env = make_env("simple_speaker_listener")
     assert [s.n for s in env.action_space] == [3, 5] and [s.shape for s in env.observation_space] == [(3,), (11,)]
     obs_n = env.reset()
-    assert [o.shape for o in obs_n] == [(3,), (11,)] and sorted(np.round(obs_n[0], 2).tolist()) == [0.15, 0.15, 0.65]
+    assert [o.shape for o in obs_n] == [(3,), (11,)] and sorted(np.round(obs_n[0].astype(np.float64), 2).tolist()) == [0.15, 0.15, 0.65]
     obs_n, rew_n, done_n, info_n = env.step([np.asarray([0.2, 0.5, 0.3], np.float32), np.eye(5, dtype=np.float32)[1]])
     np.testing.assert_allclose(obs_n[1][-3:], [0.2, 0.5, 0.3], rtol=1e-6)   # the listener hears the speaker's message
     assert rew_n[0] == rew_n[1] and done_n == [False, False]                # collaborative: shared reward
