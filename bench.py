@@ -279,6 +279,73 @@ def tensor_core_section(torch, dev):
     return out
 
 
+def next_rows_section(torch, batch, with_cpu):
+    """prioritized replay at the reference's capacity (1e6 slots: a 21-level float64 tree), one
+    sample(batch) + batch_update(batch) round per step; and one env step of every scenario at 4096 env instances."""
+    import numpy as np
+    from statistics import median
+    from maddpg_b200 import BatchedMultiAgentEnv, DevicePrioritizedReplayMemory
+    from maddpg_b200.env import SCENARIOS
+    cap, E = 1000000, 4096
+    mem = DevicePrioritizedReplayMemory(cap, numpy_io=False, strict=False)
+    z = lambda *sh: torch.zeros(sh, device="cuda")
+    for _ in range(25):  # 25 lockstep steps of 4096 env instances pending, like a rollout between two updates
+        mem.add(z(E, 18), z(E, 5), z(E), z(E, 18), torch.zeros(E, dtype=torch.uint8, device="cuda"))
+    u = torch.rand(batch, dtype=torch.float64, device="cuda")
+    err = torch.rand(batch, dtype=torch.float64, device="cuda")
+
+    def round_():
+        tidx, _, _ = mem.sample(batch, uniforms=u)
+        mem.batch_update(tidx, err)
+
+    round_()  # flushes the 102 400 pending adds
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]
+    for a, b in ev:
+        a.record(); round_(); b.record()
+    torch.cuda.synchronize()
+    round_us = median([a.elapsed_time(b) for a, b in ev]) * 1e3
+    a, b = ev[0]
+    mem.add(z(E, 18), z(E, 5), z(E), z(E, 18), torch.zeros(E, dtype=torch.uint8, device="cuda"))
+    a.record(); mem.flush(); b.record()
+    torch.cuda.synchronize()
+    prio = {"capacity": cap, "batch": batch, "sample_plus_update_us": round_us, "flush_4096_adds_us": a.elapsed_time(b) * 1e3,
+            "api": "DevicePrioritizedReplayMemory.sample(batch) + batch_update(tree_idx, |err|) (mdp_sumtree_sample / _update); "
+                   "tree indices bit-identical to the reference class given the same uniforms (tests/test_prioritized_gpu.py)"}
+    if with_cpu:
+        from oracle.prioritized import PrioritizedReplayOracle
+        orc = PrioritizedReplayOracle(cap)
+        orc.tree.add(1e6, 25 * E)
+        orc.tree.update_all()
+        uu, ee = np.random.RandomState(0).random_sample(batch), np.random.RandomState(1).random_sample(batch)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            seg = orc.tree.total_p / batch
+            idx = [orc.tree.get_leaf(seg * i + seg * uu[i])[0] for i in range(batch)]
+            orc.batch_update(idx, ee.copy())
+        prio["cpu_port_us"] = (time.perf_counter() - t0) / 3 * 1e6
+    scen = {}
+    for name in SCENARIOS:
+        env = BatchedMultiAgentEnv(name, num_envs=E, squeeze=False)
+        env.reset_device()
+        env.act.copy_(torch.softmax(torch.randn_like(env.act), -1))
+        g = torch.cuda.CUDAGraph()
+        for _ in range(2):
+            env.step_device()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            for _ in range(24):
+                env.step_device()
+        g.replay()
+        a, b = ev[1]
+        a.record(); g.replay(); b.record()
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / 24
+        scen[name] = {"agents": env.n, "obs_dims": env.obs_dims, "act_dims": env.act_dims, "env_step_us": us,
+                      "agent_env_steps_per_s": E * env.n / (us * 1e-6), "bytes_per_env_step": env.env_bytes_per_step}
+    return {"prioritized_replay": prio, "env_step_4096_envs": scen,
+            "note": "env step alone (no actor, no insert), graph-replayed; simple_reference is not built (15 action columns)"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -658,6 +725,11 @@ def main():
         torch.cuda.empty_cache()
         tensor = tensor_core_section(torch, dev)
 
+    # ---- (7) SURVEY 8(f) rows: device prioritized replay (rank 4) and the other MPE scenarios (rank 2) --------------------
+    extras = None
+    if headline and rank == 0 and world == 1:
+        extras = next_rows_section(torch, BATCH, not args.no_cpu_baseline)
+
     # dominant kernel of the timed rollout region: the persistent episode kernel
     row_bytes = 4 * sum(2 * d + k + 2 for d, k in zip(env.obs_dims, env.act_dims))
     launch_steps = min(K, EP_LEN * eps_launch) if roll.mode == "mega" else 1
@@ -742,6 +814,8 @@ def main():
         }
         if tensor is not None:
             line["tensor_core_td_target"] = tensor
+        if extras is not None:
+            line["next_rows"] = extras
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

@@ -270,7 +270,9 @@ def test_graph_rollout_and_update_round_match_eager_semantics():
 
 @pytest.mark.parametrize("scenario,units,generic", [("simple_spread", 64, True), ("simple_spread", 64, False),
                                                     ("simple_tag", 64, True), ("simple", 64, True),
-                                                    ("simple_world_comm", 128, True)])
+                                                    ("simple_world_comm", 128, True), ("simple_adversary", 64, True),
+                                                    ("simple_push", 64, True), ("simple_speaker_listener", 64, True),
+                                                    ("simple_crypto", 64, True)])
 def test_episode_kernel_matches_per_step_kernels(scenario, units, generic):
     """mdp_rollout_episode (persistent episode kernel, fp32 SIMT actor tiles) against the per-step path on the same
     seeds and Philox counters: identical replay rows, final state and observations (incl. the device reset)."""
