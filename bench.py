@@ -343,7 +343,7 @@ def next_rows_section(torch, batch, with_cpu):
         scen[name] = {"agents": env.n, "obs_dims": env.obs_dims, "act_dims": env.act_dims, "env_step_us": us,
                       "agent_env_steps_per_s": E * env.n / (us * 1e-6), "bytes_per_env_step": env.env_bytes_per_step}
     return {"prioritized_replay": prio, "env_step_4096_envs": scen,
-            "note": "env step alone (no actor, no insert), graph-replayed; simple_reference is not built (15 action columns)"}
+            "note": "env step alone (no actor, no insert), graph-replayed"}
 
 
 def main():

@@ -46,9 +46,9 @@ enum { MDP_OK = 0, MDP_EINVAL = -1, MDP_ECUDA = -2, MDP_ENOTSUP = -3 };
 
 /* scenario ids: multiagent/scenarios/<name>.py, loaded at experiments/train.py:53 */
 enum { MDP_SIMPLE = 0, MDP_SIMPLE_SPREAD = 1, MDP_SIMPLE_TAG = 2, MDP_SIMPLE_WORLD_COMM = 3,
-       /* the other scenarios `train.py --scenario` can name (simple_reference is not built: its
-        * MultiDiscrete([5, 10]) action block is wider than the 9 action columns the update kernels carry per agent) */
-       MDP_SIMPLE_ADVERSARY = 4, MDP_SIMPLE_PUSH = 5, MDP_SIMPLE_SPEAKER_LISTENER = 6, MDP_SIMPLE_CRYPTO = 7 };
+       /* the other scenarios `train.py --scenario` can name */
+       MDP_SIMPLE_ADVERSARY = 4, MDP_SIMPLE_PUSH = 5, MDP_SIMPLE_SPEAKER_LISTENER = 6, MDP_SIMPLE_CRYPTO = 7,
+       MDP_SIMPLE_REFERENCE = 8 };
 
 typedef struct mdp_env_cfg {
   int32_t scenario;   /* MDP_SIMPLE ... */

@@ -12,7 +12,8 @@ MAX_HEADS = 2
 
 MDP_OK, MDP_EINVAL, MDP_ECUDA, MDP_ENOTSUP = 0, -1, -2, -3
 SCENARIO_IDS = {"simple": 0, "simple_spread": 1, "simple_tag": 2, "simple_world_comm": 3,
-                "simple_adversary": 4, "simple_push": 5, "simple_speaker_listener": 6, "simple_crypto": 7}
+                "simple_adversary": 4, "simple_push": 5, "simple_speaker_listener": 6, "simple_crypto": 7,
+                "simple_reference": 8}
 NET_P, NET_TARGET_P, NET_Q, NET_TARGET_Q = 0, 1, 2, 3
 
 _I32A = C.c_int32 * MAX_AGENTS

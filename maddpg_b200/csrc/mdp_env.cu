@@ -425,6 +425,12 @@ static int build_env(mdp_env* env) {
     for (int i = 0; i < A; ++i) { P.size[i] = 0.075; P.sens[i] = 5.0; P.max_speed[i] = -1; }
     for (int l = 0; l < L; ++l) P.size[A + l] = 0.04;
     movable = 0x2u; P.c_dim[0] = 3;
+  } else if (sc == MDP_SIMPLE_REFERENCE) {
+    // two agents, each told (through the other's 10-channel message) which of 3 landmarks the OTHER should reach; both move
+    // and speak: MultiDiscrete([[0, 4], [0, 9]]) action blocks; goal slot i = agent i's goal_b; shared reward
+    A = 2; L = 3; P.n_goal = 2; P.collide_mask = 0; P.collaborative = 1;
+    for (int i = 0; i < A; ++i) { P.size[i] = 0.05; P.sens[i] = 5.0; P.max_speed[i] = -1; P.c_dim[i] = 10; }
+    for (int l = 0; l < L; ++l) P.size[A + l] = 0.05;
   } else if (sc == MDP_SIMPLE_CRYPTO) {
     // covert communication: agent 0 = adversary (Eve), agent 1 = listener (Bob), agent 2 = speaker (Alice); nobody moves, everybody
     // speaks (dim_c = 4); goal slot 0 = the goal landmark, slot 1 = the key
@@ -462,9 +468,11 @@ static int build_env(mdp_env* env) {
     D.act_dim[i] = D.head_dim[i][0] + D.head_dim[i][1];
     aoff += D.act_dim[i];
     if (sc >= MDP_SIMPLE_ADVERSARY) {
-      // head layout of MultiAgentEnv.__init__: Discrete(5) if movable, Discrete(dim_c) if not silent (never both here)
-      D.head_dim[i][0] = ((movable >> i) & 1u) ? 5 : P.c_dim[i];
-      D.act_dim[i] = D.head_dim[i][0];
+      // head layout of MultiAgentEnv.__init__: Discrete(5) if movable, Discrete(dim_c) if not silent, MultiDiscrete of both
+      const bool mv = (movable >> i) & 1u;
+      D.head_dim[i][0] = mv ? 5 : P.c_dim[i];
+      if (mv && P.c_dim[i]) { D.n_heads[i] = 2; D.head_dim[i][1] = P.c_dim[i]; }  // MultiDiscrete([movement, message])
+      D.act_dim[i] = D.head_dim[i][0] + D.head_dim[i][1];
       aoff += D.act_dim[i] - 5;
       const int lm0 = pc(A, 0), g0 = P.gcomp0;
       auto vel = [&]() { for (int c = 0; c < 2; ++c) push_col(cols, OK_DIRECT, i, 0, 0, vc(i, c), 0); };
@@ -507,6 +515,11 @@ static int build_env(mdp_env* env) {
         } else {       // listener
           vel(); entity_pos(); comm_of(0);
         }
+      } else if (sc == MDP_SIMPLE_REFERENCE) {
+        vel(); entity_pos();
+        for (int ch = 0; ch < 3; ++ch)  // goal_b's colour: 0.75 on its own channel, 0.25 elsewhere
+          goal_lut(i, ch == 0 ? LUT_075 : LUT_025, ch == 1 ? LUT_075 : LUT_025, ch == 2 ? LUT_075 : LUT_025, LUT_025);
+        comm_of(1 - i);
       } else {  // MDP_SIMPLE_CRYPTO: one-hot "colours" in dim_c = 4 channels
         auto onehot = [&](int slot) {
           for (int ch = 0; ch < 4; ++ch)

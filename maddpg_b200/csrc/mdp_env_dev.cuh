@@ -321,6 +321,11 @@ __device__ __forceinline__ void env_flags_rewards(const EnvParams& P, EnvTile<re
         const int ge = P.A + (int)sS[P.gcomp0 * EBP + e];  // the speaker's goal_b; goal_a is the listener (agent 1)
         const real dx = PX(1) - PX(ge), dy = PY(1) - PY(ge);
         r = -(dx * dx + dy * dy);
+      } else if (P.scenario == MDP_SIMPLE_REFERENCE) {
+        // agent i wants the OTHER agent (goal_a) on landmark goal_b_i: -sum(square(goal_a.p_pos - goal_b.p_pos))
+        const int ge = P.A + (int)sS[(P.gcomp0 + i) * EBP + e];
+        const real dx = PX(1 - i) - PX(ge), dy = PY(1 - i) - PY(ge);
+        r = -(dx * dx + dy * dy);
       } else if (P.scenario == MDP_SIMPLE_CRYPTO) {
         const int g = (int)sS[P.gcomp0 * EBP + e];  // goal landmark: its "colour" is the one-hot of its index in dim_c channels
         auto all_zero = [&](int a) -> bool {

@@ -30,8 +30,8 @@ constexpr int NT = 256;   // threads per group: 16 (row groups) x 16 (column qua
 constexpr int KUNROLL = MDP_KUNROLL;
 constexpr int KC = 32;    // K-chunk streamed through shared memory
 constexpr int XP = KC + 4;
-constexpr int KPAD = 12;  // pitch of per-row action/logit scratch (max act_dim 9)
-constexpr int MAXK = 9;
+constexpr int KPAD = 16;  // pitch of per-row action/logit scratch
+constexpr int MAXK = 15;  // widest action block: MultiDiscrete([5, 10]) of simple_reference (the tcgen05 kernels carry 9: TC_MAXK)
 
 // Layer-1 input: up to two global column segments plus an optional shared-memory override range
 // (the freshly sampled action that replaces the replayed one).

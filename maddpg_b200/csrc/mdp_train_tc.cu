@@ -23,6 +23,16 @@
 #include <algorithm>
 #include <vector>
 
+// The tensor-core epilogues keep per-row action vectors in REGISTER arrays: they carry at most 9 action columns per agent
+// (Discrete(5), MultiDiscrete([5, 4])); wider heads (simple_reference: [5, 10]) run the SIMT kernels (MDP_ENOTSUP here).
+constexpr int TC_KPAD = 12;
+constexpr int TC_MAXK = 9;
+static inline bool tc_heads_ok(const mdp_core* c) {
+  for (int i = 0; i < c->cfg.n_agents; ++i)
+    if (c->cfg.act_dim[i] > TC_MAXK) return false;
+  return true;
+}
+
 namespace mdp {
 namespace tc {
 
@@ -39,7 +49,7 @@ struct Lay {
   static constexpr uint32_t W2_IMG = (U / 32) * W_IMG;   // [U][U] image
   static constexpr uint32_t OFF_W2 = NS * 2 * W_IMG;
   static constexpr uint32_t OFF_MISC = OFF_W2 + 2 * W2_IMG;
-  static constexpr int MISC_FLOATS = U + U + U * MAXK + 16 + 2 * TMR * KPAD + TMR + 2 * TMR + 2 * TMR;  // b1 b2 W3 b3 part noise q rd rowoff
+  static constexpr int MISC_FLOATS = U + U + U * TC_MAXK + 16 + 2 * TMR * TC_KPAD + TMR + 2 * TMR + 2 * TMR;  // b1 b2 W3 b3 part noise q rd rowoff
   // tensor memory columns (512 allocated): accumulators, h1 (hi | lo), NS x-chunk slots (hi | lo, 32 columns each)
   static constexpr uint32_t T_ACC1 = 0, T_ACC2 = U, T_H1 = 2 * U, T_X = 4 * U;
   static constexpr uint32_t T_COLS = 512;
@@ -361,7 +371,7 @@ __device__ __forceinline__ void forward_hidden_tc(Bars* bars, Pipe& pipe, uint32
 
 // out[a] = sum over this thread's units of h2 * W3[:, a]   (a < KK); the two unit halves of a row are combined by the caller
 template <int U, int KK>
-__device__ __forceinline__ void head_partial(const float (&h2)[U / 2], const float* __restrict__ sW3, int half, float (&out)[MAXK]) {
+__device__ __forceinline__ void head_partial(const float (&h2)[U / 2], const float* __restrict__ sW3, int half, float (&out)[TC_MAXK]) {
 #pragma unroll
   for (int a = 0; a < KK; ++a) out[a] = 0.f;
 #pragma unroll
@@ -398,10 +408,10 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   float* sB1 = misc;
   float* sB2 = sB1 + U;
   float* sW3 = sB2 + U;
-  float* sB3 = sW3 + U * MAXK;
+  float* sB3 = sW3 + U * TC_MAXK;
   float* sPart = sB3 + 16;
-  float* sG = sPart + TMR * KPAD;  // Gumbel noise -log(-log u) of the current actor, [row][KPAD]
-  float* sQ = sG + TMR * KPAD;
+  float* sG = sPart + TMR * TC_KPAD;  // Gumbel noise -log(-log u) of the current actor, [row][TC_KPAD]
+  float* sQ = sG + TMR * TC_KPAD;
   float* sRD = sQ + TMR;
   long long* sRow = reinterpret_cast<long long*>(sRD + 2 * TMR);
   const int ASP = C.act_stride | 1;
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
   } else {
     // ===== compute warps =====
     float h2[U / 2];
-    float part[MAXK];
+    float part[TC_MAXK];
     // a'_i = gumbel_softmax(target_p_i(next_obs_i)) for every agent the critic sees
     for (int i = i_begin; i < i_end; ++i) {
       const AgentDev& ag = C.agents[i];
@@ -475,45 +485,45 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
         for (int a = half; a < K; a += 2) {
           const float u = u_target ? u_target[(row0 + min(row, nrows - 1)) * u_stride + ag.act_off + a]
                                    : philox_u(seed, counter, (uint32_t)(0x100 + i), row0 + row, a);
-          sG[row * KPAD + a] = gumbel_from_u(u);
+          sG[row * TC_KPAD + a] = gumbel_from_u(u);
         }
       });
       if (K == 5) head_partial<U, 5>(h2, sW3, half, part);
       else if (K == 9) head_partial<U, 9>(h2, sW3, half, part);
       else {
-        for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+        for (int a = 0; a < TC_MAXK; ++a) part[a] = 0.f;
         for (int a = 0; a < K; ++a)
           for (int g = 0; g < U / 64; ++g)
             for (int t = 0; t < 32; ++t) part[a] = fmaf(h2[32 * g + t], sW3[(32 * half + 64 * g + t) * K + a], part[a]);
       }
       if (half == 1)
-        for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+        for (int a = 0; a < K; ++a) sPart[row * TC_KPAD + a] = part[a];
       named_sync();
       if (half == 0) {  // one thread per batch row: logits -> Gumbel-softmax per head (distributions.py:264-266, 332-336)
-        float z[MAXK];
+        float z[TC_MAXK];
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a) {
+        for (int a = 0; a < TC_MAXK; ++a) {
           if (a < K) {
-            const float logit = part[a] + sPart[row * KPAD + a] + sB3[a];
-            z[a] = logit + sG[row * KPAD + a];
+            const float logit = part[a] + sPart[row * TC_KPAD + a] + sB3[a];
+            z[a] = logit + sG[row * TC_KPAD + a];
           }
         }
         for (int h = 0; h < ag.n_heads; ++h) {
           const int o = h ? ag.head_dim[0] : 0, n = ag.head_dim[h];
           float m = -INFINITY;
 #pragma unroll
-          for (int a = 0; a < MAXK; ++a)
+          for (int a = 0; a < TC_MAXK; ++a)
             if (a >= o && a < o + n) m = fmaxf(m, z[a]);
           float ssum = 0.f;
 #pragma unroll
-          for (int a = 0; a < MAXK; ++a)
+          for (int a = 0; a < TC_MAXK; ++a)
             if (a >= o && a < o + n) { z[a] = expf(z[a] - m); ssum += z[a]; }
 #pragma unroll
-          for (int a = 0; a < MAXK; ++a)
+          for (int a = 0; a < TC_MAXK; ++a)
             if (a >= o && a < o + n) z[a] = z[a] / ssum;
         }
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a < K) {
             actT[(size_t)row * ASP + ag.act_off + a] = z[a];
             if (target_act_out && row < nrows) target_act_out[(row0 + row) * u_stride + ag.act_off + a] = z[a];
@@ -531,13 +541,13 @@ __global__ void __launch_bounds__(NTT, 1) k_td_target_tc(CoreDev C, const AgentI
     const MlpW tq = me.net[MDP_NET_TARGET_Q];
     forward_hidden_tc<U>(&bars, pipe, tbase, xq, tq, sRow, sB1, sB2, sW3, sB3, h2, []() {});
     head_partial<U, 1>(h2, sW3, half, part);
-    if (half == 1) sPart[row * KPAD] = part[0];
+    if (half == 1) sPart[row * TC_KPAD] = part[0];
     named_sync();
     if (half == 0) {
       // y = float32(rew + gamma * (1 - done) * q')  -- float64 combine like numpy (maddpg.py:186)
       double sy = 0, syy = 0, sr = 0, sq = 0;
       if (row < nrows) {
-        const float qn = part[0] + sPart[row * KPAD] + sB3[0];
+        const float qn = part[0] + sPart[row * TC_KPAD] + sB3[0];
         const double rew = (double)sRD[2 * row], done = (double)sRD[2 * row + 1];
         const double y = rew + C.gamma * (1.0 - done) * (double)qn;
         y_out[row0 + row] = (float)y;
@@ -588,10 +598,10 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_act_tc(CoreDev C, const AgentI
   float* sB1 = misc;
   float* sB2 = sB1 + U;
   float* sW3 = sB2 + U;
-  float* sB3 = sW3 + U * MAXK;
+  float* sB3 = sW3 + U * TC_MAXK;
   float* sPart = sB3 + 16;
-  float* sG = sPart + TMR * KPAD;
-  float* sQ = sG + TMR * KPAD;
+  float* sG = sPart + TMR * TC_KPAD;
+  float* sQ = sG + TMR * TC_KPAD;
   float* sRD = sQ + TMR;
   long long* sRow = reinterpret_cast<long long*>(sRD + 2 * TMR);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -625,7 +635,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_act_tc(CoreDev C, const AgentI
     mma_net<U>(smem, &bars, pipe, tb, ag.obs_dim);
   } else {
     float h2[U / 2];
-    float part[MAXK];
+    float part[TC_MAXK];
     const MlpW w = ag.net[net];
     XT xs{obs + ag.obs_off, ag.obs_dim, nullptr, 0, 0, 0, ((ag.obs_off & 3) == 0 && (obs_stride & 3) == 0) ? 1 : 0};
     const int K = ag.act_dim;
@@ -634,46 +644,46 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_act_tc(CoreDev C, const AgentI
       for (int a = half; a < K; a += 2) {
         const long long r = row0 + min(row, nrows - 1);
         const float uu = u ? u[r * act_stride + ag.act_off + a] : philox_u(seed, counter, (uint32_t)i, r + rng_row_base, a);
-        sG[row * KPAD + a] = gumbel_from_u(uu);
+        sG[row * TC_KPAD + a] = gumbel_from_u(uu);
       }
     });
     if (K == 5) head_partial<U, 5>(h2, sW3, half, part);
     else if (K == 9) head_partial<U, 9>(h2, sW3, half, part);
     else {
-      for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+      for (int a = 0; a < TC_MAXK; ++a) part[a] = 0.f;
       for (int a = 0; a < K; ++a)
         for (int g = 0; g < U / 64; ++g)
           for (int t = 0; t < 32; ++t) part[a] = fmaf(h2[32 * g + t], sW3[(32 * half + 64 * g + t) * K + a], part[a]);
     }
     if (half == 1)
-      for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+      for (int a = 0; a < K; ++a) sPart[row * TC_KPAD + a] = part[a];
     named_sync();
     if (half == 0 && row < nrows) {  // one thread per env instance: logits -> Gumbel-softmax per head
-      float z[MAXK], lg[MAXK];
+      float z[TC_MAXK], lg[TC_MAXK];
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a) {
+      for (int a = 0; a < TC_MAXK; ++a) {
         if (a < K) {
-          lg[a] = part[a] + sPart[row * KPAD + a] + sB3[a];
-          z[a] = lg[a] + sG[row * KPAD + a];
+          lg[a] = part[a] + sPart[row * TC_KPAD + a] + sB3[a];
+          z[a] = lg[a] + sG[row * TC_KPAD + a];
         }
       }
       for (int h = 0; h < ag.n_heads; ++h) {
         const int o = h ? ag.head_dim[0] : 0, n = ag.head_dim[h];
         float m = -INFINITY;
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) m = fmaxf(m, z[a]);
         float ssum = 0.f;
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) { z[a] = expf(z[a] - m); ssum += z[a]; }
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) z[a] = z[a] / ssum;
       }
       float* arow = act + (row0 + row) * (long long)act_stride + ag.act_off;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
+      for (int a = 0; a < TC_MAXK; ++a)
         if (a < K) {
           arow[a] = z[a];
           if (logits_out) logits_out[(row0 + row) * (long long)act_stride + ag.act_off + a] = lg[a];
@@ -1183,7 +1193,7 @@ struct LayA {
   static constexpr uint32_t R1 = 0, R2 = L::OFF_W2, S1 = L::OFF_W2 + 2 * L::W2_IMG;
   static constexpr uint32_t OFF_MISC = S1 + 2 * ACT_IMG;
   // b1p b2p W3p b3p | b1q b2q W3q b3q | W1q action rows | part dl act noise | rowoff
-  static constexpr int MISC_FLOATS = (2 * U + U * MAXK + 16) + (3 * U + 16) + MAXK * U + 4 * TMR * KPAD + 2 * TMR;
+  static constexpr int MISC_FLOATS = (2 * U + U * TC_MAXK + 16) + (3 * U + 16) + TC_MAXK * U + 4 * TMR * TC_KPAD + 2 * TMR;
   static constexpr uint32_t T_DW = L::T_X;
 };
 
@@ -1211,17 +1221,17 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
   float* sB1p = misc;
   float* sB2p = sB1p + U;
   float* sW3p = sB2p + U;
-  float* sB3p = sW3p + U * MAXK;
+  float* sB3p = sW3p + U * TC_MAXK;
   float* sB1q = sB3p + 16;
   float* sB2q = sB1q + U;
   float* sW3q = sB2q + U;
   float* sB3q = sW3q + U;
   float* sW1a = sB3q + 16;             // [K][U]: critic W1 rows of agent j's action columns
-  float* sPart = sW1a + MAXK * U;      // [TMR][KPAD] half-1 partial sums
-  float* sDl = sPart + TMR * KPAD;     // [TMR][KPAD] dL/dlogits
-  float* sAct = sDl + TMR * KPAD;      // [TMR][KPAD] fresh action sample
-  float* sG = sAct + TMR * KPAD;       // [TMR][KPAD] Gumbel noise
-  long long* sRow = reinterpret_cast<long long*>(sG + TMR * KPAD);
+  float* sPart = sW1a + TC_MAXK * U;      // [TMR][TC_KPAD] half-1 partial sums
+  float* sDl = sPart + TMR * TC_KPAD;     // [TMR][TC_KPAD] dL/dlogits
+  float* sAct = sDl + TMR * TC_KPAD;      // [TMR][TC_KPAD] fresh action sample
+  float* sG = sAct + TMR * TC_KPAD;       // [TMR][TC_KPAD] Gumbel noise
+  long long* sRow = reinterpret_cast<long long*>(sG + TMR * TC_KPAD);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const AgentDev& me = C.agents[j];
   const MlpW pw = me.net[MDP_NET_P], qw = me.net[MDP_NET_Q];
@@ -1367,7 +1377,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     for (int a = half; a < K; a += 2) {  // Gumbel noise of this row, hidden behind the layer-1 MMAs
       const float u = u_actor ? u_actor[(row0 + min(row, nrows - 1)) * u_stride + me.act_off + a]
                               : philox_u(seed, counter, (uint32_t)(0x200 + j), row0 + row, a);
-      sG[row * KPAD + a] = gumbel_from_u(u);
+      sG[row * TC_KPAD + a] = gumbel_from_u(u);
     }
     mbar_wait_bounded(&bars.acc, 0);
     umma::fence_after();
@@ -1384,30 +1394,30 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     umma::fence_after();
     float h2p[32];
     umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, h2p);
-    float part[MAXK];
+    float part[TC_MAXK];
 #pragma unroll
-    for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+    for (int a = 0; a < TC_MAXK; ++a) part[a] = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       h2p[i] = fmaxf(h2p[i] + sB2p[c0 + i], 0.f);
       mask2p |= (h2p[i] > 0.f ? 1u : 0u) << i;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
+      for (int a = 0; a < TC_MAXK; ++a)
         if (a < K) part[a] = fmaf(h2p[i], sW3p[(c0 + i) * K + a], part[a]);
     }
     umma::fence_before();
     if (half == 1)
-      for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+      for (int a = 0; a < K; ++a) sPart[row * TC_KPAD + a] = part[a];
     named_sync();
-    float logit[MAXK], act[MAXK];
+    float logit[TC_MAXK], act[TC_MAXK];
     if (half == 0) {  // logits -> fresh Gumbel-softmax sample (maddpg.py:49), per head
       double sl = 0.0;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a) {
+      for (int a = 0; a < TC_MAXK; ++a) {
         logit[a] = 0.f; act[a] = 0.f;
         if (a < K) {
-          logit[a] = part[a] + sPart[row * KPAD + a] + sB3p[a];
-          act[a] = logit[a] + sG[row * KPAD + a];
+          logit[a] = part[a] + sPart[row * TC_KPAD + a] + sB3p[a];
+          act[a] = logit[a] + sG[row * TC_KPAD + a];
           if (valid) sl += (double)logit[a] * (double)logit[a];
         }
       }
@@ -1415,24 +1425,24 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
         const int o = h ? me.head_dim[0] : 0, n = me.head_dim[h];
         float m = -INFINITY, ssum = 0.f;
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) m = fmaxf(m, act[a]);
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) { act[a] = expf(act[a] - m); ssum += act[a]; }
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) act[a] = act[a] / ssum;
       }
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
-        if (a < K) sAct[row * KPAD + a] = act[a];
+      for (int a = 0; a < TC_MAXK; ++a)
+        if (a < K) sAct[row * TC_KPAD + a] = act[a];
       for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
       if (lane == 0) atomicAdd(C.stats + 8 * j + 2, sl);
     }
     named_sync();  // the sample is visible to the critic's gather
     // ---- running critic on [o, a_-j, a_hat_j]
-    const XT xq{batch, L.x_dim, sAct, KPAD, a_col0, K, 1};
+    const XT xq{batch, L.x_dim, sAct, TC_KPAD, a_col0, K, 1};
     layer1(xq, nq);
     mbar_wait_bounded(&bars.acc, 0);
     umma::fence_after();
@@ -1454,7 +1464,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
       mask2q |= (h > 0.f ? 1u : 0u) << i;
       qpart = fmaf(h, sW3q[c0 + i], qpart);
     }
-    if (half == 1) sPart[row * KPAD] = qpart;
+    if (half == 1) sPart[row * TC_KPAD] = qpart;
     // dz2q = (-1/B) W3q^T relu'(h2q) for valid rows  (the actor loss is -mean(q))
     const float dq = valid ? -1.0f / (float)B : 0.f;
 #pragma unroll
@@ -1463,7 +1473,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     warp_arrive_tmem(&bars.a_full, lane);  // a_full phase 2
     named_sync();
     if (half == 0) {
-      double sq = valid ? -(double)(qpart + sPart[row * KPAD] + sB3q[0]) : 0.0;
+      double sq = valid ? -(double)(qpart + sPart[row * TC_KPAD] + sB3q[0]) : 0.0;
       for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
       if (lane == 0) atomicAdd(C.stats + 8 * j + 1, sq);
     }
@@ -1473,41 +1483,41 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     umma::tmem_ld32(tbase + LY::T_ACC2 + lane_base + (uint32_t)c0, v);
     umma::fence_before();
 #pragma unroll
-    for (int a = 0; a < MAXK; ++a) part[a] = 0.f;
+    for (int a = 0; a < TC_MAXK; ++a) part[a] = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float dz = ((mask1q >> i) & 1u) ? v[i] : 0.f;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
+      for (int a = 0; a < TC_MAXK; ++a)
         if (a < K) part[a] = fmaf(dz, sW1a[a * U + c0 + i], part[a]);  // dQ/da = dz1q . W1q[a_col0 + a, :]
     }
     named_sync();  // the q partials in sPart have been consumed
     if (half == 1)
-      for (int a = 0; a < K; ++a) sPart[row * KPAD + a] = part[a];
+      for (int a = 0; a < K; ++a) sPart[row * TC_KPAD + a] = part[a];
     named_sync();
     if (half == 0) {  // softmax Jacobian per head + logit regulariser (maddpg.py:55-58)
       const float regc = (float)(2.0 * C.actor_reg / ((double)B * (double)K));
-      float dqa[MAXK];
+      float dqa[TC_MAXK];
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a) dqa[a] = a < K ? part[a] + sPart[row * KPAD + a] : 0.f;
+      for (int a = 0; a < TC_MAXK; ++a) dqa[a] = a < K ? part[a] + sPart[row * TC_KPAD + a] : 0.f;
       for (int h = 0; h < me.n_heads; ++h) {
         const int o = h ? me.head_dim[0] : 0, n = me.head_dim[h];
         float dot = 0.f;
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) dot = fmaf(act[a], dqa[a], dot);
 #pragma unroll
-        for (int a = 0; a < MAXK; ++a)
+        for (int a = 0; a < TC_MAXK; ++a)
           if (a >= o && a < o + n) {
             const float dl = act[a] * (dqa[a] - dot) + regc * logit[a];
-            sDl[row * KPAD + a] = valid ? dl : 0.f;
+            sDl[row * TC_KPAD + a] = valid ? dl : 0.f;
           }
       }
     }
     named_sync();
-    float dl[MAXK];
+    float dl[TC_MAXK];
 #pragma unroll
-    for (int a = 0; a < MAXK; ++a) dl[a] = a < K ? sDl[row * KPAD + a] : 0.f;
+    for (int a = 0; a < TC_MAXK; ++a) dl[a] = a < K ? sDl[row * TC_KPAD + a] : 0.f;
     // ---- actor head backward: gW3p, gb3p, dz2p
     for (int a = 0; a < K; ++a) {
       float t[32];
@@ -1526,7 +1536,7 @@ __global__ void __launch_bounds__(NTT, 1) k_actor_grads_tc(CoreDev C, const Agen
     for (int i = 0; i < 32; ++i) {
       float sacc = 0.f;
 #pragma unroll
-      for (int a = 0; a < MAXK; ++a)
+      for (int a = 0; a < TC_MAXK; ++a)
         if (a < K) sacc = fmaf(dl[a], sW3p[(c0 + i) * K + a], sacc);
       v[i] = ((mask2p >> i) & 1u) ? sacc : 0.f;  // dz2p
     }
@@ -1600,7 +1610,7 @@ static int ensure_images(mdp_core* c) {
 int launch_actor_act_tc(mdp_core* c, const CoreDev& d, int32_t agent_begin, int32_t agent_count, int32_t use_target, int32_t E,
                         const float* obs, int32_t obs_stride, float* act, int32_t act_stride, const float* u, uint64_t seed,
                         uint64_t counter, float* logits_out, long long row_base, cudaStream_t st) {
-  if (c->cfg.num_units != 64) return MDP_ENOTSUP;
+  if (c->cfg.num_units != 64 || !tc_heads_ok(c)) return MDP_ENOTSUP;
   constexpr int U = 64;
   using LY = tc::Lay<U>;
   int rc = ensure_images(c);
@@ -1628,6 +1638,7 @@ int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t co
                         const float* batch, const long long* ridx, long long idx_stride, const float* u_target, int32_t u_stride,
                         uint64_t seed, uint64_t counter, float* y_out, long long y_stride, float* target_act_out, cudaStream_t st) {
   if (c->cfg.num_units != 64) return fail(MDP_ENOTSUP, "tensor-core path: num_units %d (64 only)", c->cfg.num_units);
+  if (!tc_heads_ok(c)) return fail(MDP_ENOTSUP, "tensor-core path: an action block wider than %d columns", TC_MAXK);
   constexpr int U = 64;
   using LY = tc::Lay<U>;
   int rc = ensure_images(c);
@@ -1687,6 +1698,7 @@ int launch_critic_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t
                            const float* batch, const long long* ridx, long long idx_stride, const float* y, long long y_stride,
                            float* q_out, cudaStream_t st) {
   if (c->cfg.num_units != 64) return fail(MDP_ENOTSUP, "tensor-core path: num_units %d (64 only)", c->cfg.num_units);
+  if (!tc_heads_ok(c)) return fail(MDP_ENOTSUP, "tensor-core path: an action block wider than %d columns", TC_MAXK);
   for (int k = agent; k < agent + count; ++k)
     if (c->cfg.local_q[k]) return fail(MDP_ENOTSUP, "tensor-core critic path: local critics use the SIMT kernels");
   if ((lay->row_stride & 3) != 0) return fail(MDP_ENOTSUP, "tensor-core path: row stride");
@@ -1733,6 +1745,7 @@ int launch_actor_grads_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t 
                           const float* batch, const long long* ridx, long long idx_stride, const float* u_actor, int32_t u_stride,
                           uint64_t seed, uint64_t counter, cudaStream_t st) {
   if (c->cfg.num_units != 64) return fail(MDP_ENOTSUP, "tensor-core path: num_units %d (64 only)", c->cfg.num_units);
+  if (!tc_heads_ok(c)) return fail(MDP_ENOTSUP, "tensor-core path: an action block wider than %d columns", TC_MAXK);
   for (int k = agent; k < agent + count; ++k)
     if (c->cfg.local_q[k]) return fail(MDP_ENOTSUP, "tensor-core actor path: local critics use the SIMT kernels");
   constexpr int U = 64;

@@ -20,7 +20,7 @@ from . import _lib
 from .spaces import Box, Discrete, MultiDiscrete
 
 SCENARIOS = ("simple", "simple_spread", "simple_tag", "simple_world_comm",
-             "simple_adversary", "simple_push", "simple_speaker_listener", "simple_crypto")
+             "simple_adversary", "simple_push", "simple_speaker_listener", "simple_crypto", "simple_reference")
 
 
 def _dims_for(scenario, num_agents=None, state_f64=False):

@@ -579,7 +579,7 @@ class SimpleWorldCommScenario(BaseScenario):
 
 # --------------------------------------------------------------------------------------------
 # the other scenarios `train.py --scenario` can name.  Restated from the published upstream
-# files multiagent/scenarios/{simple_adversary,simple_push,simple_speaker_listener,simple_crypto}.py (PARITY UNPINNED like the
+# files multiagent/scenarios/{simple_adversary,simple_push,simple_speaker_listener,simple_crypto,simple_reference}.py (PARITY UNPINNED like the
 # rest of this module: the package is absent from /root/reference and from this container).  reset_world is split into the
 # goal draw (np.random.choice(world.landmarks), kept first like upstream) and ``apply_goals`` -- the goal pointers and the
 # colours upstream derives from them -- so that parity tests can inject the drawn indices.
@@ -773,6 +773,51 @@ class SimpleSpeakerListenerScenario(_GoalScenario):
         return np.concatenate([agent.state.p_vel] + entity_pos + comm)  # listener (agent.silent)
 
 
+class SimpleReferenceScenario(_GoalScenario):
+    name = "simple_reference"
+    n_goal = 2  # goal_b of agent 0, goal_b of agent 1
+
+    def make_world(self):
+        world = World()
+        world.dim_c = 10
+        world.collaborative = True
+        world.agents = [Agent() for _ in range(2)]
+        for i, agent in enumerate(world.agents):
+            agent.name = 'agent %d' % i
+            agent.collide = False
+        world.landmarks = [Landmark() for _ in range(3)]
+        for i, landmark in enumerate(world.landmarks):
+            landmark.name = 'landmark %d' % i
+            landmark.collide = False
+            landmark.movable = False
+        self.reset_world(world)
+        return world
+
+    def apply_goals(self, world, goals):
+        world.goals = list(goals)
+        world.agents[0].goal_a = world.agents[1]
+        world.agents[0].goal_b = world.landmarks[goals[0]]
+        world.agents[1].goal_a = world.agents[0]
+        world.agents[1].goal_b = world.landmarks[goals[1]]
+        world.landmarks[0].color = np.array([0.75, 0.25, 0.25])
+        world.landmarks[1].color = np.array([0.25, 0.75, 0.25])
+        world.landmarks[2].color = np.array([0.25, 0.25, 0.75])
+
+    def reward(self, agent, world):
+        if agent.goal_a is None or agent.goal_b is None:
+            return 0.0
+        dist2 = np.sum(np.square(agent.goal_a.state.p_pos - agent.goal_b.state.p_pos))
+        return -dist2
+
+    def observation(self, agent, world):
+        goal_color = [np.zeros(3), np.zeros(3)]
+        if agent.goal_b is not None:
+            goal_color[1] = agent.goal_b.color
+        entity_pos = [entity.state.p_pos - agent.state.p_pos for entity in world.landmarks]
+        comm = [other.state.c for other in world.agents if other is not agent]
+        return np.concatenate([agent.state.p_vel] + entity_pos + [goal_color[1]] + comm)
+
+
 class SimpleCryptoScenario(_GoalScenario):
     name = "simple_crypto"
     n_goal = 2  # goal landmark, key landmark
@@ -863,7 +908,8 @@ def make_scenario(name, rng=None, num_agents=None):
     if name == "simple_world_comm":
         return SimpleWorldCommScenario(rng)
     extra = {"simple_adversary": SimpleAdversaryScenario, "simple_push": SimplePushScenario,
-             "simple_speaker_listener": SimpleSpeakerListenerScenario, "simple_crypto": SimpleCryptoScenario}
+             "simple_speaker_listener": SimpleSpeakerListenerScenario, "simple_crypto": SimpleCryptoScenario,
+             "simple_reference": SimpleReferenceScenario}
     if name in extra:
         return extra[name](rng)
     raise NotImplementedError(name)

@@ -19,6 +19,7 @@ ENV_CASES = {
     "simple_push": ("simple_push", None, 16, 25),
     "simple_speaker_listener": ("simple_speaker_listener", None, 16, 25),
     "simple_crypto": ("simple_crypto", None, 16, 25),
+    "simple_reference": ("simple_reference", None, 16, 25),
 }
 
 
@@ -84,6 +85,7 @@ TRAINER_CASES = {
     "simple_speaker_listener": ("simple_speaker_listener", None, 64, 96, None),
     "simple_crypto": ("simple_crypto", None, 64, 80, None),
     "simple_adversary_ddpg_good": ("simple_adversary", None, 64, 64, [False, True, True]),
+    "simple_reference": ("simple_reference", None, 64, 72, None),   # MultiDiscrete([5, 10]) heads: 15 action columns
 }
 
 

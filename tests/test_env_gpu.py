@@ -291,7 +291,7 @@ def test_spread_warp_kernel_fused_ring_insert_matches_separate_insert(A, E):
     assert torch.equal(r0[:, L.obs_sum:L.x_dim], r1[:, L.obs_sum:L.x_dim])  # act_t is a copy of the same tape: bit-identical
 
 
-@pytest.mark.parametrize("name", ["simple_adversary", "simple_push", "simple_speaker_listener", "simple_crypto"])
+@pytest.mark.parametrize("name", ["simple_adversary", "simple_push", "simple_speaker_listener", "simple_crypto", "simple_reference"])
 def test_goal_scenarios_device_reset(name):
     """reset_world of the goal scenarios: the goal landmark index (np.random.choice(world.landmarks)) is drawn on the device per
     env instance and episode, uniformly; observations of the fresh state equal the oracle's with the same goals injected."""
@@ -342,5 +342,8 @@ def test_goal_scenarios_numpy_surface_and_spaces():
     assert rew_n[0] == rew_n[1] and done_n == [False, False]                # collaborative: shared reward
     env = make_env("simple_crypto")
     assert [s.n for s in env.action_space] == [4, 4, 4] and [s.shape for s in env.observation_space] == [(4,), (8,), (8,)]
+    env = make_env("simple_reference")
+    assert [(int(s.low[0]), int(s.high[0]), int(s.low[1]), int(s.high[1])) for s in env.action_space] == [(0, 4, 0, 9)] * 2
+    assert [s.shape for s in env.observation_space] == [(21,), (21,)]
     with pytest.raises(NotImplementedError):
-        make_env("simple_reference")
+        make_env("simple_football")

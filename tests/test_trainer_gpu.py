@@ -272,7 +272,7 @@ def test_graph_rollout_and_update_round_match_eager_semantics():
                                                     ("simple_tag", 64, True), ("simple", 64, True),
                                                     ("simple_world_comm", 128, True), ("simple_adversary", 64, True),
                                                     ("simple_push", 64, True), ("simple_speaker_listener", 64, True),
-                                                    ("simple_crypto", 64, True)])
+                                                    ("simple_crypto", 64, True), ("simple_reference", 64, True)])
 def test_episode_kernel_matches_per_step_kernels(scenario, units, generic):
     """mdp_rollout_episode (persistent episode kernel, fp32 SIMT actor tiles) against the per-step path on the same
     seeds and Philox counters: identical replay rows, final state and observations (incl. the device reset)."""
@@ -346,7 +346,7 @@ def test_train_loop_drop_in(tmp_path, num_envs):
 
 
 @pytest.mark.parametrize("scenario,num_envs", [("simple_speaker_listener", 1), ("simple_crypto", 32), ("simple_push", 32),
-                                               ("simple_adversary", 1)])
+                                               ("simple_adversary", 1), ("simple_reference", 16)])
 def test_train_loop_drop_in_goal_scenarios(tmp_path, scenario, num_envs):
     """the reference's own experiments/train.py on the other MPE scenarios (Discrete(3) / Discrete(4)
     communication heads, immovable agents, goal landmarks drawn by reset_world), reference shapes and the batched superset."""
