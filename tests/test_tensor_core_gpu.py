@@ -42,7 +42,7 @@ def test_td_target_tensor_cores_match_oracle_and_simt(name):
         _close(y_tc.cpu().numpy(), ref[j]["y"], atol=2e-6, msg="td target vs oracle")
         _close(y_tc.cpu().numpy(), y_simt.cpu().numpy(), rtol=2e-5, atol=2e-6, msg="td target vs SIMT")
         _close(ta_tc.cpu().numpy(), ta_simt.cpu().numpy(), rtol=2e-5, atol=1e-6, msg="target actions vs SIMT")
-        _close(st_tc[8 * j:8 * j + 8].cpu().numpy(), st_simt[8 * j:8 * j + 8].cpu().numpy(), rtol=1e-5, atol=1e-6, msg="stats")
+        _close(st_tc[8 * j:8 * j + 8].cpu().numpy(), st_simt[8 * j:8 * j + 8].cpu().numpy(), rtol=1e-5, atol=2e-6 * B, msg="stats")  # sums over B rows, each within 2e-6
         # fused gather: rows addressed through the index set straight from the ring
         y_idx = core.td_target(j, core.ring.ring, ut, idx=idx)
         assert torch.equal(y_idx, y_tc)
