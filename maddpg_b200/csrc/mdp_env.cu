@@ -570,7 +570,7 @@ static int build_env(mdp_env* env) {
   D.act_stride = round_up(D.act_sum, 4);
   while ((int)cols.size() < D.obs_stride) push_col(cols, OK_PAD, 0, 0, 0, 0, 0);
   for (auto& c : cols) {  // plain columns are evaluated as S[a] - S[b]; row `scomp` of the smem tile is all zeros
-    if (c.kind == OK_DIRECT) c.b = (uint8_t)P.scomp;
+    if (c.kind == OK_DIRECT || c.kind == OK_DIR_MASK) c.b = (uint8_t)P.scomp;
     if (c.kind == OK_ZERO || c.kind == OK_PAD) c.a = c.b = (uint8_t)P.scomp;
     if (c.kind > OK_ZERO) P.has_mask = 1;
   }

@@ -392,6 +392,20 @@ __device__ __forceinline__ void env_flags_rewards(const EnvParams& P, EnvTile<re
     }
   }
   __syncthreads();
+  if (P.scenario == MDP_SIMPLE_WORLD_COMM) {
+    // visibility of every other agent, once per (env, agent) instead of once per observation column: o is visible to i when both
+    // stand in the same forest, or neither stands in any, or i is the leader (simple_world_comm.py observation())
+    if (live) {
+      const int fi = T.sF[i * EBP + e] & 3;
+      int vis = 0;
+      for (int o = 0; o < P.A; ++o) {
+        const int fo = T.sF[o * EBP + e] & 3;
+        if ((fi & fo) || (fi == 0 && fo == 0) || i == 0) vis |= 1 << o;
+      }
+      T.sF[i * EBP + e] = fi | (vis << 8);  // the other threads only read bits 0-1, which do not change
+    }
+    __syncthreads();
+  }
 }
 
 // reward agent ii of env ee receives (shared reward: the sum over agents, environment.py step())
@@ -418,10 +432,8 @@ __device__ __forceinline__ float env_obs_value(const EnvTile<real, EB>& T, const
     case OK_REL: v = sS[d.a * EBP + ee] - sS[d.b * EBP + ee]; break;
     case OK_REL_MASK:
     case OK_DIR_MASK: {
-      const int fi = T.sF[d.i * EBP + ee], fo = T.sF[d.o * EBP + ee];
-      const bool inf1 = fi & 1, inf2 = fi & 2, of1 = fo & 1, of2 = fo & 2;
-      const bool vis = (inf1 && of1) || (inf2 && of2) || (!inf1 && !of1 && !inf2 && !of2) || (d.i == 0);
-      if (vis) v = (d.kind == OK_REL_MASK) ? sS[d.a * EBP + ee] - sS[d.b * EBP + ee] : sS[d.a * EBP + ee];
+      // bit 8 + o of agent i's flag word: "i sees o" (env_flags_rewards); OK_DIR_MASK columns carry b = the zero row
+      if ((T.sF[d.i * EBP + ee] >> (8 + d.o)) & 1) v = sS[d.a * EBP + ee] - sS[d.b * EBP + ee];
       break;
     }
     case OK_FOREST: v = ((T.sF[d.i * EBP + ee] >> d.k) & 1) ? (real)1 : (real)-1; break;
