@@ -190,7 +190,8 @@ __global__ void __launch_bounds__(256) k_env_step_spread_warp(EnvParams P, int E
     const float dist = __fsqrt_rn(sq_norm2(dx, dy));
     const float z = __fdiv_rn(-__fsub_rn(dist, dmin), k);
     if (z < -104.0f) continue;
-    const float pen = __fmul_rn(logaddexp0<float>(z), k);
+    // logaddexp(0, z) = log1p(exp(z)); below z = -17, exp(z) < 2^-24 and log1p(x) rounds to x itself in float32
+    const float pen = __fmul_rn(z < -17.0f ? expf(z) : logaddexp0<float>(z), k);
     fx = __fmaf_rn(__fdiv_rn(__fmul_rn(cf, dx), dist), pen, fx);
     fy = __fmaf_rn(__fdiv_rn(__fmul_rn(cf, dy), dist), pen, fy);
   }
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(256) k_env_step_spread_warp(EnvParams P, int E
   // is the sqrt of the minimum squared distance, bit for bit), lane i = agent i's collision count (sqrt only near the threshold)
   float best2 = 0.f;
   int cnt = 0;
+  unsigned amb = 0;  // pairs within 0.1 % of the collision threshold: decided on the rounded distance below (one sqrt copy)
 #pragma unroll
   for (int q = 0; q < A; ++q) {
     const float2 pq = sp[q];
@@ -221,7 +223,15 @@ __global__ void __launch_bounds__(256) k_env_step_spread_warp(EnvParams P, int E
     best2 = (q == 0 || d2l < best2) ? d2l : best2;
     const float d2a = sq_norm2(__fsub_rn(pq.x, px), __fsub_rn(pq.y, py));
     const float s = __fadd_rn(P.sizef[q], si), s2 = s * s;
-    cnt += d2a < 0.999f * s2 ? 1 : d2a > 1.001f * s2 ? 0 : (__fsqrt_rn(d2a) < s ? 1 : 0);
+    cnt += d2a < 0.999f * s2 ? 1 : 0;
+    amb |= ((d2a >= 0.999f * s2 && d2a <= 1.001f * s2) ? 1u : 0u) << q;
+  }
+  while (amb) {
+    const int q = __ffs(amb) - 1;
+    amb &= amb - 1;
+    const float2 pq = sp[q];
+    const float d2a = sq_norm2(__fsub_rn(pq.x, px), __fsub_rn(pq.y, py));
+    cnt += __fsqrt_rn(d2a) < __fadd_rn(P.sizef[q], si) ? 1 : 0;
   }
   const float best = __fsqrt_rn(best2);
   float ri = 0.f;
