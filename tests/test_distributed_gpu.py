@@ -115,3 +115,65 @@ def test_two_rank_peer_exchange_wide_critic_many_cta_path():
         for j in range(n):
             core.update_agent(j, full, ut, ua)
     np.testing.assert_allclose(out_p[0], core.params.cpu().numpy(), rtol=3e-3, atol=5e-4)
+
+
+def _oracle_worker(rank, world, port, out):
+    """One sequential update round of the seeded simple_spread trainer case, the batch split over the ranks, fused peer exchange."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from maddpg_b200 import MADDPGCore, _lib
+    from maddpg_b200.distributed import DataParallelUpdater
+    from tests.helpers import trainer_case
+    case = trainer_case("simple_spread", seed=4)
+    n, B = case["n"], case["B"]
+    core = MADDPGCore(case["obs_dims"], list(case["env"].action_space), [False] * n, device=dev, replay_capacity=4 * B, seed=5)
+    for i, o in enumerate(case["trainers"]):
+        for net, m in ((_lib.NET_P, o.p), (_lib.NET_TARGET_P, o.target_p), (_lib.NET_Q, o.q), (_lib.NET_TARGET_Q, o.target_q)):
+            core.set_weights(i, net, m.p)
+    dp = DataParallelUpdater(core, peer=True, low_latency=True)
+    L, p = core.ring.layout, case["pool"]
+    half = B // world
+    sl = slice(rank * half, (rank + 1) * half)
+    for j in range(n):  # agent j's batch = the pool rows at ITS index set, like the oracle's tr.update(index=idx[j])
+        idx = np.asarray(case["idx"][j])
+        rows = torch.zeros(B, core.ring.row_stride)
+        for i in range(n):
+            c = core.ring.cols(i)
+            rows[:, c["obs"][0]:c["obs"][1]] = torch.from_numpy(p["obs"][i][idx])
+            rows[:, c["act"][0]:c["act"][1]] = torch.from_numpy(p["act"][i][idx])
+            rows[:, c["next_obs"][0]:c["next_obs"][1]] = torch.from_numpy(p["nobs"][i][idx])
+            rows[:, c["rew"]] = torch.from_numpy(p["rew"][i][idx])
+            rows[:, c["done"]] = torch.from_numpy(p["done"][i][idx])
+        ut = torch.zeros(B, core.act_stride)
+        ut[:, :core.act_sum] = torch.from_numpy(case["u_target"][j])
+        ua = torch.zeros(B, core.act_stride)
+        ua[:, core.act_off[j]:core.act_off[j] + core.act_dims[j]] = torch.from_numpy(case["u_actor"][j])
+        dp.update_agent(j, rows[sl].contiguous().to(dev), ut[sl].contiguous().to(dev), ua[sl].contiguous().to(dev))
+    torch.cuda.synchronize()
+    out[rank] = [[w.copy() for w in core.get_weights(j, net)] for j in range(n) for net in (_lib.NET_Q, _lib.NET_P, _lib.NET_TARGET_Q, _lib.NET_TARGET_P)]
+    dist.barrier()
+    dp.peer.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_peer_exchange_matches_oracle_on_the_union_batch():
+    """The data-parallel update against the ORACLE (not against the same kernels on one GPU): every rank holds half of each
+    agent's batch; after one sequential round with the fused peer exchange the running and target nets of every agent equal the
+    numpy oracle's update on the whole batch (mean over B rows == average of the two half-batch means) at the single-GPU test's
+    tolerance."""
+    from tests.helpers import oracle_update_round, trainer_case
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_oracle_worker, args=(2, 28100 + os.getpid() % 500, out), nprocs=2, join=True)
+    ref = oracle_update_round(trainer_case("simple_spread", seed=4))
+    k = 0
+    for j in range(len(ref)):
+        for key in ("q", "p", "target_q", "target_p"):
+            for a, b, r in zip(out[0][k], out[1][k], ref[j][key]):
+                assert np.array_equal(a, b), "replicas diverged"
+                np.testing.assert_allclose(a, r, rtol=1e-3, atol=2e-4, err_msg="agent %d %s" % (j, key))
+            k += 1
