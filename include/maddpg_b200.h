@@ -92,15 +92,18 @@ int mdp_env_reset(mdp_env* env, int32_t E, void* state, const void* init_state, 
  * SURVEY Appendix A.2): one fused kernel.  state is updated in place.  ring (optional, may be null): when non-null the
  * SAME CALL also writes the joint replay rows of this transition (obs_t, act_t, next_obs, rew, done) to ring rows
  * (ring_cursor + e) % ring_capacity -- MADDPGAgentTrainer.experience / ReplayBuffer.add (maddpg.py:154-156,
- * replay_buffer.py:25-32) for all agents -- with a second launch (the joint insert kernel) on the same stream; only the
- * persistent episode kernels (mdp_rollout_episode) write the rows from inside the step.  obs_prev (joint obs_t) must then
- * be non-null. */
+ * replay_buffer.py:25-32) for all agents.  simple_spread with 7..32 agents (float32 state): the step kernel writes the rows
+ * itself (one warp per env instance assembles obs_t | act_t | next_obs | rew | done while it produces the observations);
+ * every other case: a second launch (the joint insert kernel) on the same stream.  The persistent episode kernels
+ * (mdp_rollout_episode) always write the rows from inside the step.  obs_prev (joint obs_t, a buffer distinct from obs_out)
+ * must then be non-null. */
 int mdp_env_step(mdp_env* env, int32_t E, void* state, const float* act, float* obs_out, float* rew_out,
                  uint8_t* done_out, const float* obs_prev, float* ring, int64_t ring_capacity,
                  int32_t ring_row_stride, int64_t ring_cursor, void* stream);
 
-/* mdp_env_step picks a register-resident one-thread-per-env kernel for simple_spread with <= 6 agents and float32
- * state; on = 1 forces the table-driven kernel that serves every scenario (tests compare the two). */
+/* mdp_env_step picks a register-resident one-thread-per-env kernel for simple_spread with <= 6 agents and a
+ * one-warp-per-env kernel for 7..32 agents (float32 state); on = 1 forces the table-driven kernel that serves every
+ * scenario (tests compare them). */
 int mdp_env_force_generic(mdp_env* env, int32_t on);
 
 /* Scenario.benchmark_data(agent, world) for every (env instance, agent): the info_n tape of `train.py --benchmark`
