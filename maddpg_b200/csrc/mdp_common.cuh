@@ -135,6 +135,13 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream still runs; everything it reads that the predecessor writes must come after
+// pdl_wait() (which returns once the predecessor grid has completed and flushed).  pdl_launch_dependents() in the predecessor
+// lets the dependent grid become resident early.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Gumbel-softmax noise term -log(-log(u)) in float32 (distributions.py:264-266)
 __device__ __forceinline__ float gumbel_from_u(float u) { return -logf(-logf(u)); }
 

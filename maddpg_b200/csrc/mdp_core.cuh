@@ -30,6 +30,10 @@ struct CoreDev {
   const unsigned long long* ctl;
 };
 
+// mdp_clip_adam_polyak[_all] with an optional programmatic dependent launch on the gradient kernel that precedes it (mdp_optim.cu)
+int clip_adam_polyak_impl(mdp_core* c, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak, void* stream, bool pdl);
+int clip_adam_polyak_all_impl(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream, bool pdl);
+
 }  // namespace mdp
 
 struct mdp_core {

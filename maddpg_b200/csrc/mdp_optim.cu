@@ -11,6 +11,7 @@
 #include "mdp_core.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace mdp {
 
@@ -161,8 +162,8 @@ __device__ __forceinline__ float peer_grad(const PeerCtx& P, const float* g_loca
 }
 
 __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, float* __restrict__ p, float* __restrict__ tg,
-                                                     float* __restrict__ mm, float* __restrict__ vv, long long len, int t,
-                                                     float grad_scale, float clip, double lr, double beta1, double beta2,
+                                                     float* __restrict__ mm, float* __restrict__ vv, long long len,
+                                                     const int* __restrict__ t_ptr, float grad_scale, float clip, double lr, double beta1, double beta2,
                                                      float eps, float polyak, int do_polyak, const PeerCtx& P, long long goff,
                                                      int slot) {
   __shared__ float red[32];
@@ -171,6 +172,22 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
   unsigned epoch = 0;
   const bool small = len <= (long long)OPT_PF * nt;  // every peer read of this variable fits the register prefetch
   const bool ll = P.world > 1 && P.recv != nullptr;
+  // operands the gradient kernel before this launch does not write (Adam slots, running and target parameters): loaded BEFORE
+  // the dependency wait, so that under a programmatic dependent launch they are in flight while that kernel still runs
+  float gr[OPT_PF], mr[OPT_PF], vr[OPT_PF], pr[OPT_PF], tr[OPT_PF];
+#pragma unroll
+  for (int k = 0; k < OPT_PF; ++k) {
+    const long long i = tid + (long long)k * nt;
+    const bool ok = i < len;
+    mr[k] = ok ? mm[i] : 0.f;
+    vr[k] = ok ? vv[i] : 0.f;
+    pr[k] = ok ? p[i] : 0.f;
+    tr[k] = (ok && do_polyak) ? tg[i] : 0.f;
+  }
+  pdl_wait();  // gradients (and the step counter) of the preceding launch are complete from here on
+  pdl_launch_dependents();  // a dependent launch (the actor step after the critic's optimizer) may stage its own inputs now: every
+                            // kernel before this one has completed
+  const int t = *t_ptr;
   if (P.world > 1) {
     // one slot (flag words + epoch counter) per (agent, net, variable): the actor and critic steps of an agent never share
     // epochs, so a critic-only or reordered step sequence cannot alias another net's exchange (all ranks must still issue the
@@ -186,16 +203,10 @@ __device__ __forceinline__ void clip_adam_polyak_var(float* __restrict__ g, floa
   }
   if (tid == nt - 32)  // last warp, lane 0: overlaps with the loads / reduction of the other warps
     s_lr_t = (float)(lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t)));
-  float gr[OPT_PF], mr[OPT_PF], vr[OPT_PF], pr[OPT_PF], tr[OPT_PF];
 #pragma unroll
   for (int k = 0; k < OPT_PF; ++k) {
     const long long i = tid + (long long)k * nt;
-    const bool ok = i < len;
-    gr[k] = !ok ? 0.f : ll ? g[i] : peer_grad(P, g, goff, i);
-    mr[k] = ok ? mm[i] : 0.f;
-    vr[k] = ok ? vv[i] : 0.f;
-    pr[k] = ok ? p[i] : 0.f;
-    tr[k] = (ok && do_polyak) ? tg[i] : 0.f;
+    gr[k] = !(i < len) ? 0.f : ll ? g[i] : peer_grad(P, g, goff, i);
   }
   if (ll) ll_sum_pf(P, goff, tid, nt, len, gr, epoch);
   // pass 1: ||scale * g||_2
@@ -273,7 +284,7 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak(float* __restrict__ p
                                                            long long goff_net, int slot0, int var0) {
   const int var = blockIdx.x + var0;
   const long long off = seg.off[var], len = seg.len[var];
-  clip_adam_polyak_var(grad + off, param + off, target + off, m + off, v + off, len, *t_ptr, grad_scale, clip, lr, beta1, beta2,
+  clip_adam_polyak_var(grad + off, param + off, target + off, m + off, v + off, len, t_ptr, grad_scale, clip, lr, beta1, beta2,
                        eps, polyak, do_polyak, P, goff_net + off, slot0 + var);
 }
 
@@ -411,12 +422,25 @@ __global__ void __launch_bounds__(1024) k_clip_adam_polyak_all(const AgentDev* _
   float* g = ag.grad[which].W1 + off;
   const long long goff = g - grads_base;
   clip_adam_polyak_var(g, const_cast<float*>(w.W1) + off, const_cast<float*>(wt.W1) + off, m_base + goff, v_base + goff, len,
-                       adam_t[2 * j + which], grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak, P, goff, 12 * j + 6 * which + var);
+                       adam_t + 2 * j + which, grad_scale, clip, lr, beta1, beta2, eps, polyak, do_polyak, P, goff, 12 * j + 6 * which + var);
 }
 
 }  // namespace mdp
 
 using namespace mdp;
+
+// Launch configuration of the optimizer kernels.  pdl: programmatic dependent launch on the preceding kernel of the stream (the
+// gradient kernel): this launch's CTAs become resident and prefetch their Adam slots / parameters while it still runs, and
+// block in pdl_wait() until its gradients are complete.  MDP_PDL=0 in the environment keeps plain stream order.
+static void pdl_config(cudaLaunchConfig_t* lc, cudaLaunchAttribute* at, dim3 grid, int block, cudaStream_t st, bool pdl) {
+  static const bool enabled = []() { const char* e = getenv("MDP_PDL"); return !(e && e[0] == '0'); }();
+  memset(lc, 0, sizeof(*lc));
+  lc->gridDim = grid; lc->blockDim = dim3(block); lc->dynamicSmemBytes = 0; lc->stream = st;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc->attrs = at;
+  lc->numAttrs = (pdl && enabled) ? 1 : 0;
+}
 
 static PeerCtx peer_ctx(const mdp_core* c) {
   PeerCtx P;
@@ -491,20 +515,28 @@ static int wide_w1_step(mdp_core* c, int which, int a0, int count, float grad_sc
   return MDP_OK;
 }
 
-extern "C" int mdp_clip_adam_polyak_all(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream) {
+// pdl: the caller guarantees that the preceding launch on `stream` is the gradient kernel of the same net(s) (mdp_update_agent /
+// mdp_update_all), which writes none of the Adam slots / parameters this kernel prefetches before its dependency wait
+int mdp::clip_adam_polyak_all_impl(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream, bool pdl) {
   MDP_REQUIRE(c && c->d_agents, "mdp_clip_adam_polyak_all: core not bound");
   MDP_REQUIRE(which == 0 || which == 1, "mdp_clip_adam_polyak_all: bad argument");
   int wide = 0;
   int rc = wide_w1_step(c, which, 0, c->cfg.n_agents, grad_scale, do_polyak, (cudaStream_t)stream, &wide);
   if (rc) return rc;
-  k_clip_adam_polyak_all<<<dim3(6 - wide, c->cfg.n_agents), 1024, 0, (cudaStream_t)stream>>>(
-      c->d_agents, which, c->cfg.num_units, c->grads, c->adam_m, c->adam_v, c->adam_t, grad_scale, (float)c->cfg.grad_clip,
-      c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, do_polyak, peer_ctx(c), 0, wide);
+  cudaLaunchConfig_t lc;
+  cudaLaunchAttribute at[1];
+  pdl_config(&lc, at, dim3(6 - wide, c->cfg.n_agents), 1024, (cudaStream_t)stream, pdl && wide == 0);
+  MDP_CUDA(cudaLaunchKernelEx(&lc, k_clip_adam_polyak_all, (const AgentDev*)c->d_agents, (int)which, (int)c->cfg.num_units, c->grads,
+                              c->adam_m, c->adam_v, (const int*)c->adam_t, grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
+                              c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak, (int)do_polyak, peer_ctx(c), 0, wide));
   return check_launch("k_clip_adam_polyak_all");
 }
+extern "C" int mdp_clip_adam_polyak_all(mdp_core* c, int32_t which, float grad_scale, int32_t do_polyak, void* stream) {
+  return mdp::clip_adam_polyak_all_impl(c, which, grad_scale, do_polyak, stream, false);
+}
 
-extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak,
-                                    void* stream) {
+int mdp::clip_adam_polyak_impl(mdp_core* c, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak, void* stream,
+                               bool pdl) {
   MDP_REQUIRE(c && c->d_agents, "mdp_clip_adam_polyak: core not bound");
   MDP_REQUIRE(agent >= 0 && agent < c->cfg.n_agents && (which == 0 || which == 1), "mdp_clip_adam_polyak: bad argument");
   const int U = c->cfg.num_units;
@@ -527,10 +559,16 @@ extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, f
   int wide = 0;
   int rc = wide_w1_step(c, which, agent, 1, grad_scale, do_polyak, (cudaStream_t)stream, &wide);
   if (rc) return rc;
-  k_clip_adam_polyak<<<6 - wide, 1024, 0, (cudaStream_t)stream>>>(param, target, grad, m, v, seg, c->adam_t + 2 * agent + which,
-                                                                  grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1,
-                                                                  c->cfg.beta2, (float)c->cfg.adam_eps, (float)c->cfg.polyak,
-                                                                  do_polyak, peer_ctx(c), c->lay.train_off[agent][which], 12 * agent + 6 * which,
-                                                                  wide);
+  cudaLaunchConfig_t lc;
+  cudaLaunchAttribute at[1];
+  pdl_config(&lc, at, dim3(6 - wide), 1024, (cudaStream_t)stream, pdl && wide == 0);
+  MDP_CUDA(cudaLaunchKernelEx(&lc, k_clip_adam_polyak, param, target, grad, m, v, seg, (const int*)(c->adam_t + 2 * agent + which),
+                              grad_scale, (float)c->cfg.grad_clip, c->cfg.lr, c->cfg.beta1, c->cfg.beta2, (float)c->cfg.adam_eps,
+                              (float)c->cfg.polyak, (int)do_polyak, peer_ctx(c), (long long)c->lay.train_off[agent][which],
+                              12 * agent + 6 * which, wide));
   return check_launch("k_clip_adam_polyak");
+}
+extern "C" int mdp_clip_adam_polyak(mdp_core* c, int32_t agent, int32_t which, float grad_scale, int32_t do_polyak,
+                                    void* stream) {
+  return mdp::clip_adam_polyak_impl(c, agent, which, grad_scale, do_polyak, stream, false);
 }

@@ -18,6 +18,8 @@
 // see DESIGN.md for the tensor-core plan.
 #include "mdp_mlp.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <new>
 
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
                                                       const long long* __restrict__ ridx, const float* __restrict__ u_target,
                                                       int u_stride, uint64_t seed, uint64_t counter, float* __restrict__ y_out,
                                                       float* __restrict__ target_act_out, int XPf, long long idx_stride, long long y_stride) {
+  pdl_launch_dependents();  // the optimizer launch that follows may become resident and prefetch its operands now
   const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
   if (ridx) ridx += blockIdx.y * idx_stride;
   y_out += blockIdx.y * y_stride;
@@ -582,6 +585,7 @@ template <int U, int TM>
 __global__ void __launch_bounds__(NT) k_critic_grads_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                          const long long* __restrict__ ridx, const float* __restrict__ y,
                                                          float* __restrict__ q_out, int XPf, long long idx_stride, long long y_stride) {
+  pdl_launch_dependents();  // the optimizer launch that follows may become resident and prefetch its operands now
   const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
   if (ridx) ridx += blockIdx.y * idx_stride;
   y += blockIdx.y * y_stride;
@@ -621,6 +625,7 @@ template <int U, int TM>
 __global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j0, mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                         const long long* __restrict__ ridx, const float* __restrict__ u_actor,
                                                         int u_stride, uint64_t seed, uint64_t counter, int XPf, long long idx_stride, long long y_stride) {
+  pdl_launch_dependents();  // the optimizer launch that follows may become resident and prefetch its operands now
   const int j = j0 + blockIdx.y;  // grouped launch: one agent per grid.y slice
   if (ridx) ridx += blockIdx.y * idx_stride;
   if (C.ctl) counter += C.ctl[0];
@@ -654,10 +659,13 @@ __global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j0, mdp_r
   const uint32_t nq = net_floats_padded(gq.in, U, 1), np_ = net_floats_padded(gp.in, U, gp.out);
   if (threadIdx.x == 0) {
     mbar_arrive_expect_tx(&bar, (uint32_t)nrows * x4 * 4u + (nq + np_) * 4u);
-    bulk_g2s(sNets, gq.W1, nq * 4u, &bar);
     bulk_g2s(sNets + nq, gp.W1, np_ * 4u, &bar);
   }
   bulk_rows<TM>(G, sXf, XPf, batch, L.row_stride, ridx, row0, nrows, 0, x4, &bar);
+  // Under a programmatic dependent launch the kernel before this one is the critic's optimizer step: the actor net and the
+  // sampled rows above do not depend on it, the critic's weights do.
+  pdl_wait();
+  if (threadIdx.x == 0) bulk_g2s(sNets, gq.W1, nq * 4u, &bar);
   const MlpW qw = net_at<U>(sNets, gq.in, 1);
   const MlpW pw = net_at<U>(sNets + nq, gp.in, gp.out);
   mbar_wait(&bar, 0);
@@ -1221,7 +1229,7 @@ extern "C" int mdp_critic_grads(mdp_core* c, int32_t agent, const mdp_ring_layou
 
 static int launch_actor_grads(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
                               const int64_t* idx, long long idx_stride, const float* u_actor, int32_t u_stride, uint64_t seed,
-                              uint64_t counter, void* stream) {
+                              uint64_t counter, void* stream, bool pdl = false) {
   MDP_REQUIRE(c && c->d_agents, "mdp_actor_grads: core not bound");
   int rc = check_lay(c, lay);
   if (rc) return rc;
@@ -1242,8 +1250,19 @@ static int launch_actor_grads(mdp_core* c, int32_t agent, int32_t count, const m
       auto kern = k_actor_grads_res<U, TMv>;
       int rc2 = set_smem(kern, rp.actor);
       if (rc2) return rc2;
-      kern<<<dim3(cdiv(B, TMv), count), NT, rp.actor, st>>>(d, agent, *lay, B, batch, ridx, u_actor, u_stride, seed, counter, rp.XPf,
-                                                            idx_stride, 0);
+      // pdl (mdp_update_agent / mdp_update_all): programmatic dependent launch on the critic's optimizer kernel -- the sampled
+      // rows (complete since the index draw) and the actor net stream into shared memory while that kernel still runs
+      static const bool pdl_enabled = []() { const char* e = getenv("MDP_PDL"); return !(e && e[0] == '0'); }();
+      cudaLaunchConfig_t lc;
+      cudaLaunchAttribute at[1];
+      memset(&lc, 0, sizeof(lc));
+      lc.gridDim = dim3(cdiv(B, TMv), count); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = rp.actor; lc.stream = st;
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.attrs = at;
+      lc.numAttrs = (pdl && pdl_enabled) ? 1 : 0;
+      MDP_CUDA(cudaLaunchKernelEx(&lc, kern, d, (int)agent, *lay, (int)B, batch, ridx, u_actor, (int)u_stride, (unsigned long)seed,
+                                  (unsigned long)counter, (int)rp.XPf, (long long)idx_stride, (long long)0));
       return check_launch("k_actor_grads_res");
     }
     auto kern = k_actor_grads<U, TMv, RES>;
@@ -1273,11 +1292,11 @@ extern "C" int mdp_update_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B
   const int n = c->cfg.n_agents;
   int rc = launch_td_critic(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, y_scratch, B, stream);
   if (rc) return rc;
-  rc = mdp_clip_adam_polyak_all(c, 1, grad_scale, 1, stream);
+  rc = clip_adam_polyak_all_impl(c, 1, grad_scale, 1, stream, true);
   if (rc) return rc;
-  rc = launch_actor_grads(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, stream);
+  rc = launch_actor_grads(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, stream, true);
   if (rc) return rc;
-  return mdp_clip_adam_polyak_all(c, 0, grad_scale, 1, stream);
+  return clip_adam_polyak_all_impl(c, 0, grad_scale, 1, stream, true);
 }
 
 extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
@@ -1286,9 +1305,9 @@ extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layou
   int rc = launch_td_critic(c, agent, 1, lay, B, batch, idx, 0, u_target, u_stride, seed, counter, y_scratch, 0, stream);
   if (rc) return rc;
   const float scale = c->peer_world > 1 ? 1.0f / (float)c->peer_world : 1.0f;  // fused peer all-reduce (mdp_core_bind_peers)
-  rc = mdp_clip_adam_polyak(c, agent, 1, scale, 1, stream);
+  rc = clip_adam_polyak_impl(c, agent, 1, scale, 1, stream, true);
   if (rc) return rc;
-  rc = mdp_actor_grads(c, agent, lay, B, batch, idx, u_actor, u_stride, seed, counter, stream);
+  rc = launch_actor_grads(c, agent, 1, lay, B, batch, idx, 0, u_actor, u_stride, seed, counter, stream, true);
   if (rc) return rc;
-  return mdp_clip_adam_polyak(c, agent, 0, scale, 1, stream);
+  return clip_adam_polyak_impl(c, agent, 0, scale, 1, stream, true);
 }
