@@ -253,6 +253,15 @@ int mdp_clip_adam_polyak(mdp_core* core, int32_t agent, int32_t which, float gra
 int mdp_core_bind_peers(mdp_core* core, int32_t world, int32_t rank, const void* const* h_peer_grads, void* const* h_peer_flags,
                         uint32_t* epoch_local, void* const* h_peer_recv);
 
+/* The index draw of an update (ReplayBuffer.make_index, replay_buffer.py:46-47, on the device: the Philox stream of
+ * mdp_replay_make_index, counter [+ ctl[0]], length <= 0 reads the control block's ring length) fused with the reset of the
+ * statistics accumulators of agents [agent, agent + count): B_total = B draws per agent x count agents into idx_out.  When the
+ * NEXT call on the core is mdp_update_agent(agent) (count = 1) or mdp_update_all (agent = 0, count = n_agents) on the same
+ * stream, that call skips its own reset and its TD-target kernel starts as a programmatic dependent launch: its nets stream
+ * into shared memory while the draw runs. */
+int mdp_update_prepare(mdp_core* core, int32_t agent, int32_t count, int64_t* idx_out, int32_t B_total, int64_t length,
+                       uint64_t seed, uint64_t counter, void* stream);
+
 /* MADDPGAgentTrainer.update body for agent j on one stream (maddpg.py:181-194), single GPU:
  * td_target -> critic_grads -> clip_adam(Q) -> actor_grads -> clip_adam(P) + polyak(P) + polyak(Q). */
 int mdp_update_agent(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,

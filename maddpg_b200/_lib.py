@@ -92,6 +92,7 @@ SYMBOLS = {
     "mdp_clip_adam_polyak": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),
     "mdp_update_agent": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, _P, C.c_int32,
                                    C.c_uint64, C.c_uint64, _P, _P]),
+    "mdp_update_prepare": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64, _P]),
     "mdp_update_all": (C.c_int, [_P, C.POINTER(RingLayout), C.c_int32, _P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P,
                                  C.c_float, _P]),
     "mdp_clip_adam_polyak_all": (C.c_int, [_P, C.c_int32, C.c_float, C.c_int32, _P]),

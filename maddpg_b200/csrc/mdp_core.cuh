@@ -55,6 +55,7 @@ struct mdp_core {
   uint2* const* d_peer_recv = nullptr;         // device array [world] of low-latency receive buffers (or null: barrier mode)
   void* d_peer_tables = nullptr;
   int no_fuse = 0;                 // 1: keep TD target and critic step as two launches (mdp_core_set_fused_update)
+  int prep_agent = -1, prep_count = 0;  // mdp_update_prepare zeroed these agents' statistics in the launch right before (mdp_train.cu)
   int tc_mode = 0;                 // tensor-core (tcgen05) kernels: 0 auto, 1 always where supported, -1 never
   float* tc_scratch = nullptr;     // sampled-action tiles of the tensor-core TD-target kernel when they exceed shared memory
   size_t tc_scratch_bytes = 0;

@@ -517,6 +517,9 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
     }
     bulk_g2s(q, me.net[MDP_NET_TARGET_Q].W1, net_floats_padded(me.net[MDP_NET_TARGET_Q].in, U, 1) * 4u, &bar);
   }
+  // Under a programmatic dependent launch the kernel before this one is mdp_update_prepare (index draw + statistics reset): the
+  // nets above do not depend on it (every earlier kernel has completed), the sampled rows and the statistics do.
+  pdl_wait();
   if (grp == 0) bulk_rows<TM>(G, sXf, XPf, batch, R, ridx, row0, nrows, L.nx_off, nx4, &bar);
   if (FUSE && grp == NG - 1) bulk_rows<TM>(G, sXc, XPf, batch, R, ridx, row0, nrows, 0, x4, &bar);
   for (int i = threadIdx.x; i < 2 * TM; i += blockDim.x) {
@@ -748,6 +751,22 @@ __global__ void __launch_bounds__(NT) k_actor_grads_res(CoreDev C, int j0, mdp_r
   backward_hidden_res<U, TM>(G, sXf + me.obs_off, XPf, pw, sWTp, &pg, sP1, sP2);
 }
 
+// mdp_update_prepare: the index draw of an agent update (the same Philox stream as k_replay_make_index) and the reset of the
+// agents' statistics accumulators in ONE launch, so that the TD-target kernel directly follows a kernel and can start as a
+// programmatic dependent launch (a memset node in between would serialise the two).
+__global__ void k_update_prepare(long long* __restrict__ idx_out, int B, long long length, uint64_t seed, uint64_t counter,
+                                 const unsigned long long* __restrict__ ctl, double* __restrict__ stats, int n_stats) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_stats) stats[b] = 0.0;
+  if (b >= B) return;
+  if (ctl) counter += ctl[0];
+  if (length <= 0) length = (long long)ctl[3];
+  uint4 r = Philox::gen(seed, (uint32_t)b, 0x1D3Au, (uint32_t)counter, (uint32_t)(counter >> 32));
+  long long i = (long long)(Philox::u01d(r.x, r.y) * (double)length);
+  i = i < length ? i : length - 1;
+  idx_out[b] = i > 0 ? i : 0;
+}
+
 }  // namespace mdp
 
 // =============================================================================================
@@ -792,7 +811,17 @@ CoreDev core_dev_for_rollout(const mdp_core* c) { return core_dev(c); }
 
 template <typename Kern>
 static int set_smem(Kern kern, size_t smem) {
-  if (smem > 48 * 1024) MDP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      cudaFuncAttributes fa;
+      memset(&fa, 0, sizeof(fa));
+      cudaError_t e2 = cudaFuncGetAttributes(&fa, kern);
+      cudaGetLastError();
+      return fail(MDP_ECUDA, "cudaFuncSetAttribute(max dynamic shared memory = %zu): %s (kernel: %zu B static shared, %d registers, "
+                  "attributes query: %s)", smem, cudaGetErrorString(e), fa.sharedSizeBytes, fa.numRegs, cudaGetErrorString(e2));
+    }
+  }
   return MDP_OK;
 }
 
@@ -1043,6 +1072,7 @@ struct ResPlan {
 
 static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   ResPlan r;
+  memset(&r, 0, sizeof(r));  // the early return below must leave fuse_ok false too (it was read uninitialised for local critics)
   r.ok = false;
   const int U = c->cfg.num_units, n = c->cfg.n_agents, TMv = p.TM, HP = U + 4;
   for (int i = 0; i < n; ++i)
@@ -1099,6 +1129,30 @@ static bool want_tc(const mdp_core* c, int B, int count, bool backward = false) 
   return cdiv(B, 128) * count >= 96 || max_in >= 1024;
 }
 
+// mdp_update_prepare ran as the launch right before for exactly these agents: their statistics are already zero and the
+// TD-target kernel may start as its programmatic dependent.  Consumes the mark.
+static bool take_prepared(mdp_core* c, int32_t agent, int32_t count) {
+  const bool ok = c->prep_agent == agent && c->prep_count == count;
+  c->prep_agent = -1;
+  c->prep_count = 0;
+  return ok;
+}
+
+template <typename Kern, typename... Args>
+static int launch_maybe_pdl(const char* what, bool pdl, Kern kern, dim3 grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool pdl_enabled = []() { const char* e = getenv("MDP_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t lc;
+  cudaLaunchAttribute at[1];
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = grid; lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = st;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  lc.attrs = at;
+  lc.numAttrs = (pdl && pdl_enabled) ? 1 : 0;
+  MDP_CUDA(cudaLaunchKernelEx(&lc, kern, args...));
+  return check_launch(what);
+}
+
 static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B, const float* batch,
                             const int64_t* idx, long long idx_stride, const float* u_target, int32_t u_stride, uint64_t seed,
                             uint64_t counter, float* y_out, long long y_stride, float* target_act_out, void* stream) {
@@ -1107,7 +1161,8 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
   if (rc) return rc;
   MDP_REQUIRE(batch && y_out && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_td_target: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
+  const bool prepared = take_prepared(c, agent, count);
+  if (!prepared) MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
   CoreDev d = core_dev(c);
   const Plan p = make_plan(c, B);
   const ResPlan rp = make_res_plan(c, p, agent);
@@ -1124,9 +1179,9 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
       auto kern = k_td_target_res<U, TMv, false>;
       int rc2 = set_smem(kern, rp.td);
       if (rc2) return rc2;
-      kern<<<dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td, st>>>(d, agent, *lay, B, batch, ridx, u_target, u_stride, seed,
-                                                                        counter, y_out, target_act_out, rp.XPf, idx_stride, y_stride);
-      return check_launch("k_td_target_res");
+      return launch_maybe_pdl("k_td_target_res", prepared, kern, dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td, st, d, (int)agent, *lay,
+                              (int)B, batch, ridx, u_target, (int)u_stride, (unsigned long)seed, (unsigned long)counter, y_out,
+                              target_act_out, (int)rp.XPf, (long long)idx_stride, (long long)y_stride);
     }
     auto kern = k_td_target<U, TMv, RES>;
     const size_t smem = smem_for(U, p, 1, 0, 2, TMv * KPAD + TMv + TMv * (c->act_stride | 1));
@@ -1155,17 +1210,17 @@ static int launch_td_critic(mdp_core* c, int32_t agent, int32_t count, const mdp
   const ResPlan rp = make_res_plan(c, p, agent);
   if (rp.fuse_ok && !c->no_fuse && !want_tc(c, B, count) && !want_tc(c, B, count, true)) {
     cudaStream_t st = (cudaStream_t)stream;
-    MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
+    const bool prepared = take_prepared(c, agent, count);
+    if (!prepared) MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
     CoreDev d = core_dev(c);
     return dispatch(c->cfg.num_units, p, [&](auto u_, auto tm_, auto) -> int {
       constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
       auto kern = k_td_target_res<U, TMv, true>;
       int rc2 = set_smem(kern, rp.td_fused);
       if (rc2) return rc2;
-      kern<<<dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td_fused, st>>>(d, agent, *lay, B, batch, (const long long*)idx, u_target,
-                                                                              u_stride, seed, counter, y_scratch, nullptr, rp.XPf,
-                                                                              idx_stride, y_stride);
-      return check_launch("k_td_target_res<fused critic>");
+      return launch_maybe_pdl("k_td_target_res<fused critic>", prepared, kern, dim3(cdiv(B, TMv), count), rp.td_groups * NT, rp.td_fused,
+                              st, d, (int)agent, *lay, (int)B, batch, (const long long*)idx, u_target, (int)u_stride, (unsigned long)seed,
+                              (unsigned long)counter, y_scratch, (float*)nullptr, (int)rp.XPf, (long long)idx_stride, (long long)y_stride);
     });
   }
   rc = launch_td_target(c, agent, count, lay, B, batch, idx, idx_stride, u_target, u_stride, seed, counter, y_scratch, y_stride, nullptr,
@@ -1297,6 +1352,22 @@ extern "C" int mdp_update_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B
   rc = launch_actor_grads(c, 0, n, lay, B, batch, idx, idx_agent_stride, nullptr, 0, seed, counter, stream, true);
   if (rc) return rc;
   return clip_adam_polyak_all_impl(c, 0, grad_scale, 1, stream, true);
+}
+
+extern "C" int mdp_update_prepare(mdp_core* c, int32_t agent, int32_t count, int64_t* idx_out, int32_t B_total, int64_t length,
+                                  uint64_t seed, uint64_t counter, void* stream) {
+  MDP_REQUIRE(c && c->d_agents && idx_out && B_total > 0, "mdp_update_prepare: bad argument");
+  MDP_REQUIRE(agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_update_prepare: agents [%d, %d) out of range", agent,
+              agent + count);
+  MDP_REQUIRE(length > 0 || c->ctl, "mdp_update_prepare: length <= 0 needs a control block (mdp_core_set_ctl)");
+  const int n = std::max(B_total, 8 * count);
+  k_update_prepare<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((long long*)idx_out, B_total, length, seed, counter, c->ctl,
+                                                                  c->stats + 8 * agent, 8 * count);
+  int rc = check_launch("k_update_prepare");
+  if (rc) return rc;
+  c->prep_agent = agent;
+  c->prep_count = count;
+  return MDP_OK;
 }
 
 extern "C" int mdp_update_agent(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,

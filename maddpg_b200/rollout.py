@@ -351,20 +351,21 @@ class GraphedUpdateRound(object):
         c = 0
         if self.grouped:
             flat = self.idx_all.view(-1)
+            # index draw + statistics reset in one launch; the update's first kernel is its programmatic dependent
             if relative:
-                core.make_index(flat, length=0, counter=1, ctl=self.ctl.t)
+                core.make_index(flat, length=0, counter=1, for_update=(0, core.n))
                 core.update_all(core.ring.ring, idx=self.idx_all, counter=2)
                 self.ctl.advance(2, 0, 0)
             else:
-                core.make_index(flat)
+                core.make_index(flat, for_update=(0, core.n))
                 core.update_all(core.ring.ring, idx=self.idx_all)
             return 2
         for j in range(core.n):
             c += 1
             if relative:
-                core.make_index(self.idx[j], length=0, counter=c, ctl=self.ctl.t)
+                core.make_index(self.idx[j], length=0, counter=c, for_update=(j, 1))
             else:
-                core.make_index(self.idx[j])
+                core.make_index(self.idx[j], for_update=(j, 1))
             c += 1
             core.update_agent(j, core.ring.ring, counter=c if relative else None, idx=self.idx[j])  # fused gather
         if relative:

@@ -282,8 +282,18 @@ class MADDPGCore(object):
                                            _lib.ptr(self._y[key]), float(grad_scale), _lib.current_stream()),
                    "mdp_update_all")
 
-    def make_index(self, idx_out, length=None, counter=None, ctl=None):
-        """Device-side ``ReplayBuffer.make_index`` (replay_buffer.py:46-47): B uniform draws in [0, len)."""
+    def make_index(self, idx_out, length=None, counter=None, ctl=None, for_update=None):
+        """Device-side ``ReplayBuffer.make_index`` (replay_buffer.py:46-47): B uniform draws in [0, len).
+        ``for_update=(agent, count)``: the draw of the update of these agents that is launched NEXT -- one kernel also resets
+        their statistics accumulators and the update's first kernel starts as its programmatic dependent (mdp_update_prepare);
+        ``ctl`` must then be the control block attached to the core (or None)."""
+        if for_update is not None:
+            agent, count = for_update
+            _lib.check(_lib.lib.mdp_update_prepare(self._h, agent, count, _lib.ptr(idx_out), idx_out.shape[0],
+                                                   int(self.ring.length[0] if length is None else length), self.seed,
+                                                   self.next_counter() if counter is None else counter,
+                                                   _lib.current_stream()), "mdp_update_prepare")
+            return
         _lib.check(_lib.lib.mdp_replay_make_index(_lib.ptr(idx_out), idx_out.shape[0],
                                                   int(self.ring.length[0] if length is None else length), self.seed,
                                                   self.next_counter() if counter is None else counter, _lib.ptr(ctl),
@@ -493,7 +503,7 @@ class MADDPGAgentTrainer(AgentTrainer):
             # stream (bit-identical index lists for a seeded `random`); an explicit ``index`` is always honoured.
             if self._idx_dev is None or self._idx_dev.shape[0] != B:
                 self._idx_dev = torch.zeros(B, dtype=torch.int64, device=core.device)
-            core.make_index(self._idx_dev)
+            core.make_index(self._idx_dev, for_update=(self.agent_index, 1))
             self.replay_sample_index = idx = self._idx_dev
         else:
             self.replay_sample_index = self.replay_buffer.make_index(B) if index is None else index
