@@ -758,13 +758,19 @@ __global__ void k_update_prepare(long long* __restrict__ idx_out, int B, long lo
                                  const unsigned long long* __restrict__ ctl, double* __restrict__ stats, int n_stats) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < n_stats) stats[b] = 0.0;
-  if (b >= B) return;
-  if (ctl) counter += ctl[0];
-  if (length <= 0) length = (long long)ctl[3];
-  uint4 r = Philox::gen(seed, (uint32_t)b, 0x1D3Au, (uint32_t)counter, (uint32_t)(counter >> 32));
-  long long i = (long long)(Philox::u01d(r.x, r.y) * (double)length);
-  i = i < length ? i : length - 1;
-  idx_out[b] = i > 0 ? i : 0;
+  if (b < B) {
+    if (ctl) counter += ctl[0];
+    if (length <= 0) length = (long long)ctl[3];
+    uint4 r = Philox::gen(seed, (uint32_t)b, 0x1D3Au, (uint32_t)counter, (uint32_t)(counter >> 32));
+    long long i = (long long)(Philox::u01d(r.x, r.y) * (double)length);
+    i = i < length ? i : length - 1;
+    idx_out[b] = i > 0 ? i : 0;
+  }
+  // Launched as a programmatic dependent itself: nothing above reads what the kernel before it (the previous agent's optimizer
+  // step) writes, so the draw runs under that kernel.  The TD-target kernel behind this one may only start staging its nets
+  // once that optimizer step HAS completed: wait first, then release the dependents.
+  pdl_wait();
+  pdl_launch_dependents();
 }
 
 }  // namespace mdp
@@ -1361,9 +1367,14 @@ extern "C" int mdp_update_prepare(mdp_core* c, int32_t agent, int32_t count, int
               agent + count);
   MDP_REQUIRE(length > 0 || c->ctl, "mdp_update_prepare: length <= 0 needs a control block (mdp_core_set_ctl)");
   const int n = std::max(B_total, 8 * count);
-  k_update_prepare<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((long long*)idx_out, B_total, length, seed, counter, c->ctl,
-                                                                  c->stats + 8 * agent, 8 * count);
-  int rc = check_launch("k_update_prepare");
+  // The draw reads the control block before its dependency wait: fine inside a captured graph (the block only moves at the end
+  // of a round, and graph launches are fully ordered) or without a block; otherwise keep plain stream order.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  MDP_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
+  const bool early = !c->ctl || cap == cudaStreamCaptureStatusActive;
+  int rc = launch_maybe_pdl("k_update_prepare", early, k_update_prepare, dim3(cdiv(n, 256)), 256, 0, (cudaStream_t)stream, (long long*)idx_out,
+                            (int)B_total, (long long)length, (unsigned long)seed, (unsigned long)counter,
+                            (const unsigned long long*)c->ctl, c->stats + 8 * agent, (int)(8 * count));
   if (rc) return rc;
   c->prep_agent = agent;
   c->prep_count = count;
