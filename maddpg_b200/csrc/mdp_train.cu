@@ -413,13 +413,19 @@ __global__ void __launch_bounds__(NT) k_actor_grads(CoreDev C, int j0, mdp_ring_
 template <int U, int TM>
 __device__ __forceinline__ void critic_grads_body(const Grp& G, const CoreDev& C, int j, int B, const float* sXf, int XPf, const MlpW& w,
                                                   float* sWT, float* sH1, float* sH2, float* sQ, float* sDq,
-                                                  const float* __restrict__ ytile, float* __restrict__ q_out_tile, int nrows) {
+                                                  const float* __restrict__ ytile, float* __restrict__ q_out_tile, int nrows,
+                                                  int phase = 0) {
+  // phase 0: the whole step; 1: forward pass only (q of the tile in sQ, activations in sH1 / sH2, W2^T in sWT); 2: loss and
+  // backward pass from those -- the fused TD kernel runs phase 1 on an otherwise idle thread group next to the target critic
   constexpr int HP = U + 4;
   const MlpG& g = C.agents[j].grad[1];
   const int tid = G.tid;
-  build_wT_swz<U>(G, sWT, w.W2);  // published by the barriers inside forward_hidden_res
-  forward_hidden_res<U, TM>(G, sXf, XPf, w, sH1, sH2);
-  critic_head<U, TM>(G, sH2, w, sQ);
+  if (phase != 2) {
+    build_wT_swz<U>(G, sWT, w.W2);  // published by the barriers inside forward_hidden_res
+    forward_hidden_res<U, TM>(G, sXf, XPf, w, sH1, sH2);
+    critic_head<U, TM>(G, sH2, w, sQ);
+    if (phase == 1) return;
+  }
   if (tid < 32) {
     const int r = tid;
     float d = 0.f;
@@ -476,8 +482,10 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
   const Grp G{(int)threadIdx.x % NT, NG > 1 ? grp + 1 : 0};
   SmemCarve sm(smem_raw);
   float* sXf = sm.take(TM * XPf);  // [next_obs_all | a'_all]
-  float* sH1 = sm.take(NG * TM * HP) + grp * TM * HP;
-  float* sH2 = sm.take(NG * TM * HP) + grp * TM * HP;
+  float* sH1base = sm.take(NG * TM * HP);
+  float* sH2base = sm.take(NG * TM * HP);
+  float* sH1 = sH1base + grp * TM * HP;
+  float* sH2 = sH2base + grp * TM * HP;
   float* sL = sm.take(NG * TM * KPAD) + grp * TM * KPAD;
   float* sQ = sm.take(TM);
   float* sRD = sm.take(2 * TM);    // rew_j, done_j
@@ -486,6 +494,7 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
   const int x4 = (L.x_dim + 3) & ~3;
   float* sXc = FUSE ? sm.take(TM * XPf) : nullptr;  // [obs_all | act_all] of the same rows
   float* sY = FUSE ? sm.take(TM) : nullptr;
+  float* sQc = FUSE ? sm.take(TM) : nullptr;  // q of the running critic (its forward pass runs next to the target critic's)
   float* sDq = FUSE ? sm.take(32) : nullptr;
   float* sWT = FUSE ? sm.take(U * U) : nullptr;
   float* sNetQ = FUSE ? sm.take(net_floats_padded(gq.in, U, 1)) : nullptr;
@@ -551,6 +560,15 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
       target_act_out[(row0 + r) * u_stride + c] = sXf[r * XPf + L.obs_sum + c];
     }
   }
+  // FUSE with a second thread group: group 1 runs the running critic's forward pass on the replayed [obs | act] rows (it needs
+  // neither a' nor y) while group 0 runs the target critic; a 512-thread barrier hands the activations over.
+  const bool split = FUSE && NG > 1;
+  if (split && grp == 1) {
+    const MlpW wq = net_at<U>(sNetQ, gq.in, 1);
+    critic_grads_body<U, TM>(G, C, j, B, sXc, XPf, wq, sWT, sH1, sH2, sQc, sDq, nullptr, nullptr, nrows, 1);
+    asm volatile("bar.sync 8, 512;" ::: "memory");
+    return;
+  }
   if (grp != 0) return;
   forward_hidden_res<U, TM>(G, sXf, XPf, tq, sH1, sH2);
   critic_head<U, TM>(G, sH2, tq, sQ);
@@ -580,7 +598,12 @@ __global__ void __launch_bounds__(3 * NT) k_td_target_res(CoreDev C, int j0, mdp
   if (FUSE) {
     G.sync();  // y of the tile is in shared memory
     const MlpW wq = net_at<U>(sNetQ, gq.in, 1);
-    critic_grads_body<U, TM>(G, C, j, B, sXc, XPf, wq, sWT, sH1, sH2, sQ, sDq, sY, nullptr, nrows);
+    if (split) {
+      asm volatile("bar.sync 8, 512;" ::: "memory");  // group 1's forward pass is complete
+      critic_grads_body<U, TM>(G, C, j, B, sXc, XPf, wq, sWT, sH1base + TM * HP, sH2base + TM * HP, sQc, sDq, sY, nullptr, nrows, 2);
+    } else {
+      critic_grads_body<U, TM>(G, C, j, B, sXc, XPf, wq, sWT, sH1, sH2, sQ, sDq, sY, nullptr, nrows);
+    }
   }
 }
 
@@ -1098,7 +1121,7 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   r.td = (tile + r.td_groups * (2 * r4((size_t)TMv * HP) + r4(TMv * KPAD)) + r4(TMv) + r4(2 * TMv) + actors + crit + 64) * 4;
   r.critic = (tile + 2 * r4((size_t)TMv * HP) + r4(TMv) + 32 + (size_t)U * U + crit + 64) * 4;
   r.actor = (tile + 4 * r4((size_t)TMv * HP) + 2 * r4(TMv * KPAD) + r4(TMv) + 2 * (size_t)U * U + crit + act_j + 64) * 4;
-  r.td_fused = r.td + (tile + r4(TMv) + 32 + (size_t)U * U + crit) * 4;  // k_td_target_res<FUSE>: + critic tile, y, dq, W2^T, q net
+  r.td_fused = r.td + (tile + 2 * r4(TMv) + 32 + (size_t)U * U + crit) * 4;  // k_td_target_res<FUSE>: + critic tile, y, q, dq, W2^T, q net
   const size_t limit = 200 * 1024;
   r.ok = r.td <= limit && r.critic <= limit && r.actor <= limit;
   r.fuse_ok = r.ok && r.td_fused <= limit;
