@@ -25,7 +25,9 @@ def _build(scenario, E, capacity):
     ("simple_spread", 300, 1, False, False), ("simple_spread", 300, 1, True, False), ("simple_spread", 300, 4, False, False),
     ("simple_spread", 300, 4, True, False), ("simple_spread", 300, 1, False, True), ("simple_spread", 300, 4, True, True),
     ("simple_spread", 2048, None, True, True),
-    ("simple_tag", 64, 2, True, True), ("simple_world_comm", 33, 3, True, False), ("simple", 1, 1, True, True)])
+    ("simple_tag", 64, 2, True, True), ("simple_world_comm", 33, 3, True, False), ("simple", 1, 1, True, True),
+    ("simple_speaker_listener", 66, 2, True, True), ("simple_reference", 39, 3, True, False), ("simple_crypto", 33, 1, False, True),
+    ("simple_push", 96, 4, True, True), ("simple_adversary", 50, 2, False, False)])
 def test_host_step_equals_device_api(scenario, E, chunks, graph, copy_kernels):
     """chunks > 1: the pipelined call (ranges of env instances on separate streams); graph: the call replayed as a CUDA
     graph with device-side counters; copy_kernels: host buffers moved by copy kernels instead of the copy engines.
