@@ -4,6 +4,8 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -90,3 +92,30 @@ def test_unsupported_action_space_raises_like_make_pdtype():
     assert act_heads(Discrete(5)) == [5] and act_heads(MultiDiscrete([[0, 4], [0, 3]])) == [5, 4]
     with pytest.raises(NotImplementedError):  # distributions.py:422
         act_heads(Box(-1, 1, (2,)))
+
+
+@pytest.mark.parametrize("scenario", ["simple", "simple_spread", "simple_tag", "simple_world_comm", "simple_adversary", "simple_push",
+                                      "simple_speaker_listener", "simple_crypto", "simple_reference"])
+def test_scenario_tables_match_oracle_shapes(scenario):
+    """mdp_env_create builds the entity / observation-column / action-head tables without a GPU: observation widths, action
+    heads, communication rows, goal rows and immovable agents agree with the oracle's MultiAgentEnv for all nine scenarios."""
+    from maddpg_b200.env import _dims_for
+    from oracle import mpe
+    from oracle.maddpg import act_heads
+    oenv = mpe.make_env(scenario, np.random.RandomState(0))
+    h, d = _dims_for(scenario)
+    A = d.n_agents
+    assert A == oenv.n and d.n_landmarks == len(oenv.world.landmarks)
+    assert list(d.obs_dim[:A]) == [s.shape[0] for s in oenv.observation_space]
+    heads = [act_heads(s) for s in oenv.action_space]
+    assert [list(d.head_dim[i][:d.n_heads[i]]) for i in range(A)] == heads
+    assert list(d.act_dim[:A]) == [sum(hh) for hh in heads]
+    assert list(d.movable[:A]) == [int(a.movable) for a in oenv.world.agents]
+    speaking = [0 if a.silent else oenv.world.dim_c for a in oenv.world.agents]
+    stored = list(d.comm_len[:A])
+    # a speaking agent's state.c is stored when somebody's observation reads it (simple_crypto: everybody speaks, everybody's
+    # message enters a reward)
+    assert all(s in (0, sp) for s, sp in zip(stored, speaking)) and d.comm_dim == sum(stored)
+    assert d.n_goal == getattr(oenv.scenario, "n_goal", 0)
+    assert d.state_comps == 4 * A + d.comm_dim + 2 * d.n_landmarks + d.n_goal
+    assert d.collaborative == int(oenv.world.collaborative)
