@@ -8,7 +8,8 @@
 //   * slot 0 lives in the last INTERNAL node q = 2^k - 2 (its chain to the root is one level ahead of the true leaves');
 //   * add() only marks slots dirty; the tree changes at the next get_leaf (k_sumtree_flush = SumTree.update_all);
 //   * update_all adds the SUM of both children's deltas to a parent (one rounding); update() adds one delta per ancestor, in
-//     batch order (k_sumtree_update_levels folds each node's deltas sequentially, in batch order, one thread per node).
+//     batch order (k_sumtree_update_levels folds each node's deltas sequentially, in batch order, one thread per node);
+//   * for odd k, update_all with slot 0 pending hands the root the wrong delta (k_sumtree_flush reproduces it).
 #include <math.h>
 
 #include "mdp_common.cuh"
@@ -72,8 +73,13 @@ __global__ void __launch_bounds__(1024) k_sumtree_flush(double* __restrict__ tre
         delta[n] = d;
       } else {
         const long long l = 2 * n + 1, r = l + 1;
-        const double dl = dirty_has(prev, l) ? delta[l] : 0.0, dr = dirty_has(prev, r) ? delta[r] : 0.0;
-        const double s = __dadd_rn(dl, dr);
+        const bool hl = dirty_has(prev, l), hr = dirty_has(prev, r);
+        const double dl = hl ? delta[l] : 0.0, dr = hr ? delta[r] : 0.0;
+        double s = __dadd_rn(dl, dr);
+        // The reference's parallel (node, delta) lists lose their alignment once slot 0's chain has reached the root (:95-99):
+        // for odd k the root then receives slot 0's delta again plus node 1's, and the right subtree's delta is dropped
+        // (oracle/prioritized.py, SumTreeOracle.update_all).  Reproduced: "results identical" includes the tree array.
+        if (n == 0 && s0 && (k & 1)) s = (hl && hr) ? __dadd_rn(hdr[0], dl) : hdr[0];
         tree[n] = __dadd_rn(tree[n], s);
         delta[n] = s;
       }

@@ -20,7 +20,8 @@ reference's list-popping code exactly -- including the reference's quirks, which
 * ``min_prob`` scans the LAST ``capacity`` entries of the tree array (:181-182), which for capacity < 2^k includes never-used
   leaves: min = 0, ``prob / min_prob`` = inf and every IS weight is 0.0;
 * ``sample`` reads ``total_p`` BEFORE the first ``get_leaf`` flushes the pending adds (:175 vs :124);
-* ``batch_update`` propagates one leaf after the other (float64 ``+=`` per ancestor, batch order).
+* ``batch_update`` propagates one leaf after the other (float64 ``+=`` per ancestor, batch order);
+* for odd k, ``update_all`` with slot 0 among the pending adds hands the root the wrong delta (``SumTreeOracle.update_all``).
 
 Nothing under maddpg_b200/ imports this module.
 """
@@ -57,29 +58,46 @@ class SumTreeOracle(object):
 
     def update_all(self):
         """Level-synchronous form of :58-100.  Iteration t touches the ancestors at depth k - t of the dirty true leaves and
-        the ancestor at depth k - 1 - t of slot 0's node (one level ahead, always the last node of its level)."""
+        the ancestor at depth k - 1 - t of slot 0's node (one level ahead, always the last node of its level).
+
+        One more quirk of the reference lives here.  Its loop keeps two parallel lists (nodes, deltas) and appends a parent
+        for every node except the root (:96-99), but hands the WHOLE delta list on (:95).  Slot 0's chain reaches the root one
+        iteration before the true leaves' chain; if the lists are in descending node order at that moment -- they alternate
+        direction every iteration, descending at even ones, so this is the case when k is odd -- the root's delta is the last
+        list element and the next iteration pops it for the wrong node: the root then receives ``c0 + delta(node 1)`` (or
+        ``c0`` alone when only one of its children changed) instead of ``delta(node 1) + delta(node 2)``: slot 0's delta is
+        counted twice and the right subtree's is dropped.  With k even (capacity 1e6: k = 20) the lists are ascending there
+        and the sum is right."""
         if self.dirty_count == 0:
             return
         slots = (self.dirty_start + np.arange(self.dirty_count)) % self.capacity
         self.dirty_count = 0
-        leaves = np.unique(self.leaf_of(slots))
-        delta = self.dirty_value - self.tree[leaves]
-        self.tree[leaves] = self.dirty_value
+        value = self.dirty_value
+        slot0 = bool((slots == 0).any())
+        c0 = 0.0
+        if slot0:  # slot 0's node q and its ancestors: every node gets c0 before the true leaves' sums reach it
+            q = self.leaf_of(0)
+            c0 = value - self.tree[q]
+            self.tree[q] = value
+            m = q
+            while m != 0:
+                m = (m - 1) // 2
+                self.tree[m] += c0
+        leaves = np.unique(self.leaf_of(slots[slots != 0]))
+        delta = value - self.tree[leaves]
+        self.tree[leaves] = value
         nodes = leaves
-        while nodes.size:
-            keep = nodes != 0
-            nodes, delta = nodes[keep], delta[keep]
-            if not nodes.size:
-                break
+        while nodes.size and not (nodes.size == 1 and nodes[0] == 0):
             parents = (nodes - 1) // 2
             up, first = np.unique(parents, return_index=True)
-            summed = np.zeros(up.size, dtype=np.float64)
-            # at most two children per parent; left + right in one rounding (float add commutes)
             cnt = np.diff(np.append(first, parents.size))
-            summed[:] = delta[first]
-            two = cnt == 2
-            summed[two] = delta[first[two]] + delta[first[two] + 1]
             assert cnt.max() <= 2
+            summed = delta[first].copy()
+            two = cnt == 2
+            summed[two] = delta[first[two]] + delta[first[two] + 1]  # left + right in one rounding (float add commutes)
+            if up.size == 1 and up[0] == 0 and slot0 and self.k % 2 == 1:
+                has_left = bool((nodes == 1).any())
+                summed[0] = c0 + delta[np.nonzero(nodes == 1)[0][0]] if (has_left and nodes.size == 2) else c0
             self.tree[up] += summed
             nodes, delta = up, summed
 

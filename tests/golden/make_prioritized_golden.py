@@ -72,7 +72,7 @@ def run_script(cap, script, seed):
     return out
 
 
-# (capacity, script).  37: not a power of two, wraps; 64: power of two (slot cap-1 hangs under slot 0's node), wraps;
+# (capacity, script).  37: not a power of two, wraps (k = 6); 64: power of two (slot cap-1 hangs under slot 0's node), wraps;
 # 1000: many levels, duplicate leaves inside one batch_update (48 draws from few distinct leaves early on)
 SCRIPTS = {
     37: [("add", 20), ("sample", 8), ("update", 0.3), ("sample", 8), ("update", 2.0), ("add", 30), ("sample", 16),
@@ -80,6 +80,10 @@ SCRIPTS = {
          ("sample", 12), ("update", 0.2), ("sample", 12)],
     64: [("add", 10), ("sample", 4), ("update", 0.5), ("add", 54), ("sample", 32), ("update", 0.4), ("sample", 32),
          ("update", 1.5), ("add", 70), ("sample", 64), ("update", 0.3), ("sample", 64), ("update", 0.3), ("sample", 16)],
+    # odd k (k = 7 and k = 3): the flush hands the root the wrong delta when slot 0 is among the pending adds
+    100: [("add", 60), ("sample", 16), ("update", 0.4), ("add", 61), ("sample", 32), ("update", 0.8), ("add", 100), ("sample", 50),
+          ("update", 0.3), ("add", 7), ("sample", 20)],
+    5: [("add", 3), ("sample", 2), ("update", 0.5), ("add", 4), ("sample", 4), ("update", 0.2), ("add", 12), ("sample", 5)],
     1000: [("add", 300), ("sample", 48), ("update", 0.6), ("sample", 48), ("update", 0.6), ("add", 900), ("sample", 256),
            ("update", 0.5), ("sample", 256), ("update", 0.05), ("add", 123), ("sample", 256), ("update", 1.0),
            ("sample", 100)],

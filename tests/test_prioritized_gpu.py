@@ -15,7 +15,7 @@ from tests.test_oracle_prioritized import GOLD, replay_script
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("cap", [37, 64, 1000])
+@pytest.mark.parametrize("cap", [37, 64, 100, 5, 1000])
 def test_device_memory_matches_real_reference_class(cap):
     from maddpg_b200 import DevicePrioritizedReplayMemory
     gold = np.load(GOLD)
