@@ -146,3 +146,47 @@ def test_device_priorities_use_cuda_pow():
     mem.batch_update(torch.from_numpy(ti).cuda(), torch.from_numpy(errs).cuda())
     orc.batch_update(ti, errs.copy())
     np.testing.assert_allclose(mem.tree.cpu().numpy(), orc.tree.tree, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scripts_match_oracle(seed):
+    """Random capacities (odd and even tree depths, powers of two, capacity 3) and random add / sample / batch_update scripts:
+    the device tree equals the pinned oracle's bit for bit after every call, sampled tree indices are identical, and the
+    device raises IndexError exactly where the oracle (= the reference) does."""
+    from maddpg_b200 import DevicePrioritizedReplayMemory
+    rng = np.random.RandomState(500 + seed)
+    cap = int(rng.choice([3, 4, 7, 8, 16, 33, 64, 100, 129, 200, 511, 513]))
+    mem, orc = DevicePrioritizedReplayMemory(cap), PrioritizedReplayOracle(cap)
+    last = None
+    for step in range(30):
+        op = rng.choice(["add", "sample", "update"], p=[0.4, 0.35, 0.25])
+        if op == "add":
+            n = int(rng.randint(1, 2 * cap))
+            s = torch.zeros(n, device="cuda")
+            mem.add(s[:, None].contiguous(), s[:, None].contiguous(), s, s[:, None].contiguous(), torch.zeros(n, dtype=torch.uint8, device="cuda"))
+            orc.tree.add(1e6, n)
+        elif op == "sample" and mem.ring is not None:
+            n = int(rng.randint(1, 3 * cap))
+            u = rng.random_sample(n)
+            try:
+                want = orc.sample(n, u)
+            except IndexError:
+                want = None
+            if want is None:
+                with pytest.raises(IndexError):
+                    mem.sample(n, uniforms=u)
+                mem.beta = float(orc.beta)
+            else:
+                b_idx, _, isw = mem.sample(n, uniforms=u)
+                assert np.array_equal(b_idx, np.asarray(want[0], np.int64)), (cap, step)
+                np.testing.assert_allclose(isw, np.asarray(want[2], np.float64), rtol=1e-13, atol=0)
+                last = np.asarray(want[0], np.int64)
+            assert float(mem.beta) == float(orc.beta)
+        elif op == "update" and last is not None:
+            errs = np.abs(rng.randn(last.size)) * float(rng.choice([0.05, 0.5, 3.0]))
+            for lo in range(0, last.size, 4096):
+                mem.batch_update(last[lo:lo + 4096], errs[lo:lo + 4096].copy())
+            orc.batch_update(last, errs.copy())
+        if mem.dirty_count == 0:
+            orc.tree.update_all()
+            assert np.array_equal(mem.tree.cpu().numpy(), orc.tree.tree), (cap, step, op)
