@@ -228,7 +228,11 @@ __global__ void __launch_bounds__(1024) k_sumtree_update_leaves(double* __restri
 }
 
 // Stage 2: CTA d owns tree depth d in [0, k): a node's deltas are folded in batch order by one thread (the reference's
-// `tree[idx] += change` sequence), distinct nodes in parallel; the elements are grouped per node by a sort on (node, batch position).
+// `tree[idx] += change` sequence), distinct nodes in parallel.
+//   * depth <= 5 (at most 32 nodes): one warp, lane = node; every lane walks the batch in order and adds the elements that
+//     belong to its node (a skipped element leaves the chain untouched, so the roundings are the reference's) -- no sort, the
+//     element loads are lane-uniform broadcasts and run ahead of the dependent adds;
+//   * deeper levels: the elements are grouped per node by a bitonic sort on (node, batch position), segments are short.
 __global__ void __launch_bounds__(1024) k_sumtree_update_levels(double* __restrict__ tree, int k, const long long* __restrict__ tidx,
                                                                  int B, const double* __restrict__ change,
                                                                  const int* __restrict__ flag) {
@@ -236,6 +240,34 @@ __global__ void __launch_bounds__(1024) k_sumtree_update_levels(double* __restri
   double* s_c = reinterpret_cast<double*>(s_keys + PRIO_MAX_B);
   if (*flag & 2) return;
   const int d = blockIdx.x;
+  if (d <= 5) {
+    unsigned* s_node = reinterpret_cast<unsigned*>(s_keys);  // node of element i, relative to the first node of the level
+    const long long first = (1LL << d) - 1;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+      s_node[i] = (unsigned)((((tidx[i] + 1) >> (k - d)) - 1) - first);
+      s_c[i] = change[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < (1u << d)) {
+      const unsigned me = threadIdx.x;
+      double acc = tree[first + me];
+      bool any = false;
+      int i = 0;
+      for (; i + 8 <= B; i += 8) {
+        unsigned nd[8];
+        double c[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { nd[j] = s_node[i + j]; c[j] = s_c[i + j]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (nd[j] == me) { acc = __dadd_rn(acc, c[j]); any = true; }
+      }
+      for (; i < B; ++i)
+        if (s_node[i] == me) { acc = __dadd_rn(acc, s_c[i]); any = true; }
+      if (any) tree[first + me] = acc;
+    }
+    return;
+  }
   int P = 1;
   while (P < B) P <<= 1;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
