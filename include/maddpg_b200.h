@@ -385,6 +385,9 @@ int mdp_sumtree_update(double* tree, int64_t capacity, const int64_t* tree_idx, 
                        const double* priorities, double epsilon, double abs_err_upper, double alpha, int32_t* flag,
                        double* scratch, void* stream);
 
+/* cudaStreamSynchronize(stream): the host-side wait of the calls that fill HOST result buffers (mdp_host_step*). */
+int mdp_stream_synchronize(void* stream);
+
 const char* mdp_last_error(void);
 const char* mdp_version(void);
 /* number of kernels launched by this library in this process (bench.py's gpu_launches) */

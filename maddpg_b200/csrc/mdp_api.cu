@@ -10,6 +10,13 @@ extern "C" const char* mdp_last_error(void) { return mdp::g_err; }
 extern "C" const char* mdp_version(void) { return "maddpg_b200 0.1 (sm_100a)"; }
 extern "C" int64_t mdp_launch_count(void) { return (int64_t)mdp::g_launches.load(); }
 
+// Blocks until everything enqueued on `stream` has completed (cudaStreamSynchronize): the host side of a call with host
+// result buffers (mdp_host_step) needs exactly this and nothing else from the runtime.
+extern "C" int mdp_stream_synchronize(void* stream) {
+  MDP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return MDP_OK;
+}
+
 // The uniform draws behind the kernels' Gumbel noise, computed on the HOST with the same Philox4x32-10 keying as
 // philox_u (mdp_mlp.cuh): element (r, a) = u(seed, counter, tag = agent, row = row0 + r, col = a).  Parity tests feed these
 // to the CPU oracle so that a free-running device rollout can be replayed on the CPU (TF / numpy streams cannot

@@ -242,7 +242,7 @@ class BatchedMultiAgentEnv(object):
         self._d_out[:, :self.obs_stride].copy_(self.obs)
         self._d_out[:, self.obs_stride:].copy_(self.rew)
         self._h_out.copy_(self._d_out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        _lib.synchronize_current_stream()
         host = self._h_out.numpy()
         if self.squeeze:
             obs_n = [host[0, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]

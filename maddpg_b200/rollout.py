@@ -262,7 +262,7 @@ class HostRollout(object):
         v = self._views[self._slot]
         t = torch.from_numpy(v["joint_obs"])
         t.copy_(env.obs, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        _lib.synchronize_current_stream()
         return v["obs"]
 
     def _enqueue(self, src, dst, cursor, counter):
@@ -306,7 +306,6 @@ class HostRollout(object):
         self._slot = dst
         nxt = self._views[dst]
         ring = core.ring if self.experience else None
-        stream = torch.cuda.current_stream()
         if self.use_graph and self._warm:
             if self._graphs[src] is None:
                 self._graphs[src] = self._capture(src, dst)
@@ -324,7 +323,7 @@ class HostRollout(object):
             cursor = ring.reserve_joint(E) if ring is not None else 0
             self._enqueue(src, dst, cursor, core.next_counter())
             self._warm = True  # the first call created the library's streams and events; later ones may be captured
-        stream.synchronize()
+        _lib.synchronize_current_stream()
         return nxt["act"], nxt["obs"], nxt["rew"], nxt["done"]
 
 

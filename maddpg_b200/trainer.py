@@ -183,14 +183,15 @@ class MADDPGCore(object):
         """One agent on its own (E, D_i) device array -> (E, K_i).  The kernel addresses agent i's
         columns as base + off_i, so standalone arrays are passed with the base shifted back."""
         E = obs.shape[0]
-        obs = obs.contiguous()
+        if not obs.is_contiguous():
+            obs = obs.contiguous()
         K = self.act_dims[agent]
         act = torch.empty((E, K), dtype=torch.float32, device=self.device)
         logits = torch.empty((E, K), dtype=torch.float32, device=self.device) if want_logits else None
         sh_o, sh_a = 4 * self.obs_off[agent], 4 * self.act_off[agent]
         up = None
         if u is not None:
-            u = u.contiguous()
+            u = u if u.is_contiguous() else u.contiguous()
             assert u.shape == (E, K)
             up = C.c_void_p(u.data_ptr() - sh_a)
         _lib.check(_lib.lib.mdp_actor_act(self._h, agent, 1, int(use_target), E, C.c_void_p(obs.data_ptr() - sh_o),
