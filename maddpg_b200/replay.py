@@ -156,8 +156,7 @@ class DeviceReplayBuffer(object):
             if done_t.dtype != torch.uint8:
                 done_t = (done_t != 0).to(torch.uint8)
             rew_t = reward if isinstance(reward, torch.Tensor) else torch.full((E,), float(reward), dtype=torch.float32, device=r.device)
-            r.insert_agent(i, obs_t, action, rew_t if rew_t.is_contiguous() else rew_t.contiguous(), obs_tp1,
-                           done_t if done_t.is_contiguous() else done_t.contiguous())
+            r.insert_agent(i, obs_t, action, rew_t, obs_tp1, done_t)  # column views are fine: the kernel takes their strides
             return
         # host path: E transitions (E = 1 for the reference's per-step call) packed into ONE pinned
         # staging buffer -> one H2D copy -> one insert kernel
