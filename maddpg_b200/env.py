@@ -219,6 +219,15 @@ class BatchedMultiAgentEnv(object):
                     np.asarray(a, dtype=np.float32).reshape(-1))
             self.act.copy_(h, non_blocking=True)
         elif isinstance(action_n[0], torch.Tensor) and action_n[0].is_cuda:
+            base = action_n[0].data_ptr() - 4 * self.act_off[0]
+            if all(a.dim() == 2 and a.stride(0) == self.act_stride and a.stride(1) == 1
+                   and a.data_ptr() == base + 4 * self.act_off[i] for i, a in enumerate(action_n)):
+                # the n arrays are the column blocks of ONE joint (E, act_stride) array (MADDPGCore.act_agent returns such
+                # views): step on it directly
+                joint = torch.as_strided(action_n[0], (self.num_envs, self.act_stride), (self.act_stride, 1),
+                                         action_n[0].storage_offset() - self.act_off[0])
+                self.step_device(joint)
+                return self._device_step_result()
             for i, a in enumerate(action_n):
                 dst = self.act[:, self.act_off[i]:self.act_off[i] + self.act_dims[i]]
                 if a.data_ptr() != dst.data_ptr():
@@ -231,13 +240,7 @@ class BatchedMultiAgentEnv(object):
         self.step_device()
         host_io = self.squeeze or not (isinstance(action_n[0], torch.Tensor) and action_n[0].is_cuda)
         if not host_io:
-            obs_n = self._split_obs(self.obs)
-            rew_n, done_n = [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)]
-            if self.reference_loop:  # scalars for the loop's bookkeeping (one (n,) device-to-host copy), vectors for experience()
-                m = self.rew.mean(0).cpu().tolist()
-                rew_n = [EnvBatchFloat(m[i], rew_n[i]) for i in range(self.n)]
-                done_n = [EnvBatchFlag(d) for d in done_n]
-            return obs_n, rew_n, done_n, self._info_n()
+            return self._device_step_result()
         # one packed D2H copy: [obs | rew]; done is identically False in MPE (no done callback)
         self._d_out[:, :self.obs_stride].copy_(self.obs)
         self._d_out[:, self.obs_stride:].copy_(self.rew)
@@ -252,6 +255,15 @@ class BatchedMultiAgentEnv(object):
             obs_n = [host[:, o:o + D].copy() for o, D in zip(self.obs_off, self.obs_dims)]
             rew_n = [host[:, self.obs_stride + i].copy() for i in range(self.n)]
             done_n = [np.zeros(self.num_envs, dtype=bool) for _ in range(self.n)]
+        return obs_n, rew_n, done_n, self._info_n()
+
+    def _device_step_result(self):
+        obs_n = self._split_obs(self.obs)
+        rew_n, done_n = [self.rew[:, i] for i in range(self.n)], [self.done[:, i] for i in range(self.n)]
+        if self.reference_loop:  # scalars for the loop's bookkeeping (one (n,) device-to-host copy), vectors for experience()
+            m = self.rew.mean(0).cpu().tolist()
+            rew_n = [EnvBatchFloat(m[i], rew_n[i]) for i in range(self.n)]
+            done_n = [EnvBatchFlag(d) for d in done_n]
         return obs_n, rew_n, done_n, self._info_n()
 
     def benchmark_data(self):

@@ -183,23 +183,42 @@ class MADDPGCore(object):
         """One agent on its own (E, D_i) device array -> (E, K_i).  The kernel addresses agent i's
         columns as base + off_i, so standalone arrays are passed with the base shifted back."""
         E = obs.shape[0]
-        if not obs.is_contiguous():
+        if obs.stride(1) != 1:  # rows may be strided (a column view of a joint observation array), elements must be adjacent
             obs = obs.contiguous()
         K = self.act_dims[agent]
-        act = torch.empty((E, K), dtype=torch.float32, device=self.device)
-        logits = torch.empty((E, K), dtype=torch.float32, device=self.device) if want_logits else None
         sh_o, sh_a = 4 * self.obs_off[agent], 4 * self.act_off[agent]
+        if use_target or want_logits or u is not None:
+            act = torch.empty((E, K), dtype=torch.float32, device=self.device)
+            act_base, act_ld = C.c_void_p(act.data_ptr() - sh_a), K
+        else:
+            # the rollout call (MADDPGAgentTrainer.action): the result is agent i's column block of a joint (E, act_stride)
+            # array, so that env.step can take the n results of a step without copying them together.  Two arrays alternate:
+            # a result stays valid until the agent's action() call after the next one.
+            act = self._joint_action_view(agent, E)
+            act_base, act_ld = C.c_void_p(act.data_ptr() - sh_a), self.act_stride
+        logits = torch.empty((E, K), dtype=torch.float32, device=self.device) if want_logits else None
         up = None
         if u is not None:
             u = u if u.is_contiguous() else u.contiguous()
             assert u.shape == (E, K)
             up = C.c_void_p(u.data_ptr() - sh_a)
         _lib.check(_lib.lib.mdp_actor_act(self._h, agent, 1, int(use_target), E, C.c_void_p(obs.data_ptr() - sh_o),
-                                          obs.stride(0), C.c_void_p(act.data_ptr() - sh_a), K, up, self.seed,
+                                          obs.stride(0), act_base, act_ld, up, self.seed,
                                           self.next_counter(),
                                           None if logits is None else C.c_void_p(logits.data_ptr() - sh_a),
                                           _lib.current_stream()), "mdp_actor_act")
         return (act, logits) if want_logits else act
+
+    def _joint_action_view(self, agent, E):
+        st = getattr(self, "_jact", None)
+        if st is None or st["buf"].shape[1] != E:
+            st = self._jact = {"buf": torch.zeros((2, E, self.act_stride), dtype=torch.float32, device=self.device), "slot": 0,
+                               "last": self.n}
+        if agent <= st["last"]:  # a new round of action() calls (agents are asked in order, train.py:112)
+            st["slot"] ^= 1
+        st["last"] = agent
+        o = self.act_off[agent]
+        return st["buf"][st["slot"], :, o:o + self.act_dims[agent]]
 
     def critic_q(self, agent, x, use_target=False):
         B = x.shape[0]
