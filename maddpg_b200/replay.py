@@ -128,12 +128,29 @@ class DeviceReplayBuffer(object):
         self._maxsize = ring.capacity
         D, K = ring.obs_dims[agent], ring.act_dims[agent]
         self._pack = 2 * D + K + 2
-        self._h = torch.zeros(self._pack, dtype=torch.float32)
-        if ring.device.type == "cuda":
-            self._h = self._h.pin_memory()
-        self._d = torch.zeros(self._pack, dtype=torch.float32, device=ring.device)
-        self._d_done = torch.zeros(1, dtype=torch.uint8, device=ring.device)
-        self._staged = None  # event marking the end of the last async copy out of the pinned buffer
+        self._stage_E = 0           # staging buffers of the host path are sized at the first add()
+        self._staged = None         # event marking the end of the last async copy out of the pinned buffer
+
+    def _staging(self, E):
+        """Page-locked staging buffer + device mirror for E rows: `pack - 1` floats per row (obs | act | rew | next_obs) followed by
+        the E done flags as bytes, so that ONE host-to-device copy carries everything the insert kernel reads."""
+        if self._stage_E != E:
+            dev = self.ring.device
+            nf = E * (self._pack - 1)
+            nbytes = (4 * nf + E + 15) // 16 * 16
+            hb = torch.zeros(nbytes, dtype=torch.uint8)
+            if dev.type == "cuda":
+                hb = hb.pin_memory()
+            db = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self._hb, self._db = hb, db
+            self._hf = hb[:4 * nf].view(torch.float32).view(E, self._pack - 1).numpy()
+            self._hd = hb[4 * nf:4 * nf + E].numpy()
+            self._df = db[:4 * nf].view(torch.float32).view(E, self._pack - 1)
+            self._dd = db[4 * nf:4 * nf + E]
+            self._stage_E = E
+            self._staged = torch.cuda.Event() if dev.type == "cuda" else None
+            self._staged_pending = False
+        return self._hf, self._hd, self._df, self._dd
 
     def __len__(self):
         return self.ring.length[self.agent]
@@ -162,36 +179,19 @@ class DeviceReplayBuffer(object):
         # staging buffer -> one H2D copy -> one insert kernel
         obs_h = np.asarray(obs_t, dtype=np.float32)
         E = 1 if obs_h.ndim == 1 else obs_h.shape[0]
-        pack = self._pack
-        if self._h.shape[0] < E * pack:
-            self._h = torch.zeros(E * pack, dtype=torch.float32)
-            if r.device.type == "cuda":
-                self._h = self._h.pin_memory()
-            self._d = torch.zeros(E * pack, dtype=torch.float32, device=r.device)
-            self._d_done = torch.zeros(E, dtype=torch.uint8, device=r.device)
-            self._staged = None
-        if self._staged is not None:
+        hf, hd, df, dd = self._staging(E)
+        if self._staged is not None and self._staged_pending:
             self._staged.synchronize()  # the previous H2D copy must have left the pinned buffer
-        h = self._h[:E * pack].view(E, pack).numpy()
-        h[:, :D] = obs_h.reshape(E, D)
-        h[:, D:D + K] = np.asarray(action, dtype=np.float32).reshape(E, K)
-        h[:, D + K] = np.asarray(reward, dtype=np.float32).reshape(E)
-        h[:, D + K + 1:2 * D + K + 1] = np.asarray(obs_tp1, dtype=np.float32).reshape(E, D)
-        h[:, 2 * D + K + 1] = np.asarray(done, dtype=np.float32).reshape(-1)
-        d = self._d[:E * pack].view(E, pack)
-        d.copy_(self._h[:E * pack].view(E, pack), non_blocking=True)
-        if r.device.type == "cuda":
-            self._staged = torch.cuda.Event()
+        hf[:, :D] = obs_h.reshape(E, D)
+        hf[:, D:D + K] = np.asarray(action, dtype=np.float32).reshape(E, K)
+        hf[:, D + K] = np.asarray(reward, dtype=np.float32).reshape(E)
+        hf[:, D + K + 1:2 * D + K + 1] = np.asarray(obs_tp1, dtype=np.float32).reshape(E, D)
+        hd[:] = np.asarray(done).reshape(-1) != 0
+        self._db.copy_(self._hb, non_blocking=True)
+        if self._staged is not None:
             self._staged.record()
-        dn = self._d_done[:E]
-        torch.ne(d[:, 2 * D + K + 1], 0, out=self._ne_buf(E))
-        dn.copy_(self._ne_buf(E))
-        r.insert_agent(i, d[:, :D], d[:, D:D + K], d[:, D + K], d[:, D + K + 1:2 * D + K + 1], dn)
-
-    def _ne_buf(self, E):
-        if getattr(self, "_ne", None) is None or self._ne.shape[0] < E:
-            self._ne = torch.zeros(E, dtype=torch.bool, device=self.ring.device)
-        return self._ne[:E]
+            self._staged_pending = True
+        r.insert_agent(i, df[:, :D], df[:, D:D + K], df[:, D + K], df[:, D + K + 1:2 * D + K + 1], dd)
 
     def make_index(self, batch_size):
         # replay_buffer.py:46-47 -- the same python MT19937 stream as the reference
