@@ -280,6 +280,51 @@ int mdp_update_all(mdp_core* core, const mdp_ring_layout* lay, int32_t B, const 
 /* mdp_clip_adam_polyak for every agent's actor (which = 0) or critic (which = 1) in one launch. */
 int mdp_clip_adam_polyak_all(mdp_core* core, int32_t which, float grad_scale, int32_t do_polyak, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* the fork's tanh-policy algorithms: MATD3 and the best/worst-policy "COMA" variant            */
+/* (maddpg/modules/{policy,critic,laggingnetwork,matd3module,comamodule}.py) */
+/* ------------------------------------------------------------------------------------------ */
+/* A policy group or a critic group (policygroup.py:22-42, criticgroup.py:21-41, unshared) is one mdp_core: the group's
+ * running / target policies live in its P nets, its running / target critics in its Q nets; a group that is only policies
+ * (or only critics) leaves the other nets unused.  The critic step (critic.py:78-88: mse(values - target)) is
+ * mdp_critic_grads, the Adam step mdp_clip_adam_polyak with grad_clip = 0 (grad_norm_clipping=None, tf_util.py:171-175) and
+ * do_polyak = 0.  All cores of one algorithm share n_agents, the dims and num_units; local_q is not supported.
+ *
+ * Policy._build (policy.py:63-88) for every agent in one launch: act_i = t * scale_i + shift_i with t = tanh(mlp_i(obs_i))
+ * (noise_std = 0: `predict` / `predict_target`) or t = clip(tanh(mlp_i(obs_i)) + clip(noise_std * z, -noise_clip, noise_clip),
+ * -1, 1) (`noisy_target`, :72-75).  z: injected N(0,1) draws (B, noise_stride) in the joint action layout, or NULL for
+ * in-kernel Philox draws keyed by (seed, counter, row, column).  act_scale / act_shift: HOST float[n_agents], the Box rescale
+ * `interval` and `interval + low` (:76-84); NULL = 1 and 0.  obs (B, obs_stride) and act (B, act_stride) are joint arrays. */
+int mdp_td3_policy_act(mdp_core* policies, int32_t use_target, int32_t B, const float* obs, int32_t obs_stride,
+                       const float* noise, int32_t noise_stride, float noise_std, float noise_clip, uint64_t seed,
+                       uint64_t counter, const float* act_scale, const float* act_shift, float* act, int32_t act_stride,
+                       void* stream);
+
+/* MaTD3Module.compute_qvalue (matd3module.py:113-123) / ComaModule.compute_{global,personal}_qvalue (comamodule.py:155-171)
+ * for every agent in one launch: q_j = min over the given critic groups (critics_b may be NULL) of Q_j([x | act]) with the
+ * target (use_target = 1) or running nets, x = the obs (obs_field = 0) or next_obs (1) columns of the (B, row_stride) joint
+ * rows `batch`, act a joint (B, act_stride) action array; y_j = rew_j + gamma * (1 - done_j) * q_j in float32 (the graph's
+ * arithmetic), rew_j from the rows, or rew_override[j] (float [n_agents][B]), minus rew_minus[j] when given (ComaModule's
+ * personal reward `global value - worst value`, :104-107).  shared_agent >= 0: a CriticGroup(shared=True) -- that agent's critic
+ * serves every name (criticgroup.py:24-34, 48-66); -1: one critic per agent.  q_out / y_out: float [n_agents][B], either may be
+ * NULL. */
+int mdp_td3_q_target(mdp_core* critics_a, mdp_core* critics_b, int32_t use_target, const mdp_ring_layout* lay, int32_t B,
+                     const float* batch, int32_t obs_field, const float* act, int32_t act_stride, const float* rew_override,
+                     const float* rew_minus, int32_t shared_agent, float gamma, float* q_out, float* y_out, void* stream);
+
+/* The gradient behind Policy.create_optimizer (policy.py:90-100) for every agent in one launch: loss_j = -mean(sign *
+ * Q_j(obs, a)) with a = every policy's current action (act_all, from mdp_td3_policy_act) and a_j recomputed from policy j, Q_j
+ * the critic group's target (critic_use_target = 1: matd3module.py:96-97, comamodule.py:121,126) or running net;
+ * differentiated wrt policy j's variables only (:95).  Accumulates into the policy core's gradient buffer, increments its
+ * Adam step counters, adds sum(-sign * q) to stats[8 * j + 1].  sign = -1 is ComaModule's worst policy (:127). */
+int mdp_td3_policy_grads(mdp_core* policies, mdp_core* critics, int32_t critic_use_target, float sign,
+                         const mdp_ring_layout* lay, int32_t B, const float* batch, const float* act_all, int32_t act_stride,
+                         const float* act_scale, const float* act_shift, void* stream);
+
+/* LaggingNetwork.update_target (laggingnetwork.py:36-48): target <- polyak * target + (1 - polyak) * running for every agent's
+ * policy (mask bit 0) and / or critic (mask bit 1).  The modules call it with polyak = 5e-3 (matd3module.py:104-107). */
+int mdp_td3_polyak(mdp_core* core, int32_t mask, double polyak, void* stream);
+
 /* Persistent episode kernel: `steps` lockstep iterations of experiments/train.py:112-133 (action ->
  * env.step -> experience, optional env.reset at the end) in ONE launch.  Each CTA keeps 32 env instances'
  * state, observation tile, sampled actions and (when they fit) all agents' actor weights in shared

@@ -9,7 +9,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
        -Xptxas -v --expt-relaxed-constexpr -cudart static)
 objs=()
 pids=()
-srcs=(mdp_api mdp_host mdp_env mdp_replay mdp_prio mdp_train mdp_train_tc mdp_optim mdp_rollout mdp_rollout_tc)
+srcs=(mdp_api mdp_host mdp_env mdp_replay mdp_prio mdp_train mdp_td3 mdp_train_tc mdp_optim mdp_rollout mdp_rollout_tc)
 for f in "${srcs[@]}"; do  # one nvcc per translation unit, in parallel
   "$NVCC" "${FLAGS[@]}" -c "$here/$f.cu" -o "$out/$f.o" 2> "$out/$f.ptxas.log" &
   pids+=($!)

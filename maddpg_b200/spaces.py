@@ -39,6 +39,16 @@ class Box(object):
         return "Box%s" % (self.shape,)
 
 
+class Dict(object):
+    """``gym.spaces.Dict``: the fork's algorithms take one for observations and one for actions (multiagentalgbase.py:27-35)."""
+
+    def __init__(self, spaces):
+        self.spaces = dict(spaces)
+
+    def __repr__(self):
+        return "Dict(%s)" % ", ".join("%s:%r" % kv for kv in self.spaces.items())
+
+
 def act_heads(space):
     """Soft one-hot head sizes of an action space (make_pdtype, distributions.py:408-422)."""
     if hasattr(space, "n"):

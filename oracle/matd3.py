@@ -1,0 +1,266 @@
+"""TEST INFRASTRUCTURE -- CPU restatement (numpy, float32) of the fork's tanh-policy algorithms: MATD3 and the best/worst-policy
+"COMA" variant.
+
+PARITY UNPINNED against the reference's own execution: the modules need TensorFlow 1.x and DeepMind Sonnet 1.x (``import sonnet
+as snt``), neither is installed nor fetchable, and the reference holds no golden vector for them (its tests/test_policy.py and
+tests/test_maddpg.py build TF graphs).  The restated gradients are cross-checked against torch autograd in float64
+(tests/test_oracle_matd3.py).
+
+What is restated (reference file:line):
+  LaggingNetwork            maddpg/modules/laggingnetwork.py:15-48   running + target snt.nets.MLP (ReLU, linear last layer);
+                                                                      update_target: t <- polyak*t + (1-polyak)*r
+  Policy._build             maddpg/modules/policy.py:63-88           tanh, clip(N(0,.2),-.5,.5) target noise, clip to [-1,1], Box rescale
+  Policy.create_optimizer   maddpg/modules/policy.py:90-100          loss = -mean(value); Adam(lr, use_locking), no clipping
+  Critic                    maddpg/modules/critic.py:60-88           MLP on concat([obs, act]); loss = mse(values - target)
+  Policy/CriticGroup        maddpg/modules/policygroup.py, criticgroup.py   per-name members (lr 1e-4), or one shared member
+  MaTD3Module._build        maddpg/modules/matd3module.py:46-111     twin critic groups, min of the target critics, policy loss through
+                                                                      the PRIMARY critic group's TARGET network, polyak 5e-3
+  MaTd3._train_step         maddpg/algorithms/matd3.py:63-72         policies step only when ``step and step % 2 == 0``
+  ComaModule._build         maddpg/modules/comamodule.py:58-153      best / worst policy groups, shared global critic, personal critics
+  Coma._train_step          maddpg/algorithms/coma.py:57-63
+
+Things the reference does that look like slips but are what its graph computes (kept, they are part of "same results"):
+  * ``update_targets(5e-3)`` passes 5e-3 as POLYAK, so a target keeps 0.5 % of itself and takes 99.5 % of the running net;
+  * the MATD3 / COMA policy losses run through the critics' TARGET networks (``.target_values``);
+  * TD targets use ``gamma`` = 0.9 (MaTD3Module) / 0.95 (ComaModule): the ``_build`` defaults, never overridden;
+  * COMA's shared global critic trains on the FIRST name's reward and TD target only (criticgroup.py:94-100), its "personal
+    reward" is Q_global(o, a) - Q_global^target(o', worst(o')) for every name, and the best-policy TD actions come from the
+    RUNNING best policies (``.actions``), no target noise.
+One thing is NOT reproducible: ``MaTD3Module._build`` calls ``PolicyGroup.create_optimizers(target_vals, policies.entropy)``
+(matd3module.py:98-99) but the method takes one argument (policygroup.py:123) -- building the reference's MATD3 graph raises
+TypeError.  The restatement drops the extra argument (the "entropy" is not used by any loss in the fork).
+
+All optimizer steps of one ``train_step`` belong to one ``session.run``: every gradient is taken at the pre-step variables.
+Agents are ordered by sorted name (``U.concat_map``, tf_util.py:53-55).  Nothing under maddpg_b200/ imports this module.
+"""
+import numpy as np
+
+from oracle.maddpg import MLP, Adam, polyak_update
+
+F32 = np.float32
+UNITS = 64            # policy.py:33, critic.py:31
+LR = 1e-4             # policygroup.py:127, criticgroup.py:91
+POLYAK = 5e-3         # matd3module.py:104-107, comamodule.py:137-149
+NOISE_STD, NOISE_CLIP = 0.2, 0.5   # policy.py:72-73
+
+
+class Lagging(object):
+    def __init__(self, in_dim, out_dim, rng):
+        self.running = MLP(in_dim, UNITS, out_dim, rng)
+        self.target = MLP(in_dim, UNITS, out_dim, rng)
+        self.adam = Adam(self.running.p, LR)
+
+    def update_target(self, polyak=POLYAK):
+        polyak_update(self.target, self.running, polyak)
+
+
+def box_rescale(low, high):
+    lo, hi = float(np.min(low)), float(np.max(high))
+    interval = (hi - lo) / 2
+    return F32(interval), F32(interval + lo)
+
+
+class PolicyOracle(Lagging):
+    def __init__(self, obs_dim, act_dim, low, high, rng):
+        super().__init__(obs_dim, act_dim, rng)
+        self.scale, self.shift = box_rescale(low, high)
+
+    def act(self, obs, target=False, z=None):
+        """-> (action, tanh, cache); z: N(0,1) draws for the noisy target (policy.py:72-75)."""
+        net = self.target if target else self.running
+        out, cache = net.forward(obs)
+        t = np.tanh(out).astype(F32)
+        tn = t
+        if z is not None:
+            noise = np.clip(F32(NOISE_STD) * np.asarray(z, F32), -NOISE_CLIP, NOISE_CLIP).astype(F32)
+            tn = np.clip(t + noise, -1, 1).astype(F32)
+        return (tn * self.scale + self.shift).astype(F32), t, cache
+
+    def grads(self, cache, t, da):
+        """Gradients of the running net given dL/d(action)."""
+        dout = (np.asarray(da, F32) * self.scale * (F32(1) - t * t)).astype(F32)
+        g, _ = self.running.backward(cache, dout)
+        return g
+
+
+class CriticOracle(Lagging):
+    def __init__(self, in_dim, rng):
+        super().__init__(in_dim, 1, rng)
+
+    def q(self, x, target=False):
+        net = self.target if target else self.running
+        out, cache = net.forward(x)
+        return out[:, 0].astype(F32), cache
+
+    def mse_grads(self, x, y):
+        """loss = mean((Q(x) - y)^2) and its gradients (critic.py:83)."""
+        B = x.shape[0]
+        q, cache = self.q(x)
+        diff = q - np.asarray(y, F32)
+        g, _ = self.running.backward(cache, (F32(2.0) * diff / F32(B))[:, None])
+        return F32(np.mean(diff.astype(np.float64) ** 2)), g, q
+
+    def dq_dx(self, x, dq, target=True):
+        """(q, dL/dx) for upstream dL/dq, through the target (default) or the running net."""
+        net = self.target if target else self.running
+        out, cache = net.forward(x)
+        _, dx = net.backward(cache, np.asarray(dq, F32)[:, None], need_dx=True)
+        return out[:, 0].astype(F32), dx.astype(F32)
+
+
+def td_combine(rew, done, q, gamma):
+    """R + gamma * (1 - D) * Q in float32, the graph's left-to-right arithmetic."""
+    return (np.asarray(rew, F32) + (F32(gamma) * (F32(1.0) - np.asarray(done, F32))) * np.asarray(q, F32)).astype(F32)
+
+
+class _Base(object):
+    def __init__(self, obs_dims, act_dims, lows, highs):
+        self.names = sorted(obs_dims)
+        self.obs_dims, self.act_dims = dict(obs_dims), dict(act_dims)
+        self.lows, self.highs = dict(lows), dict(highs)
+        self.x_dim = sum(obs_dims.values()) + sum(act_dims.values())
+
+    def _policies(self, rng):
+        return {n: PolicyOracle(self.obs_dims[n], self.act_dims[n], self.lows[n], self.highs[n], rng) for n in self.names}
+
+    def _critics(self, rng):
+        return {n: CriticOracle(self.x_dim, rng) for n in self.names}
+
+    def cat(self, d):
+        return np.concatenate([np.asarray(d[n], F32).reshape(len(d[n]), -1) for n in self.names], axis=1)
+
+    def _policy_step(self, policies, critics_of, obs, sign=1.0):
+        """Every policy's loss -mean(sign * Q_name^target(o, a_all)) and gradient wrt its own variables; -> (losses, grads)."""
+        B = len(next(iter(obs.values())))
+        acts, tanhs, caches = {}, {}, {}
+        for n in self.names:
+            acts[n], tanhs[n], caches[n] = policies[n].act(obs[n])
+        x = np.concatenate([self.cat(obs), self.cat(acts)], axis=1)
+        losses, grads = {}, {}
+        o_sum = sum(self.obs_dims.values())
+        col = o_sum
+        for n in self.names:
+            q, dx = critics_of(n).dq_dx(x, np.full(B, -sign / B, F32), target=True)
+            losses[n] = F32(-np.mean(sign * q.astype(np.float64)))
+            K = self.act_dims[n]
+            grads[n] = policies[n].grads(caches[n], tanhs[n], dx[:, col:col + K])
+            col += K
+        return losses, grads
+
+
+class MaTd3Oracle(_Base):
+    GAMMA = 0.9   # matd3module.py:47
+
+    def __init__(self, obs_dims, act_dims, lows, highs, seed=0):
+        super().__init__(obs_dims, act_dims, lows, highs)
+        rng = np.random.RandomState(seed)
+        self.policies = self._policies(rng)
+        self.critics = [self._critics(rng), self._critics(rng)]
+
+    def predict(self, obs):
+        return {n: self.policies[n].act(obs[n])[0] for n in self.names}
+
+    def compute_values(self, obs):
+        acts = self.predict(obs)
+        x = np.concatenate([self.cat(obs), self.cat(acts)], axis=1)
+        return {n: self.critics[0][n].q(x, target=True)[0] for n in self.names}
+
+    def td_targets(self, rew, obs_n, done, z):
+        a_n = {n: self.policies[n].act(obs_n[n], target=True, z=z[n])[0] for n in self.names}
+        xn = np.concatenate([self.cat(obs_n), self.cat(a_n)], axis=1)
+        y = {}
+        for n in self.names:
+            qmin = np.minimum(self.critics[0][n].q(xn, target=True)[0], self.critics[1][n].q(xn, target=True)[0])
+            y[n] = td_combine(np.ravel(rew[n]), np.ravel(done[n]), qmin, self.GAMMA)
+        return y, a_n
+
+    def train_step(self, obs, act, rew, obs_n, done, step=None, z=None):
+        """z: {name: (B, K) N(0,1) draws} behind ``tf.random.normal`` of the noisy target.  -> {'actor': {...} (only on policy
+        steps), 'critic': {...}} like ``unflatten_map(self._train(feed))``."""
+        y, _ = self.td_targets(rew, obs_n, done, z)
+        x = np.concatenate([self.cat(obs), self.cat(act)], axis=1)
+        closs = {n: [] for n in self.names}
+        cgrads = [{}, {}]
+        for c in range(2):
+            for n in self.names:
+                l, g, _ = self.critics[c][n].mse_grads(x, y[n])
+                closs[n].append(l)
+                cgrads[c][n] = g
+        out = {"critic": {n: F32(np.mean(np.asarray(closs[n], F32))) for n in self.names}}
+        policy_step = bool(step) and step % 2 == 0
+        if policy_step:
+            plosses, pgrads = self._policy_step(self.policies, lambda n: self.critics[0][n], obs)
+            out["actor"] = plosses
+        for c in range(2):
+            for n in self.names:
+                cr = self.critics[c][n]
+                cr.adam.step(cr.running.p, cgrads[c][n])
+        if policy_step:
+            for n in self.names:
+                po = self.policies[n]
+                po.adam.step(po.running.p, pgrads[n])
+        return out
+
+    def run_updates(self):
+        for n in self.names:
+            self.policies[n].update_target()
+            self.critics[0][n].update_target()
+            self.critics[1][n].update_target()
+
+
+class ComaOracle(_Base):
+    GAMMA = 0.95   # comamodule.py:59
+
+    def __init__(self, obs_dims, act_dims, lows, highs, seed=0, first=None):
+        super().__init__(obs_dims, act_dims, lows, highs)
+        rng = np.random.RandomState(seed)
+        self.best = self._policies(rng)
+        self.worst = self._policies(rng)
+        self.first = first if first is not None else next(iter(obs_dims))   # CriticGroup(shared=True): first key, insertion order
+        self.global_critic = CriticOracle(self.x_dim, rng)
+        self.personal = self._critics(rng)
+
+    def predict(self, obs):
+        return {n: self.best[n].act(obs[n])[0] for n in self.names}
+
+    def compute_values(self, obs):
+        acts = self.predict(obs)
+        x = np.concatenate([self.cat(obs), self.cat(acts)], axis=1)
+        return {n: self.personal[n].q(x, target=True)[0] for n in self.names}
+
+    def train_step(self, obs, act, rew, obs_n, done, step=None):
+        f = self.first
+        worst_n = {n: self.worst[n].act(obs_n[n])[0] for n in self.names}
+        best_n = {n: self.best[n].act(obs_n[n])[0] for n in self.names}
+        xn_worst = np.concatenate([self.cat(obs_n), self.cat(worst_n)], axis=1)
+        xn_best = np.concatenate([self.cat(obs_n), self.cat(best_n)], axis=1)
+        worst_q = self.global_critic.q(xn_worst, target=True)[0]
+        best_q = self.global_critic.q(xn_best, target=True)[0]
+        x = np.concatenate([self.cat(obs), self.cat(act)], axis=1)
+        y_global = td_combine(np.ravel(rew[f]), np.ravel(done[f]), best_q, self.GAMMA)
+        gl, gg, gq = self.global_critic.mse_grads(x, y_global)
+        personal_reward = (gq - worst_q).astype(F32)
+        closs, pcg = {}, {}
+        for n in self.names:
+            qn = self.personal[n].q(xn_best, target=True)[0]
+            y = td_combine(personal_reward, np.ravel(done[n]), qn, self.GAMMA)
+            l, g, _ = self.personal[n].mse_grads(x, y)
+            closs[n] = F32(np.mean(np.asarray([gl, l], F32)))
+            pcg[n] = g
+        bl, bg = self._policy_step(self.best, lambda n: self.personal[n], obs, sign=1.0)
+        wl, wg = self._policy_step(self.worst, lambda n: self.personal[n], obs, sign=-1.0)
+        out = {"critic": closs,
+               "actor": {n: F32(np.std(np.asarray([bl[n], wl[n]], F32))) for n in self.names}}
+        self.global_critic.adam.step(self.global_critic.running.p, gg)
+        for n in self.names:
+            self.personal[n].adam.step(self.personal[n].running.p, pcg[n])
+            self.best[n].adam.step(self.best[n].running.p, bg[n])
+            self.worst[n].adam.step(self.worst[n].running.p, wg[n])
+        return out
+
+    def run_updates(self):
+        self.global_critic.update_target()
+        for n in self.names:
+            self.personal[n].update_target()
+            self.best[n].update_target()
+            self.worst[n].update_target()

@@ -1,0 +1,204 @@
+"""The fork's dict-of-agents algorithms (maddpg_b200/algorithms.py: MaTd3, Coma over csrc/mdp_td3.cu) against the numpy oracle
+(oracle/matd3.py) on the same weights, batches and noise draws: losses within 1e-4 relative (BASELINE.json north_star's
+tolerance for Q-values and losses), parameters after the Adam steps, predictions, values and the target update.
+Reference: maddpg/algorithms/matd3.py:11-81, coma.py:11-63, modules/matd3module.py:46-123, comamodule.py:58-171."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.matd3 import ComaOracle, MaTd3Oracle
+from tests.test_oracle_matd3 import ACT, HIGH, LOW, NAMES, OBS, make_batch
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def spaces():
+    from maddpg_b200.spaces import Box, Dict
+    obs = Dict({n: Box(-np.inf, np.inf, (OBS[n],)) for n in NAMES})
+    act = Dict({n: Box(np.full(ACT[n], LOW[n], np.float32), np.full(ACT[n], HIGH[n], np.float32), (ACT[n],)) for n in NAMES})
+    return obs, act
+
+
+def load_policy(core, o_group, names):
+    from maddpg_b200 import _lib
+    for j, n in enumerate(names):
+        core.set_weights(j, _lib.NET_P, o_group[n].running.p)
+        core.set_weights(j, _lib.NET_TARGET_P, o_group[n].target.p)
+
+
+def load_critic(core, o_group, names):
+    from maddpg_b200 import _lib
+    for j, n in enumerate(names):
+        core.set_weights(j, _lib.NET_Q, o_group[n].running.p)
+        core.set_weights(j, _lib.NET_TARGET_Q, o_group[n].target.p)
+
+
+def params_close(core, net, j, want, what, lr=1e-4):
+    """Adam's first steps move every weight by ~lr * sign(g): an element whose gradient is rounding noise may step the other way
+    (2 lr apart).  Everything else must agree to a few percent of one step."""
+    for k, (w, r) in enumerate(zip(core.get_weights(j, net), want)):
+        d = np.abs(w - r)
+        assert d.max() <= 2.2 * lr * 3, "%s[%d]: max |diff| %g" % (what, k, d.max())
+        assert np.mean(d > 0.05 * lr) <= 0.01, "%s[%d]: %.3f%% of the elements differ by more than 5%% of a step" % (
+            what, k, 100 * np.mean(d > 0.05 * lr))
+
+
+def losses_close(got, want, what):
+    assert set(got) == set(want), what
+    for n in want:
+        assert abs(float(got[n]) - float(want[n])) <= RTOL * max(abs(float(want[n])), 1e-2), (what, n, got[n], want[n])
+
+
+@pytest.mark.parametrize("B", [48, 1024])
+def test_matd3_train_steps_match_oracle(B):
+    from maddpg_b200 import _lib
+    from maddpg_b200.algorithms import MaTd3
+    o = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=11)
+    alg = MaTd3(*spaces(), seed=1)
+    assert alg.names == o.names
+    load_policy(alg.policies, o.policies, o.names)
+    for c in range(2):
+        load_critic(alg.critics[c], o.critics[c], o.names)
+    for step in (1, 2, 3, 4):     # critic-only, full, critic-only, full (matd3.py:69)
+        obs, act, rew, obs_n, done, z = make_batch(B, 100 + step)
+        want = o.train_step(obs, act, rew, obs_n, done, step=step, z=z)
+        got = alg.train_step(obs, act, rew, obs_n, done, step=step, noise=z)
+        assert ("actor" in got) == ("actor" in want) == (step % 2 == 0)
+        for key in want:
+            losses_close(got[key], want[key], "step %d %s" % (step, key))
+        o.run_updates()
+        alg.run_updates()
+    for j, n in enumerate(o.names):
+        params_close(alg.policies, _lib.NET_P, j, o.policies[n].running.p, "policy " + n)
+        params_close(alg.policies, _lib.NET_TARGET_P, j, o.policies[n].target.p, "target policy " + n)
+        for c in range(2):
+            params_close(alg.critics[c], _lib.NET_Q, j, o.critics[c][n].running.p, "critic %d %s" % (c, n))
+            params_close(alg.critics[c], _lib.NET_TARGET_Q, j, o.critics[c][n].target.p, "target critic %d %s" % (c, n))
+    assert alg.policies.adam_t.cpu().tolist() == [2, 0] * 3 and alg.critics[1].adam_t.cpu().tolist() == [0, 4] * 3
+    # predictions and values of the trained nets on a fresh batch (the oracle evaluated on the DEVICE's weights: the comparison
+    # is of the forward arithmetic, not of four accumulated Adam steps)
+    for j, n in enumerate(o.names):
+        o.policies[n].running.p = alg.policies.get_weights(j, _lib.NET_P)
+        o.critics[0][n].target.p = alg.critics[0].get_weights(j, _lib.NET_TARGET_Q)
+    obs = make_batch(B, 999)[0]
+    want_a, got_a = o.predict(obs), alg.predict(obs, noisy=False)
+    want_v, got_v = o.compute_values(obs), alg.compute_values(obs)
+    for n in o.names:
+        np.testing.assert_allclose(got_a[n].reshape(B, -1), want_a[n], rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(got_v[n][:, 0], want_v[n], rtol=RTOL, atol=RTOL * np.abs(want_v[n]).mean())
+    noisy = alg.predict(obs, noisy=True)      # + N(0, 0.2) on the host (multiagentalgbase.py:62-64)
+    d = np.concatenate([(noisy[n].reshape(B, -1) - got_a[n].reshape(B, -1)).ravel() for n in o.names])
+    assert 0.15 < d.std() < 0.25
+
+
+def test_matd3_compute_loss_leaves_the_state_untouched_and_philox_noise_is_sane():
+    from maddpg_b200.algorithms import MaTd3
+    alg = MaTd3(*spaces(), seed=2)
+    obs, act, rew, obs_n, done, z = make_batch(256, 5)
+    before = [c.params.clone() for c in alg._cores]
+    l1 = alg.compute_loss(obs, act, rew, obs_n, done, noise=z)
+    l2 = alg.compute_loss(obs, act, rew, obs_n, done, noise=z)
+    assert set(l1) == {"actor", "critic"}
+    for key in l1:
+        for n in l1[key]:
+            assert float(l1[key][n]) == pytest.approx(float(l2[key][n]), rel=1e-6)
+    for c, b in zip(alg._cores, before):
+        assert torch.equal(c.params, b) and float(c.grads.abs().max()) == 0.0 and int(c.adam_t.abs().max()) == 0
+    # in-kernel target noise (no injected draws): clip(N(0, 0.2), -0.5, 0.5) around the clean target action
+    nx = alg._rows(obs, act, rew, obs_n, done)
+    L = alg.layout
+    view = nx[:, int(L.nx_off):]
+    clean = alg._policy_act(alg.policies, view, nx.stride(0), alg._act_buf("t_clean", 256), use_target=True).clone()
+    noisy = alg._policy_act(alg.policies, view, nx.stride(0), alg._act_buf("t_noisy", 256), use_target=True, noise_std=0.2).clone()
+    scale = np.concatenate([np.full(ACT[n], (HIGH[n] - LOW[n]) / 2) for n in alg.names])
+    d = ((noisy - clean)[:, :scale.size].cpu().numpy() / scale)
+    inside = np.abs(clean[:, :scale.size].cpu().numpy() / scale) < 10     # every column
+    assert np.abs(d).max() <= 0.5 + 1e-6 and 0.12 < d[inside].std() < 0.22 and abs(d.mean()) < 0.03
+    alg.train_step(obs, act, rew, obs_n, done, step=2)     # Philox path end to end
+    assert all(torch.isfinite(c.params).all() for c in alg._cores)
+
+
+@pytest.mark.parametrize("B", [40, 1024])
+def test_coma_train_steps_match_oracle(B):
+    from maddpg_b200 import _lib
+    from maddpg_b200.algorithms import Coma
+    o = ComaOracle(OBS, ACT, LOW, HIGH, seed=12, first=NAMES[0])
+    alg = Coma(*spaces(), seed=3)
+    assert alg.names == o.names and alg.first == NAMES[0] and alg.names[alg.shared] == NAMES[0]
+    load_policy(alg.best, o.best, o.names)
+    load_policy(alg.worst, o.worst, o.names)
+    load_critic(alg.personal, o.personal, o.names)
+    load_critic(alg.global_critic, {n: o.global_critic for n in o.names}, o.names)
+    for step in (1, 2, 3):
+        obs, act, rew, obs_n, done, _ = make_batch(B, 200 + step)
+        want = o.train_step(obs, act, rew, obs_n, done, step=step)
+        got = alg.train_step(obs, act, rew, obs_n, done, step=step)
+        losses_close(got["critic"], want["critic"], "step %d critic" % step)
+        for n in o.names:     # std of two nearly opposite losses: compare at the losses' own scale
+            assert abs(float(got["actor"][n]) - float(want["actor"][n])) <= RTOL * max(abs(float(want["actor"][n])), 1e-2)
+        o.run_updates()
+        alg.run_updates()
+    s = alg.shared
+    params_close(alg.global_critic, _lib.NET_Q, s, o.global_critic.running.p, "global critic")
+    params_close(alg.global_critic, _lib.NET_TARGET_Q, s, o.global_critic.target.p, "global target critic")
+    for j, n in enumerate(o.names):
+        params_close(alg.best, _lib.NET_P, j, o.best[n].running.p, "best " + n)
+        params_close(alg.worst, _lib.NET_P, j, o.worst[n].running.p, "worst " + n)
+        params_close(alg.worst, _lib.NET_TARGET_P, j, o.worst[n].target.p, "worst target " + n)
+        params_close(alg.personal, _lib.NET_Q, j, o.personal[n].running.p, "personal " + n)
+        params_close(alg.personal, _lib.NET_TARGET_Q, j, o.personal[n].target.p, "personal target " + n)
+
+
+def test_save_load_round_trip_and_refusals(tmp_path):
+    from maddpg_b200.algorithms import Coma, DictReplayBuffer, MaTd3
+    a = MaTd3(*spaces(), seed=4)
+    obs, act, rew, obs_n, done, z = make_batch(64, 9)
+    a.train_step(obs, act, rew, obs_n, done, step=2, noise=z)
+    a.save(tmp_path / "ckpt")
+    b = MaTd3(*spaces(), seed=5)
+    b.load(tmp_path / "ckpt")
+    for ca, cb in zip(a._cores, b._cores):
+        assert torch.equal(ca.params, cb.params) and torch.equal(ca.adam_m, cb.adam_m) and torch.equal(ca.adam_t, cb.adam_t)
+    la = a.train_step(obs, act, rew, obs_n, done, step=4, noise=z)
+    lb = b.train_step(obs, act, rew, obs_n, done, step=4, noise=z)
+    for n in la["critic"]:
+        assert float(la["critic"][n]) == pytest.approx(float(lb["critic"][n]), rel=1e-6)
+    with pytest.raises(NotImplementedError):
+        MaTd3(*spaces(), shared_policy=True)
+    with pytest.raises(NotImplementedError):
+        Coma(*spaces(), normalize={"reward": True})
+    # the fork's dict replay (common/replaybuffer.py): ring overwrite and dict-of-lists samples
+    rb = DictReplayBuffer(5)
+    for t in range(8):
+        rb.add({"a": [t]}, {"a": [t]}, {"a": t}, {"a": [t + 1]}, {"a": False})
+    assert len(rb) == 5 and sorted(x[0]["a"][0] for x in rb._storage) == [3, 4, 5, 6, 7]
+    o, ac, r, o2, d = rb.sample(16)
+    assert len(o["a"]) == 16 and all(3 <= v <= 7 for v in r["a"])
+    assert len(rb.collect()[0]["a"]) == 5
+
+
+def test_learn_generator_drives_a_dict_env():
+    """multiagentalgbase.py:106-132 against a tiny dict env: train steps fire at step > 1024 and step % 5000 == 0."""
+    from maddpg_b200.algorithms import MaTd3
+
+    class Env(object):
+        def __init__(self):
+            self.rng, self.t = np.random.RandomState(0), 0
+
+        def _obs(self):
+            return {n: self.rng.randn(OBS[n]).astype(np.float32) for n in NAMES}
+
+        def reset(self):
+            self.t = 0
+            return self._obs()
+
+        def step(self, actions):
+            assert set(actions) == set(NAMES) and all(np.shape(actions[n]) == (ACT[n],) or ACT[n] == 1 for n in NAMES)
+            self.t += 1
+            return self._obs(), -float(sum(np.sum(np.square(a)) for a in actions.values())), self.t % 25 == 0, {}
+
+    alg = MaTd3(*spaces(), seed=6)
+    fired = [info.step for info in alg.learn_generator(Env(), timesteps=5002) if info.critic_loss]
+    assert fired == [5000]
+    assert alg.critics[0].adam_t.cpu().tolist() == [0, 1] * 3

@@ -1,0 +1,168 @@
+"""oracle/matd3.py against torch autograd in float64: the restated MATD3 / best-worst "COMA" losses and gradients
+(maddpg/modules/matd3module.py:46-123, comamodule.py:58-171, policy.py:63-100, critic.py:60-88) are rebuilt as torch graphs from
+the oracle's own weights and differentiated by autograd.  Parity with the reference's execution is unpinned (oracle header)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.matd3 import ComaOracle, MaTd3Oracle, NOISE_CLIP, NOISE_STD, POLYAK
+
+NAMES = ["b_agent", "a_agent", "c_agent"]      # insertion order differs from sorted order on purpose
+OBS = {"b_agent": 7, "a_agent": 5, "c_agent": 6}
+ACT = {"b_agent": 2, "a_agent": 3, "c_agent": 1}
+LOW = {"b_agent": -1.0, "a_agent": -2.0, "c_agent": 0.0}
+HIGH = {"b_agent": 1.0, "a_agent": 2.0, "c_agent": 3.0}
+
+
+def make_batch(B, seed):
+    rng = np.random.RandomState(seed)
+    obs = {n: rng.randn(B, OBS[n]).astype(np.float32) for n in NAMES}
+    obs_n = {n: rng.randn(B, OBS[n]).astype(np.float32) for n in NAMES}
+    act = {n: rng.uniform(LOW[n], HIGH[n], (B, ACT[n])).astype(np.float32) for n in NAMES}
+    rew = {n: rng.randn(B, 1).astype(np.float32) for n in NAMES}
+    done = {n: (rng.rand(B, 1) < 0.2).astype(np.float32) for n in NAMES}
+    z = {n: rng.randn(B, ACT[n]).astype(np.float32) for n in NAMES}
+    return obs, act, rew, obs_n, done, z
+
+
+def tparams(mlp, grad=False):
+    return [torch.tensor(p.astype(np.float64), requires_grad=grad) for p in mlp.p]
+
+
+def tmlp(p, x):
+    h = torch.relu(x @ p[0] + p[1])
+    h = torch.relu(h @ p[2] + p[3])
+    return h @ p[4] + p[5]
+
+
+def tcat(o, d):
+    return torch.cat([torch.tensor(np.asarray(d[n], np.float64)) if not torch.is_tensor(d[n]) else d[n] for n in o.names], dim=1)
+
+
+def tact(pol, p, obs, z=None):
+    t = torch.tanh(tmlp(p, torch.tensor(obs.astype(np.float64))))
+    if z is not None:
+        t = torch.clamp(t + torch.clamp(NOISE_STD * torch.tensor(z.astype(np.float64)), -NOISE_CLIP, NOISE_CLIP), -1, 1)
+    return t * float(pol.scale) + float(pol.shift)
+
+
+def grads_close(got, want, tol=2e-4):
+    for g, w in zip(got, want):
+        w = w.grad.numpy()
+        assert np.abs(g - w).max() <= tol * max(1e-3, np.abs(w).max()), (np.abs(g - w).max(), np.abs(w).max())
+
+
+def test_matd3_targets_losses_and_gradients_match_autograd():
+    o = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=3)
+    obs, act, rew, obs_n, done, z = make_batch(48, 1)
+    # TD targets
+    y, _ = o.td_targets(rew, obs_n, done, z)
+    a_n = {n: tact(o.policies[n], tparams(o.policies[n].target), obs_n[n], z[n]) for n in o.names}
+    xn = torch.cat([tcat(o, obs_n), tcat(o, a_n)], dim=1)
+    for n in o.names:
+        q = torch.minimum(tmlp(tparams(o.critics[0][n].target), xn), tmlp(tparams(o.critics[1][n].target), xn))[:, 0]
+        want = rew[n][:, 0] + 0.9 * (1 - done[n][:, 0]) * q.numpy()
+        np.testing.assert_allclose(y[n], want, rtol=2e-5, atol=2e-5)
+    # critic gradients
+    x = torch.cat([tcat(o, obs), tcat(o, act)], dim=1)
+    for c in range(2):
+        for n in o.names:
+            p = tparams(o.critics[c][n].running, grad=True)
+            loss = torch.mean((tmlp(p, x)[:, 0] - torch.tensor(y[n].astype(np.float64))) ** 2)
+            loss.backward()
+            l, g, _ = o.critics[c][n].mse_grads(x.numpy().astype(np.float32), y[n])
+            assert abs(l - loss.item()) <= 2e-5 * max(1.0, abs(loss.item()))
+            grads_close(g, p)
+    # policy gradients: loss_j = -mean(Q1_j^target(o, a_all)), differentiated wrt policy j only
+    losses, pg = o._policy_step(o.policies, lambda n: o.critics[0][n], obs)
+    for n in o.names:
+        ps = {m: tparams(o.policies[m].running, grad=(m == n)) for m in o.names}
+        a = {m: tact(o.policies[m], ps[m], obs[m]) for m in o.names}
+        xa = torch.cat([tcat(o, obs), tcat(o, a)], dim=1)
+        loss = -torch.mean(tmlp(tparams(o.critics[0][n].target), xa))
+        loss.backward()
+        assert abs(losses[n] - loss.item()) <= 2e-5 * max(1.0, abs(loss.item()))
+        grads_close(pg[n], ps[n])
+
+
+def test_matd3_step_schedule_and_target_update():
+    o = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=4)
+    obs, act, rew, obs_n, done, z = make_batch(32, 2)
+    p0 = [x.copy() for x in o.policies["a_agent"].running.p]
+    c0 = [x.copy() for x in o.critics[1]["a_agent"].running.p]
+    for step in (None, 0, 1, 3):     # matd3.py:69: the policies step only when ``step and step % 2 == 0``
+        out = o.train_step(obs, act, rew, obs_n, done, step=step, z=z)
+        assert "actor" not in out and set(out["critic"]) == set(NAMES)
+        assert all(np.array_equal(a, b) for a, b in zip(p0, o.policies["a_agent"].running.p))
+    assert not np.array_equal(c0[0], o.critics[1]["a_agent"].running.p[0])
+    out = o.train_step(obs, act, rew, obs_n, done, step=2, z=z)
+    assert set(out["actor"]) == set(NAMES)
+    assert not np.array_equal(p0[0], o.policies["a_agent"].running.p[0])
+    # update_targets(5e-3): the target keeps 0.5 % of itself (matd3module.py:104-107 through laggingnetwork.py:36-48)
+    t0 = o.policies["b_agent"].target.p[0].copy()
+    o.run_updates()
+    r = o.policies["b_agent"].running.p[0]
+    np.testing.assert_allclose(o.policies["b_agent"].target.p[0], np.float32(POLYAK) * t0 + np.float32(1 - POLYAK) * r, rtol=1e-6)
+
+
+def test_coma_losses_and_gradients_match_autograd():
+    o = ComaOracle(OBS, ACT, LOW, HIGH, seed=5, first="b_agent")
+    obs, act, rew, obs_n, done, _ = make_batch(40, 3)
+    f = "b_agent"
+    worst_n = {n: tact(o.worst[n], tparams(o.worst[n].running), obs_n[n]) for n in o.names}
+    best_n = {n: tact(o.best[n], tparams(o.best[n].running), obs_n[n]) for n in o.names}
+    xw = torch.cat([tcat(o, obs_n), tcat(o, worst_n)], dim=1)
+    xb = torch.cat([tcat(o, obs_n), tcat(o, best_n)], dim=1)
+    gt = tparams(o.global_critic.target)
+    worst_q, best_q = tmlp(gt, xw)[:, 0], tmlp(gt, xb)[:, 0]
+    x = torch.cat([tcat(o, obs), tcat(o, act)], dim=1)
+    R, D = (lambda n: torch.tensor(rew[n][:, 0].astype(np.float64))), (lambda n: torch.tensor(done[n][:, 0].astype(np.float64)))
+    gp = tparams(o.global_critic.running, grad=True)
+    gq = tmlp(gp, x)[:, 0]
+    gloss = torch.mean((gq - (R(f) + 0.95 * (1 - D(f)) * best_q).detach()) ** 2)
+    gloss.backward()
+    want_critic, want_pgrads = {}, {}
+    for n in o.names:
+        pp = tparams(o.personal[n].running, grad=True)
+        y = (gq - worst_q).detach() + 0.95 * (1 - D(n)) * tmlp(tparams(o.personal[n].target), xb)[:, 0]
+        loss = torch.mean((tmlp(pp, x)[:, 0] - y.detach()) ** 2)
+        loss.backward()
+        want_critic[n] = 0.5 * (gloss.item() + loss.item())
+        want_pgrads[n] = pp
+    want_actor, want_best, want_worst = {}, {}, {}
+    for n in o.names:
+        ls = []
+        for group, sign, store in ((o.best, 1.0, want_best), (o.worst, -1.0, want_worst)):
+            ps = {m: tparams(group[m].running, grad=(m == n)) for m in o.names}
+            a = {m: tact(group[m], ps[m], obs[m]) for m in o.names}
+            xa = torch.cat([tcat(o, obs), tcat(o, a)], dim=1)
+            loss = -torch.mean(sign * tmlp(tparams(o.personal[n].target), xa))
+            loss.backward()
+            ls.append(loss.item())
+            store[n] = ps[n]
+        want_actor[n] = float(np.std(ls))
+    # the oracle's own gradients, taken before its Adam steps move anything
+    bl, bg = o._policy_step(o.best, lambda n: o.personal[n], obs, sign=1.0)
+    wl, wg = o._policy_step(o.worst, lambda n: o.personal[n], obs, sign=-1.0)
+    for n in o.names:
+        grads_close(bg[n], want_best[n])
+        grads_close(wg[n], want_worst[n])
+    before = [p.copy() for p in o.global_critic.running.p]
+    out = o.train_step(obs, act, rew, obs_n, done)
+    for n in o.names:
+        assert abs(out["critic"][n] - want_critic[n]) <= 5e-5 * max(1.0, abs(want_critic[n]))
+        assert abs(out["actor"][n] - want_actor[n]) <= 5e-5 * max(1.0, abs(want_actor[n]))
+    # first Adam step: every weight with a non-negligible gradient moved by ~lr against the gradient's sign
+    g = gp[0].grad.numpy()
+    moved = o.global_critic.running.p[0] - before[0]
+    big = np.abs(g) > 1e-4
+    assert big.any() and np.all(np.sign(moved[big]) == -np.sign(g[big]))
+    np.testing.assert_allclose(np.abs(moved[big]), 1e-4, rtol=1e-2)
+
+
+@pytest.mark.parametrize("cls", [MaTd3Oracle, ComaOracle])
+def test_sorted_name_order(cls):
+    o = cls(OBS, ACT, LOW, HIGH, seed=0)
+    assert o.names == sorted(NAMES)      # U.concat_map sorts by key (tf_util.py:53-55)
+    if cls is ComaOracle:
+        assert o.first == "b_agent"      # the shared group is named after the FIRST key in insertion order (criticgroup.py:24)
