@@ -342,8 +342,56 @@ def next_rows_section(torch, batch, with_cpu):
         us = a.elapsed_time(b) * 1e3 / 24
         scen[name] = {"agents": env.n, "obs_dims": env.obs_dims, "act_dims": env.act_dims, "env_step_us": us,
                       "agent_env_steps_per_s": E * env.n / (us * 1e-6), "bytes_per_env_step": env.env_bytes_per_step}
-    return {"prioritized_replay": prio, "env_step_4096_envs": scen,
+    return {"prioritized_replay": prio, "env_step_4096_envs": scen, "fork_algorithms": fork_algorithms_section(torch, with_cpu),
             "note": "env step alone (no actor, no insert), graph-replayed"}
+
+
+def fork_algorithms_section(torch, with_cpu):
+    """one MaTd3 / Coma train step + target update at the fork's own training shape (batch 1024,
+    multiagentalgbase.py:127; 64 units) for 3 agents with 18-wide observations and 2-wide Box actions."""
+    import numpy as np
+    from statistics import median
+    from maddpg_b200 import _lib
+    from maddpg_b200.algorithms import Coma, MaTd3
+    from maddpg_b200.spaces import Box, Dict
+    B, n, D, K = 1024, 3, 18, 2
+    names = ["agent_%d" % i for i in range(n)]
+    obs_sp = Dict({k: Box(-np.inf, np.inf, (D,)) for k in names})
+    act_sp = Dict({k: Box(-np.ones(K, np.float32), np.ones(K, np.float32), (K,)) for k in names})
+    rng = np.random.RandomState(0)
+    feed = [{k: rng.randn(B, D).astype(np.float32) for k in names}, {k: rng.uniform(-1, 1, (B, K)).astype(np.float32) for k in names},
+            {k: rng.randn(B, 1).astype(np.float32) for k in names}, {k: rng.randn(B, D).astype(np.float32) for k in names},
+            {k: (rng.rand(B, 1) < 0.1).astype(np.float32) for k in names}]
+    out = {"batch": B, "agents": n, "obs_dim": D, "act_dim": K}
+    for cls in (MaTd3, Coma):
+        alg = cls(obs_sp, act_sp, seed=0)
+        for _ in range(5):
+            alg.train_step(*feed, step=2)
+            alg.run_updates()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            alg.train_step(*feed, step=2)   # host dicts in, host losses out
+            alg.run_updates()
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        row = {"train_step_plus_target_update_ms": median(ts) * 1e3, "launches_per_step": (_lib.launch_count() - l0) / 20,
+               "api": "%s.train_step(host dicts, step=2) + run_updates()" % cls.__name__}
+        if with_cpu:
+            from oracle.matd3 import ComaOracle, MaTd3Oracle
+            o = (MaTd3Oracle if cls is MaTd3 else ComaOracle)({k: D for k in names}, {k: K for k in names}, {k: -1.0 for k in names},
+                                                              {k: 1.0 for k in names}, seed=0)
+            kw = {"z": {k: rng.randn(B, K).astype(np.float32) for k in names}} if cls is MaTd3 else {}
+            o.train_step(*feed, step=2, **kw)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                o.train_step(*feed, step=2, **kw)
+                o.run_updates()
+            row["cpu_port_ms"] = (time.perf_counter() - t0) / 3 * 1e3
+        out[cls.__name__] = row
+    return out
 
 
 def main():

@@ -228,6 +228,11 @@ int mdp_td_target_all(mdp_core* core, const mdp_ring_layout* lay, int32_t B, con
 int mdp_critic_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
                      const int64_t* idx, const float* y, float* q_out, void* stream);
 
+/* mdp_critic_grads for every agent in ONE grouped launch (grid.y = agent): y is float [n_agents][B], idx NULL or int64
+ * [n_agents][idx_agent_stride] (stride 0 shares one set). */
+int mdp_critic_grads_all(mdp_core* core, const mdp_ring_layout* lay, int32_t B, const float* batch, const int64_t* idx,
+                         int64_t idx_agent_stride, const float* y, void* stream);
+
 /* p_train forward/backward (maddpg.py:28-61): grads of -mean(Q_j(o, a_-j, gumbel_softmax(p_j(o_j))))
  * + actor_reg * mean(logits^2) wrt the actor's tensors, through the RUNNING critic (fused kernel). */
 int mdp_actor_grads(mdp_core* core, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,

@@ -87,6 +87,7 @@ SYMBOLS = {
                                 C.c_uint64, _P, _P, _P]),
     "mdp_td_target_all": (C.c_int, [_P, C.POINTER(RingLayout), C.c_int32, _P, _P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P]),
     "mdp_critic_grads": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, _P, _P]),
+    "mdp_critic_grads_all": (C.c_int, [_P, C.POINTER(RingLayout), C.c_int32, _P, _P, C.c_int64, _P, _P]),
     "mdp_actor_grads": (C.c_int, [_P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, _P, _P, C.c_int32, C.c_uint64,
                                   C.c_uint64, _P]),
     "mdp_clip_adam_polyak": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P]),

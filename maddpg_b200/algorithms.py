@@ -8,10 +8,10 @@ maddpg/algorithms/coma.py:11-63; the graphs they run are maddpg/modules/matd3mod
 One policy group or critic group is one ``MADDPGCore`` (flat parameters, gradients and Adam state on the device); a train step is
 a handful of grouped launches (grid.y = agent) from csrc/mdp_td3.cu plus the MADDPG path's critic-step and Adam kernels:
 
-    MATD3:  policy_act(target, noisy) -> q_target(min of twin target critics, TD) -> critic_grads x 2n -> [policy_act ->
+    MATD3:  policy_act(target, noisy) -> q_target(min of twin target critics, TD) -> critic_grads x 2 -> [policy_act ->
             policy_grads through the primary critics' target nets] -> Adam;  run_updates(): polyak(5e-3) of every net.
     COMA:   policy_act(worst) / policy_act(best) at o' -> q_target(global) x 2 -> critic_grads(global) -> q_target(personal, reward
-            = global value - worst value) -> critic_grads(personal) x n -> policy_grads(best, +) / policy_grads(worst, -) -> Adam.
+            = global value - worst value) -> critic_grads(personal) -> policy_grads(best, +) / policy_grads(worst, -) -> Adam.
 
 Every gradient of a step is taken before any Adam step (one ``session.run`` in the reference).  Agents are ordered by sorted
 name (``U.concat_map``, tf_util.py:53-55).  Unshared groups only (``shared_policy`` / ``shared_critic`` raise), no BatchNorm
@@ -160,6 +160,19 @@ class MultiAgentAlgBase(object):
         _lib.check(_lib.lib.mdp_td3_policy_grads(policies._h, critics._h, int(critic_use_target), float(sign), C.byref(self.layout),
                                                  batch.shape[0], _lib.ptr(batch), _lib.ptr(act_all), int(act_all.stride(0)),
                                                  self._scale, self._shift, _lib.current_stream()), "mdp_td3_policy_grads")
+
+    def _critic_grads_all(self, critics, batch, y):
+        _lib.check(_lib.lib.mdp_critic_grads_all(critics._h, C.byref(self.layout), batch.shape[0], _lib.ptr(batch), None, 0,
+                                                 _lib.ptr(y), _lib.current_stream()), "mdp_critic_grads_all")
+
+    @staticmethod
+    def _adam_all(core, which):
+        _lib.check(_lib.lib.mdp_clip_adam_polyak_all(core._h, int(which), 1.0, 0, _lib.current_stream()), "mdp_clip_adam_polyak_all")
+
+    def _read_stats(self, cores):
+        """One device-to-host read of every group's loss accumulators -> list of (n, 8) float64 arrays."""
+        host = torch.cat([c.stats for c in cores]).cpu().numpy()
+        return [host[8 * self.n * i:8 * self.n * (i + 1)].reshape(self.n, 8) for i in range(len(cores))]
 
     @staticmethod
     def _polyak(core, mask):
@@ -338,7 +351,8 @@ class MaTd3(MultiAgentAlgBase):
     def _train_step(self, rows, step, z, update):
         B, L = rows.shape[0], self.layout
         self._zero_stats()
-        self._save_adam_t()
+        if not update:
+            self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
         # noisy target actions at o', min of the twin target critics, TD combine (matd3module.py:76-83, 113-123)
         a_n = self._policy_act(self.policies, nx, rows.stride(0), self._act_buf("a_next", B), use_target=True,
@@ -346,13 +360,12 @@ class MaTd3(MultiAgentAlgBase):
         y = self._scratch(("y", B), (self.n, B))
         self._q_target(self.critics[0], self.critics[1], rows, 1, a_n, y_out=y)
         for cr in self.critics:      # both critic groups regress on the same targets (:88-95)
-            for j in range(self.n):
-                cr.critic_grads(j, rows, y[j])
+            self._critic_grads_all(cr, rows, y)
         policy_step = bool(step) and step % 2 == 0     # matd3.py:69
         if policy_step:
             a = self._policy_act(self.policies, rows, rows.stride(0), self._act_buf("a_now", B))
             self._policy_grads(self.policies, self.critics[0], rows, a)
-        stats = [c.stats.cpu().numpy().reshape(self.n, 8) for c in [self.policies] + self.critics]
+        stats = self._read_stats([self.policies] + self.critics)
         out = {"critic": {k: np.float32(np.mean(np.asarray([stats[1][j, 0] / B, stats[2][j, 0] / B], np.float32)))
                           for j, k in enumerate(self.names)}}
         if policy_step:
@@ -361,11 +374,9 @@ class MaTd3(MultiAgentAlgBase):
             self._discard_grads()
             return out
         for cr in self.critics:
-            for j in range(self.n):
-                cr.clip_adam_polyak(j, 1, do_polyak=False)
+            self._adam_all(cr, 1)
         if policy_step:
-            for j in range(self.n):
-                self.policies.clip_adam_polyak(j, 0, do_polyak=False)
+            self._adam_all(self.policies, 0)
         return out
 
 
@@ -400,7 +411,8 @@ class Coma(MultiAgentAlgBase):
     def _train_step(self, rows, step, z, update):
         B, L, s = rows.shape[0], self.layout, self.shared
         self._zero_stats()
-        self._save_adam_t()
+        if not update:
+            self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
         worst_n = self._policy_act(self.worst, nx, rows.stride(0), self._act_buf("worst_next", B))
         best_n = self._policy_act(self.best, nx, rows.stride(0), self._act_buf("best_next", B))
@@ -417,13 +429,13 @@ class Coma(MultiAgentAlgBase):
                     global_q[j].copy_(global_q[s])
         y_personal = self._scratch(("y_personal", B), (self.n, B))
         self._q_target(self.personal, None, rows, 1, best_n, y_out=y_personal, rew_override=global_q, rew_minus=worst_q)  # :104-114
-        for j in range(self.n):
-            self.personal.critic_grads(j, rows, y_personal[j])                                        # :115-116
+        self._critic_grads_all(self.personal, rows, y_personal)                                       # :115-116
         best_a = self._policy_act(self.best, rows, rows.stride(0), self._act_buf("best_now", B))
         self._policy_grads(self.best, self.personal, rows, best_a, sign=1.0)                          # :118-121, 129
         worst_a = self._policy_act(self.worst, rows, rows.stride(0), self._act_buf("worst_now", B))
         self._policy_grads(self.worst, self.personal, rows, worst_a, sign=-1.0)                       # :123-127, 130
-        st = {name: getattr(self, name).stats.cpu().numpy().reshape(self.n, 8) for name in ("best", "worst", "global_critic", "personal")}
+        st = dict(zip(("best", "worst", "global_critic", "personal"),
+                      self._read_stats([self.best, self.worst, self.global_critic, self.personal])))
         gl = np.float32(st["global_critic"][s, 0] / B)
         out = {"critic": {k: np.float32(np.mean(np.asarray([gl, st["personal"][j, 0] / B], np.float32)))
                           for j, k in enumerate(self.names)},
@@ -433,8 +445,7 @@ class Coma(MultiAgentAlgBase):
             self._discard_grads()
             return out
         self.global_critic.clip_adam_polyak(s, 1, do_polyak=False)
-        for j in range(self.n):
-            self.personal.clip_adam_polyak(j, 1, do_polyak=False)
-            self.best.clip_adam_polyak(j, 0, do_polyak=False)
-            self.worst.clip_adam_polyak(j, 0, do_polyak=False)
+        self._adam_all(self.personal, 1)
+        self._adam_all(self.best, 0)
+        self._adam_all(self.worst, 0)
         return out

@@ -1359,6 +1359,12 @@ static int launch_actor_grads(mdp_core* c, int32_t agent, int32_t count, const m
   });
 }
 
+extern "C" int mdp_critic_grads_all(mdp_core* c, const mdp_ring_layout* lay, int32_t B, const float* batch, const int64_t* idx,
+                                    int64_t idx_agent_stride, const float* y, void* stream) {
+  MDP_REQUIRE(c, "mdp_critic_grads_all: null core");
+  return launch_critic_grads(c, 0, c->cfg.n_agents, lay, B, batch, idx, idx_agent_stride, y, B, nullptr, stream);
+}
+
 extern "C" int mdp_actor_grads(mdp_core* c, int32_t agent, const mdp_ring_layout* lay, int32_t B, const float* batch,
                                const int64_t* idx, const float* u_actor, int32_t u_stride, uint64_t seed, uint64_t counter,
                                void* stream) {
