@@ -299,11 +299,13 @@ int mdp_clip_adam_polyak_all(mdp_core* core, int32_t which, float grad_scale, in
  * (noise_std = 0: `predict` / `predict_target`) or t = clip(tanh(mlp_i(obs_i)) + clip(noise_std * z, -noise_clip, noise_clip),
  * -1, 1) (`noisy_target`, :72-75).  z: injected N(0,1) draws (B, noise_stride) in the joint action layout, or NULL for
  * in-kernel Philox draws keyed by (seed, counter, row, column).  act_scale / act_shift: HOST float[n_agents], the Box rescale
- * `interval` and `interval + low` (:76-84); NULL = 1 and 0.  obs (B, obs_stride) and act (B, act_stride) are joint arrays. */
+ * `interval` and `interval + low` (:76-84); NULL = 1 and 0.  obs (B, obs_stride) and act (B, act_stride) are joint arrays.
+ * shared_agent >= 0: a PolicyGroup(shared=True) -- that agent's policy serves every name (policygroup.py:26-37, 54-70; equal
+ * spaces required); -1: one policy per agent. */
 int mdp_td3_policy_act(mdp_core* policies, int32_t use_target, int32_t B, const float* obs, int32_t obs_stride,
                        const float* noise, int32_t noise_stride, float noise_std, float noise_clip, uint64_t seed,
                        uint64_t counter, const float* act_scale, const float* act_shift, float* act, int32_t act_stride,
-                       void* stream);
+                       int32_t shared_agent, void* stream);
 
 /* MaTD3Module.compute_qvalue (matd3module.py:113-123) / ComaModule.compute_{global,personal}_qvalue (comamodule.py:155-171)
  * for every agent in one launch: q_j = min over the given critic groups (critics_b may be NULL) of Q_j([x | act]) with the
@@ -321,10 +323,14 @@ int mdp_td3_q_target(mdp_core* critics_a, mdp_core* critics_b, int32_t use_targe
  * Q_j(obs, a)) with a = every policy's current action (act_all, from mdp_td3_policy_act) and a_j recomputed from policy j, Q_j
  * the critic group's target (critic_use_target = 1: matd3module.py:96-97, comamodule.py:121,126) or running net;
  * differentiated wrt policy j's variables only (:95).  Accumulates into the policy core's gradient buffer, increments its
- * Adam step counters, adds sum(-sign * q) to stats[8 * j + 1].  sign = -1 is ComaModule's worst policy (:127). */
+ * Adam step counters, adds sum(-sign * q) to stats[8 * j + 1].  sign = -1 is ComaModule's worst policy (:127).
+ * critic_agent >= 0: every loss runs through that agent's critic (a shared critic group, or the first name's critic under a
+ * shared policy group); shared_policy >= 0: one policy net, loss = -mean(sign * Q_critic_agent) differentiated through EVERY
+ * name's action columns into that net's gradient segment (policygroup.py:129-135), step counter and loss counted once. */
 int mdp_td3_policy_grads(mdp_core* policies, mdp_core* critics, int32_t critic_use_target, float sign,
                          const mdp_ring_layout* lay, int32_t B, const float* batch, const float* act_all, int32_t act_stride,
-                         const float* act_scale, const float* act_shift, void* stream);
+                         const float* act_scale, const float* act_shift, int32_t shared_policy, int32_t critic_agent,
+                         void* stream);
 
 /* LaggingNetwork.update_target (laggingnetwork.py:36-48): target <- polyak * target + (1 - polyak) * running for every agent's
  * policy (mask bit 0) and / or critic (mask bit 1).  The modules call it with polyak = 5e-3 (matd3module.py:104-107). */

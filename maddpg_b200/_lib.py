@@ -119,11 +119,11 @@ SYMBOLS = {
                                      _P, _P, _P]),
     "mdp_sumtree_update": (C.c_int, [_P, C.c_int64, _P, C.c_int32, _P, _P, C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "mdp_td3_policy_act": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_float, C.c_float, C.c_uint64,
-                                     C.c_uint64, _P, _P, _P, C.c_int32, _P]),
+                                     C.c_uint64, _P, _P, _P, C.c_int32, C.c_int32, _P]),
     "mdp_td3_q_target": (C.c_int, [_P, _P, C.c_int32, C.POINTER(RingLayout), C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, _P,
                                    C.c_int32, C.c_float, _P, _P, _P]),
     "mdp_td3_policy_grads": (C.c_int, [_P, _P, C.c_int32, C.c_float, C.POINTER(RingLayout), C.c_int32, _P, _P, C.c_int32, _P, _P,
-                                       _P]),
+                                       C.c_int32, C.c_int32, _P]),
     "mdp_td3_polyak": (C.c_int, [_P, C.c_int32, C.c_double, _P]),
     "mdp_stream_synchronize": (C.c_int, [_P]),
     "mdp_last_error": (C.c_char_p, []),

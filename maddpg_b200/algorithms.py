@@ -14,8 +14,8 @@ a handful of grouped launches (grid.y = agent) from csrc/mdp_td3.cu plus the MAD
             = global value - worst value) -> critic_grads(personal) -> policy_grads(best, +) / policy_grads(worst, -) -> Adam.
 
 Every gradient of a step is taken before any Adam step (one ``session.run`` in the reference).  Agents are ordered by sorted
-name (``U.concat_map``, tf_util.py:53-55).  Unshared groups only (``shared_policy`` / ``shared_critic`` raise), no BatchNorm
-``normalize``.  All arithmetic runs in libmaddpg_b200.so; there is no PyTorch or CPU fallback.
+name (``U.concat_map``, tf_util.py:53-55).  ``shared_policy`` / ``shared_critic`` groups keep one member -- the first name's --
+with the reference's one-loss semantics (policygroup.py:129-135, criticgroup.py:94-100); the BatchNorm ``normalize`` option raises.  All arithmetic runs in libmaddpg_b200.so; there is no PyTorch or CPU fallback.
 """
 import ctypes as C
 from collections import namedtuple
@@ -63,6 +63,7 @@ class MultiAgentAlgBase(object):
         self.device = torch.device(device)
         self.seed = int(seed)
         self._counter = 0
+        self.sp = self.sc = -1     # index of the name a shared policy / critic group is built on, -1: one member per name
         self._cores = []
         self.max_batch = int(max_batch)
         self._buf = {}
@@ -138,13 +139,13 @@ class MultiAgentAlgBase(object):
         return out
 
     # -- kernels --------------------------------------------------------------------------------
-    def _policy_act(self, policies, x, x_stride, out, use_target=False, noise_std=0.0, noise=None):
+    def _policy_act(self, policies, x, x_stride, out, use_target=False, noise_std=0.0, noise=None, shared=-1):
         B = out.shape[0]
         self._counter += 1
         _lib.check(_lib.lib.mdp_td3_policy_act(policies._h, int(use_target), B, _lib.ptr(x), int(x_stride), _lib.ptr(noise),
                                                0 if noise is None else int(noise.stride(0)), float(noise_std), NOISE_CLIP,
                                                self.seed, self._counter, self._scale, self._shift, _lib.ptr(out),
-                                               int(out.stride(0)), _lib.current_stream()), "mdp_td3_policy_act")
+                                               int(out.stride(0)), int(shared), _lib.current_stream()), "mdp_td3_policy_act")
         return out
 
     def _q_target(self, critics_a, critics_b, batch, obs_field, act, q_out=None, y_out=None, use_target=True, rew_override=None,
@@ -156,10 +157,25 @@ class MultiAgentAlgBase(object):
                                              float(self.GAMMA), _lib.ptr(q_out), _lib.ptr(y_out), _lib.current_stream()),
                    "mdp_td3_q_target")
 
-    def _policy_grads(self, policies, critics, batch, act_all, sign=1.0, critic_use_target=True):
+    def _policy_grads(self, policies, critics, batch, act_all, sign=1.0, critic_use_target=True, shared_policy=-1, critic_agent=-1):
         _lib.check(_lib.lib.mdp_td3_policy_grads(policies._h, critics._h, int(critic_use_target), float(sign), C.byref(self.layout),
                                                  batch.shape[0], _lib.ptr(batch), _lib.ptr(act_all), int(act_all.stride(0)),
-                                                 self._scale, self._shift, _lib.current_stream()), "mdp_td3_policy_grads")
+                                                 self._scale, self._shift, int(shared_policy), int(critic_agent),
+                                                 _lib.current_stream()), "mdp_td3_policy_grads")
+
+    def _critic_step(self, critics, shared, batch, y):
+        """CriticGroup.create_optimizers (criticgroup.py:87-106): every name's critic, or -- shared -- the one critic on the first
+        name's targets."""
+        if shared >= 0:
+            critics.critic_grads(shared, batch, y[shared])
+        else:
+            self._critic_grads_all(critics, batch, y)
+
+    def _adam(self, core, which, shared):
+        if shared >= 0:
+            core.clip_adam_polyak(shared, which, do_polyak=False)
+        else:
+            self._adam_all(core, which)
 
     def _critic_grads_all(self, critics, batch, y):
         _lib.check(_lib.lib.mdp_critic_grads_all(critics._h, C.byref(self.layout), batch.shape[0], _lib.ptr(batch), None, 0,
@@ -186,7 +202,8 @@ class MultiAgentAlgBase(object):
         """multiagentalgbase.py:50-67: the running policies' actions, plus N(0, 0.2) exploration noise drawn on the host
         (``npr.normal``: numpy's global stream, exactly as the reference consumes it)."""
         obs = self._joint(observations, self.obs_dims, self._cores[0].obs_stride)
-        act = self._policy_act(self._predict_policies(), obs, obs.stride(0), self._act_buf("predict", obs.shape[0]))
+        act = self._policy_act(self._predict_policies(), obs, obs.stride(0), self._act_buf("predict", obs.shape[0]),
+                               shared=self.sp)
         actions = self._split(act, self.act_dims)
         if noisy:
             return {k: np.squeeze(a + np.random.normal(scale=0.2, size=a.shape)) for k, a in actions.items()}
@@ -196,11 +213,11 @@ class MultiAgentAlgBase(object):
         """multiagentalgbase.py:69-78: ``critic_predict`` = the value critics' TARGET nets at (obs, predicted actions)."""
         obs = self._joint(observations, self.obs_dims, self._cores[0].obs_stride)
         B = obs.shape[0]
-        act = self._policy_act(self._predict_policies(), obs, obs.stride(0), self._act_buf("predict", B))
+        act = self._policy_act(self._predict_policies(), obs, obs.stride(0), self._act_buf("predict", B), shared=self.sp)
         rows = self._scratch(("rows", B), (B, int(self.layout.row_stride)))
         rows[:, :obs.shape[1]].copy_(obs)    # only the obs columns are read (obs_field = 0, no TD combine)
         q = self._scratch(("values", B), (self.n, B))
-        self._q_target(self._value_critics(), None, rows, 0, act, q_out=q)
+        self._q_target(self._value_critics(), None, rows, 0, act, q_out=q, shared_agent=self._value_shared())
         host = q.cpu().numpy()
         return {k: host[j][:, None].copy() for j, k in enumerate(self.names)}
 
@@ -219,6 +236,11 @@ class MultiAgentAlgBase(object):
 
     def update_targets(self):
         self.run_updates()
+
+    def _check_shared(self):
+        if self.sp >= 0 and (len(set(self.obs_dims)) > 1 or len(set(self.act_dims)) > 1 or len(set(self._scale)) > 1
+                             or len(set(self._shift)) > 1):
+            raise AssertionError("a shared policy needs equal observation and action spaces (policygroup.py:32-34)")
 
     def _zero_stats(self):
         for c in self._cores:
@@ -331,17 +353,24 @@ class MaTd3(MultiAgentAlgBase):
     GAMMA = 0.9   # MaTD3Module._build(..., gamma=0.9), matd3module.py:47
 
     def __init__(self, observation_space, action_space, shared_policy=False, shared_critic=False, normalize=None, **kw):
-        if shared_policy or shared_critic or normalize:
-            raise NotImplementedError("shared groups and BatchNorm normalisation are not built (maddpg_b200/algorithms.py header)")
+        if normalize:
+            raise NotImplementedError("BatchNorm normalisation is not built (maddpg_b200/algorithms.py header)")
         super().__init__(observation_space, action_space, **kw)
         self.policies = self._group(0)                       # uses the P nets
         self.critics = [self._group(1), self._group(2)]      # twin critic groups: the Q nets
+        first = self.names.index(self.first)
+        self.sp = first if shared_policy else -1             # PolicyGroup(shared=...): the first name's member serves all
+        self.sc = first if shared_critic else -1             # CriticGroup(shared=...)
+        self._check_shared()
 
     def _predict_policies(self):
         return self.policies
 
     def _value_critics(self):
         return self.critics[0]
+
+    def _value_shared(self):
+        return self.sc
 
     def run_updates(self):
         self._polyak(self.policies, 1)
@@ -355,28 +384,31 @@ class MaTd3(MultiAgentAlgBase):
             self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
         # noisy target actions at o', min of the twin target critics, TD combine (matd3module.py:76-83, 113-123)
+        sp, sc = self.sp, self.sc
         a_n = self._policy_act(self.policies, nx, rows.stride(0), self._act_buf("a_next", B), use_target=True,
-                               noise_std=NOISE_STD, noise=z)
+                               noise_std=NOISE_STD, noise=z, shared=sp)
         y = self._scratch(("y", B), (self.n, B))
-        self._q_target(self.critics[0], self.critics[1], rows, 1, a_n, y_out=y)
+        self._q_target(self.critics[0], self.critics[1], rows, 1, a_n, y_out=y, shared_agent=sc)
         for cr in self.critics:      # both critic groups regress on the same targets (:88-95)
-            self._critic_grads_all(cr, rows, y)
+            self._critic_step(cr, sc, rows, y)
         policy_step = bool(step) and step % 2 == 0     # matd3.py:69
         if policy_step:
-            a = self._policy_act(self.policies, rows, rows.stride(0), self._act_buf("a_now", B))
-            self._policy_grads(self.policies, self.critics[0], rows, a)
+            a = self._policy_act(self.policies, rows, rows.stride(0), self._act_buf("a_now", B), shared=sp)
+            # a shared group's one loss is the first name's value (policygroup.py:129-135)
+            self._policy_grads(self.policies, self.critics[0], rows, a, shared_policy=sp, critic_agent=sc if sc >= 0 else sp)
         stats = self._read_stats([self.policies] + self.critics)
-        out = {"critic": {k: np.float32(np.mean(np.asarray([stats[1][j, 0] / B, stats[2][j, 0] / B], np.float32)))
+        out = {"critic": {k: np.float32(np.mean(np.asarray([stats[1][sc if sc >= 0 else j, 0] / B,
+                                                             stats[2][sc if sc >= 0 else j, 0] / B], np.float32)))
                           for j, k in enumerate(self.names)}}
         if policy_step:
-            out["actor"] = {k: np.float32(stats[0][j, 1] / B) for j, k in enumerate(self.names)}
+            out["actor"] = {k: np.float32(stats[0][sp if sp >= 0 else j, 1] / B) for j, k in enumerate(self.names)}
         if not update:
             self._discard_grads()
             return out
         for cr in self.critics:
-            self._adam_all(cr, 1)
+            self._adam(cr, 1, sc)
         if policy_step:
-            self._adam_all(self.policies, 0)
+            self._adam(self.policies, 0, sp)
         return out
 
 
@@ -387,20 +419,25 @@ class Coma(MultiAgentAlgBase):
     GAMMA = 0.95   # ComaModule._build(..., gamma=0.95), comamodule.py:59
 
     def __init__(self, observation_space, action_space, shared_policy=False, shared_critic=False, normalize=None, **kw):
-        if shared_policy or normalize:
-            raise NotImplementedError("shared policies and BatchNorm normalisation are not built (maddpg_b200/algorithms.py header)")
+        if normalize:
+            raise NotImplementedError("BatchNorm normalisation is not built (maddpg_b200/algorithms.py header)")
         super().__init__(observation_space, action_space, **kw)   # shared_critic is ignored by ComaModule too (comamodule.py:36-43)
         self.best = self._group(0)
         self.worst = self._group(1)
         self.global_critic = self._group(2)    # CriticGroup(shared=True): only the first name's critic exists
         self.personal = self._group(3)
         self.shared = self.names.index(self.first)
+        self.sp = self.shared if shared_policy else -1
+        self._check_shared()
 
     def _predict_policies(self):
         return self.best
 
     def _value_critics(self):
         return self.personal
+
+    def _value_shared(self):
+        return -1
 
     def run_updates(self):
         self._polyak(self.global_critic, 2)
@@ -414,8 +451,9 @@ class Coma(MultiAgentAlgBase):
         if not update:
             self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
-        worst_n = self._policy_act(self.worst, nx, rows.stride(0), self._act_buf("worst_next", B))
-        best_n = self._policy_act(self.best, nx, rows.stride(0), self._act_buf("best_next", B))
+        sp = self.sp
+        worst_n = self._policy_act(self.worst, nx, rows.stride(0), self._act_buf("worst_next", B), shared=sp)
+        best_n = self._policy_act(self.best, nx, rows.stride(0), self._act_buf("best_next", B), shared=sp)
         worst_q = self._scratch(("worst_q", B), (self.n, B))
         y_global = self._scratch(("y_global", B), (self.n, B))
         self._q_target(self.global_critic, None, rows, 1, worst_n, q_out=worst_q, shared_agent=s)     # comamodule.py:82-86
@@ -430,22 +468,23 @@ class Coma(MultiAgentAlgBase):
         y_personal = self._scratch(("y_personal", B), (self.n, B))
         self._q_target(self.personal, None, rows, 1, best_n, y_out=y_personal, rew_override=global_q, rew_minus=worst_q)  # :104-114
         self._critic_grads_all(self.personal, rows, y_personal)                                       # :115-116
-        best_a = self._policy_act(self.best, rows, rows.stride(0), self._act_buf("best_now", B))
-        self._policy_grads(self.best, self.personal, rows, best_a, sign=1.0)                          # :118-121, 129
-        worst_a = self._policy_act(self.worst, rows, rows.stride(0), self._act_buf("worst_now", B))
-        self._policy_grads(self.worst, self.personal, rows, worst_a, sign=-1.0)                       # :123-127, 130
+        best_a = self._policy_act(self.best, rows, rows.stride(0), self._act_buf("best_now", B), shared=sp)
+        self._policy_grads(self.best, self.personal, rows, best_a, sign=1.0, shared_policy=sp, critic_agent=sp)    # :118-121, 129
+        worst_a = self._policy_act(self.worst, rows, rows.stride(0), self._act_buf("worst_now", B), shared=sp)
+        self._policy_grads(self.worst, self.personal, rows, worst_a, sign=-1.0, shared_policy=sp, critic_agent=sp)  # :123-127, 130
         st = dict(zip(("best", "worst", "global_critic", "personal"),
                       self._read_stats([self.best, self.worst, self.global_critic, self.personal])))
         gl = np.float32(st["global_critic"][s, 0] / B)
         out = {"critic": {k: np.float32(np.mean(np.asarray([gl, st["personal"][j, 0] / B], np.float32)))
                           for j, k in enumerate(self.names)},
-               "actor": {k: np.float32(np.std(np.asarray([st["best"][j, 1] / B, st["worst"][j, 1] / B], np.float32)))
+               "actor": {k: np.float32(np.std(np.asarray([st["best"][sp if sp >= 0 else j, 1] / B,
+                                                           st["worst"][sp if sp >= 0 else j, 1] / B], np.float32)))
                          for j, k in enumerate(self.names)}}
         if not update:
             self._discard_grads()
             return out
         self.global_critic.clip_adam_polyak(s, 1, do_polyak=False)
         self._adam_all(self.personal, 1)
-        self._adam_all(self.best, 0)
-        self._adam_all(self.worst, 0)
+        self._adam(self.best, 0, sp)
+        self._adam(self.worst, 0, sp)
         return out

@@ -41,7 +41,7 @@ template <int U, int TM>
 __global__ void __launch_bounds__(NT) k_td3_policy_act(CoreDev C, Td3Head H, int use_target, int B, const float* __restrict__ obs,
                                                        int obs_stride, const float* __restrict__ noise, int noise_stride,
                                                        float noise_std, float noise_clip, uint64_t seed, uint64_t counter,
-                                                       float* __restrict__ act, int act_stride) {
+                                                       float* __restrict__ act, int act_stride, int shared_agent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(NT) k_td3_policy_act(CoreDev C, Td3Head H, int
   float* sL = sm.take(TM * KPAD);
   const int i = blockIdx.y;
   const AgentDev& ag = C.agents[i];
-  const MlpW w = ag.net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
+  // PolicyGroup(shared=True): one policy serves every name (policygroup.py:26-37, 54-70)
+  const MlpW w = C.agents[shared_agent >= 0 ? shared_agent : i].net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   XSrc xs = make_xsrc(obs + ag.obs_off, obs_stride, ag.obs_dim);
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(NT) k_td3_q_target(CoreDev Ca, CoreDev Cb, int
 template <int U, int TM>
 __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq, Td3Head H, int critic_use_target, float sign,
                                                          mdp_ring_layout L, int B, const float* __restrict__ batch,
-                                                         const float* __restrict__ act_all, int act_stride) {
+                                                         const float* __restrict__ act_all, int act_stride, int shared_policy,
+                                                         int critic_agent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int HP = U + 4;
   const Grp G{(int)threadIdx.x, 0};
@@ -141,13 +143,17 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
   float* sQ = sm.take(TM);
   const int j = blockIdx.y;
   const AgentDev& me = Cp.agents[j];
-  const MlpW pw = me.net[MDP_NET_P];
-  const MlpW qw = Cq.agents[j].net[critic_use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
-  const MlpG& pg = me.grad[0];
+  // shared policy group: name j's observation and action columns, the one shared net and its gradient bucket; its loss is
+  // -mean(value of the group's first name) and reaches the shared variables through EVERY name's action (policygroup.py:129-135)
+  const int pj = shared_policy >= 0 ? shared_policy : j, cj = critic_agent >= 0 ? critic_agent : j;
+  const bool lead = shared_policy < 0 || j == 0;   // step counter and loss are the group's, counted once
+  const MlpW pw = Cp.agents[pj].net[MDP_NET_P];
+  const MlpW qw = Cq.agents[cj].net[critic_use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
+  const MlpG& pg = Cp.agents[pj].grad[0];
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   const int R = L.row_stride, K = me.act_dim;
-  if (blockIdx.x == 0 && threadIdx.x == 0) Cp.adam_t[2 * j + 0] += 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && lead) Cp.adam_t[2 * pj + 0] += 1;
 
   XSrc xp = make_xsrc(batch + me.obs_off, R, me.obs_dim);
   forward_hidden<U, TM, false>(G, xp, pw, row0, nrows, sX, sW, sP1, sP2);
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
     const int r = threadIdx.x;
     double sq = (r < nrows && r < TM) ? -(double)sign * (double)sQ[r] : 0.0;
     for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (r == 0) atomicAdd(Cp.stats + 8 * j + 1, sq);
+    if (r == 0 && lead) atomicAdd(Cp.stats + 8 * pj + 1, sq);
   }
   const float dq = -sign / (float)B;
   for (int idx = threadIdx.x; idx < TM * U; idx += NT) {
@@ -270,6 +276,16 @@ static int td3_check_lay(const mdp_core* c, const mdp_ring_layout* lay, const ch
   return MDP_OK;
 }
 
+// a shared policy serves names with equal spaces only (policygroup.py:32-34)
+static int td3_check_shared(const mdp_core* c, int shared, const char* what) {
+  MDP_REQUIRE(shared < c->cfg.n_agents, "%s: shared agent %d of %d", what, shared, c->cfg.n_agents);
+  if (shared >= 0)
+    for (int i = 0; i < c->cfg.n_agents; ++i)
+      MDP_REQUIRE(c->cfg.obs_dim[i] == c->cfg.obs_dim[shared] && c->cfg.act_dim[i] == c->cfg.act_dim[shared],
+                  "%s: a shared policy needs equal observation and action spaces (policygroup.py:32-34)", what);
+  return MDP_OK;
+}
+
 static Td3Head make_head(const mdp_core* c, const float* scale, const float* shift) {
   Td3Head h;
   for (int i = 0; i < MDP_MAX_AGENTS; ++i) {
@@ -286,11 +302,12 @@ using namespace mdp;
 extern "C" int mdp_td3_policy_act(mdp_core* c, int32_t use_target, int32_t B, const float* obs, int32_t obs_stride,
                                   const float* noise, int32_t noise_stride, float noise_std, float noise_clip, uint64_t seed,
                                   uint64_t counter, const float* act_scale, const float* act_shift, float* act,
-                                  int32_t act_stride, void* stream) {
+                                  int32_t act_stride, int32_t shared_agent, void* stream) {
   int rc = td3_check_core(c, "mdp_td3_policy_act");
   if (rc) return rc;
   MDP_REQUIRE(obs && act && B > 0 && obs_stride >= c->obs_sum && act_stride >= c->act_sum, "mdp_td3_policy_act: bad argument");
   MDP_REQUIRE(!noise || noise_stride >= c->act_sum, "mdp_td3_policy_act: bad noise stride");
+  if ((rc = td3_check_shared(c, shared_agent, "mdp_td3_policy_act"))) return rc;
   const CoreDev d = core_dev_for_rollout(c);
   const Td3Head h = make_head(c, act_scale, act_shift);
   return td3_dispatch(c->cfg.num_units, B, [&](auto u_, auto tm_) -> int {
@@ -301,7 +318,7 @@ extern "C" int mdp_td3_policy_act(mdp_core* c, int32_t use_target, int32_t B, co
     if (rc2) return rc2;
     kern<<<dim3(cdiv(B, TMv), c->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(d, h, use_target, B, obs, obs_stride, noise,
                                                                                 noise_stride, noise_std, noise_clip, seed, counter,
-                                                                                act, act_stride);
+                                                                                act, act_stride, shared_agent);
     return check_launch("k_td3_policy_act");
   });
 }
@@ -336,13 +353,16 @@ extern "C" int mdp_td3_q_target(mdp_core* ca, mdp_core* cb, int32_t use_target, 
 
 extern "C" int mdp_td3_policy_grads(mdp_core* policy, mdp_core* critic, int32_t critic_use_target, float sign,
                                     const mdp_ring_layout* lay, int32_t B, const float* batch, const float* act_all,
-                                    int32_t act_stride, const float* act_scale, const float* act_shift, void* stream) {
+                                    int32_t act_stride, const float* act_scale, const float* act_shift, int32_t shared_policy,
+                                    int32_t critic_agent, void* stream) {
   int rc = td3_check_core(policy, "mdp_td3_policy_grads");
   if (rc) return rc;
   if ((rc = td3_check_core(critic, "mdp_td3_policy_grads"))) return rc;
   if ((rc = td3_same_shape(policy, critic, "mdp_td3_policy_grads"))) return rc;
   if ((rc = td3_check_lay(policy, lay, "mdp_td3_policy_grads"))) return rc;
-  MDP_REQUIRE(batch && act_all && B > 0 && act_stride >= policy->act_sum, "mdp_td3_policy_grads: bad argument");
+  MDP_REQUIRE(batch && act_all && B > 0 && act_stride >= policy->act_sum && critic_agent < critic->cfg.n_agents,
+              "mdp_td3_policy_grads: bad argument");
+  if ((rc = td3_check_shared(policy, shared_policy, "mdp_td3_policy_grads"))) return rc;
   const CoreDev dp = core_dev_for_rollout(policy), dq = core_dev_for_rollout(critic);
   const Td3Head h = make_head(policy, act_scale, act_shift);
   return td3_dispatch(policy->cfg.num_units, B, [&](auto u_, auto tm_) -> int {
@@ -352,7 +372,8 @@ extern "C" int mdp_td3_policy_grads(mdp_core* policy, mdp_core* critic, int32_t 
     int rc2 = td3_smem(kern, smem);
     if (rc2) return rc2;
     kern<<<dim3(cdiv(B, TMv), policy->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(dp, dq, h, critic_use_target, sign, *lay, B,
-                                                                                     batch, act_all, act_stride);
+                                                                                     batch, act_all, act_stride, shared_policy,
+                                                                                     critic_agent);
     return check_launch("k_td3_policy_grads");
   });
 }

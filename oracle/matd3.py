@@ -113,18 +113,51 @@ def td_combine(rew, done, q, gamma):
     return (np.asarray(rew, F32) + (F32(gamma) * (F32(1.0) - np.asarray(done, F32))) * np.asarray(q, F32)).astype(F32)
 
 
+def unique(group):
+    """The distinct members of a group (a shared group maps every name to ONE member)."""
+    seen, out = set(), []
+    for n in sorted(group):
+        if id(group[n]) not in seen:
+            seen.add(id(group[n]))
+            out.append(group[n])
+    return out
+
+
 class _Base(object):
-    def __init__(self, obs_dims, act_dims, lows, highs):
+    def __init__(self, obs_dims, act_dims, lows, highs, first=None):
         self.names = sorted(obs_dims)
+        self.first = first if first is not None else next(iter(obs_dims))   # a shared group is named after the FIRST key
         self.obs_dims, self.act_dims = dict(obs_dims), dict(act_dims)
         self.lows, self.highs = dict(lows), dict(highs)
         self.x_dim = sum(obs_dims.values()) + sum(act_dims.values())
 
-    def _policies(self, rng):
+    def _policies(self, rng, shared=False):
+        """PolicyGroup (policygroup.py:22-42): one Policy per name, or ONE for every name (equal spaces asserted, :32-34)."""
+        if shared:
+            f = self.first
+            assert all(self.obs_dims[n] == self.obs_dims[f] and self.act_dims[n] == self.act_dims[f] for n in self.names)
+            one = PolicyOracle(self.obs_dims[f], self.act_dims[f], self.lows[f], self.highs[f], rng)
+            return {n: one for n in self.names}
         return {n: PolicyOracle(self.obs_dims[n], self.act_dims[n], self.lows[n], self.highs[n], rng) for n in self.names}
 
-    def _critics(self, rng):
+    def _critics(self, rng, shared=False):
+        """CriticGroup (criticgroup.py:21-41)."""
+        if shared:
+            one = CriticOracle(self.x_dim, rng)
+            return {n: one for n in self.names}
         return {n: CriticOracle(self.x_dim, rng) for n in self.names}
+
+    def _critic_step(self, critics, x, y):
+        """CriticGroup.create_optimizers (criticgroup.py:87-106): per-name losses, or -- shared -- the first name's loss for every
+        name.  -> (losses by name, [(critic, grads)])."""
+        if len(unique(critics)) == 1 and len(self.names) > 1:
+            l, g, _ = critics[self.first].mse_grads(x, y[self.first])
+            return {n: l for n in self.names}, [(critics[self.first], g)]
+        losses, steps = {}, []
+        for n in self.names:
+            losses[n], g, _ = critics[n].mse_grads(x, y[n])
+            steps.append((critics[n], g))
+        return losses, steps
 
     def cat(self, d):
         return np.concatenate([np.asarray(d[n], F32).reshape(len(d[n]), -1) for n in self.names], axis=1)
@@ -138,6 +171,18 @@ class _Base(object):
         x = np.concatenate([self.cat(obs), self.cat(acts)], axis=1)
         losses, grads = {}, {}
         o_sum = sum(self.obs_dims.values())
+        if len(unique(policies)) == 1 and len(self.names) > 1:
+            # shared group (policygroup.py:129-135): ONE loss, -mean(value of the first name), reaching the shared variables
+            # through every name's action
+            q, dx = critics_of(self.first).dq_dx(x, np.full(B, -sign / B, F32), target=True)
+            loss = F32(-np.mean(sign * q.astype(np.float64)))
+            total, col = None, o_sum
+            for n in self.names:
+                K = self.act_dims[n]
+                g = policies[n].grads(caches[n], tanhs[n], dx[:, col:col + K])
+                total = g if total is None else [a + b for a, b in zip(total, g)]
+                col += K
+            return {n: loss for n in self.names}, {self.first: total}
         col = o_sum
         for n in self.names:
             q, dx = critics_of(n).dq_dx(x, np.full(B, -sign / B, F32), target=True)
@@ -151,11 +196,11 @@ class _Base(object):
 class MaTd3Oracle(_Base):
     GAMMA = 0.9   # matd3module.py:47
 
-    def __init__(self, obs_dims, act_dims, lows, highs, seed=0):
-        super().__init__(obs_dims, act_dims, lows, highs)
+    def __init__(self, obs_dims, act_dims, lows, highs, seed=0, shared_policy=False, shared_critic=False, first=None):
+        super().__init__(obs_dims, act_dims, lows, highs, first)
         rng = np.random.RandomState(seed)
-        self.policies = self._policies(rng)
-        self.critics = [self._critics(rng), self._critics(rng)]
+        self.policies = self._policies(rng, shared_policy)
+        self.critics = [self._critics(rng, shared_critic), self._critics(rng, shared_critic)]
 
     def predict(self, obs):
         return {n: self.policies[n].act(obs[n])[0] for n in self.names}
@@ -179,45 +224,37 @@ class MaTd3Oracle(_Base):
         steps), 'critic': {...}} like ``unflatten_map(self._train(feed))``."""
         y, _ = self.td_targets(rew, obs_n, done, z)
         x = np.concatenate([self.cat(obs), self.cat(act)], axis=1)
-        closs = {n: [] for n in self.names}
-        cgrads = [{}, {}]
+        closs, csteps = [], []
         for c in range(2):
-            for n in self.names:
-                l, g, _ = self.critics[c][n].mse_grads(x, y[n])
-                closs[n].append(l)
-                cgrads[c][n] = g
-        out = {"critic": {n: F32(np.mean(np.asarray(closs[n], F32))) for n in self.names}}
+            l, st = self._critic_step(self.critics[c], x, y)
+            closs.append(l)
+            csteps += st
+        out = {"critic": {n: F32(np.mean(np.asarray([closs[0][n], closs[1][n]], F32))) for n in self.names}}
         policy_step = bool(step) and step % 2 == 0
         if policy_step:
             plosses, pgrads = self._policy_step(self.policies, lambda n: self.critics[0][n], obs)
             out["actor"] = plosses
-        for c in range(2):
-            for n in self.names:
-                cr = self.critics[c][n]
-                cr.adam.step(cr.running.p, cgrads[c][n])
+        for cr, g in csteps:
+            cr.adam.step(cr.running.p, g)
         if policy_step:
-            for n in self.names:
-                po = self.policies[n]
-                po.adam.step(po.running.p, pgrads[n])
+            for n, g in pgrads.items():
+                self.policies[n].adam.step(self.policies[n].running.p, g)
         return out
 
     def run_updates(self):
-        for n in self.names:
-            self.policies[n].update_target()
-            self.critics[0][n].update_target()
-            self.critics[1][n].update_target()
+        for member in unique(self.policies) + unique(self.critics[0]) + unique(self.critics[1]):
+            member.update_target()
 
 
 class ComaOracle(_Base):
     GAMMA = 0.95   # comamodule.py:59
 
-    def __init__(self, obs_dims, act_dims, lows, highs, seed=0, first=None):
-        super().__init__(obs_dims, act_dims, lows, highs)
+    def __init__(self, obs_dims, act_dims, lows, highs, seed=0, first=None, shared_policy=False):
+        super().__init__(obs_dims, act_dims, lows, highs, first)
         rng = np.random.RandomState(seed)
-        self.best = self._policies(rng)
-        self.worst = self._policies(rng)
-        self.first = first if first is not None else next(iter(obs_dims))   # CriticGroup(shared=True): first key, insertion order
-        self.global_critic = CriticOracle(self.x_dim, rng)
+        self.best = self._policies(rng, shared_policy)
+        self.worst = self._policies(rng, shared_policy)
+        self.global_critic = CriticOracle(self.x_dim, rng)     # CriticGroup(shared=True): always (comamodule.py:36-39)
         self.personal = self._critics(rng)
 
     def predict(self, obs):
@@ -254,13 +291,12 @@ class ComaOracle(_Base):
         self.global_critic.adam.step(self.global_critic.running.p, gg)
         for n in self.names:
             self.personal[n].adam.step(self.personal[n].running.p, pcg[n])
-            self.best[n].adam.step(self.best[n].running.p, bg[n])
-            self.worst[n].adam.step(self.worst[n].running.p, wg[n])
+        for group, grads in ((self.best, bg), (self.worst, wg)):
+            for n, g in grads.items():
+                group[n].adam.step(group[n].running.p, g)
         return out
 
     def run_updates(self):
         self.global_critic.update_target()
-        for n in self.names:
-            self.personal[n].update_target()
-            self.best[n].update_target()
-            self.worst[n].update_target()
+        for member in unique(self.personal) + unique(self.best) + unique(self.worst):
+            member.update_target()

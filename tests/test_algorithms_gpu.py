@@ -7,17 +7,20 @@ import pytest
 import torch
 
 from oracle.matd3 import ComaOracle, MaTd3Oracle
-from tests.test_oracle_matd3 import ACT, HIGH, LOW, NAMES, OBS, make_batch
+from tests.test_oracle_matd3 import ACT, EQ_ACT, EQ_HIGH, EQ_LOW, EQ_OBS, HIGH, LOW, NAMES, OBS, make_batch
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
-def spaces():
+def spaces(OBS=OBS, ACT=ACT, LOW=LOW, HIGH=HIGH):
     from maddpg_b200.spaces import Box, Dict
     obs = Dict({n: Box(-np.inf, np.inf, (OBS[n],)) for n in NAMES})
     act = Dict({n: Box(np.full(ACT[n], LOW[n], np.float32), np.full(ACT[n], HIGH[n], np.float32), (ACT[n],)) for n in NAMES})
     return obs, act
+
+
+EQ = (EQ_OBS, EQ_ACT, EQ_LOW, EQ_HIGH)
 
 
 def load_policy(core, o_group, names):
@@ -150,6 +153,73 @@ def test_coma_train_steps_match_oracle(B):
         params_close(alg.personal, _lib.NET_TARGET_Q, j, o.personal[n].target.p, "personal target " + n)
 
 
+@pytest.mark.parametrize("shared_policy,shared_critic", [(True, False), (False, True), (True, True)])
+def test_matd3_shared_groups_match_oracle(shared_policy, shared_critic):
+    """PolicyGroup / CriticGroup(shared=True): one member (the first name's), one loss (policygroup.py:129-135,
+    criticgroup.py:94-100)."""
+    from maddpg_b200 import _lib
+    from maddpg_b200.algorithms import MaTd3
+    B = 192
+    o = MaTd3Oracle(*EQ, seed=21, shared_policy=shared_policy, shared_critic=shared_critic, first=NAMES[0])
+    alg = MaTd3(*spaces(*EQ), shared_policy=shared_policy, shared_critic=shared_critic, seed=7)
+    f = alg.names.index(NAMES[0])
+    assert alg.sp == (f if shared_policy else -1) and alg.sc == (f if shared_critic else -1)
+    load_policy(alg.policies, o.policies, o.names)
+    for c in range(2):
+        load_critic(alg.critics[c], o.critics[c], o.names)
+    for step in (2, 3, 4):
+        obs, act, rew, obs_n, done, z = make_batch(B, 300 + step, *EQ)
+        want = o.train_step(obs, act, rew, obs_n, done, step=step, z=z)
+        got = alg.train_step(obs, act, rew, obs_n, done, step=step, noise=z)
+        for key in want:
+            losses_close(got[key], want[key], "step %d %s" % (step, key))
+        o.run_updates()
+        alg.run_updates()
+    for j, n in enumerate(o.names):
+        if not shared_policy or j == f:
+            params_close(alg.policies, _lib.NET_P, j, o.policies[n].running.p, "policy " + n)
+            params_close(alg.policies, _lib.NET_TARGET_P, j, o.policies[n].target.p, "target policy " + n)
+        if not shared_critic or j == f:
+            params_close(alg.critics[1], _lib.NET_Q, j, o.critics[1][n].running.p, "critic " + n)
+    t = alg.policies.adam_t.cpu().tolist()
+    assert [t[2 * j] for j in range(3)] == ([2 if j == f else 0 for j in range(3)] if shared_policy else [2, 2, 2])
+    tc = alg.critics[0].adam_t.cpu().tolist()
+    assert [tc[2 * j + 1] for j in range(3)] == ([3 if j == f else 0 for j in range(3)] if shared_critic else [3, 3, 3])
+    # predictions of a shared policy: the same net on every name's observation
+    obs = make_batch(B, 998, *EQ)[0]
+    for j, n in enumerate(o.names):
+        src = f if shared_policy else j
+        o.policies[n].running.p = alg.policies.get_weights(src, _lib.NET_P)
+    want_a, got_a = o.predict(obs), alg.predict(obs, noisy=False)
+    for n in o.names:
+        np.testing.assert_allclose(got_a[n].reshape(B, -1), want_a[n], rtol=RTOL, atol=2e-6)
+
+
+def test_coma_shared_policy_matches_oracle():
+    from maddpg_b200 import _lib
+    from maddpg_b200.algorithms import Coma
+    B = 160
+    o = ComaOracle(*EQ, seed=22, first=NAMES[0], shared_policy=True)
+    alg = Coma(*spaces(*EQ), shared_policy=True, seed=8)
+    load_policy(alg.best, o.best, o.names)
+    load_policy(alg.worst, o.worst, o.names)
+    load_critic(alg.personal, o.personal, o.names)
+    load_critic(alg.global_critic, {n: o.global_critic for n in o.names}, o.names)
+    for step in (1, 2):
+        obs, act, rew, obs_n, done, _ = make_batch(B, 400 + step, *EQ)
+        want = o.train_step(obs, act, rew, obs_n, done, step=step)
+        got = alg.train_step(obs, act, rew, obs_n, done, step=step)
+        losses_close(got["critic"], want["critic"], "step %d critic" % step)
+        losses_close(got["actor"], want["actor"], "step %d actor" % step)
+        o.run_updates()
+        alg.run_updates()
+    f = alg.shared
+    params_close(alg.best, _lib.NET_P, f, o.best[NAMES[0]].running.p, "shared best policy")
+    params_close(alg.worst, _lib.NET_P, f, o.worst[NAMES[0]].running.p, "shared worst policy")
+    with pytest.raises(AssertionError):
+        Coma(*spaces(), shared_policy=True)     # unequal spaces (policygroup.py:32-34)
+
+
 def test_save_load_round_trip_and_refusals(tmp_path):
     from maddpg_b200.algorithms import Coma, DictReplayBuffer, MaTd3
     a = MaTd3(*spaces(), seed=4)
@@ -165,7 +235,7 @@ def test_save_load_round_trip_and_refusals(tmp_path):
     for n in la["critic"]:
         assert float(la["critic"][n]) == pytest.approx(float(lb["critic"][n]), rel=1e-6)
     with pytest.raises(NotImplementedError):
-        MaTd3(*spaces(), shared_policy=True)
+        MaTd3(*spaces(), normalize={"observation": True})
     with pytest.raises(NotImplementedError):
         Coma(*spaces(), normalize={"reward": True})
     # the fork's dict replay (common/replaybuffer.py): ring overwrite and dict-of-lists samples

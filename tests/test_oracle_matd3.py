@@ -14,7 +14,12 @@ LOW = {"b_agent": -1.0, "a_agent": -2.0, "c_agent": 0.0}
 HIGH = {"b_agent": 1.0, "a_agent": 2.0, "c_agent": 3.0}
 
 
-def make_batch(B, seed):
+# equal spaces: what a shared policy group needs (policygroup.py:32-34)
+EQ_OBS, EQ_ACT = {n: 6 for n in NAMES}, {n: 2 for n in NAMES}
+EQ_LOW, EQ_HIGH = {n: -1.0 for n in NAMES}, {n: 3.0 for n in NAMES}
+
+
+def make_batch(B, seed, OBS=OBS, ACT=ACT, LOW=LOW, HIGH=HIGH):
     rng = np.random.RandomState(seed)
     obs = {n: rng.randn(B, OBS[n]).astype(np.float32) for n in NAMES}
     obs_n = {n: rng.randn(B, OBS[n]).astype(np.float32) for n in NAMES}
@@ -158,6 +163,36 @@ def test_coma_losses_and_gradients_match_autograd():
     big = np.abs(g) > 1e-4
     assert big.any() and np.all(np.sign(moved[big]) == -np.sign(g[big]))
     np.testing.assert_allclose(np.abs(moved[big]), 1e-4, rtol=1e-2)
+
+
+def test_shared_groups_have_one_loss_through_every_action():
+    """PolicyGroup / CriticGroup with shared=True (policygroup.py:26-37, 54-70, 129-135; criticgroup.py:24-34, 48-66, 94-100)."""
+    o = MaTd3Oracle(EQ_OBS, EQ_ACT, EQ_LOW, EQ_HIGH, seed=8, shared_policy=True, shared_critic=True, first="b_agent")
+    assert len({id(p) for p in o.policies.values()}) == 1 and len({id(c) for c in o.critics[1].values()}) == 1
+    obs, act, rew, obs_n, done, z = make_batch(36, 4, EQ_OBS, EQ_ACT, EQ_LOW, EQ_HIGH)
+    f = "b_agent"
+    y, _ = o.td_targets(rew, obs_n, done, z)
+    x = torch.cat([tcat(o, obs), tcat(o, act)], dim=1)
+    # the shared critic regresses on the first name's targets only
+    p = tparams(o.critics[0][f].running, grad=True)
+    loss = torch.mean((tmlp(p, x)[:, 0] - torch.tensor(y[f].astype(np.float64))) ** 2)
+    loss.backward()
+    losses, steps = o._critic_step(o.critics[0], x.numpy().astype(np.float32), y)
+    assert len(steps) == 1 and all(abs(losses[n] - loss.item()) <= 2e-5 * max(1.0, loss.item()) for n in NAMES)
+    grads_close(steps[0][1], p)
+    # the shared policy: one loss, gradients through every name's action slice
+    ps = tparams(o.policies[f].running, grad=True)
+    a = {m: tact(o.policies[m], ps, obs[m]) for m in o.names}
+    xa = torch.cat([tcat(o, obs), tcat(o, a)], dim=1)
+    ploss = -torch.mean(tmlp(tparams(o.critics[0][f].target), xa))
+    ploss.backward()
+    pl, pg = o._policy_step(o.policies, lambda n: o.critics[0][n], obs)
+    assert list(pg) == [f] and all(abs(pl[n] - ploss.item()) <= 2e-5 * max(1.0, abs(ploss.item())) for n in NAMES)
+    grads_close(pg[f], ps)
+    t_before = o.policies[f].adam.t
+    out = o.train_step(obs, act, rew, obs_n, done, step=2, z=z)
+    assert o.policies[f].adam.t == t_before + 1 and o.critics[0][f].adam.t == 1     # ONE optimizer step per shared member
+    assert len(set(float(v) for v in out["actor"].values())) == 1
 
 
 @pytest.mark.parametrize("cls", [MaTd3Oracle, ComaOracle])
