@@ -11,10 +11,13 @@
 // The critic step itself (Critic.create_optimizer, critic.py:78-88: mse(values - target)) is mdp_critic_grads, and the Adam step
 // is mdp_clip_adam_polyak with grad_clip = 0 (grad_norm_clipping=None, tf_util.py:171-175) -- unchanged kernels.
 //
-// Every kernel owns a tile of TM batch rows per CTA and carries it through the whole 3-layer MLP(s) in shared memory (the streaming
-// tiles of mdp_mlp.cuh: W chunks staged through shared memory, FFMA2 inner loops); grid.y = agent.
+// Every kernel owns a tile of TM batch rows per CTA and carries it through the whole 3-layer MLP(s) in shared memory (the tiles
+// of mdp_mlp.cuh, FFMA2 inner loops); grid.y = agent.  The fork's 64-unit nets stay resident in shared memory for the whole
+// kernel (RES: one load per CTA, a critic + a policy + both transposed W2 for the gradient kernel); wider nets stream their
+// weights through a staging chunk.
 #include "mdp_mlp.cuh"
 
+#include <algorithm>
 #include <type_traits>
 
 namespace mdp {
@@ -37,15 +40,15 @@ __device__ __forceinline__ float rescale(float t, float scale, float shift) { re
 // ---------------------------------------------------------------------------------------------
 // tanh-policy actions of every agent.  grid = (ceil(B/TM), n_agents)
 // ---------------------------------------------------------------------------------------------
-template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_td3_policy_act(CoreDev C, Td3Head H, int use_target, int B, const float* __restrict__ obs,
+template <int U, int TM, bool RES>
+__global__ void __launch_bounds__(NT) k_td3_policy_act(CoreDev C, Td3Head H, int max_net, int use_target, int B, const float* __restrict__ obs,
                                                        int obs_stride, const float* __restrict__ noise, int noise_stride,
                                                        float noise_std, float noise_clip, uint64_t seed, uint64_t counter,
                                                        float* __restrict__ act, int act_stride, int shared_agent) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);   // RES: the whole net stays in shared memory; else a staging chunk
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * (U + 4));
   float* sH2 = sm.take(TM * (U + 4));
@@ -53,11 +56,12 @@ __global__ void __launch_bounds__(NT) k_td3_policy_act(CoreDev C, Td3Head H, int
   const int i = blockIdx.y;
   const AgentDev& ag = C.agents[i];
   // PolicyGroup(shared=True): one policy serves every name (policygroup.py:26-37, 54-70)
-  const MlpW w = C.agents[shared_agent >= 0 ? shared_agent : i].net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
+  MlpW w = C.agents[shared_agent >= 0 ? shared_agent : i].net[use_target ? MDP_NET_TARGET_P : MDP_NET_P];
+  if (RES) w = load_net<U>(G, sW, w);  // visible after the first barrier inside layer1
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   XSrc xs = make_xsrc(obs + ag.obs_off, obs_stride, ag.obs_dim);
-  forward_hidden<U, TM, false>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+  forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
   actor_head<U, TM>(G, sH2, w, sL);
   const int K = ag.act_dim;
   for (int idx = threadIdx.x; idx < nrows * K; idx += NT) {
@@ -75,8 +79,8 @@ __global__ void __launch_bounds__(NT) k_td3_policy_act(CoreDev C, Td3Head H, int
 // ---------------------------------------------------------------------------------------------
 // q_j = min_c Q_{c,j}([x | act]) and y_j = rew_j + gamma (1 - done_j) q_j.  grid = (ceil(B/TM), n_agents)
 // ---------------------------------------------------------------------------------------------
-template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_td3_q_target(CoreDev Ca, CoreDev Cb, int n_critics, int use_target, mdp_ring_layout L, int B,
+template <int U, int TM, bool RES>
+__global__ void __launch_bounds__(NT) k_td3_q_target(CoreDev Ca, CoreDev Cb, int max_net, int n_critics, int use_target, mdp_ring_layout L, int B,
                                                      const float* __restrict__ batch, int obs_col0, const float* __restrict__ act,
                                                      int act_stride, const float* __restrict__ rew_override,
                                                      const float* __restrict__ rew_minus, int shared_agent, float gamma,
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(NT) k_td3_q_target(CoreDev Ca, CoreDev Cb, int
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * (U + 4));
   float* sH2 = sm.take(TM * (U + 4));
@@ -97,8 +101,9 @@ __global__ void __launch_bounds__(NT) k_td3_q_target(CoreDev Ca, CoreDev Cb, int
   xs.g1 = act; xs.ld1 = act_stride; xs.n1 = L.act_sum;
   for (int c = 0; c < n_critics; ++c) {
     const AgentDev& me = (c ? Cb : Ca).agents[shared_agent >= 0 ? shared_agent : j];  // shared group: one critic serves every name
-    const MlpW w = me.net[use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
-    forward_hidden<U, TM, false>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
+    MlpW w = me.net[use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
+    if (RES) w = load_net<U>(G, sW, w);  // the previous user of sW finished before the barrier that ends critic_head
+    forward_hidden<U, TM, RES>(G, xs, w, row0, nrows, sX, sW, sH1, sH2);
     critic_head<U, TM>(G, sH2, w, sQ + c * TM);
   }
   if (threadIdx.x < nrows) {
@@ -122,8 +127,8 @@ __global__ void __launch_bounds__(NT) k_td3_q_target(CoreDev Ca, CoreDev Cb, int
 // (the other policies' current actions: the loss of policy j is differentiated wrt policy j's variables only, policy.py:95-99).
 // grid = (ceil(B/TM), n_agents)
 // ---------------------------------------------------------------------------------------------
-template <int U, int TM>
-__global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq, Td3Head H, int critic_use_target, float sign,
+template <int U, int TM, bool RES>
+__global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq, Td3Head H, int max_net, int critic_use_target, float sign,
                                                          mdp_ring_layout L, int B, const float* __restrict__ batch,
                                                          const float* __restrict__ act_all, int act_stride, int shared_policy,
                                                          int critic_agent) {
@@ -131,7 +136,10 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
   constexpr int HP = U + 4;
   const Grp G{(int)threadIdx.x, 0};
   SmemCarve sm(smem_raw);
-  float* sW = sm.take(KC * U);
+  float* sW = sm.take(RES ? max_net : KC * U);   // RES: critic net ; else staging chunk
+  float* sWp = sm.take(RES ? max_net : 4);       // RES: policy net
+  float* sWT = sm.take(RES ? U * U : 4);         // RES: critic W2^T
+  float* sWTp = sm.take(RES ? U * U : 4);        // RES: policy W2^T
   float* sX = sm.take(TM * XP);
   float* sH1 = sm.take(TM * HP);
   float* sH2 = sm.take(TM * HP);
@@ -147,16 +155,22 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
   // -mean(value of the group's first name) and reaches the shared variables through EVERY name's action (policygroup.py:129-135)
   const int pj = shared_policy >= 0 ? shared_policy : j, cj = critic_agent >= 0 ? critic_agent : j;
   const bool lead = shared_policy < 0 || j == 0;   // step counter and loss are the group's, counted once
-  const MlpW pw = Cp.agents[pj].net[MDP_NET_P];
-  const MlpW qw = Cq.agents[cj].net[critic_use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
+  MlpW pw = Cp.agents[pj].net[MDP_NET_P];
+  MlpW qw = Cq.agents[cj].net[critic_use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
   const MlpG& pg = Cp.agents[pj].grad[0];
+  if (RES) {
+    load_wT_rows<U>(G, sWT, qw.W2, 0, U);
+    load_wT_rows<U>(G, sWTp, pw.W2, 0, U);
+    qw = load_net<U>(G, sW, qw);
+    pw = load_net<U>(G, sWp, pw);
+  }
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
   const int R = L.row_stride, K = me.act_dim;
   if (blockIdx.x == 0 && threadIdx.x == 0 && lead) Cp.adam_t[2 * pj + 0] += 1;
 
   XSrc xp = make_xsrc(batch + me.obs_off, R, me.obs_dim);
-  forward_hidden<U, TM, false>(G, xp, pw, row0, nrows, sX, sW, sP1, sP2);
+  forward_hidden<U, TM, RES>(G, xp, pw, row0, nrows, sX, sW, sP1, sP2);
   actor_head<U, TM>(G, sP2, pw, sT);
   const float scale = H.scale[j], shift = H.shift[j];
   for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
@@ -171,7 +185,7 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
   XSrc xq = make_xsrc(batch, R, L.obs_sum);
   xq.g1 = act_all; xq.ld1 = act_stride; xq.n1 = L.act_sum;
   xq.s_over = sA; xq.over_ld = KPAD; xq.over_c0 = a_col0; xq.over_n = K;
-  forward_hidden<U, TM, false>(G, xq, qw, row0, nrows, sX, sW, sH1, sH2);
+  forward_hidden<U, TM, RES>(G, xq, qw, row0, nrows, sX, sW, sH1, sH2);
   critic_head<U, TM>(G, sH2, qw, sQ);
   if (threadIdx.x < 32) {
     const int r = threadIdx.x;
@@ -186,7 +200,7 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
     sH2[r * HP + u] = (h > 0.f && r < nrows) ? dq * qw.W3[u] : 0.f;
   }
   __syncthreads();
-  backward_hidden<U, TM, false>(G, xq, qw, nullptr, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 of the critic -> sH1
+  backward_hidden<U, TM, RES>(G, xq, qw, sWT, nullptr, row0, nrows, sX, sW, sH1, sH2);  // dz1 of the critic -> sH1
   for (int idx = threadIdx.x; idx < TM * K; idx += NT) {
     const int r = idx / K, a = idx - r * K;
     const float* w1row = qw.W1 + (size_t)(a_col0 + a) * U;
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
     sP2[r * HP + u] = s;
   }
   __syncthreads();
-  backward_hidden<U, TM, false>(G, xp, pw, nullptr, &pg, row0, nrows, sX, sW, sP1, sP2);
+  backward_hidden<U, TM, RES>(G, xp, pw, sWTp, &pg, row0, nrows, sX, sW, sP1, sP2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -241,17 +255,42 @@ static int td3_smem(Kern kern, size_t smem) {
   return MDP_OK;
 }
 
-static size_t td3_floats(int U, int TM, int n_act, int extra) {
-  return ((size_t)KC * U + (size_t)TM * XP + (size_t)n_act * TM * (U + 4) + extra + 128) * sizeof(float);
+// Launch plan, like the MADDPG kernels' (mdp_train.cu make_plan): 64-unit nets small enough that a critic, a policy and their two
+// transposed W2 fit one CTA's shared memory stay resident there (RES); wider nets stream their weights in KC-row chunks.
+struct Td3Plan {
+  bool res;
+  int max_net;
+};
+
+static Td3Plan td3_plan(const mdp_core* c) {
+  Td3Plan p;
+  int mx = 0;
+  for (int i = 0; i < c->cfg.n_agents; ++i)
+    for (int k = 0; k < 4; ++k) mx = std::max(mx, net_floats_padded(c->lay.net_in[i][k], c->cfg.num_units, c->lay.net_out[i][k]));
+  p.max_net = mx;
+  p.res = c->cfg.num_units == 64 && (size_t)(2 * mx + 2 * 64 * 64) * 4 <= 120 * 1024;
+  return p;
 }
 
+// bytes of dynamic shared memory: weight buffers + transposed W2 copies + x chunk + n_act activation tiles + extras
+static size_t td3_floats(int U, int TM, const Td3Plan& p, int n_wbuf, int n_wT, int n_act, int extra) {
+  size_t f = (size_t)(p.res ? p.max_net : KC * U) + (size_t)(n_wbuf - 1) * (p.res ? p.max_net : 4);
+  f += (size_t)n_wT * (p.res ? U * U : 4);
+  f += (size_t)TM * XP + (size_t)n_act * TM * (U + 4) + extra + 128;
+  return f * sizeof(float);
+}
+
+template <int V> using IC = std::integral_constant<int, V>;
+template <bool V> using BC = std::integral_constant<bool, V>;
+
 template <typename F>
-static int td3_dispatch(int U, int rows, F&& f) {
+static int td3_dispatch(int U, int rows, const Td3Plan& p, F&& f) {
   const bool small = rows <= 2048;  // 16-row tiles double the CTA count for the reference's batch of 1024
-  if (U == 64) return small ? f(std::integral_constant<int, 64>{}, std::integral_constant<int, 16>{})
-                            : f(std::integral_constant<int, 64>{}, std::integral_constant<int, 32>{});
-  if (U == 128) return small ? f(std::integral_constant<int, 128>{}, std::integral_constant<int, 16>{})
-                             : f(std::integral_constant<int, 128>{}, std::integral_constant<int, 32>{});
+  if (U == 64) {
+    if (small) return p.res ? f(IC<64>{}, IC<16>{}, BC<true>{}) : f(IC<64>{}, IC<16>{}, BC<false>{});
+    return p.res ? f(IC<64>{}, IC<32>{}, BC<true>{}) : f(IC<64>{}, IC<32>{}, BC<false>{});
+  }
+  if (U == 128) return small ? f(IC<128>{}, IC<16>{}, BC<false>{}) : f(IC<128>{}, IC<32>{}, BC<false>{});
   return fail(MDP_ENOTSUP, "num_units %d: the MLP tiles are built for 64 and 128", U);
 }
 
@@ -310,13 +349,15 @@ extern "C" int mdp_td3_policy_act(mdp_core* c, int32_t use_target, int32_t B, co
   if ((rc = td3_check_shared(c, shared_agent, "mdp_td3_policy_act"))) return rc;
   const CoreDev d = core_dev_for_rollout(c);
   const Td3Head h = make_head(c, act_scale, act_shift);
-  return td3_dispatch(c->cfg.num_units, B, [&](auto u_, auto tm_) -> int {
+  const Td3Plan p = td3_plan(c);
+  return td3_dispatch(c->cfg.num_units, B, p, [&](auto u_, auto tm_, auto res_) -> int {
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
-    auto kern = k_td3_policy_act<U, TMv>;
-    const size_t smem = td3_floats(U, TMv, 2, TMv * KPAD);
+    constexpr bool RES = decltype(res_)::value;
+    auto kern = k_td3_policy_act<U, TMv, RES>;
+    const size_t smem = td3_floats(U, TMv, p, 1, 0, 2, TMv * KPAD);
     int rc2 = td3_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<dim3(cdiv(B, TMv), c->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(d, h, use_target, B, obs, obs_stride, noise,
+    kern<<<dim3(cdiv(B, TMv), c->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(d, h, p.max_net, use_target, B, obs, obs_stride, noise,
                                                                                 noise_stride, noise_std, noise_clip, seed, counter,
                                                                                 act, act_stride, shared_agent);
     return check_launch("k_td3_policy_act");
@@ -337,13 +378,15 @@ extern "C" int mdp_td3_q_target(mdp_core* ca, mdp_core* cb, int32_t use_target, 
   MDP_REQUIRE(batch && act && B > 0 && act_stride >= ca->act_sum && (q_out || y_out) && (obs_field == 0 || obs_field == 1) &&
                   shared_agent < ca->cfg.n_agents, "mdp_td3_q_target: bad argument");
   const CoreDev da = core_dev_for_rollout(ca), db = core_dev_for_rollout(cb ? cb : ca);
-  return td3_dispatch(ca->cfg.num_units, B, [&](auto u_, auto tm_) -> int {
+  const Td3Plan p = td3_plan(ca);
+  return td3_dispatch(ca->cfg.num_units, B, p, [&](auto u_, auto tm_, auto res_) -> int {
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
-    auto kern = k_td3_q_target<U, TMv>;
-    const size_t smem = td3_floats(U, TMv, 2, 2 * TMv);
+    constexpr bool RES = decltype(res_)::value;
+    auto kern = k_td3_q_target<U, TMv, RES>;
+    const size_t smem = td3_floats(U, TMv, p, 1, 0, 2, 2 * TMv);
     int rc2 = td3_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<dim3(cdiv(B, TMv), ca->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(da, db, cb ? 2 : 1, use_target, *lay, B, batch,
+    kern<<<dim3(cdiv(B, TMv), ca->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(da, db, p.max_net, cb ? 2 : 1, use_target, *lay, B, batch,
                                                                                  obs_field ? lay->nx_off : 0, act, act_stride,
                                                                                  rew_override, rew_minus, shared_agent, gamma, q_out,
                                                                                  y_out);
@@ -365,13 +408,15 @@ extern "C" int mdp_td3_policy_grads(mdp_core* policy, mdp_core* critic, int32_t 
   if ((rc = td3_check_shared(policy, shared_policy, "mdp_td3_policy_grads"))) return rc;
   const CoreDev dp = core_dev_for_rollout(policy), dq = core_dev_for_rollout(critic);
   const Td3Head h = make_head(policy, act_scale, act_shift);
-  return td3_dispatch(policy->cfg.num_units, B, [&](auto u_, auto tm_) -> int {
+  const Td3Plan p = td3_plan(policy);
+  return td3_dispatch(policy->cfg.num_units, B, p, [&](auto u_, auto tm_, auto res_) -> int {
     constexpr int U = decltype(u_)::value, TMv = decltype(tm_)::value;
-    auto kern = k_td3_policy_grads<U, TMv>;
-    const size_t smem = td3_floats(U, TMv, 4, 3 * TMv * KPAD + TMv);
+    constexpr bool RES = decltype(res_)::value;
+    auto kern = k_td3_policy_grads<U, TMv, RES>;
+    const size_t smem = td3_floats(U, TMv, p, 2, 2, 4, 3 * TMv * KPAD + TMv);
     int rc2 = td3_smem(kern, smem);
     if (rc2) return rc2;
-    kern<<<dim3(cdiv(B, TMv), policy->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(dp, dq, h, critic_use_target, sign, *lay, B,
+    kern<<<dim3(cdiv(B, TMv), policy->cfg.n_agents), NT, smem, (cudaStream_t)stream>>>(dp, dq, h, p.max_net, critic_use_target, sign, *lay, B,
                                                                                      batch, act_all, act_stride, shared_policy,
                                                                                      critic_agent);
     return check_launch("k_td3_policy_grads");

@@ -95,6 +95,41 @@ def test_matd3_train_steps_match_oracle(B):
     assert 0.15 < d.std() < 0.25
 
 
+def test_wide_observations_take_the_streaming_tiles():
+    """Nets too large to stay resident in shared memory (critic input 3 x 44 + 6 columns) stream their weights in chunks: the other
+    template branch of every csrc/mdp_td3.cu kernel, same arithmetic."""
+    from maddpg_b200.algorithms import Coma, MaTd3
+    W_OBS, W_ACT = {n: 44 for n in NAMES}, {n: 2 for n in NAMES}
+    W = (W_OBS, W_ACT, EQ_LOW, EQ_HIGH)
+    B = 80
+    o = MaTd3Oracle(*W, seed=31)
+    alg = MaTd3(*spaces(*W), seed=9)
+    load_policy(alg.policies, o.policies, o.names)
+    for c in range(2):
+        load_critic(alg.critics[c], o.critics[c], o.names)
+    for step in (1, 2):
+        obs, act, rew, obs_n, done, z = make_batch(B, 500 + step, *W)
+        want = o.train_step(obs, act, rew, obs_n, done, step=step, z=z)
+        got = alg.train_step(obs, act, rew, obs_n, done, step=step, noise=z)
+        for key in want:
+            losses_close(got[key], want[key], "wide step %d %s" % (step, key))
+    from maddpg_b200 import _lib
+    for j, n in enumerate(o.names):
+        params_close(alg.policies, _lib.NET_P, j, o.policies[n].running.p, "wide policy " + n)
+        params_close(alg.critics[0], _lib.NET_Q, j, o.critics[0][n].running.p, "wide critic " + n)
+    oc = ComaOracle(*W, seed=32, first=NAMES[0])
+    ac = Coma(*spaces(*W), seed=10)
+    load_policy(ac.best, oc.best, oc.names)
+    load_policy(ac.worst, oc.worst, oc.names)
+    load_critic(ac.personal, oc.personal, oc.names)
+    load_critic(ac.global_critic, {n: oc.global_critic for n in oc.names}, oc.names)
+    obs, act, rew, obs_n, done, _ = make_batch(B, 600, *W)
+    want = oc.train_step(obs, act, rew, obs_n, done)
+    got = ac.train_step(obs, act, rew, obs_n, done)
+    losses_close(got["critic"], want["critic"], "wide coma critic")
+    losses_close(got["actor"], want["actor"], "wide coma actor")
+
+
 def test_matd3_compute_loss_leaves_the_state_untouched_and_philox_noise_is_sane():
     from maddpg_b200.algorithms import MaTd3
     alg = MaTd3(*spaces(), seed=2)
