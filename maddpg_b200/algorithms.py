@@ -1,4 +1,5 @@
-"""The fork's dict-of-agents algorithms on the B200 kernels: ``MaTd3`` and ``Coma``.
+"""The fork's dict-of-agents algorithms on the B200 kernels: ``MaTd3`` and ``Coma``, plus the fork's own
+``Maddpg`` and the two inference-only classes built from the same pieces.
 
 Reference surface: maddpg/algorithms/multiagentalgbase.py:22-212 (``predict``, ``compute_values``, ``compute_loss``,
 ``train_step``, ``learn_generator``, ``learn``, ``save``, ``load``, ``run_updates``), maddpg/algorithms/matd3.py:11-81,
@@ -488,3 +489,92 @@ class Coma(MultiAgentAlgBase):
         self._adam(self.best, 0, sp)
         self._adam(self.worst, 0, sp)
         return out
+
+
+class Maddpg(MultiAgentAlgBase):
+    """maddpg/algorithms/maddpg.py:11-76 over MaddpgModule (maddpgmodule.py:19-127): the fork's own MADDPG -- tanh policies, one
+    critic group, TD actions from the target policies (no noise), policy loss through the critics' target nets, every group
+    steps on every train step.  ``hyperparameters`` is accepted and, like the reference (maddpg.py:19 replaces any given dict by
+    ``{}``), has no effect: gamma 0.95, learning rates 1e-4."""
+
+    GAMMA = 0.95
+
+    def __init__(self, observation_space, action_space, shared_policy=False, shared_critic=False, hyperparameters=None, **kw):
+        super().__init__(observation_space, action_space, **kw)
+        self.policies = self._group(0)
+        self.critics = self._group(1)
+        first = self.names.index(self.first)
+        self.sp = first if shared_policy else -1
+        self.sc = first if shared_critic else -1
+        self._check_shared()
+
+    def _predict_policies(self):
+        return self.policies
+
+    def _value_critics(self):
+        return self.critics
+
+    def _value_shared(self):
+        return self.sc
+
+    def run_updates(self):
+        self._polyak(self.policies, 1)
+        self._polyak(self.critics, 2)
+
+    def _train_step(self, rows, step, z, update):
+        B, L, sp, sc = rows.shape[0], self.layout, self.sp, self.sc
+        self._zero_stats()
+        if not update:
+            self._save_adam_t()
+        nx = rows[:, int(L.nx_off):]
+        a_n = self._policy_act(self.policies, nx, rows.stride(0), self._act_buf("a_next", B), use_target=True, shared=sp)  # :77
+        y = self._scratch(("y", B), (self.n, B))
+        self._q_target(self.critics, None, rows, 1, a_n, y_out=y, shared_agent=sc)                                       # :82-83, 113-118
+        self._critic_step(self.critics, sc, rows, y)                                                                    # :89-93
+        a = self._policy_act(self.policies, rows, rows.stride(0), self._act_buf("a_now", B), shared=sp)
+        self._policy_grads(self.policies, self.critics, rows, a, shared_policy=sp, critic_agent=sc if sc >= 0 else sp)   # :94-98
+        st = self._read_stats([self.policies, self.critics])
+        out = {"actor": {k: np.float32(st[0][sp if sp >= 0 else j, 1] / B) for j, k in enumerate(self.names)},
+               "critic": {k: np.float32(st[1][sc if sc >= 0 else j, 0] / B) for j, k in enumerate(self.names)}}
+        if not update:
+            self._discard_grads()
+            return out
+        self._adam(self.critics, 1, sc)
+        self._adam(self.policies, 0, sp)
+        return out
+
+
+class _Inference(MultiAgentAlgBase):
+    """MaddpgInference (maddpg/algorithms/maddpg.py:79-118) / ComaInference (coma.py:73-112): a policy group and ``predict`` only;
+    the other methods are the reference's ``...`` bodies (they return None)."""
+
+    def __init__(self, observation_space, action_space, shared_policy=False, normalize=None, **kw):
+        if normalize:
+            raise NotImplementedError("BatchNorm normalisation is not built (maddpg_b200/algorithms.py header)")
+        super().__init__(observation_space, action_space, **kw)
+        self.policies = self._group(0)
+        self.sp = self.names.index(self.first) if shared_policy else -1
+        self._check_shared()
+
+    def _predict_policies(self):
+        return self.policies
+
+    def compute_values(self, observations):
+        return None
+
+    def compute_loss(self, *args, **kw):
+        return None
+
+    def train_step(self, *args, **kw):
+        return None
+
+    def run_updates(self):
+        return None
+
+
+class MaddpgInference(_Inference):
+    pass
+
+
+class ComaInference(_Inference):
+    pass

@@ -300,3 +300,43 @@ class ComaOracle(_Base):
         self.global_critic.update_target()
         for member in unique(self.personal) + unique(self.best) + unique(self.worst):
             member.update_target()
+
+
+class MaddpgOracle(_Base):
+    """The fork's third spelling of MADDPG (maddpg/modules/maddpgmodule.py:52-111, maddpg/algorithms/maddpg.py:11-76): tanh
+    policies, ONE critic group, TD actions from the TARGET policies without noise (``.target_actions``, :77), policy loss
+    through the critics' TARGET nets (:96-97), both groups step on every train step, polyak 5e-3.  ``gamma`` is
+    ``hyperparameters.get('gamma', 0.95)`` -- and the constructor's ``{} if hyperparameters else hyperparameters`` (maddpg.py:19)
+    turns any given dict into ``{}`` (and dies on None), so it is always 0.95."""
+    GAMMA = 0.95
+
+    def __init__(self, obs_dims, act_dims, lows, highs, seed=0, shared_policy=False, shared_critic=False, first=None):
+        super().__init__(obs_dims, act_dims, lows, highs, first)
+        rng = np.random.RandomState(seed)
+        self.policies = self._policies(rng, shared_policy)
+        self.critics = self._critics(rng, shared_critic)
+
+    def predict(self, obs):
+        return {n: self.policies[n].act(obs[n])[0] for n in self.names}
+
+    def compute_values(self, obs):
+        x = np.concatenate([self.cat(obs), self.cat(self.predict(obs))], axis=1)
+        return {n: self.critics[n].q(x, target=True)[0] for n in self.names}
+
+    def train_step(self, obs, act, rew, obs_n, done, step=None):
+        a_n = {n: self.policies[n].act(obs_n[n], target=True)[0] for n in self.names}
+        xn = np.concatenate([self.cat(obs_n), self.cat(a_n)], axis=1)
+        y = {n: td_combine(np.ravel(rew[n]), np.ravel(done[n]), self.critics[n].q(xn, target=True)[0], self.GAMMA)
+             for n in self.names}
+        x = np.concatenate([self.cat(obs), self.cat(act)], axis=1)
+        closs, csteps = self._critic_step(self.critics, x, y)
+        plosses, pgrads = self._policy_step(self.policies, lambda n: self.critics[n], obs)
+        for cr, g in csteps:
+            cr.adam.step(cr.running.p, g)
+        for n, g in pgrads.items():
+            self.policies[n].adam.step(self.policies[n].running.p, g)
+        return {"actor": plosses, "critic": closs}
+
+    def run_updates(self):
+        for member in unique(self.policies) + unique(self.critics):
+            member.update_target()

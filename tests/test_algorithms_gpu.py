@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.matd3 import ComaOracle, MaTd3Oracle
+from oracle.matd3 import ComaOracle, MaddpgOracle, MaTd3Oracle
 from tests.test_oracle_matd3 import ACT, EQ_ACT, EQ_HIGH, EQ_LOW, EQ_OBS, HIGH, LOW, NAMES, OBS, make_batch
 
 pytestmark = pytest.mark.gpu
@@ -253,6 +253,43 @@ def test_coma_shared_policy_matches_oracle():
     params_close(alg.worst, _lib.NET_P, f, o.worst[NAMES[0]].running.p, "shared worst policy")
     with pytest.raises(AssertionError):
         Coma(*spaces(), shared_policy=True)     # unequal spaces (policygroup.py:32-34)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_fork_maddpg_and_inference_classes_match_oracle(shared):
+    """maddpg/algorithms/maddpg.py:11-118, coma.py:73-112."""
+    from maddpg_b200 import _lib
+    from maddpg_b200.algorithms import ComaInference, Maddpg, MaddpgInference
+    B = 128
+    dims = EQ if shared else (OBS, ACT, LOW, HIGH)
+    o = MaddpgOracle(*dims, seed=41, shared_policy=shared, shared_critic=shared, first=NAMES[0])
+    alg = Maddpg(*spaces(*dims), shared_policy=shared, shared_critic=shared, hyperparameters={"gamma": 0.5}, seed=11)
+    assert alg.GAMMA == 0.95      # the reference discards the given hyperparameters (maddpg.py:19)
+    load_policy(alg.policies, o.policies, o.names)
+    load_critic(alg.critics, o.critics, o.names)
+    for step in (1, 2, 3):
+        obs, act, rew, obs_n, done, _ = make_batch(B, 700 + step, *dims)
+        want = o.train_step(obs, act, rew, obs_n, done, step=step)
+        got = alg.train_step(obs, act, rew, obs_n, done, step=step)
+        losses_close(got["critic"], want["critic"], "step %d critic" % step)
+        losses_close(got["actor"], want["actor"], "step %d actor" % step)
+        o.run_updates()
+        alg.run_updates()
+    f = alg.names.index(NAMES[0])
+    for j, n in enumerate(o.names):
+        if not shared or j == f:
+            params_close(alg.policies, _lib.NET_P, j, o.policies[n].running.p, "policy " + n)
+            params_close(alg.policies, _lib.NET_TARGET_P, j, o.policies[n].target.p, "target policy " + n)
+            params_close(alg.critics, _lib.NET_Q, j, o.critics[n].running.p, "critic " + n)
+    # the inference-only classes: predict() of a policy group, everything else returns None like the reference's `...` bodies
+    obs = make_batch(B, 997, *dims)[0]
+    for cls in (MaddpgInference, ComaInference):
+        inf = cls(*spaces(*dims), shared_policy=shared, seed=12)
+        for j, n in enumerate(o.names):
+            inf.policies.set_weights(j, _lib.NET_P, alg.policies.get_weights(f if shared else j, _lib.NET_P))
+        a, b = inf.predict(obs, noisy=False), alg.predict(obs, noisy=False)
+        assert all(np.array_equal(a[n], b[n]) for n in o.names)
+        assert inf.train_step(obs, obs, obs, obs, obs) is None and inf.compute_values(obs) is None and inf.run_updates() is None
 
 
 def test_save_load_round_trip_and_refusals(tmp_path):

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.matd3 import ComaOracle, MaTd3Oracle, NOISE_CLIP, NOISE_STD, POLYAK
+from oracle.matd3 import ComaOracle, MaddpgOracle, MaTd3Oracle, NOISE_CLIP, NOISE_STD, POLYAK
 
 NAMES = ["b_agent", "a_agent", "c_agent"]      # insertion order differs from sorted order on purpose
 OBS = {"b_agent": 7, "a_agent": 5, "c_agent": 6}
@@ -193,6 +193,27 @@ def test_shared_groups_have_one_loss_through_every_action():
     out = o.train_step(obs, act, rew, obs_n, done, step=2, z=z)
     assert o.policies[f].adam.t == t_before + 1 and o.critics[0][f].adam.t == 1     # ONE optimizer step per shared member
     assert len(set(float(v) for v in out["actor"].values())) == 1
+
+
+def test_fork_maddpg_targets_and_losses_match_autograd():
+    o = MaddpgOracle(OBS, ACT, LOW, HIGH, seed=9)
+    obs, act, rew, obs_n, done, _ = make_batch(44, 6)
+    a_n = {n: tact(o.policies[n], tparams(o.policies[n].target), obs_n[n]) for n in o.names}     # target policies, no noise
+    xn = torch.cat([tcat(o, obs_n), tcat(o, a_n)], dim=1)
+    x = torch.cat([tcat(o, obs), tcat(o, act)], dim=1)
+    want_c, want_a = {}, {}
+    for n in o.names:
+        y = torch.tensor(rew[n][:, 0].astype(np.float64)) + 0.95 * (1 - torch.tensor(done[n][:, 0].astype(np.float64))) * \
+            tmlp(tparams(o.critics[n].target), xn)[:, 0]
+        want_c[n] = torch.mean((tmlp(tparams(o.critics[n].running), x)[:, 0] - y) ** 2).item()
+        a = {m: tact(o.policies[m], tparams(o.policies[m].running), obs[m]) for m in o.names}
+        xa = torch.cat([tcat(o, obs), tcat(o, a)], dim=1)
+        want_a[n] = -torch.mean(tmlp(tparams(o.critics[n].target), xa)).item()
+    out = o.train_step(obs, act, rew, obs_n, done)
+    for n in o.names:
+        assert abs(out["critic"][n] - want_c[n]) <= 5e-5 * max(1.0, abs(want_c[n]))
+        assert abs(out["actor"][n] - want_a[n]) <= 5e-5 * max(1.0, abs(want_a[n]))
+    assert o.policies["a_agent"].adam.t == 1 and o.critics["a_agent"].adam.t == 1
 
 
 @pytest.mark.parametrize("cls", [MaTd3Oracle, ComaOracle])
