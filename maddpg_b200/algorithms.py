@@ -16,7 +16,8 @@ a handful of grouped launches (grid.y = agent) from csrc/mdp_td3.cu plus the MAD
 
 Every gradient of a step is taken before any Adam step (one ``session.run`` in the reference).  Agents are ordered by sorted
 name (``U.concat_map``, tf_util.py:53-55).  ``shared_policy`` / ``shared_critic`` groups keep one member -- the first name's --
-with the reference's one-loss semantics (policygroup.py:129-135, criticgroup.py:94-100); the BatchNorm ``normalize`` option raises.  All arithmetic runs in libmaddpg_b200.so; there is no PyTorch or CPU fallback.
+with the reference's one-loss semantics (policygroup.py:129-135, criticgroup.py:94-100); the ``normalize`` option is the
+inference-mode BatchNorm the modules apply (a constant gain, see BATCH_NORM_INFERENCE).  All arithmetic runs in libmaddpg_b200.so; there is no PyTorch or CPU fallback.
 """
 import ctypes as C
 from collections import namedtuple
@@ -34,6 +35,11 @@ UNITS = 64               # policy.py:33, critic.py:31
 LEARNING_RATE = 1e-4     # policygroup.py:127, criticgroup.py:91
 TARGET_POLYAK = 5e-3     # update_targets(5e-3): matd3module.py:104-107, comamodule.py:137-149
 NOISE_STD, NOISE_CLIP = 0.2, 0.5   # policy.py:72-73
+# ``normalize``: snt.BatchNormV2()(x, is_training=False) (matd3module.py:65-74, comamodule.py:71-80, maddpgmodule.py:67-76).  The
+# modules only ever call it in inference mode and hand none of its variables to an optimizer, so the moving mean stays 0, the moving
+# variance 1 and the offset 0 (Sonnet's default has no learned scale): y = x * rsqrt(1 + eps), eps = 1e-3.  Applied while the feed
+# dicts are packed into the joint rows.
+BATCH_NORM_INFERENCE = np.float32(1.0) / np.sqrt(np.float32(1.0) + np.float32(1e-3))
 
 
 def _spaces(space):
@@ -45,8 +51,11 @@ class MultiAgentAlgBase(object):
 
     GAMMA = 0.9
 
-    def __init__(self, observation_space, action_space, device="cuda", seed=0, max_batch=4096):
+    def __init__(self, observation_space, action_space, device="cuda", seed=0, max_batch=4096, normalize=None):
         self.observation_space, self.action_space = observation_space, action_space
+        normalize = normalize or {}
+        self._obs_gain = BATCH_NORM_INFERENCE if normalize.get("observation") else None
+        self._rew_gain = BATCH_NORM_INFERENCE if normalize.get("reward") else None
         obs_sp, act_sp = _spaces(observation_space), _spaces(action_space)
         self.first = next(iter(obs_sp))      # the key a shared group is named after (criticgroup.py:24)
         self.names = sorted(obs_sp)
@@ -107,7 +116,7 @@ class MultiAgentAlgBase(object):
         return t
 
     # -- host <-> device ------------------------------------------------------------------------
-    def _joint(self, d, dims, stride):
+    def _joint(self, d, dims, stride, gain=None):
         """dict name -> (B, dim) host arrays  ->  (B, stride) device array in sorted-name column order."""
         B = int(np.reshape(d[self.names[0]], (-1, dims[0])).shape[0])
         host = np.zeros((B, stride), np.float32)
@@ -115,6 +124,8 @@ class MultiAgentAlgBase(object):
         for k, dim in zip(self.names, dims):
             host[:, o:o + dim] = np.reshape(d[k], (-1, dim))
             o += dim
+        if gain is not None:
+            host *= gain
         return torch.from_numpy(host).to(self.device, non_blocking=False)
 
     def _rows(self, observations, actions, rewards, observations_n, dones):
@@ -129,6 +140,11 @@ class MultiAgentAlgBase(object):
             host[:, int(L.obs_sum) + a:int(L.obs_sum) + a + K] = np.reshape(actions[k], (-1, K))
             host[:, int(L.rw_off) + j] = np.reshape(rewards[k], -1)
             host[:, int(L.dn_off) + j] = np.reshape(dones[k], -1)
+        if self._obs_gain is not None:
+            host[:, :int(L.obs_sum)] *= self._obs_gain
+            host[:, int(L.nx_off):int(L.nx_off) + int(L.obs_sum)] *= self._obs_gain
+        if self._rew_gain is not None:
+            host[:, int(L.rw_off):int(L.rw_off) + self.n] *= self._rew_gain
         return torch.from_numpy(host).to(self.device)
 
     def _split(self, joint, dims):
@@ -202,7 +218,7 @@ class MultiAgentAlgBase(object):
     def predict(self, observations, noisy=True):
         """multiagentalgbase.py:50-67: the running policies' actions, plus N(0, 0.2) exploration noise drawn on the host
         (``npr.normal``: numpy's global stream, exactly as the reference consumes it)."""
-        obs = self._joint(observations, self.obs_dims, self._cores[0].obs_stride)
+        obs = self._joint(observations, self.obs_dims, self._cores[0].obs_stride, self._obs_gain)
         act = self._policy_act(self._predict_policies(), obs, obs.stride(0), self._act_buf("predict", obs.shape[0]),
                                shared=self.sp)
         actions = self._split(act, self.act_dims)
@@ -212,7 +228,7 @@ class MultiAgentAlgBase(object):
 
     def compute_values(self, observations):
         """multiagentalgbase.py:69-78: ``critic_predict`` = the value critics' TARGET nets at (obs, predicted actions)."""
-        obs = self._joint(observations, self.obs_dims, self._cores[0].obs_stride)
+        obs = self._joint(observations, self.obs_dims, self._cores[0].obs_stride, self._obs_gain)
         B = obs.shape[0]
         act = self._policy_act(self._predict_policies(), obs, obs.stride(0), self._act_buf("predict", B), shared=self.sp)
         rows = self._scratch(("rows", B), (B, int(self.layout.row_stride)))
@@ -354,9 +370,7 @@ class MaTd3(MultiAgentAlgBase):
     GAMMA = 0.9   # MaTD3Module._build(..., gamma=0.9), matd3module.py:47
 
     def __init__(self, observation_space, action_space, shared_policy=False, shared_critic=False, normalize=None, **kw):
-        if normalize:
-            raise NotImplementedError("BatchNorm normalisation is not built (maddpg_b200/algorithms.py header)")
-        super().__init__(observation_space, action_space, **kw)
+        super().__init__(observation_space, action_space, normalize=normalize, **kw)
         self.policies = self._group(0)                       # uses the P nets
         self.critics = [self._group(1), self._group(2)]      # twin critic groups: the Q nets
         first = self.names.index(self.first)
@@ -420,9 +434,7 @@ class Coma(MultiAgentAlgBase):
     GAMMA = 0.95   # ComaModule._build(..., gamma=0.95), comamodule.py:59
 
     def __init__(self, observation_space, action_space, shared_policy=False, shared_critic=False, normalize=None, **kw):
-        if normalize:
-            raise NotImplementedError("BatchNorm normalisation is not built (maddpg_b200/algorithms.py header)")
-        super().__init__(observation_space, action_space, **kw)   # shared_critic is ignored by ComaModule too (comamodule.py:36-43)
+        super().__init__(observation_space, action_space, normalize=normalize, **kw)   # shared_critic: ignored by ComaModule too (:36-43)
         self.best = self._group(0)
         self.worst = self._group(1)
         self.global_critic = self._group(2)    # CriticGroup(shared=True): only the first name's critic exists
@@ -500,7 +512,7 @@ class Maddpg(MultiAgentAlgBase):
     GAMMA = 0.95
 
     def __init__(self, observation_space, action_space, shared_policy=False, shared_critic=False, hyperparameters=None, **kw):
-        super().__init__(observation_space, action_space, **kw)
+        super().__init__(observation_space, action_space, **kw)   # no normalize: it would come from the discarded hyperparameters
         self.policies = self._group(0)
         self.critics = self._group(1)
         first = self.names.index(self.first)
@@ -549,9 +561,9 @@ class _Inference(MultiAgentAlgBase):
     the other methods are the reference's ``...`` bodies (they return None)."""
 
     def __init__(self, observation_space, action_space, shared_policy=False, normalize=None, **kw):
-        if normalize:
-            raise NotImplementedError("BatchNorm normalisation is not built (maddpg_b200/algorithms.py header)")
-        super().__init__(observation_space, action_space, **kw)
+        if normalize and normalize.get("reward"):
+            normalize = {"observation": normalize.get("observation")}   # the inference modules only normalise observations
+        super().__init__(observation_space, action_space, normalize=normalize, **kw)
         self.policies = self._group(0)
         self.sp = self.names.index(self.first) if shared_policy else -1
         self._check_shared()

@@ -123,7 +123,30 @@ def unique(group):
     return out
 
 
+BN_EPS = 1e-3   # snt.BatchNormV2 default ``eps``
+
+
+def batch_norm_inference(x):
+    """``snt.BatchNormV2()(x, is_training=False)`` as the modules call it (matd3module.py:65-74, comamodule.py:71-80,
+    maddpgmodule.py:67-76: ``norm(obs, False)``): never trained, so the moving mean stays 0 and the moving variance 1, there is no
+    learned scale (Sonnet's default ``scale=False``) and the offset -- not among the variables any optimizer of the fork is given
+    (``get_trainable_variables`` returns the running MLP's only, laggingnetwork.py:50-52) -- stays 0:
+    y = (x - 0) * rsqrt(1 + eps) + 0."""
+    return (np.asarray(x, F32) * (F32(1.0) / np.sqrt(F32(1.0) + F32(BN_EPS)))).astype(F32)
+
+
 class _Base(object):
+    normalize = None
+
+    def _normalized(self, obs=None, rew=None):
+        """The ``normalize`` option: {'observation': bool, 'reward': bool} -> inference-mode BatchNorm of the feeds."""
+        nz = self.normalize or {}
+        if obs is not None and nz.get("observation"):
+            obs = {n: batch_norm_inference(obs[n]) for n in obs}
+        if rew is not None and nz.get("reward"):
+            rew = {n: batch_norm_inference(rew[n]) for n in rew}
+        return obs if rew is None else (rew if obs is None else (obs, rew))
+
     def __init__(self, obs_dims, act_dims, lows, highs, first=None):
         self.names = sorted(obs_dims)
         self.first = first if first is not None else next(iter(obs_dims))   # a shared group is named after the FIRST key
@@ -203,10 +226,12 @@ class MaTd3Oracle(_Base):
         self.critics = [self._critics(rng, shared_critic), self._critics(rng, shared_critic)]
 
     def predict(self, obs):
+        obs = self._normalized(obs=obs)
         return {n: self.policies[n].act(obs[n])[0] for n in self.names}
 
     def compute_values(self, obs):
         acts = self.predict(obs)
+        obs = self._normalized(obs=obs)
         x = np.concatenate([self.cat(obs), self.cat(acts)], axis=1)
         return {n: self.critics[0][n].q(x, target=True)[0] for n in self.names}
 
@@ -222,6 +247,7 @@ class MaTd3Oracle(_Base):
     def train_step(self, obs, act, rew, obs_n, done, step=None, z=None):
         """z: {name: (B, K) N(0,1) draws} behind ``tf.random.normal`` of the noisy target.  -> {'actor': {...} (only on policy
         steps), 'critic': {...}} like ``unflatten_map(self._train(feed))``."""
+        obs, obs_n, rew = self._normalized(obs=obs), self._normalized(obs=obs_n), self._normalized(rew=rew)
         y, _ = self.td_targets(rew, obs_n, done, z)
         x = np.concatenate([self.cat(obs), self.cat(act)], axis=1)
         closs, csteps = [], []
@@ -267,6 +293,7 @@ class ComaOracle(_Base):
 
     def train_step(self, obs, act, rew, obs_n, done, step=None):
         f = self.first
+        obs, obs_n, rew = self._normalized(obs=obs), self._normalized(obs=obs_n), self._normalized(rew=rew)
         worst_n = {n: self.worst[n].act(obs_n[n])[0] for n in self.names}
         best_n = {n: self.best[n].act(obs_n[n])[0] for n in self.names}
         xn_worst = np.concatenate([self.cat(obs_n), self.cat(worst_n)], axis=1)
@@ -324,6 +351,7 @@ class MaddpgOracle(_Base):
         return {n: self.critics[n].q(x, target=True)[0] for n in self.names}
 
     def train_step(self, obs, act, rew, obs_n, done, step=None):
+        obs, obs_n, rew = self._normalized(obs=obs), self._normalized(obs=obs_n), self._normalized(rew=rew)
         a_n = {n: self.policies[n].act(obs_n[n], target=True)[0] for n in self.names}
         xn = np.concatenate([self.cat(obs_n), self.cat(a_n)], axis=1)
         y = {n: td_combine(np.ravel(rew[n]), np.ravel(done[n]), self.critics[n].q(xn, target=True)[0], self.GAMMA)

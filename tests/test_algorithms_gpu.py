@@ -292,6 +292,42 @@ def test_fork_maddpg_and_inference_classes_match_oracle(shared):
         assert inf.train_step(obs, obs, obs, obs, obs) is None and inf.compute_values(obs) is None and inf.run_updates() is None
 
 
+@pytest.mark.parametrize("cls_name", ["MaTd3", "Coma"])
+def test_normalize_option_is_inference_mode_batch_norm(cls_name):
+    """normalize={'observation': True, 'reward': True}: ``snt.BatchNormV2()(x, False)`` of the feeds (matd3module.py:65-74,
+    comamodule.py:71-80) -- with never-updated moving statistics a constant gain rsqrt(1 + 1e-3)."""
+    from maddpg_b200 import algorithms
+    B = 96
+    nz = {"observation": True, "reward": True}
+    if cls_name == "MaTd3":
+        o = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=51)
+        alg = algorithms.MaTd3(*spaces(), normalize=nz, seed=13)
+        load_policy(alg.policies, o.policies, o.names)
+        for c in range(2):
+            load_critic(alg.critics[c], o.critics[c], o.names)
+    else:
+        o = ComaOracle(OBS, ACT, LOW, HIGH, seed=52, first=NAMES[0])
+        alg = algorithms.Coma(*spaces(), normalize=nz, seed=14)
+        load_policy(alg.best, o.best, o.names)
+        load_policy(alg.worst, o.worst, o.names)
+        load_critic(alg.personal, o.personal, o.names)
+        load_critic(alg.global_critic, {n: o.global_critic for n in o.names}, o.names)
+    o.normalize = nz
+    obs, act, rew, obs_n, done, z = make_batch(B, 800)
+    obs = {n: 3.0 * v for n, v in obs.items()}      # make the 0.05 % gain matter at the 1e-4 tolerance
+    rew = {n: 5.0 * v for n, v in rew.items()}
+    kw_o, kw_a = ({"z": z}, {"noise": z}) if cls_name == "MaTd3" else ({}, {})
+    want = o.train_step(obs, act, rew, obs_n, done, step=2, **kw_o)
+    got = alg.train_step(obs, act, rew, obs_n, done, step=2, **kw_a)
+    for key in want:
+        losses_close(got[key], want[key], "normalized %s" % key)
+    o.normalize = None                                # and the gain is really there: the un-normalised losses differ
+    o2 = o.train_step(obs, act, rew, obs_n, done, step=2, **kw_o)
+    assert any(abs(float(o2["critic"][n]) - float(want["critic"][n])) > 3e-4 * abs(float(want["critic"][n])) for n in o.names)
+    want_a = o.predict(obs)                           # (oracle weights moved by two steps: compare like with like)
+    assert set(alg.predict(obs, noisy=False)) == set(want_a)
+
+
 def test_save_load_round_trip_and_refusals(tmp_path):
     from maddpg_b200.algorithms import Coma, DictReplayBuffer, MaTd3
     a = MaTd3(*spaces(), seed=4)
@@ -306,10 +342,8 @@ def test_save_load_round_trip_and_refusals(tmp_path):
     lb = b.train_step(obs, act, rew, obs_n, done, step=4, noise=z)
     for n in la["critic"]:
         assert float(la["critic"][n]) == pytest.approx(float(lb["critic"][n]), rel=1e-6)
-    with pytest.raises(NotImplementedError):
-        MaTd3(*spaces(), normalize={"observation": True})
-    with pytest.raises(NotImplementedError):
-        Coma(*spaces(), normalize={"reward": True})
+    with pytest.raises(AssertionError):
+        MaTd3(*spaces(), shared_policy=True)      # unequal spaces (policygroup.py:32-34)
     # the fork's dict replay (common/replaybuffer.py): ring overwrite and dict-of-lists samples
     rb = DictReplayBuffer(5)
     for t in range(8):
