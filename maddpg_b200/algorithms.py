@@ -51,7 +51,7 @@ class MultiAgentAlgBase(object):
 
     GAMMA = 0.9
 
-    def __init__(self, observation_space, action_space, device="cuda", seed=0, max_batch=4096, normalize=None):
+    def __init__(self, observation_space, action_space, device="cuda", seed=0, normalize=None):
         self.observation_space, self.action_space = observation_space, action_space
         normalize = normalize or {}
         self._obs_gain = BATCH_NORM_INFERENCE if normalize.get("observation") else None
@@ -75,7 +75,6 @@ class MultiAgentAlgBase(object):
         self._counter = 0
         self.sp = self.sc = -1     # index of the name a shared policy / critic group is built on, -1: one member per name
         self._cores = []
-        self.max_batch = int(max_batch)
         self._buf = {}
 
     # -- groups ---------------------------------------------------------------------------------
