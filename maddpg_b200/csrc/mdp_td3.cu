@@ -159,10 +159,14 @@ __global__ void __launch_bounds__(NT) k_td3_policy_grads(CoreDev Cp, CoreDev Cq,
   MlpW qw = Cq.agents[cj].net[critic_use_target ? MDP_NET_TARGET_Q : MDP_NET_Q];
   const MlpG& pg = Cp.agents[pj].grad[0];
   if (RES) {
-    load_wT_rows<U>(G, sWT, qw.W2, 0, U);
-    load_wT_rows<U>(G, sWTp, pw.W2, 0, U);
-    qw = load_net<U>(G, sW, qw);
+    qw = load_net<U>(G, sW, qw);   // coalesced 16-byte loads; the transposed W2 copies are then made from shared memory
     pw = load_net<U>(G, sWp, pw);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < U * U; idx += NT) {
+      const int k = idx / U, ul = idx - k * U;
+      sWT[ul * U + k] = qw.W2[idx];
+      sWTp[ul * U + k] = pw.W2[idx];
+    }  // published by the first barrier inside layer1
   }
   const long long row0 = (long long)blockIdx.x * TM;
   const int nrows = (int)min((long long)TM, B - row0);
