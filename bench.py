@@ -377,8 +377,9 @@ def fork_algorithms_section(torch, with_cpu):
             alg.run_updates()
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
-        row = {"train_step_plus_target_update_ms": median(ts) * 1e3, "launches_per_step": (_lib.launch_count() - l0) / 20,
-               "api": "%s.train_step(host dicts, step=2) + run_updates()" % cls.__name__}
+        row = {"train_step_plus_target_update_ms": median(ts) * 1e3, "launches_outside_the_graph": (_lib.launch_count() - l0) / 20,
+               "api": "%s.train_step(host dicts, step=2) + run_updates(): the step's kernels replay as one CUDA graph, the "
+                      "target updates launch one by one" % cls.__name__}
         if with_cpu:
             from oracle.matd3 import ComaOracle, MaTd3Oracle
             o = (MaTd3Oracle if cls is MaTd3 else ComaOracle)({k: D for k in names}, {k: K for k in names}, {k: -1.0 for k in names},

@@ -76,6 +76,12 @@ class MultiAgentAlgBase(object):
         self.sp = self.sc = -1     # index of the name a shared policy / critic group is built on, -1: one member per name
         self._cores = []
         self._buf = {}
+        # a train step is 12-19 dependent launches of 5-40 us: from its second call on, every (batch, step kind) replays as one
+        # CUDA graph.  The graph bakes the Philox counter of its capture; a device control word (mdp_core_set_ctl) advanced
+        # inside the graph keeps every replay on a fresh noise stream.
+        self.use_graphs = True
+        self._graphs, self._graph_seen = {}, {}
+        self._ctl = torch.zeros(4, dtype=torch.int64, device=self.device)
 
     # -- groups ---------------------------------------------------------------------------------
     def _group(self, seed_offset):
@@ -84,6 +90,7 @@ class MultiAgentAlgBase(object):
                           gamma=self.GAMMA, device=self.device, seed=self.seed + seed_offset, replay_capacity=1,
                           polyak=TARGET_POLYAK, grad_clip=0.0, actor_reg=0.0)
         core.set_tensor_cores(-1)   # the critic step of these algorithms runs on the fp32 SIMT tiles (batch 1024, 64 units)
+        core.set_ctl(self._ctl)
         # snt.Linear's defaults (snt.nets.MLP, laggingnetwork.py:22-23): truncated normal, stddev 1/sqrt(fan_in), zero biases;
         # running and target nets are initialised independently
         rng = np.random.RandomState(self.seed + 7919 * (seed_offset + 1))
@@ -115,8 +122,9 @@ class MultiAgentAlgBase(object):
         return t
 
     # -- host <-> device ------------------------------------------------------------------------
-    def _joint(self, d, dims, stride, gain=None):
-        """dict name -> (B, dim) host arrays  ->  (B, stride) device array in sorted-name column order."""
+    def _joint(self, d, dims, stride, gain=None, key=None):
+        """dict name -> (B, dim) host arrays  ->  (B, stride) device array in sorted-name column order (``key``: into the
+        persistent buffer of that name, whose address a captured train step keeps reading)."""
         B = int(np.reshape(d[self.names[0]], (-1, dims[0])).shape[0])
         host = np.zeros((B, stride), np.float32)
         o = 0
@@ -125,7 +133,11 @@ class MultiAgentAlgBase(object):
             o += dim
         if gain is not None:
             host *= gain
-        return torch.from_numpy(host).to(self.device, non_blocking=False)
+        if key is None:
+            return torch.from_numpy(host).to(self.device, non_blocking=False)
+        dev = self._scratch((key, B), (B, stride))
+        dev.copy_(torch.from_numpy(host))
+        return dev
 
     def _rows(self, observations, actions, rewards, observations_n, dones):
         """The five feed dicts as (B, row_stride) joint rows (the replay ring's row layout, include/maddpg_b200.h)."""
@@ -144,7 +156,9 @@ class MultiAgentAlgBase(object):
             host[:, int(L.nx_off):int(L.nx_off) + int(L.obs_sum)] *= self._obs_gain
         if self._rew_gain is not None:
             host[:, int(L.rw_off):int(L.rw_off) + self.n] *= self._rew_gain
-        return torch.from_numpy(host).to(self.device)
+        dev = self._scratch(("rows_in", B), (B, int(L.row_stride)))     # persistent: a captured train step reads this address
+        dev.copy_(torch.from_numpy(host))
+        return dev
 
     def _split(self, joint, dims):
         out, o = {}, 0
@@ -211,7 +225,7 @@ class MultiAgentAlgBase(object):
         _lib.check(_lib.lib.mdp_td3_polyak(core._h, int(mask), TARGET_POLYAK, _lib.current_stream()), "mdp_td3_polyak")
 
     def _act_buf(self, key, B):
-        return self._scratch(key, (B, self._cores[0].act_stride))
+        return self._scratch((key, B), (B, self._cores[0].act_stride))   # one buffer per batch size: captured graphs keep the address
 
     # -- reference surface ----------------------------------------------------------------------
     def predict(self, observations, noisy=True):
@@ -241,17 +255,47 @@ class MultiAgentAlgBase(object):
         """multiagentalgbase.py:92-104.  -> {'actor': {name: loss}, 'critic': {name: loss}} (``unflatten_map`` of the outputs).
         ``noise``: optional {name: (B, K)} N(0, 1) draws behind the noisy target's ``tf.random.normal`` (parity runs)."""
         rows = self._rows(observations, actions, rewards, observations_n, dones)
-        z = None if noise is None else self._joint(noise, self.act_dims, self._cores[0].act_stride)
+        z = None if noise is None else self._joint(noise, self.act_dims, self._cores[0].act_stride, key="z_in")
         return self._train_step(rows, step, z, update=True)
 
     def compute_loss(self, observations, actions, rewards, observations_n, dones, noise=None):
         """multiagentalgbase.py:80-90: the losses of a policy step without the optimizer."""
         rows = self._rows(observations, actions, rewards, observations_n, dones)
-        z = None if noise is None else self._joint(noise, self.act_dims, self._cores[0].act_stride)
+        z = None if noise is None else self._joint(noise, self.act_dims, self._cores[0].act_stride, key="z_in")
         return self._train_step(rows, 2, z, update=False)
 
     def update_targets(self):
         self.run_updates()
+
+    def _is_policy_step(self, step):
+        return True
+
+    def _train_step(self, rows, step, z, update):
+        """All launches of one train step (``_launch``), eagerly the first time a (batch, step kind) is seen and as one CUDA graph
+        afterwards, then one read of the loss accumulators (``_losses``)."""
+        B, policy_step = rows.shape[0], self._is_policy_step(step)
+        if not update:     # compute_loss: gradients only, then put the state back
+            self._save_adam_t()
+            self._launch(rows, z, policy_step, False)
+            out = self._losses(B, policy_step)
+            self._discard_grads()
+            return out
+        key = (B, policy_step, z is not None)
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if not self.use_graphs or seen == 0:
+            self._launch(rows, z, policy_step, True)
+        else:
+            graph = self._graphs.get(key)
+            if graph is None:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    _lib.check(_lib.lib.mdp_ctl_advance(_lib.ptr(self._ctl), 1 << 32, 0, 1, 0, _lib.current_stream()),
+                               "mdp_ctl_advance")
+                    self._launch(rows, z, policy_step, True)
+                self._graphs[key] = graph
+            graph.replay()
+        return self._losses(B, policy_step)
 
     def _check_shared(self):
         if self.sp >= 0 and (len(set(self.obs_dims)) > 1 or len(set(self.act_dims)) > 1 or len(set(self._scale)) > 1
@@ -391,11 +435,12 @@ class MaTd3(MultiAgentAlgBase):
         self._polyak(self.critics[0], 2)
         self._polyak(self.critics[1], 2)
 
-    def _train_step(self, rows, step, z, update):
+    def _is_policy_step(self, step):
+        return bool(step) and step % 2 == 0     # matd3.py:69
+
+    def _launch(self, rows, z, policy_step, update):
         B, L = rows.shape[0], self.layout
         self._zero_stats()
-        if not update:
-            self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
         # noisy target actions at o', min of the twin target critics, TD combine (matd3module.py:76-83, 113-123)
         sp, sc = self.sp, self.sc
@@ -405,24 +450,24 @@ class MaTd3(MultiAgentAlgBase):
         self._q_target(self.critics[0], self.critics[1], rows, 1, a_n, y_out=y, shared_agent=sc)
         for cr in self.critics:      # both critic groups regress on the same targets (:88-95)
             self._critic_step(cr, sc, rows, y)
-        policy_step = bool(step) and step % 2 == 0     # matd3.py:69
         if policy_step:
             a = self._policy_act(self.policies, rows, rows.stride(0), self._act_buf("a_now", B), shared=sp)
             # a shared group's one loss is the first name's value (policygroup.py:129-135)
             self._policy_grads(self.policies, self.critics[0], rows, a, shared_policy=sp, critic_agent=sc if sc >= 0 else sp)
+        if update:
+            for cr in self.critics:
+                self._adam(cr, 1, sc)
+            if policy_step:
+                self._adam(self.policies, 0, sp)
+
+    def _losses(self, B, policy_step):
+        sp, sc = self.sp, self.sc
         stats = self._read_stats([self.policies] + self.critics)
         out = {"critic": {k: np.float32(np.mean(np.asarray([stats[1][sc if sc >= 0 else j, 0] / B,
                                                              stats[2][sc if sc >= 0 else j, 0] / B], np.float32)))
                           for j, k in enumerate(self.names)}}
         if policy_step:
             out["actor"] = {k: np.float32(stats[0][sp if sp >= 0 else j, 1] / B) for j, k in enumerate(self.names)}
-        if not update:
-            self._discard_grads()
-            return out
-        for cr in self.critics:
-            self._adam(cr, 1, sc)
-        if policy_step:
-            self._adam(self.policies, 0, sp)
         return out
 
 
@@ -457,11 +502,9 @@ class Coma(MultiAgentAlgBase):
         self._polyak(self.worst, 1)
         self._polyak(self.best, 1)
 
-    def _train_step(self, rows, step, z, update):
+    def _launch(self, rows, z, policy_step, update):
         B, L, s = rows.shape[0], self.layout, self.shared
         self._zero_stats()
-        if not update:
-            self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
         sp = self.sp
         worst_n = self._policy_act(self.worst, nx, rows.stride(0), self._act_buf("worst_next", B), shared=sp)
@@ -484,6 +527,14 @@ class Coma(MultiAgentAlgBase):
         self._policy_grads(self.best, self.personal, rows, best_a, sign=1.0, shared_policy=sp, critic_agent=sp)    # :118-121, 129
         worst_a = self._policy_act(self.worst, rows, rows.stride(0), self._act_buf("worst_now", B), shared=sp)
         self._policy_grads(self.worst, self.personal, rows, worst_a, sign=-1.0, shared_policy=sp, critic_agent=sp)  # :123-127, 130
+        if update:
+            self.global_critic.clip_adam_polyak(s, 1, do_polyak=False)
+            self._adam_all(self.personal, 1)
+            self._adam(self.best, 0, sp)
+            self._adam(self.worst, 0, sp)
+
+    def _losses(self, B, policy_step):
+        s, sp = self.shared, self.sp
         st = dict(zip(("best", "worst", "global_critic", "personal"),
                       self._read_stats([self.best, self.worst, self.global_critic, self.personal])))
         gl = np.float32(st["global_critic"][s, 0] / B)
@@ -492,13 +543,6 @@ class Coma(MultiAgentAlgBase):
                "actor": {k: np.float32(np.std(np.asarray([st["best"][sp if sp >= 0 else j, 1] / B,
                                                            st["worst"][sp if sp >= 0 else j, 1] / B], np.float32)))
                          for j, k in enumerate(self.names)}}
-        if not update:
-            self._discard_grads()
-            return out
-        self.global_critic.clip_adam_polyak(s, 1, do_polyak=False)
-        self._adam_all(self.personal, 1)
-        self._adam(self.best, 0, sp)
-        self._adam(self.worst, 0, sp)
         return out
 
 
@@ -532,11 +576,9 @@ class Maddpg(MultiAgentAlgBase):
         self._polyak(self.policies, 1)
         self._polyak(self.critics, 2)
 
-    def _train_step(self, rows, step, z, update):
+    def _launch(self, rows, z, policy_step, update):
         B, L, sp, sc = rows.shape[0], self.layout, self.sp, self.sc
         self._zero_stats()
-        if not update:
-            self._save_adam_t()
         nx = rows[:, int(L.nx_off):]
         a_n = self._policy_act(self.policies, nx, rows.stride(0), self._act_buf("a_next", B), use_target=True, shared=sp)  # :77
         y = self._scratch(("y", B), (self.n, B))
@@ -544,14 +586,15 @@ class Maddpg(MultiAgentAlgBase):
         self._critic_step(self.critics, sc, rows, y)                                                                    # :89-93
         a = self._policy_act(self.policies, rows, rows.stride(0), self._act_buf("a_now", B), shared=sp)
         self._policy_grads(self.policies, self.critics, rows, a, shared_policy=sp, critic_agent=sc if sc >= 0 else sp)   # :94-98
+        if update:
+            self._adam(self.critics, 1, sc)
+            self._adam(self.policies, 0, sp)
+
+    def _losses(self, B, policy_step):
+        sp, sc = self.sp, self.sc
         st = self._read_stats([self.policies, self.critics])
         out = {"actor": {k: np.float32(st[0][sp if sp >= 0 else j, 1] / B) for j, k in enumerate(self.names)},
                "critic": {k: np.float32(st[1][sc if sc >= 0 else j, 0] / B) for j, k in enumerate(self.names)}}
-        if not update:
-            self._discard_grads()
-            return out
-        self._adam(self.critics, 1, sc)
-        self._adam(self.policies, 0, sp)
         return out
 
 

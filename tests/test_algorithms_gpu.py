@@ -328,6 +328,42 @@ def test_normalize_option_is_inference_mode_batch_norm(cls_name):
     assert set(alg.predict(obs, noisy=False)) == set(want_a)
 
 
+@pytest.mark.parametrize("cls_name", ["MaTd3", "Coma", "Maddpg"])
+def test_graph_replayed_steps_equal_eager_steps(cls_name):
+    """From the second call of a (batch, step kind) on a train step replays as one CUDA graph: same losses and parameters as the
+    launch-by-launch path, and the in-kernel target noise of a replay differs from the previous replay's."""
+    from maddpg_b200 import algorithms
+    cls = getattr(algorithms, cls_name)
+    a, b = cls(*spaces(), seed=15), cls(*spaces(), seed=15)
+    b.use_graphs = False
+    for ca, cb in zip(a._cores, b._cores):
+        assert torch.equal(ca.params, cb.params)
+    B = 128
+    kw = lambda z: {"noise": z} if cls_name == "MaTd3" else {}
+    for step in range(1, 7):
+        obs, act, rew, obs_n, done, z = make_batch(B, 900 + step)
+        la = a.train_step(obs, act, rew, obs_n, done, step=2 * step, **kw(z))
+        lb = b.train_step(obs, act, rew, obs_n, done, step=2 * step, **kw(z))
+        for key in lb:
+            losses_close(la[key], lb[key], "%s step %d %s" % (cls_name, step, key))
+        a.run_updates()
+        b.run_updates()
+    assert len(a._graphs) == 1 and len(b._graphs) == 0
+    for ca, cb in zip(a._cores, b._cores):
+        d = (ca.params - cb.params).abs()
+        assert float(d.max()) <= 6.6e-4 and float((d > 5e-6).float().mean()) <= 0.01
+        assert torch.equal(ca.adam_t, cb.adam_t)
+    if cls_name == "MaTd3":     # Philox target noise under replay: a fresh stream every time
+        obs, act, rew, obs_n, done, z = make_batch(B, 950)
+        seen = []
+        for _ in range(4):
+            a.train_step(obs, act, rew, obs_n, done, step=2)
+            seen.append(a._buf[("a_next", B)].clone())
+        assert len(a._graphs) == 2
+        for i in range(3):
+            assert not torch.equal(seen[i], seen[i + 1])
+
+
 def test_save_load_round_trip_and_refusals(tmp_path):
     from maddpg_b200.algorithms import Coma, DictReplayBuffer, MaTd3
     a = MaTd3(*spaces(), seed=4)
