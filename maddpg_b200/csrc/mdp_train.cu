@@ -1128,6 +1128,24 @@ static ResPlan make_res_plan(const mdp_core* c, const Plan& p, int agent) {
   return r;
 }
 
+// Plan of a launch over `count` agents (grid.y): a grouped round of 16-row tiles is cdiv(rows, 16) * count CTAs, one resident CTA
+// per SM -- past 148 they run as two waves, and 32-row tiles (half the CTAs, two rows per thread against every weight load) finish
+// sooner: batch 1024 x 3 agents 0.088 -> 0.069 ms per round, simple_tag 0.107 -> 0.077, simple_world_comm with 128 units 0.71 ->
+// 0.55 (tools/time_upd_scen.py).  Not when the taller tile would push the nets out of shared memory (simple_spread N=4: the
+// resident plan fits at 16 rows only, 0.117 vs 0.151 ms), and never for a single agent's launch (64 CTAs: one wave either way).
+static Plan plan_for(const mdp_core* c, int rows, int count) {
+  Plan p = make_plan(c, rows);
+  if (count > 1 && p.TM == 16 && (long long)cdiv(rows, 16) * count > 148) {
+    Plan q = p;
+    q.TM = 32;
+    const ResPlan r16 = make_res_plan(c, p, 0), r32 = make_res_plan(c, q, 0);
+    if (!r16.ok || r32.ok) p = q;  // also when the fused TD-target + critic tile no longer fits: two launches of 32-row tiles still win
+  }
+  static const int force_tm = []() { const char* e = getenv("MDP_PLAN_TM"); return e ? atoi(e) : 0; }();
+  if (force_tm == 16 || force_tm == 32) p.TM = force_tm;  // diagnostic override (tools/time_upd_scen.py)
+  return p;
+}
+
 namespace mdp {
 int launch_td_target_tc(mdp_core* c, const CoreDev& d, int32_t agent, int32_t count, const mdp_ring_layout* lay, int32_t B,
                         const float* batch, const long long* ridx, long long idx_stride, const float* u_target, int32_t u_stride,
@@ -1193,7 +1211,7 @@ static int launch_td_target(mdp_core* c, int32_t agent, int32_t count, const mdp
   const bool prepared = take_prepared(c, agent, count);
   if (!prepared) MDP_CUDA(cudaMemsetAsync(c->stats + 8 * agent, 0, 8 * sizeof(double) * count, st));
   CoreDev d = core_dev(c);
-  const Plan p = make_plan(c, B);
+  const Plan p = plan_for(c, B, count);
   const ResPlan rp = make_res_plan(c, p, agent);
   const long long* ridx = (const long long*)idx;
   if (want_tc(c, B, count)) {
@@ -1235,7 +1253,7 @@ static int launch_td_critic(mdp_core* c, int32_t agent, int32_t count, const mdp
   int rc = check_lay(c, lay);
   if (rc) return rc;
   MDP_REQUIRE(batch && y_scratch && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_update: bad argument");
-  const Plan p = make_plan(c, B);
+  const Plan p = plan_for(c, B, count);
   const ResPlan rp = make_res_plan(c, p, agent);
   if (rp.fuse_ok && !c->no_fuse && !want_tc(c, B, count) && !want_tc(c, B, count, true)) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -1280,7 +1298,7 @@ static int launch_critic_grads(mdp_core* c, int32_t agent, int32_t count, const 
   MDP_REQUIRE(batch && y && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_critic_grads: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
-  const Plan p = make_plan(c, B);
+  const Plan p = plan_for(c, B, count);
   const ResPlan rp = make_res_plan(c, p, agent);
   const long long* ridx = (const long long*)idx;
   if (want_tc(c, B, count, true)) {
@@ -1320,7 +1338,7 @@ static int launch_actor_grads(mdp_core* c, int32_t agent, int32_t count, const m
   MDP_REQUIRE(batch && B > 0 && agent >= 0 && count > 0 && agent + count <= c->cfg.n_agents, "mdp_actor_grads: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   CoreDev d = core_dev(c);
-  const Plan p = make_plan(c, B);
+  const Plan p = plan_for(c, B, count);
   const ResPlan rp = make_res_plan(c, p, agent);
   const long long* ridx = (const long long*)idx;
   if (want_tc(c, B, count, true)) {
