@@ -367,7 +367,7 @@ class MultiAgentAlgBase(object):
 
 class DictReplayBuffer(object):
     """maddpg/common/replaybuffer.py:10-103: the fork's host-side dict replay (tuples of per-name dicts, ``random.randint``
-    index draws).  ``learn_generator`` keeps it on the host like the reference; the sampled batch crosses to the device once per
+    index draws).  Pinned to the real class: tests/golden/dict_replay_ref.npz (tests/test_dict_replay.py).  ``learn_generator`` keeps it on the host like the reference; the sampled batch crosses to the device once per
     train step (every 5000 env steps, multiagentalgbase.py:126)."""
 
     def __init__(self, size):
@@ -391,6 +391,11 @@ class DictReplayBuffer(object):
 
     def make_index(self, batch_size):
         return [self._random.randint(0, len(self._storage) - 1) for _ in range(batch_size)]
+
+    def make_latest_index(self, batch_size):
+        idx = [(self._next_idx - 1 - i) % self._maxsize for i in range(batch_size)]
+        np.random.shuffle(idx)
+        return idx
 
     def sample_index(self, idxes):
         out = tuple({} for _ in range(5))
