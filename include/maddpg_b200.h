@@ -298,8 +298,8 @@ int mdp_clip_adam_polyak_all(mdp_core* core, int32_t which, float grad_scale, in
  * Policy._build (policy.py:63-88) for every agent in one launch: act_i = t * scale_i + shift_i with t = tanh(mlp_i(obs_i))
  * (noise_std = 0: `predict` / `predict_target`) or t = clip(tanh(mlp_i(obs_i)) + clip(noise_std * z, -noise_clip, noise_clip),
  * -1, 1) (`noisy_target`, :72-75).  z: injected N(0,1) draws (B, noise_stride) in the joint action layout, or NULL for
- * in-kernel Philox draws keyed by (seed, counter, row, column).  act_scale / act_shift: HOST float[n_agents], the Box rescale
- * `interval` and `interval + low` (:76-84); NULL = 1 and 0.  obs (B, obs_stride) and act (B, act_stride) are joint arrays.
+ * in-kernel Philox draws keyed by (seed, counter [+ ctl[0] of an attached control block, mdp_core_set_ctl], row, column).
+ * act_scale / act_shift: HOST float[n_agents], the Box rescale `interval` and `interval + low` (:76-84); NULL = 1 and 0.  obs (B, obs_stride) and act (B, act_stride) are joint arrays.
  * shared_agent >= 0: a PolicyGroup(shared=True) -- that agent's policy serves every name (policygroup.py:26-37, 54-70; equal
  * spaces required); -1: one policy per agent. */
 int mdp_td3_policy_act(mdp_core* policies, int32_t use_target, int32_t B, const float* obs, int32_t obs_stride,
