@@ -335,7 +335,8 @@ class MultiAgentAlgBase(object):
             yield TrainInfo(observations, rewards, dones, infos, train_info.get("actor"), train_info.get("critic"), step)
 
     def learn(self, env, timesteps=10 ** 6, replay=None, verbose=True):
-        """multiagentalgbase.py:134-165 without the tqdm bar: returns the running episode reward."""
+        """multiagentalgbase.py:134-165 without the tqdm bar.  Returns None like the reference; the running episode reward it
+        prints is kept in ``self.running_reward``."""
         ep_reward, total_reward = None, 0
         for info in self.learn_generator(env, timesteps, replay):
             total_reward += float(np.mean(list(info.rewards.values())))
@@ -346,7 +347,7 @@ class MultiAgentAlgBase(object):
                 print("Training Step:", info.step, "Running Reward: {:+6.6f}".format(ep_reward or 0.0),
                       "Actor Loss:", float(np.mean(list(info.actor_loss.values()))),
                       "Critic Loss:", float(np.mean(list(info.critic_loss.values()))))
-        return ep_reward
+            self.running_reward = ep_reward
 
     def save(self, path):
         """multiagentalgbase.py:167-173: every group's parameters and Adam state."""
