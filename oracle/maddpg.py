@@ -2,12 +2,21 @@
 
 TEST INFRASTRUCTURE ONLY (see oracle/mpe.py header for who may import ``oracle/``).
 
-PARITY UNPINNED against the reference's own execution: maddpg/trainer/maddpg.py needs
-TensorFlow 1.8.0 (reference README.md:16), which is not installed and cannot be fetched, and the
-reference has no test or golden vector for trainer/, distributions.py or train.py.
-The restated math is cross-checked instead against torch autograd in float64
-(tests/test_oracle_maddpg.py) and its polyak step against the one invariant the reference does
-test (tests/test_policy.py:71-86: polyak with tau such that target==running).
+PARITY PARTLY PINNED.  The TensorFlow GRAPH pieces (mlp_model, the Gumbel-softmax sample, the two
+losses and their gradients, clip_by_norm, Adam, polyak) are unpinned against the reference's own
+execution: maddpg/trainer/maddpg.py builds them with TensorFlow 1.8.0 (reference README.md:16),
+which is not installed and cannot be fetched, and the reference has no test or golden vector for
+trainer/, distributions.py or train.py.  They are cross-checked against torch autograd
+in float64 (tests/test_oracle_maddpg.py) and the polyak step against the one invariant the
+reference does test (tests/test_policy.py:71-86: polyak with tau such that target==running).
+Everything AROUND the graph is pinned: the REAL ``MADDPGAgentTrainer.update`` / ``experience`` /
+``preupdate`` / ``action`` methods (maddpg.py:151-196) were executed unmodified in the build
+container on top of these restated graph callables and the REAL ReplayBuffer
+(tests/golden/make_update_golden.py -> update_orchestration_ref.npz), and
+``OracleAgentTrainer``'s own restatement of them reproduces that run bit for bit
+(test_update_orchestration_matches_the_reference_method): the warm-up and every-100-steps gates,
+the python-``random`` index draws, the per-agent gathers, the float64 numpy TD combine, the call
+order q_train, p_train, p_update, q_update and the six returned statistics.
 
 What is restated (reference file:line):
   mlp_model                      experiments/train.py:39-46      (3 x fully_connected, ReLU, ReLU, none)

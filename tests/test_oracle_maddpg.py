@@ -130,3 +130,43 @@ def test_gumbel_softmax_heads_sum_to_one():
     rng = np.random.RandomState(1)
     a = om.gumbel_softmax(rng.randn(7, 9), rng.uniform(0.01, 1, (7, 9)), [5, 4])
     assert np.allclose(a[:, :5].sum(1), 1, atol=1e-6) and np.allclose(a[:, 5:].sum(1), 1, atol=1e-6)
+
+
+def test_update_orchestration_matches_the_reference_method():
+    """tests/golden/update_orchestration_ref.npz was recorded by the REAL ``MADDPGAgentTrainer.update`` / ``experience`` /
+    ``preupdate`` / ``action`` (maddpg/trainer/maddpg.py:151-196, executed unmodified around oracle-backed graph callables and the
+    REAL ReplayBuffer; tests/golden/make_update_golden.py).  ``OracleAgentTrainer``'s own restatement of those methods -- the thing
+    every GPU update-round test is compared with -- must reproduce it bit for bit: both gates, the index draws, the float64 TD
+    combine, the call order and the six statistics."""
+    import os
+    import random
+    from tests.update_case import N, T_SEQUENCE, build_oracle_trainers, transition
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "update_orchestration_ref.npz"))
+    agents = build_oracle_trainers()
+    random.seed(11)
+    rows, ran = 0, 0
+    for step, t in enumerate(T_SEQUENCE):
+        for _ in range(40):
+            tr = transition(rows)
+            for i, a in enumerate(agents):
+                a.experience(tr["obs"][i], tr["act"][i], tr["rew"][i], tr["obs2"][i], tr["done"][i], False)
+            rows += 1
+        for a in agents:
+            a.preupdate()
+        for i, a in enumerate(agents):
+            res = a.update(agents, t)
+            want = gold["s%d_a%d_stats" % (step, i)]
+            if res is None:
+                assert np.isnan(want).all(), (step, i)
+            else:
+                assert np.array_equal(np.asarray(res, np.float64), want), (step, i, res, want)
+                ran += 1
+            idx = np.asarray([] if a.replay_sample_index is None else a.replay_sample_index, np.int64)
+            assert np.array_equal(idx, gold["s%d_a%d_index" % (step, i)]), (step, i)
+        sums = np.asarray([float(np.sum([np.sum(p.astype(np.float64)) for net in (o.q, o.target_q, o.p, o.target_p) for p in net.p]))
+                           for o in agents])
+        assert np.array_equal(sums, gold["s%d_params" % step]), step
+    assert ran == 2 * N      # gated at 40 and 80 rows (warm-up) and at t = 150 (period); two rounds ran
+    obs = transition(999)["obs"]
+    act = np.concatenate([np.asarray(a.action(obs[i]), np.float64) for i, a in enumerate(agents)])
+    assert np.array_equal(act, gold["action"])
