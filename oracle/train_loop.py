@@ -5,6 +5,15 @@ gym and MPE, none of which can be installed here.
 
 TEST INFRASTRUCTURE ONLY -- used as the timed CPU baseline by bench.py (``cpu_baseline`` and
 ``--impl reference``), never by the product path.
+
+PINNED (the loop, not the TF graph): the REAL experiments/train.py was executed unmodified in the
+build container on these oracle classes -- its own ``train(arglist)`` loop, the REAL
+MADDPGAgentTrainer.action / experience / preupdate / update methods and the REAL ReplayBuffer, with
+oracle/mpe.py behind ``multiagent.*`` and oracle/maddpg.py's graph callables where TensorFlow would
+be (tests/golden/make_train_loop_golden.py -> train_loop_ref.npz) -- and ``run_training`` below
+reproduces the learning-curve lists it pickled bit for bit
+(tests/test_oracle_golden.py::test_train_loop_matches_the_reference_script).  ``time_rollout`` and
+``time_updates`` are the same iteration without the reward bookkeeping.
 """
 import argparse
 import time
@@ -64,6 +73,53 @@ def time_rollout(scenario, num_agents=None, steps=2000, seed=0, arglist=None):
             agent.update(trainers, train_step)  # returns at the warm-up gate
     dt = time.perf_counter() - t0
     return steps * env.n / dt, steps / dt, dt
+
+
+def run_training(scenario, num_episodes, arglist, seed=0, save_rate=1000, num_agents=None):
+    """The whole loop of ``train(arglist)`` (experiments/train.py:76-197, training mode: no display / benchmark / restore) with
+    its bookkeeping: -> (final_ep_rewards, final_ep_ag_rewards, train_step), the two lists the reference pickles for its
+    learning curves (:176-178, :181-187).  PINNED: tests/golden/train_loop_ref.npz holds what the REAL train.py computed when it
+    was executed unmodified on these same oracle classes (tests/golden/make_train_loop_golden.py); the test
+    test_oracle_golden.py::test_train_loop_matches_the_reference_script holds this function to it bit for bit."""
+    env = ompe.make_env(scenario, np.random.RandomState(seed), num_agents)
+    obs_shape_n = [env.observation_space[i].shape for i in range(env.n)]
+    num_adversaries = min(env.n, arglist.num_adversaries)
+    trainers = get_trainers(env, num_adversaries, obs_shape_n, arglist, seed)
+    episode_rewards = [0.0]
+    agent_rewards = [[0.0] for _ in range(env.n)]
+    final_ep_rewards, final_ep_ag_rewards = [], []
+    obs_n = env.reset()
+    episode_step = 0
+    train_step = 0
+    while True:
+        action_n = [agent.action(obs) for agent, obs in zip(trainers, obs_n)]
+        new_obs_n, rew_n, done_n, info_n = env.step(action_n)
+        episode_step += 1
+        done = all(done_n)
+        terminal = (episode_step >= arglist.max_episode_len)
+        for i, agent in enumerate(trainers):
+            agent.experience(obs_n[i], action_n[i], rew_n[i], new_obs_n[i], done_n[i], terminal)
+        obs_n = new_obs_n
+        for i, rew in enumerate(rew_n):
+            episode_rewards[-1] += rew
+            agent_rewards[i][-1] += rew
+        if done or terminal:
+            obs_n = env.reset()
+            episode_step = 0
+            episode_rewards.append(0)
+            for a in agent_rewards:
+                a.append(0)
+        train_step += 1
+        for agent in trainers:
+            agent.preupdate()
+        for agent in trainers:
+            agent.update(trainers, train_step)
+        if terminal and (len(episode_rewards) % save_rate == 0):
+            final_ep_rewards.append(np.mean(episode_rewards[-save_rate:]))
+            for rew in agent_rewards:
+                final_ep_ag_rewards.append(np.mean(rew[-save_rate:]))
+        if len(episode_rewards) > num_episodes:
+            return final_ep_rewards, final_ep_ag_rewards, train_step
 
 
 def time_updates(scenario, num_agents=None, rounds=5, seed=0, arglist=None, prefill=None):

@@ -32,3 +32,26 @@ def test_update_oracle_matches_golden(name):
         for key in ("q", "p", "target_q", "target_p"):
             s = np.asarray([float(np.sum(x, dtype=np.float64)) for x in r[key]])
             np.testing.assert_allclose(s, g["%s_sum_%d" % (key, j)], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["spread", "tag_ddpg_adv"])
+def test_train_loop_matches_the_reference_script(case):
+    """tests/golden/train_loop_ref.npz: the learning-curve lists the REAL experiments/train.py pickled (:181-187) when it was
+    executed unmodified -- its own loop, the REAL MADDPGAgentTrainer methods and ReplayBuffer -- on the oracle's MPE and graph
+    callables (tests/golden/make_train_loop_golden.py).  oracle/train_loop.py::run_training, the loop bench.py's reference arm
+    times, must reproduce them bit for bit."""
+    import argparse
+    import random
+    from oracle import train_loop
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_loop_ref.npz"))
+    argv = dict(zip(gold[case + "_argv"][0::2], gold[case + "_argv"][1::2]))
+    arglist = argparse.Namespace(scenario=str(argv["--scenario"]), max_episode_len=int(argv["--max-episode-len"]), lr=1e-2, gamma=0.95,
+                                 batch_size=int(argv["--batch-size"]), num_units=int(argv["--num-units"]),
+                                 num_adversaries=int(argv.get("--num-adversaries", 0)), good_policy="maddpg",
+                                 adv_policy=str(argv.get("--adv-policy", "maddpg")))
+    random.seed(3)
+    rewards, agrewards, steps = train_loop.run_training(arglist.scenario, int(argv["--num-episodes"]), arglist, seed=3,
+                                                        save_rate=int(argv["--save-rate"]))
+    assert np.array_equal(np.asarray(rewards, np.float64), gold[case + "_rewards"])
+    assert np.array_equal(np.asarray(agrewards, np.float64), gold[case + "_agrewards"])
+    assert steps >= 200      # update rounds ran (t = 100, 200 past the warm-up gate)
