@@ -9,6 +9,15 @@ which is not installed and cannot be fetched, and the reference has no test or g
 trainer/, distributions.py or train.py.  They are cross-checked against torch autograd
 in float64 (tests/test_oracle_maddpg.py) and the polyak step against the one invariant the
 reference does test (tests/test_policy.py:71-86: polyak with tau such that target==running).
+The graph WIRING is pinned one level down: the reference's own graph-building code
+(``MADDPGAgentTrainer.__init__``, ``q_train``, ``p_train``, ``make_update_exp``, ``SoftCategoricalPd``,
+``U.function`` / ``scope_vars`` / ``minimize_and_clip``, ``mlp_model``) was executed unmodified on a
+torch-backed stand-in for the TensorFlow calls it makes (tests/tf_shim.py: dense layer, softmax,
+clip_by_norm, Adam and autograd are the stand-in's, restated from TensorFlow's documentation) and
+driven through the real ``update``; this module reproduces its debug surfaces and statistics to
+8e-7 relative and its variables after two update rounds to 6e-8
+(tests/golden/make_graph_golden.py -> graph_ref.npz,
+test_oracle_matches_the_reference_graph_code).
 Everything AROUND the graph is pinned: the REAL ``MADDPGAgentTrainer.update`` / ``experience`` /
 ``preupdate`` / ``action`` methods (maddpg.py:151-196) were executed unmodified in the build
 container on top of these restated graph callables and the REAL ReplayBuffer

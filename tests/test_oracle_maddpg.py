@@ -170,3 +170,47 @@ def test_update_orchestration_matches_the_reference_method():
     obs = transition(999)["obs"]
     act = np.concatenate([np.asarray(a.action(obs[i]), np.float64) for i, a in enumerate(agents)])
     assert np.array_equal(act, gold["action"])
+
+
+def test_oracle_matches_the_reference_graph_code():
+    """tests/golden/graph_ref.npz: the reference's OWN graph-building code (``MADDPGAgentTrainer.__init__``, ``q_train``,
+    ``p_train``, ``make_update_exp``, ``SoftCategoricalPd``, ``U.function`` / ``scope_vars`` / ``minimize_and_clip``, ``mlp_model``)
+    executed unmodified on a torch-backed stand-in for TensorFlow (tests/tf_shim.py, tests/golden/make_graph_golden.py), driven
+    through the real ``update``.  The restated trainer must give the same debug surfaces, statistics and variables -- i.e. the
+    same graph wiring: centralized vs local critic inputs, loss expressions, per-optimizer variable sets, clip placement, polyak
+    pairing.  (float32 sums in a different order: statistics agree to 8e-7 relative, variables to 6e-8.)"""
+    import os
+    import random
+    from tests.update_case import N, build_oracle_trainers, shared_noise, transition
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_ref.npz"))
+    agents = build_oracle_trainers(noise=shared_noise())
+    random.seed(11)
+    for k in range(120):
+        tr = transition(k)
+        for i, a in enumerate(agents):
+            a.experience(tr["obs"][i], tr["act"][i], tr["rew"][i], tr["obs2"][i], tr["done"][i], False)
+    batch = [transition(500 + k) for k in range(10)]
+    obs_n = [np.asarray([b["obs"][i] for b in batch]) for i in range(N)]
+    act_n = [np.asarray([b["act"][i] for b in batch]) for i in range(N)]
+    for i, a in enumerate(agents):
+        for key, got in (("p_values", a.p_debug["p_values"](obs_n[i])), ("q_values", a.q_debug["q_values"](*(obs_n + act_n))),
+                         ("target_q_values", a.q_debug["target_q_values"](*(obs_n + act_n))), ("act", a.act(obs_n[i])),
+                         ("target_act", a.p_debug["target_act"](obs_n[i]))):
+            np.testing.assert_allclose(np.asarray(got, np.float64), gold["a%d_%s" % (i, key)], rtol=2e-5, atol=2e-6,
+                                       err_msg="agent %d %s" % (i, key))
+    for rnd, t in enumerate((100, 200)):
+        for a in agents:
+            a.preupdate()
+        for i, a in enumerate(agents):
+            stats = np.asarray(a.update(agents, t), np.float64)
+            np.testing.assert_allclose(stats, gold["r%d_a%d_stats" % (rnd, i)], rtol=1e-5, atol=1e-6, err_msg="round %d agent %d" % (rnd, i))
+        for i, a in enumerate(agents):
+            for attr in ("q", "target_q", "p", "target_p"):
+                for k, w in enumerate(getattr(a, attr).p):
+                    d = np.abs(w - gold["r%d_a%d_%s_%d" % (rnd, i, attr, k)])
+                    assert d.max() <= 2e-6, (rnd, i, attr, k, d.max())      # measured 6e-8: 1e-4 of one Adam step (lr = 1e-2)
+    names = [str(x) for x in gold["variable_names"]]
+    assert names[:6] == ["agent_0/q_func/fully_connected/weights:0", "agent_0/q_func/fully_connected/biases:0",
+                         "agent_0/q_func/fully_connected_1/weights:0", "agent_0/q_func/fully_connected_1/biases:0",
+                         "agent_0/q_func/fully_connected_2/weights:0", "agent_0/q_func/fully_connected_2/biases:0"]
+    assert len(names) == N * 24      # q_func, target_q_func, p_func, target_p_func per agent: no second critic from reuse=True

@@ -1,0 +1,314 @@
+"""TEST INFRASTRUCTURE -- a small stand-in for the slice of TensorFlow 1.x that the reference's MADDPG graph code uses
+(maddpg/trainer/maddpg.py:20-110 ``make_update_exp`` / ``p_train`` / ``q_train``, maddpg/common/distributions.py SoftCategorical,
+maddpg/common/tf_util.py ``function`` / ``scope_vars`` / ``minimize_and_clip`` / sessions, experiments/train.py:39-46
+``mlp_model``), so that THAT CODE -- unmodified -- can be executed in the build container and its results recorded as golden
+vectors (tests/golden/make_graph_golden.py).
+
+It is a lazy graph: every ``tf.*`` call returns a ``Tensor`` node; ``Session.run`` evaluates the fetched nodes once per run
+(memoised, so a loss and its gradients see the same ``random_uniform`` draw, like a TF run) with torch float32 tensors and torch
+autograd for ``compute_gradients``.  What the reference's code decides is therefore executed for real: which tensors are
+concatenated into which network, which variables each optimizer owns (``scope_vars`` by name prefix), the loss expressions, where
+``clip_by_norm`` sits, how ``make_update_exp`` pairs variables by sorted name, what ``U.function`` feeds and fetches.  What this
+file RESTATES, from TensorFlow's documentation, is the primitive semantics: ``fully_connected`` = x @ W + b with variables
+``<scope>/fully_connected[_k]/{weights,biases}`` (sub-scope counters reset when the enclosing named scope is left, which is what
+makes ``reuse=True`` find them), ``clip_by_norm`` = t * c / max(||t||, c), and ``AdamOptimizer`` = TF's formula with the epsilon
+outside the bias correction.  ``random_uniform`` draws from the pluggable ``NOISE`` callback.
+"""
+import re
+import sys
+import types
+
+import numpy as np
+import torch
+
+NOISE = [lambda shape: np.random.uniform(size=shape).astype(np.float32)]
+_VARIABLES = []          # every Variable, creation order
+_SCOPES = [("", False)]  # (full name, reuse)
+_SUBSCOPE_COUNT = {}     # full scope name -> {default name -> times opened}
+_SESSIONS = []
+_UNIQUE = {}
+
+
+def reset():
+    del _VARIABLES[:]
+    del _SCOPES[1:]
+    _SUBSCOPE_COUNT.clear()
+    _UNIQUE.clear()
+
+
+def _unique(name):
+    k = _UNIQUE.get(name, 0)
+    _UNIQUE[name] = k + 1
+    return name if k == 0 else "%s_%d" % (name, k)
+
+
+class _Ctx(object):
+    def __init__(self, feed):
+        self.feed, self.cache = feed, {}
+
+
+class Tensor(object):
+    """A graph node.  ``type(x) is tf.Tensor and len(x.op.inputs) == 0`` identifies a placeholder (tf_util.py:58-59)."""
+
+    def __init__(self, fn, inputs=(), name="op", last_dim=None):
+        self._fn, self._inputs, self.last_dim = fn, tuple(inputs), last_dim
+        full = (_SCOPES[-1][0] + "/" if _SCOPES[-1][0] else "") + name
+        self.name = _unique(full) + ":0"
+        self.op = types.SimpleNamespace(inputs=self._inputs, name=self.name[:-2])
+
+    def eval(self, ctx):
+        key = id(self)
+        if key not in ctx.cache:
+            ctx.cache[key] = self._fn(ctx, *[i.eval(ctx) if isinstance(i, Tensor) else i for i in self._inputs])
+        return ctx.cache[key]
+
+    def _bin(self, other, f, name):
+        return Tensor(lambda c, a, b: f(a, b), (self, other), name, self.last_dim)
+
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b, "add")
+    def __radd__(self, o): return self._bin(o, lambda a, b: b + a, "add")
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b, "sub")
+    def __rsub__(self, o): return self._bin(o, lambda a, b: b - a, "sub")
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b, "mul")
+    def __rmul__(self, o): return self._bin(o, lambda a, b: b * a, "mul")
+    def __truediv__(self, o): return self._bin(o, lambda a, b: a / b, "div")
+    def __neg__(self): return Tensor(lambda c, a: -a, (self,), "neg", self.last_dim)
+    def __getitem__(self, idx): return Tensor(lambda c, a: a[idx], (self,), "strided_slice")
+    __hash__ = object.__hash__
+
+
+class Variable(Tensor):
+    def __init__(self, name, shape, init):
+        self._fn, self._inputs, self.last_dim = None, (), shape[-1]
+        self.name = name + ":0"
+        self.op = types.SimpleNamespace(inputs=(), name=name)
+        self.value = torch.tensor(np.asarray(init(shape), np.float32), requires_grad=True)
+        _VARIABLES.append(self)
+
+    def eval(self, ctx):
+        return self.value
+
+    def assign(self, expr):
+        def run(c, v):
+            with torch.no_grad():
+                self.value.copy_(v.detach())
+            return None
+        return Tensor(run, (expr,), "Assign")
+
+    def load(self, array):
+        with torch.no_grad():
+            self.value.copy_(torch.as_tensor(np.asarray(array, np.float32)).view_as(self.value))
+
+    def numpy(self):
+        return self.value.detach().numpy().copy()
+
+
+def _as_node(x):
+    return x
+
+
+# -- scopes ----------------------------------------------------------------------------------------------------------------------
+class _VarScopeInfo(object):
+    def __init__(self, name):
+        self.name = name
+
+
+class variable_scope(object):
+    def __init__(self, name_or_scope, default_name=None, values=None, reuse=None):
+        self._name, self._default, self._reuse = name_or_scope, default_name, reuse
+
+    def __enter__(self):
+        parent, parent_reuse = _SCOPES[-1]
+        name = self._name.name if isinstance(self._name, _VarScopeInfo) else self._name
+        if name is None:   # default-named scope: uniquified by how often this name was opened under the parent
+            counts = _SUBSCOPE_COUNT.setdefault(parent, {})
+            k = counts.get(self._default, 0)
+            counts[self._default] = k + 1
+            name = self._default if k == 0 else "%s_%d" % (self._default, k)
+        full = (parent + "/" if parent else "") + name
+        self._full = full
+        _SCOPES.append((full, bool(self._reuse) or parent_reuse))
+        return _VarScopeInfo(full)
+
+    def __exit__(self, *a):
+        full = _SCOPES.pop()[0]
+        for k in list(_SUBSCOPE_COUNT):   # leaving a scope closes its sub-scope counters (what makes a later reuse=True line up)
+            if k == full or k.startswith(full + "/"):
+                del _SUBSCOPE_COUNT[k]
+        return False
+
+
+def get_variable_scope():
+    return _VarScopeInfo(_SCOPES[-1][0])
+
+
+def get_variable(name, shape, initializer):
+    full = (_SCOPES[-1][0] + "/" if _SCOPES[-1][0] else "") + name
+    if _SCOPES[-1][1]:
+        for v in _VARIABLES:
+            if v.op.name == full:
+                return v
+        raise ValueError("Variable %s does not exist, or was not created with tf.get_variable()" % full)
+    if any(v.op.name == full for v in _VARIABLES):
+        raise ValueError("Variable %s already exists, disallowed. Did you mean to set reuse=True?" % full)
+    return Variable(full, list(shape), initializer)
+
+
+def _xavier(shape):
+    lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+    return np.random.uniform(-lim, lim, size=shape)
+
+
+def fully_connected(inputs, num_outputs, activation_fn=None, scope=None, reuse=None):
+    """tf.contrib.layers.fully_connected defaults: xavier weights, zero biases, variables under <scope>/fully_connected[_k]."""
+    with variable_scope(scope, "fully_connected", [inputs], reuse=reuse):
+        W = get_variable("weights", [inputs.last_dim, num_outputs], _xavier)
+        b = get_variable("biases", [num_outputs], lambda s: np.zeros(s))
+    out = Tensor(lambda c, x, w, bb: x @ w + bb, (inputs, W, b), "fully_connected/BiasAdd", num_outputs)
+    return activation_fn(out) if activation_fn is not None else out
+
+
+# -- ops -------------------------------------------------------------------------------------------------------------------------
+def placeholder(dtype, shape=None, name=None):
+    t = Tensor(None, (), name or "Placeholder", None if not shape else shape[-1])
+    t._fn = lambda c: torch.as_tensor(np.asarray(c.feed[t], np.float32))   # fed values are cast to the placeholder's float32
+    return t
+
+
+def concat(values, axis):
+    return Tensor(lambda c, *xs: torch.cat(xs, dim=axis), values, "concat", sum(v.last_dim for v in values) if axis in (1, -1) else None)
+
+
+def reduce_mean(x, axis=None, keep_dims=False):
+    return Tensor(lambda c, a: a.mean() if axis is None else a.mean(dim=axis, keepdim=keep_dims), (x,), "Mean")
+
+
+def square(x):
+    return Tensor(lambda c, a: a * a, (x,), "Square", x.last_dim)
+
+
+def log(x):
+    return Tensor(lambda c, a: torch.log(a), (x,), "Log", x.last_dim)
+
+
+def shape(x):
+    return Tensor(lambda c, a: tuple(a.shape), (x,), "Shape")
+
+
+def random_uniform(shp):
+    return Tensor(lambda c, s: torch.as_tensor(np.asarray(NOISE[0](tuple(s)), np.float32)), (shp,), "random_uniform")
+
+
+def clip_by_norm(t, clip_norm):
+    def run(c, a):
+        n = torch.sqrt(torch.sum(a * a))
+        return a * clip_norm / torch.maximum(n, torch.tensor(clip_norm, dtype=a.dtype))
+    return Tensor(run, (t,), "clip_by_norm")
+
+
+def group(*ops):
+    return Tensor(lambda c, *a: None, ops, "group_deps")
+
+
+def global_variables():
+    return list(_VARIABLES)
+
+
+def variables_initializer(variables):
+    return Tensor(lambda c: None, (), "init")
+
+
+def get_collection(key, scope=None):
+    return [v for v in _VARIABLES if scope is None or re.match(scope, v.name)]
+
+
+class _Gradients(object):
+    """One backward pass per run for all of an optimizer's variables."""
+
+    def __init__(self, loss, var_list):
+        self.loss, self.var_list = loss, var_list
+
+    def node(self, i):
+        def run(c):
+            key = ("grads", id(self))
+            if key not in c.cache:
+                c.cache[key] = torch.autograd.grad(self.loss.eval(c), [v.value for v in self.var_list], retain_graph=True)
+            return c.cache[key][i]
+        # the loss is listed as an input so that the node is not mistaken for a placeholder
+        return Tensor(lambda c, _loss: run(c), (self.loss,), "gradients")
+
+
+class AdamOptimizer(object):
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.lr, self.b1, self.b2, self.eps, self.t, self.slots = learning_rate, beta1, beta2, epsilon, 0, {}
+
+    def compute_gradients(self, loss, var_list=None):
+        g = _Gradients(loss, var_list)
+        return [(g.node(i), v) for i, v in enumerate(var_list)]
+
+    def apply_gradients(self, grads_and_vars):
+        grads_and_vars = list(grads_and_vars)
+
+        def run(c, *grads):
+            self.t += 1
+            lr_t = np.float32(self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t))
+            with torch.no_grad():
+                for g, (_, v) in zip(grads, grads_and_vars):
+                    m, s = self.slots.setdefault(id(v), (torch.zeros_like(v.value), torch.zeros_like(v.value)))
+                    m.mul_(np.float32(self.b1)).add_(np.float32(1.0 - self.b1) * g)
+                    s.mul_(np.float32(self.b2)).add_(np.float32(1.0 - self.b2) * g * g)
+                    v.value.sub_(lr_t * m / (torch.sqrt(s) + np.float32(self.eps)))
+            return None
+        return Tensor(run, [g for g, _ in grads_and_vars], "Adam")
+
+
+class Session(object):
+    def __init__(self, config=None):
+        pass
+
+    def __enter__(self):
+        _SESSIONS.append(self)
+        return self
+
+    def __exit__(self, *a):
+        _SESSIONS.pop()
+        return False
+
+    def run(self, fetches, feed_dict=None):
+        ctx = _Ctx(feed_dict or {})
+        single = not isinstance(fetches, (list, tuple))
+        out = []
+        for f in ([fetches] if single else fetches):   # in fetch order: outputs before the update group (tf_util.py:325-326)
+            r = f.eval(ctx)
+            out.append(r.detach().numpy().copy() if torch.is_tensor(r) else r)
+        return out[0] if single else out
+
+
+def get_default_session():
+    return _SESSIONS[-1]
+
+
+def install():
+    """Registers the stand-in as ``tensorflow`` (+ the sub-modules the reference imports) and returns it."""
+    tf = types.ModuleType("tensorflow")
+    for k, v in globals().items():
+        if not k.startswith("_") and k not in ("re", "sys", "types", "np", "torch", "install"):
+            setattr(tf, k, v)
+    tf.float32, tf.int32 = "float32", "int32"
+    tf.nn = types.SimpleNamespace(relu=lambda x: Tensor(lambda c, a: torch.relu(a), (x,), "Relu", x.last_dim),
+                                  softmax=lambda x, axis=None: Tensor(lambda c, a: torch.softmax(a, dim=-1 if axis is None else axis),
+                                                                      (x,), "Softmax", x.last_dim))
+    tf.train = types.SimpleNamespace(AdamOptimizer=AdamOptimizer, Saver=lambda *a, **k: object())
+    tf.GraphKeys = types.SimpleNamespace(GLOBAL_VARIABLES="variables", TRAINABLE_VARIABLES="trainable_variables")
+    tf.ConfigProto = lambda **k: None
+    contrib, layers = types.ModuleType("tensorflow.contrib"), types.ModuleType("tensorflow.contrib.layers")
+    layers.fully_connected = fully_connected
+    contrib.layers = layers
+    tf.contrib = contrib
+    python, ops = types.ModuleType("tensorflow.python"), types.ModuleType("tensorflow.python.ops")
+    ops.math_ops, ops.nn = types.SimpleNamespace(), types.SimpleNamespace()
+    python.ops = ops
+    tf.python = python
+    sys.modules.update({"tensorflow": tf, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers,
+                        "tensorflow.python": python, "tensorflow.python.ops": ops})
+    return tf

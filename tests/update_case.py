@@ -16,12 +16,22 @@ class _Discrete(object):
         self.n = n
 
 
-def build_oracle_trainers():
-    args = types.SimpleNamespace(lr=1e-2, gamma=0.95, batch_size=24, num_units=16, max_episode_len=4)
+def make_args():
+    return types.SimpleNamespace(lr=1e-2, gamma=0.95, batch_size=24, num_units=16, max_episode_len=4)
+
+
+def shared_noise(seed=77):
+    """One U[0,1) float32 stream for every Gumbel draw of a run (what a single TF graph-level generator would be)."""
+    rng = np.random.RandomState(seed)
+    return lambda shape: np.minimum(rng.uniform(size=shape).astype(np.float32), np.nextafter(np.float32(1), np.float32(0)))
+
+
+def build_oracle_trainers(noise=None, act_space_n=None):
+    args = make_args()
     obs_shape_n = [(d,) for d in OBS_DIMS]
-    act_space_n = [_Discrete(5)] * N
+    act_space_n = act_space_n or [_Discrete(5)] * N
     return [OracleAgentTrainer("agent_%d" % i, None, obs_shape_n, act_space_n, i, args, local_q_func=(i == 2),
-                               rng=np.random.RandomState(100 + i)) for i in range(N)]
+                               rng=np.random.RandomState(100 + i), noise=noise) for i in range(N)]
 
 
 def transition(k):
