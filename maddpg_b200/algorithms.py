@@ -16,7 +16,8 @@ a handful of grouped launches (grid.y = agent) from csrc/mdp_td3.cu plus the MAD
 
 Every gradient of a step is taken before any Adam step (one ``session.run`` in the reference).  Agents are ordered by sorted
 name (``U.concat_map``, tf_util.py:53-55).  ``shared_policy`` / ``shared_critic`` groups keep one member -- the first name's --
-with the reference's one-loss semantics (policygroup.py:129-135, criticgroup.py:94-100); the ``normalize`` option is the
+with the reference's one-loss semantics (policygroup.py:129-135, criticgroup.py:94-100) and its assertion that all names have
+equal spaces (which ``Coma``, whose global critic group is always shared, therefore demands too); the ``normalize`` option is the
 inference-mode BatchNorm the modules apply (a constant gain, see BATCH_NORM_INFERENCE).  All arithmetic runs in libmaddpg_b200.so; there is no PyTorch or CPU fallback.
 """
 import ctypes as C
@@ -297,10 +298,12 @@ class MultiAgentAlgBase(object):
             graph.replay()
         return self._losses(B, policy_step)
 
-    def _check_shared(self):
-        if self.sp >= 0 and (len(set(self.obs_dims)) > 1 or len(set(self.act_dims)) > 1 or len(set(self._scale)) > 1
-                             or len(set(self._shift)) > 1):
-            raise AssertionError("a shared policy needs equal observation and action spaces (policygroup.py:32-34)")
+    def _check_shared(self, always_shared_critic=False):
+        """A shared group asserts that every name has the first name's spaces (policygroup.py:32-34, criticgroup.py:28-30)."""
+        if (self.sp >= 0 or self.sc >= 0 or always_shared_critic) and (
+                len(set(self.obs_dims)) > 1 or len(set(self.act_dims)) > 1 or len(set(self._scale)) > 1 or len(set(self._shift)) > 1):
+            raise AssertionError("a shared policy / critic group needs equal observation and action spaces "
+                                 "(policygroup.py:32-34, criticgroup.py:28-30)")
 
     def _zero_stats(self):
         for c in self._cores:
@@ -491,7 +494,7 @@ class Coma(MultiAgentAlgBase):
         self.personal = self._group(3)
         self.shared = self.names.index(self.first)
         self.sp = self.shared if shared_policy else -1
-        self._check_shared()
+        self._check_shared(always_shared_critic=True)   # ComaModule's global critic group is CriticGroup(shared=True), always
 
     def _predict_policies(self):
         return self.best

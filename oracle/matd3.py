@@ -1,10 +1,16 @@
 """TEST INFRASTRUCTURE -- CPU restatement (numpy, float32) of the fork's tanh-policy algorithms: MATD3 and the best/worst-policy
 "COMA" variant.
 
-PARITY UNPINNED against the reference's own execution: the modules need TensorFlow 1.x and DeepMind Sonnet 1.x (``import sonnet
-as snt``), neither is installed nor fetchable, and the reference holds no golden vector for them (its tests/test_policy.py and
-tests/test_maddpg.py build TF graphs).  The restated gradients are cross-checked against torch autograd in float64
-(tests/test_oracle_matd3.py).
+PARITY PARTLY PINNED.  The modules need TensorFlow 1.x and DeepMind Sonnet 1.x (``import sonnet as snt``), neither is installed
+nor fetchable, and the reference holds no golden vector for them (its tests/test_policy.py and tests/test_maddpg.py build TF
+graphs).  What IS pinned is the wiring: the fork's own ``Coma`` and ``Maddpg`` classes, their modules, groups, policies, critics
+and ``TfFunction`` plumbing were executed unmodified in the build container on tests/tf_shim.py, a torch-backed stand-in for the
+TensorFlow and Sonnet calls those files make (tests/golden/make_fork_graph_golden.py -> fork_graph_ref.npz), and ComaOracle /
+MaddpgOracle reproduce the losses ``train_step`` returned to 1.5e-6 relative and every variable after three train steps +
+target updates to 1.3e-7 (tests/test_oracle_matd3.py::test_oracle_matches_the_fork_graph_code).  The same run records that the
+reference's ``MaTd3`` cannot be constructed (below), so MaTd3Oracle has nothing to be pinned to beyond the pieces it shares with
+the other two (Policy, Critic, the groups, the target update).  The primitive op semantics (dense layer, tanh, Adam) are the
+stand-in's, restated; every restated gradient is also cross-checked against torch autograd in float64.
 
 What is restated (reference file:line):
   LaggingNetwork            maddpg/modules/laggingnetwork.py:15-48   running + target snt.nets.MLP (ReLU, linear last layer);
@@ -26,6 +32,9 @@ Things the reference does that look like slips but are what its graph computes (
   * COMA's shared global critic trains on the FIRST name's reward and TD target only (criticgroup.py:94-100), its "personal
     reward" is Q_global(o, a) - Q_global^target(o', worst(o')) for every name, and the best-policy TD actions come from the
     RUNNING best policies (``.actions``), no target noise.
+  * ``CriticGroup(shared=True)`` / ``PolicyGroup(shared=True)`` assert that every name has the first name's spaces
+    (criticgroup.py:28-30, policygroup.py:32-34) -- ComaModule's global critic group is always shared, so the reference's Coma
+    only accepts equal spaces.
 One thing is NOT reproducible: ``MaTD3Module._build`` calls ``PolicyGroup.create_optimizers(target_vals, policies.entropy)``
 (matd3module.py:98-99) but the method takes one argument (policygroup.py:123) -- building the reference's MATD3 graph raises
 TypeError.  The restatement drops the extra argument (the "entropy" is not used by any loss in the fork).

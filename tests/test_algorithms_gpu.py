@@ -161,15 +161,15 @@ def test_matd3_compute_loss_leaves_the_state_untouched_and_philox_noise_is_sane(
 def test_coma_train_steps_match_oracle(B):
     from maddpg_b200 import _lib
     from maddpg_b200.algorithms import Coma
-    o = ComaOracle(OBS, ACT, LOW, HIGH, seed=12, first=NAMES[0])
-    alg = Coma(*spaces(), seed=3)
+    o = ComaOracle(*EQ, seed=12, first=NAMES[0])      # equal spaces: ComaModule's shared global critic asserts them
+    alg = Coma(*spaces(*EQ), seed=3)
     assert alg.names == o.names and alg.first == NAMES[0] and alg.names[alg.shared] == NAMES[0]
     load_policy(alg.best, o.best, o.names)
     load_policy(alg.worst, o.worst, o.names)
     load_critic(alg.personal, o.personal, o.names)
     load_critic(alg.global_critic, {n: o.global_critic for n in o.names}, o.names)
     for step in (1, 2, 3):
-        obs, act, rew, obs_n, done, _ = make_batch(B, 200 + step)
+        obs, act, rew, obs_n, done, _ = make_batch(B, 200 + step, *EQ)
         want = o.train_step(obs, act, rew, obs_n, done, step=step)
         got = alg.train_step(obs, act, rew, obs_n, done, step=step)
         losses_close(got["critic"], want["critic"], "step %d critic" % step)
@@ -306,14 +306,15 @@ def test_normalize_option_is_inference_mode_batch_norm(cls_name):
         for c in range(2):
             load_critic(alg.critics[c], o.critics[c], o.names)
     else:
-        o = ComaOracle(OBS, ACT, LOW, HIGH, seed=52, first=NAMES[0])
-        alg = algorithms.Coma(*spaces(), normalize=nz, seed=14)
+        o = ComaOracle(*EQ, seed=52, first=NAMES[0])
+        alg = algorithms.Coma(*spaces(*EQ), normalize=nz, seed=14)
         load_policy(alg.best, o.best, o.names)
         load_policy(alg.worst, o.worst, o.names)
         load_critic(alg.personal, o.personal, o.names)
         load_critic(alg.global_critic, {n: o.global_critic for n in o.names}, o.names)
     o.normalize = nz
-    obs, act, rew, obs_n, done, z = make_batch(B, 800)
+    dims = (OBS, ACT, LOW, HIGH) if cls_name == "MaTd3" else EQ
+    obs, act, rew, obs_n, done, z = make_batch(B, 800, *dims)
     obs = {n: 3.0 * v for n, v in obs.items()}      # make the 0.05 % gain matter at the 1e-4 tolerance
     rew = {n: 5.0 * v for n, v in rew.items()}
     kw_o, kw_a = ({"z": z}, {"noise": z}) if cls_name == "MaTd3" else ({}, {})
@@ -334,14 +335,15 @@ def test_graph_replayed_steps_equal_eager_steps(cls_name):
     launch-by-launch path, and the in-kernel target noise of a replay differs from the previous replay's."""
     from maddpg_b200 import algorithms
     cls = getattr(algorithms, cls_name)
-    a, b = cls(*spaces(), seed=15), cls(*spaces(), seed=15)
+    dims = EQ if cls_name == "Coma" else (OBS, ACT, LOW, HIGH)
+    a, b = cls(*spaces(*dims), seed=15), cls(*spaces(*dims), seed=15)
     b.use_graphs = False
     for ca, cb in zip(a._cores, b._cores):
         assert torch.equal(ca.params, cb.params)
     B = 128
     kw = lambda z: {"noise": z} if cls_name == "MaTd3" else {}
     for step in range(1, 7):
-        obs, act, rew, obs_n, done, z = make_batch(B, 900 + step)
+        obs, act, rew, obs_n, done, z = make_batch(B, 900 + step, *dims)
         la = a.train_step(obs, act, rew, obs_n, done, step=2 * step, **kw(z))
         lb = b.train_step(obs, act, rew, obs_n, done, step=2 * step, **kw(z))
         for key in lb:
@@ -354,7 +356,7 @@ def test_graph_replayed_steps_equal_eager_steps(cls_name):
         assert float(d.max()) <= 6.6e-4 and float((d > 5e-6).float().mean()) <= 0.01
         assert torch.equal(ca.adam_t, cb.adam_t)
     if cls_name == "MaTd3":     # Philox target noise under replay: a fresh stream every time
-        obs, act, rew, obs_n, done, z = make_batch(B, 950)
+        obs, act, rew, obs_n, done, z = make_batch(B, 950, *dims)
         seen = []
         for _ in range(4):
             a.train_step(obs, act, rew, obs_n, done, step=2)
@@ -380,6 +382,10 @@ def test_save_load_round_trip_and_refusals(tmp_path):
         assert float(la["critic"][n]) == pytest.approx(float(lb["critic"][n]), rel=1e-6)
     with pytest.raises(AssertionError):
         MaTd3(*spaces(), shared_policy=True)      # unequal spaces (policygroup.py:32-34)
+    with pytest.raises(AssertionError):
+        MaTd3(*spaces(), shared_critic=True)      # (criticgroup.py:28-30)
+    with pytest.raises(AssertionError):
+        Coma(*spaces())                           # ComaModule's global critic group is always shared
     # the fork's dict replay (common/replaybuffer.py): ring overwrite and dict-of-lists samples
     rb = DictReplayBuffer(5)
     for t in range(8):

@@ -222,3 +222,55 @@ def test_sorted_name_order(cls):
     assert o.names == sorted(NAMES)      # U.concat_map sorts by key (tf_util.py:53-55)
     if cls is ComaOracle:
         assert o.first == "b_agent"      # the shared group is named after the FIRST key in insertion order (criticgroup.py:24)
+
+
+def test_oracle_matches_the_fork_graph_code():
+    """tests/golden/fork_graph_ref.npz: the fork's OWN ``Coma`` / ``Maddpg`` algorithm classes, modules, groups, policies, critics
+    and ``TfFunction`` plumbing executed unmodified on the torch-backed stand-in for TensorFlow + Sonnet (tests/tf_shim.py,
+    tests/golden/make_fork_graph_golden.py).  The restated oracle must reproduce the losses ``train_step`` returned, the
+    predictions, the values and every variable after three train steps + target updates -- i.e. the same wiring: shared global
+    critic on the first name's reward, personal reward, worst-policy sign, losses through the TARGET critics, per-optimizer
+    variable sets, the 5e-3 polyak.  Also recorded there: the reference's ``MaTd3`` cannot be constructed at all."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fork_graph_ref.npz"))
+    assert "takes 2 positional arguments but 3 were given" in str(gold["matd3_error"])        # matd3module.py:98-99
+    assert "'NoneType' object has no attribute 'get'" in str(gold["maddpg_none_hyperparameters_error"])   # maddpg.py:19-29
+    assert str(gold["coma_unequal_spaces_error"]) == "AssertionError"                          # criticgroup.py:28-30
+    eq = (EQ_OBS, EQ_ACT, EQ_LOW, EQ_HIGH)
+    worst = {"loss": 0.0, "var": 0.0}
+
+    def drive(o, prefix, dims):
+        for step in (1, 2, 3):
+            obs, act, rew, obs_n, done, _ = make_batch(48, 1000 + step, *dims)
+            res = o.train_step(obs, act, rew, obs_n, done, step=step)
+            o.run_updates()
+            for kind in ("actor", "critic"):
+                got, want = np.asarray([res[kind][n] for n in NAMES], np.float64), gold["%s_s%d_%s" % (prefix, step, kind)]
+                worst["loss"] = max(worst["loss"], float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-2))))
+                np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-7, err_msg="%s step %d %s" % (prefix, step, kind))
+        obs = make_batch(16, 2000, *dims)[0]
+        pred, val = o.predict(obs), o.compute_values(obs)
+        for n in NAMES:
+            np.testing.assert_allclose(pred[n], gold["%s_predict_%s" % (prefix, n)], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(val[n], gold["%s_values_%s" % (prefix, n)], rtol=1e-5, atol=1e-6)
+
+    def check(member, key):
+        for net, attr in (("running", member.running), ("target", member.target)):
+            for i, w in enumerate(attr.p):
+                d = float(np.abs(w - gold["%s_%s_%d" % (key, net, i)]).max())
+                worst["var"] = max(worst["var"], d)
+                assert d <= 2e-6, (key, net, i, d)      # 2 % of one Adam step (lr = 1e-4)
+
+    o = ComaOracle(*eq, seed=61, first=NAMES[0])
+    drive(o, "coma", eq)
+    for n in NAMES:
+        check(o.best[n], "coma_best_" + n)
+        check(o.worst[n], "coma_worst_" + n)
+        check(o.personal[n], "coma_personal_" + n)
+    check(o.global_critic, "coma_global")
+    m = MaddpgOracle(OBS, ACT, LOW, HIGH, seed=62, first=NAMES[0])
+    drive(m, "maddpg", (OBS, ACT, LOW, HIGH))
+    for n in NAMES:
+        check(m.policies[n], "maddpg_policy_" + n)
+        check(m.critics[n], "maddpg_critic_" + n)
+    print("worst relative loss difference %.2e, worst variable difference %.2e" % (worst["loss"], worst["var"]))

@@ -12,7 +12,13 @@ concatenated into which network, which variables each optimizer owns (``scope_va
 file RESTATES, from TensorFlow's documentation, is the primitive semantics: ``fully_connected`` = x @ W + b with variables
 ``<scope>/fully_connected[_k]/{weights,biases}`` (sub-scope counters reset when the enclosing named scope is left, which is what
 makes ``reuse=True`` find them), ``clip_by_norm`` = t * c / max(||t||, c), and ``AdamOptimizer`` = TF's formula with the epsilon
-outside the bias correction.  ``random_uniform`` draws from the pluggable ``NOISE`` callback.
+outside the bias correction.  ``random_uniform`` draws from the pluggable ``NOISE`` callback.  Variable
+writes of one ``Session.run`` are committed together when the run ends (every gradient of a run is taken at the variables the run
+started with).
+
+The second half stands in for the slice of DeepMind Sonnet 1.x the fork's modules use (``snt.AbstractModule``,
+``snt.reuse_variables``, ``snt.nets.MLP``) plus the extra TensorFlow calls of maddpg/modules/*.py and maddpg/algorithms/*.py, for
+tests/golden/make_fork_graph_golden.py.
 """
 import re
 import sys
@@ -44,7 +50,7 @@ def _unique(name):
 
 class _Ctx(object):
     def __init__(self, feed):
-        self.feed, self.cache = feed, {}
+        self.feed, self.cache, self.pending = feed, {}, []   # pending: variable writes, committed when the run ends
 
 
 class Tensor(object):
@@ -88,10 +94,9 @@ class Variable(Tensor):
     def eval(self, ctx):
         return self.value
 
-    def assign(self, expr):
+    def assign(self, expr, use_locking=None):
         def run(c, v):
-            with torch.no_grad():
-                self.value.copy_(v.detach())
+            c.pending.append((self, v.detach().clone()))
             return None
         return Tensor(run, (expr,), "Assign")
 
@@ -144,6 +149,11 @@ def get_variable_scope():
 
 def get_variable(name, shape, initializer):
     full = (_SCOPES[-1][0] + "/" if _SCOPES[-1][0] else "") + name
+    if _SCOPES[-1][1] == "auto":     # a Sonnet module's scope: created on the first call, shared by the later ones
+        for v in _VARIABLES:
+            if v.op.name == full:
+                return v
+        return Variable(full, list(shape), initializer)
     if _SCOPES[-1][1]:
         for v in _VARIABLES:
             if v.op.name == full:
@@ -176,7 +186,9 @@ def placeholder(dtype, shape=None, name=None):
 
 
 def concat(values, axis):
-    return Tensor(lambda c, *xs: torch.cat(xs, dim=axis), values, "concat", sum(v.last_dim for v in values) if axis in (1, -1) else None)
+    values = list(values)
+    return Tensor(lambda c, *xs: torch.cat(xs, dim=axis), values, "concat",
+                  sum(v.last_dim for v in values) if axis in (1, -1) else values[0].last_dim)
 
 
 def reduce_mean(x, axis=None, keep_dims=False):
@@ -206,8 +218,11 @@ def clip_by_norm(t, clip_norm):
     return Tensor(run, (t,), "clip_by_norm")
 
 
-def group(*ops):
-    return Tensor(lambda c, *a: None, ops, "group_deps")
+def group(*ops, name=None):
+    flat = []
+    for o in ops:
+        flat += list(o) if isinstance(o, (list, tuple)) else [o]
+    return Tensor(lambda c, *a: None, flat or (1.0,), "group_deps")
 
 
 def global_variables():
@@ -239,7 +254,7 @@ class _Gradients(object):
 
 
 class AdamOptimizer(object):
-    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8, use_locking=False):
         self.lr, self.b1, self.b2, self.eps, self.t, self.slots = learning_rate, beta1, beta2, epsilon, 0, {}
 
     def compute_gradients(self, loss, var_list=None):
@@ -257,14 +272,104 @@ class AdamOptimizer(object):
                     m, s = self.slots.setdefault(id(v), (torch.zeros_like(v.value), torch.zeros_like(v.value)))
                     m.mul_(np.float32(self.b1)).add_(np.float32(1.0 - self.b1) * g)
                     s.mul_(np.float32(self.b2)).add_(np.float32(1.0 - self.b2) * g * g)
-                    v.value.sub_(lr_t * m / (torch.sqrt(s) + np.float32(self.eps)))
+                    c.pending.append((v, v.value.detach() - lr_t * m / (torch.sqrt(s) + np.float32(self.eps))))
             return None
         return Tensor(run, [g for g, _ in grads_and_vars], "Adam")
 
 
+
+NORMAL = [lambda shape: np.random.standard_normal(size=shape).astype(np.float32)]   # N(0, 1) draws behind tf.random.normal
+
+
+def tanh(x):
+    return Tensor(lambda c, a: torch.tanh(a), (x,), "Tanh", x.last_dim)
+
+
+def clip_by_value(x, lo, hi):
+    return Tensor(lambda c, a: torch.clamp(a, lo, hi), (x,), "clip_by_value", x.last_dim)
+
+
+def random_normal(shp, mean=0.0, stddev=1.0):
+    return Tensor(lambda c, s: torch.as_tensor(np.asarray(NORMAL[0](tuple(s)), np.float32)) * np.float32(stddev) + np.float32(mean),
+                  (shp,), "random_normal")
+
+
+def stack(values, axis=0):
+    return Tensor(lambda c, *xs: torch.stack(xs, dim=axis), values, "stack")
+
+
+def reduce_min(x, axis=None):
+    return Tensor(lambda c, a: a.min() if axis is None else a.min(dim=axis).values, (x,), "Min")
+
+
+def reduce_std(x, axis=None):
+    return Tensor(lambda c, a: a.std(unbiased=False) if axis is None else a.std(dim=axis, unbiased=False), (x,), "reduce_std")
+
+
+def stop_gradient(x):
+    return Tensor(lambda c, a: a.detach(), (x,), "StopGradient", x.last_dim)
+
+
+def split(value, num, axis=0):
+    return [Tensor((lambda k: lambda c, a: torch.chunk(a, num, dim=axis)[k])(k), (value,), "split", value.last_dim) for k in range(num)]
+
+
+_CONTROL = [()]
+
+
+class control_dependencies(object):
+    """Nodes created inside run the given ops after their own inputs (the losses a TfFunction returns are computed from the
+    pre-step variables: the same forward pass feeds the gradients)."""
+
+    def __init__(self, ops):
+        self.ops = tuple(ops)
+
+    def __enter__(self):
+        _CONTROL.append(_CONTROL[-1] + self.ops)
+
+    def __exit__(self, *a):
+        _CONTROL.pop()
+        return False
+
+
+def identity(x):
+    deps = _CONTROL[-1]
+
+    def run(c, a):
+        for d in deps:
+            d.eval(c)
+        return a
+    return Tensor(run, (x,), "Identity", getattr(x, "last_dim", None))
+
+
+def no_op():
+    deps = _CONTROL[-1]
+
+    def run(c, _one):
+        for d in deps:
+            d.eval(c)
+        return None
+    return Tensor(run, (1.0,), "NoOp")
+
+
+class Graph(object):
+    def as_default(self):
+        return self
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def global_variables_initializer():
+    return Tensor(lambda c, _one: None, (1.0,), "init")
+
+
 class Session(object):
-    def __init__(self, config=None):
-        pass
+    def __init__(self, config=None, graph=None):
+        self.graph = graph or Graph()
 
     def __enter__(self):
         _SESSIONS.append(self)
@@ -276,11 +381,17 @@ class Session(object):
 
     def run(self, fetches, feed_dict=None):
         ctx = _Ctx(feed_dict or {})
+        if isinstance(fetches, dict):
+            keys = list(fetches)
+            return dict(zip(keys, self.run([fetches[k] for k in keys], feed_dict)))
         single = not isinstance(fetches, (list, tuple))
         out = []
         for f in ([fetches] if single else fetches):   # in fetch order: outputs before the update group (tf_util.py:325-326)
             r = f.eval(ctx)
             out.append(r.detach().numpy().copy() if torch.is_tensor(r) else r)
+        with torch.no_grad():   # every read of a run sees the variables as they were when it started; writes land together
+            for var, value in ctx.pending:
+                var.value.copy_(value)
         return out[0] if single else out
 
 
@@ -292,7 +403,7 @@ def install():
     """Registers the stand-in as ``tensorflow`` (+ the sub-modules the reference imports) and returns it."""
     tf = types.ModuleType("tensorflow")
     for k, v in globals().items():
-        if not k.startswith("_") and k not in ("re", "sys", "types", "np", "torch", "install"):
+        if not k.startswith("_") and k not in ("re", "sys", "types", "np", "torch", "install", "install_sonnet"):
             setattr(tf, k, v)
     tf.float32, tf.int32 = "float32", "int32"
     tf.nn = types.SimpleNamespace(relu=lambda x: Tensor(lambda c, a: torch.relu(a), (x,), "Relu", x.last_dim),
@@ -300,7 +411,9 @@ def install():
                                                                       (x,), "Softmax", x.last_dim))
     tf.train = types.SimpleNamespace(AdamOptimizer=AdamOptimizer, Saver=lambda *a, **k: object())
     tf.GraphKeys = types.SimpleNamespace(GLOBAL_VARIABLES="variables", TRAINABLE_VARIABLES="trainable_variables")
-    tf.ConfigProto = lambda **k: None
+    tf.ConfigProto = lambda **k: types.SimpleNamespace(gpu_options=types.SimpleNamespace())
+    tf.random = types.SimpleNamespace(normal=random_normal)
+    tf.math = types.SimpleNamespace(reduce_std=reduce_std)
     contrib, layers = types.ModuleType("tensorflow.contrib"), types.ModuleType("tensorflow.contrib.layers")
     layers.fully_connected = fully_connected
     contrib.layers = layers
@@ -312,3 +425,88 @@ def install():
     sys.modules.update({"tensorflow": tf, "tensorflow.contrib": contrib, "tensorflow.contrib.layers": layers,
                         "tensorflow.python": python, "tensorflow.python.ops": ops})
     return tf
+
+
+# -- the slice of DeepMind Sonnet 1.x the fork's modules use -----------------------------------------------------------------------
+class AbstractModule(object):
+    """snt.AbstractModule: the module's variable scope is fixed at construction (uniquified default name); every call to the
+    module -- and every ``snt.reuse_variables`` method -- runs inside that scope and shares its variables."""
+
+    def __init__(self, _sentinel=None, custom_getter=None, name=None):
+        with variable_scope(None, default_name=name or type(self).__name__.lower()) as scope:
+            self._scope_name = scope.name
+        self._connected = False
+
+    def _enter(self):
+        return _ModuleScope(self._scope_name)
+
+    def __call__(self, *args, **kwargs):
+        with self._enter():
+            out = self._build(*args, **kwargs)
+        self._connected = True
+        return out
+
+
+class _ModuleScope(object):
+    """Re-enters a module's absolute scope; variables are created on first use and found afterwards (template semantics)."""
+
+    def __init__(self, full):
+        self.full = full
+
+    def __enter__(self):
+        _SCOPES.append((self.full, "auto"))
+
+    def __exit__(self, *a):
+        _SCOPES.pop()
+        return False
+
+
+def reuse_variables(method):
+    def wrapped(self, *args, **kwargs):
+        with self._enter():
+            return method(self, *args, **kwargs)
+    return wrapped
+
+
+class Linear(AbstractModule):
+    def __init__(self, output_size, name="linear"):
+        super().__init__(name=name)
+        self.output_size = output_size
+
+    def _build(self, inputs):
+        self.w = get_variable("w", [inputs.last_dim, self.output_size], lambda s: np.random.standard_normal(s) / np.sqrt(s[0]))
+        self.b = get_variable("b", [self.output_size], lambda s: np.zeros(s))
+        return Tensor(lambda c, x, w, b: x @ w + b, (inputs, self.w, self.b), "linear/add", self.output_size)
+
+
+class MLP(AbstractModule):
+    """snt.nets.MLP(output_sizes): Linear layers linear_0..linear_{n-1}, ReLU between them, no final activation."""
+
+    def __init__(self, output_sizes, name="mlp"):
+        super().__init__(name=name)
+        with self._enter():
+            self._layers = [Linear(n, name="linear_%d" % i) for i, n in enumerate(output_sizes)]
+
+    def _build(self, inputs):
+        net = inputs
+        for i, layer in enumerate(self._layers):
+            net = layer(net)
+            if i + 1 < len(self._layers):
+                net = Tensor(lambda c, a: torch.relu(a), (net,), "Relu", net.last_dim)
+        return net
+
+    @property
+    def trainable_variables(self):
+        out = []
+        for layer in self._layers:
+            out += [layer.w, layer.b]
+        return tuple(out)
+
+
+def install_sonnet():
+    snt = types.ModuleType("sonnet")
+    snt.AbstractModule, snt.reuse_variables, snt.Linear = AbstractModule, reuse_variables, Linear
+    snt.nets = types.SimpleNamespace(MLP=MLP)
+    snt.BatchNormV2 = None
+    sys.modules["sonnet"] = snt
+    return snt
