@@ -417,7 +417,10 @@ class DictReplayBuffer(object):
 
 
 class MaTd3(MultiAgentAlgBase):
-    """maddpg/algorithms/matd3.py:11-81 over MaTD3Module (matd3module.py:20-134)."""
+    """maddpg/algorithms/matd3.py:11-81 over MaTD3Module (matd3module.py:20-134).  Two deliberate differences from the reference
+    as written: it can be constructed (the reference's module passes ``create_optimizers`` an argument it does not take,
+    matd3module.py:98-99 -- dropped), and a critic-only step returns ``{'critic': {name: loss}}`` where the reference pushes the
+    un-prefixed dict through ``unflatten_map`` and returns the names split at "_" (matd3.py:71-72)."""
 
     GAMMA = 0.9   # MaTD3Module._build(..., gamma=0.9), matd3module.py:47
 

@@ -8,8 +8,9 @@ and ``TfFunction`` plumbing were executed unmodified in the build container on t
 TensorFlow and Sonnet calls those files make (tests/golden/make_fork_graph_golden.py -> fork_graph_ref.npz), and ComaOracle /
 MaddpgOracle reproduce the losses ``train_step`` returned to 1.5e-6 relative and every variable after three train steps +
 target updates to 1.3e-7 (tests/test_oracle_matd3.py::test_oracle_matches_the_fork_graph_code).  The same run records that the
-reference's ``MaTd3`` cannot be constructed (below), so MaTd3Oracle has nothing to be pinned to beyond the pieces it shares with
-the other two (Policy, Critic, the groups, the target update).  The primitive op semantics (dense layer, tanh, Adam) are the
+reference's ``MaTd3`` cannot be constructed as written (below); with the one crashing call made tolerant of its extra argument --
+the generator's only modification of reference code -- MaTD3Module / MaTd3 run too (noisy targets fed the recorded N(0,1) draws,
+four steps: critic-only, full, critic-only, full) and MaTd3Oracle reproduces them to the same accuracy.  The primitive op semantics (dense layer, tanh, Adam) are the
 stand-in's, restated; every restated gradient is also cross-checked against torch autograd in float64.
 
 What is restated (reference file:line):
@@ -37,7 +38,10 @@ Things the reference does that look like slips but are what its graph computes (
     only accepts equal spaces.
 One thing is NOT reproducible: ``MaTD3Module._build`` calls ``PolicyGroup.create_optimizers(target_vals, policies.entropy)``
 (matd3module.py:98-99) but the method takes one argument (policygroup.py:123) -- building the reference's MATD3 graph raises
-TypeError.  The restatement drops the extra argument (the "entropy" is not used by any loss in the fork).
+TypeError.  The restatement drops the extra argument (the "entropy" is not used by any loss in the fork).  And one thing is not
+reproduced on purpose: on critic-only steps ``MaTd3._train_step`` passes the un-prefixed per-name loss dict through
+``unflatten_map`` (matd3.py:71-72), which splits every name at its first "_" ({'a': {'agent': loss}, ...} for "a_agent") and raises
+ValueError for a name without one; here, and in maddpg_b200.algorithms, those losses come back as {'critic': {name: loss}}.
 
 All optimizer steps of one ``train_step`` belong to one ``session.run``: every gradient is taken at the pre-step variables.
 Agents are ordered by sorted name (``U.concat_map``, tf_util.py:53-55).  Nothing under maddpg_b200/ imports this module.

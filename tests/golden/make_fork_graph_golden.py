@@ -9,8 +9,10 @@ Sonnet 1.x calls those files make.  Build container only:
 As with make_graph_golden.py the primitive ops are the stand-in's (restated), everything the fork's code decides is executed for
 real: which policies / critics / targets feed which loss, the shared global critic on the first name's reward, the personal
 reward, the sign of the worst policy's loss, which variables each optimizer owns, the 5e-3 "polyak" target update, what
-``train_step`` returns.  Two facts about the reference are recorded as well: ``MaTd3(...)`` cannot be constructed (TypeError, the
-two-argument ``create_optimizers`` call) and ``Maddpg(...)`` needs a truthy ``hyperparameters`` that it then discards.
+``train_step`` returns.  Facts about the reference recorded as well: ``MaTd3(...)`` cannot be constructed (TypeError, the
+two-argument ``create_optimizers`` call) -- it is then run with that one call made tolerant of its extra argument, the only
+modification of reference code here --, ``Maddpg(...)`` needs a truthy ``hyperparameters`` that it then discards, ``Coma`` asserts
+equal spaces, and MaTd3's critic-only steps return their per-name losses split at the "_" of the names.
 oracle/matd3.py must reproduce the recorded losses, predictions, values and variables
 (tests/test_oracle_matd3.py::test_oracle_matches_the_fork_graph_code).
 """
@@ -143,13 +145,58 @@ def main():
     for i, name in enumerate(NAMES):
         dump(out, "maddpg_policy_" + name, i)
         dump(out, "maddpg_critic_" + name, n + i)
-    # ---- MaTd3: the reference's graph cannot be built
+    # ---- MaTd3: the reference's graph cannot be built ...
     tf_shim.reset()
     try:
         MaTd3(obs_space, act_space)
         out["matd3_error"] = np.asarray("")
     except TypeError as e:
         out["matd3_error"] = np.asarray(str(e))
+    # ... unless the one call that kills it is made to tolerate its extra argument: PolicyGroup.create_optimizers(values, entropy)
+    # (matd3module.py:98-99 against policygroup.py:123).  The ONLY modification of reference code in this file: the argument is
+    # dropped, everything else of MaTD3Module / MaTd3 runs as written.  LaggingNetworks: policies[names], critics 1, critics 2.
+    import maddpg.modules.policygroup as policygroup_module
+    original = policygroup_module.PolicyGroup.create_optimizers
+    policygroup_module.PolicyGroup.create_optimizers = lambda self, values, *dropped: original(self, values)
+    from oracle.matd3 import MaTd3Oracle
+    tf_shim.reset()
+    alg = MaTd3(obs_space, act_space)
+    _ = alg.session
+    assert len(tf_shim._VARIABLES) == 3 * n * 12
+    o = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=63)
+    for i, name in enumerate(NAMES):
+        load(i, o.policies[name])
+        load(n + i, o.critics[0][name])
+        load(2 * n + i, o.critics[1][name])
+    queue = []
+
+    def normal(shape):      # tf.random.normal of the noisy targets: one (B, K_name) draw per policy, sorted-name order
+        z = queue.pop(0)
+        assert tuple(shape) == z.shape, (shape, z.shape)
+        return z
+    tf_shim.NORMAL[0] = normal
+    for step in (1, 2, 3, 4):
+        obs, act, rew, obs_n, done, z = make_batch(48, 3000 + step)
+        queue[:] = [z[name] for name in sorted(NAMES)]
+        res = alg.train_step(obs, act, rew, obs_n, done, step)
+        assert not queue
+        alg.run_updates()
+        if step % 2 == 0:
+            out["matd3_s%d_actor" % step] = np.asarray([res["actor"][nm] for nm in NAMES], np.float64)
+            out["matd3_s%d_critic" % step] = np.asarray([res["critic"][nm] for nm in NAMES], np.float64)
+        else:   # critic-only steps: unflatten_map splits the un-prefixed names at "_" (matd3.py:71-72, utils_common.py:69-77)
+            out["matd3_s%d_raw_keys" % step] = np.asarray(sorted(res))
+            out["matd3_s%d_critic" % step] = np.asarray([res[nm.split("_", 1)[0]][nm.split("_", 1)[1]] for nm in NAMES], np.float64)
+    obs = make_batch(16, 2000)[0]
+    pred, val = alg.predict(obs, noisy=False), alg.compute_values(obs)
+    for nm in NAMES:
+        out["matd3_predict_%s" % nm] = np.asarray(pred[nm], np.float64).reshape(16, -1)
+        out["matd3_values_%s" % nm] = np.asarray(val[nm], np.float64).reshape(16)
+    for i, name in enumerate(NAMES):
+        dump(out, "matd3_policy_" + name, i)
+        dump(out, "matd3_critic0_" + name, n + i)
+        dump(out, "matd3_critic1_" + name, 2 * n + i)
+    policygroup_module.PolicyGroup.create_optimizers = original
     np.savez_compressed(os.path.join(HERE, "fork_graph_ref.npz"), **out)
     print("wrote fork_graph_ref.npz: %d arrays" % len(out))
     print("coma step 1 actor", out["coma_s1_actor"], "critic", out["coma_s1_critic"])

@@ -230,7 +230,8 @@ def test_oracle_matches_the_fork_graph_code():
     tests/golden/make_fork_graph_golden.py).  The restated oracle must reproduce the losses ``train_step`` returned, the
     predictions, the values and every variable after three train steps + target updates -- i.e. the same wiring: shared global
     critic on the first name's reward, personal reward, worst-policy sign, losses through the TARGET critics, per-optimizer
-    variable sets, the 5e-3 polyak.  Also recorded there: the reference's ``MaTd3`` cannot be constructed at all."""
+    variable sets, the 5e-3 polyak.  Also recorded there: the reference's ``MaTd3`` cannot be constructed as written; it is run with
+    the one crashing call made tolerant of its extra argument."""
     import os
     gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fork_graph_ref.npz"))
     assert "takes 2 positional arguments but 3 were given" in str(gold["matd3_error"])        # matd3module.py:98-99
@@ -273,4 +274,25 @@ def test_oracle_matches_the_fork_graph_code():
     for n in NAMES:
         check(m.policies[n], "maddpg_policy_" + n)
         check(m.critics[n], "maddpg_critic_" + n)
+    # MaTd3: the reference's graph only builds once PolicyGroup.create_optimizers tolerates the extra argument MaTD3Module passes
+    # (the generator's one modification of reference code); twin critics, min of the targets, noisy target actions, delayed policies
+    t = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=63)
+    for step in (1, 2, 3, 4):
+        obs, act, rew, obs_n, done, z = make_batch(48, 3000 + step)
+        res = t.train_step(obs, act, rew, obs_n, done, step=step, z=z)
+        t.run_updates()
+        assert ("actor" in res) == (step % 2 == 0)
+        for kind in res:
+            got, want = np.asarray([res[kind][n] for n in NAMES], np.float64), gold["matd3_s%d_%s" % (step, kind)]
+            worst["loss"] = max(worst["loss"], float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-2))))
+            np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-7, err_msg="matd3 step %d %s" % (step, kind))
+    assert list(gold["matd3_s1_raw_keys"]) == ["a", "b", "c"]     # the reference's critic-only result: names split at "_"
+    obs = make_batch(16, 2000)[0]
+    pred, val = t.predict(obs), t.compute_values(obs)
+    for n in NAMES:
+        np.testing.assert_allclose(pred[n], gold["matd3_predict_%s" % n], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(val[n], gold["matd3_values_%s" % n], rtol=1e-5, atol=1e-6)
+        check(t.policies[n], "matd3_policy_" + n)
+        check(t.critics[0][n], "matd3_critic0_" + n)
+        check(t.critics[1][n], "matd3_critic1_" + n)
     print("worst relative loss difference %.2e, worst variable difference %.2e" % (worst["loss"], worst["var"]))
