@@ -145,6 +145,30 @@ def main():
     for i, name in enumerate(NAMES):
         dump(out, "maddpg_policy_" + name, i)
         dump(out, "maddpg_critic_" + name, n + i)
+    # ---- shared groups (PolicyGroup / CriticGroup(shared=True)): ONE policy and ONE critic LaggingNetwork, equal spaces
+    tf_shim.reset()
+    alg = Maddpg(eq_obs_space, eq_act_space, shared_policy=True, shared_critic=True, hyperparameters={"x": 1})
+    _ = alg.session
+    assert len(tf_shim._VARIABLES) == 2 * 12, len(tf_shim._VARIABLES)
+    o = MaddpgOracle(*eq, seed=64, shared_policy=True, shared_critic=True, first=NAMES[0])
+    load(0, o.policies[NAMES[0]])
+    load(1, o.critics[NAMES[0]])
+    drive(alg, out, "maddpg_shared", (1, 2, 3), eq)
+    dump(out, "maddpg_shared_policy", 0)
+    dump(out, "maddpg_shared_critic", 1)
+    tf_shim.reset()
+    alg = Coma(eq_obs_space, eq_act_space, shared_policy=True)      # best, worst: one policy each; global critic; personal[names]
+    _ = alg.session
+    assert len(tf_shim._VARIABLES) == (3 + n) * 12, len(tf_shim._VARIABLES)
+    o = ComaOracle(*eq, seed=65, first=NAMES[0], shared_policy=True)
+    load(0, o.best[NAMES[0]])
+    load(1, o.worst[NAMES[0]])
+    load(2, o.global_critic)
+    for i, name in enumerate(NAMES):
+        load(3 + i, o.personal[name])
+    drive(alg, out, "coma_shared", (1, 2), eq)
+    dump(out, "coma_shared_best", 0)
+    dump(out, "coma_shared_worst", 1)
     # ---- MaTd3: the reference's graph cannot be built ...
     tf_shim.reset()
     try:

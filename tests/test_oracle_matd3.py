@@ -274,6 +274,21 @@ def test_oracle_matches_the_fork_graph_code():
     for n in NAMES:
         check(m.policies[n], "maddpg_policy_" + n)
         check(m.critics[n], "maddpg_critic_" + n)
+    # shared groups: one policy / one critic for every name, ONE loss (the first name's) -- policygroup.py:129-135, criticgroup.py:94-100
+    ms = MaddpgOracle(*eq, seed=64, shared_policy=True, shared_critic=True, first=NAMES[0])
+    drive(ms, "maddpg_shared", eq)
+    check(ms.policies[NAMES[0]], "maddpg_shared_policy")
+    check(ms.critics[NAMES[0]], "maddpg_shared_critic")
+    cs = ComaOracle(*eq, seed=65, first=NAMES[0], shared_policy=True)
+    for step in (1, 2):
+        obs, act, rew, obs_n, done, _ = make_batch(48, 1000 + step, *eq)
+        res = cs.train_step(obs, act, rew, obs_n, done, step=step)
+        cs.run_updates()
+        for kind in ("actor", "critic"):
+            np.testing.assert_allclose(np.asarray([res[kind][n] for n in NAMES], np.float64), gold["coma_shared_s%d_%s" % (step, kind)],
+                                       rtol=2e-5, atol=2e-7, err_msg="coma shared step %d %s" % (step, kind))
+    check(cs.best[NAMES[0]], "coma_shared_best")
+    check(cs.worst[NAMES[0]], "coma_shared_worst")
     # MaTd3: the reference's graph only builds once PolicyGroup.create_optimizers tolerates the extra argument MaTD3Module passes
     # (the generator's one modification of reference code); twin critics, min of the targets, noisy target actions, delayed policies
     t = MaTd3Oracle(OBS, ACT, LOW, HIGH, seed=63)
