@@ -101,6 +101,28 @@ def main():
                     for k, v in enumerate(variables_of(i, scope)):
                         out["r%d_a%d_%s_%d" % (rnd, i, attr, k)] = v.numpy()
         out["variable_names"] = np.asarray([v.name for v in tf_shim._VARIABLES])
+        # the multi-head sample (simple_world_comm's leader): SoftMultiCategoricalPd (distributions.py:305-336), the class this
+        # fork's make_pdtype no longer reaches (:416-418) -- one random_uniform per head, in head order
+        from maddpg.common.distributions import SoftMultiCategoricalPdType, make_pdtype
+        rng = np.random.RandomState(9)
+        logits, u = rng.randn(12, 9).astype(np.float32), rng.uniform(size=(12, 9)).astype(np.float32)
+        pdtype = SoftMultiCategoricalPdType(np.array([0, 0]), np.array([4, 3]))
+        flat = pdtype.param_placeholder([None])
+        sample = pdtype.pdfromflat(flat).sample()
+        pieces = [u[:, :5], u[:, 5:]]
+
+        def per_head(shape):
+            z = pieces.pop(0)
+            assert tuple(shape) == z.shape
+            return z
+        tf_shim.NOISE[0] = per_head
+        out["multi_logits"], out["multi_u"] = logits, u
+        out["multi_sample"] = np.asarray(tf.get_default_session().run(sample, feed_dict={flat: logits}), np.float64)
+        try:
+            make_pdtype(types.SimpleNamespace(low=np.array([0, 0]), high=np.array([4, 3])))
+            out["make_pdtype_multidiscrete"] = np.asarray("")
+        except NotImplementedError:
+            out["make_pdtype_multidiscrete"] = np.asarray("NotImplementedError")
     np.savez_compressed(os.path.join(HERE, "graph_ref.npz"), **out)
     print("wrote graph_ref.npz: %d arrays; stats of round 0: %s" % (len(out), out["r0_a0_stats"]))
 

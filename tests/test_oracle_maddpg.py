@@ -214,3 +214,16 @@ def test_oracle_matches_the_reference_graph_code():
                          "agent_0/q_func/fully_connected_1/weights:0", "agent_0/q_func/fully_connected_1/biases:0",
                          "agent_0/q_func/fully_connected_2/weights:0", "agent_0/q_func/fully_connected_2/biases:0"]
     assert len(names) == N * 24      # q_func, target_q_func, p_func, target_p_func per agent: no second critic from reuse=True
+
+
+def test_multi_head_sample_matches_the_reference_class():
+    """``SoftMultiCategoricalPd.sample`` (distributions.py:305-336: per-head Gumbel-softmax, ``low`` added, concatenated), the
+    class behind simple_world_comm's MultiDiscrete leader -- executed on tests/tf_shim.py with one uniform block per head.  The
+    fork's ``make_pdtype`` no longer reaches it (:416-418 commented out: NotImplementedError for MultiDiscrete, recorded)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "graph_ref.npz"))
+    got = om.gumbel_softmax(gold["multi_logits"], gold["multi_u"], [5, 4])
+    np.testing.assert_allclose(got, gold["multi_sample"], rtol=2e-6, atol=2e-7)
+    np.testing.assert_allclose(got[:, :5].sum(axis=1), 1.0, atol=1e-6)
+    np.testing.assert_allclose(got[:, 5:].sum(axis=1), 1.0, atol=1e-6)
+    assert str(gold["make_pdtype_multidiscrete"]) == "NotImplementedError"

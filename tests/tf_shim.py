@@ -69,7 +69,8 @@ class Tensor(object):
         return ctx.cache[key]
 
     def _bin(self, other, f, name):
-        return Tensor(lambda c, a, b: f(a, b), (self, other), name, self.last_dim)
+        last = self.last_dim if self.last_dim is not None else getattr(other, "last_dim", None)
+        return Tensor(lambda c, a, b: f(a, b), (self, other), name, last)
 
     def __add__(self, o): return self._bin(o, lambda a, b: a + b, "add")
     def __radd__(self, o): return self._bin(o, lambda a, b: b + a, "add")
@@ -80,6 +81,7 @@ class Tensor(object):
     def __truediv__(self, o): return self._bin(o, lambda a, b: a / b, "div")
     def __neg__(self): return Tensor(lambda c, a: -a, (self,), "neg", self.last_dim)
     def __getitem__(self, idx): return Tensor(lambda c, a: a[idx], (self,), "strided_slice")
+    def get_shape(self): return [None, self.last_dim]      # every tensor the reference asks is a (batch, features) matrix
     __hash__ = object.__hash__
 
 
@@ -311,7 +313,15 @@ def stop_gradient(x):
 
 
 def split(value, num, axis=0):
-    return [Tensor((lambda k: lambda c, a: torch.chunk(a, num, dim=axis)[k])(k), (value,), "split", value.last_dim) for k in range(num)]
+    if np.ndim(num) == 0:
+        return [Tensor((lambda k: lambda c, a: torch.chunk(a, int(num), dim=axis)[k])(k), (value,), "split", value.last_dim)
+                for k in range(int(num))]
+    sizes = [int(x) for x in num]      # tf.split(value, size_splits, axis)
+    return [Tensor((lambda k: lambda c, a: torch.split(a, sizes, dim=axis)[k])(k), (value,), "split", sizes[k]) for k in range(len(sizes))]
+
+
+def constant(value, dtype=None):
+    return Tensor(lambda c, _one: torch.as_tensor(np.asarray(value, np.float32)), (1.0,), "Const")
 
 
 _CONTROL = [()]
