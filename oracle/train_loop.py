@@ -31,14 +31,14 @@ def make_arglist(scenario="simple_spread", batch_size=1024, num_units=64, max_ep
                               good_policy="maddpg", adv_policy="maddpg")
 
 
-def get_trainers(env, num_adversaries, obs_shape_n, arglist, seed=0):
+def get_trainers(env, num_adversaries, obs_shape_n, arglist, seed=0, noise=None):
     # experiments/train.py:63-75
     trainers = []
     for i in range(env.n):
         policy = arglist.adv_policy if i < num_adversaries else arglist.good_policy
         trainers.append(omaddpg.OracleAgentTrainer("agent_%d" % i, None, obs_shape_n, env.action_space, i, arglist,
                                                    local_q_func=(policy == "ddpg"),
-                                                   rng=np.random.RandomState(seed * 1000 + i)))
+                                                   rng=np.random.RandomState(seed * 1000 + i), noise=noise))
     return trainers
 
 
@@ -75,7 +75,7 @@ def time_rollout(scenario, num_agents=None, steps=2000, seed=0, arglist=None):
     return steps * env.n / dt, steps / dt, dt
 
 
-def run_training(scenario, num_episodes, arglist, seed=0, save_rate=1000, num_agents=None):
+def run_training(scenario, num_episodes, arglist, seed=0, save_rate=1000, num_agents=None, noise=None):
     """The whole loop of ``train(arglist)`` (experiments/train.py:76-197, training mode: no display / benchmark / restore) with
     its bookkeeping: -> (final_ep_rewards, final_ep_ag_rewards, train_step), the two lists the reference pickles for its
     learning curves (:176-178, :181-187).  PINNED: tests/golden/train_loop_ref.npz holds what the REAL train.py computed when it
@@ -84,7 +84,7 @@ def run_training(scenario, num_episodes, arglist, seed=0, save_rate=1000, num_ag
     env = ompe.make_env(scenario, np.random.RandomState(seed), num_agents)
     obs_shape_n = [env.observation_space[i].shape for i in range(env.n)]
     num_adversaries = min(env.n, arglist.num_adversaries)
-    trainers = get_trainers(env, num_adversaries, obs_shape_n, arglist, seed)
+    trainers = get_trainers(env, num_adversaries, obs_shape_n, arglist, seed, noise)   # noise: one shared U[0,1) stream, or per agent
     episode_rewards = [0.0]
     agent_rewards = [[0.0] for _ in range(env.n)]
     final_ep_rewards, final_ep_ag_rewards = [], []

@@ -55,3 +55,28 @@ def test_train_loop_matches_the_reference_script(case):
     assert np.array_equal(np.asarray(rewards, np.float64), gold[case + "_rewards"])
     assert np.array_equal(np.asarray(agrewards, np.float64), gold[case + "_agrewards"])
     assert steps >= 200      # update rounds ran (t = 100, 200 past the warm-up gate)
+
+
+def test_whole_program_matches_the_oracle_loop():
+    """tests/golden/whole_program_ref.npz: the reference's whole training program -- experiments/train.py, the real
+    MADDPGAgentTrainer with its real graph-building code (q_train, p_train, make_update_exp), distributions.py, tf_util.py and
+    replay_buffer.py, all unmodified -- executed on two stand-ins only (tests/tf_shim.py for TensorFlow, oracle/mpe.py for the
+    un-vendored MPE package; tests/golden/make_whole_program_golden.py).  The all-oracle loop started from the same weights and
+    fed the same noise stream must produce the same learning curve: 300 environment steps, 61 episodes, update rounds at
+    t = 100, 200, 300 feeding back into the actions (float32 sums in another order: measured 4.5e-9 relative, held to 1e-6)."""
+    import argparse
+    import random
+    from oracle import train_loop
+    from tests.update_case import shared_noise
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whole_program_ref.npz"))
+    argv = dict(zip(gold["argv"][0::2], gold["argv"][1::2]))
+    arglist = argparse.Namespace(scenario=str(argv["--scenario"]), max_episode_len=int(argv["--max-episode-len"]), lr=1e-2, gamma=0.95,
+                                 batch_size=int(argv["--batch-size"]), num_units=int(argv["--num-units"]), num_adversaries=0,
+                                 good_policy="maddpg", adv_policy="maddpg")
+    random.seed(3)
+    rewards, agrewards, steps = train_loop.run_training(arglist.scenario, int(argv["--num-episodes"]), arglist, seed=3,
+                                                        save_rate=int(argv["--save-rate"]), noise=shared_noise(3))
+    assert len(rewards) == len(gold["rewards"]) == 15 and steps == 300
+    np.testing.assert_allclose(np.asarray(rewards, np.float64), gold["rewards"], rtol=1e-6)
+    np.testing.assert_allclose(np.asarray(agrewards, np.float64), gold["agrewards"], rtol=1e-6)
+    print("worst relative difference of the learning curve: %.2e" % np.max(np.abs(np.asarray(rewards) - gold["rewards"]) / np.abs(gold["rewards"])))
