@@ -80,3 +80,20 @@ def test_whole_program_matches_the_oracle_loop():
     np.testing.assert_allclose(np.asarray(rewards, np.float64), gold["rewards"], rtol=1e-6)
     np.testing.assert_allclose(np.asarray(agrewards, np.float64), gold["agrewards"], rtol=1e-6)
     print("worst relative difference of the learning curve: %.2e" % np.max(np.abs(np.asarray(rewards) - gold["rewards"]) / np.abs(gold["rewards"])))
+
+
+def test_every_golden_file_has_its_generating_script():
+    """Each fixture under tests/golden/ is written by a committed script in the same directory (the rule for vectors produced from
+    the reference or from the oracle): the script names the file it writes."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    scripts = "".join(open(os.path.join(here, f)).read() for f in sorted(os.listdir(here)) if f.startswith("make_") and f.endswith(".py"))
+    missing = []
+    for f in sorted(os.listdir(here)):
+        if not f.endswith(".npz"):
+            continue
+        stem = f[:-4]
+        family = stem.split("_")[0] + "_"            # env_<case>.npz / update_<case>.npz are written by one loop over the cases
+        if f not in scripts and not (family in ("env_", "update_") and ('"%s%%s.npz"' % family in scripts or "'%s%%s.npz'" % family in scripts
+                                                                       or family + "%s.npz" in scripts)):
+            missing.append(f)
+    assert not missing, missing
